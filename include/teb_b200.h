@@ -1,0 +1,246 @@
+/*
+ * teb_b200.h — C-ABI of the B200-native Timed-Elastic-Band optimizer.
+ *
+ * This is the drop-in boundary for the hot path of rst-tu-dortmund/teb_local_planner:
+ *   TebOptimalPlanner::optimizeTEB            src/optimal_planner.cpp:182-231
+ *   TebOptimalPlanner::buildGraph/optimizeGraph/computeCurrentCost
+ *                                             src/optimal_planner.cpp:323-366, 368-402, 1041-1094
+ *   g2o SparseOptimizer + LM + CSparse        call sites src/optimal_planner.cpp:161-179, 385-387
+ *   HomotopyClassPlanner::optimizeAllTEBs     src/homotopy_class_planner.cpp:466-493
+ *   HomotopyClassPlanner::selectBestTeb       src/homotopy_class_planner.cpp:564-667
+ *   TimedElasticBand::autoResize              src/timed_elastic_band.cpp:227-286
+ *
+ * Plain C, plain pointers and sizes, no torch / CUDA types in any signature.
+ * All state is fp64 (the reference is fp64 throughout).
+ *
+ * Band storage ("pose records"): one band = n_cap records of 4 doubles
+ *   rec[i] = { x_i, y_i, theta_i, dt_i }      dt_i = TimeDiff(i) connects pose i -> i+1
+ * the last valid record (i = n-1) carries dt = 0.  Pose 0 and pose n-1 are fixed
+ * during optimisation (timed_elastic_band.cpp:330,377), every dt is free.
+ */
+#ifndef TEB_B200_H
+#define TEB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEBGPU_OK                  0
+#define TEBGPU_ERR_INVALID_ARG    -1
+#define TEBGPU_ERR_CUDA           -2
+#define TEBGPU_ERR_UNSUPPORTED    -3   /* a cost term / option that has no kernel yet: fail loudly */
+#define TEBGPU_ERR_CAPACITY       -4
+#define TEBGPU_ERR_NO_DEVICE      -5
+
+/* per-band status bits written to status[] */
+#define TEB_STATUS_OPTIMIZED       1   /* optimizeTEB returned true (optimal_planner.cpp:220)      */
+#define TEB_STATUS_TOO_FEW_POSES   2   /* sizePoses < min_samples guard (optimal_planner.cpp:377)   */
+#define TEB_STATUS_CHOL_FAILED     4   /* at least one trial factorisation hit a non-positive pivot */
+#define TEB_STATUS_NONFINITE       8   /* non-finite chi2 / lambda encountered                      */
+#define TEB_STATUS_TERMINATED     16   /* LM returned Terminate in the last optimizeGraph call      */
+#define TEB_STATUS_DISABLED       32   /* optimization_activate == false / max_vel_x < 0.01          */
+
+enum { TEB_FOOTPRINT_POINT = 0, TEB_FOOTPRINT_CIRCULAR = 1, TEB_FOOTPRINT_TWO_CIRCLES = 2 };
+enum { TEB_OBST_POINT = 0, TEB_OBST_CIRCULAR = 1 };
+enum { TEB_ROTDIR_NONE = 0, TEB_ROTDIR_LEFT = 1, TEB_ROTDIR_RIGHT = 2 };
+
+/* POD mirror of the TebConfig fields read on the hot path
+ * (include/teb_local_planner/teb_config.h:72-229, defaults :245-390). */
+typedef struct TebParams {
+  /* trajectory */
+  double  dt_ref;
+  double  dt_hysteresis;
+  double  force_reinit_new_goal_dist;
+  double  force_reinit_new_goal_angular;
+  int32_t teb_autosize;
+  int32_t min_samples;
+  int32_t max_samples;
+  int32_t exact_arc_length;
+  int32_t via_points_ordered;
+  int32_t allow_init_with_backwards_motion;
+  int32_t global_plan_overwrite_orientation;
+  int32_t _pad0;
+  /* robot */
+  double  max_vel_x;
+  double  max_vel_x_backwards;
+  double  max_vel_y;
+  double  max_vel_trans;
+  double  max_vel_theta;
+  double  acc_lim_x;
+  double  acc_lim_y;
+  double  acc_lim_theta;
+  double  min_turning_radius;
+  /* footprint model (robot_footprint_model.h) */
+  double  footprint_radius;        /* circular  */
+  double  footprint_front_offset;  /* two circles */
+  double  footprint_front_radius;
+  double  footprint_rear_offset;
+  double  footprint_rear_radius;
+  int32_t footprint_type;
+  int32_t _pad1;
+  /* obstacles */
+  double  min_obstacle_dist;
+  double  inflation_dist;
+  double  dynamic_obstacle_inflation_dist;
+  double  obstacle_association_force_inclusion_factor;
+  double  obstacle_association_cutoff_factor;
+  double  obstacle_proximity_ratio_max_vel;
+  double  obstacle_proximity_lower_bound;
+  double  obstacle_proximity_upper_bound;
+  int32_t include_dynamic_obstacles;
+  int32_t legacy_obstacle_association;
+  int32_t obstacle_poses_affected;
+  int32_t _pad2;
+  /* optim */
+  double  penalty_epsilon;
+  double  weight_max_vel_x;
+  double  weight_max_vel_y;
+  double  weight_max_vel_theta;
+  double  weight_acc_lim_x;
+  double  weight_acc_lim_y;
+  double  weight_acc_lim_theta;
+  double  weight_kinematics_nh;
+  double  weight_kinematics_forward_drive;
+  double  weight_kinematics_turning_radius;
+  double  weight_optimaltime;
+  double  weight_shortest_path;
+  double  weight_obstacle;
+  double  weight_inflation;
+  double  weight_dynamic_obstacle;
+  double  weight_dynamic_obstacle_inflation;
+  double  weight_velocity_obstacle_ratio;
+  double  weight_viapoint;
+  double  weight_prefer_rotdir;
+  double  weight_adapt_factor;
+  double  obstacle_cost_exponent;
+  int32_t no_inner_iterations;
+  int32_t no_outer_iterations;
+  int32_t optimization_activate;
+  int32_t _pad3;
+  /* hcp (selection only) */
+  double  selection_cost_hysteresis;
+  double  selection_prefer_initial_plan;
+  double  selection_obst_cost_scale;
+  double  selection_viapoint_cost_scale;
+  int32_t selection_alternative_time_cost;
+  int32_t enable_multithreading;
+  /* recovery */
+  int32_t divergence_detection_enable;
+  int32_t _pad4;
+  double  divergence_detection_max_chi_squared;
+} TebParams;
+
+/* Obstacle table row (48 bytes): Point / Circular obstacles with constant-velocity model
+ * (include/teb_local_planner/obstacles.h:305-445 PointObstacle, :447-595 CircularObstacle). */
+typedef struct TebObstacle {
+  double  x, y;       /* centroid */
+  double  vx, vy;     /* centroid velocity (obstacles.h:206) */
+  double  radius;     /* 0 for point obstacles */
+  int32_t dynamic;    /* isDynamic() (obstacles.h:199) */
+  int32_t type;       /* TEB_OBST_* */
+} TebObstacle;
+
+/* A batch of bands (homotopy candidates x planning requests). All pointers are HOST pointers for
+ * tebgpu_optimize_batch and DEVICE pointers for tebgpu_optimize_batch_device. */
+typedef struct TebBatch {
+  int32_t B;          /* number of bands                                   */
+  int32_t n_cap;      /* records per band (stride); >= every n[b]           */
+  int32_t S;          /* number of scenes (obstacle tables)                 */
+  int32_t M_cap;      /* obstacle rows per scene (stride)                   */
+  int32_t V_cap;      /* via-points per band (stride); may be 0             */
+  int32_t _pad;
+  double*            poses;       /* [B][n_cap][4]  in/out                              */
+  int32_t*           n;           /* [B]            in/out (autoResize changes it)      */
+  const int32_t*     scene_id;    /* [B]                                                */
+  const TebObstacle* obstacles;   /* [S][M_cap]                                         */
+  const int32_t*     obst_count;  /* [S]                                                */
+  const double*      via;         /* [B][V_cap][2] or NULL                              */
+  const int32_t*     via_count;   /* [B] or NULL                                        */
+  const double*      vel_start;   /* [B][4] = vx, vy, omega, active(0/1)  (optimal_planner.cpp:233-245) */
+  const double*      vel_goal;    /* [B][4] = vx, vy, omega, active(0/1); active=0 <=> free_goal_vel     */
+  const int32_t*     prefer_rotdir; /* [B] TEB_ROTDIR_* or NULL (optimal_planner.cpp:961-997)           */
+  double*            cost;        /* [B] out: getCurrentCost() (optimal_planner.h:437)  */
+  double*            chi2;        /* [B] out: chi2 of the final state of the last LM iteration (hasDiverged) */
+  int32_t*           status;      /* [B] out: TEB_STATUS_* bits                          */
+  int32_t*           lm_iters;    /* [B] out: inner LM iterations executed (all outer iterations) */
+} TebBatch;
+
+/* Arguments of TebOptimalPlanner::optimizeTEB (optimal_planner.h:231). */
+typedef struct TebOptimizeArgs {
+  int32_t iterations_innerloop;
+  int32_t iterations_outerloop;
+  int32_t compute_cost_afterwards;
+  int32_t alternative_time_cost;
+  double  obst_cost_scale;
+  double  viapoint_cost_scale;
+} TebOptimizeArgs;
+
+typedef struct TebGpuLimits {
+  int32_t max_bands;      /* B capacity */
+  int32_t max_poses;      /* n_cap capacity (<= 512) */
+  int32_t max_scenes;
+  int32_t max_obstacles;  /* M_cap capacity (<= 256) */
+  int32_t max_viapoints;  /* V_cap capacity */
+  int32_t _pad;
+} TebGpuLimits;
+
+typedef struct tebgpu_ctx tebgpu_ctx;
+
+/* Fill `p` with the TebConfig() constructor defaults (teb_config.h:245-390). The three fields the
+ * reference leaves uninitialised in the ctor get their dynamic_reconfigure defaults
+ * (divergence_detection_enable=0, divergence_detection_max_chi_squared=10). */
+void tebgpu_default_params(TebParams* p);
+
+/* sizeof() of the ABI structs, for binding sanity checks. which: 0 TebParams, 1 TebObstacle, 2 TebBatch,
+ * 3 TebOptimizeArgs, 4 TebGpuLimits. */
+int32_t tebgpu_sizeof(int32_t which);
+
+/* Context life cycle. One context = one device + one stream + its device workspaces.
+ * Replaces initOptimizer()/SparseOptimizer ownership (optimal_planner.cpp:161-179). */
+int32_t tebgpu_create(const TebGpuLimits* limits, int32_t device, tebgpu_ctx** out);
+int32_t tebgpu_destroy(tebgpu_ctx* ctx);
+const char* tebgpu_last_error_string(const tebgpu_ctx* ctx);
+
+/* cfg_ pointer equivalent (optimal_planner.h:675): parameters are copied, call again after changes. */
+int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* params);
+
+/* optimizeTEB over a whole batch, HOST buffers: H2D copy, all outer x inner LM iterations on the
+ * device, D2H copy of poses / n / cost / chi2 / status / lm_iters, synchronous.
+ * Replaces HomotopyClassPlanner::optimizeAllTEBs' thread fan-out (homotopy_class_planner.cpp:466-493). */
+int32_t tebgpu_optimize_batch(tebgpu_ctx* ctx, const TebBatch* batch, const TebOptimizeArgs* args);
+
+/* Same, every pointer in `batch` is a DEVICE pointer on the context's device. Stream-ordered on the
+ * context stream (or `cuda_stream` if non-NULL, a cudaStream_t passed as void*); does NOT synchronise. */
+int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* batch, const TebOptimizeArgs* args,
+                                     void* cuda_stream);
+int32_t tebgpu_synchronize(tebgpu_ctx* ctx);
+
+/* Number of kernels launched by the last optimize call (for bench.py's gpu_launches). */
+int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx);
+
+/* Linearise only: build the padded banded normal equations of every band at its current state for
+ * outer iteration `outer_index` (obstacle weight multiplier = weight_adapt_factor^outer_index).
+ * Hb_out [B][4*n_cap][12] (device or host per `device_ptrs`): row r = 11 lower-band entries
+ * H[r][r-k], k=0..10, then b[r]; chi2_out[B]. Test / profiling entry point for kernel A
+ * (BlockSolver::buildSystem). */
+int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* batch, int32_t outer_index,
+                            double* Hb_out, double* chi2_out, int32_t device_ptrs);
+
+/* HomotopyClassPlanner::selectBestTeb (homotopy_class_planner.cpp:564-667) on gathered costs:
+ * argmin over cost[i], with cost[last_best] * selection_cost_hysteresis and
+ * cost[initial_plan] * selection_prefer_initial_plan (pass -1 for none). Strict '<', first wins.
+ * Host-side, pure function. Returns the index or -1 if count == 0. */
+int32_t tebgpu_select_best(const double* cost, int32_t count, int32_t last_best, int32_t initial_plan,
+                           double selection_cost_hysteresis, double selection_prefer_initial_plan);
+
+/* TimedElasticBand::autoResize (timed_elastic_band.cpp:227-286) on one host band; same routine the
+ * device kernel runs. rec: [n_cap][4] in/out, returns the new n (or <0 on error). */
+int32_t tebgpu_auto_resize_host(double* rec, int32_t n, int32_t n_cap, double dt_ref, double dt_hysteresis,
+                                int32_t min_samples, int32_t max_samples, int32_t fast_mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEB_B200_H */

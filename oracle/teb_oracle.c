@@ -1,0 +1,1371 @@
+/*
+ * teb_oracle.c — CPU restatement of the reference's TEB optimisation path ("g2o mode").
+ * TEST INFRASTRUCTURE ONLY — see teb_oracle.h. PARITY UNPINNED (no reference golden vectors exist
+ * for anything but autoResize; g2o/CSparse are third-party and absent from /root/reference).
+ *
+ * What is restated and from where (all paths relative to /root/reference):
+ *   penalties                         include/teb_local_planner/g2o_types/penalties.h:57-117
+ *   fast_sigmoid / cross2d            include/teb_local_planner/misc.h:95, :120
+ *   PoseSE2::plus / average           include/teb_local_planner/pose_se2.h:238-243, :266-269
+ *   obstacle distances                include/teb_local_planner/obstacles.h:358-361, 382-385, 502-505, 526-529
+ *   footprint distances               include/teb_local_planner/robot_footprint_model.h:160-176, 263-278, 351-372
+ *   edge computeError bodies          include/teb_local_planner/g2o_types/edge_*.h (cited per function)
+ *   buildGraph / AddEdges*            src/optimal_planner.cpp:323-366, 444-548, 646-718, 720-997
+ *   optimizeTEB / optimizeGraph       src/optimal_planner.cpp:182-231, 368-402
+ *   computeCurrentCost                src/optimal_planner.cpp:1041-1094
+ *   autoResize / initTrajectoryToGoal src/timed_elastic_band.cpp:227-286, 325-387
+ *   g2o LM / numeric Jacobians / quadratic form / helpers: SURVEY.md Appendix A (upstream g2o,
+ *   call sites src/optimal_planner.cpp:161-179, 385-387).
+ *
+ * Structure mirrors g2o on purpose (heap-allocated polymorphic edges rebuilt every outer iteration,
+ * generic numeric linearisation through computeError callbacks, sparse(banded) Cholesky per LM trial)
+ * so that timing it is a fair "reference CPU path" baseline.
+ */
+#include "teb_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+#define HBW 10 /* half bandwidth of H in g2o vertex-id order (acceleration edge spans 11 scalars) */
+
+/* ------------------------------------------------------------------ g2o/stuff/misc.h helpers (App. A.7) */
+double teb_oracle_normalize_theta(double theta) {
+  if (theta >= -M_PI && theta < M_PI) return theta;
+  double multiplier = floor(theta / (2 * M_PI));
+  theta = theta - multiplier * 2 * M_PI;
+  if (theta >= M_PI) theta -= 2 * M_PI;
+  if (theta < -M_PI) theta += 2 * M_PI;
+  return theta;
+}
+double teb_oracle_average_angle(double a, double b) {
+  double x = cos(a) + cos(b), y = sin(a) + sin(b);
+  if (x == 0 && y == 0) return 0;
+  return atan2(y, x);
+}
+static inline double nt(double t) { return teb_oracle_normalize_theta(t); }
+static inline double sgn(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
+
+/* ------------------------------------------------------------------ penalties.h:57-117 */
+double teb_oracle_penalty_interval(double var, double a, double eps) {
+  if (var < -a + eps) return (-var - (a - eps));
+  if (var <= a - eps) return 0.;
+  return (var - (a - eps));
+}
+double teb_oracle_penalty_interval2(double var, double a, double b, double eps) {
+  if (var < a + eps) return (-var + (a + eps));
+  if (var <= b - eps) return 0.;
+  return (var - (b - eps));
+}
+double teb_oracle_penalty_below(double var, double a, double eps) {
+  if (var >= a + eps) return 0.;
+  return (-var + (a + eps));
+}
+/* slopes (penalties.h:127-189) */
+static inline double d_interval(double var, double a, double eps) {
+  if (var < -a + eps) return -1;
+  if (var <= a - eps) return 0;
+  return 1;
+}
+static inline double d_interval2(double var, double a, double b, double eps) {
+  if (var < a + eps) return -1;
+  if (var <= b - eps) return 0;
+  return 1;
+}
+static inline double d_below(double var, double a, double eps) { return (var >= a + eps) ? 0.0 : -1.0; }
+
+static inline double fast_sigmoid(double x) { return x / (1 + fabs(x)); } /* misc.h:95 */
+
+/* ------------------------------------------------------------------ band / graph data structures */
+enum EdgeType {
+  E_OBST = 0, E_INFL, E_DYN, E_VIA, E_VEL, E_ACC, E_ACC_START, E_ACC_GOAL, E_TIMEOPT, E_SHORTEST,
+  E_KIN_DD, E_KIN_CL, E_ROTDIR, E_NTYPES
+};
+
+typedef struct Graph Graph;
+
+typedef struct Edge {
+  int type;
+  int nv;          /* number of vertices */
+  int vkind[5];    /* 0 pose, 1 timediff */
+  int vidx[5];     /* pose / timediff index in the band */
+  int dim;         /* error dimension */
+  double info[2];  /* diagonal information matrix */
+  double err[2];   /* cached _error */
+  double t;        /* EdgeDynamicObstacle::t_ */
+  double meas;     /* EdgePreferRotDir::_measurement */
+  const TebObstacle* ob;
+  const double* via;
+  const double* twist; /* vel_start / vel_goal */
+  void (*compute_error)(struct Edge*, Graph*);
+  double J[5][6];  /* per vertex: row-major dim x vdim */
+} Edge;
+
+struct Graph {
+  const TebParams* cfg;
+  double* rec;  /* [n][4] */
+  int n;
+  const TebObstacle* obst;
+  int M;
+  const double* via;
+  int V;
+  double vel_start[4], vel_goal[4];
+  int rotdir;
+  Edge** edges;
+  int n_edges, cap_edges;
+  int N;          /* number of scalar unknowns */
+  double* Hb;     /* banded lower [N][HBW+1]: Hb[r][k] = H[r][r-k] */
+  double* b;      /* [N] */
+  double* x;      /* [N] solution */
+  double* work;   /* factor storage [N][HBW+1] */
+  double* backup; /* [n][4] state backup (push/pop) */
+  double* Hd;     /* dense workspace (optional) */
+};
+
+static inline int pose_fixed(const Graph* g, int i) { return i == 0 || i == g->n - 1; }
+/* hessian index of first scalar of a vertex in g2o id order (pose_i id=2i, dt_i id=2i+1; fixed excluded):
+ * dt_0, pose_1, dt_1, pose_2, ..., pose_{n-2}, dt_{n-2}  (optimal_planner.cpp:426-437, App. A.1) */
+static inline int hidx(const Graph* g, int kind, int i) {
+  if (kind == 1) return 4 * i;
+  if (pose_fixed(g, i)) return -1;
+  return 4 * i - 3;
+}
+static inline int vdim(int kind) { return kind == 0 ? 3 : 1; }
+
+static inline double* P(Graph* g, int i) { return g->rec + 4 * i; }
+static inline double DT(Graph* g, int i) { return g->rec[4 * i + 3]; }
+
+/* ------------------------------------------------------------------ distances */
+/* Obstacle::getMinimumDistance (Point obstacles.h:358, Circular :502) */
+static inline double obst_dist(const TebObstacle* o, double px, double py) {
+  double dx = px - o->x, dy = py - o->y;
+  return sqrt(dx * dx + dy * dy) - o->radius;
+}
+/* getMinimumSpatioTemporalDistance (Point obstacles.h:382, Circular :526) */
+static inline double obst_dist_t(const TebObstacle* o, double px, double py, double t) {
+  double dx = o->x + t * o->vx - px, dy = o->y + t * o->vy - py;
+  return sqrt(dx * dx + dy * dy) - o->radius;
+}
+/* BaseRobotFootprintModel::calculateDistance (robot_footprint_model.h:160, :263, :351) */
+static double footprint_dist(const TebParams* c, const double* pose, const TebObstacle* o) {
+  switch (c->footprint_type) {
+    case TEB_FOOTPRINT_CIRCULAR: return obst_dist(o, pose[0], pose[1]) - c->footprint_radius;
+    case TEB_FOOTPRINT_TWO_CIRCLES: {
+      double cx = cos(pose[2]), sy = sin(pose[2]);
+      double df = obst_dist(o, pose[0] + c->footprint_front_offset * cx, pose[1] + c->footprint_front_offset * sy) -
+                  c->footprint_front_radius;
+      double dr = obst_dist(o, pose[0] - c->footprint_rear_offset * cx, pose[1] - c->footprint_rear_offset * sy) -
+                  c->footprint_rear_radius;
+      return df < dr ? df : dr; /* std::min(front, rear) */
+    }
+    default: return obst_dist(o, pose[0], pose[1]);
+  }
+}
+/* estimateSpatioTemporalDistance (robot_footprint_model.h:172, :275, :366) */
+static double footprint_dist_t(const TebParams* c, const double* pose, const TebObstacle* o, double t) {
+  switch (c->footprint_type) {
+    case TEB_FOOTPRINT_CIRCULAR: return obst_dist_t(o, pose[0], pose[1], t) - c->footprint_radius;
+    case TEB_FOOTPRINT_TWO_CIRCLES: {
+      double cx = cos(pose[2]), sy = sin(pose[2]);
+      double df = obst_dist_t(o, pose[0] + c->footprint_front_offset * cx, pose[1] + c->footprint_front_offset * sy, t) -
+                  c->footprint_front_radius;
+      double dr = obst_dist_t(o, pose[0] - c->footprint_rear_offset * cx, pose[1] - c->footprint_rear_offset * sy, t) -
+                  c->footprint_rear_radius;
+      return df < dr ? df : dr;
+    }
+    default: return obst_dist_t(o, pose[0], pose[1], t);
+  }
+}
+
+/* ------------------------------------------------------------------ edge cost functions (computeError) */
+/* EdgeObstacle::computeError g2o_types/edge_obstacle.h:85-106 */
+static void ce_obstacle(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double dist = footprint_dist(c, P(g, e->vidx[0]), e->ob);
+  e->err[0] = teb_oracle_penalty_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
+  if (c->obstacle_cost_exponent != 1.0 && c->min_obstacle_dist > 0.0)
+    e->err[0] = c->min_obstacle_dist * pow(e->err[0] / c->min_obstacle_dist, c->obstacle_cost_exponent);
+}
+/* EdgeInflatedObstacle::computeError edge_obstacle.h:207-233 */
+static void ce_inflated(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double dist = footprint_dist(c, P(g, e->vidx[0]), e->ob);
+  e->err[0] = teb_oracle_penalty_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
+  if (c->obstacle_cost_exponent != 1.0 && c->min_obstacle_dist > 0.0)
+    e->err[0] = c->min_obstacle_dist * pow(e->err[0] / c->min_obstacle_dist, c->obstacle_cost_exponent);
+  e->err[1] = teb_oracle_penalty_below(dist, c->inflation_dist, 0.0);
+}
+/* EdgeDynamicObstacle::computeError edge_dynamic_obstacle.h:93-104 */
+static void ce_dynamic(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double dist = footprint_dist_t(c, P(g, e->vidx[0]), e->ob, e->t);
+  e->err[0] = teb_oracle_penalty_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
+  e->err[1] = teb_oracle_penalty_below(dist, c->dynamic_obstacle_inflation_dist, 0.0);
+}
+/* EdgeViaPoint::computeError edge_via_point.h:81-89 */
+static void ce_via(Edge* e, Graph* g) {
+  const double* p = P(g, e->vidx[0]);
+  double dx = p[0] - e->via[0], dy = p[1] - e->via[1];
+  e->err[0] = sqrt(dx * dx + dy * dy);
+}
+/* shared by velocity / acceleration edges: dist (optionally arc length), direction sigmoid */
+static inline void seg_vel(const TebParams* c, const double* p1, const double* p2, double dt, double* vel, double* omega) {
+  double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+  double dist = sqrt(dx * dx + dy * dy);
+  double angle_diff = nt(p2[2] - p1[2]);
+  if (c->exact_arc_length && angle_diff != 0) {
+    double radius = dist / (2 * sin(angle_diff / 2));
+    dist = fabs(angle_diff * radius);
+  }
+  double v = dist / dt;
+  v *= fast_sigmoid(100 * (dx * cos(p1[2]) + dy * sin(p1[2])));
+  *vel = v;
+  *omega = angle_diff / dt;
+}
+/* EdgeVelocity::computeError edge_velocity.h:92-117 */
+static void ce_velocity(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double vel, omega;
+  seg_vel(c, P(g, e->vidx[0]), P(g, e->vidx[1]), DT(g, e->vidx[2]), &vel, &omega);
+  e->err[0] = teb_oracle_penalty_interval2(vel, -c->max_vel_x_backwards, c->max_vel_x, c->penalty_epsilon);
+  e->err[1] = teb_oracle_penalty_interval(omega, c->max_vel_theta, c->penalty_epsilon);
+}
+/* EdgeAcceleration::computeError edge_acceleration.h:93-150 */
+static void ce_acceleration(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double dt1 = DT(g, e->vidx[3]), dt2 = DT(g, e->vidx[4]);
+  double vel1, vel2, omega1, omega2;
+  seg_vel(c, P(g, e->vidx[0]), P(g, e->vidx[1]), dt1, &vel1, &omega1);
+  seg_vel(c, P(g, e->vidx[1]), P(g, e->vidx[2]), dt2, &vel2, &omega2);
+  double acc_lin = (vel2 - vel1) * 2 / (dt1 + dt2);
+  e->err[0] = teb_oracle_penalty_interval(acc_lin, c->acc_lim_x, c->penalty_epsilon);
+  double acc_rot = (omega2 - omega1) * 2 / (dt1 + dt2);
+  e->err[1] = teb_oracle_penalty_interval(acc_rot, c->acc_lim_theta, c->penalty_epsilon);
+}
+/* EdgeAccelerationStart::computeError edge_acceleration.h:311-345 */
+static void ce_acc_start(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double dt = DT(g, e->vidx[2]);
+  double vel2, omega2;
+  seg_vel(c, P(g, e->vidx[0]), P(g, e->vidx[1]), dt, &vel2, &omega2);
+  double vel1 = e->twist[0];
+  double acc_lin = (vel2 - vel1) / dt;
+  e->err[0] = teb_oracle_penalty_interval(acc_lin, c->acc_lim_x, c->penalty_epsilon);
+  double omega1 = e->twist[2];
+  double acc_rot = (omega2 - omega1) / dt;
+  e->err[1] = teb_oracle_penalty_interval(acc_rot, c->acc_lim_theta, c->penalty_epsilon);
+}
+/* EdgeAccelerationGoal::computeError edge_acceleration.h:402-437 */
+static void ce_acc_goal(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double dt = DT(g, e->vidx[2]);
+  double vel1, omega1;
+  seg_vel(c, P(g, e->vidx[0]), P(g, e->vidx[1]), dt, &vel1, &omega1);
+  double vel2 = e->twist[0];
+  double acc_lin = (vel2 - vel1) / dt;
+  e->err[0] = teb_oracle_penalty_interval(acc_lin, c->acc_lim_x, c->penalty_epsilon);
+  double omega2 = e->twist[2];
+  double acc_rot = (omega2 - omega1) / dt;
+  e->err[1] = teb_oracle_penalty_interval(acc_rot, c->acc_lim_theta, c->penalty_epsilon);
+}
+/* EdgeTimeOptimal::computeError edge_time_optimal.h:88-96 */
+static void ce_timeopt(Edge* e, Graph* g) { e->err[0] = DT(g, e->vidx[0]); }
+/* EdgeShortestPath::computeError edge_shortest_path.h:73-81 */
+static void ce_shortest(Edge* e, Graph* g) {
+  const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
+  double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+  e->err[0] = sqrt(dx * dx + dy * dy);
+}
+/* EdgeKinematicsDiffDrive::computeError edge_kinematics.h:89-105 */
+static void ce_kin_dd(Edge* e, Graph* g) {
+  const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
+  double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+  e->err[0] = fabs((cos(p1[2]) + cos(p2[2])) * dy - (sin(p1[2]) + sin(p2[2])) * dx);
+  double dot = dx * cos(p1[2]) + dy * sin(p1[2]);
+  e->err[1] = teb_oracle_penalty_below(dot, 0, 0);
+}
+/* EdgeKinematicsCarlike::computeError edge_kinematics.h:198-218 */
+static void ce_kin_cl(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
+  double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+  e->err[0] = fabs((cos(p1[2]) + cos(p2[2])) * dy - (sin(p1[2]) + sin(p2[2])) * dx);
+  double angle_diff = nt(p2[2] - p1[2]);
+  double norm = sqrt(dx * dx + dy * dy);
+  if (angle_diff == 0)
+    e->err[1] = 0;
+  else if (c->exact_arc_length)
+    e->err[1] = teb_oracle_penalty_below(fabs(norm / (2 * sin(angle_diff / 2))), c->min_turning_radius, 0.0);
+  else
+    e->err[1] = teb_oracle_penalty_below(norm / fabs(angle_diff), c->min_turning_radius, 0.0);
+}
+/* EdgePreferRotDir::computeError edge_prefer_rotdir.h:80-88 */
+static void ce_rotdir(Edge* e, Graph* g) {
+  const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
+  e->err[0] = teb_oracle_penalty_below(e->meas * nt(p2[2] - p1[2]), 0, 0);
+}
+
+/* ------------------------------------------------------------------ Jacobians */
+static inline int edge_vertex_fixed(const Graph* g, const Edge* e, int k) {
+  return e->vkind[k] == 0 && pose_fixed(g, e->vidx[k]);
+}
+
+/* VertexPose::oplusImpl -> PoseSE2::plus (vertex_pose.h:195, pose_se2.h:238); VertexTimeDiff::oplusImpl (vertex_timediff.h:113) */
+static inline void vertex_oplus(Graph* g, int kind, int idx, const double* d) {
+  double* r = g->rec + 4 * idx;
+  if (kind == 0) {
+    r[0] += d[0];
+    r[1] += d[1];
+    r[2] = nt(r[2] + d[2]);
+  } else {
+    r[3] += d[0];
+  }
+}
+
+/* g2o BaseMultiEdge/BaseBinaryEdge/BaseUnaryEdge::linearizeOplus numeric default (App. A.3) */
+static void linearize_numeric(Edge* e, Graph* g) {
+  const double delta = 1e-9;
+  const double scalar = 1.0 / (2 * delta);
+  double err_before[2] = {e->err[0], e->err[1]};
+  for (int k = 0; k < e->nv; ++k) {
+    if (edge_vertex_fixed(g, e, k)) continue;
+    int vd = vdim(e->vkind[k]);
+    double* r = g->rec + 4 * e->vidx[k];
+    for (int d = 0; d < vd; ++d) {
+      double add[3] = {0, 0, 0};
+      double save[4] = {r[0], r[1], r[2], r[3]}; /* push() */
+      add[d] = delta;
+      vertex_oplus(g, e->vkind[k], e->vidx[k], add);
+      e->compute_error(e, g);
+      double eb0 = e->err[0], eb1 = e->err[1];
+      r[0] = save[0]; r[1] = save[1]; r[2] = save[2]; r[3] = save[3]; /* pop() */
+      add[d] = -delta;
+      vertex_oplus(g, e->vkind[k], e->vidx[k], add);
+      e->compute_error(e, g);
+      eb0 -= e->err[0];
+      eb1 -= e->err[1];
+      r[0] = save[0]; r[1] = save[1]; r[2] = save[2]; r[3] = save[3];
+      e->J[k][0 * vd + d] = scalar * eb0;
+      if (e->dim > 1) e->J[k][1 * vd + d] = scalar * eb1;
+    }
+  }
+  e->err[0] = err_before[0];
+  e->err[1] = err_before[1];
+}
+
+/* EdgeKinematicsDiffDrive::linearizeOplus — the analytic override compiled into the reference
+ * (edge_kinematics.h:107-151, `#if 1`). */
+static void linearize_kin_dd_reference(Edge* e, Graph* g) {
+  const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
+  double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+  double cos1 = cos(p1[2]), cos2 = cos(p2[2]), sin1 = sin(p1[2]), sin2 = sin(p2[2]);
+  double aux1 = sin1 + sin2, aux2 = cos1 + cos2;
+  double dd_error_1 = dx * cos1, dd_error_2 = dy * sin1;
+  double dd_dev = d_below(dd_error_1 + dd_error_2, 0, 0);
+  double dev_nh_abs = sgn((cos1 + cos2) * dy - (sin1 + sin2) * dx);
+  double* Ji = e->J[0];
+  double* Jj = e->J[1];
+  Ji[0] = aux1 * dev_nh_abs;
+  Ji[1] = -aux2 * dev_nh_abs;
+  Ji[3] = -cos1 * dd_dev;
+  Ji[4] = -sin1 * dd_dev;
+  Ji[2] = (-dd_error_2 - dd_error_1) * dev_nh_abs;
+  Ji[5] = (-sin1 * dx + cos1 * dy) * dd_dev;
+  Jj[0] = -aux1 * dev_nh_abs;
+  Jj[1] = aux2 * dev_nh_abs;
+  Jj[3] = cos1 * dd_dev;
+  Jj[4] = sin1 * dd_dev;
+  Jj[2] = (-sin2 * dy - cos2 * dx) * dev_nh_abs;
+  Jj[5] = 0;
+}
+
+/* ---- closed-form Jacobians for every edge (ORACLE_JAC_ANALYTIC); derivations in DESIGN.md §4 ---- */
+typedef struct SegD {
+  double v, w;
+  double dv[7]; /* d v / d (x1,y1,th1,x2,y2,th2,dt) */
+  double dw[7];
+} SegD;
+
+static void seg_derivs(const TebParams* c, const double* p1, const double* p2, double dt, SegD* s) {
+  double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+  double dist = sqrt(dx * dx + dy * dy);
+  double ad = nt(p2[2] - p1[2]);
+  double c1 = cos(p1[2]), s1 = sin(p1[2]);
+  double ux = dist > 0 ? dx / dist : 0.0, uy = dist > 0 ? dy / dist : 0.0;
+  double L = dist, gfac = 1.0, dg = 0.0;
+  if (c->exact_arc_length && ad != 0) {
+    double h = ad / 2, sh = sin(h);
+    gfac = fabs(ad / (2 * sh));
+    double q = ad / (2 * sh);
+    double dq = (2 * sh - ad * cos(h)) / (4 * sh * sh);
+    dg = sgn(q) * dq;
+    L = fabs(ad * (dist / (2 * sh)));
+  }
+  double dL[7] = {-gfac * ux, -gfac * uy, -dist * dg, gfac * ux, gfac * uy, dist * dg, 0};
+  double proj = dx * c1 + dy * s1;
+  double u = 100 * proj;
+  double sig = u / (1 + fabs(u));
+  double dsig = 1.0 / ((1 + fabs(u)) * (1 + fabs(u)));
+  double dproj[7] = {-c1, -s1, -dx * s1 + dy * c1, c1, s1, 0, 0};
+  s->v = L / dt * sig;
+  s->w = ad / dt;
+  for (int k = 0; k < 6; ++k) s->dv[k] = (dL[k] * sig + L * 100 * dsig * dproj[k]) / dt;
+  s->dv[6] = -s->v / dt;
+  s->dw[0] = s->dw[1] = s->dw[3] = s->dw[4] = 0;
+  s->dw[2] = -1 / dt;
+  s->dw[5] = 1 / dt;
+  s->dw[6] = -s->w / dt;
+}
+
+/* distance gradient of the footprint model wrt (x,y,theta); pos of obstacle given (ox,oy) */
+static void footprint_grad(const TebParams* c, const double* pose, double ox, double oy, double orad, double* dist,
+                           double grad[3]) {
+  double px = pose[0], py = pose[1];
+  if (c->footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) {
+    double cx = cos(pose[2]), sy = sin(pose[2]);
+    double fx = px + c->footprint_front_offset * cx - ox, fy = py + c->footprint_front_offset * sy - oy;
+    double rx = px - c->footprint_rear_offset * cx - ox, ry = py - c->footprint_rear_offset * sy - oy;
+    double nf = sqrt(fx * fx + fy * fy), nr = sqrt(rx * rx + ry * ry);
+    double df = nf - orad - c->footprint_front_radius, dr = nr - orad - c->footprint_rear_radius;
+    if (df < dr) {
+      *dist = df;
+      double ux = nf > 0 ? fx / nf : 0, uy = nf > 0 ? fy / nf : 0;
+      grad[0] = ux; grad[1] = uy;
+      grad[2] = c->footprint_front_offset * (-sy * ux + cx * uy);
+    } else {
+      *dist = dr;
+      double ux = nr > 0 ? rx / nr : 0, uy = nr > 0 ? ry / nr : 0;
+      grad[0] = ux; grad[1] = uy;
+      grad[2] = -c->footprint_rear_offset * (-sy * ux + cx * uy);
+    }
+    return;
+  }
+  double dx = px - ox, dy = py - oy;
+  double nrm = sqrt(dx * dx + dy * dy);
+  *dist = nrm - orad - (c->footprint_type == TEB_FOOTPRINT_CIRCULAR ? c->footprint_radius : 0.0);
+  grad[0] = nrm > 0 ? dx / nrm : 0;
+  grad[1] = nrm > 0 ? dy / nrm : 0;
+  grad[2] = 0;
+}
+
+static void linearize_analytic(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  memset(e->J, 0, sizeof(e->J));
+  switch (e->type) {
+    case E_OBST:
+    case E_INFL:
+    case E_DYN: {
+      double dist, gr[3];
+      double ox = e->ob->x, oy = e->ob->y;
+      if (e->type == E_DYN) { ox += e->t * e->ob->vx; oy += e->t * e->ob->vy; }
+      footprint_grad(c, P(g, e->vidx[0]), ox, oy, e->ob->radius, &dist, gr);
+      double s0 = d_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
+      if (e->type != E_DYN && c->obstacle_cost_exponent != 1.0 && c->min_obstacle_dist > 0.0) {
+        double e0 = teb_oracle_penalty_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
+        s0 *= (e0 > 0) ? c->obstacle_cost_exponent * pow(e0 / c->min_obstacle_dist, c->obstacle_cost_exponent - 1.0) : 0.0;
+      }
+      for (int d = 0; d < 3; ++d) e->J[0][d] = s0 * gr[d];
+      if (e->type == E_INFL) {
+        double s1 = d_below(dist, c->inflation_dist, 0.0);
+        for (int d = 0; d < 3; ++d) e->J[0][3 + d] = s1 * gr[d];
+      } else if (e->type == E_DYN) {
+        double s1 = d_below(dist, c->dynamic_obstacle_inflation_dist, 0.0);
+        for (int d = 0; d < 3; ++d) e->J[0][3 + d] = s1 * gr[d];
+      }
+      break;
+    }
+    case E_VIA: {
+      const double* p = P(g, e->vidx[0]);
+      double dx = p[0] - e->via[0], dy = p[1] - e->via[1];
+      double nrm = sqrt(dx * dx + dy * dy);
+      e->J[0][0] = nrm > 0 ? dx / nrm : 0;
+      e->J[0][1] = nrm > 0 ? dy / nrm : 0;
+      break;
+    }
+    case E_VEL: {
+      SegD s;
+      seg_derivs(c, P(g, e->vidx[0]), P(g, e->vidx[1]), DT(g, e->vidx[2]), &s);
+      double s0 = d_interval2(s.v, -c->max_vel_x_backwards, c->max_vel_x, c->penalty_epsilon);
+      double s1 = d_interval(s.w, c->max_vel_theta, c->penalty_epsilon);
+      for (int d = 0; d < 3; ++d) {
+        e->J[0][d] = s0 * s.dv[d];       e->J[0][3 + d] = s1 * s.dw[d];
+        e->J[1][d] = s0 * s.dv[3 + d];   e->J[1][3 + d] = s1 * s.dw[3 + d];
+      }
+      e->J[2][0] = s0 * s.dv[6];
+      e->J[2][1] = s1 * s.dw[6];
+      break;
+    }
+    case E_ACC: {
+      SegD a, bq;
+      double dt1 = DT(g, e->vidx[3]), dt2 = DT(g, e->vidx[4]);
+      seg_derivs(c, P(g, e->vidx[0]), P(g, e->vidx[1]), dt1, &a);
+      seg_derivs(c, P(g, e->vidx[1]), P(g, e->vidx[2]), dt2, &bq);
+      double T = dt1 + dt2;
+      double acc = (bq.v - a.v) * 2 / T, accr = (bq.w - a.w) * 2 / T;
+      double s0 = d_interval(acc, c->acc_lim_x, c->penalty_epsilon);
+      double s1 = d_interval(accr, c->acc_lim_theta, c->penalty_epsilon);
+      for (int d = 0; d < 3; ++d) {
+        /* pose1: only segment a (as first pose) */
+        e->J[0][d] = s0 * (-2 * a.dv[d] / T);             e->J[0][3 + d] = s1 * (-2 * a.dw[d] / T);
+        /* pose2: second pose of a, first pose of b */
+        e->J[1][d] = s0 * (2 * (bq.dv[d] - a.dv[3 + d]) / T); e->J[1][3 + d] = s1 * (2 * (bq.dw[d] - a.dw[3 + d]) / T);
+        /* pose3: second pose of b */
+        e->J[2][d] = s0 * (2 * bq.dv[3 + d] / T);         e->J[2][3 + d] = s1 * (2 * bq.dw[3 + d] / T);
+      }
+      e->J[3][0] = s0 * (-2 * a.dv[6] / T - acc / T);
+      e->J[3][1] = s1 * (-2 * a.dw[6] / T - accr / T);
+      e->J[4][0] = s0 * (2 * bq.dv[6] / T - acc / T);
+      e->J[4][1] = s1 * (2 * bq.dw[6] / T - accr / T);
+      break;
+    }
+    case E_ACC_START: {
+      SegD s;
+      double dt = DT(g, e->vidx[2]);
+      seg_derivs(c, P(g, e->vidx[0]), P(g, e->vidx[1]), dt, &s);
+      double acc = (s.v - e->twist[0]) / dt, accr = (s.w - e->twist[2]) / dt;
+      double s0 = d_interval(acc, c->acc_lim_x, c->penalty_epsilon);
+      double s1 = d_interval(accr, c->acc_lim_theta, c->penalty_epsilon);
+      for (int d = 0; d < 3; ++d) {
+        e->J[0][d] = s0 * s.dv[d] / dt;       e->J[0][3 + d] = s1 * s.dw[d] / dt;
+        e->J[1][d] = s0 * s.dv[3 + d] / dt;   e->J[1][3 + d] = s1 * s.dw[3 + d] / dt;
+      }
+      e->J[2][0] = s0 * (s.dv[6] / dt - acc / dt);
+      e->J[2][1] = s1 * (s.dw[6] / dt - accr / dt);
+      break;
+    }
+    case E_ACC_GOAL: {
+      SegD s;
+      double dt = DT(g, e->vidx[2]);
+      seg_derivs(c, P(g, e->vidx[0]), P(g, e->vidx[1]), dt, &s);
+      double acc = (e->twist[0] - s.v) / dt, accr = (e->twist[2] - s.w) / dt;
+      double s0 = d_interval(acc, c->acc_lim_x, c->penalty_epsilon);
+      double s1 = d_interval(accr, c->acc_lim_theta, c->penalty_epsilon);
+      for (int d = 0; d < 3; ++d) {
+        e->J[0][d] = -s0 * s.dv[d] / dt;       e->J[0][3 + d] = -s1 * s.dw[d] / dt;
+        e->J[1][d] = -s0 * s.dv[3 + d] / dt;   e->J[1][3 + d] = -s1 * s.dw[3 + d] / dt;
+      }
+      e->J[2][0] = s0 * (-s.dv[6] / dt - acc / dt);
+      e->J[2][1] = s1 * (-s.dw[6] / dt - accr / dt);
+      break;
+    }
+    case E_TIMEOPT: e->J[0][0] = 1; break;
+    case E_SHORTEST: {
+      const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
+      double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+      double nrm = sqrt(dx * dx + dy * dy);
+      double ux = nrm > 0 ? dx / nrm : 0, uy = nrm > 0 ? dy / nrm : 0;
+      e->J[0][0] = -ux; e->J[0][1] = -uy;
+      e->J[1][0] = ux;  e->J[1][1] = uy;
+      break;
+    }
+    case E_KIN_DD: linearize_kin_dd_reference(e, g); break;
+    case E_KIN_CL: {
+      const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
+      double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+      double cos1 = cos(p1[2]), cos2 = cos(p2[2]), sin1 = sin(p1[2]), sin2 = sin(p2[2]);
+      double A = (cos1 + cos2) * dy - (sin1 + sin2) * dx;
+      double sa = sgn(A);
+      e->J[0][0] = (sin1 + sin2) * sa;
+      e->J[0][1] = -(cos1 + cos2) * sa;
+      e->J[0][2] = (-sin1 * dy - cos1 * dx) * sa;
+      e->J[1][0] = -(sin1 + sin2) * sa;
+      e->J[1][1] = (cos1 + cos2) * sa;
+      e->J[1][2] = (-sin2 * dy - cos2 * dx) * sa;
+      double ad = nt(p2[2] - p1[2]);
+      double nrm = sqrt(dx * dx + dy * dy);
+      if (ad != 0) {
+        double ux = nrm > 0 ? dx / nrm : 0, uy = nrm > 0 ? dy / nrm : 0;
+        double r, dr_dn, dr_dad;
+        if (c->exact_arc_length) {
+          double h = ad / 2, sh = sin(h);
+          double q = nrm / (2 * sh);
+          r = fabs(q);
+          dr_dn = sgn(q) / (2 * sh);
+          dr_dad = sgn(q) * (-nrm * cos(h) / (4 * sh * sh));
+        } else {
+          r = nrm / fabs(ad);
+          dr_dn = 1 / fabs(ad);
+          dr_dad = -nrm * sgn(ad) / (ad * ad);
+        }
+        double s1 = d_below(r, c->min_turning_radius, 0.0);
+        e->J[0][3] = s1 * dr_dn * (-ux);
+        e->J[0][4] = s1 * dr_dn * (-uy);
+        e->J[0][5] = s1 * (-dr_dad);
+        e->J[1][3] = s1 * dr_dn * ux;
+        e->J[1][4] = s1 * dr_dn * uy;
+        e->J[1][5] = s1 * dr_dad;
+      }
+      break;
+    }
+    case E_ROTDIR: {
+      const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
+      double s0 = d_below(e->meas * nt(p2[2] - p1[2]), 0, 0);
+      e->J[0][2] = -s0 * e->meas;
+      e->J[1][2] = s0 * e->meas;
+      break;
+    }
+    default: break;
+  }
+}
+
+static void linearize(Edge* e, Graph* g, int jac_mode) {
+  if (jac_mode == ORACLE_JAC_ANALYTIC) {
+    linearize_analytic(e, g);
+    return;
+  }
+  /* g2o mode: USE_ANALYTIC_JACOBI is defined (teb_config.h:52) but only two overrides are compiled in */
+  if (e->type == E_KIN_DD) {
+    linearize_kin_dd_reference(e, g);
+  } else if (e->type == E_TIMEOPT) {
+    e->J[0][0] = 1; /* edge_time_optimal.h:98-107 */
+  } else {
+    linearize_numeric(e, g);
+  }
+}
+
+/* ------------------------------------------------------------------ graph construction (buildGraph) */
+static Edge* new_edge(Graph* g, int type, int dim, void (*ce)(Edge*, Graph*)) {
+  Edge* e = (Edge*)calloc(1, sizeof(Edge)); /* `new EdgeXxx` per edge per outer iteration, as the reference does */
+  e->type = type;
+  e->dim = dim;
+  e->compute_error = ce;
+  if (g->n_edges == g->cap_edges) {
+    g->cap_edges = g->cap_edges ? 2 * g->cap_edges : 1024;
+    g->edges = (Edge**)realloc(g->edges, sizeof(Edge*) * g->cap_edges);
+  }
+  g->edges[g->n_edges++] = e;
+  return e;
+}
+static inline void set_vertex(Edge* e, int k, int kind, int idx) {
+  e->vkind[k] = kind;
+  e->vidx[k] = idx;
+  if (k + 1 > e->nv) e->nv = k + 1;
+}
+
+/* AddEdgesObstacles optimal_planner.cpp:444-548 */
+static void add_edges_obstacles(Graph* g, double weight_multiplier) {
+  const TebParams* c = g->cfg;
+  if (c->weight_obstacle == 0 || weight_multiplier == 0 || g->obst == NULL) return;
+  int inflated = c->inflation_dist > c->min_obstacle_dist;
+  const int first_vertex = c->weight_velocity_obstacle_ratio == 0 ? 1 : 0;
+  int* list = (int*)malloc(sizeof(int) * (g->M + 2));
+  for (int i = first_vertex; i < g->n - 1; ++i) {
+    int cnt = 0;
+    double left_min = DBL_MAX, right_min = DBL_MAX;
+    int left = -1, right = -1;
+    const double* p = P(g, i);
+    double ox = cos(p[2]), oy = sin(p[2]); /* orientationUnitVec */
+    for (int m = 0; m < g->M; ++m) {
+      const TebObstacle* ob = &g->obst[m];
+      if (c->include_dynamic_obstacles && ob->dynamic) continue;
+      double dist = footprint_dist(c, p, ob);
+      if (dist < c->min_obstacle_dist * c->obstacle_association_force_inclusion_factor) {
+        list[cnt++] = m;
+        continue;
+      }
+      if (dist > c->min_obstacle_dist * c->obstacle_association_cutoff_factor) continue;
+      /* cross2d(pose_orient, centroid - position) > 0 -> left (misc.h:120) */
+      double cx = ob->x - p[0], cy = ob->y - p[1];
+      if (ox * cy - cx * oy > 0) {
+        if (dist < left_min) { left_min = dist; left = m; }
+      } else {
+        if (dist < right_min) { right_min = dist; right = m; }
+      }
+    }
+    if (left >= 0) list[cnt++] = left;
+    if (right >= 0) list[cnt++] = right;
+    if (i == 0) continue;
+    for (int k = 0; k < cnt; ++k) {
+      Edge* e;
+      if (inflated) {
+        e = new_edge(g, E_INFL, 2, ce_inflated);
+        e->info[0] = c->weight_obstacle * weight_multiplier;
+        e->info[1] = c->weight_inflation;
+      } else {
+        e = new_edge(g, E_OBST, 1, ce_obstacle);
+        e->info[0] = c->weight_obstacle * weight_multiplier;
+      }
+      set_vertex(e, 0, 0, i);
+      e->ob = &g->obst[list[k]];
+    }
+  }
+  free(list);
+}
+
+/* AddEdgesDynamicObstacles optimal_planner.cpp:646-673 (called with weight_multiplier = 1, :343) */
+static void add_edges_dynamic_obstacles(Graph* g, double weight_multiplier) {
+  const TebParams* c = g->cfg;
+  if (c->weight_obstacle == 0 || weight_multiplier == 0 || g->obst == NULL) return;
+  for (int m = 0; m < g->M; ++m) {
+    if (!g->obst[m].dynamic) continue;
+    double time = DT(g, 0);
+    for (int i = 1; i < g->n - 1; ++i) {
+      Edge* e = new_edge(g, E_DYN, 2, ce_dynamic);
+      e->t = time;
+      set_vertex(e, 0, 0, i);
+      e->info[0] = c->weight_dynamic_obstacle * weight_multiplier;
+      e->info[1] = c->weight_dynamic_obstacle_inflation;
+      e->ob = &g->obst[m];
+      time += DT(g, i);
+    }
+  }
+}
+
+/* TimedElasticBand::findClosestTrajectoryPose(point) timed_elastic_band.cpp:455-478 */
+static int find_closest_pose(Graph* g, const double* pt, int begin_idx) {
+  int n = g->n;
+  if (begin_idx < 0 || begin_idx >= n) return -1;
+  double min_dist_sq = DBL_MAX;
+  int min_idx = -1;
+  for (int i = begin_idx; i < n; i++) {
+    double dx = pt[0] - P(g, i)[0], dy = pt[1] - P(g, i)[1];
+    double dist_sq = dx * dx + dy * dy;
+    if (dist_sq < min_dist_sq) { min_dist_sq = dist_sq; min_idx = i; }
+  }
+  return min_idx;
+}
+
+/* AddEdgesViaPoints optimal_planner.cpp:675-718 */
+static void add_edges_via_points(Graph* g) {
+  const TebParams* c = g->cfg;
+  if (c->weight_viapoint == 0 || g->via == NULL || g->V == 0) return;
+  int start_pose_idx = 0;
+  int n = g->n;
+  if (n < 3) return;
+  for (int k = 0; k < g->V; ++k) {
+    const double* vp = g->via + 2 * k;
+    int index = find_closest_pose(g, vp, start_pose_idx);
+    if (c->via_points_ordered) start_pose_idx = index + 2;
+    if (index > n - 2) index = n - 2;
+    if (index < 1) {
+      if (c->via_points_ordered) index = 1;
+      else continue;
+    }
+    Edge* e = new_edge(g, E_VIA, 1, ce_via);
+    set_vertex(e, 0, 0, index);
+    e->info[0] = c->weight_viapoint;
+    e->via = vp;
+  }
+}
+
+/* AddEdgesVelocity optimal_planner.cpp:720-769 (non-holonomic branch) */
+static void add_edges_velocity(Graph* g) {
+  const TebParams* c = g->cfg;
+  if (c->weight_max_vel_x == 0 && c->weight_max_vel_theta == 0) return;
+  for (int i = 0; i < g->n - 1; ++i) {
+    Edge* e = new_edge(g, E_VEL, 2, ce_velocity);
+    set_vertex(e, 0, 0, i);
+    set_vertex(e, 1, 0, i + 1);
+    set_vertex(e, 2, 1, i);
+    e->info[0] = c->weight_max_vel_x;
+    e->info[1] = c->weight_max_vel_theta;
+  }
+}
+
+/* AddEdgesAcceleration optimal_planner.cpp:771-873 (non-holonomic branch) */
+static void add_edges_acceleration(Graph* g) {
+  const TebParams* c = g->cfg;
+  if (c->weight_acc_lim_x == 0 && c->weight_acc_lim_theta == 0) return;
+  int n = g->n;
+  if (g->vel_start[3] != 0) {
+    Edge* e = new_edge(g, E_ACC_START, 2, ce_acc_start);
+    set_vertex(e, 0, 0, 0);
+    set_vertex(e, 1, 0, 1);
+    set_vertex(e, 2, 1, 0);
+    e->twist = g->vel_start;
+    e->info[0] = c->weight_acc_lim_x;
+    e->info[1] = c->weight_acc_lim_theta;
+  }
+  for (int i = 0; i < n - 2; ++i) {
+    Edge* e = new_edge(g, E_ACC, 2, ce_acceleration);
+    set_vertex(e, 0, 0, i);
+    set_vertex(e, 1, 0, i + 1);
+    set_vertex(e, 2, 0, i + 2);
+    set_vertex(e, 3, 1, i);
+    set_vertex(e, 4, 1, i + 1);
+    e->info[0] = c->weight_acc_lim_x;
+    e->info[1] = c->weight_acc_lim_theta;
+  }
+  if (g->vel_goal[3] != 0) {
+    Edge* e = new_edge(g, E_ACC_GOAL, 2, ce_acc_goal);
+    set_vertex(e, 0, 0, n - 2);
+    set_vertex(e, 1, 0, n - 1);
+    set_vertex(e, 2, 1, n - 2); /* TimeDiffVertex(sizeTimeDiffs()-1) */
+    e->twist = g->vel_goal;
+    e->info[0] = c->weight_acc_lim_x;
+    e->info[1] = c->weight_acc_lim_theta;
+  }
+}
+
+/* AddEdgesTimeOptimal :877-893, AddEdgesShortestPath :895-913 */
+static void add_edges_time_optimal(Graph* g) {
+  const TebParams* c = g->cfg;
+  if (c->weight_optimaltime == 0) return;
+  for (int i = 0; i < g->n - 1; ++i) {
+    Edge* e = new_edge(g, E_TIMEOPT, 1, ce_timeopt);
+    set_vertex(e, 0, 1, i);
+    e->info[0] = c->weight_optimaltime;
+  }
+}
+static void add_edges_shortest_path(Graph* g) {
+  const TebParams* c = g->cfg;
+  if (c->weight_shortest_path == 0) return;
+  for (int i = 0; i < g->n - 1; ++i) {
+    Edge* e = new_edge(g, E_SHORTEST, 1, ce_shortest);
+    set_vertex(e, 0, 0, i);
+    set_vertex(e, 1, 0, i + 1);
+    e->info[0] = c->weight_shortest_path;
+  }
+}
+/* AddEdgesKinematicsDiffDrive :916-936, AddEdgesKinematicsCarlike :938-958 */
+static void add_edges_kinematics(Graph* g) {
+  const TebParams* c = g->cfg;
+  int carlike = !(c->min_turning_radius == 0 || c->weight_kinematics_turning_radius == 0); /* :355 */
+  if (!carlike) {
+    if (c->weight_kinematics_nh == 0 && c->weight_kinematics_forward_drive == 0) return;
+  } else {
+    if (c->weight_kinematics_nh == 0 && c->weight_kinematics_turning_radius == 0) return;
+  }
+  for (int i = 0; i < g->n - 1; i++) {
+    Edge* e = carlike ? new_edge(g, E_KIN_CL, 2, ce_kin_cl) : new_edge(g, E_KIN_DD, 2, ce_kin_dd);
+    set_vertex(e, 0, 0, i);
+    set_vertex(e, 1, 0, i + 1);
+    e->info[0] = c->weight_kinematics_nh;
+    e->info[1] = carlike ? c->weight_kinematics_turning_radius : c->weight_kinematics_forward_drive;
+  }
+}
+/* AddEdgesPreferRotDir :961-997 */
+static void add_edges_prefer_rotdir(Graph* g) {
+  const TebParams* c = g->cfg;
+  if (g->rotdir == TEB_ROTDIR_NONE || c->weight_prefer_rotdir == 0) return;
+  if (g->rotdir != TEB_ROTDIR_RIGHT && g->rotdir != TEB_ROTDIR_LEFT) return;
+  for (int i = 0; i < g->n - 1 && i < 3; ++i) {
+    Edge* e = new_edge(g, E_ROTDIR, 1, ce_rotdir);
+    set_vertex(e, 0, 0, i);
+    set_vertex(e, 1, 0, i + 1);
+    e->info[0] = c->weight_prefer_rotdir;
+    e->meas = (g->rotdir == TEB_ROTDIR_LEFT) ? 1 : -1;
+  }
+}
+
+static void clear_graph(Graph* g) {
+  for (int k = 0; k < g->n_edges; ++k) free(g->edges[k]);
+  g->n_edges = 0;
+}
+
+/* buildGraph optimal_planner.cpp:323-366 */
+static int build_graph(Graph* g, double weight_multiplier) {
+  const TebParams* c = g->cfg;
+  if (c->legacy_obstacle_association) return TEBGPU_ERR_UNSUPPORTED;
+  if (c->max_vel_y != 0) return TEBGPU_ERR_UNSUPPORTED;                 /* holonomic edges not restated */
+  if (c->weight_velocity_obstacle_ratio > 0) return TEBGPU_ERR_UNSUPPORTED;
+  add_edges_obstacles(g, weight_multiplier);
+  if (c->include_dynamic_obstacles) add_edges_dynamic_obstacles(g, 1.0);
+  add_edges_via_points(g);
+  add_edges_velocity(g);
+  add_edges_acceleration(g);
+  add_edges_time_optimal(g);
+  add_edges_shortest_path(g);
+  add_edges_kinematics(g);
+  add_edges_prefer_rotdir(g);
+  /* initializeOptimization(): edges whose vertices are all fixed are not active (App. A.1) */
+  int w = 0;
+  for (int k = 0; k < g->n_edges; ++k) {
+    Edge* e = g->edges[k];
+    int all_fixed = 1;
+    for (int v = 0; v < e->nv; ++v)
+      if (!edge_vertex_fixed(g, e, v)) all_fixed = 0;
+    if (all_fixed) free(e);
+    else g->edges[w++] = e;
+  }
+  g->n_edges = w;
+  g->N = 4 * g->n - 7;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ errors / quadratic form */
+static double compute_active_errors(Graph* g) {
+  double chi2 = 0;
+  for (int k = 0; k < g->n_edges; ++k) {
+    Edge* e = g->edges[k];
+    e->compute_error(e, g);
+    for (int d = 0; d < e->dim; ++d) chi2 += e->err[d] * e->info[d] * e->err[d];
+  }
+  return chi2;
+}
+static inline void H_add(Graph* g, int r, int q, double v) {
+  if (r < q) { int t = r; r = q; q = t; }
+  g->Hb[(size_t)r * (HBW + 1) + (r - q)] += v;
+}
+
+/* BlockSolver::buildSystem: linearizeOplus + constructQuadraticForm per edge (App. A.3) */
+static void build_system(Graph* g, int jac_mode) {
+  memset(g->Hb, 0, sizeof(double) * (size_t)g->N * (HBW + 1));
+  memset(g->b, 0, sizeof(double) * (size_t)g->N);
+  for (int k = 0; k < g->n_edges; ++k) {
+    Edge* e = g->edges[k];
+    linearize(e, g, jac_mode);
+    double omega_r[2];
+    for (int d = 0; d < e->dim; ++d) omega_r[d] = -e->info[d] * e->err[d];
+    for (int i = 0; i < e->nv; ++i) {
+      if (edge_vertex_fixed(g, e, i)) continue;
+      int di = vdim(e->vkind[i]);
+      int hi = hidx(g, e->vkind[i], e->vidx[i]);
+      const double* A = e->J[i];
+      for (int a = 0; a < di; ++a) {
+        double s = 0;
+        for (int d = 0; d < e->dim; ++d) s += A[d * di + a] * omega_r[d];
+        g->b[hi + a] += s;
+      }
+      /* H_ii += A^T Omega A (lower triangle only) */
+      for (int a = 0; a < di; ++a)
+        for (int bq = 0; bq <= a; ++bq) {
+          double s = 0;
+          for (int d = 0; d < e->dim; ++d) s += A[d * di + a] * e->info[d] * A[d * di + bq];
+          H_add(g, hi + a, hi + bq, s);
+        }
+      for (int j = i + 1; j < e->nv; ++j) {
+        if (edge_vertex_fixed(g, e, j)) continue;
+        int dj = vdim(e->vkind[j]);
+        int hj = hidx(g, e->vkind[j], e->vidx[j]);
+        const double* Bm = e->J[j];
+        for (int a = 0; a < di; ++a)
+          for (int bq = 0; bq < dj; ++bq) {
+            double s = 0;
+            for (int d = 0; d < e->dim; ++d) s += A[d * di + a] * e->info[d] * Bm[d * dj + bq];
+            H_add(g, hi + a, hj + bq, s);
+          }
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ linear solvers */
+/* banded Cholesky (LL^T), lower storage; stand-in for LinearSolverCSparse (App. A.6). Returns 0 on
+ * non-positive pivot. */
+static int solve_banded(Graph* g, double lambda) {
+  const int N = g->N, W = HBW + 1;
+  double* L = g->work;
+  memcpy(L, g->Hb, sizeof(double) * (size_t)N * W);
+  for (int r = 0; r < N; ++r) L[(size_t)r * W] += lambda;
+  for (int j = 0; j < N; ++j) {
+    /* row j of L: entries L[j][j-k], k = HBW..0 */
+    int kmax = j < HBW ? j : HBW;
+    for (int k = kmax; k >= 0; --k) {
+      int col = j - k;
+      double s = L[(size_t)j * W + k];
+      /* subtract sum_{m < col} L[j][m] L[col][m], m >= j-HBW */
+      int m0 = j - HBW; if (m0 < 0) m0 = 0;
+      for (int m = m0; m < col; ++m) s -= L[(size_t)j * W + (j - m)] * L[(size_t)col * W + (col - m)];
+      if (k == 0) {
+        if (!(s > 0) || !isfinite(s)) return 0;
+        L[(size_t)j * W] = sqrt(s);
+      } else {
+        L[(size_t)j * W + k] = s / L[(size_t)col * W];
+      }
+    }
+  }
+  double* x = g->x;
+  for (int j = 0; j < N; ++j) {
+    double s = g->b[j];
+    int m0 = j - HBW; if (m0 < 0) m0 = 0;
+    for (int m = m0; m < j; ++m) s -= L[(size_t)j * W + (j - m)] * x[m];
+    x[j] = s / L[(size_t)j * W];
+  }
+  for (int j = N - 1; j >= 0; --j) {
+    double s = x[j];
+    int m1 = j + HBW; if (m1 > N - 1) m1 = N - 1;
+    for (int m = j + 1; m <= m1; ++m) s -= L[(size_t)m * W + (m - j)] * x[m];
+    x[j] = s / L[(size_t)j * W];
+  }
+  return 1;
+}
+static int solve_dense(Graph* g, double lambda) {
+  const int N = g->N, W = HBW + 1;
+  if (!g->Hd) g->Hd = (double*)malloc(sizeof(double) * (size_t)N * N);
+  double* A = g->Hd;
+  memset(A, 0, sizeof(double) * (size_t)N * N);
+  for (int r = 0; r < N; ++r)
+    for (int k = 0; k <= HBW && k <= r; ++k) A[(size_t)r * N + (r - k)] = g->Hb[(size_t)r * W + k];
+  for (int r = 0; r < N; ++r) A[(size_t)r * N + r] += lambda;
+  for (int j = 0; j < N; ++j) {
+    for (int i = j; i < N; ++i) {
+      double s = A[(size_t)i * N + j];
+      for (int m = 0; m < j; ++m) s -= A[(size_t)i * N + m] * A[(size_t)j * N + m];
+      if (i == j) {
+        if (!(s > 0) || !isfinite(s)) return 0;
+        A[(size_t)j * N + j] = sqrt(s);
+      } else {
+        A[(size_t)i * N + j] = s / A[(size_t)j * N + j];
+      }
+    }
+  }
+  double* x = g->x;
+  for (int j = 0; j < N; ++j) {
+    double s = g->b[j];
+    for (int m = 0; m < j; ++m) s -= A[(size_t)j * N + m] * x[m];
+    x[j] = s / A[(size_t)j * N + j];
+  }
+  for (int j = N - 1; j >= 0; --j) {
+    double s = x[j];
+    for (int m = j + 1; m < N; ++m) s -= A[(size_t)m * N + j] * x[m];
+    x[j] = s / A[(size_t)j * N + j];
+  }
+  return 1;
+}
+
+/* SparseOptimizer::update: every non-fixed vertex oplus its slice of x */
+static void apply_update(Graph* g) {
+  for (int i = 0; i < g->n - 1; ++i) {
+    if (!pose_fixed(g, i)) vertex_oplus(g, 0, i, g->x + hidx(g, 0, i));
+    vertex_oplus(g, 1, i, g->x + hidx(g, 1, i));
+  }
+}
+
+/* ------------------------------------------------------------------ Levenberg-Marquardt (App. A.4/A.5) */
+typedef struct LMState { double lambda, ni; } LMState;
+
+/* returns 1 = OK, 0 = Terminate */
+static int lm_solve(Graph* g, int iteration, LMState* lm, const OracleOptions* opt, OracleStats* st) {
+  double currentChi = compute_active_errors(g);
+  double tempChi = currentChi;
+  build_system(g, opt->jac_mode);
+  if (iteration == 0) {
+    double maxDiagonal = 0;
+    for (int r = 0; r < g->N; ++r) {
+      double d = fabs(g->Hb[(size_t)r * (HBW + 1)]);
+      if (d > maxDiagonal) maxDiagonal = d;
+    }
+    lm->lambda = 1e-5 * maxDiagonal;
+    lm->ni = 2;
+  }
+  double rho = 0;
+  int qmax = 0;
+  do {
+    memcpy(g->backup, g->rec, sizeof(double) * 4 * (size_t)g->n); /* _optimizer->push() */
+    int ok2 = (opt->solver == ORACLE_SOLVER_DENSE) ? solve_dense(g, lm->lambda) : solve_banded(g, lm->lambda);
+    if (!ok2) {
+      st->status |= TEB_STATUS_CHOL_FAILED;
+      /* g2o still calls update(x) with whatever the solver left in x; CSparse leaves x = b on failure.
+       * The state is restored below (tempChi = DBL_MAX -> reject), so only the cached errors differ. */
+      memcpy(g->x, g->b, sizeof(double) * (size_t)g->N);
+    }
+    st->lm_trials++;
+    apply_update(g);
+    tempChi = compute_active_errors(g);
+    if (!ok2) tempChi = DBL_MAX;
+    rho = (currentChi - tempChi);
+    double scale = 0;
+    for (int j = 0; j < g->N; ++j) scale += g->x[j] * (lm->lambda * g->x[j] + g->b[j]);
+    scale += 1e-3;
+    rho /= scale;
+    if (rho > 0 && isfinite(tempChi)) {
+      double alpha = 1. - pow((2 * rho - 1), 3);
+      alpha = alpha < (2. / 3.) ? alpha : (2. / 3.);
+      double scaleFactor = (1. / 3.) > alpha ? (1. / 3.) : alpha;
+      lm->lambda *= scaleFactor;
+      lm->ni = 2;
+      currentChi = tempChi;
+    } else {
+      lm->lambda *= lm->ni;
+      lm->ni *= 2;
+      memcpy(g->rec, g->backup, sizeof(double) * 4 * (size_t)g->n); /* pop() */
+      st->rejected++;
+      if (!isfinite(lm->lambda)) { st->status |= TEB_STATUS_NONFINITE; break; }
+    }
+    qmax++;
+  } while (rho < 0 && qmax < 10);
+  st->chi2_final = currentChi;
+  st->lambda_final = lm->lambda;
+  if (qmax == 10 || rho == 0 || !isfinite(lm->lambda)) return 0;
+  return 1;
+}
+
+/* SparseOptimizer::optimize(iterations) */
+static int optimize_graph_lm(Graph* g, int iterations, const OracleOptions* opt, OracleStats* st) {
+  LMState lm = {0, 2};
+  int ok = 1, cj = 0;
+  for (int i = 0; i < iterations && ok; ++i) {
+    ok = lm_solve(g, i, &lm, opt, st);
+    if (g->cfg->divergence_detection_enable) st->chi2_final = compute_active_errors(g); /* batch statistics */
+    ++cj;
+  }
+  if (!ok) st->status |= TEB_STATUS_TERMINATED; else st->status &= ~TEB_STATUS_TERMINATED;
+  return cj;
+}
+
+/* computeCurrentCost optimal_planner.cpp:1041-1094 (graph exists; uses the cached _error of every edge) */
+static double compute_current_cost(Graph* g, double obst_scale, double via_scale, int alt_time) {
+  double cost = 0;
+  if (alt_time)
+    for (int i = 0; i < g->n - 1; ++i) cost += DT(g, i);
+  for (int k = 0; k < g->n_edges; ++k) {
+    const Edge* e = g->edges[k];
+    double cur = 0;
+    for (int d = 0; d < e->dim; ++d) cur += e->err[d] * e->info[d] * e->err[d];
+    if (e->type == E_OBST || e->type == E_INFL || e->type == E_DYN) cur *= obst_scale;
+    else if (e->type == E_VIA) cur *= via_scale;
+    else if (e->type == E_TIMEOPT && alt_time) continue;
+    cost += cur;
+  }
+  return cost;
+}
+
+/* ------------------------------------------------------------------ autoResize timed_elastic_band.cpp:227-286 */
+static void rec_insert(double* rec, int* n, int at, const double* r4) {
+  memmove(rec + 4 * (at + 1), rec + 4 * at, sizeof(double) * 4 * (size_t)(*n - at));
+  memcpy(rec + 4 * at, r4, sizeof(double) * 4);
+  (*n)++;
+}
+int32_t teb_oracle_auto_resize(double* rec, int32_t n, int32_t n_cap, double dt_ref, double dt_hysteresis,
+                               int32_t min_samples, int32_t max_samples, int32_t fast_mode) {
+  /* rec[i] = (x,y,theta,dt_i); sizeTimeDiffs() = n-1. Pose i+1 travels with dt_i when inserting/deleting. */
+  int modified = 1;
+  for (int rep = 0; rep < 100 && modified; ++rep) {
+    modified = 0;
+    for (int i = 0; i < n - 1; ++i) {
+      double dti = rec[4 * i + 3];
+      if (dti > dt_ref + dt_hysteresis && (n - 1) < max_samples) {
+        if (dti > 2 * dt_ref) {
+          if (n + 1 > n_cap) return TEBGPU_ERR_CAPACITY;
+          double newtime = 0.5 * dti;
+          rec[4 * i + 3] = newtime;
+          /* insertPose(i+1, average(Pose(i),Pose(i+1))); insertTimeDiff(i+1,newtime) */
+          double nr[4];
+          nr[0] = (rec[4 * i] + rec[4 * (i + 1)]) / 2;
+          nr[1] = (rec[4 * i + 1] + rec[4 * (i + 1) + 1]) / 2;
+          nr[2] = teb_oracle_average_angle(rec[4 * i + 2], rec[4 * (i + 1) + 2]);
+          nr[3] = newtime;
+          rec_insert(rec, &n, i + 1, nr);
+          i--;
+          modified = 1;
+        } else {
+          if (i < n - 2) rec[4 * (i + 1) + 3] += rec[4 * i + 3] - dt_ref;
+          rec[4 * i + 3] = dt_ref;
+        }
+      } else if (dti < dt_ref - dt_hysteresis && (n - 1) > min_samples) {
+        if (i < n - 2) {
+          /* TimeDiff(i+1) += TimeDiff(i); deleteTimeDiff(i); deletePose(i+1) */
+          double merged = rec[4 * (i + 1) + 3] + rec[4 * i + 3];
+          memmove(rec + 4 * (i + 1), rec + 4 * (i + 2), sizeof(double) * 4 * (size_t)(n - i - 2));
+          n--;
+          rec[4 * i + 3] = merged;
+          i--;
+        } else {
+          /* last interval: TimeDiff(i-1) += TimeDiff(i); deleteTimeDiff(i); deletePose(i) */
+          rec[4 * (i - 1) + 3] += rec[4 * i + 3];
+          memmove(rec + 4 * i, rec + 4 * (i + 1), sizeof(double) * 4 * (size_t)(n - i - 1));
+          n--;
+        }
+        modified = 1;
+      }
+    }
+    if (fast_mode) break;
+  }
+  rec[4 * (n - 1) + 3] = 0.0;
+  return n;
+}
+
+/* initTrajectoryToGoal(start, goal, diststep, max_vel_x, min_samples, guess_backwards) timed_elastic_band.cpp:325-387 */
+int32_t teb_oracle_init_trajectory(const double* start, const double* goal, double diststep, double max_vel_x,
+                                   int32_t min_samples, int32_t guess_backwards_motion, double* rec, int32_t n_cap) {
+  int n = 0;
+#define ADD_POSE(X, Y, T) do { if (n >= n_cap) return TEBGPU_ERR_CAPACITY; rec[4*n]=(X); rec[4*n+1]=(Y); rec[4*n+2]=(T); rec[4*n+3]=0; n++; } while (0)
+#define ADD_POSE_DT(X, Y, T, D) do { rec[4*(n-1)+3]=(D); ADD_POSE(X, Y, T); } while (0)
+  ADD_POSE(start[0], start[1], start[2]);
+  double timestep = 0.1;
+  if (diststep != 0) {
+    double ptgx = goal[0] - start[0], ptgy = goal[1] - start[1];
+    double dir_to_goal = atan2(ptgy, ptgx);
+    double dx = diststep * cos(dir_to_goal), dy = diststep * sin(dir_to_goal);
+    double orient_init = dir_to_goal;
+    if (guess_backwards_motion && (ptgx * cos(start[2]) + ptgy * sin(start[2])) < 0) orient_init = nt(orient_init + M_PI);
+    double dist_to_goal = sqrt(ptgx * ptgx + ptgy * ptgy);
+    double no_steps_d = dist_to_goal / fabs(diststep);
+    unsigned int no_steps = (unsigned int)floor(no_steps_d);
+    if (max_vel_x > 0) timestep = diststep / max_vel_x;
+    for (unsigned int i = 1; i <= no_steps; i++) {
+      if (i == no_steps && no_steps_d == (float)no_steps) break;
+      ADD_POSE_DT(start[0] + i * dx, start[1] + i * dy, orient_init, timestep);
+    }
+  }
+  if (n < min_samples - 1) {
+    while (n < min_samples - 1) {
+      const double* back = rec + 4 * (n - 1);
+      double ix = (back[0] + goal[0]) / 2, iy = (back[1] + goal[1]) / 2;
+      double it = teb_oracle_average_angle(back[2], goal[2]);
+      if (max_vel_x > 0) timestep = sqrt((ix - back[0]) * (ix - back[0]) + (iy - back[1]) * (iy - back[1])) / max_vel_x;
+      ADD_POSE_DT(ix, iy, it, timestep);
+    }
+  }
+  {
+    const double* back = rec + 4 * (n - 1);
+    if (max_vel_x > 0) timestep = sqrt((goal[0] - back[0]) * (goal[0] - back[0]) + (goal[1] - back[1]) * (goal[1] - back[1])) / max_vel_x;
+    ADD_POSE_DT(goal[0], goal[1], goal[2], timestep);
+  }
+#undef ADD_POSE
+#undef ADD_POSE_DT
+  return n;
+}
+
+/* ------------------------------------------------------------------ optimizeTEB optimal_planner.cpp:182-231 */
+static void graph_alloc(Graph* g, int n_cap) {
+  int Ncap = 4 * n_cap;
+  g->Hb = (double*)malloc(sizeof(double) * (size_t)Ncap * (HBW + 1));
+  g->work = (double*)malloc(sizeof(double) * (size_t)Ncap * (HBW + 1));
+  g->b = (double*)malloc(sizeof(double) * (size_t)Ncap);
+  g->x = (double*)malloc(sizeof(double) * (size_t)Ncap);
+  g->backup = (double*)malloc(sizeof(double) * 4 * (size_t)n_cap);
+}
+static void graph_free(Graph* g) {
+  clear_graph(g);
+  free(g->edges); free(g->Hb); free(g->work); free(g->b); free(g->x); free(g->backup); free(g->Hd);
+}
+
+int32_t teb_oracle_optimize(const TebParams* cfg, double* rec, int32_t* n_io, int32_t n_cap,
+                            const TebObstacle* obst, int32_t M, const double* via, int32_t V,
+                            const double* vel_start4, const double* vel_goal4, int32_t prefer_rotdir,
+                            const TebOptimizeArgs* args, const OracleOptions* opt,
+                            double* cost_out, OracleStats* stats) {
+  OracleStats st;
+  memset(&st, 0, sizeof(st));
+  OracleOptions o = {ORACLE_JAC_G2O, ORACLE_SOLVER_BANDED, 0, 0};
+  if (opt) o = *opt;
+  int rc = 0;
+  if (!cfg->optimization_activate) { st.status |= TEB_STATUS_DISABLED; goto done; }
+  {
+    Graph g;
+    memset(&g, 0, sizeof(g));
+    g.cfg = cfg; g.rec = rec; g.n = *n_io; g.obst = obst; g.M = M; g.via = via; g.V = V;
+    memcpy(g.vel_start, vel_start4, sizeof(double) * 4);
+    memcpy(g.vel_goal, vel_goal4, sizeof(double) * 4);
+    g.rotdir = prefer_rotdir;
+    graph_alloc(&g, n_cap);
+    double weight_multiplier = 1.0;
+    int fast_mode = !cfg->include_dynamic_obstacles;
+    int success = 1;
+    for (int i = 0; i < args->iterations_outerloop; ++i) {
+      if (cfg->teb_autosize) {
+        int nn = teb_oracle_auto_resize(rec, g.n, n_cap, cfg->dt_ref, cfg->dt_hysteresis, cfg->min_samples,
+                                        cfg->max_samples, fast_mode);
+        if (nn < 0) { rc = nn; success = 0; break; }
+        g.n = nn;
+      }
+      rc = build_graph(&g, weight_multiplier);
+      if (rc) { success = 0; break; }
+      /* optimizeGraph guards optimal_planner.cpp:370-382 */
+      if (cfg->max_vel_x < 0.01) { st.status |= TEB_STATUS_DISABLED; success = 0; clear_graph(&g); break; }
+      if (g.n < cfg->min_samples || g.n < 3) { st.status |= TEB_STATUS_TOO_FEW_POSES; success = 0; clear_graph(&g); break; }
+      st.lm_iters += optimize_graph_lm(&g, args->iterations_innerloop, &o, &st);
+      st.n_edges_last = g.n_edges;
+      if (args->compute_cost_afterwards && i == args->iterations_outerloop - 1 && cost_out)
+        *cost_out = compute_current_cost(&g, args->obst_cost_scale, args->viapoint_cost_scale, args->alternative_time_cost);
+      clear_graph(&g);
+      weight_multiplier *= cfg->weight_adapt_factor;
+    }
+    if (success && args->iterations_outerloop > 0) st.status |= TEB_STATUS_OPTIMIZED;
+    *n_io = g.n;
+    graph_free(&g);
+  }
+done:
+  st.n_final = *n_io;
+  if (stats) *stats = st;
+  return rc;
+}
+
+int32_t teb_oracle_build_system(const TebParams* cfg, const double* rec_in, int32_t n,
+                                const TebObstacle* obst, int32_t M, const double* via, int32_t V,
+                                const double* vel_start4, const double* vel_goal4, int32_t prefer_rotdir,
+                                double weight_multiplier, int32_t jac_mode,
+                                double* H_dense, double* b, double* chi2) {
+  Graph g;
+  memset(&g, 0, sizeof(g));
+  double* rec = (double*)malloc(sizeof(double) * 4 * (size_t)n);
+  memcpy(rec, rec_in, sizeof(double) * 4 * (size_t)n);
+  g.cfg = cfg; g.rec = rec; g.n = n; g.obst = obst; g.M = M; g.via = via; g.V = V;
+  memcpy(g.vel_start, vel_start4, sizeof(double) * 4);
+  memcpy(g.vel_goal, vel_goal4, sizeof(double) * 4);
+  g.rotdir = prefer_rotdir;
+  graph_alloc(&g, n);
+  int rc = build_graph(&g, weight_multiplier);
+  if (rc) { graph_free(&g); free(rec); return rc; }
+  double c2 = compute_active_errors(&g);
+  build_system(&g, jac_mode);
+  int N = g.N;
+  if (H_dense) {
+    memset(H_dense, 0, sizeof(double) * (size_t)N * N);
+    for (int r = 0; r < N; ++r)
+      for (int k = 0; k <= HBW && k <= r; ++k) {
+        double v = g.Hb[(size_t)r * (HBW + 1) + k];
+        H_dense[(size_t)r * N + (r - k)] = v;
+        H_dense[(size_t)(r - k) * N + r] = v;
+      }
+  }
+  if (b) memcpy(b, g.b, sizeof(double) * (size_t)N);
+  if (chi2) *chi2 = c2;
+  graph_free(&g);
+  free(rec);
+  return N;
+}
+
+/* ------------------------------------------------------------------ batch driver (thread per band) */
+typedef struct BatchJob {
+  const TebParams* cfg; const TebBatch* batch; const TebOptimizeArgs* args; const OracleOptions* opt;
+  int next; pthread_mutex_t mu; int rc;
+} BatchJob;
+
+static void* batch_worker(void* p) {
+  BatchJob* job = (BatchJob*)p;
+  const TebBatch* bt = job->batch;
+  for (;;) {
+    pthread_mutex_lock(&job->mu);
+    int bidx = job->next++;
+    pthread_mutex_unlock(&job->mu);
+    if (bidx >= bt->B) break;
+    int s = bt->scene_id ? bt->scene_id[bidx] : 0;
+    const double zero4[4] = {0, 0, 0, 1};
+    double cost = HUGE_VAL;
+    OracleStats st;
+    int nb = bt->n[bidx];
+    int rc = teb_oracle_optimize(job->cfg, bt->poses + (size_t)bidx * bt->n_cap * 4, &nb, bt->n_cap,
+                                 bt->obstacles + (size_t)s * bt->M_cap, bt->obst_count ? bt->obst_count[s] : 0,
+                                 bt->via ? bt->via + (size_t)bidx * bt->V_cap * 2 : NULL,
+                                 bt->via_count ? bt->via_count[bidx] : 0,
+                                 bt->vel_start ? bt->vel_start + 4 * bidx : zero4,
+                                 bt->vel_goal ? bt->vel_goal + 4 * bidx : zero4,
+                                 bt->prefer_rotdir ? bt->prefer_rotdir[bidx] : 0, job->args, job->opt, &cost, &st);
+    bt->n[bidx] = nb;
+    if (bt->cost) bt->cost[bidx] = cost;
+    if (bt->chi2) bt->chi2[bidx] = st.chi2_final;
+    if (bt->status) bt->status[bidx] = st.status;
+    if (bt->lm_iters) bt->lm_iters[bidx] = st.lm_iters;
+    if (rc) job->rc = rc;
+  }
+  return NULL;
+}
+
+int32_t teb_oracle_optimize_batch(const TebParams* cfg, const TebBatch* batch, const TebOptimizeArgs* args,
+                                  const OracleOptions* opt, int32_t threads) {
+  BatchJob job;
+  job.cfg = cfg; job.batch = batch; job.args = args; job.opt = opt; job.next = 0; job.rc = 0;
+  pthread_mutex_init(&job.mu, NULL);
+  if (threads < 1) threads = 1;
+  if (threads > batch->B) threads = batch->B;
+  if (threads == 1) {
+    batch_worker(&job);
+  } else {
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
+    for (int t = 0; t < threads; ++t) pthread_create(&th[t], NULL, batch_worker, &job);
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    free(th);
+  }
+  pthread_mutex_destroy(&job.mu);
+  return job.rc;
+}
