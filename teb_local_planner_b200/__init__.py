@@ -1,0 +1,125 @@
+"""teb_local_planner_b200 — B200-native (sm_100a) batched Timed-Elastic-Band optimizer.
+
+Python side: ctypes loader for the in-tree CUDA library (C-ABI in include/teb_b200.h) and a thin
+`TebGpu` convenience wrapper used by tests and bench.py. There is no CPU fallback: if the CUDA
+library is missing or no GPU is present, loading / creating a context raises.
+"""
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libteb_b200.so")
+_lib = None
+
+
+def load_library(build_if_missing=False):
+    """Load libteb_b200.so (raises if it has not been built: run `python __graft_entry__.py` / build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            from . import build as _b
+            _b.build()
+        else:
+            raise RuntimeError(f"{LIB_PATH} is missing: build the CUDA extension first "
+                               "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.tebgpu_default_params.restype = None
+    L.tebgpu_default_params.argtypes = [C.POINTER(abi.TebParams)]
+    L.tebgpu_sizeof.restype = C.c_int32
+    L.tebgpu_sizeof.argtypes = [C.c_int32]
+    L.tebgpu_create.restype = C.c_int32
+    L.tebgpu_create.argtypes = [C.POINTER(abi.TebGpuLimits), C.c_int32, C.POINTER(vp)]
+    L.tebgpu_destroy.restype = C.c_int32
+    L.tebgpu_destroy.argtypes = [vp]
+    L.tebgpu_last_error_string.restype = C.c_char_p
+    L.tebgpu_last_error_string.argtypes = [vp]
+    L.tebgpu_set_params.restype = C.c_int32
+    L.tebgpu_set_params.argtypes = [vp, C.POINTER(abi.TebParams)]
+    L.tebgpu_optimize_batch.restype = C.c_int32
+    L.tebgpu_optimize_batch.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs)]
+    L.tebgpu_optimize_batch_device.restype = C.c_int32
+    L.tebgpu_optimize_batch_device.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs), vp]
+    L.tebgpu_synchronize.restype = C.c_int32
+    L.tebgpu_synchronize.argtypes = [vp]
+    L.tebgpu_last_launch_count.restype = C.c_int64
+    L.tebgpu_last_launch_count.argtypes = [vp]
+    L.tebgpu_build_system.restype = C.c_int32
+    L.tebgpu_build_system.argtypes = [vp, C.POINTER(abi.TebBatch), C.c_int32, vp, vp, C.c_int32]
+    L.tebgpu_select_best.restype = C.c_int32
+    L.tebgpu_select_best.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double]
+    L.tebgpu_auto_resize_host.restype = C.c_int32
+    L.tebgpu_auto_resize_host.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32]
+    for which, st in enumerate((abi.TebParams, abi.TebObstacle, abi.TebBatch, abi.TebOptimizeArgs, abi.TebGpuLimits)):
+        if L.tebgpu_sizeof(which) != C.sizeof(st):
+            raise RuntimeError(f"ABI mismatch for {st.__name__}: C {L.tebgpu_sizeof(which)} vs ctypes {C.sizeof(st)}")
+    _lib = L
+    return L
+
+
+class TebGpuError(RuntimeError):
+    pass
+
+
+class TebGpu:
+    """One tebgpu context (one device, one stream, its workspaces)."""
+
+    def __init__(self, max_bands, max_poses, max_scenes=1, max_obstacles=64, max_viapoints=0, device=0):
+        self.lib = load_library()
+        lim = abi.TebGpuLimits(max_bands, max_poses, max_scenes, max_obstacles, max_viapoints, 0)
+        self.ctx = C.c_void_p()
+        rc = self.lib.tebgpu_create(C.byref(lim), device, C.byref(self.ctx))
+        if rc != 0:
+            msg = self.lib.tebgpu_last_error_string(self.ctx).decode() if self.ctx else ""
+            if self.ctx:
+                self.lib.tebgpu_destroy(self.ctx)
+                self.ctx = None
+            raise TebGpuError(f"tebgpu_create failed rc={rc} {msg}")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise TebGpuError(f"{what} rc={rc}: {self.lib.tebgpu_last_error_string(self.ctx).decode()}")
+
+    def set_params(self, params):
+        self._check(self.lib.tebgpu_set_params(self.ctx, C.byref(params)), "tebgpu_set_params")
+
+    def optimize(self, hb, args):
+        """Host-buffer call: hb is an abi.HostBatch, updated in place."""
+        bs = hb.struct()
+        self._check(self.lib.tebgpu_optimize_batch(self.ctx, C.byref(bs), C.byref(args)), "tebgpu_optimize_batch")
+        return hb
+
+    def optimize_device(self, batch_struct, args, stream=None):
+        self._check(self.lib.tebgpu_optimize_batch_device(self.ctx, C.byref(batch_struct), C.byref(args), stream),
+                    "tebgpu_optimize_batch_device")
+
+    def synchronize(self):
+        self._check(self.lib.tebgpu_synchronize(self.ctx), "tebgpu_synchronize")
+
+    def launch_count(self):
+        return int(self.lib.tebgpu_last_launch_count(self.ctx))
+
+    def build_system(self, hb, outer_index=0):
+        """Returns (Hb [B][4*n_cap][12], chi2 [B]) as numpy arrays (host-buffer path)."""
+        import numpy as np
+        Hb = np.zeros((hb.B, 4 * hb.n_cap, 12))
+        chi2 = np.zeros(hb.B)
+        bs = hb.struct()
+        self._check(self.lib.tebgpu_build_system(self.ctx, C.byref(bs), outer_index, Hb.ctypes.data, chi2.ctypes.data, 0),
+                    "tebgpu_build_system")
+        return Hb, chi2
+
+    def close(self):
+        if self.ctx:
+            self.lib.tebgpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,410 @@
+/*
+ * teb_cabi.cu — C-ABI (include/teb_b200.h) over the sm_100a kernels in teb_kernels.cuh.
+ * No CPU fallback: every entry point that optimises needs a CUDA device and fails loudly otherwise.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "teb_kernels.cuh"
+
+using namespace tebgpu;
+
+struct tebgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  TebGpuLimits lim{};
+  TebParams params{};
+  bool have_params = false;
+  std::string err;
+  int64_t launches = 0;
+  int MW = 1;
+  int chunks = 1;
+  /* device workspaces */
+  double* Hb = nullptr;
+  unsigned long long* assoc = nullptr;
+  double* dyn_t = nullptr;
+  int32_t* via_idx = nullptr;
+  double* chi_parts = nullptr;
+  BandState* state = nullptr;
+  /* device mirrors for the host-buffer entry point */
+  double* d_poses = nullptr; int32_t* d_n = nullptr; int32_t* d_scene = nullptr; TebObstacle* d_obst = nullptr;
+  int32_t* d_ocount = nullptr; double* d_via = nullptr; int32_t* d_vcount = nullptr; double* d_vs = nullptr;
+  double* d_vg = nullptr; int32_t* d_rot = nullptr; double* d_cost = nullptr; double* d_chi2 = nullptr;
+  int32_t* d_status = nullptr; int32_t* d_iters = nullptr;
+  size_t smem_a = 0, smem_b = 0, smem_g = 0;
+};
+
+#define CUDA_TRY(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                           \
+      return TEBGPU_ERR_CUDA;                                                                    \
+    }                                                                                            \
+  } while (0)
+
+extern "C" {
+
+void tebgpu_default_params(TebParams* p) {
+  /* TebConfig::TebConfig() teb_config.h:245-390 */
+  std::memset(p, 0, sizeof(*p));
+  p->dt_ref = 0.3; p->dt_hysteresis = 0.1;
+  p->force_reinit_new_goal_dist = 1; p->force_reinit_new_goal_angular = 0.5 * M_PI;
+  p->teb_autosize = 1; p->min_samples = 3; p->max_samples = 500; p->exact_arc_length = 0;
+  p->via_points_ordered = 0; p->allow_init_with_backwards_motion = 0; p->global_plan_overwrite_orientation = 1;
+  p->max_vel_x = 0.4; p->max_vel_x_backwards = 0.2; p->max_vel_y = 0.0; p->max_vel_trans = 0.0; p->max_vel_theta = 0.3;
+  p->acc_lim_x = 0.5; p->acc_lim_y = 0.5; p->acc_lim_theta = 0.5; p->min_turning_radius = 0;
+  p->footprint_type = TEB_FOOTPRINT_POINT;
+  p->min_obstacle_dist = 0.5; p->inflation_dist = 0.6; p->dynamic_obstacle_inflation_dist = 0.6;
+  p->obstacle_association_force_inclusion_factor = 1.5; p->obstacle_association_cutoff_factor = 5;
+  p->obstacle_proximity_ratio_max_vel = 1; p->obstacle_proximity_lower_bound = 0; p->obstacle_proximity_upper_bound = 0.5;
+  p->include_dynamic_obstacles = 1; p->legacy_obstacle_association = 0; p->obstacle_poses_affected = 25;
+  p->penalty_epsilon = 0.05;
+  p->weight_max_vel_x = 2; p->weight_max_vel_y = 2; p->weight_max_vel_theta = 1;
+  p->weight_acc_lim_x = 1; p->weight_acc_lim_y = 1; p->weight_acc_lim_theta = 1;
+  p->weight_kinematics_nh = 1000; p->weight_kinematics_forward_drive = 1; p->weight_kinematics_turning_radius = 1;
+  p->weight_optimaltime = 1; p->weight_shortest_path = 0;
+  p->weight_obstacle = 50; p->weight_inflation = 0.1;
+  p->weight_dynamic_obstacle = 50; p->weight_dynamic_obstacle_inflation = 0.1;
+  p->weight_velocity_obstacle_ratio = 0; p->weight_viapoint = 1; p->weight_prefer_rotdir = 50;
+  p->weight_adapt_factor = 2.0; p->obstacle_cost_exponent = 1.0;
+  p->no_inner_iterations = 5; p->no_outer_iterations = 4; p->optimization_activate = 1;
+  p->selection_cost_hysteresis = 1.0; p->selection_prefer_initial_plan = 0.95;
+  p->selection_obst_cost_scale = 100.0; p->selection_viapoint_cost_scale = 1.0;
+  p->selection_alternative_time_cost = 0; p->enable_multithreading = 1;
+  p->divergence_detection_enable = 0; p->divergence_detection_max_chi_squared = 10;
+}
+
+int32_t tebgpu_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return (int32_t)sizeof(TebParams);
+    case 1: return (int32_t)sizeof(TebObstacle);
+    case 2: return (int32_t)sizeof(TebBatch);
+    case 3: return (int32_t)sizeof(TebOptimizeArgs);
+    case 4: return (int32_t)sizeof(TebGpuLimits);
+    default: return -1;
+  }
+}
+
+const char* tebgpu_last_error_string(const tebgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static void free_all(tebgpu_ctx* c) {
+  void* ptrs[] = {c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+                  c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
+                  c->d_status, c->d_iters};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+}
+
+int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out) {
+  if (!lim || !out) return TEBGPU_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= device || device < 0) {
+    std::fprintf(stderr, "tebgpu_create: no CUDA device %d available (this library has no CPU fallback)\n", device);
+    return TEBGPU_ERR_NO_DEVICE;
+  }
+  if (lim->max_bands < 1 || lim->max_poses < 3 || lim->max_poses > 512 || lim->max_scenes < 1 || lim->max_obstacles < 0 ||
+      lim->max_obstacles > 64 * MAX_MW || lim->max_viapoints < 0)
+    return TEBGPU_ERR_INVALID_ARG;
+  tebgpu_ctx* c = new (std::nothrow) tebgpu_ctx();
+  if (!c) return TEBGPU_ERR_CUDA;
+  c->device = device;
+  c->lim = *lim;
+  if (c->lim.max_obstacles < 1) c->lim.max_obstacles = 1;
+  c->MW = (c->lim.max_obstacles + 63) / 64;
+  c->chunks = (c->lim.max_poses + TP - 1) / TP;
+  *out = c;
+  CUDA_TRY(c, cudaSetDevice(device));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  const size_t B = c->lim.max_bands, nc = c->lim.max_poses, S = c->lim.max_scenes, M = c->lim.max_obstacles,
+               V = c->lim.max_viapoints > 0 ? c->lim.max_viapoints : 1;
+  CUDA_TRY(c, cudaMalloc(&c->Hb, B * 4 * nc * HROW * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->assoc, B * nc * c->MW * sizeof(unsigned long long)));
+  CUDA_TRY(c, cudaMalloc(&c->dyn_t, B * nc * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->via_idx, B * V * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->chi_parts, B * c->chunks * 4 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->state, B * sizeof(BandState)));
+  CUDA_TRY(c, cudaMalloc(&c->d_poses, B * nc * 4 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_n, B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_scene, B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_obst, S * M * sizeof(TebObstacle)));
+  CUDA_TRY(c, cudaMalloc(&c->d_ocount, S * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_via, B * V * 2 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_vcount, B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_vs, B * 4 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_vg, B * 4 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_rot, B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_cost, B * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_chi2, B * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_status, B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->d_iters, B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMemsetAsync(c->dyn_t, 0, B * nc * sizeof(double), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->via_idx, 0xff, B * V * sizeof(int32_t), c->stream));
+  c->smem_a = ka_smem_bytes((int)M);
+  c->smem_b = kb_smem_bytes((int)nc, (int)M);
+  c->smem_g = M * sizeof(TebObstacle);
+  if (c->smem_b > 232448 || c->smem_a > 232448) {
+    c->err = "shared-memory footprint exceeds 227 KB for these limits (max_poses / max_obstacles too large)";
+    return TEBGPU_ERR_CAPACITY;
+  }
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_build_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_g));
+  tebgpu_default_params(&c->params);
+  c->have_params = true;
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_destroy(tebgpu_ctx* ctx) {
+  if (!ctx) return TEBGPU_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+  free_all(ctx);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* p) {
+  if (!ctx || !p) return TEBGPU_ERR_INVALID_ARG;
+  /* cost terms without a kernel yet: refuse instead of silently dropping them */
+  if (p->max_vel_y != 0) { ctx->err = "holonomic edges (max_vel_y != 0) are not implemented"; return TEBGPU_ERR_UNSUPPORTED; }
+  if (p->weight_velocity_obstacle_ratio > 0) { ctx->err = "EdgeVelocityObstacleRatio is not implemented"; return TEBGPU_ERR_UNSUPPORTED; }
+  if (p->legacy_obstacle_association) { ctx->err = "legacy obstacle association is not implemented"; return TEBGPU_ERR_UNSUPPORTED; }
+  if (p->footprint_type < 0 || p->footprint_type > TEB_FOOTPRINT_TWO_CIRCLES) { ctx->err = "unsupported footprint model"; return TEBGPU_ERR_UNSUPPORTED; }
+  ctx->params = *p;
+  ctx->have_params = true;
+  return TEBGPU_OK;
+}
+
+static KParams make_kparams(const TebParams& p, double weight_multiplier) {
+  KParams k;
+  std::memset(&k, 0, sizeof(k));
+  k.p = p;
+  k.w_obst = p.weight_obstacle * weight_multiplier;
+  k.sw_vel_x = std::sqrt(p.weight_max_vel_x); k.sw_vel_th = std::sqrt(p.weight_max_vel_theta);
+  k.sw_acc_x = std::sqrt(p.weight_acc_lim_x); k.sw_acc_th = std::sqrt(p.weight_acc_lim_theta);
+  k.inflated = p.inflation_dist > p.min_obstacle_dist;
+  k.carlike = !(p.min_turning_radius == 0 || p.weight_kinematics_turning_radius == 0);
+  k.sw_kin_nh = std::sqrt(p.weight_kinematics_nh);
+  k.sw_kin_2 = std::sqrt(k.carlike ? p.weight_kinematics_turning_radius : p.weight_kinematics_forward_drive);
+  k.sw_sp = std::sqrt(p.weight_shortest_path);
+  k.sw_rot = std::sqrt(p.weight_prefer_rotdir);
+  k.has_vel = !(p.weight_max_vel_x == 0 && p.weight_max_vel_theta == 0);
+  k.has_acc = !(p.weight_acc_lim_x == 0 && p.weight_acc_lim_theta == 0);
+  k.has_kin = k.carlike ? !(p.weight_kinematics_nh == 0 && p.weight_kinematics_turning_radius == 0)
+                        : !(p.weight_kinematics_nh == 0 && p.weight_kinematics_forward_drive == 0);
+  k.has_sp = p.weight_shortest_path != 0;
+  k.has_rot = p.weight_prefer_rotdir != 0;
+  k.has_time = p.weight_optimaltime != 0;
+  k.has_obst = !(p.weight_obstacle == 0 || weight_multiplier == 0);
+  k.has_dyn = p.include_dynamic_obstacles && p.weight_obstacle != 0; /* optimal_planner.cpp:342, :648 */
+  k.has_via = p.weight_viapoint != 0;
+  k.pow_exponent = (p.obstacle_cost_exponent != 1.0 && p.min_obstacle_dist > 0.0);
+  return k;
+}
+
+static int32_t check_batch(tebgpu_ctx* ctx, const TebBatch* bt) {
+  if (!ctx || !bt) return TEBGPU_ERR_INVALID_ARG;
+  if (bt->B < 1 || bt->n_cap < 3 || bt->S < 1 || bt->M_cap < 0 || bt->V_cap < 0) { ctx->err = "bad batch dimensions"; return TEBGPU_ERR_INVALID_ARG; }
+  if (bt->B > ctx->lim.max_bands || bt->n_cap > ctx->lim.max_poses || bt->S > ctx->lim.max_scenes ||
+      bt->M_cap > ctx->lim.max_obstacles || bt->V_cap > ctx->lim.max_viapoints) { ctx->err = "batch exceeds the context limits"; return TEBGPU_ERR_CAPACITY; }
+  if (!bt->poses || !bt->n || !bt->scene_id || !bt->obst_count || !bt->vel_start || !bt->vel_goal) { ctx->err = "missing required batch array"; return TEBGPU_ERR_INVALID_ARG; }
+  if (bt->M_cap > 0 && !bt->obstacles) { ctx->err = "obstacles == NULL"; return TEBGPU_ERR_INVALID_ARG; }
+  if (bt->V_cap > 0 && (!bt->via || !bt->via_count)) { ctx->err = "via == NULL"; return TEBGPU_ERR_INVALID_ARG; }
+  return TEBGPU_OK;
+}
+
+static DevBatch make_devbatch(tebgpu_ctx* ctx, const TebBatch* bt) {
+  DevBatch d;
+  std::memset(&d, 0, sizeof(d));
+  d.B = bt->B; d.n_cap = bt->n_cap; d.S = bt->S; d.M_cap = bt->M_cap; d.V_cap = bt->V_cap;
+  d.MW = (bt->M_cap + 63) / 64; if (d.MW < 1) d.MW = 1;
+  d.poses = bt->poses; d.n = bt->n; d.scene_id = bt->scene_id; d.obstacles = bt->obstacles; d.obst_count = bt->obst_count;
+  d.via = bt->via; d.via_count = bt->via_count; d.vel_start = bt->vel_start; d.vel_goal = bt->vel_goal;
+  d.prefer_rotdir = bt->prefer_rotdir;
+  d.cost = bt->cost; d.chi2 = bt->chi2; d.status = bt->status; d.lm_iters = bt->lm_iters;
+  d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts;
+  d.state = ctx->state;
+  d.chunks = (bt->n_cap + TP - 1) / TP;
+  return d;
+}
+
+int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimizeArgs* args, void* cuda_stream) {
+  int32_t rc = check_batch(ctx, bt);
+  if (rc) return rc;
+  if (!args || args->iterations_innerloop < 0 || args->iterations_outerloop < 0) { ctx->err = "bad optimize args"; return TEBGPU_ERR_INVALID_ARG; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  DevBatch db = make_devbatch(ctx, bt);
+  const TebParams& p = ctx->params;
+  const int B = bt->B;
+  const int tb = 128, gb = (B + tb - 1) / tb;
+  int64_t launches = 0;
+  const size_t smem_a = ka_smem_bytes(bt->M_cap);
+  const size_t smem_b = kb_smem_bytes(bt->n_cap, bt->M_cap);
+  const size_t smem_g = (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle);
+  double weight_multiplier = 1.0;
+  KParams kp = make_kparams(p, weight_multiplier);
+  k_begin<<<gb, tb, 0, st>>>(db, kp); ++launches;
+  for (int o = 0; o < args->iterations_outerloop; ++o) {
+    kp = make_kparams(p, weight_multiplier);
+    if (p.teb_autosize) { k_auto_resize<<<gb, tb, 0, st>>>(db, kp); ++launches; }
+    k_build_graph<<<B, 256, smem_g, st>>>(db, kp); ++launches;
+    for (int it = 0; it < args->iterations_innerloop; ++it) {
+      k_linearize<<<dim3(db.chunks, B), KA_THREADS, smem_a, st>>>(db, kp); ++launches;
+      k_lm_step<<<B, KB_THREADS, smem_b, st>>>(db, kp, it); ++launches;
+    }
+    weight_multiplier *= p.weight_adapt_factor; /* optimal_planner.cpp:227 */
+  }
+  k_finalize<<<gb, tb, 0, st>>>(db, kp, *args); ++launches;
+  ctx->launches = launches;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_synchronize(tebgpu_ctx* ctx) {
+  if (!ctx) return TEBGPU_ERR_INVALID_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return TEBGPU_OK;
+}
+
+static TebBatch mirror_batch(tebgpu_ctx* ctx, const TebBatch* bt) {
+  TebBatch d = *bt;
+  d.poses = ctx->d_poses; d.n = ctx->d_n; d.scene_id = ctx->d_scene; d.obstacles = ctx->d_obst; d.obst_count = ctx->d_ocount;
+  d.via = bt->V_cap > 0 ? ctx->d_via : nullptr; d.via_count = bt->V_cap > 0 ? ctx->d_vcount : nullptr;
+  d.vel_start = ctx->d_vs; d.vel_goal = ctx->d_vg; d.prefer_rotdir = bt->prefer_rotdir ? ctx->d_rot : nullptr;
+  d.cost = ctx->d_cost; d.chi2 = ctx->d_chi2; d.status = ctx->d_status; d.lm_iters = ctx->d_iters;
+  return d;
+}
+
+static int32_t upload_batch(tebgpu_ctx* ctx, const TebBatch* bt) {
+  cudaStream_t st = ctx->stream;
+  const size_t B = bt->B, nc = bt->n_cap;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_poses, bt->poses, B * nc * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_n, bt->n, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scene, bt->scene_id, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (bt->M_cap > 0)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_obst, bt->obstacles, (size_t)bt->S * bt->M_cap * sizeof(TebObstacle), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ocount, bt->obst_count, (size_t)bt->S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (bt->V_cap > 0) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_via, bt->via, B * bt->V_cap * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vcount, bt->via_count, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vs, bt->vel_start, B * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vg, bt->vel_goal, B * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (bt->prefer_rotdir)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_rot, bt->prefer_rotdir, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_optimize_batch(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimizeArgs* args) {
+  int32_t rc = check_batch(ctx, bt);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rc = upload_batch(ctx, bt);
+  if (rc) return rc;
+  TebBatch d = mirror_batch(ctx, bt);
+  rc = tebgpu_optimize_batch_device(ctx, &d, args, nullptr);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const size_t B = bt->B, nc = bt->n_cap;
+  CUDA_TRY(ctx, cudaMemcpyAsync(bt->poses, ctx->d_poses, B * nc * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(bt->n, ctx->d_n, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (bt->cost) CUDA_TRY(ctx, cudaMemcpyAsync(bt->cost, ctx->d_cost, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (bt->chi2) CUDA_TRY(ctx, cudaMemcpyAsync(bt->chi2, ctx->d_chi2, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (bt->status) CUDA_TRY(ctx, cudaMemcpyAsync(bt->status, ctx->d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (bt->lm_iters) CUDA_TRY(ctx, cudaMemcpyAsync(bt->lm_iters, ctx->d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* bt, int32_t outer_index, double* Hb_out, double* chi2_out,
+                            int32_t device_ptrs) {
+  int32_t rc = check_batch(ctx, bt);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  TebBatch d = *bt;
+  if (!device_ptrs) {
+    rc = upload_batch(ctx, bt);
+    if (rc) return rc;
+    d = mirror_batch(ctx, bt);
+  }
+  cudaStream_t st = ctx->stream;
+  DevBatch db = make_devbatch(ctx, &d);
+  double mult = 1.0;
+  for (int o = 0; o < outer_index; ++o) mult *= ctx->params.weight_adapt_factor;
+  KParams kp = make_kparams(ctx->params, mult);
+  const int B = bt->B, tb = 128, gb = (B + tb - 1) / tb;
+  k_begin<<<gb, tb, 0, st>>>(db, kp);
+  k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
+  k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(bt->M_cap), st>>>(db, kp);
+  ctx->launches = 3;
+  CUDA_TRY(ctx, cudaGetLastError());
+  const size_t per_band = (size_t)4 * bt->n_cap * HROW;
+  if (Hb_out)
+    CUDA_TRY(ctx, cudaMemcpyAsync(Hb_out, ctx->Hb, (size_t)B * per_band * sizeof(double),
+                                  device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (chi2_out) {
+    /* sum the tile partials on the host side of the call */
+    std::string hold;
+    const size_t cnt = (size_t)B * db.chunks * 4;
+    double* tmp = new (std::nothrow) double[cnt];
+    int32_t* hn = new (std::nothrow) int32_t[B];
+    if (!tmp || !hn) { delete[] tmp; delete[] hn; return TEBGPU_ERR_CUDA; }
+    cudaError_t e1 = cudaMemcpyAsync(tmp, ctx->chi_parts, cnt * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaMemcpyAsync(hn, d.n, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { delete[] tmp; delete[] hn; ctx->err = "chi2 readback failed"; return TEBGPU_ERR_CUDA; }
+    double* host_chi = device_ptrs ? new (std::nothrow) double[B] : chi2_out;
+    for (int b = 0; b < B; ++b) {
+      double s = 0;
+      const int used = (hn[b] + TP - 1) / TP;
+      for (int c = 0; c < used; ++c)
+        for (int k = 0; k < 4; ++k) s += tmp[((size_t)b * db.chunks + c) * 4 + k];
+      host_chi[b] = s;
+    }
+    if (device_ptrs) {
+      cudaMemcpy(chi2_out, host_chi, (size_t)B * sizeof(double), cudaMemcpyHostToDevice);
+      delete[] host_chi;
+    }
+    delete[] tmp;
+    delete[] hn;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_select_best(const double* cost, int32_t count, int32_t last_best, int32_t initial_plan,
+                           double selection_cost_hysteresis, double selection_prefer_initial_plan) {
+  /* HomotopyClassPlanner::selectBestTeb homotopy_class_planner.cpp:564-616 */
+  if (!cost || count <= 0) return -1;
+  double min_cost = 1.7976931348623157e308;
+  int best = -1;
+  for (int i = 0; i < count; ++i) {
+    double teb_cost;
+    if (i == last_best) teb_cost = cost[i] * selection_cost_hysteresis;
+    else if (i == initial_plan) teb_cost = cost[i] * selection_prefer_initial_plan;
+    else teb_cost = cost[i];
+    if (teb_cost < min_cost) { best = i; min_cost = teb_cost; }
+  }
+  return best;
+}
+
+int32_t tebgpu_auto_resize_host(double* rec, int32_t n, int32_t n_cap, double dt_ref, double dt_hysteresis,
+                                int32_t min_samples, int32_t max_samples, int32_t fast_mode) {
+  if (!rec || n < 1 || n > n_cap) return TEBGPU_ERR_INVALID_ARG;
+  int nn = teb_auto_resize_records(rec, n, n_cap, dt_ref, dt_hysteresis, min_samples, max_samples, fast_mode);
+  return nn < 0 ? TEBGPU_ERR_CAPACITY : nn;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,244 @@
+/*
+ * teb_device.cuh — device-side arithmetic of the TEB cost terms (residuals and closed-form Jacobians).
+ *
+ * Every function cites the reference body it reproduces (paths relative to the reference checkout):
+ *   g2o_types/penalties.h, misc.h, pose_se2.h, obstacles.h, robot_footprint_model.h, g2o_types/edge_*.h.
+ * The reference linearises numerically (central differences, delta 1e-9) for all edges except
+ * EdgeKinematicsDiffDrive / EdgeTimeOptimal; the closed forms here use the same branch predicates as the
+ * computeError bodies and the sub-gradient policy of SURVEY.md Appendix B (0 at ||0||, sign(0) = 0).
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/teb_b200.h"
+
+#define TEB_PI 3.14159265358979323846
+
+namespace tebgpu {
+
+/* Parameters as seen by the kernels: the POD mirror plus values derived once per launch on the host. */
+struct KParams {
+  TebParams p;
+  double w_obst;       /* weight_obstacle * weight_multiplier (optimal_planner.cpp:453)            */
+  double sw_vel_x, sw_vel_th, sw_acc_x, sw_acc_th, sw_kin_nh, sw_kin_2, sw_sp, sw_rot; /* sqrt of chain weights */
+  int32_t inflated;    /* inflation_dist > min_obstacle_dist (optimal_planner.cpp:450)              */
+  int32_t carlike;     /* !(min_turning_radius == 0 || weight_kinematics_turning_radius == 0) (:355) */
+  int32_t has_vel, has_acc, has_kin, has_sp, has_rot, has_time, has_obst, has_dyn, has_via;
+  int32_t pow_exponent; /* obstacle_cost_exponent != 1 && min_obstacle_dist > 0                     */
+};
+
+/* ------------------------------------------------------------------ g2o/stuff/misc.h */
+__device__ __forceinline__ double normalize_theta(double theta) {
+  if (theta >= -TEB_PI && theta < TEB_PI) return theta;
+  double multiplier = floor(theta / (2 * TEB_PI));
+  theta = theta - multiplier * 2 * TEB_PI;
+  if (theta >= TEB_PI) theta -= 2 * TEB_PI;
+  if (theta < -TEB_PI) theta += 2 * TEB_PI;
+  return theta;
+}
+__device__ __forceinline__ double sgn(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
+
+/* ------------------------------------------------------------------ penalties.h:57-117 and slopes :127-189 */
+__device__ __forceinline__ double pen_interval(double var, double a, double eps, double& slope) {
+  if (var < -a + eps) { slope = -1; return (-var - (a - eps)); }
+  if (var <= a - eps) { slope = 0; return 0.; }
+  slope = 1;
+  return (var - (a - eps));
+}
+__device__ __forceinline__ double pen_interval2(double var, double a, double b, double eps, double& slope) {
+  if (var < a + eps) { slope = -1; return (-var + (a + eps)); }
+  if (var <= b - eps) { slope = 0; return 0.; }
+  slope = 1;
+  return (var - (b - eps));
+}
+__device__ __forceinline__ double pen_below(double var, double a, double eps, double& slope) {
+  if (var >= a + eps) { slope = 0; return 0.; }
+  slope = -1;
+  return (-var + (a + eps));
+}
+
+/* ------------------------------------------------------------------ segment quantities shared by EdgeVelocity /
+ * EdgeAcceleration{,Start,Goal} (edge_velocity.h:97-111, edge_acceleration.h:103-145, :316-341, :408-433). */
+struct SegVal { double v, w; };
+
+__device__ __forceinline__ SegVal seg_value(const KParams& kp, double xa, double ya, double tha, double ca, double sa,
+                                            double xb, double yb, double thb, double dt) {
+  const double dx = xb - xa, dy = yb - ya;
+  double dist = sqrt(dx * dx + dy * dy);
+  const double ad = normalize_theta(thb - tha);
+  if (kp.p.exact_arc_length && ad != 0) {
+    const double radius = dist / (2 * sin(ad / 2));
+    dist = fabs(ad * radius);
+  }
+  const double u = 100 * (dx * ca + dy * sa);
+  SegVal s;
+  s.v = dist / dt * (u / (1 + fabs(u)));  /* fast_sigmoid misc.h:95 */
+  s.w = ad / dt;
+  return s;
+}
+
+/* value + derivatives: dv[0..5] = d v / d(xa, ya, tha, xb, yb, thb); d v/d dt = -v/dt;
+ * d w / d(tha, thb, dt) = (-1/dt, 1/dt, -w/dt). */
+struct SegDer { double v, w, idt, dv[6]; };
+
+__device__ __forceinline__ SegDer seg_derivs(const KParams& kp, double xa, double ya, double tha, double ca, double sa,
+                                             double xb, double yb, double thb, double dt) {
+  const double dx = xb - xa, dy = yb - ya;
+  const double d2 = dx * dx + dy * dy;
+  const double dist = sqrt(d2);
+  const double ad = normalize_theta(thb - tha);
+  const double idist = dist > 0 ? 1.0 / dist : 0.0;
+  const double ux = dx * idist, uy = dy * idist;
+  double L = dist, gfac = 1.0, dLth = 0.0;
+  if (kp.p.exact_arc_length && ad != 0) {
+    const double h = ad / 2, sh = sin(h);
+    const double q = ad / (2 * sh);
+    gfac = fabs(q);
+    dLth = dist * sgn(q) * (2 * sh - ad * cos(h)) / (4 * sh * sh);
+    L = fabs(ad * (dist / (2 * sh)));
+  }
+  const double proj = dx * ca + dy * sa;
+  const double u = 100 * proj;
+  const double den = 1 + fabs(u);
+  const double sig = u / den;
+  const double dsig100 = 100.0 / (den * den);
+  const double idt = 1.0 / dt;
+  SegDer s;
+  s.idt = idt;
+  s.v = L / dt * sig;
+  s.w = ad / dt;
+  const double a = gfac * sig * idt;      /* coefficient of d dist */
+  const double bq = L * dsig100 * idt;    /* coefficient of d proj */
+  s.dv[0] = -a * ux - bq * ca;
+  s.dv[1] = -a * uy - bq * sa;
+  s.dv[2] = -dLth * sig * idt + bq * (-dx * sa + dy * ca);
+  s.dv[3] = a * ux + bq * ca;
+  s.dv[4] = a * uy + bq * sa;
+  s.dv[5] = dLth * sig * idt;
+  return s;
+}
+
+/* ------------------------------------------------------------------ footprint / obstacle distance
+ * Obstacle::getMinimumDistance (obstacles.h:358, :502), getMinimumSpatioTemporalDistance (:382, :526),
+ * BaseRobotFootprintModel::calculateDistance / estimateSpatioTemporalDistance
+ * (robot_footprint_model.h:160-176 Point, :263-278 Circular, :351-372 TwoCircles). (ox, oy) is the obstacle
+ * centroid already advanced to time t for dynamic edges. Returns d, fills grad = d d / d(x, y, theta). */
+__device__ __forceinline__ double footprint_distance(const KParams& kp, double px, double py, double c, double s,
+                                                     double ox, double oy, double orad, double grad[3]) {
+  if (kp.p.footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) {
+    const double fo = kp.p.footprint_front_offset, ro = kp.p.footprint_rear_offset;
+    const double fx = px + fo * c - ox, fy = py + fo * s - oy;
+    const double rx = px - ro * c - ox, ry = py - ro * s - oy;
+    const double nf = sqrt(fx * fx + fy * fy), nr = sqrt(rx * rx + ry * ry);
+    const double df = nf - orad - kp.p.footprint_front_radius;
+    const double dr = nr - orad - kp.p.footprint_rear_radius;
+    if (df < dr) { /* std::min(dist_front, dist_rear) */
+      const double inv = nf > 0 ? 1.0 / nf : 0.0;
+      grad[0] = fx * inv; grad[1] = fy * inv;
+      grad[2] = fo * (-s * grad[0] + c * grad[1]);
+      return df;
+    }
+    const double inv = nr > 0 ? 1.0 / nr : 0.0;
+    grad[0] = rx * inv; grad[1] = ry * inv;
+    grad[2] = -ro * (-s * grad[0] + c * grad[1]);
+    return dr;
+  }
+  const double dx = px - ox, dy = py - oy;
+  const double nrm = sqrt(dx * dx + dy * dy);
+  const double inv = nrm > 0 ? 1.0 / nrm : 0.0;
+  grad[0] = dx * inv; grad[1] = dy * inv; grad[2] = 0;
+  double d = nrm - orad;
+  if (kp.p.footprint_type == TEB_FOOTPRINT_CIRCULAR) d -= kp.p.footprint_radius;
+  return d;
+}
+/* distance only (association, trial chi2) */
+__device__ __forceinline__ double footprint_distance_only(const KParams& kp, double px, double py, double c, double s,
+                                                          double ox, double oy, double orad) {
+  if (kp.p.footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) {
+    const double fo = kp.p.footprint_front_offset, ro = kp.p.footprint_rear_offset;
+    const double fx = px + fo * c - ox, fy = py + fo * s - oy;
+    const double rx = px - ro * c - ox, ry = py - ro * s - oy;
+    const double df = sqrt(fx * fx + fy * fy) - orad - kp.p.footprint_front_radius;
+    const double dr = sqrt(rx * rx + ry * ry) - orad - kp.p.footprint_rear_radius;
+    return df < dr ? df : dr;
+  }
+  const double dx = px - ox, dy = py - oy;
+  double d = sqrt(dx * dx + dy * dy) - orad;
+  if (kp.p.footprint_type == TEB_FOOTPRINT_CIRCULAR) d -= kp.p.footprint_radius;
+  return d;
+}
+
+/* EdgeObstacle / EdgeInflatedObstacle residual pair (edge_obstacle.h:85-106, :207-233): returns weighted
+ * chi2, kappa = sum_k w_k slope_k^2, beta = sum_k w_k e_k slope_k so that H += kappa g g^T, b -= beta g. */
+__device__ __forceinline__ double obstacle_terms(const KParams& kp, double d, double& kappa, double& beta) {
+  double s0;
+  double e0 = pen_below(d, kp.p.min_obstacle_dist, kp.p.penalty_epsilon, s0);
+  if (kp.pow_exponent) {
+    const double base = e0 / kp.p.min_obstacle_dist;
+    const double ex = kp.p.obstacle_cost_exponent;
+    s0 *= (e0 > 0) ? ex * pow(base, ex - 1.0) : 0.0;
+    e0 = kp.p.min_obstacle_dist * pow(base, ex);
+  }
+  double chi = kp.w_obst * e0 * e0;
+  kappa = kp.w_obst * s0 * s0;
+  beta = kp.w_obst * e0 * s0;
+  if (kp.inflated) {
+    double s1;
+    const double e1 = pen_below(d, kp.p.inflation_dist, 0.0, s1);
+    chi += kp.p.weight_inflation * e1 * e1;
+    kappa += kp.p.weight_inflation * s1 * s1;
+    beta += kp.p.weight_inflation * e1 * s1;
+  }
+  return chi;
+}
+/* EdgeDynamicObstacle (edge_dynamic_obstacle.h:93-104); information diag(weight_dynamic_obstacle * 1,
+ * weight_dynamic_obstacle_inflation) (optimal_planner.cpp:652-653, called without multiplier :343). */
+__device__ __forceinline__ double dynamic_terms(const KParams& kp, double d, double& kappa, double& beta) {
+  double s0, s1;
+  const double e0 = pen_below(d, kp.p.min_obstacle_dist, kp.p.penalty_epsilon, s0);
+  const double e1 = pen_below(d, kp.p.dynamic_obstacle_inflation_dist, 0.0, s1);
+  kappa = kp.p.weight_dynamic_obstacle * s0 * s0 + kp.p.weight_dynamic_obstacle_inflation * s1 * s1;
+  beta = kp.p.weight_dynamic_obstacle * e0 * s0 + kp.p.weight_dynamic_obstacle_inflation * e1 * s1;
+  return kp.p.weight_dynamic_obstacle * e0 * e0 + kp.p.weight_dynamic_obstacle_inflation * e1 * e1;
+}
+
+/* ------------------------------------------------------------------ TMA (1-D bulk copy) + mbarrier wrappers */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/* global -> shared bulk copy; bytes multiple of 16, both addresses 16-byte aligned */
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+/* shared -> global bulk copy */
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace tebgpu

@@ -1,0 +1,993 @@
+/*
+ * teb_kernels.cuh — sm_100a kernels of the batched Timed-Elastic-Band optimizer.
+ *
+ *   k_begin          per-call state reset, optimizeTEB guards                (optimal_planner.cpp:185)
+ *   k_auto_resize    TimedElasticBand::autoResize per band                  (timed_elastic_band.cpp:227-286)
+ *   k_build_graph    buildGraph: obstacle association, dynamic-obstacle times, via-point assignment
+ *                                                                            (optimal_planner.cpp:323-366, 444-548, 646-718)
+ *   k_linearize      "kernel A": residuals + analytic Jacobians of every edge family + banded J^T Omega J / b
+ *                    assembly in shared memory, TMA-staged inputs, TMA bulk store of the band tile
+ *                                                                            (g2o buildSystem)
+ *   k_lm_step        "kernel B": one Levenberg-Marquardt iteration per band: banded LDL^T, update, trial chi2,
+ *                    rho / lambda accept-reject loop                          
+ *   k_finalize       computeCurrentCost with the selection scales, outputs   (optimal_planner.cpp:1041-1094)
+ *
+ * Unknown layout ("padded group layout"): scalar index 4*i + c, c = 0,1,2 -> (x,y,theta) of pose i, c = 3 -> dt_i.
+ * It equals the g2o vertex-id order (dt_0, pose_1, dt_1, ...) shifted by 3; the fixed start/goal pose and the
+ * non-existent dt_{n-1} are identity rows. H is SPD banded with half bandwidth 10 (an acceleration edge spans the 11
+ * consecutive scalars 4i .. 4i+10). Storage per band: Hb[4*n_cap][12], row r = H[r][r-k] for k = 0..10, then b[r].
+ */
+#pragma once
+
+#include "teb_device.cuh"
+#include "teb_resize.h"
+
+namespace tebgpu {
+
+constexpr int TP = 64;                 /* poses per kernel-A tile */
+constexpr int KA_THREADS = 4 * TP;     /* one thread per band row of the tile */
+constexpr int JSTRIDE = 65;            /* doubles per anchor Jacobian block (6x7 + 2x11 = 64, +1 pad) */
+constexpr int HROW = 12;               /* doubles per band row: 11 band entries + rhs */
+constexpr int KB_THREADS = 128;
+constexpr int MAX_MW = 4;              /* association bitmask words per pose (<= 256 obstacles) */
+
+struct BandState {
+  double lambda, ni, current_chi, chi2_final;
+  double parts_last[4];  /* chi2 by family at the last evaluated LM trial: obstacles, via, time-optimal, other */
+  double parts_cur[4];   /* same at the current (accepted) state */
+  int32_t active;        /* optimizeGraph still iterating (no Terminate yet) */
+  int32_t failed;        /* optimizeTEB returned false */
+  int32_t status;
+  int32_t lm_iters;
+};
+
+/* Device view of one batch + workspaces. */
+struct DevBatch {
+  int32_t B, n_cap, S, M_cap, V_cap, MW;
+  double* poses;
+  int32_t* n;
+  const int32_t* scene_id;
+  const TebObstacle* obstacles;
+  const int32_t* obst_count;
+  const double* via;
+  const int32_t* via_count;
+  const double* vel_start;
+  const double* vel_goal;
+  const int32_t* prefer_rotdir;
+  double* cost;
+  double* chi2;
+  int32_t* status;
+  int32_t* lm_iters;
+  /* workspaces */
+  double* Hb;                 /* [B][4*n_cap][12] */
+  unsigned long long* assoc;  /* [B][n_cap][MW]   */
+  double* dyn_t;              /* [B][n_cap]       */
+  int32_t* via_idx;           /* [B][V_cap]       */
+  double* chi_parts;          /* [B][chunks][4]   */
+  BandState* state;           /* [B]              */
+  int32_t chunks;
+};
+
+/* ------------------------------------------------------------------ small block utilities */
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+/* deterministic block sum of NV values per thread; result valid in thread 0 (and written to out[]) */
+template <int NV, int NWARPS>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* scratch /* NV*NWARPS */, double* out /* NV, smem */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = warp_sum(v[k]);
+    if (lane == 0) scratch[k * NWARPS + wid] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0;
+      for (int w = 0; w < NWARPS; ++w) s += scratch[k * NWARPS + w];
+      out[k] = s;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ bool row_is_real(int r, int n) {
+  const int i = r >> 2, c = r & 3;
+  return c == 3 ? (i <= n - 2) : (i >= 1 && i <= n - 2);
+}
+
+/* ------------------------------------------------------------------ k_begin */
+__global__ void k_begin(DevBatch db, KParams kp) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= db.B) return;
+  BandState st;
+  st.lambda = 0; st.ni = 2; st.current_chi = 0; st.chi2_final = 0;
+  for (int k = 0; k < 4; ++k) { st.parts_last[k] = 0; st.parts_cur[k] = 0; }
+  st.active = 0; st.failed = 0; st.status = 0; st.lm_iters = 0;
+  if (!kp.p.optimization_activate) { st.failed = 1; st.status |= TEB_STATUS_DISABLED; }
+  db.state[b] = st;
+}
+
+/* ------------------------------------------------------------------ k_auto_resize (thread per band) */
+__global__ void k_auto_resize(DevBatch db, KParams kp) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= db.B) return;
+  if (db.state[b].failed) return;
+  const int fast_mode = !kp.p.include_dynamic_obstacles; /* optimal_planner.cpp:197 */
+  int n = db.n[b];
+  int nn = teb_auto_resize_records(db.poses + (size_t)b * db.n_cap * 4, n, db.n_cap, kp.p.dt_ref, kp.p.dt_hysteresis,
+                                   kp.p.min_samples, kp.p.max_samples, fast_mode);
+  if (nn < 0) { db.state[b].failed = 1; db.state[b].status |= TEB_STATUS_TOO_FEW_POSES; return; }
+  db.n[b] = nn;
+}
+
+/* ------------------------------------------------------------------ k_build_graph (CTA per band) */
+__global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(smem_raw);
+  const int b = blockIdx.x;
+  BandState* st = &db.state[b];
+  const int n = db.n[b];
+  if (threadIdx.x == 0) {
+    /* optimizeGraph guards (optimal_planner.cpp:370-382) */
+    int failed = st->failed;
+    if (!failed && kp.p.max_vel_x < 0.01) { failed = 1; st->status |= TEB_STATUS_DISABLED; }
+    if (!failed && (n < kp.p.min_samples || n < 3)) { failed = 1; st->status |= TEB_STATUS_TOO_FEW_POSES; }
+    st->failed = failed;
+    st->active = !failed;
+    st->lambda = 0;
+    st->ni = 2;
+  }
+  __syncthreads();
+  if (st->failed) return;
+  const int s = db.scene_id[b];
+  const int M = db.obst_count[s];
+  const TebObstacle* go = db.obstacles + (size_t)s * db.M_cap;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) so[m] = go[m];
+  __syncthreads();
+  const double* P = db.poses + (size_t)b * db.n_cap * 4;
+  unsigned long long* assoc = db.assoc + (size_t)b * db.n_cap * db.MW;
+
+  /* AddEdgesObstacles association (optimal_planner.cpp:484-547) */
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned long long mask[MAX_MW] = {0, 0, 0, 0};
+    if (kp.has_obst && i >= 1 && i <= n - 2) {
+      const double px = P[4 * i], py = P[4 * i + 1], th = P[4 * i + 2];
+      double sn, cs;
+      sincos(th, &sn, &cs);
+      double left_min = 1.7976931348623157e308, right_min = 1.7976931348623157e308;
+      int left = -1, right = -1;
+      const double force_d = kp.p.min_obstacle_dist * kp.p.obstacle_association_force_inclusion_factor;
+      const double cut_d = kp.p.min_obstacle_dist * kp.p.obstacle_association_cutoff_factor;
+      for (int m = 0; m < M; ++m) {
+        const TebObstacle ob = so[m];
+        if (kp.p.include_dynamic_obstacles && ob.dynamic) continue;
+        const double dist = footprint_distance_only(kp, px, py, cs, sn, ob.x, ob.y, ob.radius);
+        if (dist < force_d) { mask[m >> 6] |= 1ull << (m & 63); continue; }
+        if (dist > cut_d) continue;
+        const double cx = ob.x - px, cy = ob.y - py;
+        if (cs * cy - cx * sn > 0) {
+          if (dist < left_min) { left_min = dist; left = m; }
+        } else {
+          if (dist < right_min) { right_min = dist; right = m; }
+        }
+      }
+      if (left >= 0) mask[left >> 6] |= 1ull << (left & 63);
+      if (right >= 0) mask[right >> 6] |= 1ull << (right & 63);
+    }
+    for (int w = 0; w < db.MW; ++w) assoc[(size_t)i * db.MW + w] = mask[w];
+  }
+  /* EdgeDynamicObstacle times: t_1 = dt_0, t_{i+1} = t_i + dt_i, frozen at build (optimal_planner.cpp:662-670);
+   * sequential like the reference so the sums are bitwise identical. */
+  if (kp.has_dyn && threadIdx.x == 32) {
+    double* T = db.dyn_t + (size_t)b * db.n_cap;
+    double time = P[3];
+    for (int i = 1; i < n - 1; ++i) { T[i] = time; time += P[4 * i + 3]; }
+  }
+  /* AddEdgesViaPoints (optimal_planner.cpp:675-718), findClosestTrajectoryPose (timed_elastic_band.cpp:455-478) */
+  if (kp.has_via && db.V_cap > 0) {
+    const int V = db.via_count[b];
+    const double* via = db.via + (size_t)b * db.V_cap * 2;
+    int32_t* vidx = db.via_idx + (size_t)b * db.V_cap;
+    if (!kp.p.via_points_ordered) {
+      for (int v = threadIdx.x; v < db.V_cap; v += blockDim.x) {
+        int index = -1;
+        if (v < V && n >= 3) {
+          double best = 1.7976931348623157e308;
+          for (int i = 0; i < n; ++i) {
+            const double dx = via[2 * v] - P[4 * i], dy = via[2 * v + 1] - P[4 * i + 1];
+            const double d2 = dx * dx + dy * dy;
+            if (d2 < best) { best = d2; index = i; }
+          }
+          if (index > n - 2) index = n - 2;
+          if (index < 1) index = -1; /* skipped: too close to / behind the robot */
+        }
+        vidx[v] = index;
+      }
+    } else if (threadIdx.x == 64) {
+      int start_pose_idx = 0;
+      for (int v = 0; v < db.V_cap; ++v) {
+        int index = -1;
+        if (v < V && n >= 3) {
+          if (start_pose_idx >= 0 && start_pose_idx < n) {
+            double best = 1.7976931348623157e308;
+            for (int i = start_pose_idx; i < n; ++i) {
+              const double dx = via[2 * v] - P[4 * i], dy = via[2 * v + 1] - P[4 * i + 1];
+              const double d2 = dx * dx + dy * dy;
+              if (d2 < best) { best = d2; index = i; }
+            }
+          }
+          start_pose_idx = index + 2;
+          if (index > n - 2) index = n - 2;
+          if (index < 1) index = 1;
+        }
+        vidx[v] = index;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ unary terms of one pose (obstacles, dynamic
+ * obstacles, via-points): accumulates U = sum kappa g g^T (xx,xy,yy,xt,yt,tt), ub = -sum beta g, chi2 by family */
+__device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& db, int b, int i, int n, double px,
+                                            double py, double cs, double sn, const TebObstacle* so, int M,
+                                            bool want_grad, double U[6], double ub[3], double& chi_obst,
+                                            double& chi_via) {
+  if (i < 1 || i > n - 2) return;
+  if (kp.has_obst) {
+    const unsigned long long* assoc = db.assoc + ((size_t)b * db.n_cap + i) * db.MW;
+    for (int w = 0; w < db.MW; ++w) {
+      unsigned long long mask = assoc[w];
+      while (mask) {
+        const int m = (w << 6) + __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const TebObstacle ob = so[m];
+        double g[3], kappa, beta;
+        const double d = footprint_distance(kp, px, py, cs, sn, ob.x, ob.y, ob.radius, g);
+        chi_obst += obstacle_terms(kp, d, kappa, beta);
+        if (want_grad && (kappa != 0 || beta != 0)) {
+          U[0] += kappa * g[0] * g[0]; U[1] += kappa * g[0] * g[1]; U[2] += kappa * g[1] * g[1];
+          U[3] += kappa * g[0] * g[2]; U[4] += kappa * g[1] * g[2]; U[5] += kappa * g[2] * g[2];
+          ub[0] -= beta * g[0]; ub[1] -= beta * g[1]; ub[2] -= beta * g[2];
+        }
+      }
+    }
+  }
+  if (kp.has_dyn) {
+    const double t = db.dyn_t[(size_t)b * db.n_cap + i];
+    for (int m = 0; m < M; ++m) {
+      const TebObstacle ob = so[m];
+      if (!ob.dynamic) continue;
+      double g[3], kappa, beta;
+      const double d = footprint_distance(kp, px, py, cs, sn, ob.x + t * ob.vx, ob.y + t * ob.vy, ob.radius, g);
+      chi_obst += dynamic_terms(kp, d, kappa, beta);
+      if (want_grad && (kappa != 0 || beta != 0)) {
+        U[0] += kappa * g[0] * g[0]; U[1] += kappa * g[0] * g[1]; U[2] += kappa * g[1] * g[1];
+        U[3] += kappa * g[0] * g[2]; U[4] += kappa * g[1] * g[2]; U[5] += kappa * g[2] * g[2];
+        ub[0] -= beta * g[0]; ub[1] -= beta * g[1]; ub[2] -= beta * g[2];
+      }
+    }
+  }
+  if (kp.has_via && db.V_cap > 0) {
+    const int32_t* vidx = db.via_idx + (size_t)b * db.V_cap;
+    const double* via = db.via + (size_t)b * db.V_cap * 2;
+    const double wv = kp.p.weight_viapoint;
+    for (int v = 0; v < db.V_cap; ++v) {
+      if (vidx[v] != i) continue;
+      const double dx = px - via[2 * v], dy = py - via[2 * v + 1];
+      const double e = sqrt(dx * dx + dy * dy); /* EdgeViaPoint edge_via_point.h:86 */
+      chi_via += wv * e * e;
+      if (want_grad && e > 0) {
+        const double gx = dx / e, gy = dy / e;
+        U[0] += wv * gx * gx; U[1] += wv * gx * gy; U[2] += wv * gy * gy;
+        ub[0] -= wv * e * gx; ub[1] -= wv * e * gy;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ k_linearize ("kernel A") */
+struct KASmem {
+  /* sizes in doubles */
+  static constexpr int POSES = (TP + 4) * 4;
+  static constexpr int SC = (TP + 4) * 2;
+  static constexpr int SEG = (TP + 3) * 9;
+  static constexpr int JB = (TP + 2) * JSTRIDE;
+  static constexpr int EH = (TP + 2) * 8;
+  static constexpr int START = 2 * 7 + 2;
+  static constexpr int UN = TP * 9;
+  static constexpr int RED = 4 * (KA_THREADS / 32) + 4;
+  static constexpr int STAGE = KA_THREADS * HROW; /* aliases JB..: needs JB+EH+START+UN >= STAGE? no: separate */
+};
+
+__host__ __device__ inline size_t ka_smem_bytes(int M_cap) {
+  size_t d = KASmem::POSES + KASmem::SC + KASmem::SEG + KASmem::EH + KASmem::START + KASmem::UN + KASmem::RED + 2;
+  size_t jb = KASmem::JB > KASmem::STAGE ? KASmem::JB : KASmem::STAGE;
+  return (d + jb) * sizeof(double) + (size_t)M_cap * sizeof(TebObstacle) + 64;
+}
+
+__global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams kp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int b = blockIdx.y;
+  const BandState* st = &db.state[b];
+  if (!st->active) return;
+  const int n = db.n[b];
+  const int p0 = blockIdx.x * TP;
+  if (p0 >= n) return;
+  const int tid = threadIdx.x;
+
+  double* sP = reinterpret_cast<double*>(smem_raw);             /* poses tile, slot j <-> pose p0-2+j */
+  double* sJ = sP + KASmem::POSES;                              /* Jacobian blocks, later the output stage */
+  constexpr int JBMAX = KASmem::JB > KASmem::STAGE ? KASmem::JB : KASmem::STAGE;
+  double* sSC = sJ + JBMAX;
+  double* sSeg = sSC + KASmem::SC;
+  double* sE = sSeg + KASmem::SEG;
+  double* sStart = sE + KASmem::EH;
+  double* sU = sStart + KASmem::START;
+  double* sRed = sU + KASmem::UN;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sRed + KASmem::RED);
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(
+      (reinterpret_cast<uintptr_t>(bar) + 16 + 15) & ~static_cast<uintptr_t>(15)); /* TMA destination: 16-byte aligned */
+
+  const int s = db.scene_id[b];
+  const int M = db.obst_count[s];
+  const int lo = max(p0 - 2, 0), hi = min(p0 + TP + 2, n); /* poses staged */
+  const double* gP = db.poses + (size_t)b * db.n_cap * 4;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytesP = (uint32_t)(hi - lo) * 32u;
+    const uint32_t bytesO = (uint32_t)M * (uint32_t)sizeof(TebObstacle);
+    mbar_expect_tx(bar, bytesP + bytesO);
+    tma_load_1d(sP + (size_t)(lo - (p0 - 2)) * 4, gP + (size_t)lo * 4, bytesP, bar);
+    if (bytesO) tma_load_1d(so, db.obstacles + (size_t)s * db.M_cap, bytesO, bar);
+  }
+  /* zero the Jacobian blocks while the copies are in flight */
+  for (int k = tid; k < KASmem::JB; k += KA_THREADS) sJ[k] = 0.0;
+  for (int k = tid; k < KASmem::EH + KASmem::START; k += KA_THREADS) sE[k] = 0.0;
+  mbar_wait(bar, 0);
+
+  /* stage 1: sin/cos per staged pose */
+  if (tid < TP + 4) {
+    const int i = p0 - 2 + tid;
+    if (i >= lo && i < hi) {
+      double sn, cs;
+      sincos(sP[4 * tid + 2], &sn, &cs);
+      sSC[2 * tid] = cs;
+      sSC[2 * tid + 1] = sn;
+    }
+  }
+  __syncthreads();
+
+  /* stage 2: segment bundles, slot j <-> segment (p0-2+j) between poses a and a+1 */
+  if (tid < TP + 3) {
+    const int a = p0 - 2 + tid;
+    if (a >= 0 && a + 1 < hi && a <= n - 2) {
+      const double* pa = sP + 4 * tid;
+      const double* pb = pa + 4;
+      SegDer sd = seg_derivs(kp, pa[0], pa[1], pa[2], sSC[2 * tid], sSC[2 * tid + 1], pb[0], pb[1], pb[2], pa[3]);
+      double* q = sSeg + 9 * tid;
+      q[0] = sd.v; q[1] = sd.w; q[2] = sd.idt;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) q[3 + k] = sd.dv[k];
+    }
+  }
+  __syncthreads();
+
+  double chi[4] = {0, 0, 0, 0}; /* obstacles, via, time-optimal, other */
+
+  /* stage 3a: chain edges anchored at a (EdgeVelocity, EdgeKinematics*, EdgeShortestPath, EdgePreferRotDir,
+   * EdgeAcceleration / Start / Goal) -> sqrt(weight)-scaled Jacobian rows over the columns 4a .. 4a+10 */
+  if (tid < TP + 2) {
+    const int a = p0 - 2 + tid;
+    if (a >= 0 && a <= n - 2) {
+      double* J = sJ + (size_t)tid * JSTRIDE; /* rows 0..5: 7 columns, rows 6,7: 11 columns at offset 42 */
+      double* eh = sE + 8 * tid;
+      const double* pa = sP + 4 * tid;
+      const double* pb = pa + 4;
+      const double ca = sSC[2 * tid], sa = sSC[2 * tid + 1], cb = sSC[2 * tid + 2], sb = sSC[2 * tid + 3];
+      const double* q1 = sSeg + 9 * tid;
+      const double v1 = q1[0], w1 = q1[1], idt1 = q1[2];
+      const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
+      const bool fa = (a == 0), fb = (a + 1 == n - 1);
+      double csum = 0;
+      if (kp.has_vel) { /* EdgeVelocity edge_velocity.h:113-114 */
+        double s0, s1;
+        const double e0 = pen_interval2(v1, -kp.p.max_vel_x_backwards, kp.p.max_vel_x, kp.p.penalty_epsilon, s0);
+        const double e1 = pen_interval(w1, kp.p.max_vel_theta, kp.p.penalty_epsilon, s1);
+        const double k0 = kp.sw_vel_x * s0, k1 = kp.sw_vel_th * s1;
+        J[0] = k0 * q1[3]; J[1] = k0 * q1[4]; J[2] = k0 * q1[5]; J[3] = -k0 * v1 * idt1;
+        J[4] = k0 * q1[6]; J[5] = k0 * q1[7]; J[6] = k0 * q1[8];
+        J[7 + 2] = -k1 * idt1; J[7 + 3] = -k1 * w1 * idt1; J[7 + 6] = k1 * idt1;
+        eh[0] = kp.sw_vel_x * e0; eh[1] = kp.sw_vel_th * e1;
+      }
+      if (kp.has_kin) { /* EdgeKinematicsDiffDrive / Carlike edge_kinematics.h:94-101, :118-148, :203-215 */
+        const double A = (ca + cb) * dy - (sa + sb) * dx;
+        const double sA = sgn(A) * kp.sw_kin_nh;
+        double* R = J + 14;
+        R[0] = (sa + sb) * sA; R[1] = -(ca + cb) * sA; R[2] = (-sa * dy - ca * dx) * sA;
+        R[4] = -(sa + sb) * sA; R[5] = (ca + cb) * sA; R[6] = (-sb * dy - cb * dx) * sA;
+        eh[2] = kp.sw_kin_nh * fabs(A);
+        double* R2 = J + 21;
+        if (!kp.carlike) {
+          double dd;
+          const double e1 = pen_below(dx * ca + dy * sa, 0, 0, dd);
+          dd *= kp.sw_kin_2;
+          R2[0] = -ca * dd; R2[1] = -sa * dd; R2[2] = (-sa * dx + ca * dy) * dd;
+          R2[4] = ca * dd; R2[5] = sa * dd;
+          eh[3] = kp.sw_kin_2 * e1;
+        } else {
+          const double ad = normalize_theta(pb[2] - pa[2]);
+          if (ad != 0) {
+            const double nrm = sqrt(dx * dx + dy * dy);
+            const double inr = nrm > 0 ? 1.0 / nrm : 0.0;
+            const double ux = dx * inr, uy = dy * inr;
+            double r, dr_dn, dr_dad;
+            if (kp.p.exact_arc_length) {
+              const double h = ad / 2, sh = sin(h);
+              const double qq = nrm / (2 * sh);
+              r = fabs(qq);
+              dr_dn = sgn(qq) / (2 * sh);
+              dr_dad = sgn(qq) * (-nrm * cos(h) / (4 * sh * sh));
+            } else {
+              r = nrm / fabs(ad);
+              dr_dn = 1 / fabs(ad);
+              dr_dad = -nrm * sgn(ad) / (ad * ad);
+            }
+            double s1;
+            const double e1 = pen_below(r, kp.p.min_turning_radius, 0.0, s1);
+            s1 *= kp.sw_kin_2;
+            R2[0] = -s1 * dr_dn * ux; R2[1] = -s1 * dr_dn * uy; R2[2] = -s1 * dr_dad;
+            R2[4] = s1 * dr_dn * ux; R2[5] = s1 * dr_dn * uy; R2[6] = s1 * dr_dad;
+            eh[3] = kp.sw_kin_2 * e1;
+          }
+        }
+      }
+      if (kp.has_sp) { /* EdgeShortestPath edge_shortest_path.h:78 */
+        const double nrm = sqrt(dx * dx + dy * dy);
+        const double inr = nrm > 0 ? 1.0 / nrm : 0.0;
+        double* R = J + 28;
+        R[0] = -kp.sw_sp * dx * inr; R[1] = -kp.sw_sp * dy * inr;
+        R[4] = kp.sw_sp * dx * inr; R[5] = kp.sw_sp * dy * inr;
+        eh[4] = kp.sw_sp * nrm;
+      }
+      if (kp.has_rot && a < 3) { /* EdgePreferRotDir edge_prefer_rotdir.h:85, first three pairs optimal_planner.cpp:983 */
+        const int rd = db.prefer_rotdir ? db.prefer_rotdir[b] : 0;
+        if (rd == TEB_ROTDIR_LEFT || rd == TEB_ROTDIR_RIGHT) {
+          const double meas = (rd == TEB_ROTDIR_LEFT) ? 1.0 : -1.0;
+          double s0;
+          const double e0 = pen_below(meas * normalize_theta(pb[2] - pa[2]), 0, 0, s0);
+          double* R = J + 35;
+          R[2] = -kp.sw_rot * s0 * meas;
+          R[6] = kp.sw_rot * s0 * meas;
+          eh[5] = kp.sw_rot * e0;
+        }
+      }
+      if (kp.has_acc) {
+        double* R0 = J + 42;
+        double* R1 = J + 53;
+        if (a <= n - 3) { /* EdgeAcceleration edge_acceleration.h:134-145 */
+          const double* q2 = q1 + 9;
+          const double v2 = q2[0], w2 = q2[1], idt2 = q2[2];
+          const double dt1 = pa[3], dt2 = pb[3];
+          const double iT = 1.0 / (dt1 + dt2);
+          const double acc = (v2 - v1) * 2 * iT;
+          const double accr = (w2 - w1) * 2 * iT;
+          double s0, s1;
+          const double e0 = pen_interval(acc, kp.p.acc_lim_x, kp.p.penalty_epsilon, s0);
+          const double e1 = pen_interval(accr, kp.p.acc_lim_theta, kp.p.penalty_epsilon, s1);
+          const double k0 = kp.sw_acc_x * s0 * iT, k1 = kp.sw_acc_th * s1 * iT;
+          R0[0] = -2 * k0 * q1[3]; R0[1] = -2 * k0 * q1[4]; R0[2] = -2 * k0 * q1[5];
+          R0[3] = k0 * (2 * v1 * idt1 - acc);
+          R0[4] = 2 * k0 * (q2[3] - q1[6]); R0[5] = 2 * k0 * (q2[4] - q1[7]); R0[6] = 2 * k0 * (q2[5] - q1[8]);
+          R0[7] = k0 * (-2 * v2 * idt2 - acc);
+          R0[8] = 2 * k0 * q2[6]; R0[9] = 2 * k0 * q2[7]; R0[10] = 2 * k0 * q2[8];
+          R1[2] = 2 * k1 * idt1;
+          R1[3] = k1 * (2 * w1 * idt1 - accr);
+          R1[6] = 2 * k1 * (-idt2 - idt1);
+          R1[7] = k1 * (-2 * w2 * idt2 - accr);
+          R1[10] = 2 * k1 * idt2;
+          eh[6] = kp.sw_acc_x * e0; eh[7] = kp.sw_acc_th * e1;
+          if (a + 2 == n - 1) { R0[8] = R0[9] = R0[10] = 0; R1[10] = 0; }
+        } else { /* a == n-2: EdgeAccelerationGoal edge_acceleration.h:420-433 */
+          const double* vg = db.vel_goal + 4 * (size_t)b;
+          if (vg[3] != 0) {
+            const double acc = (vg[0] - v1) * idt1;
+            const double accr = (vg[2] - w1) * idt1;
+            double s0, s1;
+            const double e0 = pen_interval(acc, kp.p.acc_lim_x, kp.p.penalty_epsilon, s0);
+            const double e1 = pen_interval(accr, kp.p.acc_lim_theta, kp.p.penalty_epsilon, s1);
+            const double k0 = kp.sw_acc_x * s0 * idt1, k1 = kp.sw_acc_th * s1 * idt1;
+            R0[0] = -k0 * q1[3]; R0[1] = -k0 * q1[4]; R0[2] = -k0 * q1[5];
+            R0[3] = k0 * (v1 * idt1 - acc);
+            R0[4] = -k0 * q1[6]; R0[5] = -k0 * q1[7]; R0[6] = -k0 * q1[8];
+            R1[2] = k1 * idt1; R1[3] = k1 * (w1 * idt1 - accr); R1[6] = -k1 * idt1;
+            eh[6] = kp.sw_acc_x * e0; eh[7] = kp.sw_acc_th * e1;
+          }
+        }
+        if (a == 0) { /* EdgeAccelerationStart edge_acceleration.h:328-341 */
+          const double* vs = db.vel_start + 4 * (size_t)b;
+          if (vs[3] != 0) {
+            const double acc = (v1 - vs[0]) * idt1;
+            const double accr = (w1 - vs[2]) * idt1;
+            double s0, s1;
+            const double e0 = pen_interval(acc, kp.p.acc_lim_x, kp.p.penalty_epsilon, s0);
+            const double e1 = pen_interval(accr, kp.p.acc_lim_theta, kp.p.penalty_epsilon, s1);
+            const double k0 = kp.sw_acc_x * s0 * idt1, k1 = kp.sw_acc_th * s1 * idt1;
+            double* S0 = sStart;
+            double* S1 = sStart + 7;
+            S0[0] = 0; S0[1] = 0; S0[2] = 0; /* pose 0 is fixed */
+            S0[3] = k0 * (-v1 * idt1 - acc);
+            S0[4] = k0 * q1[6]; S0[5] = k0 * q1[7]; S0[6] = k0 * q1[8];
+            S1[0] = S1[1] = S1[2] = S1[4] = S1[5] = 0;
+            S1[3] = k1 * (-w1 * idt1 - accr);
+            S1[6] = k1 * idt1;
+            if (fb) { S0[4] = S0[5] = S0[6] = 0; S1[6] = 0; }
+            sStart[14] = kp.sw_acc_x * e0; sStart[15] = kp.sw_acc_th * e1;
+            if (a >= p0) csum += sStart[14] * sStart[14] + sStart[15] * sStart[15];
+          }
+        }
+      }
+      /* columns of fixed poses carry no unknowns (g2o skips fixed vertices) */
+      if (fa) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { J[7 * k] = 0; J[7 * k + 1] = 0; J[7 * k + 2] = 0; }
+        J[42] = J[43] = J[44] = 0; J[53] = J[54] = J[55] = 0;
+      }
+      if (fb) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { J[7 * k + 4] = 0; J[7 * k + 5] = 0; J[7 * k + 6] = 0; }
+        J[46] = J[47] = J[48] = 0; J[57] = J[58] = J[59] = 0;
+      }
+      if (a >= p0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) csum += eh[k] * eh[k];
+        chi[3] += csum;
+      }
+    }
+  }
+
+  /* stage 3b: unary terms of pose i (threads TP+2 .. 2TP+1 so that they overlap with the chain warps) */
+  {
+    const int il = tid - (KA_THREADS - TP); /* last TP threads */
+    if (il >= 0) {
+      const int i = p0 + il;
+      double U[6] = {0, 0, 0, 0, 0, 0}, ub[3] = {0, 0, 0};
+      if (i < n) {
+        const int j = il + 2;
+        unary_terms(kp, db, b, i, n, sP[4 * j], sP[4 * j + 1], sSC[2 * j], sSC[2 * j + 1], so, M, true, U, ub, chi[0],
+                    chi[1]);
+        if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
+          const double dt = sP[4 * j + 3];
+          chi[2] += kp.p.weight_optimaltime * dt * dt;
+        }
+      }
+      double* u = sU + 9 * il;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) u[k] = U[k];
+      u[6] = ub[0]; u[7] = ub[1]; u[8] = ub[2];
+    }
+  }
+  __syncthreads();
+
+  /* stage 4: one thread per band row r = 4i + c gathers J^T J over the (<= 3) anchors that touch it */
+  double acc[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) acc[k] = 0;
+  double brow = 0;
+  {
+    const int il = tid >> 2, c = tid & 3;
+    const int i = p0 + il;
+    const int r = 4 * i + c;
+    if (i < n) {
+      if (!row_is_real(r, n)) {
+        acc[0] = 1.0;
+      } else {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int a = i - d;
+          const int l = c + 4 * d;
+          if (a < 0 || a > n - 2 || l > 10) continue;
+          const int slot = a - (p0 - 2);
+          const double* J = sJ + (size_t)slot * JSTRIDE;
+          const double* eh = sE + 8 * slot;
+          if (l <= 6) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              const double jl = J[7 * k + l];
+              if (jl != 0) {
+                brow -= jl * eh[k];
+#pragma unroll
+                for (int o = 0; o <= 6; ++o)
+                  if (o <= l) acc[o] += jl * J[7 * k + l - o];
+              }
+            }
+            if (a == 0) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const double jl = sStart[7 * k + l];
+                if (jl != 0) {
+                  brow -= jl * sStart[14 + k];
+#pragma unroll
+                  for (int o = 0; o <= 6; ++o)
+                    if (o <= l) acc[o] += jl * sStart[7 * k + l - o];
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const double* R = J + 42 + 11 * k;
+            const double jl = R[l];
+            if (jl != 0) {
+              brow -= jl * eh[6 + k];
+#pragma unroll
+              for (int o = 0; o <= 10; ++o)
+                if (o <= l) acc[o] += jl * R[l - o];
+            }
+          }
+        }
+        if (c < 3) {
+          const double* u = sU + 9 * il;
+          if (c == 0) { acc[0] += u[0]; brow += u[6]; }
+          else if (c == 1) { acc[0] += u[2]; acc[1] += u[1]; brow += u[7]; }
+          else { acc[0] += u[5]; acc[1] += u[4]; acc[2] += u[3]; brow += u[8]; }
+        } else if (kp.has_time) {
+          acc[0] += kp.p.weight_optimaltime;
+          brow -= kp.p.weight_optimaltime * sP[4 * (il + 2) + 3];
+        }
+      }
+    }
+  }
+  __syncthreads(); /* every thread is done reading sJ: reuse it as the output stage */
+  {
+    double* o = sJ + (size_t)tid * HROW;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) o[k] = acc[k];
+    o[11] = brow;
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    const int rows = 4 * (min(p0 + TP, n) - p0);
+    double* gH = db.Hb + ((size_t)b * 4 * db.n_cap + (size_t)4 * p0) * HROW;
+    tma_store_1d(gH, sJ, (uint32_t)rows * HROW * 8u);
+    tma_store_commit_wait();
+  }
+  /* chi2 partials of this tile */
+  block_sum<4, KA_THREADS / 32>(chi, sRed, sRed + 4 * (KA_THREADS / 32));
+  if (tid == 0) {
+    double* cp = db.chi_parts + ((size_t)b * db.chunks + blockIdx.x) * 4;
+    const double* r = sRed + 4 * (KA_THREADS / 32);
+    cp[0] = r[0]; cp[1] = r[1]; cp[2] = r[2]; cp[3] = r[3];
+  }
+}
+
+/* ------------------------------------------------------------------ trial chi2 (residuals only) on a band held in
+ * shared memory: sT[n][4]; block-wide, result in out[4] (shared) after the call */
+template <int NTHREADS>
+__device__ __forceinline__ void eval_chi2_parts(const KParams& kp, const DevBatch& db, int b, int n, const double* sT,
+                                                const TebObstacle* so, int M, double* scratch, double* out) {
+  double chi[4] = {0, 0, 0, 0};
+  const double* vs = db.vel_start + 4 * (size_t)b;
+  const double* vg = db.vel_goal + 4 * (size_t)b;
+  for (int i = threadIdx.x; i < n; i += NTHREADS) {
+    const double* pa = sT + 4 * i;
+    double sa, ca;
+    sincos(pa[2], &sa, &ca);
+    if (i <= n - 2) {
+      const double* pb = pa + 4;
+      double sb, cb;
+      sincos(pb[2], &sb, &cb);
+      const SegVal s1 = seg_value(kp, pa[0], pa[1], pa[2], ca, sa, pb[0], pb[1], pb[2], pa[3]);
+      const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
+      double sl, csum = 0;
+      if (kp.has_vel) {
+        const double e0 = kp.sw_vel_x * pen_interval2(s1.v, -kp.p.max_vel_x_backwards, kp.p.max_vel_x, kp.p.penalty_epsilon, sl);
+        const double e1 = kp.sw_vel_th * pen_interval(s1.w, kp.p.max_vel_theta, kp.p.penalty_epsilon, sl);
+        csum += e0 * e0 + e1 * e1;
+      }
+      if (kp.has_kin) {
+        const double e0 = kp.sw_kin_nh * fabs((ca + cb) * dy - (sa + sb) * dx);
+        double e1 = 0;
+        if (!kp.carlike) {
+          e1 = pen_below(dx * ca + dy * sa, 0, 0, sl);
+        } else {
+          const double ad = normalize_theta(pb[2] - pa[2]);
+          if (ad != 0) {
+            const double nrm = sqrt(dx * dx + dy * dy);
+            const double r = kp.p.exact_arc_length ? fabs(nrm / (2 * sin(ad / 2))) : nrm / fabs(ad);
+            e1 = pen_below(r, kp.p.min_turning_radius, 0.0, sl);
+          }
+        }
+        e1 *= kp.sw_kin_2;
+        csum += e0 * e0 + e1 * e1;
+      }
+      if (kp.has_sp) {
+        const double e = kp.sw_sp * sqrt(dx * dx + dy * dy);
+        csum += e * e;
+      }
+      if (kp.has_rot && i < 3) {
+        const int rd = db.prefer_rotdir ? db.prefer_rotdir[b] : 0;
+        if (rd == TEB_ROTDIR_LEFT || rd == TEB_ROTDIR_RIGHT) {
+          const double meas = (rd == TEB_ROTDIR_LEFT) ? 1.0 : -1.0;
+          const double e = kp.sw_rot * pen_below(meas * normalize_theta(pb[2] - pa[2]), 0, 0, sl);
+          csum += e * e;
+        }
+      }
+      if (kp.has_acc) {
+        const double idt1 = 1.0 / pa[3];
+        if (i <= n - 3) {
+          const double* pc = pb + 4;
+          const SegVal s2 = seg_value(kp, pb[0], pb[1], pb[2], cb, sb, pc[0], pc[1], pc[2], pb[3]);
+          const double iT = 1.0 / (pa[3] + pb[3]);
+          const double e0 = kp.sw_acc_x * pen_interval((s2.v - s1.v) * 2 * iT, kp.p.acc_lim_x, kp.p.penalty_epsilon, sl);
+          const double e1 = kp.sw_acc_th * pen_interval((s2.w - s1.w) * 2 * iT, kp.p.acc_lim_theta, kp.p.penalty_epsilon, sl);
+          csum += e0 * e0 + e1 * e1;
+        } else if (vg[3] != 0) {
+          const double e0 = kp.sw_acc_x * pen_interval((vg[0] - s1.v) * idt1, kp.p.acc_lim_x, kp.p.penalty_epsilon, sl);
+          const double e1 = kp.sw_acc_th * pen_interval((vg[2] - s1.w) * idt1, kp.p.acc_lim_theta, kp.p.penalty_epsilon, sl);
+          csum += e0 * e0 + e1 * e1;
+        }
+        if (i == 0 && vs[3] != 0) {
+          const double e0 = kp.sw_acc_x * pen_interval((s1.v - vs[0]) * idt1, kp.p.acc_lim_x, kp.p.penalty_epsilon, sl);
+          const double e1 = kp.sw_acc_th * pen_interval((s1.w - vs[2]) * idt1, kp.p.acc_lim_theta, kp.p.penalty_epsilon, sl);
+          csum += e0 * e0 + e1 * e1;
+        }
+      }
+      chi[3] += csum;
+      if (kp.has_time) chi[2] += kp.p.weight_optimaltime * pa[3] * pa[3];
+    }
+    double U[6], ub[3];
+    unary_terms(kp, db, b, i, n, pa[0], pa[1], ca, sa, so, M, false, U, ub, chi[0], chi[1]);
+  }
+  block_sum<4, NTHREADS / 32>(chi, scratch, out);
+}
+
+/* ------------------------------------------------------------------ banded LDL^T + substitutions, one warp, in
+ * shared memory. Hs[N][12]: on entry band + rhs, on exit L (unit lower, offsets 1..10), 1/d (offset 0) and the
+ * solution (offset 11). Returns false on a non-positive / non-finite pivot (LinearSolverCSparse would fail). */
+__device__ __forceinline__ bool warp_band_solve(double* Hs, int N, int n, double lambda) {
+  const int lane = threadIdx.x & 31;
+  /* trailing-window entries handled by this lane: e in {lane, lane+32, lane+64}; e < 55 -> (u,q), 1<=q<=u<=10;
+   * 55 <= e < 65 -> rhs of row j+u, u = e-54 */
+  int eu[3], eq[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int e = lane + 32 * t;
+    if (e < 55) {
+      int u = 1;
+      while ((u * (u + 1)) / 2 <= e) ++u;
+      eu[t] = u;
+      eq[t] = e - (u * (u - 1)) / 2 + 1;
+    } else if (e < 65) {
+      eu[t] = e - 54;
+      eq[t] = 0; /* rhs */
+    } else {
+      eu[t] = 0;
+      eq[t] = 0;
+    }
+  }
+  bool ok = true;
+  for (int j = 0; j < N; ++j) {
+    const double d = Hs[j * HROW] + (row_is_real(j, n) ? lambda : 0.0);
+    if (!(d > 0) || !isfinite(d)) { ok = false; break; }
+    const double inv = 1.0 / d;
+    const double yj = Hs[j * HROW + 11];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int u = eu[t];
+      if (u == 0 || j + u >= N) continue;
+      const double cu = Hs[(j + u) * HROW + u];
+      if (eq[t] == 0) {
+        Hs[(j + u) * HROW + 11] -= cu * inv * yj;
+      } else {
+        const int q = eq[t];
+        const double cq = Hs[(j + q) * HROW + q];
+        Hs[(j + u) * HROW + (u - q)] -= cu * inv * cq;
+      }
+    }
+    __syncwarp();
+    if (lane >= 1 && lane <= 10 && j + lane < N) Hs[(j + lane) * HROW + lane] *= inv;
+    if (lane == 0) Hs[j * HROW] = inv;
+    __syncwarp();
+  }
+  if (!ok) return false;
+  /* z = D^-1 y */
+  for (int j = lane; j < N; j += 32) Hs[j * HROW + 11] *= Hs[j * HROW];
+  __syncwarp();
+  /* L^T x = z, column-oriented */
+  for (int j = N - 1; j >= 1; --j) {
+    const double xj = Hs[j * HROW + 11];
+    if (lane >= 1 && lane <= 10 && j - lane >= 0) Hs[(j - lane) * HROW + 11] -= Hs[j * HROW + lane] * xj;
+    __syncwarp();
+  }
+  return true;
+}
+
+/* ------------------------------------------------------------------ k_lm_step ("kernel B"), CTA per band */
+__host__ __device__ inline size_t kb_smem_bytes(int n_cap, int M_cap) {
+  return ((size_t)4 * n_cap * HROW + (size_t)4 * n_cap + 64) * sizeof(double) + (size_t)M_cap * sizeof(TebObstacle) + 64;
+}
+
+__global__ void __launch_bounds__(KB_THREADS) k_lm_step(DevBatch db, KParams kp, int iteration) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  BandState* st = &db.state[b];
+  if (!st->active) return;
+  const int n = db.n[b];
+  const int N = 4 * n;
+  const int tid = threadIdx.x;
+
+  double* Hs = reinterpret_cast<double*>(smem_raw);
+  double* sT = Hs + (size_t)4 * db.n_cap * HROW;   /* trial poses [n][4] */
+  double* sRed = sT + (size_t)4 * db.n_cap;        /* 64 doubles scratch */
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sRed + 56);
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(sRed + 64);
+  __shared__ int s_flag[4];
+
+  const int s = db.scene_id[b];
+  const int M = db.obst_count[s];
+  double* gP = db.poses + (size_t)b * db.n_cap * 4;
+  const double* gH = db.Hb + (size_t)b * 4 * db.n_cap * HROW;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  const uint32_t bytesH = (uint32_t)N * HROW * 8u;
+  if (tid == 0) {
+    const uint32_t bytesO = (uint32_t)M * (uint32_t)sizeof(TebObstacle);
+    mbar_expect_tx(bar, bytesH + bytesO);
+    tma_load_1d(Hs, gH, bytesH, bar);
+    if (bytesO) tma_load_1d(so, db.obstacles + (size_t)s * db.M_cap, bytesO, bar);
+  }
+  /* chi2 at the linearisation point = sum of the kernel-A tile partials (computeActiveErrors, App. A.4) */
+  double cur_parts[4] = {0, 0, 0, 0};
+  {
+    const int chunks_used = (n + TP - 1) / TP;
+    const double* cp = db.chi_parts + (size_t)b * db.chunks * 4;
+    for (int c = 0; c < chunks_used; ++c)
+      for (int k = 0; k < 4; ++k) cur_parts[k] += cp[4 * c + k];
+  }
+  double currentChi = cur_parts[0] + cur_parts[1] + cur_parts[2] + cur_parts[3];
+  mbar_wait(bar, parity);
+  parity ^= 1;
+
+  double lambda = st->lambda, ni = st->ni;
+  if (iteration == 0) { /* computeLambdaInit: tau * max diagonal (App. A.4) */
+    double mx = 0;
+    for (int r = tid; r < N; r += KB_THREADS)
+      if (row_is_real(r, n)) mx = fmax(mx, fabs(Hs[r * HROW]));
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) sRed[tid >> 5] = mx;
+    __syncthreads();
+    mx = 0;
+    for (int w = 0; w < KB_THREADS / 32; ++w) mx = fmax(mx, sRed[w]);
+    __syncthreads();
+    lambda = 1e-5 * mx;
+    ni = 2;
+  }
+
+  double rho = 0;
+  int qmax = 0;
+  int status_add = 0;
+  double last_parts[4] = {cur_parts[0], cur_parts[1], cur_parts[2], cur_parts[3]};
+  bool accepted_any = false;
+  while (true) {
+    /* (H + lambda I) dx = b */
+    if (tid < 32) {
+      const bool ok = warp_band_solve(Hs, N, n, lambda);
+      if (tid == 0) s_flag[0] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    const bool ok2 = s_flag[0] != 0;
+    /* trial state x [+] dx (VertexPose::oplusImpl / VertexTimeDiff::oplusImpl) and computeScale() */
+    double sc = 0;
+    for (int r = tid; r < N; r += KB_THREADS) {
+      const int i = r >> 2, c = r & 3;
+      double xv = gP[r];
+      if (row_is_real(r, n)) {
+        const double bb = gH[(size_t)r * HROW + 11];
+        const double dx = ok2 ? Hs[r * HROW + 11] : bb; /* CSparse leaves x = b when the factorisation fails */
+        sc += dx * (lambda * dx + bb);
+        xv = (c == 2) ? normalize_theta(xv + dx) : xv + dx;
+      }
+      sT[4 * i + c] = xv;
+    }
+    __syncthreads();
+    double red[1] = {sc};
+    block_sum<1, KB_THREADS / 32>(red, sRed, sRed + 40);
+    const double scale = sRed[40] + 1e-3;
+    __syncthreads();
+    eval_chi2_parts<KB_THREADS>(kp, db, b, n, sT, so, M, sRed, sRed + 40);
+    for (int k = 0; k < 4; ++k) last_parts[k] = sRed[40 + k];
+    __syncthreads();
+    double tempChi = last_parts[0] + last_parts[1] + last_parts[2] + last_parts[3];
+    if (!ok2) { tempChi = 1.7976931348623157e308; status_add |= TEB_STATUS_CHOL_FAILED; }
+    rho = (currentChi - tempChi) / scale;
+    if (rho > 0 && isfinite(tempChi)) {
+      double alpha = 1. - pow((2 * rho - 1), 3);
+      alpha = fmin(alpha, 2. / 3.);
+      const double scaleFactor = fmax(1. / 3., alpha);
+      lambda *= scaleFactor;
+      ni = 2;
+      currentChi = tempChi;
+      for (int k = 0; k < 4; ++k) cur_parts[k] = last_parts[k];
+      for (int r = tid; r < N; r += KB_THREADS) gP[r] = sT[r]; /* discardTop(): keep the new state */
+      accepted_any = true;
+    } else {
+      lambda *= ni;
+      ni *= 2;
+      if (!isfinite(lambda)) { status_add |= TEB_STATUS_NONFINITE; break; }
+    }
+    qmax++;
+    if (!(rho < 0 && qmax < 10)) break;
+    /* rejected: restore H (the factorisation ran in place) and retry with the larger lambda */
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar, bytesH);
+      tma_load_1d(Hs, gH, bytesH, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+  }
+  (void)accepted_any;
+  if (tid == 0) {
+    const bool terminate = (qmax == 10 || rho == 0 || !isfinite(lambda));
+    st->lambda = lambda;
+    st->ni = ni;
+    st->current_chi = currentChi;
+    st->chi2_final = currentChi;
+    for (int k = 0; k < 4; ++k) { st->parts_last[k] = last_parts[k]; st->parts_cur[k] = cur_parts[k]; }
+    st->lm_iters += 1;
+    int stt = st->status | status_add;
+    if (terminate) { stt |= TEB_STATUS_TERMINATED; st->active = 0; }
+    else stt &= ~TEB_STATUS_TERMINATED;
+    st->status = stt;
+  }
+}
+
+/* ------------------------------------------------------------------ k_finalize (thread per band) */
+__global__ void k_finalize(DevBatch db, KParams kp, TebOptimizeArgs args) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= db.B) return;
+  const BandState st = db.state[b];
+  int status = st.status;
+  if (!st.failed && args.iterations_outerloop > 0 && args.iterations_innerloop > 0) status |= TEB_STATUS_OPTIMIZED;
+  double cost = __longlong_as_double(0x7ff0000000000000LL); /* cost_ = HUGE_VAL until computed (optimal_planner.cpp:90) */
+  if ((status & TEB_STATUS_OPTIMIZED) && args.compute_cost_afterwards) {
+    /* computeCurrentCost (optimal_planner.cpp:1041-1094): chi2 of the cached edge errors = last evaluated LM
+     * trial, unless batch statistics (divergence detection) refreshed them at the final state */
+    const double* parts = kp.p.divergence_detection_enable ? st.parts_cur : st.parts_last;
+    cost = 0;
+    if (args.alternative_time_cost) {
+      const int n = db.n[b];
+      const double* P = db.poses + (size_t)b * db.n_cap * 4;
+      for (int i = 0; i < n - 1; ++i) cost += P[4 * i + 3];
+    }
+    cost += args.obst_cost_scale * parts[0] + args.viapoint_cost_scale * parts[1] + parts[3];
+    if (!args.alternative_time_cost) cost += parts[2];
+  }
+  if (db.cost) db.cost[b] = cost;
+  if (db.chi2) db.chi2[b] = st.chi2_final;
+  if (db.status) db.status[b] = status;
+  if (db.lm_iters) db.lm_iters[b] = st.lm_iters;
+}
+
+}  // namespace tebgpu
