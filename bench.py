@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py — TEB trajectories/s (and LM iterations/s) of the B200-native optimizer, BASELINE.json's metric.
+
+A "step" is one optimizeTEB pass (no_outer x no_inner LM iterations + cost) over one batch of synthetic planning
+requests: `candidates` homotopy candidates x `requests` requests per GPU (weak scaling: per-GPU work is fixed).
+Default workload = BASELINE config C2 (diff-drive, 100 poses, 20 point obstacles, 32 candidates per request).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3                 # this framework
+  python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # the reference's CPU path (oracle port, all host threads)
+
+Prints ONE JSON line on rank 0 (see the contract in the task statement / DESIGN.md §6).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from teb_local_planner_b200 import abi, scenes  # noqa: E402
+
+METRIC = "TEB trajectories/sec (complete optimizeTEB: outer x inner LM iterations + cost)"
+UNIT = "trajectories/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--requests", type=int, default=64, help="planning requests per GPU per step")
+    ap.add_argument("--candidates", type=int, default=None, help="candidates per request (default: config's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_workload(a, rank):
+    n, M, cand, inflated, moving, via_pts = scenes.CONFIG_SHAPES[a.workload]
+    cand = a.candidates or (32 if a.workload in ("C1",) else cand)
+    if a.workload == "C3" and a.candidates is None:
+        cand = 32  # north-star scene: 200 poses / 64 obstacles / 32 candidates
+    if a.workload == "C4" and a.candidates is None:
+        cand = 32
+    p = scenes.config_params(a.workload)
+    p.teb_autosize = 0  # throughput runs use fixed n; autosize parity is covered by tests/
+    hb = scenes.make_batch(n, M, cand, a.requests, seed=1000 + rank, inflated=inflated, moving=moving,
+                           via_points=via_pts)
+    args = abi.make_args(p.no_inner_iterations, p.no_outer_iterations, True, p.selection_obst_cost_scale,
+                         p.selection_viapoint_cost_scale, bool(p.selection_alternative_time_cost))
+    desc = {"workload": f"{a.workload}: {'car-like' if p.min_turning_radius > 0 else 'diff-drive'}, {n} poses, {M} "
+                        f"{'moving ' if moving else ''}{'inflated ' if inflated else 'point '}obstacles, "
+                        f"{cand} candidates/request x {a.requests} requests/GPU, {p.no_outer_iterations}x"
+                        f"{p.no_inner_iterations} LM iterations, teb_autosize=false",
+            "n_poses": n, "n_obstacles": M, "candidates": cand, "requests_per_gpu": a.requests,
+            "bands_per_gpu": hb.B, "via_points": via_pts}
+    return p, hb, args, desc, cand
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(n, M, V, B):
+    """per band per LM iteration; N = 4n - 7 unknowns, band rows of 11 + rhs."""
+    N = 4 * n - 7
+    a = 32 * n + 48 * M + 16 * V + 8 * (11 * N + N) + 8
+    b = 8 * 12 * N + 32 * n + 48 * M + 32 * n + 32
+    return a * B, b * B
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def pick_threads(p, hb, args, cand):
+    """'all the host threads it can use': the box may expose more logical CPUs than its cgroup quota serves, so try
+    a few thread counts on a small sample and keep the fastest."""
+    from tests import oracle_binding as ob
+    tmax = host_threads()
+    keep = min(hb.B, max(cand, 4 * tmax))
+    sub = abi.HostBatch(hb.poses[:keep], hb.n[:keep], hb.obstacles, hb.obst_count, hb.scene_id[:keep],
+                        hb.via[:keep] if hb.V_cap else None, hb.via_count[:keep] if hb.V_cap else None)
+    best_t, best_rate = 1, 0.0
+    t = tmax
+    tried = []
+    while t >= 1:
+        h = sub.copy()
+        t0 = time.perf_counter()
+        ob.optimize_batch(p, h, args, jac_mode=ob.JAC_G2O, threads=t)
+        rate = keep / (time.perf_counter() - t0)
+        tried.append((t, round(rate, 1)))
+        if rate > best_rate:
+            best_t, best_rate = t, rate
+        if t == 1:
+            break
+        t = max(1, t // 2)
+        if t < tmax // 16:
+            break
+    return best_t, tried
+
+
+def cpu_reference_run(p, hb, args, threads, steps, warmup):
+    """The reference's CPU path = the oracle port in g2o mode (numeric Jacobians), one band per host thread."""
+    from tests import oracle_binding as ob
+    times = []
+    for s in range(warmup + steps):
+        h = hb.copy()
+        t0 = time.perf_counter()
+        ob.optimize_batch(p, h, args, jac_mode=ob.JAC_G2O, threads=threads)
+        t1 = time.perf_counter()
+        if s >= warmup:
+            times.append(t1 - t0)
+    return float(np.mean(times)), int(h.lm_iters.sum())
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    p, hb, args, desc, cand = make_workload(a, 0)
+    threads, tried = pick_threads(p, hb, args, cand)
+    # bounded sample: cap CPU work at roughly 20 s of single-thread time per step
+    per_band_ms = {"C1": 2.5, "C2": 8.0, "C3": 18.0, "C4": 28.0}[a.workload]
+    max_bands = max(threads, int(20000.0 / per_band_ms))
+    if hb.B > max_bands:
+        keep = max(cand, (max_bands // cand) * cand)
+        hb = abi.HostBatch(hb.poses[:keep], hb.n[:keep], hb.obstacles, hb.obst_count, hb.scene_id[:keep],
+                           hb.via[:keep] if hb.V_cap else None, hb.via_count[:keep] if hb.V_cap else None)
+    sec, iters = cpu_reference_run(p, hb, args, threads, a.steps, a.warmup)
+    value = hb.B / sec
+    sample = (f"{hb.B} bands of the same workload per step, oracle port (g2o mode: numeric Jacobians, banded Cholesky), "
+              f"{threads} host threads (of {host_threads()} visible; thread-count probe {tried})")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": desc,
+            "lm_iters_per_s": iters / sec,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "restated CPU g2o path (oracle/teb_oracle.c), not the upstream g2o binary: the reference cannot be built here"}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(a, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import teb_local_planner_b200 as T
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    p, hb, args, desc, cand = make_workload(a, rank)
+    B, n_cap = hb.B, hb.n_cap
+    g = T.TebGpu(B, n_cap, hb.S, max(hb.M_cap, 1), hb.V_cap, device=local_rank)
+    g.set_params(p)
+    # a non-default torch stream: its handle is passed to the C-ABI so that torch ops (input restore, NCCL) and
+    # the optimizer kernels are ordered on ONE stream, and torch.cuda.Event timing sees the kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def to_dev(arr):
+        return torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(dev)
+
+    # ---------------- device-resident path ("value"): inputs already in HBM
+    d_pristine = to_dev(hb.poses)
+    d_poses = d_pristine.clone()
+    d_n, d_sid, d_ob, d_oc = to_dev(hb.n), to_dev(hb.scene_id), to_dev(hb.obstacles), to_dev(hb.obst_count)
+    d_vs, d_vg, d_rot = to_dev(hb.vel_start), to_dev(hb.vel_goal), to_dev(hb.prefer_rotdir)
+    d_via = to_dev(hb.via) if hb.V_cap else None
+    d_vc = to_dev(hb.via_count) if hb.V_cap else None
+    d_cost = torch.zeros(B, dtype=torch.float64, device=dev)
+    d_chi2 = torch.zeros_like(d_cost)
+    d_status = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_iters = torch.zeros_like(d_status)
+    d_all_cost = torch.zeros(B * world, dtype=torch.float64, device=dev)
+    bs = abi.TebBatch()
+    bs.B, bs.n_cap, bs.S, bs.M_cap, bs.V_cap = B, n_cap, hb.S, hb.M_cap, hb.V_cap
+    bs.poses, bs.n, bs.scene_id = d_poses.data_ptr(), d_n.data_ptr(), d_sid.data_ptr()
+    bs.obstacles, bs.obst_count = d_ob.data_ptr(), d_oc.data_ptr()
+    bs.via = d_via.data_ptr() if hb.V_cap else None
+    bs.via_count = d_vc.data_ptr() if hb.V_cap else None
+    bs.vel_start, bs.vel_goal, bs.prefer_rotdir = d_vs.data_ptr(), d_vg.data_ptr(), d_rot.data_ptr()
+    bs.cost, bs.chi2, bs.status, bs.lm_iters = d_cost.data_ptr(), d_chi2.data_ptr(), d_status.data_ptr(), d_iters.data_ptr()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def device_step():
+        d_poses.copy_(d_pristine)                       # fresh synthetic inputs, already resident in HBM
+        g.optimize_device(bs, args, stream.cuda_stream)  # all kernels of optimizeTEB for the whole batch
+        if world > 1:
+            dist.all_gather_into_tensor(d_all_cost, d_cost)  # the ONE collective: per-candidate costs
+
+    for _ in range(a.warmup):
+        flush.zero_()
+        device_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    for k in range(a.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (outside the events)
+        ev[k][0].record(stream)
+        device_step()
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    launches_per_step = g.launch_count()
+    lm_iters_step = int(d_iters.sum().item())
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        it = torch.tensor([lm_iters_step], dtype=torch.float64, device=dev)
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+        lm_iters_step = int(it.item())
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / a.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # best-candidate selection on the gathered costs (host, selectBestTeb) - sanity only, outside the timing
+    costs = (d_all_cost if world > 1 else d_cost).cpu().numpy()
+    from teb_local_planner_b200 import distributed as D
+    best = D.select_best_per_request(costs, cand, p)
+
+    # ---------------- per-kernel times for the roofline (separate profiled pass, CUDA events around every launch)
+    g.set_profiling(True)
+    for _ in range(2):
+        flush.zero_()
+        d_poses.copy_(d_pristine)
+        g.optimize_device(bs, args, stream.cuda_stream)
+    kt = g.kernel_times()
+    g.set_profiling(False)
+    peak, peak_src = hbm_peak()
+    bytes_a, bytes_b = algorithmic_bytes(desc["n_poses"], desc["n_obstacles"], desc["via_points"], B)
+
+    def roof(name, nbytes):
+        ms, cnt = kt[name]
+        if cnt == 0:
+            return None
+        avg_ms = ms / cnt
+        ach = nbytes / (avg_ms * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": nbytes,
+                "peak_source": peak_src}
+
+    total_ms = sum(v[0] for v in kt.values())
+    shares = {k: (v[0] / total_ms if total_ms > 0 else 0.0) for k, v in kt.items()}
+    roof_a, roof_b = roof("k_linearize", bytes_a), roof("k_lm_step", bytes_b)
+    dominant = roof_b if kt["k_lm_step"][0] >= kt["k_linearize"][0] else roof_a
+    working_set_mb = B * 4 * n_cap * 96 / 1e6
+    for r in (roof_a, roof_b):
+        if r is not None:
+            r["note"] = ("H/b working set %.0f MB %s the 126 MB L2" % (working_set_mb, ">" if working_set_mb > 126 else "<=")
+                         + ("" if working_set_mb > 126 else ": L2-resident, latency-bound; HBM fraction is indicative only"))
+    # ncu-measured DRAM traffic per launch, when a capture of this workload has been summarised under profiles/
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f)
+        key = f"{a.workload}_B{B}"
+        for r in (roof_a, roof_b):
+            if r is not None and key in tr and r["kernel"] in tr[key]:
+                r["traffic"] = tr[key][r["kernel"]]
+    except Exception:
+        pass
+
+    # ---------------- end-to-end path: public C-ABI call with HOST (pinned) buffers, H2D + D2H inside
+    pin = {}
+    def pinned_like(arr):
+        tt = torch.empty(arr.nbytes, dtype=torch.uint8).pin_memory()
+        view = tt.numpy().view(arr.dtype).reshape(arr.shape)
+        view[...] = arr
+        pin[id(view)] = tt
+        return view
+    hp = abi.HostBatch.__new__(abi.HostBatch)
+    hp.__dict__.update(hb.__dict__)
+    for name in ("poses", "n", "scene_id", "obstacles", "obst_count", "via", "via_count", "vel_start", "vel_goal",
+                 "prefer_rotdir", "cost", "chi2", "status", "lm_iters"):
+        setattr(hp, name, pinned_like(getattr(hb, name)))
+    h2d = sum(getattr(hp, k).nbytes for k in ("poses", "n", "scene_id", "obstacles", "obst_count", "vel_start",
+                                               "vel_goal", "prefer_rotdir")) + (hp.via.nbytes + hp.via_count.nbytes if hb.V_cap else 0)
+    d2h = sum(getattr(hp, k).nbytes for k in ("poses", "n", "cost", "chi2", "status", "lm_iters"))
+    pristine_host = hb.poses.copy()
+    e2e_t = []
+    gather_in = torch.zeros(B, dtype=torch.float64, device=dev)
+    for k in range(a.warmup + a.steps):
+        hp.poses[...] = pristine_host
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        g.optimize(hp, args)                            # H2D, all kernels, D2H of poses/cost/status, synchronous
+        if world > 1:
+            gather_in.copy_(torch.from_numpy(hp.cost))
+            dist.all_gather_into_tensor(d_all_cost, gather_in)
+            _ = d_all_cost.cpu()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if k >= a.warmup:
+            e2e_t.append(t1 - t0)
+    e2e_ms = float(np.mean(e2e_t)) * 1e3
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    e2e_value = B * world / (e2e_ms * 1e-3)
+    # device-resident result == host-path result (same kernels): guard against a silently different path
+    assert np.array_equal(hp.cost, d_cost.cpu().numpy()), "device-resident and host entry points disagree"
+
+    # ---------------- CPU baseline on the host cores (rank 0, N = 1 only): oracle port, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        threads, tried = pick_threads(p, hb, args, cand)
+        per_band_ms = {"C1": 2.5, "C2": 8.0, "C3": 18.0, "C4": 28.0}[a.workload]
+        max_bands = max(threads, int(20000.0 / per_band_ms))
+        keep = min(hb.B, max(cand, (max_bands // cand) * cand))
+        sub = abi.HostBatch(hb.poses[:keep], hb.n[:keep], hb.obstacles, hb.obst_count, hb.scene_id[:keep],
+                            hb.via[:keep] if hb.V_cap else None, hb.via_count[:keep] if hb.V_cap else None)
+        sec, _ = cpu_reference_run(p, sub, args, threads, 1, 1)
+        sec1, _ = cpu_reference_run(p, abi.HostBatch(hb.poses[:cand], hb.n[:cand], hb.obstacles, hb.obst_count,
+                                                     hb.scene_id[:cand], hb.via[:cand] if hb.V_cap else None,
+                                                     hb.via_count[:cand] if hb.V_cap else None), args, 1, 1, 0)
+        cpu = {"value": keep / sec, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{keep} bands of this workload, oracle/teb_oracle.c in g2o mode (numeric Jacobians, banded "
+                         f"Cholesky), one band per host thread, {threads} threads (of {host_threads()} visible; probe {tried})",
+               "single_thread_value": cand / sec1}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": dict(desc, l2="flushed between timed steps (256 MB memset)", timing="CUDA events per step on the launching stream, max over ranks"),
+                "lm_iters_per_s": lm_iters_step / (ms_per_step * 1e-3),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms, "api": "tebgpu_optimize_batch (C-ABI, pinned host buffers)"},
+                "gpu_launches": int(launches_per_step * a.steps),
+                "gpu_launches_per_step": int(launches_per_step),
+                "roofline": dominant, "roofline_kernel_a": roof_a, "roofline_kernel_b": roof_b,
+                "kernel_time_share": shares,
+                "cpu_baseline": cpu, "clocks": clocks,
+                "best_candidate_of_request0": int(best[0])}
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_b200(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -212,10 +212,19 @@ int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* params);
 int32_t tebgpu_optimize_batch(tebgpu_ctx* ctx, const TebBatch* batch, const TebOptimizeArgs* args);
 
 /* Same, every pointer in `batch` is a DEVICE pointer on the context's device. Stream-ordered on the
- * context stream (or `cuda_stream` if non-NULL, a cudaStream_t passed as void*); does NOT synchronise. */
+ * context stream (or `cuda_stream` if non-NULL, a cudaStream_t passed as void*; NULL means the context's own
+ * stream, so pass cudaStreamLegacy / cudaStreamPerThread explicitly to target a default stream); does NOT
+ * synchronise. */
 int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* batch, const TebOptimizeArgs* args,
                                      void* cuda_stream);
 int32_t tebgpu_synchronize(tebgpu_ctx* ctx);
+
+/* Per-kernel device timing (CUDA events on the launching stream around every launch) for roofline reporting.
+ * enable != 0 -> subsequent optimize calls record events. tebgpu_get_kernel_times synchronises, then returns for
+ * kernel kind k (0 begin, 1 auto_resize, 2 build_graph, 3 linearize ["kernel A"], 4 lm_step ["kernel B"], 5 finalize)
+ * the accumulated milliseconds and launch count since profiling was enabled, and resets the accumulators. */
+int32_t tebgpu_set_profiling(tebgpu_ctx* ctx, int32_t enable);
+int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[6], int64_t count_out[6]);
 
 /* Number of kernels launched by the last optimize call (for bench.py's gpu_launches). */
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx);

@@ -1084,6 +1084,7 @@ static int lm_solve(Graph* g, int iteration, LMState* lm, const OracleOptions* o
   } while (rho < 0 && qmax < 10);
   st->chi2_final = currentChi;
   st->lambda_final = lm->lambda;
+  if (opt->verbose) fprintf(stderr, "LMTRIALS %d %d %.6g %.6g\n", iteration, qmax, currentChi, lm->lambda);
   if (qmax == 10 || rho == 0 || !isfinite(lm->lambda)) return 0;
   return 1;
 }

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "teb_kernels.cuh"
 
@@ -37,7 +38,43 @@ struct tebgpu_ctx {
   double* d_vg = nullptr; int32_t* d_rot = nullptr; double* d_cost = nullptr; double* d_chi2 = nullptr;
   int32_t* d_status = nullptr; int32_t* d_iters = nullptr;
   size_t smem_a = 0, smem_b = 0, smem_g = 0;
+  /* profiling */
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;      /* pairs */
+  std::vector<int> ev_kind;
+  size_t ev_used = 0;
+  double prof_ms[6] = {0, 0, 0, 0, 0, 0};
+  int64_t prof_cnt[6] = {0, 0, 0, 0, 0, 0};
 };
+
+static void prof_begin(tebgpu_ctx* c, cudaStream_t st, int kind) {
+  if (!c->profiling) return;
+  if (c->ev_used + 2 > c->ev.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    c->ev.push_back(a);
+    c->ev.push_back(b);
+    c->ev_kind.push_back(kind);
+  }
+  c->ev_kind[c->ev_used / 2] = kind;
+  cudaEventRecord(c->ev[c->ev_used], st);
+}
+static void prof_end(tebgpu_ctx* c, cudaStream_t st) {
+  if (!c->profiling) return;
+  cudaEventRecord(c->ev[c->ev_used + 1], st);
+  c->ev_used += 2;
+}
+static void prof_collect(tebgpu_ctx* c) {
+  for (size_t k = 0; k + 1 < c->ev_used + 1 && k < c->ev_used; k += 2) {
+    float ms = 0;
+    cudaEventSynchronize(c->ev[k + 1]);
+    cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1]);
+    c->prof_ms[c->ev_kind[k / 2]] += ms;
+    c->prof_cnt[c->ev_kind[k / 2]] += 1;
+  }
+  c->ev_used = 0;
+}
 
 #define CUDA_TRY(ctx, expr)                                                                      \
   do {                                                                                           \
@@ -168,6 +205,7 @@ int32_t tebgpu_destroy(tebgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
   free_all(ctx);
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return TEBGPU_OK;
@@ -254,20 +292,40 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   const size_t smem_g = (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle);
   double weight_multiplier = 1.0;
   KParams kp = make_kparams(p, weight_multiplier);
-  k_begin<<<gb, tb, 0, st>>>(db, kp); ++launches;
+  prof_begin(ctx, st, 0); k_begin<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st);
   for (int o = 0; o < args->iterations_outerloop; ++o) {
     kp = make_kparams(p, weight_multiplier);
-    if (p.teb_autosize) { k_auto_resize<<<gb, tb, 0, st>>>(db, kp); ++launches; }
-    k_build_graph<<<B, 256, smem_g, st>>>(db, kp); ++launches;
+    if (p.teb_autosize) { prof_begin(ctx, st, 1); k_auto_resize<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st); }
+    prof_begin(ctx, st, 2); k_build_graph<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st);
     for (int it = 0; it < args->iterations_innerloop; ++it) {
-      k_linearize<<<dim3(db.chunks, B), KA_THREADS, smem_a, st>>>(db, kp); ++launches;
-      k_lm_step<<<B, KB_THREADS, smem_b, st>>>(db, kp, it); ++launches;
+      prof_begin(ctx, st, 3); k_linearize<<<dim3(db.chunks, B), KA_THREADS, smem_a, st>>>(db, kp); ++launches; prof_end(ctx, st);
+      prof_begin(ctx, st, 4); k_lm_step<<<B, KB_THREADS, smem_b, st>>>(db, kp, it); ++launches; prof_end(ctx, st);
     }
     weight_multiplier *= p.weight_adapt_factor; /* optimal_planner.cpp:227 */
   }
-  k_finalize<<<gb, tb, 0, st>>>(db, kp, *args); ++launches;
+  prof_begin(ctx, st, 5); k_finalize<<<gb, tb, 0, st>>>(db, kp, *args); ++launches; prof_end(ctx, st);
   ctx->launches = launches;
+  if (ctx->profiling && ctx->ev_used > 4096) { cudaStreamSynchronize(st); prof_collect(ctx); }
   CUDA_TRY(ctx, cudaGetLastError());
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_set_profiling(tebgpu_ctx* ctx, int32_t enable) {
+  if (!ctx) return TEBGPU_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  prof_collect(ctx);
+  ctx->profiling = enable != 0;
+  for (int k = 0; k < 6; ++k) { ctx->prof_ms[k] = 0; ctx->prof_cnt[k] = 0; }
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[6], int64_t count_out[6]) {
+  if (!ctx || !ms_out || !count_out) return TEBGPU_ERR_INVALID_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  prof_collect(ctx);
+  for (int k = 0; k < 6; ++k) { ms_out[k] = ctx->prof_ms[k]; count_out[k] = ctx->prof_cnt[k]; ctx->prof_ms[k] = 0; ctx->prof_cnt[k] = 0; }
   return TEBGPU_OK;
 }
 
