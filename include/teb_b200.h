@@ -219,6 +219,10 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* batch, con
                                      void* cuda_stream);
 int32_t tebgpu_synchronize(tebgpu_ctx* ctx);
 
+/* Linear solver of the LM step (replaces LinearSolverCSparse, optimal_planner.h:75-79):
+ * 1 (default) block cyclic reduction on 8x8 blocks when max_poses <= 256, 0 sequential banded LDL^T. */
+int32_t tebgpu_set_solver(tebgpu_ctx* ctx, int32_t solver);
+
 /* Per-kernel device timing (CUDA events on the launching stream around every launch) for roofline reporting.
  * enable != 0 -> subsequent optimize calls record events. tebgpu_get_kernel_times synchronises, then returns for
  * kernel kind k (0 begin, 1 auto_resize, 2 build_graph, 3 linearize ["kernel A"], 4 lm_step ["kernel B"], 5 finalize)

@@ -23,6 +23,7 @@ struct tebgpu_ctx {
   bool have_params = false;
   std::string err;
   int64_t launches = 0;
+  int solver = 1;  /* 1: block cyclic reduction when it fits, 0: sequential banded LDL^T */
   int MW = 1;
   int chunks = 1;
   /* device workspaces */
@@ -192,7 +193,10 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     return TEBGPU_ERR_CAPACITY;
   }
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
+  if ((int)nc <= BCR_MAX_POSES && kb_bcr_smem_bytes((int)nc, (int)M) <= 232448)
+    CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kb_bcr_smem_bytes((int)nc, (int)M)));
   CUDA_TRY(c, cudaFuncSetAttribute(k_build_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_g));
   tebgpu_default_params(&c->params);
   c->have_params = true;
@@ -289,6 +293,9 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   int64_t launches = 0;
   const size_t smem_a = ka_smem_bytes(bt->M_cap);
   const size_t smem_b = kb_smem_bytes(bt->n_cap, bt->M_cap);
+  const size_t smem_bcr = kb_bcr_smem_bytes(bt->n_cap, bt->M_cap);
+  const bool use_bcr = ctx->solver != 0 && bt->n_cap <= BCR_MAX_POSES && smem_bcr <= 232448 &&
+                       ctx->lim.max_poses <= BCR_MAX_POSES;
   const size_t smem_g = (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle);
   double weight_multiplier = 1.0;
   KParams kp = make_kparams(p, weight_multiplier);
@@ -299,7 +306,10 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
     prof_begin(ctx, st, 2); k_build_graph<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st);
     for (int it = 0; it < args->iterations_innerloop; ++it) {
       prof_begin(ctx, st, 3); k_linearize<<<dim3(db.chunks, B), KA_THREADS, smem_a, st>>>(db, kp); ++launches; prof_end(ctx, st);
-      prof_begin(ctx, st, 4); k_lm_step<<<B, KB_THREADS, smem_b, st>>>(db, kp, it); ++launches; prof_end(ctx, st);
+      prof_begin(ctx, st, 4);
+      if (use_bcr) k_lm_step_t<1, KB_BCR_THREADS><<<B, KB_BCR_THREADS, smem_bcr, st>>>(db, kp, it);
+      else k_lm_step_t<0, KB_THREADS><<<B, KB_THREADS, smem_b, st>>>(db, kp, it);
+      ++launches; prof_end(ctx, st);
     }
     weight_multiplier *= p.weight_adapt_factor; /* optimal_planner.cpp:227 */
   }
@@ -326,6 +336,12 @@ int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[6], int64_t count
   CUDA_TRY(ctx, cudaDeviceSynchronize());
   prof_collect(ctx);
   for (int k = 0; k < 6; ++k) { ms_out[k] = ctx->prof_ms[k]; count_out[k] = ctx->prof_cnt[k]; ctx->prof_ms[k] = 0; ctx->prof_cnt[k] = 0; }
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_set_solver(tebgpu_ctx* ctx, int32_t solver) {
+  if (!ctx || solver < 0 || solver > 1) return TEBGPU_ERR_INVALID_ARG;
+  ctx->solver = solver;
   return TEBGPU_OK;
 }
 

@@ -818,12 +818,244 @@ __device__ __forceinline__ bool warp_band_solve(double* Hs, int N, int n, double
   return true;
 }
 
-/* ------------------------------------------------------------------ k_lm_step ("kernel B"), CTA per band */
+/* ------------------------------------------------------------------ block cyclic reduction (BCR) solver
+ * The padded normal matrix is block tridiagonal with 8x8 blocks (two pose groups per block; an acceleration edge spans
+ * the scalars 4i..4i+10, i.e. at most two adjacent blocks). BCR eliminates every other block per level: log2(m)
+ * dependent levels instead of 4n dependent pivots. SPD Schur complements stay SPD, so every pivot block has a Cholesky
+ * factor unless H + lambda I is not numerically positive definite (the LinearSolverCSparse failure condition).
+ *
+ * Per eliminated block i (neighbours p = i-s, q = i+s at stride s): D_i = C C^T,
+ *   W^L = C^-1 A_ip, W^R = C^-1 A_iq (stored transposed in q's coupling slot), w = C^-1 b_i,
+ *   D_p -= W^L^T W^L, D_q -= W^R^T W^R, A_qp(new) = -W^R^T W^L, b_p -= W^L^T w, b_q -= W^R^T w,
+ *   back-substitution x_i = C^-T (w - W^L x_p - W^R x_q). Only C^-1 (packed lower) is stored. */
+struct BcrSmem {
+  double* Dp;     /* [m][36] packed lower diagonal blocks -> C^-1 after elimination */
+  double* L0;     /* [m][64] level-0 left couplings A_{i,i-1}, row major             */
+  double* Lpool;  /* couplings created at levels >= 1                                 */
+  double* bs;     /* [m][8] rhs -> w                                                  */
+  double* xs;     /* [m][8] solution                                                  */
+  int off[12];    /* pool offset (in blocks) of level l                               */
+};
+__device__ __forceinline__ double* bcr_L(const BcrSmem& S, int lvl, int i) {
+  return lvl == 0 ? S.L0 + 64 * i : S.Lpool + 64 * (S.off[lvl] + (i >> lvl));
+}
+#define PIDX(a, c) (((a) * ((a) + 1)) / 2 + (c))
+
+/* in-register Cholesky of a packed 8x8 SPD block and inverse of its factor; in-place safe. */
+__device__ __forceinline__ bool chol8_inverse(const double* din, double* cinv_out) {
+  double c[36], rinv[8];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) c[k] = din[k];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double d = c[PIDX(j, j)];
+    if (!(d > 0) || !isfinite(d)) ok = false;
+    const double r = rsqrt(d);
+    rinv[j] = r;
+#pragma unroll
+    for (int a = j + 1; a < 8; ++a) c[PIDX(a, j)] *= r;
+#pragma unroll
+    for (int a = j + 1; a < 8; ++a)
+#pragma unroll
+      for (int b2 = j + 1; b2 <= a; ++b2) c[PIDX(a, b2)] -= c[PIDX(a, j)] * c[PIDX(b2, j)];
+  }
+  /* in-place inverse of the lower-triangular factor, column by column (column j of C is dead once X(:,j) is known) */
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    c[PIDX(j, j)] = rinv[j];
+#pragma unroll
+    for (int a = j + 1; a < 8; ++a) {
+      double sacc = c[PIDX(a, j)] * rinv[j];
+#pragma unroll
+      for (int k = j + 1; k < a; ++k) sacc += c[PIDX(a, k)] * c[PIDX(k, j)];
+      c[PIDX(a, j)] = -sacc * rinv[a];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 36; ++k) cinv_out[k] = c[k];
+  return ok;
+}
+/* z = Cinv v (lower-triangular mat-vec), Cinv packed in shared memory */
+__device__ __forceinline__ void tri_mv(const double* ci, const double (&v)[8], double (&z)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double sacc = 0;
+#pragma unroll
+    for (int c = 0; c <= k; ++c) sacc += ci[PIDX(k, c)] * v[c];
+    z[k] = sacc;
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void bcr_solve(const BcrSmem& S, int m, int* s_fail) {
+  const int tid = threadIdx.x;
+  int Lmax = 0;
+  while ((1 << Lmax) < m) ++Lmax;
+  for (int lvl = 0; lvl < Lmax; ++lvl) {
+    const int s = 1 << lvl;
+    const int E = (m > s) ? ((m - s - 1) / (2 * s) + 1) : 0;
+    /* phase 1a: C^-1 of every eliminated diagonal block */
+    for (int t = tid; t < E; t += NT) {
+      const int i = s * (2 * t + 1);
+      if (!chol8_inverse(S.Dp + 36 * i, S.Dp + 36 * i)) *s_fail = 1;
+    }
+    __syncthreads();
+    /* phase 1b: W^L (columns of A_ip), W^R^T (rows of A_qi), w */
+    for (int t = tid; t < 17 * E; t += NT) {
+      const int e = t / 17, r = t - 17 * e;
+      const int i = s * (2 * e + 1), q = i + s;
+      const double* ci = S.Dp + 36 * i;
+      double v[8], z[8];
+      if (r < 8) {
+        double* L = bcr_L(S, lvl, i);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = L[8 * k + r];
+        tri_mv(ci, v, z);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) L[8 * k + r] = z[k];
+      } else if (r < 16) {
+        if (q < m) {
+          double* L = bcr_L(S, lvl, q) + 8 * (r - 8);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = L[k];
+          tri_mv(ci, v, z);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) L[k] = z[k];
+        }
+      } else {
+        double* bb = S.bs + 8 * i;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = bb[k];
+        tri_mv(ci, v, z);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bb[k] = z[k];
+      }
+    }
+    __syncthreads();
+    /* phase 2: Schur updates of the surviving blocks e = 2s*u, one thread per block row */
+    const int SC = (m + 2 * s - 1) / (2 * s);
+    for (int t = tid; t < 8 * SC; t += NT) {
+      const int u = t >> 3, a = t & 7;
+      const int e = 2 * s * u, iR = e + s, iL = e - s;
+      const bool hasR = iR < m, hasL = u > 0;
+      double dacc[8], lacc[8], bacc = 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { dacc[c] = 0; lacc[c] = 0; }
+      if (hasR) {
+        const double* WL = bcr_L(S, lvl, iR);
+        const double* w = S.bs + 8 * iR;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const double wa = WL[8 * k + a];
+          bacc += wa * w[k];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c <= a) dacc[c] += wa * WL[8 * k + c];
+        }
+      }
+      if (hasL) {
+        const double* Z = bcr_L(S, lvl, e);
+        const double* WLl = bcr_L(S, lvl, iL);
+        const double* w = S.bs + 8 * iL;
+        double za[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) za[k] = Z[8 * a + k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bacc += za[k] * w[k];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c <= a) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sacc += za[k] * Z[8 * c + k];
+            dacc[c] += sacc;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) lacc[c] += za[k] * WLl[8 * k + c];
+        double* Ln = bcr_L(S, lvl + 1, e) + 8 * a;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Ln[c] = -lacc[c];
+      }
+      double* De = S.Dp + 36 * e;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c <= a) De[PIDX(a, c)] -= dacc[c];
+      S.bs[8 * e + a] -= bacc;
+    }
+    __syncthreads();
+  }
+  /* top: block 0 */
+  if (tid == 0) {
+    if (!chol8_inverse(S.Dp, S.Dp)) *s_fail = 1;
+    double v[8], z[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = S.bs[k];
+    tri_mv(S.Dp, v, z);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      double sacc = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k >= c) sacc += S.Dp[PIDX(k, c)] * z[k];
+      S.xs[c] = sacc;
+    }
+  }
+  __syncthreads();
+  for (int lvl = Lmax - 1; lvl >= 0; --lvl) {
+    const int s = 1 << lvl;
+    const int E = (m > s) ? ((m - s - 1) / (2 * s) + 1) : 0;
+    for (int t = tid; t < 8 * E; t += NT) {
+      const int e = t >> 3, k = t & 7;
+      const int i = s * (2 * e + 1), p = i - s, q = i + s;
+      const double* WL = bcr_L(S, lvl, i);
+      double acc = S.bs[8 * i + k];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc -= WL[8 * k + c] * S.xs[8 * p + c];
+      if (q < m) {
+        const double* Z = bcr_L(S, lvl, q);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) acc -= Z[8 * a + k] * S.xs[8 * q + a];
+      }
+      S.bs[8 * i + k] = acc;
+    }
+    __syncthreads();
+    for (int t = tid; t < 8 * E; t += NT) {
+      const int e = t >> 3, c = t & 7;
+      const int i = s * (2 * e + 1);
+      const double* ci = S.Dp + 36 * i;
+      double sacc = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k >= c) sacc += ci[PIDX(k, c)] * S.bs[8 * i + k];
+      S.xs[8 * i + c] = sacc;
+    }
+    __syncthreads();
+  }
+}
+
+/* ------------------------------------------------------------------ k_lm_step ("kernel B"), CTA per band.
+ * SOLVER 0: sequential banded LDL^T by one warp on the TMA-loaded band (any n_cap <= 512);
+ * SOLVER 1: block cyclic reduction on the expanded 8x8 block-tridiagonal form (n_cap <= BCR_MAX_POSES). */
+constexpr int BCR_MAX_POSES = 256;
+constexpr int KB_BCR_THREADS = 256;
+
 __host__ __device__ inline size_t kb_smem_bytes(int n_cap, int M_cap) {
   return ((size_t)4 * n_cap * HROW + (size_t)4 * n_cap + 64) * sizeof(double) + (size_t)M_cap * sizeof(TebObstacle) + 64;
 }
+__host__ __device__ inline int bcr_blocks(int n_cap) { return (4 * n_cap + 7) / 8; }
+__host__ __device__ inline size_t kb_bcr_smem_bytes(int n_cap, int M_cap) {
+  const size_t m = bcr_blocks(n_cap);
+  /* Dp 36m + L0 64m + Lpool 64(m + 12) + bs 8m + xs 8m + b0 8m + trial poses 4 n_cap + scratch 64 */
+  return ((36 + 64 + 64 + 8 + 8 + 8) * m + 64 * 12 + (size_t)4 * n_cap + 64) * sizeof(double) +
+         (size_t)M_cap * sizeof(TebObstacle) + 64;
+}
 
-__global__ void __launch_bounds__(KB_THREADS) k_lm_step(DevBatch db, KParams kp, int iteration) {
+template <int SOLVER, int NT>
+__global__ void __launch_bounds__(NT, SOLVER == 1 ? 2 : 1) k_lm_step_t(DevBatch db, KParams kp, int iteration) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = blockIdx.x;
   BandState* st = &db.state[b];
@@ -831,13 +1063,36 @@ __global__ void __launch_bounds__(KB_THREADS) k_lm_step(DevBatch db, KParams kp,
   const int n = db.n[b];
   const int N = 4 * n;
   const int tid = threadIdx.x;
+  __shared__ int s_flag[4];
 
-  double* Hs = reinterpret_cast<double*>(smem_raw);
-  double* sT = Hs + (size_t)4 * db.n_cap * HROW;   /* trial poses [n][4] */
-  double* sRed = sT + (size_t)4 * db.n_cap;        /* 64 doubles scratch */
+  /* ---- shared memory carve-up */
+  double* Hs = nullptr;   /* SOLVER 0: band [N][12] */
+  BcrSmem S;              /* SOLVER 1 */
+  double* b0 = nullptr;
+  double* sT;
+  double* sRed;
+  int m = 0;
+  if constexpr (SOLVER == 0) {
+    Hs = reinterpret_cast<double*>(smem_raw);
+    sT = Hs + (size_t)4 * db.n_cap * HROW;
+  } else {
+    const int mc = bcr_blocks(db.n_cap);
+    m = (N + 7) / 8;
+    double* base = reinterpret_cast<double*>(smem_raw);
+    S.Dp = base;
+    S.L0 = S.Dp + 36 * mc;
+    S.Lpool = S.L0 + 64 * mc;
+    S.bs = S.Lpool + 64 * (mc + 12);
+    S.xs = S.bs + 8 * mc;
+    b0 = S.xs + 8 * mc;
+    sT = b0 + 8 * mc;
+    S.off[0] = 0;
+    S.off[1] = 0;
+    for (int l = 1; l < 11; ++l) S.off[l + 1] = S.off[l] + ((m + (1 << l) - 1) >> l);
+  }
+  sRed = sT + (size_t)4 * db.n_cap; /* 64 doubles scratch */
   uint64_t* bar = reinterpret_cast<uint64_t*>(sRed + 56);
   TebObstacle* so = reinterpret_cast<TebObstacle*>(sRed + 64);
-  __shared__ int s_flag[4];
 
   const int s = db.scene_id[b];
   const int M = db.obst_count[s];
@@ -847,14 +1102,15 @@ __global__ void __launch_bounds__(KB_THREADS) k_lm_step(DevBatch db, KParams kp,
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
+    s_flag[1] = 0;
   }
   __syncthreads();
   uint32_t parity = 0;
   const uint32_t bytesH = (uint32_t)N * HROW * 8u;
   if (tid == 0) {
     const uint32_t bytesO = (uint32_t)M * (uint32_t)sizeof(TebObstacle);
-    mbar_expect_tx(bar, bytesH + bytesO);
-    tma_load_1d(Hs, gH, bytesH, bar);
+    mbar_expect_tx(bar, (SOLVER == 0 ? bytesH : 0u) + bytesO);
+    if constexpr (SOLVER == 0) tma_load_1d(Hs, gH, bytesH, bar);
     if (bytesO) tma_load_1d(so, db.obstacles + (size_t)s * db.M_cap, bytesO, bar);
   }
   /* chi2 at the linearisation point = sum of the kernel-A tile partials (computeActiveErrors, App. A.4) */
@@ -872,13 +1128,13 @@ __global__ void __launch_bounds__(KB_THREADS) k_lm_step(DevBatch db, KParams kp,
   double lambda = st->lambda, ni = st->ni;
   if (iteration == 0) { /* computeLambdaInit: tau * max diagonal (App. A.4) */
     double mx = 0;
-    for (int r = tid; r < N; r += KB_THREADS)
-      if (row_is_real(r, n)) mx = fmax(mx, fabs(Hs[r * HROW]));
+    for (int r = tid; r < N; r += NT)
+      if (row_is_real(r, n)) mx = fmax(mx, fabs(SOLVER == 0 ? Hs[r * HROW] : gH[(size_t)r * HROW]));
     mx = warp_max(mx);
     if ((tid & 31) == 0) sRed[tid >> 5] = mx;
     __syncthreads();
     mx = 0;
-    for (int w = 0; w < KB_THREADS / 32; ++w) mx = fmax(mx, sRed[w]);
+    for (int w = 0; w < NT / 32; ++w) mx = fmax(mx, sRed[w]);
     __syncthreads();
     lambda = 1e-5 * mx;
     ni = 2;
@@ -888,23 +1144,59 @@ __global__ void __launch_bounds__(KB_THREADS) k_lm_step(DevBatch db, KParams kp,
   int qmax = 0;
   int status_add = 0;
   double last_parts[4] = {cur_parts[0], cur_parts[1], cur_parts[2], cur_parts[3]};
-  bool accepted_any = false;
   while (true) {
     /* (H + lambda I) dx = b */
-    if (tid < 32) {
-      const bool ok = warp_band_solve(Hs, N, n, lambda);
-      if (tid == 0) s_flag[0] = ok ? 1 : 0;
+    bool ok2;
+    if constexpr (SOLVER == 0) {
+      if (tid < 32) {
+        const bool ok = warp_band_solve(Hs, N, n, lambda);
+        if (tid == 0) s_flag[0] = ok ? 1 : 0;
+      }
+      __syncthreads();
+      ok2 = s_flag[0] != 0;
+    } else {
+      /* expand the band rows into 8x8 blocks (coalesced 16-byte loads of each 96-byte row) */
+      for (int r = tid; r < 8 * m; r += NT) {
+        const int i = r >> 3, a = r & 7;
+        double* Lrow = S.L0 + 64 * i + 8 * a;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Lrow[c] = 0.0;
+        double* Dblk = S.Dp + 36 * i;
+        if (r < N) {
+          const double2* src = reinterpret_cast<const double2*>(gH + (size_t)r * HROW);
+          double h[12];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { const double2 v2 = src[k]; h[2 * k] = v2.x; h[2 * k + 1] = v2.y; }
+          if (row_is_real(r, n)) h[0] += lambda;
+#pragma unroll
+          for (int k = 0; k < 11; ++k) {
+            const int c = a - k;
+            if (c >= 0) Dblk[PIDX(a, c)] = h[k];
+            else if (c >= -8) Lrow[8 + c] = h[k];
+          }
+          S.bs[r] = h[11];
+          b0[r] = h[11];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c <= a) Dblk[PIDX(a, c)] = (c == a) ? 1.0 : 0.0;
+          S.bs[r] = 0.0;
+          b0[r] = 0.0;
+        }
+      }
+      if (tid == 0) s_flag[1] = 0;
+      __syncthreads();
+      bcr_solve<NT>(S, m, &s_flag[1]);
+      ok2 = s_flag[1] == 0;
     }
-    __syncthreads();
-    const bool ok2 = s_flag[0] != 0;
     /* trial state x [+] dx (VertexPose::oplusImpl / VertexTimeDiff::oplusImpl) and computeScale() */
     double sc = 0;
-    for (int r = tid; r < N; r += KB_THREADS) {
+    for (int r = tid; r < N; r += NT) {
       const int i = r >> 2, c = r & 3;
       double xv = gP[r];
       if (row_is_real(r, n)) {
-        const double bb = gH[(size_t)r * HROW + 11];
-        const double dx = ok2 ? Hs[r * HROW + 11] : bb; /* CSparse leaves x = b when the factorisation fails */
+        const double bb = (SOLVER == 0) ? gH[(size_t)r * HROW + 11] : b0[r];
+        const double dx = ok2 ? ((SOLVER == 0) ? Hs[r * HROW + 11] : S.xs[r]) : bb; /* CSparse leaves x = b on failure */
         sc += dx * (lambda * dx + bb);
         xv = (c == 2) ? normalize_theta(xv + dx) : xv + dx;
       }
@@ -912,10 +1204,10 @@ __global__ void __launch_bounds__(KB_THREADS) k_lm_step(DevBatch db, KParams kp,
     }
     __syncthreads();
     double red[1] = {sc};
-    block_sum<1, KB_THREADS / 32>(red, sRed, sRed + 40);
+    block_sum<1, NT / 32>(red, sRed, sRed + 40);
     const double scale = sRed[40] + 1e-3;
     __syncthreads();
-    eval_chi2_parts<KB_THREADS>(kp, db, b, n, sT, so, M, sRed, sRed + 40);
+    eval_chi2_parts<NT>(kp, db, b, n, sT, so, M, sRed, sRed + 40);
     for (int k = 0; k < 4; ++k) last_parts[k] = sRed[40 + k];
     __syncthreads();
     double tempChi = last_parts[0] + last_parts[1] + last_parts[2] + last_parts[3];
@@ -929,8 +1221,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_lm_step(DevBatch db, KParams kp,
       ni = 2;
       currentChi = tempChi;
       for (int k = 0; k < 4; ++k) cur_parts[k] = last_parts[k];
-      for (int r = tid; r < N; r += KB_THREADS) gP[r] = sT[r]; /* discardTop(): keep the new state */
-      accepted_any = true;
+      for (int r = tid; r < N; r += NT) gP[r] = sT[r]; /* discardTop(): keep the new state */
     } else {
       lambda *= ni;
       ni *= 2;
@@ -938,16 +1229,17 @@ __global__ void __launch_bounds__(KB_THREADS) k_lm_step(DevBatch db, KParams kp,
     }
     qmax++;
     if (!(rho < 0 && qmax < 10)) break;
-    /* rejected: restore H (the factorisation ran in place) and retry with the larger lambda */
+    /* rejected: retry with the larger lambda (SOLVER 0 factorised in place: restore H first) */
     __syncthreads();
-    if (tid == 0) {
-      mbar_expect_tx(bar, bytesH);
-      tma_load_1d(Hs, gH, bytesH, bar);
+    if constexpr (SOLVER == 0) {
+      if (tid == 0) {
+        mbar_expect_tx(bar, bytesH);
+        tma_load_1d(Hs, gH, bytesH, bar);
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1;
     }
-    mbar_wait(bar, parity);
-    parity ^= 1;
   }
-  (void)accepted_any;
   if (tid == 0) {
     const bool terminate = (qmax == 10 || rho == 0 || !isfinite(lambda));
     st->lambda = lambda;
