@@ -219,16 +219,20 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* batch, con
                                      void* cuda_stream);
 int32_t tebgpu_synchronize(tebgpu_ctx* ctx);
 
-/* Linear solver of the LM step (replaces LinearSolverCSparse, optimal_planner.h:75-79):
- * 1 (default) block cyclic reduction on 8x8 blocks when max_poses <= 256, 0 sequential banded LDL^T. */
+/* Linear solver / scheduling of the LM step (replaces LinearSolverCSparse, optimal_planner.h:75-79):
+ * 2 (default) speculative: the next 4 damping trials are solved concurrently, one thread per (band, trial), banded
+ *   LDL^T with the active window in registers, and the accept / reject chain is replayed in order;
+ * 1 block cyclic reduction on 8x8 blocks in shared memory (max_poses <= 256), one CTA per band;
+ * 0 sequential banded LDL^T in shared memory, one CTA per band.  All three give the same results up to round-off. */
 int32_t tebgpu_set_solver(tebgpu_ctx* ctx, int32_t solver);
 
 /* Per-kernel device timing (CUDA events on the launching stream around every launch) for roofline reporting.
  * enable != 0 -> subsequent optimize calls record events. tebgpu_get_kernel_times synchronises, then returns for
- * kernel kind k (0 begin, 1 auto_resize, 2 build_graph, 3 linearize ["kernel A"], 4 lm_step ["kernel B"], 5 finalize)
+ * kernel kind k (0 begin, 1 auto_resize, 2 build_graph, 3 linearize ["kernel A"], 4 lm_step [fused "kernel B",
+ * solvers 0/1], 5 finalize, 6 solve_tpb, 7 trial_eval, 8 decide ["kernel B" of the default speculative solver])
  * the accumulated milliseconds and launch count since profiling was enabled, and resets the accumulators. */
 int32_t tebgpu_set_profiling(tebgpu_ctx* ctx, int32_t enable);
-int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[6], int64_t count_out[6]);
+int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[9], int64_t count_out[9]);
 
 /* Number of kernels launched by the last optimize call (for bench.py's gpu_launches). */
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx);

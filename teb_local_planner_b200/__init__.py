@@ -53,7 +53,7 @@ def load_library(build_if_missing=False):
     L.tebgpu_set_profiling.restype = C.c_int32
     L.tebgpu_set_profiling.argtypes = [vp, C.c_int32]
     L.tebgpu_get_kernel_times.restype = C.c_int32
-    L.tebgpu_get_kernel_times.argtypes = [vp, C.POINTER(C.c_double * 6), C.POINTER(C.c_int64 * 6)]
+    L.tebgpu_get_kernel_times.argtypes = [vp, C.POINTER(C.c_double * 9), C.POINTER(C.c_int64 * 9)]
     L.tebgpu_build_system.restype = C.c_int32
     L.tebgpu_build_system.argtypes = [vp, C.POINTER(abi.TebBatch), C.c_int32, vp, vp, C.c_int32]
     L.tebgpu_select_best.restype = C.c_int32
@@ -114,9 +114,10 @@ class TebGpu:
 
     def kernel_times(self):
         """{kernel name: (total ms, launches)} since profiling was enabled / last read."""
-        ms, cnt = (C.c_double * 6)(), (C.c_int64 * 6)()
+        ms, cnt = (C.c_double * 9)(), (C.c_int64 * 9)()
         self._check(self.lib.tebgpu_get_kernel_times(self.ctx, C.byref(ms), C.byref(cnt)), "tebgpu_get_kernel_times")
-        names = ("k_begin", "k_auto_resize", "k_build_graph", "k_linearize", "k_lm_step", "k_finalize")
+        names = ("k_begin", "k_auto_resize", "k_build_graph", "k_linearize", "k_lm_step", "k_finalize",
+                 "k_solve_tpb", "k_trial_eval", "k_decide")
         return {nme: (ms[i], cnt[i]) for i, nme in enumerate(names)}
 
     def launch_count(self):

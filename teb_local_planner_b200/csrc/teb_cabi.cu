@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "teb_kernels.cuh"
+#include "teb_spec.cuh"
 
 using namespace tebgpu;
 
@@ -23,7 +24,7 @@ struct tebgpu_ctx {
   bool have_params = false;
   std::string err;
   int64_t launches = 0;
-  int solver = 1;  /* 1: block cyclic reduction when it fits, 0: sequential banded LDL^T */
+  int solver = 2;  /* 2: speculative thread-per-(band,trial) LDL^T (default), 1: block cyclic reduction, 0: sequential */
   int MW = 1;
   int chunks = 1;
   /* device workspaces */
@@ -32,6 +33,9 @@ struct tebgpu_ctx {
   double* dyn_t = nullptr;
   int32_t* via_idx = nullptr;
   double* chi_parts = nullptr;
+  double* dmax_parts = nullptr;
+  double* rhs = nullptr;
+  SpecBufs spec{};
   BandState* state = nullptr;
   /* device mirrors for the host-buffer entry point */
   double* d_poses = nullptr; int32_t* d_n = nullptr; int32_t* d_scene = nullptr; TebObstacle* d_obst = nullptr;
@@ -44,8 +48,8 @@ struct tebgpu_ctx {
   std::vector<cudaEvent_t> ev;      /* pairs */
   std::vector<int> ev_kind;
   size_t ev_used = 0;
-  double prof_ms[6] = {0, 0, 0, 0, 0, 0};
-  int64_t prof_cnt[6] = {0, 0, 0, 0, 0, 0};
+  double prof_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t prof_cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 static void prof_begin(tebgpu_ctx* c, cudaStream_t st, int kind) {
@@ -133,7 +137,7 @@ const char* tebgpu_last_error_string(const tebgpu_ctx* ctx) { return ctx ? ctx->
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static void free_all(tebgpu_ctx* c) {
-  void* ptrs[] = {c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+  void* ptrs[] = {c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.T, c->spec.res, c->spec.need, c->spec.qmax, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
                   c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
                   c->d_status, c->d_iters};
   for (void* p : ptrs)
@@ -169,6 +173,15 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaMalloc(&c->via_idx, B * V * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->chi_parts, B * c->chunks * 4 * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->state, B * sizeof(BandState)));
+  CUDA_TRY(c, cudaMalloc(&c->dmax_parts, B * c->chunks * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->rhs, B * 4 * nc * sizeof(double)));
+  const size_t spec_sys = ((B * SPEC_K + 31) / 32) * 32; /* whole warps of (band, trial) systems */
+  CUDA_TRY(c, cudaMalloc(&c->spec.Lf, spec_sys * 4 * nc * HROW * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.dx, spec_sys * 4 * nc * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.T, B * SPEC_K * 4 * nc * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.res, B * SPEC_K * RES_STRIDE * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.need, B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.qmax, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->d_poses, B * nc * 4 * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->d_n, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->d_scene, B * sizeof(int32_t)));
@@ -198,6 +211,10 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kb_bcr_smem_bytes((int)nc, (int)M)));
   CUDA_TRY(c, cudaFuncSetAttribute(k_build_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_g));
+  /* ask for the full shared-memory carveout: occupancy of the tile kernels is shared-memory bound */
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   tebgpu_default_params(&c->params);
   c->have_params = true;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -274,7 +291,7 @@ static DevBatch make_devbatch(tebgpu_ctx* ctx, const TebBatch* bt) {
   d.via = bt->via; d.via_count = bt->via_count; d.vel_start = bt->vel_start; d.vel_goal = bt->vel_goal;
   d.prefer_rotdir = bt->prefer_rotdir;
   d.cost = bt->cost; d.chi2 = bt->chi2; d.status = bt->status; d.lm_iters = bt->lm_iters;
-  d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts;
+  d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts; d.dmax_parts = ctx->dmax_parts; d.rhs = ctx->rhs;
   d.state = ctx->state;
   d.chunks = (bt->n_cap + TP - 1) / TP;
   return d;
@@ -294,7 +311,7 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   const size_t smem_a = ka_smem_bytes(bt->M_cap);
   const size_t smem_b = kb_smem_bytes(bt->n_cap, bt->M_cap);
   const size_t smem_bcr = kb_bcr_smem_bytes(bt->n_cap, bt->M_cap);
-  const bool use_bcr = ctx->solver != 0 && bt->n_cap <= BCR_MAX_POSES && smem_bcr <= 232448 &&
+  const bool use_bcr = ctx->solver == 1 && bt->n_cap <= BCR_MAX_POSES && smem_bcr <= 232448 &&
                        ctx->lim.max_poses <= BCR_MAX_POSES;
   const size_t smem_g = (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle);
   double weight_multiplier = 1.0;
@@ -306,10 +323,19 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
     prof_begin(ctx, st, 2); k_build_graph<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st);
     for (int it = 0; it < args->iterations_innerloop; ++it) {
       prof_begin(ctx, st, 3); k_linearize<<<dim3(db.chunks, B), KA_THREADS, smem_a, st>>>(db, kp); ++launches; prof_end(ctx, st);
-      prof_begin(ctx, st, 4);
-      if (use_bcr) k_lm_step_t<1, KB_BCR_THREADS><<<B, KB_BCR_THREADS, smem_bcr, st>>>(db, kp, it);
-      else k_lm_step_t<0, KB_THREADS><<<B, KB_THREADS, smem_b, st>>>(db, kp, it);
-      ++launches; prof_end(ctx, st);
+      if (ctx->solver == 2) {
+        const int bk = B * SPEC_K;
+        for (int round = 0; round < SPEC_ROUNDS; ++round) {
+          prof_begin(ctx, st, 6); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
+          prof_begin(ctx, st, 7); k_trial_eval<<<(bk + 3) / 4, 128, 0, st>>>(db, kp, ctx->spec, round); ++launches; prof_end(ctx, st);
+          prof_begin(ctx, st, 8); k_decide<<<(B + 3) / 4, 128, 0, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
+        }
+      } else {
+        prof_begin(ctx, st, 4);
+        if (use_bcr) k_lm_step_t<1, KB_BCR_THREADS><<<B, KB_BCR_THREADS, smem_bcr, st>>>(db, kp, it);
+        else k_lm_step_t<0, KB_THREADS><<<B, KB_THREADS, smem_b, st>>>(db, kp, it);
+        ++launches; prof_end(ctx, st);
+      }
     }
     weight_multiplier *= p.weight_adapt_factor; /* optimal_planner.cpp:227 */
   }
@@ -326,21 +352,21 @@ int32_t tebgpu_set_profiling(tebgpu_ctx* ctx, int32_t enable) {
   cudaStreamSynchronize(ctx->stream);
   prof_collect(ctx);
   ctx->profiling = enable != 0;
-  for (int k = 0; k < 6; ++k) { ctx->prof_ms[k] = 0; ctx->prof_cnt[k] = 0; }
+  for (int k = 0; k < 9; ++k) { ctx->prof_ms[k] = 0; ctx->prof_cnt[k] = 0; }
   return TEBGPU_OK;
 }
 
-int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[6], int64_t count_out[6]) {
+int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[9], int64_t count_out[9]) {
   if (!ctx || !ms_out || !count_out) return TEBGPU_ERR_INVALID_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaDeviceSynchronize());
   prof_collect(ctx);
-  for (int k = 0; k < 6; ++k) { ms_out[k] = ctx->prof_ms[k]; count_out[k] = ctx->prof_cnt[k]; ctx->prof_ms[k] = 0; ctx->prof_cnt[k] = 0; }
+  for (int k = 0; k < 9; ++k) { ms_out[k] = ctx->prof_ms[k]; count_out[k] = ctx->prof_cnt[k]; ctx->prof_ms[k] = 0; ctx->prof_cnt[k] = 0; }
   return TEBGPU_OK;
 }
 
 int32_t tebgpu_set_solver(tebgpu_ctx* ctx, int32_t solver) {
-  if (!ctx || solver < 0 || solver > 1) return TEBGPU_ERR_INVALID_ARG;
+  if (!ctx || solver < 0 || solver > 2) return TEBGPU_ERR_INVALID_ARG;
   ctx->solver = solver;
   return TEBGPU_OK;
 }

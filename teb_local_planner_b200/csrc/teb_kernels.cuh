@@ -64,6 +64,8 @@ struct DevBatch {
   double* dyn_t;              /* [B][n_cap]       */
   int32_t* via_idx;           /* [B][V_cap]       */
   double* chi_parts;          /* [B][chunks][4]   */
+  double* rhs;                /* [B][4*n_cap] compact copy of b (coalesced reads in the trial evaluation) */
+  double* dmax_parts;         /* [B][chunks] max |H_rr| over the real rows of the tile (LM lambda init) */
   BandState* state;           /* [B]              */
   int32_t chunks;
 };
@@ -305,7 +307,7 @@ struct KASmem {
   static constexpr int EH = (TP + 2) * 8;
   static constexpr int START = 2 * 7 + 2;
   static constexpr int UN = TP * 9;
-  static constexpr int RED = 4 * (KA_THREADS / 32) + 4;
+  static constexpr int RED = 4 * (KA_THREADS / 32) + 8 + (KA_THREADS / 32);
   static constexpr int STAGE = KA_THREADS * HROW; /* aliases JB..: needs JB+EH+START+UN >= STAGE? no: separate */
 };
 
@@ -658,6 +660,7 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
 #pragma unroll
     for (int k = 0; k < 11; ++k) o[k] = acc[k];
     o[11] = brow;
+    if (p0 + (tid >> 2) < n) db.rhs[(size_t)b * 4 * db.n_cap + 4 * p0 + tid] = brow;
   }
   fence_proxy_async();
   __syncthreads();
@@ -667,24 +670,33 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
     tma_store_1d(gH, sJ, (uint32_t)rows * HROW * 8u);
     tma_store_commit_wait();
   }
+  /* max diagonal of the tile's real rows (computeLambdaInit) */
+  {
+    const int il = tid >> 2, c = tid & 3;
+    const int r = 4 * (p0 + il) + c;
+    double dm = (p0 + il < n && row_is_real(r, n)) ? fabs(acc[0]) : 0.0;
+    dm = warp_max(dm);
+    if ((tid & 31) == 0) sRed[4 * (KA_THREADS / 32) + 8 + (tid >> 5)] = dm;
+  }
   /* chi2 partials of this tile */
   block_sum<4, KA_THREADS / 32>(chi, sRed, sRed + 4 * (KA_THREADS / 32));
   if (tid == 0) {
     double* cp = db.chi_parts + ((size_t)b * db.chunks + blockIdx.x) * 4;
     const double* r = sRed + 4 * (KA_THREADS / 32);
     cp[0] = r[0]; cp[1] = r[1]; cp[2] = r[2]; cp[3] = r[3];
+    double dm = 0;
+    for (int w = 0; w < KA_THREADS / 32; ++w) dm = fmax(dm, sRed[4 * (KA_THREADS / 32) + 8 + w]);
+    db.dmax_parts[(size_t)b * db.chunks + blockIdx.x] = dm;
   }
 }
 
 /* ------------------------------------------------------------------ trial chi2 (residuals only) on a band held in
  * shared memory: sT[n][4]; block-wide, result in out[4] (shared) after the call */
-template <int NTHREADS>
-__device__ __forceinline__ void eval_chi2_parts(const KParams& kp, const DevBatch& db, int b, int n, const double* sT,
-                                                const TebObstacle* so, int M, double* scratch, double* out) {
-  double chi[4] = {0, 0, 0, 0};
-  const double* vs = db.vel_start + 4 * (size_t)b;
-  const double* vg = db.vel_goal + 4 * (size_t)b;
-  for (int i = threadIdx.x; i < n; i += NTHREADS) {
+/* chi2 contributions (residuals only) of everything anchored at pose i of the band stored at sT[n][4]
+ * (shared or global memory): chain edges of segment i, time-optimal edge i, unary edges of pose i */
+__device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db, int b, int i, int n, const double* sT,
+                                          const TebObstacle* so, int M, const double* vs, const double* vg,
+                                          double (&chi)[4]) {
     const double* pa = sT + 4 * i;
     double sa, ca;
     sincos(pa[2], &sa, &ca);
@@ -753,7 +765,15 @@ __device__ __forceinline__ void eval_chi2_parts(const KParams& kp, const DevBatc
     }
     double U[6], ub[3];
     unary_terms(kp, db, b, i, n, pa[0], pa[1], ca, sa, so, M, false, U, ub, chi[0], chi[1]);
-  }
+}
+
+template <int NTHREADS>
+__device__ __forceinline__ void eval_chi2_parts(const KParams& kp, const DevBatch& db, int b, int n, const double* sT,
+                                                const TebObstacle* so, int M, double* scratch, double* out) {
+  double chi[4] = {0, 0, 0, 0};
+  const double* vs = db.vel_start + 4 * (size_t)b;
+  const double* vg = db.vel_goal + 4 * (size_t)b;
+  for (int i = threadIdx.x; i < n; i += NTHREADS) pose_chi2(kp, db, b, i, n, sT, so, M, vs, vg, chi);
   block_sum<4, NTHREADS / 32>(chi, scratch, out);
 }
 
