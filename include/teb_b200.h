@@ -245,6 +245,10 @@ int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx);
 int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* batch, int32_t outer_index,
                             double* Hb_out, double* chi2_out, int32_t device_ptrs);
 
+/* TebOptimalPlanner::computeCurrentCost called OUTSIDE optimizeTEB (optimal_planner.cpp:1041-1094, graph rebuilt with
+ * weight multiplier 1, errors evaluated at the current state): HOST buffers; writes cost[], chi2[], status[]. */
+int32_t tebgpu_compute_cost(tebgpu_ctx* ctx, const TebBatch* batch, const TebOptimizeArgs* args);
+
 /* HomotopyClassPlanner::selectBestTeb (homotopy_class_planner.cpp:564-667) on gathered costs:
  * argmin over cost[i], with cost[last_best] * selection_cost_hysteresis and
  * cost[initial_plan] * selection_prefer_initial_plan (pass -1 for none). Strict '<', first wins.

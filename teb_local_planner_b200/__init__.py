@@ -54,6 +54,8 @@ def load_library(build_if_missing=False):
     L.tebgpu_set_profiling.argtypes = [vp, C.c_int32]
     L.tebgpu_get_kernel_times.restype = C.c_int32
     L.tebgpu_get_kernel_times.argtypes = [vp, C.POINTER(C.c_double * 9), C.POINTER(C.c_int64 * 9)]
+    L.tebgpu_compute_cost.restype = C.c_int32
+    L.tebgpu_compute_cost.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs)]
     L.tebgpu_build_system.restype = C.c_int32
     L.tebgpu_build_system.argtypes = [vp, C.POINTER(abi.TebBatch), C.c_int32, vp, vp, C.c_int32]
     L.tebgpu_select_best.restype = C.c_int32
@@ -97,6 +99,11 @@ class TebGpu:
         """Host-buffer call: hb is an abi.HostBatch, updated in place."""
         bs = hb.struct()
         self._check(self.lib.tebgpu_optimize_batch(self.ctx, C.byref(bs), C.byref(args)), "tebgpu_optimize_batch")
+        return hb
+
+    def compute_cost(self, hb, args):
+        bs = hb.struct()
+        self._check(self.lib.tebgpu_compute_cost(self.ctx, C.byref(bs), C.byref(args)), "tebgpu_compute_cost")
         return hb
 
     def optimize_device(self, batch_struct, args, stream=None):

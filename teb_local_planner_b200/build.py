@@ -11,7 +11,7 @@ DEPS = [os.path.join(CSRC, f) for f in ("teb_cabi.cu", "teb_kernels.cuh", "teb_d
     os.path.join(os.path.dirname(HERE), "include", "teb_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def needs_build():
@@ -35,6 +35,37 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(HERE, "libteb_local_planner_b200.so")
+HOST_TEST = os.path.join(HOST_DIR, "test", "test_dropin")
+HOST_SRCS = [os.path.join(HOST_DIR, "src", f) for f in ("timed_elastic_band.cpp", "optimal_planner.cpp",
+                                                         "homotopy_class_planner.cpp")]
+
+
+def build_host(force=False, verbose=False):
+    """Drop-in C++ classes (TebOptimalPlanner, HomotopyClassPlanner, TimedElasticBand ...) over the C-ABI + their test."""
+    inc = ["-I", os.path.join(os.path.dirname(HERE), "include"), "-I", os.path.join(HOST_DIR, "include")]
+    hdrs = [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(HOST_DIR, "include")) for f in fs]
+    deps = HOST_SRCS + hdrs + [os.path.join(HOST_DIR, "test", "test_dropin.cpp"), LIB]
+    if (not force and os.path.exists(HOST_LIB) and os.path.exists(HOST_TEST)
+            and all(os.path.getmtime(d) <= min(os.path.getmtime(HOST_LIB), os.path.getmtime(HOST_TEST)) for d in deps)):
+        return HOST_LIB
+    gxx = os.environ.get("CXX", "g++")
+    common = [gxx, "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra", "-march=x86-64-v3"] + inc
+    link = ["-L", HERE, "-lteb_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + HERE]
+    cmds = [common + ["-shared", "-o", HOST_LIB] + HOST_SRCS + link,
+            common + ["-o", HOST_TEST, os.path.join(HOST_DIR, "test", "test_dropin.cpp"), "-L", HERE,
+                      "-lteb_local_planner_b200", "-lteb_b200", "-Wl,-rpath," + HERE]]
+    for cmd in cmds:
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("g++ failed building the host drop-in layer")
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     build(force=True, verbose=True)
-    print(LIB)
+    build_host(force=True, verbose=True)
+    print(LIB, HOST_LIB)

@@ -428,6 +428,31 @@ int32_t tebgpu_optimize_batch(tebgpu_ctx* ctx, const TebBatch* bt, const TebOpti
   return TEBGPU_OK;
 }
 
+int32_t tebgpu_compute_cost(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimizeArgs* args) {
+  int32_t rc = check_batch(ctx, bt);
+  if (rc) return rc;
+  if (!args) return TEBGPU_ERR_INVALID_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rc = upload_batch(ctx, bt);
+  if (rc) return rc;
+  TebBatch d = mirror_batch(ctx, bt);
+  cudaStream_t st = ctx->stream;
+  DevBatch db = make_devbatch(ctx, &d);
+  KParams kp = make_kparams(ctx->params, 1.0); /* buildGraph() default weight_multiplier (optimal_planner.h:536) */
+  const int B = bt->B, tb = 128, gb = (B + tb - 1) / tb;
+  k_begin<<<gb, tb, 0, st>>>(db, kp);
+  k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
+  k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(bt->M_cap), st>>>(db, kp);
+  k_cost_only<<<gb, tb, 0, st>>>(db, kp, *args);
+  ctx->launches = 4;
+  CUDA_TRY(ctx, cudaGetLastError());
+  if (bt->cost) CUDA_TRY(ctx, cudaMemcpyAsync(bt->cost, ctx->d_cost, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (bt->chi2) CUDA_TRY(ctx, cudaMemcpyAsync(bt->chi2, ctx->d_chi2, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (bt->status) CUDA_TRY(ctx, cudaMemcpyAsync(bt->status, ctx->d_status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return TEBGPU_OK;
+}
+
 int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* bt, int32_t outer_index, double* Hb_out, double* chi2_out,
                             int32_t device_ptrs) {
   int32_t rc = check_batch(ctx, bt);

@@ -1302,4 +1302,35 @@ __global__ void k_finalize(DevBatch db, KParams kp, TebOptimizeArgs args) {
   if (db.lm_iters) db.lm_iters[b] = st.lm_iters;
 }
 
+/* ------------------------------------------------------------------ k_cost_only (thread per band):
+ * computeCurrentCost on a freshly built graph (optimal_planner.cpp:1045-1051): chi2 at the current state from the
+ * kernel-A tile partials, with the selection scales. */
+__global__ void k_cost_only(DevBatch db, KParams kp, TebOptimizeArgs args) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= db.B) return;
+  const BandState st = db.state[b];
+  double cost = __longlong_as_double(0x7ff0000000000000LL);
+  double chi = 0;
+  if (!st.failed) {
+    const int n = db.n[b];
+    const int chunks_used = (n + TP - 1) / TP;
+    const double* cp = db.chi_parts + (size_t)b * db.chunks * 4;
+    double parts[4] = {0, 0, 0, 0};
+    for (int c = 0; c < chunks_used; ++c)
+      for (int k = 0; k < 4; ++k) parts[k] += cp[4 * c + k];
+    chi = parts[0] + parts[1] + parts[2] + parts[3];
+    cost = 0;
+    if (args.alternative_time_cost) {
+      const double* P = db.poses + (size_t)b * db.n_cap * 4;
+      for (int i = 0; i < n - 1; ++i) cost += P[4 * i + 3];
+    }
+    cost += args.obst_cost_scale * parts[0] + args.viapoint_cost_scale * parts[1] + parts[3];
+    if (!args.alternative_time_cost) cost += parts[2];
+  }
+  if (db.cost) db.cost[b] = cost;
+  if (db.chi2) db.chi2[b] = chi;
+  if (db.status) db.status[b] = st.status;
+  if (db.lm_iters) db.lm_iters[b] = 0;
+}
+
 }  // namespace tebgpu

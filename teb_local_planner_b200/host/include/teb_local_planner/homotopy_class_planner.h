@@ -1,0 +1,84 @@
+/*
+ * homotopy_class_planner.h — drop-in HomotopyClassPlanner: candidate container + ONE batched GPU optimisation of all
+ * candidates + best-candidate selection.
+ *
+ * Mirrors teb_local_planner::HomotopyClassPlanner (include/teb_local_planner/homotopy_class_planner.h:108-560,
+ * src/homotopy_class_planner.cpp): plan() = updateAllTEBs -> exploreEquivalenceClassesAndInitTebs -> via-points ->
+ * optimizeAllTEBs -> selectBestTeb (:107-125). optimizeAllTEBs (:466-493) and selectBestTeb (:564-667) are the
+ * hot-path rows; the graph search / H-signature exploration (graph_search.cpp, h_signature.h) that decides WHICH
+ * candidates exist is out of scope for this round: exploreEquivalenceClassesAndInitTebs keeps
+ * the existing candidates and makes sure at least one band exists; further candidates are seeded by the caller with
+ * addAndInitNewTeb().
+ */
+#ifndef TEB_B200_HOMOTOPY_CLASS_PLANNER_H_
+#define TEB_B200_HOMOTOPY_CLASS_PLANNER_H_
+
+#include <chrono>
+
+#include "teb_local_planner/optimal_planner.h"
+
+namespace teb_local_planner {
+
+class HomotopyClassPlanner : public PlannerInterface {
+ public:
+  HomotopyClassPlanner();
+  HomotopyClassPlanner(const TebConfig& cfg, ObstContainer* obstacles = NULL, TebVisualizationPtr visualization = TebVisualizationPtr(),
+                       const ViaPointContainer* via_points = NULL);
+  virtual ~HomotopyClassPlanner() {}
+  void initialize(const TebConfig& cfg, ObstContainer* obstacles = NULL, TebVisualizationPtr visualization = TebVisualizationPtr(),
+                  const ViaPointContainer* via_points = NULL);
+  void updateRobotModel(RobotFootprintModelPtr robot_model) override { robot_model_ = robot_model; }
+
+  bool plan(const std::vector<geometry_msgs::PoseStamped>& initial_plan, const geometry_msgs::Twist* start_vel = NULL, bool free_goal_vel = false) override;
+  bool plan(const tf::Pose& start, const tf::Pose& goal, const geometry_msgs::Twist* start_vel = NULL, bool free_goal_vel = false) override;
+  bool plan(const PoseSE2& start, const PoseSE2& goal, const geometry_msgs::Twist* start_vel = NULL, bool free_goal_vel = false) override;
+  bool getVelocityCommand(double& vx, double& vy, double& omega, int look_ahead_poses) const override;
+
+  TebOptimalPlannerPtr bestTeb() const { return tebs_.empty() ? TebOptimalPlannerPtr() : tebs_.size() == 1 ? tebs_.front() : best_teb_; }
+  void exploreEquivalenceClassesAndInitTebs(const PoseSE2& start, const PoseSE2& goal, double dist_to_obst,
+                                            const geometry_msgs::Twist* start_vel, bool free_goal_vel = false);
+  /* homotopy_class_planner.cpp:359 (start/goal straight-line init) */
+  TebOptimalPlannerPtr addAndInitNewTeb(const PoseSE2& start, const PoseSE2& goal, const geometry_msgs::Twist* start_velocity,
+                                        bool free_goal_vel = false);
+  /* homotopy_class_planner.cpp:414 (init from a reference path) */
+  TebOptimalPlannerPtr addAndInitNewTeb(const std::vector<geometry_msgs::PoseStamped>& initial_plan,
+                                        const geometry_msgs::Twist* start_velocity, bool free_goal_vel = false);
+  void updateAllTEBs(const PoseSE2* start, const PoseSE2* goal, const geometry_msgs::Twist* start_velocity);
+  void optimizeAllTEBs(int iter_innerloop, int iter_outerloop);
+  TebOptimalPlannerPtr getInitialPlanTEB();
+  TebOptimalPlannerPtr selectBestTeb();
+  void clearPlanner() override;
+  void setPreferredTurningDir(RotType dir) override;
+  const TebOptPlannerContainer& getTrajectoryContainer() const { return tebs_; }
+  bool hasDiverged() const override;
+  void computeCurrentCost(std::vector<double>& cost, double obst_cost_scale = 1.0, double viapoint_cost_scale = 1.0,
+                          bool alternative_time_cost = false);
+  void computeCurrentCost(std::vector<double>& cost, double obst_cost_scale, bool alternative_time_cost) override {
+    computeCurrentCost(cost, obst_cost_scale, 1.0, alternative_time_cost);
+  }
+  int bestTebIdx() const;
+  TebOptPlannerContainer::iterator removeTeb(TebOptimalPlannerPtr& teb);
+  const TebConfig* config() const { return cfg_; }
+  const ObstContainer* obstacles() const { return obstacles_; }
+  bool isInitialized() const { return initialized_; }
+  void setGpuContext(TebGpuContextPtr ctx) { gpu_ = ctx; }
+
+ protected:
+  const TebConfig* cfg_ = nullptr;
+  ObstContainer* obstacles_ = nullptr;
+  const ViaPointContainer* via_points_ = nullptr;
+  TebVisualizationPtr visualization_;
+  TebOptimalPlannerPtr best_teb_;
+  TebOptimalPlannerPtr last_best_teb_;
+  TebOptimalPlannerPtr initial_plan_teb_;
+  RobotFootprintModelPtr robot_model_;
+  const std::vector<geometry_msgs::PoseStamped>* initial_plan_ = nullptr;
+  TebOptPlannerContainer tebs_;
+  std::chrono::steady_clock::time_point last_eq_class_switching_time_;
+  bool initialized_ = false;
+  TebGpuContextPtr gpu_;
+};
+typedef std::shared_ptr<HomotopyClassPlanner> HomotopyClassPlannerPtr;
+
+}  // namespace teb_local_planner
+#endif

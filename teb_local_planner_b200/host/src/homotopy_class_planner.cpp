@@ -1,0 +1,215 @@
+/* homotopy_class_planner.cpp — see include/teb_local_planner/homotopy_class_planner.h. Line references:
+ * src/homotopy_class_planner.cpp of the reference. */
+#include "teb_local_planner/homotopy_class_planner.h"
+
+#include <algorithm>
+#include <limits>
+
+namespace teb_local_planner {
+
+HomotopyClassPlanner::HomotopyClassPlanner() {}
+HomotopyClassPlanner::HomotopyClassPlanner(const TebConfig& cfg, ObstContainer* obstacles, TebVisualizationPtr visual,
+                                           const ViaPointContainer* via_points) {
+  initialize(cfg, obstacles, visual, via_points);
+}
+
+/* :61-78 */
+void HomotopyClassPlanner::initialize(const TebConfig& cfg, ObstContainer* obstacles, TebVisualizationPtr visual,
+                                      const ViaPointContainer* via_points) {
+  cfg_ = &cfg;
+  obstacles_ = obstacles;
+  via_points_ = via_points;
+  visualization_ = visual;
+  last_eq_class_switching_time_ = std::chrono::steady_clock::now();
+  initialized_ = true;
+}
+
+/* :85-96 */
+bool HomotopyClassPlanner::plan(const std::vector<geometry_msgs::PoseStamped>& initial_plan, const geometry_msgs::Twist* start_vel,
+                                bool free_goal_vel) {
+  if (!initialized_ || initial_plan.empty()) return false;
+  initial_plan_ = &initial_plan;
+  PoseSE2 start(initial_plan.front().pose);
+  PoseSE2 goal(initial_plan.back().pose);
+  return plan(start, goal, start_vel, free_goal_vel);
+}
+bool HomotopyClassPlanner::plan(const tf::Pose& start, const tf::Pose& goal, const geometry_msgs::Twist* start_vel, bool free_goal_vel) {
+  PoseSE2 start_pose(start);
+  PoseSE2 goal_pose(goal);
+  return plan(start_pose, goal_pose, start_vel, free_goal_vel);
+}
+
+/* :107-125 */
+bool HomotopyClassPlanner::plan(const PoseSE2& start, const PoseSE2& goal, const geometry_msgs::Twist* start_vel, bool free_goal_vel) {
+  if (!initialized_) return false;
+  updateAllTEBs(&start, &goal, start_vel);
+  exploreEquivalenceClassesAndInitTebs(start, goal, cfg_->obstacles.min_obstacle_dist, start_vel, free_goal_vel);
+  /* updateReferenceTrajectoryViaPoints (:304-335): all candidates, or only the one that follows the initial plan */
+  for (auto& teb : tebs_) {
+    if (cfg_->hcp.viapoints_all_candidates || teb == initial_plan_teb_) teb->setViaPoints(via_points_);
+    else teb->setViaPoints(NULL);
+  }
+  optimizeAllTEBs(cfg_->optim.no_inner_iterations, cfg_->optim.no_outer_iterations);
+  selectBestTeb();
+  initial_plan_ = nullptr;
+  return true;
+}
+
+bool HomotopyClassPlanner::getVelocityCommand(double& vx, double& vy, double& omega, int look_ahead_poses) const {
+  TebOptimalPlannerConstPtr best_teb = bestTeb();
+  if (!best_teb) { vx = 0; vy = 0; omega = 0; return false; }
+  return best_teb->getVelocityCommand(vx, vy, omega, look_ahead_poses);
+}
+
+/* :337-357 — exploration of NEW homotopy classes (graph search + H-signatures) is not part of this round; the
+ * existing candidates are kept and a first band is created from the initial plan or the straight line. */
+void HomotopyClassPlanner::exploreEquivalenceClassesAndInitTebs(const PoseSE2& start, const PoseSE2& goal, double dist_to_obst,
+                                                                const geometry_msgs::Twist* start_vel, bool free_goal_vel) {
+  (void)dist_to_obst;
+  if (initial_plan_ && !initial_plan_teb_) {
+    initial_plan_teb_ = addAndInitNewTeb(*initial_plan_, start_vel, free_goal_vel);
+  }
+  if (tebs_.empty()) addAndInitNewTeb(start, goal, start_vel, free_goal_vel);
+}
+
+/* :359-386 */
+TebOptimalPlannerPtr HomotopyClassPlanner::addAndInitNewTeb(const PoseSE2& start, const PoseSE2& goal,
+                                                            const geometry_msgs::Twist* start_velocity, bool free_goal_vel) {
+  if ((int)tebs_.size() >= cfg_->hcp.max_number_classes) return TebOptimalPlannerPtr();
+  TebOptimalPlannerPtr candidate(new TebOptimalPlanner(*cfg_, obstacles_, visualization_));
+  candidate->setGpuContext(gpu_);
+  if (robot_model_) candidate->updateRobotModel(robot_model_);
+  candidate->teb().initTrajectoryToGoal(start, goal, 0, cfg_->robot.max_vel_x, cfg_->trajectory.min_samples,
+                                        cfg_->trajectory.allow_init_with_backwards_motion);
+  if (start_velocity) candidate->setVelocityStart(*start_velocity);
+  if (free_goal_vel) candidate->setVelocityGoalFree();
+  tebs_.push_back(candidate);
+  return tebs_.back();
+}
+
+/* :414-441 */
+TebOptimalPlannerPtr HomotopyClassPlanner::addAndInitNewTeb(const std::vector<geometry_msgs::PoseStamped>& initial_plan,
+                                                            const geometry_msgs::Twist* start_velocity, bool free_goal_vel) {
+  if ((int)tebs_.size() >= cfg_->hcp.max_number_classes) return TebOptimalPlannerPtr();
+  TebOptimalPlannerPtr candidate(new TebOptimalPlanner(*cfg_, obstacles_, visualization_));
+  candidate->setGpuContext(gpu_);
+  if (robot_model_) candidate->updateRobotModel(robot_model_);
+  candidate->teb().initTrajectoryToGoal(initial_plan, cfg_->robot.max_vel_x, cfg_->robot.max_vel_theta,
+                                        cfg_->trajectory.global_plan_overwrite_orientation, cfg_->trajectory.min_samples,
+                                        cfg_->trajectory.allow_init_with_backwards_motion);
+  if (start_velocity) candidate->setVelocityStart(*start_velocity);
+  if (free_goal_vel) candidate->setVelocityGoalFree();
+  tebs_.push_back(candidate);
+  return tebs_.back();
+}
+
+/* :443-463 */
+void HomotopyClassPlanner::updateAllTEBs(const PoseSE2* start, const PoseSE2* goal, const geometry_msgs::Twist* start_velocity) {
+  if (!tebs_.empty() &&
+      ((goal->position() - tebs_.front()->teb().BackPose().position()).norm() >= cfg_->trajectory.force_reinit_new_goal_dist ||
+       std::fabs(g2o::normalize_theta(goal->theta() - tebs_.front()->teb().BackPose().theta())) >=
+           cfg_->trajectory.force_reinit_new_goal_angular)) {
+    tebs_.clear();
+    initial_plan_teb_.reset();
+  }
+  for (auto& teb : tebs_) {
+    teb->teb().updateAndPruneTEB(*start, *goal);
+    if (start_velocity) teb->setVelocityStart(*start_velocity);
+  }
+}
+
+/* :466-493 — the per-candidate boost::thread fan-out becomes ONE batched launch sequence over all candidates */
+void HomotopyClassPlanner::optimizeAllTEBs(int iter_innerloop, int iter_outerloop) {
+  if (tebs_.empty() || !cfg_->optim.optimization_activate) return;
+  std::vector<TebOptimalPlanner*> all;
+  for (auto& teb : tebs_) all.push_back(teb.get());
+  optimizeTebBatch(*cfg_, all, iter_innerloop, iter_outerloop, true, cfg_->hcp.selection_obst_cost_scale,
+                   cfg_->hcp.selection_viapoint_cost_scale, cfg_->hcp.selection_alternative_time_cost, gpu_);
+}
+
+/* :495-537 (equivalence-class lookup reduced to the stored pointer: no H-signatures in this round) */
+TebOptimalPlannerPtr HomotopyClassPlanner::getInitialPlanTEB() {
+  if (initial_plan_teb_) {
+    if (std::find(tebs_.begin(), tebs_.end(), initial_plan_teb_) != tebs_.end()) return initial_plan_teb_;
+    initial_plan_teb_.reset();
+  }
+  return TebOptimalPlannerPtr();
+}
+
+/* :564-667 */
+TebOptimalPlannerPtr HomotopyClassPlanner::selectBestTeb() {
+  double min_cost = std::numeric_limits<double>::max();
+  double min_cost_last_best = std::numeric_limits<double>::max();
+  double min_cost_initial_plan_teb = std::numeric_limits<double>::max();
+  TebOptimalPlannerPtr initial_plan_teb = getInitialPlanTEB();
+  if (best_teb_ && std::find(tebs_.begin(), tebs_.end(), best_teb_) != tebs_.end()) {
+    min_cost_last_best = best_teb_->getCurrentCost() * cfg_->hcp.selection_cost_hysteresis;
+    last_best_teb_ = best_teb_;
+  } else {
+    last_best_teb_.reset();
+  }
+  if (initial_plan_teb) min_cost_initial_plan_teb = initial_plan_teb->getCurrentCost() * cfg_->hcp.selection_prefer_initial_plan;
+  best_teb_.reset();
+  for (auto it_teb = tebs_.begin(); it_teb != tebs_.end(); ++it_teb) {
+    double teb_cost;
+    if (*it_teb == last_best_teb_) teb_cost = min_cost_last_best;
+    else if (*it_teb == initial_plan_teb) teb_cost = min_cost_initial_plan_teb;
+    else teb_cost = it_teb->get()->getCurrentCost();
+    if (teb_cost < min_cost) {
+      best_teb_ = *it_teb;
+      min_cost = teb_cost;
+    }
+  }
+  if (last_best_teb_ && best_teb_ != last_best_teb_) {
+    auto now = std::chrono::steady_clock::now();
+    if (std::chrono::duration<double>(now - last_eq_class_switching_time_).count() > cfg_->hcp.switching_blocking_period) {
+      last_eq_class_switching_time_ = now;
+    } else {
+      best_teb_ = last_best_teb_;
+    }
+  }
+  return best_teb_;
+}
+
+/* :669-683 */
+int HomotopyClassPlanner::bestTebIdx() const {
+  if (tebs_.size() == 1) return 0;
+  if (!best_teb_) return -1;
+  int idx = 0;
+  for (auto it_teb = tebs_.begin(); it_teb != tebs_.end(); ++it_teb, ++idx)
+    if (*it_teb == best_teb_) return idx;
+  return -1;
+}
+
+TebOptPlannerContainer::iterator HomotopyClassPlanner::removeTeb(TebOptimalPlannerPtr& teb) {
+  for (auto it = tebs_.begin(); it != tebs_.end(); ++it)
+    if (*it == teb) return tebs_.erase(it);
+  return tebs_.end();
+}
+
+void HomotopyClassPlanner::clearPlanner() {
+  tebs_.clear();
+  best_teb_.reset();
+  last_best_teb_.reset();
+  initial_plan_teb_.reset();
+  initial_plan_ = nullptr;
+}
+
+void HomotopyClassPlanner::setPreferredTurningDir(RotType dir) {
+  for (auto& teb : tebs_) teb->setPreferredTurningDir(dir);
+}
+
+bool HomotopyClassPlanner::hasDiverged() const {
+  if (!best_teb_) return false;
+  return best_teb_->hasDiverged();
+}
+
+void HomotopyClassPlanner::computeCurrentCost(std::vector<double>& cost, double obst_cost_scale, double viapoint_cost_scale,
+                                              bool alternative_time_cost) {
+  for (auto& teb : tebs_) {
+    teb->computeCurrentCost(obst_cost_scale, viapoint_cost_scale, alternative_time_cost);
+    cost.push_back(teb->getCurrentCost());
+  }
+}
+
+}  // namespace teb_local_planner

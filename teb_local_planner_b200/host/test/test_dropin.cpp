@@ -1,0 +1,174 @@
+/*
+ * test_dropin.cpp — exercises the drop-in C++ classes the way the reference's own callers do.
+ *   (no argument)  CPU-only checks: the three gtests of the reference (test/teb_basics.cpp:5-68) restated against this
+ *                  TimedElasticBand, cold-start initialisation, config defaults.
+ *   gpu            the test_optim_node scene (src/test_optim_node.cpp:106-117, :168) through TebOptimalPlanner::plan()
+ *                  and three seeded candidates through HomotopyClassPlanner::plan(); prints the results as
+ *                  "KEY v0 v1 ..." lines that tests/test_host_dropin.py compares with the CPU oracle.
+ */
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "teb_local_planner/homotopy_class_planner.h"
+#include "teb_local_planner/optimal_planner.h"
+
+using namespace teb_local_planner;
+
+static int g_fail = 0;
+#define CHECK(cond)                                                          \
+  do {                                                                       \
+    if (!(cond)) { std::printf("CHECK FAILED %s:%d %s\n", __FILE__, __LINE__, #cond); ++g_fail; } \
+  } while (0)
+
+static void check_dts(const TimedElasticBand& teb, double dt, double hyst) {
+  for (int i = 0; i < teb.sizeTimeDiffs(); ++i) {
+    CHECK(teb.TimeDiff(i) <= dt + hyst + 1e-3);
+    CHECK(dt - hyst - 1e-3 <= teb.TimeDiff(i));
+  }
+}
+
+/* TEST(TEBBasic, autoResizeLargeValueAtEnd) test/teb_basics.cpp:5 */
+static void autoResizeLargeValueAtEnd() {
+  double dt = 0.1, dt_hysteresis = dt / 3.;
+  TimedElasticBand teb;
+  teb.addPose(PoseSE2(0., 0., 0.));
+  for (int i = 1; i < 10; ++i) teb.addPoseAndTimeDiff(PoseSE2(i * 1., 0., 0.), dt);
+  teb.addPoseAndTimeDiff(PoseSE2(10., 0., 0.), dt + 2 * dt_hysteresis);
+  teb.autoResize(dt, dt_hysteresis, 3, 100, false);
+  check_dts(teb, dt, dt_hysteresis);
+}
+/* TEST(TEBBasic, autoResizeSmallValueAtEnd) test/teb_basics.cpp:27 */
+static void autoResizeSmallValueAtEnd() {
+  double dt = 0.1, dt_hysteresis = dt / 3.;
+  TimedElasticBand teb;
+  teb.addPose(PoseSE2(0., 0., 0.));
+  for (int i = 1; i < 10; ++i) teb.addPoseAndTimeDiff(PoseSE2(i * 1., 0., 0.), dt);
+  teb.addPoseAndTimeDiff(PoseSE2(10., 0., 0.), dt - 2 * dt_hysteresis);
+  teb.autoResize(dt, dt_hysteresis, 3, 100, false);
+  check_dts(teb, dt, dt_hysteresis);
+}
+/* TEST(TEBBasic, autoResize) test/teb_basics.cpp:49 */
+static void autoResizeMiddle() {
+  double dt = 0.1, dt_hysteresis = dt / 3.;
+  TimedElasticBand teb;
+  teb.addPose(PoseSE2(0., 0., 0.));
+  for (int i = 1; i < 10; ++i) teb.addPoseAndTimeDiff(PoseSE2(i * 1., 0., 0.), dt);
+  teb.TimeDiff(5) = dt + 2 * dt_hysteresis;
+  teb.addPoseAndTimeDiff(PoseSE2(10., 0., 0.), dt - 2 * dt_hysteresis);
+  teb.autoResize(dt, dt_hysteresis, 3, 100, false);
+  check_dts(teb, dt, dt_hysteresis);
+}
+
+static void cpu_checks() {
+  autoResizeLargeValueAtEnd();
+  autoResizeSmallValueAtEnd();
+  autoResizeMiddle();
+  /* cold start of plan(start, goal): start, one forced mid sample, goal (timed_elastic_band.cpp:325-387) */
+  TimedElasticBand teb;
+  CHECK(teb.initTrajectoryToGoal(PoseSE2(-4, 0, 0), PoseSE2(4, 0, 0), 0, 0.4, 3, false));
+  CHECK(teb.sizePoses() == 3 && teb.sizeTimeDiffs() == 2);
+  CHECK(std::fabs(teb.Pose(1).x()) < 1e-15 && std::fabs(teb.TimeDiff(0) - 10.0) < 1e-12);
+  CHECK(!teb.initTrajectoryToGoal(PoseSE2(-4, 0, 0), PoseSE2(4, 0, 0)));  /* already initialised */
+  /* warm start pruning (timed_elastic_band.cpp:555-597) */
+  TimedElasticBand w;
+  w.addPose(0, 0, 0);
+  for (int i = 1; i <= 12; ++i) w.addPoseAndTimeDiff(0.1 * i, 0, 0, 0.25);
+  PoseSE2 ns(0.21, 0, 0), ng(1.3, 0, 0);
+  w.updateAndPruneTEB(ns, ng, 3);
+  CHECK(w.sizePoses() == 11 && std::fabs(w.Pose(0).x() - 0.21) < 1e-15 && std::fabs(w.BackPose().x() - 1.3) < 1e-15);
+  CHECK(std::fabs(w.Pose(1).x() - 0.3) < 1e-12);
+  /* config defaults == C-ABI defaults */
+  TebConfig cfg;
+  TebParams a = cfg.toParams(), b;
+  tebgpu_default_params(&b);
+  CHECK(std::memcmp(&a, &b, sizeof(TebParams)) == 0);
+  PointObstacle po(1, 2);
+  CHECK(!po.isDynamic());
+  po.setCentroidVelocity(Eigen::Vector2d(0.1, 0));
+  CHECK(po.isDynamic() && po.toRow().dynamic == 1);
+  TwoCirclesRobotFootprint fp(0.3, 0.2, 0.2, 0.25);
+  CircularObstacle co(2, 0, 0.5);
+  CHECK(std::fabs(fp.calculateDistance(PoseSE2(0, 0, 0), &co) - (2 - 0.3 - 0.5 - 0.2)) < 1e-12);
+}
+
+static void print_band(const char* key, const TimedElasticBand& teb) {
+  std::printf("%s_N %d\n", key, teb.sizePoses());
+  for (int i = 0; i < teb.sizePoses(); ++i)
+    std::printf("%s_POSE %d %.17g %.17g %.17g %.17g\n", key, i, teb.Pose(i).x(), teb.Pose(i).y(), teb.Pose(i).theta(),
+                i < teb.sizeTimeDiffs() ? teb.TimeDiff(i) : 0.0);
+}
+
+static std::vector<geometry_msgs::PoseStamped> sine_plan(double amp, int m) {
+  std::vector<geometry_msgs::PoseStamped> plan(m);
+  for (int i = 0; i < m; ++i) {
+    double s = (double)i / (m - 1);
+    plan[i].pose.position.x = -4 + 8 * s;
+    plan[i].pose.position.y = amp * std::sin(M_PI * s);
+    plan[i].pose.orientation = tf::createQuaternionFromYaw(0);
+  }
+  return plan;
+}
+
+static int gpu_checks() {
+  /* ---- test_optim_node scene: TebOptimalPlanner::plan(start, goal) twice (cold start, then warm start) */
+  TebConfig cfg;
+  ObstContainer obst;
+  obst.push_back(ObstaclePtr(new PointObstacle(-3, 1)));
+  obst.push_back(ObstaclePtr(new PointObstacle(6, 2)));
+  obst.push_back(ObstaclePtr(new PointObstacle(0, 0.1)));
+  obst[0]->setCentroidVelocity(Eigen::Vector2d(0.1, -0.3));
+  obst[1]->setCentroidVelocity(Eigen::Vector2d(-0.3, -0.2));
+  ViaPointContainer via;
+  TebOptimalPlanner planner(cfg, &obst, TebVisualizationPtr(), &via);
+  bool ok = planner.plan(PoseSE2(-4, 0, 0), PoseSE2(4, 0, 0));
+  std::printf("SINGLE_OK %d\nSINGLE_STATUS %d\n", ok ? 1 : 0, planner.lastStatus());
+  print_band("SINGLE", planner.teb());
+  double vx, vy, om;
+  CHECK(planner.getVelocityCommand(vx, vy, om, 1));
+  std::printf("SINGLE_CMD %.17g %.17g %.17g\n", vx, vy, om);
+  planner.computeCurrentCost(1.0, 1.0, false);
+  std::printf("SINGLE_COST %.17g\n", planner.getCurrentCost());
+  geometry_msgs::Twist v0;
+  v0.linear.x = vx;
+  v0.angular.z = om;
+  ok = planner.plan(PoseSE2(-3.9, 0.01, 0.02), PoseSE2(4, 0, 0), &v0);
+  std::printf("WARM_OK %d\n", ok ? 1 : 0);
+  print_band("WARM", planner.teb());
+
+  /* ---- HomotopyClassPlanner: three seeded candidates, one batched optimisation, selection */
+  TebConfig hcfg;
+  hcfg.obstacles.include_dynamic_obstacles = false;
+  ObstContainer hob;
+  hob.push_back(ObstaclePtr(new PointObstacle(0, 0.1)));
+  hob.push_back(ObstaclePtr(new PointObstacle(-1.5, -0.4)));
+  hob.push_back(ObstaclePtr(new CircularObstacle(2, 0.6, 0.2)));
+  HomotopyClassPlanner hcp(hcfg, &hob);
+  auto p0 = sine_plan(0.0, 21), p1 = sine_plan(1.2, 21), p2 = sine_plan(-1.0, 21);
+  hcp.addAndInitNewTeb(p1, NULL);
+  hcp.addAndInitNewTeb(p2, NULL);
+  ok = hcp.plan(p0, NULL);  /* the initial-plan candidate is created by exploreEquivalenceClassesAndInitTebs */
+  std::printf("HCP_OK %d\nHCP_NUM %d\nHCP_BEST %d\n", ok ? 1 : 0, (int)hcp.getTrajectoryContainer().size(), hcp.bestTebIdx());
+  int k = 0;
+  for (auto& t : hcp.getTrajectoryContainer()) {
+    std::printf("HCP_COST %d %.17g\n", k, t->getCurrentCost());
+    char key[32];
+    std::snprintf(key, sizeof(key), "HCP%d", k);
+    print_band(key, t->teb());
+    ++k;
+  }
+  CHECK(hcp.bestTeb() != nullptr);
+  CHECK(hcp.getVelocityCommand(vx, vy, om, 1));
+  /* second cycle: hysteresis path of selectBestTeb + warm start of all candidates */
+  ok = hcp.plan(PoseSE2(-3.95, 0, 0), PoseSE2(4, 0, 0), NULL);
+  std::printf("HCP2_OK %d\nHCP2_BEST %d\n", ok ? 1 : 0, hcp.bestTebIdx());
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  cpu_checks();
+  if (argc > 1 && std::string(argv[1]) == "gpu") gpu_checks();
+  std::printf("RESULT %s (%d failed checks)\n", g_fail ? "FAIL" : "PASS", g_fail);
+  return g_fail ? 1 : 0;
+}

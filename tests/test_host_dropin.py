@@ -1,0 +1,146 @@
+"""The drop-in C++ classes (TebOptimalPlanner / HomotopyClassPlanner / TimedElasticBand) driven by their C++ test
+program teb_local_planner_b200/host/test/test_dropin: CPU checks always, the GPU scenes under -m gpu, where the printed
+bands are compared with the CPU oracle fed with the same initialisation logic restated in Python."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from teb_local_planner_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "teb_local_planner_b200", "host", "test", "test_dropin")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    from teb_local_planner_b200 import build as b
+    try:
+        b.build()
+        b.build_host()
+    except Exception:
+        if not os.path.exists(EXE):
+            raise
+    return EXE
+
+
+def test_dropin_cpu_checks(exe):
+    """test/teb_basics.cpp gtests on the drop-in TimedElasticBand, cold/warm start plumbing, config defaults"""
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "RESULT PASS" in out.stdout, out.stdout + out.stderr
+
+
+def _parse(stdout):
+    vals, bands = {}, {}
+    for ln in stdout.splitlines():
+        f = ln.split()
+        if not f:
+            continue
+        if f[0].endswith("_POSE"):
+            bands.setdefault(f[0][:-5], []).append([float(x) for x in f[2:6]])
+        else:
+            vals.setdefault(f[0], []).append(f[1:])
+    return vals, {k: np.array(v) for k, v in bands.items()}
+
+
+def _nt(t):
+    return (t + math.pi) % (2 * math.pi) - math.pi if not (-math.pi <= t < math.pi) else t
+
+
+def _init_from_plan(plan, max_vel_x, max_vel_theta):
+    """initTrajectoryToGoal(plan, ..., estimate_orient=True) (timed_elastic_band.cpp:389-452)"""
+    def est(a, b):
+        dt = math.hypot(b[0] - a[0], b[1] - a[1]) / max_vel_x
+        return max(dt, abs(_nt(b[2] - a[2])) / max_vel_theta)
+    rec = [[plan[0][0], plan[0][1], plan[0][2], 0.0]]
+    for i in range(1, len(plan) - 1):
+        yaw = math.atan2(plan[i + 1][1] - plan[i][1], plan[i + 1][0] - plan[i][0])
+        p = [plan[i][0], plan[i][1], yaw, 0.0]
+        rec[-1][3] = est(rec[-1], p)
+        rec.append(p)
+    g = [plan[-1][0], plan[-1][1], plan[-1][2], 0.0]
+    rec[-1][3] = est(rec[-1], g)
+    rec.append(g)
+    return np.array(rec)
+
+
+def _prune(rec, new_start, new_goal, min_samples=3):
+    """updateAndPruneTEB (timed_elastic_band.cpp:555-597)"""
+    rec = rec.copy()
+    n = len(rec)
+    d_cache = math.hypot(new_start[0] - rec[0, 0], new_start[1] - rec[0, 1])
+    nearest = 0
+    for i in range(1, min(n - min_samples, 10) + 1):
+        d = math.hypot(new_start[0] - rec[i, 0], new_start[1] - rec[i, 1])
+        if d < d_cache:
+            d_cache, nearest = d, i
+        else:
+            break
+    if nearest > 0:
+        # deletePoses(1, nearest) / deleteTimeDiffs(1, nearest): pose 0 keeps timediff 0
+        keep = np.concatenate([rec[:1], rec[1 + nearest:]])
+        rec = keep
+    rec[0, :3] = new_start
+    rec[-1, :3] = new_goal
+    return rec
+
+
+@pytest.mark.gpu
+def test_dropin_gpu_scenes_match_oracle(exe, oracle):
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "RESULT PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    vals, bands = _parse(out.stdout)
+    # ---- test_optim_node scene through TebOptimalPlanner::plan(start, goal) (cold start + autoResize from 3 poses)
+    p = abi.default_params()
+    obst = np.zeros(3, abi.OBST_DTYPE)
+    obst["x"], obst["y"] = [-3.0, 6.0, 0.0], [1.0, 2.0, 0.1]
+    obst["vx"], obst["vy"] = [0.1, -0.3, 0.0], [-0.3, -0.2, 0.0]
+    obst["dynamic"] = [1, 1, 0]
+    rec0 = oracle.init_trajectory([-4, 0, 0], [4, 0, 0], 0.0, p.max_vel_x, p.min_samples)
+    ref, _, st = oracle.optimize_band(p, rec0, len(rec0), obst, args=abi.make_args(5, 4, False), jac_mode=oracle.JAC_ANALYTIC,
+                                      n_cap=512)
+    got = bands["SINGLE"]
+    assert vals["SINGLE_OK"][0][0] == "1" and int(vals["SINGLE_STATUS"][0][0]) & abi.TEB_STATUS_OPTIMIZED
+    assert len(got) == len(ref) and len(got) > 20          # autoResize grew the 3-pose cold start
+    assert np.abs(got - ref).max() < 1e-6
+    # computeCurrentCost outside optimizeTEB = chi2 of the freshly built graph at the final state, multiplier 1
+    _, _, chi2 = oracle.build_system(p, ref, len(ref), obst, weight_multiplier=1.0, jac_mode=oracle.JAC_ANALYTIC)
+    assert abs(float(vals["SINGLE_COST"][0][0]) - chi2) <= 1e-6 * max(chi2, 1.0)
+    # getVelocityCommand (optimal_planner.cpp:1136-1172) on the optimised band
+    vx, vy, om = (float(x) for x in vals["SINGLE_CMD"][0])
+    dt0 = ref[0, 3]
+    dx, dy = ref[1, 0] - ref[0, 0], ref[1, 1] - ref[0, 1]
+    sgn = np.sign(dx * math.cos(ref[0, 2]) + dy * math.sin(ref[0, 2]))
+    assert abs(vx - sgn * math.hypot(dx, dy) / dt0) < 1e-6 and vy == 0 and abs(om - _nt(ref[1, 2] - ref[0, 2]) / dt0) < 1e-6
+    # warm start: prune + new start + start velocity
+    w0 = _prune(ref, [-3.9, 0.01, 0.02], [4, 0, 0])
+    wref, _, _ = oracle.optimize_band(p, w0, len(w0), obst, vel_start=[vx, 0, om, 1.0], args=abi.make_args(5, 4, False),
+                                      jac_mode=oracle.JAC_ANALYTIC, n_cap=512)
+    wgot = bands["WARM"]
+    assert len(wgot) == len(wref) and np.abs(wgot - wref).max() < 1e-6
+    # ---- HomotopyClassPlanner: 3 candidates optimised in one batch, costs with the selection scales, selectBestTeb
+    hp = abi.default_params()
+    hp.include_dynamic_obstacles = 0
+    hob = np.zeros(3, abi.OBST_DTYPE)
+    hob["x"], hob["y"], hob["radius"] = [0.0, -1.5, 2.0], [0.1, -0.4, 0.6], [0.0, 0.0, 0.2]
+    hob["type"] = [0, 0, 1]
+    plans = []
+    for amp in (1.2, -1.0, 0.0):     # candidate order in the container: two seeded, then the initial plan
+        s = np.linspace(0, 1, 21)
+        plans.append(np.stack([-4 + 8 * s, amp * np.sin(np.pi * s), np.zeros(21)], axis=1))
+    args = abi.make_args(5, 4, True, hp.selection_obst_cost_scale, hp.selection_viapoint_cost_scale, False)
+    costs = []
+    assert vals["HCP_NUM"][0][0] == "3"
+    for k, plan in enumerate(plans):
+        r0 = _init_from_plan(plan, hp.max_vel_x, hp.max_vel_theta)
+        ref_k, cost_k, _ = oracle.optimize_band(hp, r0, len(r0), hob, args=args, jac_mode=oracle.JAC_ANALYTIC, n_cap=512)
+        got_k = bands[f"HCP{k}"]
+        assert len(got_k) == len(ref_k) and np.abs(got_k - ref_k).max() < 1e-6
+        gcost = float([v for v in vals["HCP_COST"] if int(v[0]) == k][0][1])
+        assert abs(gcost - cost_k) <= 1e-6 * max(abs(cost_k), 1.0)
+        costs.append(cost_k)
+    from teb_local_planner_b200 import distributed as D
+    assert int(vals["HCP_BEST"][0][0]) == D.select_best(costs, -1, 2, hp.selection_cost_hysteresis, hp.selection_prefer_initial_plan)
+    assert vals["HCP2_OK"][0][0] == "1" and int(vals["HCP2_BEST"][0][0]) in (0, 1, 2)
