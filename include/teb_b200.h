@@ -41,6 +41,7 @@ extern "C" {
 #define TEB_STATUS_NONFINITE       8   /* non-finite chi2 / lambda encountered                      */
 #define TEB_STATUS_TERMINATED     16   /* LM returned Terminate in the last optimizeGraph call      */
 #define TEB_STATUS_DISABLED       32   /* optimization_activate == false / max_vel_x < 0.01          */
+#define TEB_STATUS_CAPACITY       64   /* autoResize needed more than n_cap poses: band left unoptimised */
 
 enum { TEB_FOOTPRINT_POINT = 0, TEB_FOOTPRINT_CIRCULAR = 1, TEB_FOOTPRINT_TWO_CIRCLES = 2 };
 enum { TEB_OBST_POINT = 0, TEB_OBST_CIRCULAR = 1 };

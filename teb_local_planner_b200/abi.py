@@ -20,6 +20,7 @@ TEB_STATUS_CHOL_FAILED = 4
 TEB_STATUS_NONFINITE = 8
 TEB_STATUS_TERMINATED = 16
 TEB_STATUS_DISABLED = 32
+TEB_STATUS_CAPACITY = 64
 
 TEB_FOOTPRINT_POINT, TEB_FOOTPRINT_CIRCULAR, TEB_FOOTPRINT_TWO_CIRCLES = 0, 1, 2
 TEB_OBST_POINT, TEB_OBST_CIRCULAR = 0, 1

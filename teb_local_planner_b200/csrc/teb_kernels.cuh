@@ -128,7 +128,7 @@ __global__ void k_auto_resize(DevBatch db, KParams kp) {
   int n = db.n[b];
   int nn = teb_auto_resize_records(db.poses + (size_t)b * db.n_cap * 4, n, db.n_cap, kp.p.dt_ref, kp.p.dt_hysteresis,
                                    kp.p.min_samples, kp.p.max_samples, fast_mode);
-  if (nn < 0) { db.state[b].failed = 1; db.state[b].status |= TEB_STATUS_TOO_FEW_POSES; return; }
+  if (nn < 0) { db.state[b].failed = 1; db.state[b].status |= TEB_STATUS_CAPACITY; return; }
   db.n[b] = nn;
 }
 
@@ -317,7 +317,7 @@ __host__ __device__ inline size_t ka_smem_bytes(int M_cap) {
   return (d + jb) * sizeof(double) + (size_t)M_cap * sizeof(TebObstacle) + 64;
 }
 
-__global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams kp) {
+__global__ void __launch_bounds__(KA_THREADS, 3) k_linearize(DevBatch db, KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = blockIdx.y;
   const BandState* st = &db.state[b];
@@ -362,7 +362,10 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
   for (int k = tid; k < KASmem::EH + KASmem::START; k += KA_THREADS) sE[k] = 0.0;
   mbar_wait(bar, 0);
 
-  /* stage 1: sin/cos per staged pose */
+  double chi[4] = {0, 0, 0, 0}; /* obstacles, via, time-optimal, other */
+
+  /* stage 1 (warps 0-2): sin/cos of every staged pose and the derivative bundle of the segment that starts there
+   * (slot j <-> pose / segment p0-2+j); stage 1' (warps 6-7, concurrently): unary terms of the tile's poses */
   if (tid < TP + 4) {
     const int i = p0 - 2 + tid;
     if (i >= lo && i < hi) {
@@ -370,43 +373,60 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
       sincos(sP[4 * tid + 2], &sn, &cs);
       sSC[2 * tid] = cs;
       sSC[2 * tid + 1] = sn;
-    }
-  }
-  __syncthreads();
-
-  /* stage 2: segment bundles, slot j <-> segment (p0-2+j) between poses a and a+1 */
-  if (tid < TP + 3) {
-    const int a = p0 - 2 + tid;
-    if (a >= 0 && a + 1 < hi && a <= n - 2) {
-      const double* pa = sP + 4 * tid;
-      const double* pb = pa + 4;
-      SegDer sd = seg_derivs(kp, pa[0], pa[1], pa[2], sSC[2 * tid], sSC[2 * tid + 1], pb[0], pb[1], pb[2], pa[3]);
-      double* q = sSeg + 9 * tid;
-      q[0] = sd.v; q[1] = sd.w; q[2] = sd.idt;
+      if (tid < TP + 3 && i + 1 < hi && i <= n - 2) {
+        const double* pa = sP + 4 * tid;
+        const double* pb = pa + 4;
+        SegDer sd = seg_derivs(kp, pa[0], pa[1], pa[2], cs, sn, pb[0], pb[1], pb[2], pa[3]);
+        double* q = sSeg + 9 * tid;
+        q[0] = sd.v; q[1] = sd.w; q[2] = sd.idt;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) q[3 + k] = sd.dv[k];
+        for (int k = 0; k < 6; ++k) q[3 + k] = sd.dv[k];
+      }
+    }
+  }
+  {
+    const int il = tid - (KA_THREADS - TP); /* last TP threads */
+    if (il >= 0) {
+      const int i = p0 + il;
+      double U[6] = {0, 0, 0, 0, 0, 0}, ub[3] = {0, 0, 0};
+      if (i < n) {
+        const int j = il + 2;
+        double sn = 0, cs = 1;
+        if (kp.p.footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
+        unary_terms(kp, db, b, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
+        if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
+          const double dt = sP[4 * j + 3];
+          chi[2] += kp.p.weight_optimaltime * dt * dt;
+        }
+      }
+      double* u = sU + 9 * il;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) u[k] = U[k];
+      u[6] = ub[0]; u[7] = ub[1]; u[8] = ub[2];
     }
   }
   __syncthreads();
 
-  double chi[4] = {0, 0, 0, 0}; /* obstacles, via, time-optimal, other */
 
   /* stage 3a: chain edges anchored at a (EdgeVelocity, EdgeKinematics*, EdgeShortestPath, EdgePreferRotDir,
    * EdgeAcceleration / Start / Goal) -> sqrt(weight)-scaled Jacobian rows over the columns 4a .. 4a+10 */
-  if (tid < TP + 2) {
-    const int a = p0 - 2 + tid;
+  /* group 0 (warps 0-2): velocity / kinematics / shortest-path / rotdir rows; group 1 (warps 3-5): acceleration rows */
+  const int part = (tid < TP + 2) ? 0 : ((tid >= 96 && tid < 96 + TP + 2) ? 1 : -1);
+  if (part >= 0) {
+    const int at = part == 0 ? tid : tid - 96; /* anchor slot */
+    const int a = p0 - 2 + at;
     if (a >= 0 && a <= n - 2) {
-      double* J = sJ + (size_t)tid * JSTRIDE; /* rows 0..5: 7 columns, rows 6,7: 11 columns at offset 42 */
-      double* eh = sE + 8 * tid;
-      const double* pa = sP + 4 * tid;
+      double* J = sJ + (size_t)at * JSTRIDE; /* rows 0..5: 7 columns, rows 6,7: 11 columns at offset 42 */
+      double* eh = sE + 8 * at;
+      const double* pa = sP + 4 * at;
       const double* pb = pa + 4;
-      const double ca = sSC[2 * tid], sa = sSC[2 * tid + 1], cb = sSC[2 * tid + 2], sb = sSC[2 * tid + 3];
-      const double* q1 = sSeg + 9 * tid;
+      const double ca = sSC[2 * at], sa = sSC[2 * at + 1], cb = sSC[2 * at + 2], sb = sSC[2 * at + 3];
+      const double* q1 = sSeg + 9 * at;
       const double v1 = q1[0], w1 = q1[1], idt1 = q1[2];
       const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
       const bool fa = (a == 0), fb = (a + 1 == n - 1);
       double csum = 0;
-      if (kp.has_vel) { /* EdgeVelocity edge_velocity.h:113-114 */
+      if (part == 0 && kp.has_vel) { /* EdgeVelocity edge_velocity.h:113-114 */
         double s0, s1;
         const double e0 = pen_interval2(v1, -kp.p.max_vel_x_backwards, kp.p.max_vel_x, kp.p.penalty_epsilon, s0);
         const double e1 = pen_interval(w1, kp.p.max_vel_theta, kp.p.penalty_epsilon, s1);
@@ -416,7 +436,7 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
         J[7 + 2] = -k1 * idt1; J[7 + 3] = -k1 * w1 * idt1; J[7 + 6] = k1 * idt1;
         eh[0] = kp.sw_vel_x * e0; eh[1] = kp.sw_vel_th * e1;
       }
-      if (kp.has_kin) { /* EdgeKinematicsDiffDrive / Carlike edge_kinematics.h:94-101, :118-148, :203-215 */
+      if (part == 0 && kp.has_kin) { /* EdgeKinematicsDiffDrive / Carlike edge_kinematics.h:94-101, :118-148, :203-215 */
         const double A = (ca + cb) * dy - (sa + sb) * dx;
         const double sA = sgn(A) * kp.sw_kin_nh;
         double* R = J + 14;
@@ -458,7 +478,7 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
           }
         }
       }
-      if (kp.has_sp) { /* EdgeShortestPath edge_shortest_path.h:78 */
+      if (part == 0 && kp.has_sp) { /* EdgeShortestPath edge_shortest_path.h:78 */
         const double nrm = sqrt(dx * dx + dy * dy);
         const double inr = nrm > 0 ? 1.0 / nrm : 0.0;
         double* R = J + 28;
@@ -466,7 +486,7 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
         R[4] = kp.sw_sp * dx * inr; R[5] = kp.sw_sp * dy * inr;
         eh[4] = kp.sw_sp * nrm;
       }
-      if (kp.has_rot && a < 3) { /* EdgePreferRotDir edge_prefer_rotdir.h:85, first three pairs optimal_planner.cpp:983 */
+      if (part == 0 && kp.has_rot && a < 3) { /* EdgePreferRotDir edge_prefer_rotdir.h:85, first three pairs optimal_planner.cpp:983 */
         const int rd = db.prefer_rotdir ? db.prefer_rotdir[b] : 0;
         if (rd == TEB_ROTDIR_LEFT || rd == TEB_ROTDIR_RIGHT) {
           const double meas = (rd == TEB_ROTDIR_LEFT) ? 1.0 : -1.0;
@@ -478,7 +498,7 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
           eh[5] = kp.sw_rot * e0;
         }
       }
-      if (kp.has_acc) {
+      if (part == 1 && kp.has_acc) {
         double* R0 = J + 42;
         double* R1 = J + 53;
         if (a <= n - 3) { /* EdgeAcceleration edge_acceleration.h:134-145 */
@@ -545,44 +565,33 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
       }
       /* columns of fixed poses carry no unknowns (g2o skips fixed vertices) */
       if (fa) {
+        if (part == 0) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { J[7 * k] = 0; J[7 * k + 1] = 0; J[7 * k + 2] = 0; }
-        J[42] = J[43] = J[44] = 0; J[53] = J[54] = J[55] = 0;
+          for (int k = 0; k < 6; ++k) { J[7 * k] = 0; J[7 * k + 1] = 0; J[7 * k + 2] = 0; }
+        } else {
+          J[42] = J[43] = J[44] = 0; J[53] = J[54] = J[55] = 0;
+        }
       }
       if (fb) {
+        if (part == 0) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { J[7 * k + 4] = 0; J[7 * k + 5] = 0; J[7 * k + 6] = 0; }
-        J[46] = J[47] = J[48] = 0; J[57] = J[58] = J[59] = 0;
+          for (int k = 0; k < 6; ++k) { J[7 * k + 4] = 0; J[7 * k + 5] = 0; J[7 * k + 6] = 0; }
+        } else {
+          J[46] = J[47] = J[48] = 0; J[57] = J[58] = J[59] = 0;
+        }
       }
       if (a >= p0) {
+        if (part == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) csum += eh[k] * eh[k];
+          for (int k = 0; k < 6; ++k) csum += eh[k] * eh[k];
+        } else {
+          csum += eh[6] * eh[6] + eh[7] * eh[7];
+        }
         chi[3] += csum;
       }
     }
   }
 
-  /* stage 3b: unary terms of pose i (threads TP+2 .. 2TP+1 so that they overlap with the chain warps) */
-  {
-    const int il = tid - (KA_THREADS - TP); /* last TP threads */
-    if (il >= 0) {
-      const int i = p0 + il;
-      double U[6] = {0, 0, 0, 0, 0, 0}, ub[3] = {0, 0, 0};
-      if (i < n) {
-        const int j = il + 2;
-        unary_terms(kp, db, b, i, n, sP[4 * j], sP[4 * j + 1], sSC[2 * j], sSC[2 * j + 1], so, M, true, U, ub, chi[0],
-                    chi[1]);
-        if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
-          const double dt = sP[4 * j + 3];
-          chi[2] += kp.p.weight_optimaltime * dt * dt;
-        }
-      }
-      double* u = sU + 9 * il;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) u[k] = U[k];
-      u[6] = ub[0]; u[7] = ub[1]; u[8] = ub[2];
-    }
-  }
   __syncthreads();
 
   /* stage 4: one thread per band row r = 4i + c gathers J^T J over the (<= 3) anchors that touch it */
@@ -694,17 +703,30 @@ __global__ void __launch_bounds__(KA_THREADS) k_linearize(DevBatch db, KParams k
  * shared memory: sT[n][4]; block-wide, result in out[4] (shared) after the call */
 /* chi2 contributions (residuals only) of everything anchored at pose i of the band stored at sT[n][4]
  * (shared or global memory): chain edges of segment i, time-optimal edge i, unary edges of pose i */
+/* Carry between consecutive poses of one thread's chunk: sin/cos of the next pose and the (v, omega) of the next
+ * segment are produced while evaluating pose i and are exactly what pose i+1 needs first. */
+struct ChainCarry {
+  double ca, sa;
+  SegVal s;
+  bool has_cs, has_seg;
+};
+
 __device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db, int b, int i, int n, const double* sT,
                                           const TebObstacle* so, int M, const double* vs, const double* vg,
-                                          double (&chi)[4]) {
+                                          double (&chi)[4], ChainCarry& cy) {
     const double* pa = sT + 4 * i;
     double sa, ca;
-    sincos(pa[2], &sa, &ca);
+    if (cy.has_cs) { sa = cy.sa; ca = cy.ca; }
+    else sincos(pa[2], &sa, &ca);
+    cy.has_cs = false;
+    const bool had_seg = cy.has_seg;
+    cy.has_seg = false;
     if (i <= n - 2) {
       const double* pb = pa + 4;
       double sb, cb;
       sincos(pb[2], &sb, &cb);
-      const SegVal s1 = seg_value(kp, pa[0], pa[1], pa[2], ca, sa, pb[0], pb[1], pb[2], pa[3]);
+      cy.ca = cb; cy.sa = sb; cy.has_cs = true;
+      const SegVal s1 = had_seg ? cy.s : seg_value(kp, pa[0], pa[1], pa[2], ca, sa, pb[0], pb[1], pb[2], pa[3]);
       const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
       double sl, csum = 0;
       if (kp.has_vel) {
@@ -745,6 +767,7 @@ __device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db,
         if (i <= n - 3) {
           const double* pc = pb + 4;
           const SegVal s2 = seg_value(kp, pb[0], pb[1], pb[2], cb, sb, pc[0], pc[1], pc[2], pb[3]);
+          cy.s = s2; cy.has_seg = true;
           const double iT = 1.0 / (pa[3] + pb[3]);
           const double e0 = kp.sw_acc_x * pen_interval((s2.v - s1.v) * 2 * iT, kp.p.acc_lim_x, kp.p.penalty_epsilon, sl);
           const double e1 = kp.sw_acc_th * pen_interval((s2.w - s1.w) * 2 * iT, kp.p.acc_lim_theta, kp.p.penalty_epsilon, sl);
@@ -773,7 +796,11 @@ __device__ __forceinline__ void eval_chi2_parts(const KParams& kp, const DevBatc
   double chi[4] = {0, 0, 0, 0};
   const double* vs = db.vel_start + 4 * (size_t)b;
   const double* vg = db.vel_goal + 4 * (size_t)b;
-  for (int i = threadIdx.x; i < n; i += NTHREADS) pose_chi2(kp, db, b, i, n, sT, so, M, vs, vg, chi);
+  for (int i = threadIdx.x; i < n; i += NTHREADS) {
+    ChainCarry cy;
+    cy.has_cs = false; cy.has_seg = false;
+    pose_chi2(kp, db, b, i, n, sT, so, M, vs, vg, chi, cy);
+  }
   block_sum<4, NTHREADS / 32>(chi, scratch, out);
 }
 

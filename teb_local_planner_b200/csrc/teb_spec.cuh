@@ -253,7 +253,15 @@ __global__ void __launch_bounds__(128) k_trial_eval(DevBatch db, KParams kp, Spe
   const double* vs = db.vel_start + 4 * (size_t)b;
   const double* vg = db.vel_goal + 4 * (size_t)b;
   double chi[4] = {0, 0, 0, 0};
-  for (int i = lane; i < n; i += 32) pose_chi2(kp, db, b, i, n, gT, so, M, vs, vg, chi);
+  {
+    /* contiguous chunk per lane: sin/cos and segment velocities are carried from pose to pose instead of being
+     * recomputed by the neighbour (5/8 of the transcendental work of a strided assignment at 4 poses per lane) */
+    const int per = (n + 31) >> 5;
+    const int i0 = lane * per, i1 = min(i0 + per, n);
+    ChainCarry cy;
+    cy.has_cs = false; cy.has_seg = false;
+    for (int i = i0; i < i1; ++i) pose_chi2(kp, db, b, i, n, gT, so, M, vs, vg, chi, cy);
+  }
 #pragma unroll
   for (int c = 0; c < 4; ++c) chi[c] = warp_sum(chi[c]);
   sc = warp_sum(sc);

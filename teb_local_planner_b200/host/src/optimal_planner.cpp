@@ -165,7 +165,7 @@ bool TebOptimalPlanner::runBatch(const TebConfig& cfg, const std::vector<TebOpti
     if (pl->via_points_) V_max = std::max(V_max, (int)pl->via_points_->size());
   }
   int n_cap = n_max;
-  if (cfg.trajectory.teb_autosize && !cost_only) n_cap = std::min(512, std::max(2 * n_max + 8, 64));
+  if (cfg.trajectory.teb_autosize && !cost_only) n_cap = std::min(512, std::max(cfg.trajectory.max_samples + 1, n_max));
   n_cap = std::max(n_cap, 3);
   if (n_max > 512) { std::fprintf(stderr, "optimizeTEB: band longer than 512 poses is not supported\n"); return false; }
   /* every planner may carry its own obstacle container: one scene per distinct container */
