@@ -35,6 +35,8 @@ struct tebgpu_ctx {
   double* chi_parts = nullptr;
   double* dmax_parts = nullptr;
   double* rhs = nullptr;
+  int32_t* dyn_idx = nullptr;
+  int32_t* dyn_cnt = nullptr;
   SpecBufs spec{};
   BandState* state = nullptr;
   /* device mirrors for the host-buffer entry point */
@@ -137,7 +139,7 @@ const char* tebgpu_last_error_string(const tebgpu_ctx* ctx) { return ctx ? ctx->
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static void free_all(tebgpu_ctx* c) {
-  void* ptrs[] = {c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.T, c->spec.res, c->spec.need, c->spec.qmax, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+  void* ptrs[] = {c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.T, c->spec.res, c->spec.need, c->spec.qmax, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
                   c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
                   c->d_status, c->d_iters};
   for (void* p : ptrs)
@@ -175,6 +177,9 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaMalloc(&c->state, B * sizeof(BandState)));
   CUDA_TRY(c, cudaMalloc(&c->dmax_parts, B * c->chunks * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->rhs, B * 4 * nc * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->dyn_idx, S * M * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->dyn_cnt, S * sizeof(int32_t)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes((int)nc, (int)M)));
   const size_t spec_sys = ((B * SPEC_K + 31) / 32) * 32; /* whole warps of (band, trial) systems */
   CUDA_TRY(c, cudaMalloc(&c->spec.Lf, spec_sys * 4 * nc * HROW * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->spec.dx, spec_sys * 4 * nc * sizeof(double)));
@@ -291,7 +296,7 @@ static DevBatch make_devbatch(tebgpu_ctx* ctx, const TebBatch* bt) {
   d.via = bt->via; d.via_count = bt->via_count; d.vel_start = bt->vel_start; d.vel_goal = bt->vel_goal;
   d.prefer_rotdir = bt->prefer_rotdir;
   d.cost = bt->cost; d.chi2 = bt->chi2; d.status = bt->status; d.lm_iters = bt->lm_iters;
-  d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts; d.dmax_parts = ctx->dmax_parts; d.rhs = ctx->rhs;
+  d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts; d.dmax_parts = ctx->dmax_parts; d.rhs = ctx->rhs; d.dyn_idx = ctx->dyn_idx; d.dyn_cnt = ctx->dyn_cnt;
   d.state = ctx->state;
   d.chunks = (bt->n_cap + TP - 1) / TP;
   return d;
@@ -306,7 +311,7 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   DevBatch db = make_devbatch(ctx, bt);
   const TebParams& p = ctx->params;
   const int B = bt->B;
-  const int tb = 128, gb = (B + tb - 1) / tb;
+  const int tb = 128, gb = ((B > bt->S ? B : bt->S) + tb - 1) / tb;
   int64_t launches = 0;
   const size_t smem_a = ka_smem_bytes(bt->M_cap);
   const size_t smem_b = kb_smem_bytes(bt->n_cap, bt->M_cap);
@@ -327,7 +332,7 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
         const int bk = B * SPEC_K;
         for (int round = 0; round < SPEC_ROUNDS; ++round) {
           prof_begin(ctx, st, 6); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
-          prof_begin(ctx, st, 7); k_trial_eval<<<(bk + 3) / 4, 128, 0, st>>>(db, kp, ctx->spec, round); ++launches; prof_end(ctx, st);
+          prof_begin(ctx, st, 7); k_trial_eval<<<B, 32 * SPEC_K, eval_smem_bytes(bt->n_cap, bt->M_cap), st>>>(db, kp, ctx->spec, round); ++launches; prof_end(ctx, st);
           prof_begin(ctx, st, 8); k_decide<<<(B + 3) / 4, 128, 0, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
         }
       } else {
@@ -439,7 +444,7 @@ int32_t tebgpu_compute_cost(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimi
   cudaStream_t st = ctx->stream;
   DevBatch db = make_devbatch(ctx, &d);
   KParams kp = make_kparams(ctx->params, 1.0); /* buildGraph() default weight_multiplier (optimal_planner.h:536) */
-  const int B = bt->B, tb = 128, gb = (B + tb - 1) / tb;
+  const int B = bt->B, tb = 128, gb = ((B > bt->S ? B : bt->S) + tb - 1) / tb;
   k_begin<<<gb, tb, 0, st>>>(db, kp);
   k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
   k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(bt->M_cap), st>>>(db, kp);
@@ -469,7 +474,7 @@ int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* bt, int32_t outer_i
   double mult = 1.0;
   for (int o = 0; o < outer_index; ++o) mult *= ctx->params.weight_adapt_factor;
   KParams kp = make_kparams(ctx->params, mult);
-  const int B = bt->B, tb = 128, gb = (B + tb - 1) / tb;
+  const int B = bt->B, tb = 128, gb = ((B > bt->S ? B : bt->S) + tb - 1) / tb;
   k_begin<<<gb, tb, 0, st>>>(db, kp);
   k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
   k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(bt->M_cap), st>>>(db, kp);

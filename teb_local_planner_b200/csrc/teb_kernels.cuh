@@ -24,7 +24,8 @@
 
 namespace tebgpu {
 
-constexpr int TP = 64;                 /* poses per kernel-A tile */
+constexpr int TP = 32;                 /* poses per kernel-A tile */
+constexpr int KA_P1OFF = ((TP + 2 + 31) / 32) * 32; /* first thread of the acceleration-row group */
 constexpr int KA_THREADS = 4 * TP;     /* one thread per band row of the tile */
 constexpr int JSTRIDE = 65;            /* doubles per anchor Jacobian block (6x7 + 2x11 = 64, +1 pad) */
 constexpr int HROW = 12;               /* doubles per band row: 11 band entries + rhs */
@@ -64,6 +65,8 @@ struct DevBatch {
   double* dyn_t;              /* [B][n_cap]       */
   int32_t* via_idx;           /* [B][V_cap]       */
   double* chi_parts;          /* [B][chunks][4]   */
+  int32_t* dyn_idx;           /* [S][M_cap] indices of the dynamic obstacles of a scene (built once per call) */
+  int32_t* dyn_cnt;           /* [S] */
   double* rhs;                /* [B][4*n_cap] compact copy of b (coalesced reads in the trial evaluation) */
   double* dmax_parts;         /* [B][chunks] max |H_rr| over the real rows of the tile (LM lambda init) */
   BandState* state;           /* [B]              */
@@ -110,6 +113,14 @@ __device__ __forceinline__ bool row_is_real(int r, int n) {
 /* ------------------------------------------------------------------ k_begin */
 __global__ void k_begin(DevBatch db, KParams kp) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < db.S) { /* compact list of the scene's dynamic obstacles (AddEdgesDynamicObstacles iterates only those) */
+    const TebObstacle* go = db.obstacles + (size_t)b * db.M_cap;
+    int cnt = 0;
+    const int M = db.obst_count[b];
+    for (int m = 0; m < M; ++m)
+      if (go[m].dynamic) db.dyn_idx[(size_t)b * db.M_cap + cnt++] = m;
+    db.dyn_cnt[b] = cnt;
+  }
   if (b >= db.B) return;
   BandState st;
   st.lambda = 0; st.ni = 2; st.current_chi = 0; st.chi2_final = 0;
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
 
 /* ------------------------------------------------------------------ unary terms of one pose (obstacles, dynamic
  * obstacles, via-points): accumulates U = sum kappa g g^T (xx,xy,yy,xt,yt,tt), ub = -sum beta g, chi2 by family */
-__device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& db, int b, int i, int n, double px,
+__device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& db, int b, int sc, int i, int n, double px,
                                             double py, double cs, double sn, const TebObstacle* so, int M,
                                             bool want_grad, double U[6], double ub[3], double& chi_obst,
                                             double& chi_via) {
@@ -266,9 +277,10 @@ __device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& d
   }
   if (kp.has_dyn) {
     const double t = db.dyn_t[(size_t)b * db.n_cap + i];
-    for (int m = 0; m < M; ++m) {
-      const TebObstacle ob = so[m];
-      if (!ob.dynamic) continue;
+    const int nd = db.dyn_cnt[sc];
+    const int32_t* di = db.dyn_idx + (size_t)sc * db.M_cap;
+    for (int q = 0; q < nd; ++q) {
+      const TebObstacle ob = so[di[q]];
       double g[3], kappa, beta;
       const double d = footprint_distance(kp, px, py, cs, sn, ob.x + t * ob.vx, ob.y + t * ob.vy, ob.radius, g);
       chi_obst += dynamic_terms(kp, d, kappa, beta);
@@ -317,7 +329,7 @@ __host__ __device__ inline size_t ka_smem_bytes(int M_cap) {
   return (d + jb) * sizeof(double) + (size_t)M_cap * sizeof(TebObstacle) + 64;
 }
 
-__global__ void __launch_bounds__(KA_THREADS, 3) k_linearize(DevBatch db, KParams kp) {
+__global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = blockIdx.y;
   const BandState* st = &db.state[b];
@@ -358,7 +370,10 @@ __global__ void __launch_bounds__(KA_THREADS, 3) k_linearize(DevBatch db, KParam
     if (bytesO) tma_load_1d(so, db.obstacles + (size_t)s * db.M_cap, bytesO, bar);
   }
   /* zero the Jacobian blocks while the copies are in flight */
-  for (int k = tid; k < KASmem::JB; k += KA_THREADS) sJ[k] = 0.0;
+  {
+    double2* z2 = reinterpret_cast<double2*>(sJ); /* sJ is 16-byte aligned, JB is even */
+    for (int k = tid; k < KASmem::JB / 2; k += KA_THREADS) z2[k] = make_double2(0.0, 0.0);
+  }
   for (int k = tid; k < KASmem::EH + KASmem::START; k += KA_THREADS) sE[k] = 0.0;
   mbar_wait(bar, 0);
 
@@ -393,7 +408,7 @@ __global__ void __launch_bounds__(KA_THREADS, 3) k_linearize(DevBatch db, KParam
         const int j = il + 2;
         double sn = 0, cs = 1;
         if (kp.p.footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
-        unary_terms(kp, db, b, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
+        unary_terms(kp, db, b, s, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
         if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
           const double dt = sP[4 * j + 3];
           chi[2] += kp.p.weight_optimaltime * dt * dt;
@@ -411,9 +426,9 @@ __global__ void __launch_bounds__(KA_THREADS, 3) k_linearize(DevBatch db, KParam
   /* stage 3a: chain edges anchored at a (EdgeVelocity, EdgeKinematics*, EdgeShortestPath, EdgePreferRotDir,
    * EdgeAcceleration / Start / Goal) -> sqrt(weight)-scaled Jacobian rows over the columns 4a .. 4a+10 */
   /* group 0 (warps 0-2): velocity / kinematics / shortest-path / rotdir rows; group 1 (warps 3-5): acceleration rows */
-  const int part = (tid < TP + 2) ? 0 : ((tid >= 96 && tid < 96 + TP + 2) ? 1 : -1);
+  const int part = (tid < TP + 2) ? 0 : ((tid >= KA_P1OFF && tid < KA_P1OFF + TP + 2) ? 1 : -1);
   if (part >= 0) {
-    const int at = part == 0 ? tid : tid - 96; /* anchor slot */
+    const int at = part == 0 ? tid : tid - KA_P1OFF; /* anchor slot */
     const int a = p0 - 2 + at;
     if (a >= 0 && a <= n - 2) {
       double* J = sJ + (size_t)at * JSTRIDE; /* rows 0..5: 7 columns, rows 6,7: 11 columns at offset 42 */
@@ -711,7 +726,7 @@ struct ChainCarry {
   bool has_cs, has_seg;
 };
 
-__device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db, int b, int i, int n, const double* sT,
+__device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db, int b, int sc, int i, int n, const double* sT,
                                           const TebObstacle* so, int M, const double* vs, const double* vg,
                                           double (&chi)[4], ChainCarry& cy) {
     const double* pa = sT + 4 * i;
@@ -787,7 +802,7 @@ __device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db,
       if (kp.has_time) chi[2] += kp.p.weight_optimaltime * pa[3] * pa[3];
     }
     double U[6], ub[3];
-    unary_terms(kp, db, b, i, n, pa[0], pa[1], ca, sa, so, M, false, U, ub, chi[0], chi[1]);
+    unary_terms(kp, db, b, sc, i, n, pa[0], pa[1], ca, sa, so, M, false, U, ub, chi[0], chi[1]);
 }
 
 template <int NTHREADS>
@@ -796,10 +811,11 @@ __device__ __forceinline__ void eval_chi2_parts(const KParams& kp, const DevBatc
   double chi[4] = {0, 0, 0, 0};
   const double* vs = db.vel_start + 4 * (size_t)b;
   const double* vg = db.vel_goal + 4 * (size_t)b;
+  const int sc = db.scene_id[b];
   for (int i = threadIdx.x; i < n; i += NTHREADS) {
     ChainCarry cy;
     cy.has_cs = false; cy.has_seg = false;
-    pose_chi2(kp, db, b, i, n, sT, so, M, vs, vg, chi, cy);
+    pose_chi2(kp, db, b, sc, i, n, sT, so, M, vs, vg, chi, cy);
   }
   block_sum<4, NTHREADS / 32>(chi, scratch, out);
 }

@@ -213,61 +213,82 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
   cp_async_wait<0>();
 }
 
-/* ------------------------------------------------------------------ k_trial_eval: warp per (band, trial) */
-__global__ void __launch_bounds__(128) k_trial_eval(DevBatch db, KParams kp, SpecBufs sp, int round) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int b = w / SPEC_K, k = w - b * SPEC_K;
-  if (b >= db.B) return;
+/* ------------------------------------------------------------------ k_trial_eval: CTA per band, warp k = trial k.
+ * The four trial solutions of a band sit in adjacent lanes of the solver's interleaved scratch (one 32-byte sector per
+ * row), so the CTA stages them - and the scene's obstacle table and the four trial states - in shared memory once. */
+__host__ __device__ inline size_t eval_smem_bytes(int n_cap, int M_cap) {
+  return (size_t)SPEC_K * 4 * n_cap * sizeof(double) * 2 + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 16;
+}
+
+__global__ void __launch_bounds__(32 * SPEC_K) k_trial_eval(DevBatch db, KParams kp, SpecBufs sp, int round) {
+  extern __shared__ __align__(16) unsigned char ev_raw[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
   const BandState* st = &db.state[b];
   if (!st->active) return;
   if (round > 0 && !sp.need[b]) return;
   const int q0 = (round == 0) ? 0 : sp.qmax[b];
-  if (q0 + k >= 10) return;
   const int n = db.n[b];
   const int N = 4 * n;
-  double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
-  const bool ok = res[5] != 0.0;
-  const double lambda = res[6];
-  const double* gP = db.poses + (size_t)b * db.n_cap * 4;
-  const double* grhs = db.rhs + (size_t)b * 4 * db.n_cap;
-  const int tsys = b * SPEC_K + k; /* system index = thread index of k_solve_tpb */
-  const double* gx = sp.dx + (size_t)(tsys >> 5) * 32 * 4 * db.n_cap + (tsys & 31);
-  double* gT = sp.T + ((size_t)b * SPEC_K + k) * 4 * db.n_cap;
-  /* trial state x [+] dx and computeScale() = sum dx (lambda dx + b) */
-  double sc = 0;
-  for (int r = lane; r < N; r += 32) {
-    double xv = gP[r];
-    if (row_is_real(r, n)) {
-      const double bb = grhs[r];
-      const double dx = ok ? gx[(size_t)r * 32] : bb; /* CSparse leaves x = b when the factorisation fails */
-      sc += dx * (lambda * dx + bb);
-      xv = ((r & 3) == 2) ? normalize_theta(xv + dx) : xv + dx;
-    }
-    gT[r] = xv;
-  }
-  __syncwarp();
-  const int s = db.scene_id[b];
-  const int M = db.obst_count[s];
-  const TebObstacle* so = db.obstacles + (size_t)s * db.M_cap;
-  const double* vs = db.vel_start + 4 * (size_t)b;
-  const double* vg = db.vel_goal + 4 * (size_t)b;
-  double chi[4] = {0, 0, 0, 0};
+  double* sdx = reinterpret_cast<double*>(ev_raw);           /* [K][4 n_cap] */
+  double* sT = sdx + (size_t)SPEC_K * 4 * db.n_cap;           /* [K][n_cap][4] */
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(sT + (size_t)SPEC_K * 4 * db.n_cap);
+  const int sc = db.scene_id[b];
+  const int M = db.obst_count[sc];
   {
-    /* contiguous chunk per lane: sin/cos and segment velocities are carried from pose to pose instead of being
-     * recomputed by the neighbour (5/8 of the transcendental work of a strided assignment at 4 poses per lane) */
+    const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
+    for (int m = tid; m < M; m += 32 * SPEC_K) so[m] = go[m];
+    /* rows of the 4 trial solutions: system index 4b+k -> solver warp (4b)>>5, lanes (4b)&31 .. +3 */
+    const int tsys = b * SPEC_K;
+    const double* gx = sp.dx + (size_t)(tsys >> 5) * 32 * 4 * db.n_cap + (tsys & 31);
+    for (int r = tid; r < N; r += 32 * SPEC_K) {
+      const double2* src = reinterpret_cast<const double2*>(gx + (size_t)r * 32);
+      const double2 a = src[0], c = src[1];
+      sdx[0 * 4 * db.n_cap + r] = a.x; sdx[1 * 4 * db.n_cap + r] = a.y;
+      sdx[2 * 4 * db.n_cap + r] = c.x; sdx[3 * 4 * db.n_cap + r] = c.y;
+    }
+  }
+  __syncthreads();
+  const bool mine = (q0 + k < 10);
+  double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
+  double chi[4] = {0, 0, 0, 0};
+  double scl = 0;
+  if (mine) {
+    const bool ok = res[5] != 0.0;
+    const double lambda = res[6];
+    const double* gP = db.poses + (size_t)b * db.n_cap * 4;
+    const double* grhs = db.rhs + (size_t)b * 4 * db.n_cap;
+    const double* mydx = sdx + (size_t)k * 4 * db.n_cap;
+    double* myT = sT + (size_t)k * 4 * db.n_cap;
+    double* gT = sp.T + ((size_t)b * SPEC_K + k) * 4 * db.n_cap;
+    /* trial state x [+] dx and computeScale() = sum dx (lambda dx + b) */
+    for (int r = lane; r < N; r += 32) {
+      double xv = gP[r];
+      if (row_is_real(r, n)) {
+        const double bb = grhs[r];
+        const double dx = ok ? mydx[r] : bb; /* CSparse leaves x = b when the factorisation fails */
+        scl += dx * (lambda * dx + bb);
+        xv = ((r & 3) == 2) ? normalize_theta(xv + dx) : xv + dx;
+      }
+      myT[r] = xv;
+      gT[r] = xv;
+    }
+    __syncwarp();
+    const double* vs = db.vel_start + 4 * (size_t)b;
+    const double* vg = db.vel_goal + 4 * (size_t)b;
+    /* contiguous chunk per lane: sin/cos and segment velocities are carried from pose to pose */
     const int per = (n + 31) >> 5;
     const int i0 = lane * per, i1 = min(i0 + per, n);
     ChainCarry cy;
     cy.has_cs = false; cy.has_seg = false;
-    for (int i = i0; i < i1; ++i) pose_chi2(kp, db, b, i, n, gT, so, M, vs, vg, chi, cy);
+    for (int i = i0; i < i1; ++i) pose_chi2(kp, db, b, sc, i, n, myT, so, M, vs, vg, chi, cy);
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) chi[c] = warp_sum(chi[c]);
-  sc = warp_sum(sc);
-  if (lane == 0) {
+  scl = warp_sum(scl);
+  if (mine && lane == 0) {
     res[0] = chi[0]; res[1] = chi[1]; res[2] = chi[2]; res[3] = chi[3];
-    res[4] = sc;
+    res[4] = scl;
   }
 }
 
