@@ -24,6 +24,7 @@ struct tebgpu_ctx {
   bool have_params = false;
   std::string err;
   int64_t launches = 0;
+  int spec_k = 0;  /* speculation width: 0 = auto (6 when B*6 systems fit one warp per SM sub-partition, else 4) */
   int solver = 2;  /* 2: speculative thread-per-(band,trial) LDL^T (default), 1: block cyclic reduction, 0: sequential */
   int MW = 1;
   int chunks = 1;
@@ -179,12 +180,16 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaMalloc(&c->rhs, B * 4 * nc * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->dyn_idx, S * M * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->dyn_cnt, S * sizeof(int32_t)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes((int)nc, (int)M)));
-  const size_t spec_sys = ((B * SPEC_K + 31) / 32) * 32; /* whole warps of (band, trial) systems */
+  {
+    size_t ev = eval_smem_bytes((int)nc, (int)M, SPEC_K_MAX);
+    if (ev > 232448) ev = 232448; /* wide speculation is only chosen when its staging fits (tebgpu_optimize_batch_device) */
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
+  }
+  const size_t spec_sys = ((B * SPEC_K_MAX + 31) / 32) * 32; /* whole warps of (band, trial) systems */
   CUDA_TRY(c, cudaMalloc(&c->spec.Lf, spec_sys * 4 * nc * HROW * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->spec.dx, spec_sys * 4 * nc * sizeof(double)));
-  CUDA_TRY(c, cudaMalloc(&c->spec.T, B * SPEC_K * 4 * nc * sizeof(double)));
-  CUDA_TRY(c, cudaMalloc(&c->spec.res, B * SPEC_K * RES_STRIDE * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.T, B * SPEC_K_MAX * 4 * nc * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.res, B * SPEC_K_MAX * RES_STRIDE * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->spec.need, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.qmax, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->d_poses, B * nc * 4 * sizeof(double)));
@@ -319,6 +324,12 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   const bool use_bcr = ctx->solver == 1 && bt->n_cap <= BCR_MAX_POSES && smem_bcr <= 232448 &&
                        ctx->lim.max_poses <= BCR_MAX_POSES;
   const size_t smem_g = (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle);
+  /* speculation width: one solver warp per SM sub-partition is the latency-optimal regime (148 SMs x 4 x 32 lanes);
+   * below it the wider speculation is free and removes the second round, above it the factor traffic dominates */
+  int spec_K = ctx->spec_k;
+  if (spec_K == 0) spec_K = ((long long)B * 6 <= 148LL * 4 * 32) ? 6 : 4;
+  while (spec_K > 4 && eval_smem_bytes(bt->n_cap, bt->M_cap, spec_K) > 232448) spec_K -= 2;
+  if (eval_smem_bytes(bt->n_cap, bt->M_cap, spec_K) > 232448) { ctx->err = "trial-evaluation staging exceeds shared memory"; return TEBGPU_ERR_CAPACITY; }
   double weight_multiplier = 1.0;
   KParams kp = make_kparams(p, weight_multiplier);
   prof_begin(ctx, st, 0); k_begin<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st);
@@ -329,10 +340,13 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
     for (int it = 0; it < args->iterations_innerloop; ++it) {
       prof_begin(ctx, st, 3); k_linearize<<<dim3(db.chunks, B), KA_THREADS, smem_a, st>>>(db, kp); ++launches; prof_end(ctx, st);
       if (ctx->solver == 2) {
-        const int bk = B * SPEC_K;
-        for (int round = 0; round < SPEC_ROUNDS; ++round) {
+        const int K = spec_K;
+        ctx->spec.K = K;
+        const int bk = B * K;
+        const int rounds = (10 + K - 1) / K; /* g2o's maxTrialsAfterFailure = 10 */
+        for (int round = 0; round < rounds; ++round) {
           prof_begin(ctx, st, 6); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
-          prof_begin(ctx, st, 7); k_trial_eval<<<B, 32 * SPEC_K, eval_smem_bytes(bt->n_cap, bt->M_cap), st>>>(db, kp, ctx->spec, round); ++launches; prof_end(ctx, st);
+          prof_begin(ctx, st, 7); k_trial_eval<<<B, 32 * K, eval_smem_bytes(bt->n_cap, bt->M_cap, K), st>>>(db, kp, ctx->spec, round); ++launches; prof_end(ctx, st);
           prof_begin(ctx, st, 8); k_decide<<<(B + 3) / 4, 128, 0, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
         }
       } else {
@@ -367,6 +381,12 @@ int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[9], int64_t count
   CUDA_TRY(ctx, cudaDeviceSynchronize());
   prof_collect(ctx);
   for (int k = 0; k < 9; ++k) { ms_out[k] = ctx->prof_ms[k]; count_out[k] = ctx->prof_cnt[k]; ctx->prof_ms[k] = 0; ctx->prof_cnt[k] = 0; }
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k) {
+  if (!ctx || !(k == 0 || k == 4 || k == 6 || k == 8)) return TEBGPU_ERR_INVALID_ARG;
+  ctx->spec_k = k;
   return TEBGPU_OK;
 }
 

@@ -21,8 +21,7 @@
 
 namespace tebgpu {
 
-constexpr int SPEC_K = 4;        /* trials solved concurrently per round */
-constexpr int SPEC_ROUNDS = 3;   /* 4 + 4 + 2 = g2o's maxTrialsAfterFailure (10) */
+constexpr int SPEC_K_MAX = 8;    /* trials solved concurrently per round: 4, 6 or 8 (runtime, SpecBufs::K) */
 constexpr int RES_STRIDE = 8;    /* per (band, trial): chi parts [4], scale, ok, lambda, unused */
 
 struct SpecBufs {
@@ -32,6 +31,7 @@ struct SpecBufs {
   double* res;   /* [B][K][RES_STRIDE]                                         */
   int32_t* need; /* [B] band still needs trials in this LM iteration          */
   int32_t* qmax; /* [B] trials consumed in this LM iteration                  */
+  int32_t K;     /* speculation width of this call                            */
 };
 
 /* lambda / nu of trial q0 + k given the state before trial q0 (only rejections in between) */
@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
   extern __shared__ __align__(16) unsigned char ring_raw[];
   const int lane = threadIdx.x;
   const int t = blockIdx.x * 32 + lane;
+  const int SPEC_K = sp.K;
   int b = t / SPEC_K;
   const int k = t - b * SPEC_K;
   bool work = b < db.B;
@@ -216,12 +217,13 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
 /* ------------------------------------------------------------------ k_trial_eval: CTA per band, warp k = trial k.
  * The four trial solutions of a band sit in adjacent lanes of the solver's interleaved scratch (one 32-byte sector per
  * row), so the CTA stages them - and the scene's obstacle table and the four trial states - in shared memory once. */
-__host__ __device__ inline size_t eval_smem_bytes(int n_cap, int M_cap) {
-  return (size_t)SPEC_K * 4 * n_cap * sizeof(double) * 2 + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 16;
+__host__ __device__ inline size_t eval_smem_bytes(int n_cap, int M_cap, int K) {
+  return (size_t)K * 4 * n_cap * sizeof(double) * 2 + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 16;
 }
 
-__global__ void __launch_bounds__(32 * SPEC_K) k_trial_eval(DevBatch db, KParams kp, SpecBufs sp, int round) {
+__global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KParams kp, SpecBufs sp, int round) {
   extern __shared__ __align__(16) unsigned char ev_raw[];
+  const int SPEC_K = sp.K;
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
   const BandState* st = &db.state[b];
@@ -238,14 +240,16 @@ __global__ void __launch_bounds__(32 * SPEC_K) k_trial_eval(DevBatch db, KParams
   {
     const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
     for (int m = tid; m < M; m += 32 * SPEC_K) so[m] = go[m];
-    /* rows of the 4 trial solutions: system index 4b+k -> solver warp (4b)>>5, lanes (4b)&31 .. +3 */
-    const int tsys = b * SPEC_K;
-    const double* gx = sp.dx + (size_t)(tsys >> 5) * 32 * 4 * db.n_cap + (tsys & 31);
+    /* rows of the K trial solutions: system index K b + k -> solver warp (K b + k) >> 5, lane (K b + k) & 31: the
+     * trials of a band are adjacent lanes of the interleaved scratch (K even: pairs never straddle a tile) */
     for (int r = tid; r < N; r += 32 * SPEC_K) {
-      const double2* src = reinterpret_cast<const double2*>(gx + (size_t)r * 32);
-      const double2 a = src[0], c = src[1];
-      sdx[0 * 4 * db.n_cap + r] = a.x; sdx[1 * 4 * db.n_cap + r] = a.y;
-      sdx[2 * 4 * db.n_cap + r] = c.x; sdx[3 * 4 * db.n_cap + r] = c.y;
+      for (int kk = 0; kk < SPEC_K; kk += 2) {
+        const int tsys = b * SPEC_K + kk;
+        const double2 a = *reinterpret_cast<const double2*>(sp.dx + (size_t)(tsys >> 5) * 32 * 4 * db.n_cap +
+                                                            (size_t)r * 32 + (tsys & 31));
+        sdx[(size_t)kk * 4 * db.n_cap + r] = a.x;
+        sdx[(size_t)(kk + 1) * 4 * db.n_cap + r] = a.y;
+      }
     }
   }
   __syncthreads();
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(32 * SPEC_K) k_trial_eval(DevBatch db, KParams
 
 /* ------------------------------------------------------------------ k_decide: warp per band */
 __global__ void __launch_bounds__(128) k_decide(DevBatch db, SpecBufs sp, int iteration, int round) {
+  const int SPEC_K = sp.K;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= db.B) return;

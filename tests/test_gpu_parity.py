@@ -209,6 +209,28 @@ def test_full_size_properties_c3():
     g.close()
 
 
+def test_solvers_and_speculation_widths_agree():
+    """the three linear solvers give the same bands up to round-off; the speculation width K does not change a bit"""
+    p, hb0 = scenes.make_config_batch("C4", candidates=12, seed=9)
+    args = abi.make_args(5, 4, True, 100.0, 1.0, False)
+    g = _gpu(hb0, p)
+    outs = {}
+    for name, solver, k in (("spec4", 2, 4), ("spec6", 2, 6), ("spec8", 2, 8), ("bcr", 1, 0), ("seq", 0, 0)):
+        g.set_solver(solver)
+        g.set_speculation(k)
+        h = hb0.copy()
+        g.optimize(h, args)
+        outs[name] = h
+    g.close()
+    for name in ("spec6", "spec8"):
+        assert np.array_equal(outs[name].poses, outs["spec4"].poses) and np.array_equal(outs[name].cost, outs["spec4"].cost)
+        assert np.array_equal(outs[name].lm_iters, outs["spec4"].lm_iters)
+    for name in ("bcr", "seq"):
+        assert _pose_diff(outs[name], outs["spec4"]).max() < 1e-7
+        assert np.allclose(outs[name].cost, outs["spec4"].cost, rtol=1e-7)
+        assert np.array_equal(outs[name].status, outs["spec4"].status)
+
+
 def test_errors_are_loud():
     p, hb = scenes.make_config_batch("C1", candidates=2)
     g = T.TebGpu(2, 50, 1, 8, 0)
@@ -255,5 +277,5 @@ def test_device_pointer_entry_point_matches_host_entry_point():
     got = poses.cpu().numpy().view(np.float64).reshape(hb0.poses.shape)
     assert np.array_equal(got, ref.poses)
     assert np.array_equal(cost.cpu().numpy(), ref.cost)
-    assert g.launch_count() == 1 + 4 * (1 + 5 * (1 + 3 * 3)) + 1   # begin + outer*(build + inner*(A + 3 rounds x 3)) + finalize
+    assert g.launch_count() == 1 + 4 * (1 + 5 * (1 + 2 * 3)) + 1   # begin + outer*(build + inner*(A + 2 rounds x 3 [K=6])) + finalize
     g.close()
