@@ -3,7 +3,8 @@
 
 A "step" is one optimizeTEB pass (no_outer x no_inner LM iterations + cost) over one batch of synthetic planning
 requests: `candidates` homotopy candidates x `requests` requests per GPU (weak scaling: per-GPU work is fixed).
-Default workload = BASELINE config C2 (diff-drive, 100 poses, 20 point obstacles, 32 candidates per request).
+Default workload = BASELINE config C2 (diff-drive, 100 poses, 20 point obstacles, 32 candidates per request) x 256
+requests = 8192 bands per GPU, i.e. a 315 MB H/b working set (> the 126 MB L2).
 
   python bench.py --gpus 1 --steps 5 --warmup 3                 # this framework
   python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # the reference's CPU path (oracle port, all host threads)
@@ -37,7 +38,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
-    ap.add_argument("--requests", type=int, default=64, help="planning requests per GPU per step")
+    ap.add_argument("--requests", type=int, default=256, help="planning requests per GPU per step")
     ap.add_argument("--candidates", type=int, default=None, help="candidates per request (default: config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
