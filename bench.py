@@ -120,12 +120,17 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def algorithmic_bytes(n, M, V, B):
-    """per band per LM iteration; N = 4n - 7 unknowns, band rows of 11 + rhs."""
+def algorithmic_bytes(n, M, V, B, K):
+    """per band per LM iteration; N = 4n - 7 unknowns, band rows of 11 + rhs.
+    a: kernel A (read poses/obstacles/via, write band + rhs + chi2); b: fused kernel B of solvers 0/1;
+    s: k_solve_tpb round 0 (read band once per band, write + read the factor and write the solution per trial);
+    e: k_trial_eval round 0 (read K solutions, poses, rhs, obstacles; write K trial states)."""
     N = 4 * n - 7
     a = 32 * n + 48 * M + 16 * V + 8 * (11 * N + N) + 8
     b = 8 * 12 * N + 32 * n + 48 * M + 32 * n + 32
-    return a * B, b * B
+    s = 96 * N + K * (2 * 96 * N + 8 * N)
+    e = K * 8 * N + 32 * n + 8 * N + 48 * M + K * 32 * n
+    return a * B, b * B, s * B, e * B
 
 
 def host_threads():
@@ -298,7 +303,8 @@ def run_b200(a, rank, local_rank, world):
     kt = g.kernel_times()
     g.set_profiling(False)
     peak, peak_src = hbm_peak()
-    bytes_a, bytes_b = algorithmic_bytes(desc["n_poses"], desc["n_obstacles"], desc["via_points"], B)
+    spec_k = 6 if B * 6 <= 148 * 4 * 32 else 4   # the library's automatic speculation width (tebgpu_set_speculation)
+    bytes_a, bytes_b, bytes_s, bytes_e = algorithmic_bytes(desc["n_poses"], desc["n_obstacles"], desc["via_points"], B, spec_k)
 
     def roof(name, nbytes):
         ms, cnt = kt[name]
@@ -312,10 +318,12 @@ def run_b200(a, rank, local_rank, world):
 
     total_ms = sum(v[0] for v in kt.values())
     shares = {k: (v[0] / total_ms if total_ms > 0 else 0.0) for k, v in kt.items()}
-    roof_a, roof_b = roof("k_linearize", bytes_a), roof("k_lm_step", bytes_b)
-    dominant = roof_b if kt["k_lm_step"][0] >= kt["k_linearize"][0] else roof_a
+    roof_a, roof_s, roof_e = roof("k_linearize", bytes_a), roof("k_solve_tpb", bytes_s), roof("k_trial_eval", bytes_e)
+    roof_b = roof_s
+    cands = [r for r in (roof_a, roof_s, roof_e) if r is not None]
+    dominant = max(cands, key=lambda r: kt[r["kernel"]][0])
     working_set_mb = B * 4 * n_cap * 96 / 1e6
-    for r in (roof_a, roof_b):
+    for r in (roof_a, roof_s, roof_e):
         if r is not None:
             r["note"] = ("H/b working set %.0f MB %s the 126 MB L2" % (working_set_mb, ">" if working_set_mb > 126 else "<=")
                          + ("" if working_set_mb > 126 else ": L2-resident, latency-bound; HBM fraction is indicative only"))
@@ -324,7 +332,7 @@ def run_b200(a, rank, local_rank, world):
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tr = json.load(f)
         key = f"{a.workload}_B{B}"
-        for r in (roof_a, roof_b):
+        for r in (roof_a, roof_s, roof_e):
             if r is not None and key in tr and r["kernel"] in tr[key]:
                 r["traffic"] = tr[key][r["kernel"]]
     except Exception:
@@ -401,7 +409,8 @@ def run_b200(a, rank, local_rank, world):
                         "ms_per_step": e2e_ms, "api": "tebgpu_optimize_batch (C-ABI, pinned host buffers)"},
                 "gpu_launches": int(launches_per_step * a.steps),
                 "gpu_launches_per_step": int(launches_per_step),
-                "roofline": dominant, "roofline_kernel_a": roof_a, "roofline_kernel_b": roof_b,
+                "roofline": dominant, "roofline_kernel_a": roof_a, "roofline_kernel_b_solve": roof_s,
+                "roofline_kernel_b_eval": roof_e, "speculation_width": spec_k,
                 "kernel_time_share": shares,
                 "cpu_baseline": cpu, "clocks": clocks,
                 "best_candidate_of_request0": int(best[0])}

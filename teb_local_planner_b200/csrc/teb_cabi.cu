@@ -345,8 +345,8 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
         const int bk = B * K;
         const int rounds = (10 + K - 1) / K; /* g2o's maxTrialsAfterFailure = 10 */
         for (int round = 0; round < rounds; ++round) {
-          prof_begin(ctx, st, 6); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
-          prof_begin(ctx, st, 7); k_trial_eval<<<B, 32 * K, eval_smem_bytes(bt->n_cap, bt->M_cap, K), st>>>(db, kp, ctx->spec, round); ++launches; prof_end(ctx, st);
+          prof_begin(ctx, st, round == 0 ? 6 : 4); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
+          prof_begin(ctx, st, round == 0 ? 7 : 4); k_trial_eval<<<B, 32 * K, eval_smem_bytes(bt->n_cap, bt->M_cap, K), st>>>(db, kp, ctx->spec, round); ++launches; prof_end(ctx, st);
           prof_begin(ctx, st, 8); k_decide<<<(B + 3) / 4, 128, 0, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
         }
       } else {

@@ -7,7 +7,7 @@ out_dir = os.path.join(root, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 lines = []
 # ---- launch list: time share per kernel (cold-cache, serialised: compare SHARES)
-rows = [r for r in csv.reader(open(launches_csv)) if len(r) > 5]
+rows = [r for r in csv.reader(l for l in open(launches_csv) if l.startswith('"')) if len(r) > 5]
 hdr = rows[0]
 ki, mi, vi = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
 agg = collections.OrderedDict()
@@ -25,7 +25,7 @@ lines.append("| kernel | launches | total | share |\n|---|---|---|---|")
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append(f"| {k} | {c} | {t:.1f} {unit} | {100*t/tot:.1f} % |")
 with open(os.path.join(out_dir, f"{tag}_launches.csv"), "w") as f:
-    f.write(open(launches_csv).read())
+    f.write("".join(l for l in open(launches_csv) if l.startswith('"')))
 # ---- full capture: key metrics per kernel
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw)))
