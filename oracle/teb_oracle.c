@@ -86,7 +86,7 @@ static inline double fast_sigmoid(double x) { return x / (1 + fabs(x)); } /* mis
 /* ------------------------------------------------------------------ band / graph data structures */
 enum EdgeType {
   E_OBST = 0, E_INFL, E_DYN, E_VIA, E_VEL, E_ACC, E_ACC_START, E_ACC_GOAL, E_TIMEOPT, E_SHORTEST,
-  E_KIN_DD, E_KIN_CL, E_ROTDIR, E_NTYPES
+  E_KIN_DD, E_KIN_CL, E_ROTDIR, E_VEL_OBST_RATIO, E_NTYPES
 };
 
 typedef struct Graph Graph;
@@ -127,6 +127,8 @@ struct Graph {
   double* work;   /* factor storage [N][HBW+1] */
   double* backup; /* [n][4] state backup (push/pop) */
   double* Hd;     /* dense workspace (optional) */
+  int* opv;       /* obstacles_per_vertex_: [n][M] indices (optimal_planner.h:690) */
+  int* opv_cnt;   /* [n] */
 };
 
 static inline int pose_fixed(const Graph* g, int i) { return i == 0 || i == g->n - 1; }
@@ -274,6 +276,23 @@ static void ce_acc_goal(Edge* e, Graph* g) {
   double omega2 = e->twist[2];
   double acc_rot = (omega2 - omega1) / dt;
   e->err[1] = teb_oracle_penalty_interval(acc_rot, c->acc_lim_theta, c->penalty_epsilon);
+}
+/* EdgeVelocityObstacleRatio::computeError edge_velocity_obstacle_ratio.h:82-122 */
+static void ce_vel_obst_ratio(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double vel, omega;
+  seg_vel(c, P(g, e->vidx[0]), P(g, e->vidx[1]), DT(g, e->vidx[2]), &vel, &omega);
+  double dist_to_obstacle = footprint_dist(c, P(g, e->vidx[0]), e->ob);
+  double ratio;
+  if (dist_to_obstacle < c->obstacle_proximity_lower_bound) ratio = 0;
+  else if (dist_to_obstacle > c->obstacle_proximity_upper_bound) ratio = 1;
+  else ratio = (dist_to_obstacle - c->obstacle_proximity_lower_bound) /
+               (c->obstacle_proximity_upper_bound - c->obstacle_proximity_lower_bound);
+  ratio *= c->obstacle_proximity_ratio_max_vel;
+  const double max_vel_fwd = ratio * c->max_vel_x;
+  const double max_omega = ratio * c->max_vel_theta;
+  e->err[0] = teb_oracle_penalty_interval(vel, max_vel_fwd, 0);
+  e->err[1] = teb_oracle_penalty_interval(omega, max_omega, 0);
 }
 /* EdgeTimeOptimal::computeError edge_time_optimal.h:88-96 */
 static void ce_timeopt(Edge* e, Graph* g) { e->err[0] = DT(g, e->vidx[0]); }
@@ -555,6 +574,31 @@ static void linearize_analytic(Edge* e, Graph* g) {
       e->J[2][1] = s1 * (-s.dw[6] / dt - accr / dt);
       break;
     }
+    case E_VEL_OBST_RATIO: {
+      SegD s;
+      seg_derivs(c, P(g, e->vidx[0]), P(g, e->vidx[1]), DT(g, e->vidx[2]), &s);
+      double dist, gr[3];
+      footprint_grad(c, P(g, e->vidx[0]), e->ob->x, e->ob->y, e->ob->radius, &dist, gr);
+      double ratio, dratio = 0;
+      if (dist < c->obstacle_proximity_lower_bound) ratio = 0;
+      else if (dist > c->obstacle_proximity_upper_bound) ratio = 1;
+      else {
+        ratio = (dist - c->obstacle_proximity_lower_bound) / (c->obstacle_proximity_upper_bound - c->obstacle_proximity_lower_bound);
+        dratio = 1.0 / (c->obstacle_proximity_upper_bound - c->obstacle_proximity_lower_bound);
+      }
+      ratio *= c->obstacle_proximity_ratio_max_vel;
+      dratio *= c->obstacle_proximity_ratio_max_vel;
+      double s0 = d_interval(s.v, ratio * c->max_vel_x, 0), s1 = d_interval(s.w, ratio * c->max_vel_theta, 0);
+      /* e = |var| - a outside the interval: d e / d a = -1 whenever the penalty is active */
+      double a0 = (s0 != 0) ? -c->max_vel_x * dratio : 0.0, a1 = (s1 != 0) ? -c->max_vel_theta * dratio : 0.0;
+      for (int d = 0; d < 3; ++d) {
+        e->J[0][d] = s0 * s.dv[d] + a0 * gr[d];       e->J[0][3 + d] = s1 * s.dw[d] + a1 * gr[d];
+        e->J[1][d] = s0 * s.dv[3 + d];                e->J[1][3 + d] = s1 * s.dw[3 + d];
+      }
+      e->J[2][0] = s0 * s.dv[6];
+      e->J[2][1] = s1 * s.dw[6];
+      break;
+    }
     case E_TIMEOPT: e->J[0][0] = 1; break;
     case E_SHORTEST: {
       const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
@@ -681,6 +725,8 @@ static void add_edges_obstacles(Graph* g, double weight_multiplier) {
     }
     if (left >= 0) list[cnt++] = left;
     if (right >= 0) list[cnt++] = right;
+    for (int k = 0; k < cnt; ++k) g->opv[(size_t)i * (g->M + 2) + k] = list[k];
+    g->opv_cnt[i] = cnt;
     if (i == 0) continue;
     for (int k = 0; k < cnt; ++k) {
       Edge* e;
@@ -697,6 +743,58 @@ static void add_edges_obstacles(Graph* g, double weight_multiplier) {
     }
   }
   free(list);
+}
+
+/* AddEdgesObstaclesLegacy optimal_planner.cpp:551-643 (note: the centre pose receives three identical edges:
+ * the explicit one plus neighbourIdx = 0 on both sides) */
+static void add_obstacle_edge(Graph* g, int i, int m, int inflated, double weight_multiplier) {
+  const TebParams* c = g->cfg;
+  Edge* e;
+  if (inflated) {
+    e = new_edge(g, E_INFL, 2, ce_inflated);
+    e->info[0] = c->weight_obstacle * weight_multiplier;
+    e->info[1] = c->weight_inflation;
+  } else {
+    e = new_edge(g, E_OBST, 1, ce_obstacle);
+    e->info[0] = c->weight_obstacle * weight_multiplier;
+  }
+  set_vertex(e, 0, 0, i);
+  e->ob = &g->obst[m];
+}
+static int find_closest_pose(Graph* g, const double* pt, int begin_idx);
+static void add_edges_obstacles_legacy(Graph* g, double weight_multiplier) {
+  const TebParams* c = g->cfg;
+  if (c->weight_obstacle == 0 || weight_multiplier == 0 || g->obst == NULL) return;
+  int inflated = c->inflation_dist > c->min_obstacle_dist;
+  for (int m = 0; m < g->M; ++m) {
+    const TebObstacle* ob = &g->obst[m];
+    if (c->include_dynamic_obstacles && ob->dynamic) continue;
+    int index;
+    if (c->obstacle_poses_affected >= g->n) index = g->n / 2;
+    else { double pt[2] = {ob->x, ob->y}; index = find_closest_pose(g, pt, 0); }
+    if ((index <= 1) || (index > g->n - 2)) continue;
+    add_obstacle_edge(g, index, m, inflated, weight_multiplier);
+    for (int nb = 0; nb < (int)floor(c->obstacle_poses_affected / 2); nb++) {
+      if (index + nb < g->n) add_obstacle_edge(g, index + nb, m, inflated, weight_multiplier);
+      if (index - nb >= 0) add_obstacle_edge(g, index - nb, m, inflated, weight_multiplier);
+    }
+  }
+}
+
+/* AddEdgesVelocityObstacleRatio optimal_planner.cpp:999-1021 */
+static void add_edges_velocity_obstacle_ratio(Graph* g) {
+  const TebParams* c = g->cfg;
+  for (int index = 0; index < g->n - 1; ++index) {
+    for (int k = 0; k < g->opv_cnt[index]; ++k) {
+      Edge* e = new_edge(g, E_VEL_OBST_RATIO, 2, ce_vel_obst_ratio);
+      set_vertex(e, 0, 0, index);
+      set_vertex(e, 1, 0, index + 1);
+      set_vertex(e, 2, 1, index);
+      e->info[0] = c->weight_velocity_obstacle_ratio;
+      e->info[1] = c->weight_velocity_obstacle_ratio;
+      e->ob = &g->obst[g->opv[(size_t)index * (g->M + 2) + k]];
+    }
+  }
 }
 
 /* AddEdgesDynamicObstacles optimal_planner.cpp:646-673 (called with weight_multiplier = 1, :343) */
@@ -863,10 +961,13 @@ static void clear_graph(Graph* g) {
 /* buildGraph optimal_planner.cpp:323-366 */
 static int build_graph(Graph* g, double weight_multiplier) {
   const TebParams* c = g->cfg;
-  if (c->legacy_obstacle_association) return TEBGPU_ERR_UNSUPPORTED;
   if (c->max_vel_y != 0) return TEBGPU_ERR_UNSUPPORTED;                 /* holonomic edges not restated */
-  if (c->weight_velocity_obstacle_ratio > 0) return TEBGPU_ERR_UNSUPPORTED;
-  add_edges_obstacles(g, weight_multiplier);
+  /* AddTEBVertices resizes and clears obstacles_per_vertex_ (optimal_planner.cpp:427-439) */
+  free(g->opv); free(g->opv_cnt);
+  g->opv = (int*)malloc(sizeof(int) * (size_t)g->n * (g->M + 2));
+  g->opv_cnt = (int*)calloc((size_t)g->n, sizeof(int));
+  if (c->legacy_obstacle_association) add_edges_obstacles_legacy(g, weight_multiplier);
+  else add_edges_obstacles(g, weight_multiplier);
   if (c->include_dynamic_obstacles) add_edges_dynamic_obstacles(g, 1.0);
   add_edges_via_points(g);
   add_edges_velocity(g);
@@ -875,6 +976,7 @@ static int build_graph(Graph* g, double weight_multiplier) {
   add_edges_shortest_path(g);
   add_edges_kinematics(g);
   add_edges_prefer_rotdir(g);
+  if (c->weight_velocity_obstacle_ratio > 0) add_edges_velocity_obstacle_ratio(g);
   /* initializeOptimization(): edges whose vertices are all fixed are not active (App. A.1) */
   int w = 0;
   for (int k = 0; k < g->n_edges; ++k) {
@@ -1227,6 +1329,7 @@ static void graph_alloc(Graph* g, int n_cap) {
 }
 static void graph_free(Graph* g) {
   clear_graph(g);
+  free(g->opv); free(g->opv_cnt);
   free(g->edges); free(g->Hb); free(g->work); free(g->b); free(g->x); free(g->backup); free(g->Hd);
 }
 

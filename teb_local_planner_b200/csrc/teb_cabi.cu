@@ -31,6 +31,7 @@ struct tebgpu_ctx {
   /* device workspaces */
   double* Hb = nullptr;
   unsigned long long* assoc = nullptr;
+  unsigned long long* assoc3 = nullptr;
   double* dyn_t = nullptr;
   int32_t* via_idx = nullptr;
   double* chi_parts = nullptr;
@@ -140,7 +141,7 @@ const char* tebgpu_last_error_string(const tebgpu_ctx* ctx) { return ctx ? ctx->
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static void free_all(tebgpu_ctx* c) {
-  void* ptrs[] = {c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.T, c->spec.res, c->spec.need, c->spec.qmax, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+  void* ptrs[] = {c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.T, c->spec.res, c->spec.need, c->spec.qmax, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
                   c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
                   c->d_status, c->d_iters};
   for (void* p : ptrs)
@@ -172,6 +173,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
                V = c->lim.max_viapoints > 0 ? c->lim.max_viapoints : 1;
   CUDA_TRY(c, cudaMalloc(&c->Hb, B * 4 * nc * HROW * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->assoc, B * nc * c->MW * sizeof(unsigned long long)));
+  CUDA_TRY(c, cudaMalloc(&c->assoc3, B * nc * c->MW * sizeof(unsigned long long)));
   CUDA_TRY(c, cudaMalloc(&c->dyn_t, B * nc * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->via_idx, B * V * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->chi_parts, B * c->chunks * 4 * sizeof(double)));
@@ -246,8 +248,6 @@ int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* p) {
   if (!ctx || !p) return TEBGPU_ERR_INVALID_ARG;
   /* cost terms without a kernel yet: refuse instead of silently dropping them */
   if (p->max_vel_y != 0) { ctx->err = "holonomic edges (max_vel_y != 0) are not implemented"; return TEBGPU_ERR_UNSUPPORTED; }
-  if (p->weight_velocity_obstacle_ratio > 0) { ctx->err = "EdgeVelocityObstacleRatio is not implemented"; return TEBGPU_ERR_UNSUPPORTED; }
-  if (p->legacy_obstacle_association) { ctx->err = "legacy obstacle association is not implemented"; return TEBGPU_ERR_UNSUPPORTED; }
   if (p->footprint_type < 0 || p->footprint_type > TEB_FOOTPRINT_TWO_CIRCLES) { ctx->err = "unsupported footprint model"; return TEBGPU_ERR_UNSUPPORTED; }
   ctx->params = *p;
   ctx->have_params = true;
@@ -278,6 +278,8 @@ static KParams make_kparams(const TebParams& p, double weight_multiplier) {
   k.has_dyn = p.include_dynamic_obstacles && p.weight_obstacle != 0; /* optimal_planner.cpp:342, :648 */
   k.has_via = p.weight_viapoint != 0;
   k.pow_exponent = (p.obstacle_cost_exponent != 1.0 && p.min_obstacle_dist > 0.0);
+  /* optimal_planner.cpp:362; with the legacy association obstacles_per_vertex_ stays empty -> no ratio edges */
+  k.has_vor = p.weight_velocity_obstacle_ratio > 0 && !p.legacy_obstacle_association;
   return k;
 }
 
@@ -301,7 +303,7 @@ static DevBatch make_devbatch(tebgpu_ctx* ctx, const TebBatch* bt) {
   d.via = bt->via; d.via_count = bt->via_count; d.vel_start = bt->vel_start; d.vel_goal = bt->vel_goal;
   d.prefer_rotdir = bt->prefer_rotdir;
   d.cost = bt->cost; d.chi2 = bt->chi2; d.status = bt->status; d.lm_iters = bt->lm_iters;
-  d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts; d.dmax_parts = ctx->dmax_parts; d.rhs = ctx->rhs; d.dyn_idx = ctx->dyn_idx; d.dyn_cnt = ctx->dyn_cnt;
+  d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.assoc3 = ctx->assoc3; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts; d.dmax_parts = ctx->dmax_parts; d.rhs = ctx->rhs; d.dyn_idx = ctx->dyn_idx; d.dyn_cnt = ctx->dyn_cnt;
   d.state = ctx->state;
   d.chunks = (bt->n_cap + TP - 1) / TP;
   return d;
@@ -339,6 +341,7 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
     prof_begin(ctx, st, 2); k_build_graph<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st);
     for (int it = 0; it < args->iterations_innerloop; ++it) {
       prof_begin(ctx, st, 3); k_linearize<<<dim3(db.chunks, B), KA_THREADS, smem_a, st>>>(db, kp); ++launches; prof_end(ctx, st);
+      if (kp.has_vor) { prof_begin(ctx, st, 3); k_vor<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st); }
       if (ctx->solver == 2) {
         const int K = spec_K;
         ctx->spec.K = K;
@@ -468,6 +471,7 @@ int32_t tebgpu_compute_cost(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimi
   k_begin<<<gb, tb, 0, st>>>(db, kp);
   k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
   k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(bt->M_cap), st>>>(db, kp);
+  if (kp.has_vor) k_vor<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
   k_cost_only<<<gb, tb, 0, st>>>(db, kp, *args);
   ctx->launches = 4;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -498,6 +502,7 @@ int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* bt, int32_t outer_i
   k_begin<<<gb, tb, 0, st>>>(db, kp);
   k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
   k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(bt->M_cap), st>>>(db, kp);
+  if (kp.has_vor) k_vor<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
   ctx->launches = 3;
   CUDA_TRY(ctx, cudaGetLastError());
   const size_t per_band = (size_t)4 * bt->n_cap * HROW;

@@ -28,6 +28,7 @@ struct KParams {
   int32_t carlike;     /* !(min_turning_radius == 0 || weight_kinematics_turning_radius == 0) (:355) */
   int32_t has_vel, has_acc, has_kin, has_sp, has_rot, has_time, has_obst, has_dyn, has_via;
   int32_t pow_exponent; /* obstacle_cost_exponent != 1 && min_obstacle_dist > 0                     */
+  int32_t has_vor;      /* weight_velocity_obstacle_ratio > 0 (optimal_planner.cpp:362)              */
 };
 
 /* ------------------------------------------------------------------ g2o/stuff/misc.h */
@@ -203,6 +204,21 @@ __device__ __forceinline__ double dynamic_terms(const KParams& kp, double d, dou
   kappa = kp.p.weight_dynamic_obstacle * s0 * s0 + kp.p.weight_dynamic_obstacle_inflation * s1 * s1;
   beta = kp.p.weight_dynamic_obstacle * e0 * s0 + kp.p.weight_dynamic_obstacle_inflation * e1 * s1;
   return kp.p.weight_dynamic_obstacle * e0 * e0 + kp.p.weight_dynamic_obstacle_inflation * e1 * e1;
+}
+
+/* EdgeVelocityObstacleRatio (edge_velocity_obstacle_ratio.h:82-122): velocity bounds scaled by the proximity ratio of
+ * the first pose to an associated obstacle. Returns the ratio and d ratio / d distance. */
+__device__ __forceinline__ double proximity_ratio(const KParams& kp, double d, double& dratio) {
+  double ratio;
+  dratio = 0;
+  if (d < kp.p.obstacle_proximity_lower_bound) ratio = 0;
+  else if (d > kp.p.obstacle_proximity_upper_bound) ratio = 1;
+  else {
+    ratio = (d - kp.p.obstacle_proximity_lower_bound) / (kp.p.obstacle_proximity_upper_bound - kp.p.obstacle_proximity_lower_bound);
+    dratio = 1.0 / (kp.p.obstacle_proximity_upper_bound - kp.p.obstacle_proximity_lower_bound);
+  }
+  dratio *= kp.p.obstacle_proximity_ratio_max_vel;
+  return ratio * kp.p.obstacle_proximity_ratio_max_vel;
 }
 
 /* ------------------------------------------------------------------ TMA (1-D bulk copy) + mbarrier wrappers */

@@ -62,6 +62,7 @@ struct DevBatch {
   /* workspaces */
   double* Hb;                 /* [B][4*n_cap][12] */
   unsigned long long* assoc;  /* [B][n_cap][MW]   */
+  unsigned long long* assoc3; /* [B][n_cap][MW] legacy association: edges with multiplicity 3 (centre pose) */
   double* dyn_t;              /* [B][n_cap]       */
   int32_t* via_idx;           /* [B][V_cap]       */
   double* chi_parts;          /* [B][chunks][4]   */
@@ -170,34 +171,71 @@ __global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
   const double* P = db.poses + (size_t)b * db.n_cap * 4;
   unsigned long long* assoc = db.assoc + (size_t)b * db.n_cap * db.MW;
 
-  /* AddEdgesObstacles association (optimal_planner.cpp:484-547) */
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    unsigned long long mask[MAX_MW] = {0, 0, 0, 0};
-    if (kp.has_obst && i >= 1 && i <= n - 2) {
-      const double px = P[4 * i], py = P[4 * i + 1], th = P[4 * i + 2];
-      double sn, cs;
-      sincos(th, &sn, &cs);
-      double left_min = 1.7976931348623157e308, right_min = 1.7976931348623157e308;
-      int left = -1, right = -1;
-      const double force_d = kp.p.min_obstacle_dist * kp.p.obstacle_association_force_inclusion_factor;
-      const double cut_d = kp.p.min_obstacle_dist * kp.p.obstacle_association_cutoff_factor;
-      for (int m = 0; m < M; ++m) {
+  unsigned long long* assoc3 = db.assoc3 + (size_t)b * db.n_cap * db.MW;
+  if (!kp.p.legacy_obstacle_association) {
+    /* AddEdgesObstacles association (optimal_planner.cpp:484-547); pose 0 takes part only to feed
+     * EdgeVelocityObstacleRatio (first_vertex, :482) */
+    const int first_vertex = kp.has_vor ? 0 : 1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      unsigned long long mask[MAX_MW] = {0, 0, 0, 0};
+      if (kp.has_obst && i >= first_vertex && i <= n - 2) {
+        const double px = P[4 * i], py = P[4 * i + 1], th = P[4 * i + 2];
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        double left_min = 1.7976931348623157e308, right_min = 1.7976931348623157e308;
+        int left = -1, right = -1;
+        const double force_d = kp.p.min_obstacle_dist * kp.p.obstacle_association_force_inclusion_factor;
+        const double cut_d = kp.p.min_obstacle_dist * kp.p.obstacle_association_cutoff_factor;
+        for (int m = 0; m < M; ++m) {
+          const TebObstacle ob = so[m];
+          if (kp.p.include_dynamic_obstacles && ob.dynamic) continue;
+          const double dist = footprint_distance_only(kp, px, py, cs, sn, ob.x, ob.y, ob.radius);
+          if (dist < force_d) { mask[m >> 6] |= 1ull << (m & 63); continue; }
+          if (dist > cut_d) continue;
+          const double cx = ob.x - px, cy = ob.y - py;
+          if (cs * cy - cx * sn > 0) {
+            if (dist < left_min) { left_min = dist; left = m; }
+          } else {
+            if (dist < right_min) { right_min = dist; right = m; }
+          }
+        }
+        if (left >= 0) mask[left >> 6] |= 1ull << (left & 63);
+        if (right >= 0) mask[right >> 6] |= 1ull << (right & 63);
+      }
+      for (int w = 0; w < db.MW; ++w) assoc[(size_t)i * db.MW + w] = mask[w];
+    }
+  } else {
+    /* AddEdgesObstaclesLegacy (optimal_planner.cpp:551-643): per obstacle the closest pose and its
+     * obstacle_poses_affected/2 neighbours on both sides; the centre pose carries three identical edges */
+    for (int k = threadIdx.x; k < n * db.MW; k += blockDim.x) { assoc[k] = 0ull; assoc3[k] = 0ull; }
+    __syncthreads();
+    if (kp.has_obst) {
+      for (int m = threadIdx.x; m < M; m += blockDim.x) {
         const TebObstacle ob = so[m];
         if (kp.p.include_dynamic_obstacles && ob.dynamic) continue;
-        const double dist = footprint_distance_only(kp, px, py, cs, sn, ob.x, ob.y, ob.radius);
-        if (dist < force_d) { mask[m >> 6] |= 1ull << (m & 63); continue; }
-        if (dist > cut_d) continue;
-        const double cx = ob.x - px, cy = ob.y - py;
-        if (cs * cy - cx * sn > 0) {
-          if (dist < left_min) { left_min = dist; left = m; }
-        } else {
-          if (dist < right_min) { right_min = dist; right = m; }
+        int index = -1;
+        if (kp.p.obstacle_poses_affected >= n) {
+          index = n / 2;
+        } else { /* findClosestTrajectoryPose(centroid) timed_elastic_band.cpp:455-478, :540-553 */
+          double best = 1.7976931348623157e308;
+          for (int i = 0; i < n; ++i) {
+            const double dx = ob.x - P[4 * i], dy = ob.y - P[4 * i + 1];
+            const double d2 = dx * dx + dy * dy;
+            if (d2 < best) { best = d2; index = i; }
+          }
+        }
+        if (index <= 1 || index > n - 2) continue;
+        const unsigned long long bit = 1ull << (m & 63);
+        const int w = m >> 6;
+        atomicOr(&assoc[(size_t)index * db.MW + w], bit);
+        const int half = kp.p.obstacle_poses_affected / 2;
+        if (half >= 1) atomicOr(&assoc3[(size_t)index * db.MW + w], bit); /* explicit edge + neighbourIdx 0 twice */
+        for (int nb = 1; nb < half; ++nb) {
+          if (index + nb < n) atomicOr(&assoc[(size_t)(index + nb) * db.MW + w], bit);
+          if (index - nb >= 0) atomicOr(&assoc[(size_t)(index - nb) * db.MW + w], bit);
         }
       }
-      if (left >= 0) mask[left >> 6] |= 1ull << (left & 63);
-      if (right >= 0) mask[right >> 6] |= 1ull << (right & 63);
     }
-    for (int w = 0; w < db.MW; ++w) assoc[(size_t)i * db.MW + w] = mask[w];
   }
   /* EdgeDynamicObstacle times: t_1 = dt_0, t_{i+1} = t_i + dt_i, frozen at build (optimal_planner.cpp:662-670);
    * sequential like the reference so the sums are bitwise identical. */
@@ -266,7 +304,12 @@ __device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& d
         const TebObstacle ob = so[m];
         double g[3], kappa, beta;
         const double d = footprint_distance(kp, px, py, cs, sn, ob.x, ob.y, ob.radius, g);
-        chi_obst += obstacle_terms(kp, d, kappa, beta);
+        double cterm = obstacle_terms(kp, d, kappa, beta);
+        if (kp.p.legacy_obstacle_association &&
+            ((db.assoc3[((size_t)b * db.n_cap + i) * db.MW + w] >> (m & 63)) & 1ull)) {
+          cterm *= 3; kappa *= 3; beta *= 3; /* three identical edges on the centre pose */
+        }
+        chi_obst += cterm;
         if (want_grad && (kappa != 0 || beta != 0)) {
           U[0] += kappa * g[0] * g[0]; U[1] += kappa * g[0] * g[1]; U[2] += kappa * g[1] * g[1];
           U[3] += kappa * g[0] * g[2]; U[4] += kappa * g[1] * g[2]; U[5] += kappa * g[2] * g[2];
@@ -796,6 +839,23 @@ __device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db,
           const double e0 = kp.sw_acc_x * pen_interval((s1.v - vs[0]) * idt1, kp.p.acc_lim_x, kp.p.penalty_epsilon, sl);
           const double e1 = kp.sw_acc_th * pen_interval((s1.w - vs[2]) * idt1, kp.p.acc_lim_theta, kp.p.penalty_epsilon, sl);
           csum += e0 * e0 + e1 * e1;
+        }
+      }
+      if (kp.has_vor) { /* EdgeVelocityObstacleRatio: obstacles associated with pose i (pose 0 included) */
+        const unsigned long long* am = db.assoc + ((size_t)b * db.n_cap + i) * db.MW;
+        for (int w = 0; w < db.MW; ++w) {
+          unsigned long long mask = am[w];
+          while (mask) {
+            const int m = (w << 6) + __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            const TebObstacle ob = so[m];
+            double dratio;
+            const double d = footprint_distance_only(kp, pa[0], pa[1], ca, sa, ob.x, ob.y, ob.radius);
+            const double ratio = proximity_ratio(kp, d, dratio);
+            const double e0 = pen_interval(s1.v, ratio * kp.p.max_vel_x, 0, sl);
+            const double e1 = pen_interval(s1.w, ratio * kp.p.max_vel_theta, 0, sl);
+            csum += kp.p.weight_velocity_obstacle_ratio * (e0 * e0 + e1 * e1);
+          }
         }
       }
       chi[3] += csum;
@@ -1343,6 +1403,105 @@ __global__ void k_finalize(DevBatch db, KParams kp, TebOptimizeArgs args) {
   if (db.chi2) db.chi2[b] = st.chi2_final;
   if (db.status) db.status[b] = status;
   if (db.lm_iters) db.lm_iters[b] = st.lm_iters;
+}
+
+/* ------------------------------------------------------------------ k_vor (CTA per band; launched only when
+ * weight_velocity_obstacle_ratio > 0): EdgeVelocityObstacleRatio (edge_velocity_obstacle_ratio.h:82-122,
+ * optimal_planner.cpp:999-1021). One edge per obstacle associated with pose a over (pose a, pose a+1, dt_a); the
+ * 7x7 J^T Omega J of every anchor is added to the band written by kernel A. Even anchors first, then odd ones, so
+ * that overlapping rows are updated in a fixed order (deterministic, no atomics). */
+__global__ void __launch_bounds__(256) k_vor(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp) {
+  extern __shared__ __align__(16) unsigned char vor_raw[];
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(vor_raw);
+  __shared__ double s_red[8];
+  const int b = blockIdx.x;
+  if (!db.state[b].active) return;
+  const int n = db.n[b];
+  const int sc = db.scene_id[b];
+  const int M = db.obst_count[sc];
+  for (int m = threadIdx.x; m < M; m += blockDim.x) so[m] = db.obstacles[(size_t)sc * db.M_cap + m];
+  __syncthreads();
+  const double* P = db.poses + (size_t)b * db.n_cap * 4;
+  double* H = db.Hb + (size_t)b * 4 * db.n_cap * HROW;
+  double* rhs = db.rhs + (size_t)b * 4 * db.n_cap;
+  const double wv = kp.p.weight_velocity_obstacle_ratio;
+  double csum = 0, dmax = 0;
+  for (int parity = 0; parity < 2; ++parity) {
+    for (int a = 2 * threadIdx.x + parity; a <= n - 2; a += 2 * blockDim.x) {
+      const double* pa = P + 4 * a;
+      const double* pb = pa + 4;
+      double sn, cs;
+      sincos(pa[2], &sn, &cs);
+      const SegDer sd = seg_derivs(kp, pa[0], pa[1], pa[2], cs, sn, pb[0], pb[1], pb[2], pa[3]);
+      const bool fa = (a == 0), fb = (a + 1 == n - 1);
+      double G[28], gb[7];
+#pragma unroll
+      for (int k = 0; k < 28; ++k) G[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) gb[k] = 0;
+      const unsigned long long* am = db.assoc + ((size_t)b * db.n_cap + a) * db.MW;
+      for (int w = 0; w < db.MW; ++w) {
+        unsigned long long mask = am[w];
+        while (mask) {
+          const int m = (w << 6) + __ffsll((long long)mask) - 1;
+          mask &= mask - 1;
+          const TebObstacle ob = so[m];
+          double g[3], dratio;
+          const double d = footprint_distance(kp, pa[0], pa[1], cs, sn, ob.x, ob.y, ob.radius, g);
+          const double ratio = proximity_ratio(kp, d, dratio);
+          double s0, s1;
+          const double e0 = pen_interval(sd.v, ratio * kp.p.max_vel_x, 0, s0);
+          const double e1 = pen_interval(sd.w, ratio * kp.p.max_vel_theta, 0, s1);
+          /* e = |var| - a outside the interval: d e / d a = -1 whenever the penalty is active */
+          const double a0 = (s0 != 0) ? -kp.p.max_vel_x * dratio : 0.0, a1 = (s1 != 0) ? -kp.p.max_vel_theta * dratio : 0.0;
+          double r0[7], r1[7];
+          r0[0] = s0 * sd.dv[0] + a0 * g[0]; r0[1] = s0 * sd.dv[1] + a0 * g[1]; r0[2] = s0 * sd.dv[2] + a0 * g[2];
+          r0[3] = -s0 * sd.v * sd.idt; r0[4] = s0 * sd.dv[3]; r0[5] = s0 * sd.dv[4]; r0[6] = s0 * sd.dv[5];
+          r1[0] = a1 * g[0]; r1[1] = a1 * g[1]; r1[2] = -s1 * sd.idt + a1 * g[2];
+          r1[3] = -s1 * sd.w * sd.idt; r1[4] = 0; r1[5] = 0; r1[6] = s1 * sd.idt;
+          if (fa) { r0[0] = r0[1] = r0[2] = 0; r1[0] = r1[1] = r1[2] = 0; }
+          if (fb) { r0[4] = r0[5] = r0[6] = 0; r1[4] = r1[5] = r1[6] = 0; }
+#pragma unroll
+          for (int l = 0; l < 7; ++l) {
+#pragma unroll
+            for (int mm = 0; mm <= l; ++mm) G[(l * (l + 1)) / 2 + mm] += wv * (r0[l] * r0[mm] + r1[l] * r1[mm]);
+            gb[l] -= wv * (r0[l] * e0 + r1[l] * e1);
+          }
+          csum += wv * (e0 * e0 + e1 * e1);
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < 7; ++l) {
+        const int r = 4 * a + l;
+        if (!row_is_real(r, n)) continue; /* fixed rows stay identity (their Gram entries are zero anyway) */
+#pragma unroll
+        for (int mm = 0; mm <= l; ++mm) H[(size_t)r * HROW + (l - mm)] += G[(l * (l + 1)) / 2 + mm];
+        dmax = fmax(dmax, fabs(H[(size_t)r * HROW]));
+        H[(size_t)r * HROW + 11] += gb[l];
+        rhs[r] += gb[l];
+      }
+    }
+    __syncthreads();
+  }
+  /* chi2 of these edges belongs to the "other" family (computeCurrentCost does not scale them): chunk 0's partial */
+  csum = warp_sum(csum);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = csum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    db.chi_parts[(size_t)b * db.chunks * 4 + 3] += t;
+  }
+  __syncthreads();
+  /* the diagonal grew: keep the band's max diagonal (LM lambda init) up to date */
+  dmax = warp_max(dmax);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = db.dmax_parts[(size_t)b * db.chunks];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmax(t, s_red[w]);
+    db.dmax_parts[(size_t)b * db.chunks] = t;
+  }
 }
 
 /* ------------------------------------------------------------------ k_cost_only (thread per band):

@@ -209,6 +209,35 @@ def test_full_size_properties_c3():
     g.close()
 
 
+@pytest.mark.parametrize("legacy,vor", [(1, 0.0), (0, 2.0), (1, 2.0)])
+def test_legacy_association_and_velocity_obstacle_ratio(oracle, legacy, vor):
+    """AddEdgesObstaclesLegacy (optimal_planner.cpp:551-643, incl. the triple edge on the centre pose) and
+    EdgeVelocityObstacleRatio (edge_velocity_obstacle_ratio.h:82-122): kernel-A system and full optimisation vs oracle"""
+    p, hb0 = scenes.make_config_batch("C3", candidates=6, seed=4)
+    p.legacy_obstacle_association = legacy
+    p.obstacle_poses_affected = 10
+    p.weight_velocity_obstacle_ratio = vor
+    p.obstacle_proximity_lower_bound, p.obstacle_proximity_upper_bound = 0.2, 1.0
+    g = _gpu(hb0, p)
+    Hb, chi2 = g.build_system(hb0, 1)
+    for b in range(hb0.B):
+        n = hb0.n[b]
+        Hd, bd, c2 = oracle.build_system(p, hb0.poses[b], n, hb0.obstacles[0][:hb0.obst_count[0]], weight_multiplier=2.0,
+                                         jac_mode=oracle.JAC_ANALYTIC)
+        ref = _padded_from_dense(Hd, bd, n)
+        got = Hb[b, :4 * n]
+        assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max()
+        assert abs(chi2[b] - c2) <= 1e-12 * max(c2, 1.0)
+    args = abi.make_args(5, 4, True, 100.0, 1.0, False)
+    hg = hb0.copy()
+    g.optimize(hg, args)
+    g.close()
+    ha = hb0.copy()
+    oracle.optimize_batch(p, ha, args, jac_mode=oracle.JAC_ANALYTIC, threads=8)
+    assert _pose_diff(hg, ha).max() < 1e-6
+    assert np.allclose(hg.cost, ha.cost, rtol=1e-6) and np.array_equal(hg.lm_iters, ha.lm_iters)
+
+
 def test_solvers_and_speculation_widths_agree():
     """the three linear solvers give the same bands up to round-off; the speculation width K does not change a bit"""
     p, hb0 = scenes.make_config_batch("C4", candidates=12, seed=9)
@@ -238,10 +267,6 @@ def test_errors_are_loud():
     q.max_vel_y = 0.1
     with pytest.raises(T.TebGpuError, match="rc=-3"):
         g.set_params(q)                                   # holonomic edges: unsupported, not silently ignored
-    q = abi.default_params()
-    q.weight_velocity_obstacle_ratio = 1.0
-    with pytest.raises(T.TebGpuError, match="rc=-3"):
-        g.set_params(q)
     p2, big = scenes.make_config_batch("C2", candidates=4)
     with pytest.raises(T.TebGpuError, match="rc=-4"):
         g.optimize(big, abi.make_args())                  # exceeds the context limits
