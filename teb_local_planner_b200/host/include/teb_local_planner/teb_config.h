@@ -27,262 +27,144 @@ class TebConfig {
   RobotFootprintModelPtr robot_model;
 
   struct Trajectory {
-    double teb_autosize;
-    double dt_ref;
-    double dt_hysteresis;
-    int min_samples;
-    int max_samples;
-    bool global_plan_overwrite_orientation;
-    bool allow_init_with_backwards_motion;
-    double global_plan_viapoint_sep;
-    bool via_points_ordered;
-    double max_global_plan_lookahead_dist;
-    double global_plan_prune_distance;
-    bool exact_arc_length;
-    double force_reinit_new_goal_dist;
-    double force_reinit_new_goal_angular;
-    int feasibility_check_no_poses;
-    double feasibility_check_lookahead_distance;
-    bool publish_feedback;
-    double min_resolution_collision_check_angular;
-    int control_look_ahead_poses;
-    int prevent_look_ahead_poses_near_goal;
+    double teb_autosize = true;
+    double dt_ref = 0.3;
+    double dt_hysteresis = 0.1;
+    int min_samples = 3;
+    int max_samples = 500;
+    bool global_plan_overwrite_orientation = true;
+    bool allow_init_with_backwards_motion = false;
+    double global_plan_viapoint_sep = -1;
+    bool via_points_ordered = false;
+    double max_global_plan_lookahead_dist = 1;
+    double global_plan_prune_distance = 1;
+    bool exact_arc_length = false;
+    double force_reinit_new_goal_dist = 1;
+    double force_reinit_new_goal_angular = 0.5 * M_PI;
+    int feasibility_check_no_poses = 5;
+    double feasibility_check_lookahead_distance = -1;
+    bool publish_feedback = false;
+    double min_resolution_collision_check_angular = M_PI;
+    int control_look_ahead_poses = 1;
+    int prevent_look_ahead_poses_near_goal = 0;
   } trajectory;
 
   struct Robot {
-    double max_vel_x;
-    double max_vel_x_backwards;
-    double max_vel_y;
-    double max_vel_trans;
-    double max_vel_theta;
-    double acc_lim_x;
-    double acc_lim_y;
-    double acc_lim_theta;
-    double min_turning_radius;
-    double wheelbase;
-    bool cmd_angle_instead_rotvel;
-    bool is_footprint_dynamic;
-    bool use_proportional_saturation;
+    double max_vel_x = 0.4;
+    double max_vel_x_backwards = 0.2;
+    double max_vel_y = 0.0;
+    double max_vel_trans = 0.0;
+    double max_vel_theta = 0.3;
+    double acc_lim_x = 0.5;
+    double acc_lim_y = 0.5;
+    double acc_lim_theta = 0.5;
+    double min_turning_radius = 0;
+    double wheelbase = 1.0;
+    bool cmd_angle_instead_rotvel = false;
+    bool is_footprint_dynamic = false;
+    bool use_proportional_saturation = false;
     double transform_tolerance = 0.5;
   } robot;
 
   struct GoalTolerance {
-    double yaw_goal_tolerance;
-    double xy_goal_tolerance;
-    bool free_goal_vel;
-    double trans_stopped_vel;
-    double theta_stopped_vel;
-    bool complete_global_plan;
+    double yaw_goal_tolerance = 0.2;
+    double xy_goal_tolerance = 0.2;
+    bool free_goal_vel = false;
+    double trans_stopped_vel = 0.1;
+    double theta_stopped_vel = 0.1;
+    bool complete_global_plan = true;
   } goal_tolerance;
 
   struct Obstacles {
-    double min_obstacle_dist;
-    double inflation_dist;
-    double dynamic_obstacle_inflation_dist;
-    bool include_dynamic_obstacles;
-    bool include_costmap_obstacles;
-    double costmap_obstacles_behind_robot_dist;
-    int obstacle_poses_affected;
-    bool legacy_obstacle_association;
-    double obstacle_association_force_inclusion_factor;
-    double obstacle_association_cutoff_factor;
-    std::string costmap_converter_plugin;
-    bool costmap_converter_spin_thread;
-    int costmap_converter_rate;
-    double obstacle_proximity_ratio_max_vel;
-    double obstacle_proximity_lower_bound;
-    double obstacle_proximity_upper_bound;
+    double min_obstacle_dist = 0.5;
+    double inflation_dist = 0.6;
+    double dynamic_obstacle_inflation_dist = 0.6;
+    bool include_dynamic_obstacles = true;
+    bool include_costmap_obstacles = true;
+    double costmap_obstacles_behind_robot_dist = 1.5;
+    int obstacle_poses_affected = 25;
+    bool legacy_obstacle_association = false;
+    double obstacle_association_force_inclusion_factor = 1.5;
+    double obstacle_association_cutoff_factor = 5;
+    std::string costmap_converter_plugin = "";
+    bool costmap_converter_spin_thread = true;
+    int costmap_converter_rate = 5;
+    double obstacle_proximity_ratio_max_vel = 1;
+    double obstacle_proximity_lower_bound = 0;
+    double obstacle_proximity_upper_bound = 0.5;
   } obstacles;
 
   struct Optimization {
-    int no_inner_iterations;
-    int no_outer_iterations;
-    bool optimization_activate;
-    bool optimization_verbose;
-    double penalty_epsilon;
-    double weight_max_vel_x;
-    double weight_max_vel_y;
-    double weight_max_vel_theta;
-    double weight_acc_lim_x;
-    double weight_acc_lim_y;
-    double weight_acc_lim_theta;
-    double weight_kinematics_nh;
-    double weight_kinematics_forward_drive;
-    double weight_kinematics_turning_radius;
-    double weight_optimaltime;
-    double weight_shortest_path;
-    double weight_obstacle;
-    double weight_inflation;
-    double weight_dynamic_obstacle;
-    double weight_dynamic_obstacle_inflation;
-    double weight_velocity_obstacle_ratio;
-    double weight_viapoint;
-    double weight_prefer_rotdir;
-    double weight_adapt_factor;
-    double obstacle_cost_exponent;
+    int no_inner_iterations = 5;
+    int no_outer_iterations = 4;
+    bool optimization_activate = true;
+    bool optimization_verbose = false;
+    double penalty_epsilon = 0.05;
+    double weight_max_vel_x = 2;
+    double weight_max_vel_y = 2;
+    double weight_max_vel_theta = 1;
+    double weight_acc_lim_x = 1;
+    double weight_acc_lim_y = 1;
+    double weight_acc_lim_theta = 1;
+    double weight_kinematics_nh = 1000;
+    double weight_kinematics_forward_drive = 1;
+    double weight_kinematics_turning_radius = 1;
+    double weight_optimaltime = 1;
+    double weight_shortest_path = 0;
+    double weight_obstacle = 50;
+    double weight_inflation = 0.1;
+    double weight_dynamic_obstacle = 50;
+    double weight_dynamic_obstacle_inflation = 0.1;
+    double weight_velocity_obstacle_ratio = 0;
+    double weight_viapoint = 1;
+    double weight_prefer_rotdir = 50;
+    double weight_adapt_factor = 2.0;
+    double obstacle_cost_exponent = 1.0;
   } optim;
 
   struct HomotopyClasses {
-    bool enable_homotopy_class_planning;
-    bool enable_multithreading;
-    bool simple_exploration;
-    int max_number_classes;
-    int max_number_plans_in_current_class;
-    double selection_cost_hysteresis;
-    double selection_prefer_initial_plan;
-    double selection_obst_cost_scale;
-    double selection_viapoint_cost_scale;
-    bool selection_alternative_time_cost;
-    double selection_dropping_probability;
-    double switching_blocking_period;
-    int roadmap_graph_no_samples;
-    double roadmap_graph_area_width;
-    double roadmap_graph_area_length_scale;
-    double h_signature_prescaler;
-    double h_signature_threshold;
-    double obstacle_keypoint_offset;
-    double obstacle_heading_threshold;
-    bool viapoints_all_candidates;
-    bool visualize_hc_graph;
-    double visualize_with_time_as_z_axis_scale;
-    bool delete_detours_backwards;
-    double detours_orientation_tolerance;
-    double length_start_orientation_vector;
-    double max_ratio_detours_duration_best_duration;
+    bool enable_homotopy_class_planning = true;
+    bool enable_multithreading = true;
+    bool simple_exploration = false;
+    int max_number_classes = 5;
+    int max_number_plans_in_current_class = 1;
+    double selection_cost_hysteresis = 1.0;
+    double selection_prefer_initial_plan = 0.95;
+    double selection_obst_cost_scale = 100.0;
+    double selection_viapoint_cost_scale = 1.0;
+    bool selection_alternative_time_cost = false;
+    double selection_dropping_probability = 0.0;
+    double switching_blocking_period = 0.0;
+    int roadmap_graph_no_samples = 15;
+    double roadmap_graph_area_width = 6;
+    double roadmap_graph_area_length_scale = 1.0;
+    double h_signature_prescaler = 1;
+    double h_signature_threshold = 0.1;
+    double obstacle_keypoint_offset = 0.1;
+    double obstacle_heading_threshold = 0.45;
+    bool viapoints_all_candidates = true;
+    bool visualize_hc_graph = false;
+    double visualize_with_time_as_z_axis_scale = 0.0;
+    bool delete_detours_backwards = true;
+    double detours_orientation_tolerance = M_PI / 2.0;
+    double length_start_orientation_vector = 0.4;
+    double max_ratio_detours_duration_best_duration = 3.0;
   } hcp;
 
   struct Recovery {
-    bool shrink_horizon_backup;
-    double shrink_horizon_min_duration;
-    bool oscillation_recovery;
-    double oscillation_v_eps;
-    double oscillation_omega_eps;
-    double oscillation_recovery_min_duration;
-    double oscillation_filter_duration;
-    bool divergence_detection_enable;
-    int divergence_detection_max_chi_squared;
+    bool shrink_horizon_backup = true;
+    double shrink_horizon_min_duration = 10;
+    bool oscillation_recovery = true;
+    double oscillation_v_eps = 0.1;
+    double oscillation_omega_eps = 0.1;
+    double oscillation_recovery_min_duration = 10;
+    double oscillation_filter_duration = 10;
+    bool divergence_detection_enable = false;
+    int divergence_detection_max_chi_squared = 10;
   } recovery;
 
-  TebConfig() {
-    odom_topic = "odom";
-    map_frame = "odom";
-    robot_model = std::make_shared<PointRobotFootprint>();
-    trajectory.teb_autosize = true;
-    trajectory.dt_ref = 0.3;
-    trajectory.dt_hysteresis = 0.1;
-    trajectory.min_samples = 3;
-    trajectory.max_samples = 500;
-    trajectory.global_plan_overwrite_orientation = true;
-    trajectory.allow_init_with_backwards_motion = false;
-    trajectory.global_plan_viapoint_sep = -1;
-    trajectory.via_points_ordered = false;
-    trajectory.max_global_plan_lookahead_dist = 1;
-    trajectory.global_plan_prune_distance = 1;
-    trajectory.exact_arc_length = false;
-    trajectory.force_reinit_new_goal_dist = 1;
-    trajectory.force_reinit_new_goal_angular = 0.5 * M_PI;
-    trajectory.feasibility_check_no_poses = 5;
-    trajectory.feasibility_check_lookahead_distance = -1;
-    trajectory.publish_feedback = false;
-    trajectory.min_resolution_collision_check_angular = M_PI;
-    trajectory.control_look_ahead_poses = 1;
-    trajectory.prevent_look_ahead_poses_near_goal = 0;
-    robot.max_vel_x = 0.4;
-    robot.max_vel_x_backwards = 0.2;
-    robot.max_vel_y = 0.0;
-    robot.max_vel_trans = 0.0;
-    robot.max_vel_theta = 0.3;
-    robot.acc_lim_x = 0.5;
-    robot.acc_lim_y = 0.5;
-    robot.acc_lim_theta = 0.5;
-    robot.min_turning_radius = 0;
-    robot.wheelbase = 1.0;
-    robot.cmd_angle_instead_rotvel = false;
-    robot.is_footprint_dynamic = false;
-    robot.use_proportional_saturation = false;
-    goal_tolerance.xy_goal_tolerance = 0.2;
-    goal_tolerance.yaw_goal_tolerance = 0.2;
-    goal_tolerance.free_goal_vel = false;
-    goal_tolerance.trans_stopped_vel = 0.1;
-    goal_tolerance.theta_stopped_vel = 0.1;
-    goal_tolerance.complete_global_plan = true;
-    obstacles.min_obstacle_dist = 0.5;
-    obstacles.inflation_dist = 0.6;
-    obstacles.dynamic_obstacle_inflation_dist = 0.6;
-    obstacles.include_dynamic_obstacles = true;
-    obstacles.include_costmap_obstacles = true;
-    obstacles.costmap_obstacles_behind_robot_dist = 1.5;
-    obstacles.obstacle_poses_affected = 25;
-    obstacles.legacy_obstacle_association = false;
-    obstacles.obstacle_association_force_inclusion_factor = 1.5;
-    obstacles.obstacle_association_cutoff_factor = 5;
-    obstacles.costmap_converter_plugin = "";
-    obstacles.costmap_converter_spin_thread = true;
-    obstacles.costmap_converter_rate = 5;
-    obstacles.obstacle_proximity_ratio_max_vel = 1;
-    obstacles.obstacle_proximity_lower_bound = 0;
-    obstacles.obstacle_proximity_upper_bound = 0.5;
-    optim.no_inner_iterations = 5;
-    optim.no_outer_iterations = 4;
-    optim.optimization_activate = true;
-    optim.optimization_verbose = false;
-    optim.penalty_epsilon = 0.05;
-    optim.weight_max_vel_x = 2;
-    optim.weight_max_vel_y = 2;
-    optim.weight_max_vel_theta = 1;
-    optim.weight_acc_lim_x = 1;
-    optim.weight_acc_lim_y = 1;
-    optim.weight_acc_lim_theta = 1;
-    optim.weight_kinematics_nh = 1000;
-    optim.weight_kinematics_forward_drive = 1;
-    optim.weight_kinematics_turning_radius = 1;
-    optim.weight_optimaltime = 1;
-    optim.weight_shortest_path = 0;
-    optim.weight_obstacle = 50;
-    optim.weight_inflation = 0.1;
-    optim.weight_dynamic_obstacle = 50;
-    optim.weight_dynamic_obstacle_inflation = 0.1;
-    optim.weight_velocity_obstacle_ratio = 0;
-    optim.weight_viapoint = 1;
-    optim.weight_prefer_rotdir = 50;
-    optim.weight_adapt_factor = 2.0;
-    optim.obstacle_cost_exponent = 1.0;
-    hcp.enable_homotopy_class_planning = true;
-    hcp.enable_multithreading = true;
-    hcp.simple_exploration = false;
-    hcp.max_number_classes = 5;
-    hcp.max_number_plans_in_current_class = 1;
-    hcp.selection_cost_hysteresis = 1.0;
-    hcp.selection_prefer_initial_plan = 0.95;
-    hcp.selection_obst_cost_scale = 100.0;
-    hcp.selection_viapoint_cost_scale = 1.0;
-    hcp.selection_alternative_time_cost = false;
-    hcp.selection_dropping_probability = 0.0;
-    hcp.obstacle_keypoint_offset = 0.1;
-    hcp.obstacle_heading_threshold = 0.45;
-    hcp.roadmap_graph_no_samples = 15;
-    hcp.roadmap_graph_area_width = 6;
-    hcp.roadmap_graph_area_length_scale = 1.0;
-    hcp.h_signature_prescaler = 1;
-    hcp.h_signature_threshold = 0.1;
-    hcp.switching_blocking_period = 0.0;
-    hcp.viapoints_all_candidates = true;
-    hcp.visualize_hc_graph = false;
-    hcp.visualize_with_time_as_z_axis_scale = 0.0;
-    hcp.delete_detours_backwards = true;
-    hcp.detours_orientation_tolerance = M_PI / 2.0;
-    hcp.length_start_orientation_vector = 0.4;
-    hcp.max_ratio_detours_duration_best_duration = 3.0;
-    recovery.shrink_horizon_backup = true;
-    recovery.shrink_horizon_min_duration = 10;
-    recovery.oscillation_recovery = true;
-    recovery.oscillation_v_eps = 0.1;
-    recovery.oscillation_omega_eps = 0.1;
-    recovery.oscillation_recovery_min_duration = 10;
-    recovery.oscillation_filter_duration = 10;
-    recovery.divergence_detection_enable = false;
-    recovery.divergence_detection_max_chi_squared = 10;
-  }
+  /* defaults = the reference's TebConfig() constructor (teb_config.h:245-390), written as member initialisers */
+  TebConfig() : odom_topic("odom"), map_frame("odom"), robot_model(std::make_shared<PointRobotFootprint>()) {}
 
   /* POD block for the device (every field the kernels read) */
   TebParams toParams() const {
