@@ -44,6 +44,8 @@ def load_library(build_if_missing=False):
     L.tebgpu_optimize_batch.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs)]
     L.tebgpu_optimize_batch_device.restype = C.c_int32
     L.tebgpu_optimize_batch_device.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs), vp]
+    L.tebgpu_set_linearize_variant.restype = C.c_int32
+    L.tebgpu_set_linearize_variant.argtypes = [vp, C.c_int32]
     L.tebgpu_set_speculation.restype = C.c_int32
     L.tebgpu_set_speculation.argtypes = [vp, C.c_int32]
     L.tebgpu_set_solver.restype = C.c_int32
@@ -111,6 +113,9 @@ class TebGpu:
     def optimize_device(self, batch_struct, args, stream=None):
         self._check(self.lib.tebgpu_optimize_batch_device(self.ctx, C.byref(batch_struct), C.byref(args), stream),
                     "tebgpu_optimize_batch_device")
+
+    def set_linearize_variant(self, v):
+        self._check(self.lib.tebgpu_set_linearize_variant(self.ctx, int(v)), "tebgpu_set_linearize_variant")
 
     def set_speculation(self, k):
         self._check(self.lib.tebgpu_set_speculation(self.ctx, int(k)), "tebgpu_set_speculation")

@@ -24,6 +24,8 @@ struct tebgpu_ctx {
   bool have_params = false;
   std::string err;
   int64_t launches = 0;
+  int linearize_variant = 0;  /* 0: 128-thread CTA per 32-pose tile (default, measured faster: 24 warps/SM resident);
+                                 1: one warp per tile (full lanes, but 8 warps/SM by shared memory) */
   int spec_k = 0;  /* speculation width: 0 = auto (6 when B*6 systems fit one warp per SM sub-partition, else 4) */
   int solver = 2;  /* 2: speculative thread-per-(band,trial) LDL^T (default), 1: block cyclic reduction, 0: sequential */
   int MW = 1;
@@ -218,6 +220,8 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     return TEBGPU_ERR_CAPACITY;
   }
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
   if ((int)nc <= BCR_MAX_POSES && kb_bcr_smem_bytes((int)nc, (int)M) <= 232448)
     CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -252,6 +256,15 @@ int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* p) {
   ctx->params = *p;
   ctx->have_params = true;
   return TEBGPU_OK;
+}
+
+static void launch_linearize(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int M_cap, cudaStream_t st) {
+  if (ctx->linearize_variant == 1) {
+    const int groups = (db.chunks + KW_WARPS - 1) / KW_WARPS;
+    k_linearize_w<<<dim3(groups, B), 32 * KW_WARPS, kw_smem_bytes(M_cap), st>>>(db, kp);
+  } else {
+    k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(M_cap), st>>>(db, kp);
+  }
 }
 
 static KParams make_kparams(const TebParams& p, double weight_multiplier) {
@@ -340,7 +353,7 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
     if (p.teb_autosize) { prof_begin(ctx, st, 1); k_auto_resize<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st); }
     prof_begin(ctx, st, 2); k_build_graph<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st);
     for (int it = 0; it < args->iterations_innerloop; ++it) {
-      prof_begin(ctx, st, 3); k_linearize<<<dim3(db.chunks, B), KA_THREADS, smem_a, st>>>(db, kp); ++launches; prof_end(ctx, st);
+      prof_begin(ctx, st, 3); launch_linearize(ctx, db, kp, B, bt->M_cap, st); ++launches; prof_end(ctx, st);
       if (kp.has_vor) { prof_begin(ctx, st, 3); k_vor<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st); }
       if (ctx->solver == 2) {
         const int K = spec_K;
@@ -384,6 +397,12 @@ int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[9], int64_t count
   CUDA_TRY(ctx, cudaDeviceSynchronize());
   prof_collect(ctx);
   for (int k = 0; k < 9; ++k) { ms_out[k] = ctx->prof_ms[k]; count_out[k] = ctx->prof_cnt[k]; ctx->prof_ms[k] = 0; ctx->prof_cnt[k] = 0; }
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_set_linearize_variant(tebgpu_ctx* ctx, int32_t v) {
+  if (!ctx || v < 0 || v > 1) return TEBGPU_ERR_INVALID_ARG;
+  ctx->linearize_variant = v;
   return TEBGPU_OK;
 }
 
@@ -470,7 +489,7 @@ int32_t tebgpu_compute_cost(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimi
   const int B = bt->B, tb = 128, gb = ((B > bt->S ? B : bt->S) + tb - 1) / tb;
   k_begin<<<gb, tb, 0, st>>>(db, kp);
   k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
-  k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(bt->M_cap), st>>>(db, kp);
+  launch_linearize(ctx, db, kp, B, bt->M_cap, st);
   if (kp.has_vor) k_vor<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
   k_cost_only<<<gb, tb, 0, st>>>(db, kp, *args);
   ctx->launches = 4;
@@ -501,7 +520,7 @@ int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* bt, int32_t outer_i
   const int B = bt->B, tb = 128, gb = ((B > bt->S ? B : bt->S) + tb - 1) / tb;
   k_begin<<<gb, tb, 0, st>>>(db, kp);
   k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
-  k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(bt->M_cap), st>>>(db, kp);
+  launch_linearize(ctx, db, kp, B, bt->M_cap, st);
   if (kp.has_vor) k_vor<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
   ctx->launches = 3;
   CUDA_TRY(ctx, cudaGetLastError());

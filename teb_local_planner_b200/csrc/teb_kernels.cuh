@@ -352,126 +352,13 @@ __device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& d
   }
 }
 
-/* ------------------------------------------------------------------ k_linearize ("kernel A") */
-struct KASmem {
-  /* sizes in doubles */
-  static constexpr int POSES = (TP + 4) * 4;
-  static constexpr int SC = (TP + 4) * 2;
-  static constexpr int SEG = (TP + 3) * 9;
-  static constexpr int JB = (TP + 2) * JSTRIDE;
-  static constexpr int EH = (TP + 2) * 8;
-  static constexpr int START = 2 * 7 + 2;
-  static constexpr int UN = TP * 9;
-  static constexpr int RED = 4 * (KA_THREADS / 32) + 8 + (KA_THREADS / 32);
-  static constexpr int STAGE = KA_THREADS * HROW; /* aliases JB..: needs JB+EH+START+UN >= STAGE? no: separate */
-};
-
-__host__ __device__ inline size_t ka_smem_bytes(int M_cap) {
-  size_t d = KASmem::POSES + KASmem::SC + KASmem::SEG + KASmem::EH + KASmem::START + KASmem::UN + KASmem::RED + 2;
-  size_t jb = KASmem::JB > KASmem::STAGE ? KASmem::JB : KASmem::STAGE;
-  return (d + jb) * sizeof(double) + (size_t)M_cap * sizeof(TebObstacle) + 64;
-}
-
-__global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParams kp) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int b = blockIdx.y;
-  const BandState* st = &db.state[b];
-  if (!st->active) return;
-  const int n = db.n[b];
-  const int p0 = blockIdx.x * TP;
-  if (p0 >= n) return;
-  const int tid = threadIdx.x;
-
-  double* sP = reinterpret_cast<double*>(smem_raw);             /* poses tile, slot j <-> pose p0-2+j */
-  double* sJ = sP + KASmem::POSES;                              /* Jacobian blocks, later the output stage */
-  constexpr int JBMAX = KASmem::JB > KASmem::STAGE ? KASmem::JB : KASmem::STAGE;
-  double* sSC = sJ + JBMAX;
-  double* sSeg = sSC + KASmem::SC;
-  double* sE = sSeg + KASmem::SEG;
-  double* sStart = sE + KASmem::EH;
-  double* sU = sStart + KASmem::START;
-  double* sRed = sU + KASmem::UN;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sRed + KASmem::RED);
-  TebObstacle* so = reinterpret_cast<TebObstacle*>(
-      (reinterpret_cast<uintptr_t>(bar) + 16 + 15) & ~static_cast<uintptr_t>(15)); /* TMA destination: 16-byte aligned */
-
-  const int s = db.scene_id[b];
-  const int M = db.obst_count[s];
-  const int lo = max(p0 - 2, 0), hi = min(p0 + TP + 2, n); /* poses staged */
-  const double* gP = db.poses + (size_t)b * db.n_cap * 4;
-
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t bytesP = (uint32_t)(hi - lo) * 32u;
-    const uint32_t bytesO = (uint32_t)M * (uint32_t)sizeof(TebObstacle);
-    mbar_expect_tx(bar, bytesP + bytesO);
-    tma_load_1d(sP + (size_t)(lo - (p0 - 2)) * 4, gP + (size_t)lo * 4, bytesP, bar);
-    if (bytesO) tma_load_1d(so, db.obstacles + (size_t)s * db.M_cap, bytesO, bar);
-  }
-  /* zero the Jacobian blocks while the copies are in flight */
-  {
-    double2* z2 = reinterpret_cast<double2*>(sJ); /* sJ is 16-byte aligned, JB is even */
-    for (int k = tid; k < KASmem::JB / 2; k += KA_THREADS) z2[k] = make_double2(0.0, 0.0);
-  }
-  for (int k = tid; k < KASmem::EH + KASmem::START; k += KA_THREADS) sE[k] = 0.0;
-  mbar_wait(bar, 0);
-
-  double chi[4] = {0, 0, 0, 0}; /* obstacles, via, time-optimal, other */
-
-  /* stage 1 (warps 0-2): sin/cos of every staged pose and the derivative bundle of the segment that starts there
-   * (slot j <-> pose / segment p0-2+j); stage 1' (warps 6-7, concurrently): unary terms of the tile's poses */
-  if (tid < TP + 4) {
-    const int i = p0 - 2 + tid;
-    if (i >= lo && i < hi) {
-      double sn, cs;
-      sincos(sP[4 * tid + 2], &sn, &cs);
-      sSC[2 * tid] = cs;
-      sSC[2 * tid + 1] = sn;
-      if (tid < TP + 3 && i + 1 < hi && i <= n - 2) {
-        const double* pa = sP + 4 * tid;
-        const double* pb = pa + 4;
-        SegDer sd = seg_derivs(kp, pa[0], pa[1], pa[2], cs, sn, pb[0], pb[1], pb[2], pa[3]);
-        double* q = sSeg + 9 * tid;
-        q[0] = sd.v; q[1] = sd.w; q[2] = sd.idt;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) q[3 + k] = sd.dv[k];
-      }
-    }
-  }
-  {
-    const int il = tid - (KA_THREADS - TP); /* last TP threads */
-    if (il >= 0) {
-      const int i = p0 + il;
-      double U[6] = {0, 0, 0, 0, 0, 0}, ub[3] = {0, 0, 0};
-      if (i < n) {
-        const int j = il + 2;
-        double sn = 0, cs = 1;
-        if (kp.p.footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
-        unary_terms(kp, db, b, s, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
-        if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
-          const double dt = sP[4 * j + 3];
-          chi[2] += kp.p.weight_optimaltime * dt * dt;
-        }
-      }
-      double* u = sU + 9 * il;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) u[k] = U[k];
-      u[6] = ub[0]; u[7] = ub[1]; u[8] = ub[2];
-    }
-  }
-  __syncthreads();
-
-
-  /* stage 3a: chain edges anchored at a (EdgeVelocity, EdgeKinematics*, EdgeShortestPath, EdgePreferRotDir,
-   * EdgeAcceleration / Start / Goal) -> sqrt(weight)-scaled Jacobian rows over the columns 4a .. 4a+10 */
-  /* group 0 (warps 0-2): velocity / kinematics / shortest-path / rotdir rows; group 1 (warps 3-5): acceleration rows */
-  const int part = (tid < TP + 2) ? 0 : ((tid >= KA_P1OFF && tid < KA_P1OFF + TP + 2) ? 1 : -1);
-  if (part >= 0) {
-    const int at = part == 0 ? tid : tid - KA_P1OFF; /* anchor slot */
+/* Jacobian rows of the chain edges anchored at a = p0-2+at (sqrt(weight)-scaled, columns 4a .. 4a+10).
+ * part 0: EdgeVelocity, EdgeKinematics*, EdgeShortestPath, EdgePreferRotDir rows; part 1: EdgeAcceleration / Start / Goal
+ * rows. Returns this part's chi2 contribution if the anchor belongs to the tile (a >= p0), else 0. */
+__device__ __forceinline__ double anchor_rows(const KParams& kp, const DevBatch& db, int b, int part, int at, int p0, int n,
+                                              const double* sP, const double* sSC, const double* sSeg, double* sJ,
+                                              double* sE, double* sStart) {
+  double chi3 = 0;
     const int a = p0 - 2 + at;
     if (a >= 0 && a <= n - 2) {
       double* J = sJ + (size_t)at * JSTRIDE; /* rows 0..5: 7 columns, rows 6,7: 11 columns at offset 42 */
@@ -645,18 +532,21 @@ __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParam
         } else {
           csum += eh[6] * eh[6] + eh[7] * eh[7];
         }
-        chi[3] += csum;
+        chi3 += csum;
       }
     }
-  }
+  return chi3;
+}
 
-  __syncthreads();
-
-  /* stage 4: one thread per band row r = 4i + c gathers J^T J over the (<= 3) anchors that touch it */
-  double acc[11];
+/* One band row r = 4(p0 + t/4) + t%4: gathers J^T J over the (<= 3) anchors that touch it, adds the unary block and
+ * the time-optimal term. acc[k] = H[r][r-k], brow = b[r]. */
+__device__ __forceinline__ void gather_row(const KParams& kp, int t, int p0, int n, const double* sP, const double* sJ,
+                                           const double* sE, const double* sStart, const double* sU, double (&acc)[11],
+                                           double& brow) {
 #pragma unroll
   for (int k = 0; k < 11; ++k) acc[k] = 0;
-  double brow = 0;
+  brow = 0;
+  const int tid = t;
   {
     const int il = tid >> 2, c = tid & 3;
     const int i = p0 + il;
@@ -721,6 +611,137 @@ __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParam
       }
     }
   }
+}
+
+/* ------------------------------------------------------------------ k_linearize ("kernel A") */
+struct KASmem {
+  /* sizes in doubles */
+  static constexpr int POSES = (TP + 4) * 4;
+  static constexpr int SC = (TP + 4) * 2;
+  static constexpr int SEG = (TP + 3) * 9;
+  static constexpr int JB = (TP + 2) * JSTRIDE;
+  static constexpr int EH = (TP + 2) * 8;
+  static constexpr int START = 2 * 7 + 2;
+  static constexpr int UN = TP * 9;
+  static constexpr int RED = 4 * (KA_THREADS / 32) + 8 + (KA_THREADS / 32);
+  static constexpr int STAGE = KA_THREADS * HROW; /* aliases JB..: needs JB+EH+START+UN >= STAGE? no: separate */
+};
+
+__host__ __device__ inline size_t ka_smem_bytes(int M_cap) {
+  size_t d = KASmem::POSES + KASmem::SC + KASmem::SEG + KASmem::EH + KASmem::START + KASmem::UN + KASmem::RED + 2;
+  size_t jb = KASmem::JB > KASmem::STAGE ? KASmem::JB : KASmem::STAGE;
+  return (d + jb) * sizeof(double) + (size_t)M_cap * sizeof(TebObstacle) + 64;
+}
+
+__global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParams kp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int b = blockIdx.y;
+  const BandState* st = &db.state[b];
+  if (!st->active) return;
+  const int n = db.n[b];
+  const int p0 = blockIdx.x * TP;
+  if (p0 >= n) return;
+  const int tid = threadIdx.x;
+
+  double* sP = reinterpret_cast<double*>(smem_raw);             /* poses tile, slot j <-> pose p0-2+j */
+  double* sJ = sP + KASmem::POSES;                              /* Jacobian blocks, later the output stage */
+  constexpr int JBMAX = KASmem::JB > KASmem::STAGE ? KASmem::JB : KASmem::STAGE;
+  double* sSC = sJ + JBMAX;
+  double* sSeg = sSC + KASmem::SC;
+  double* sE = sSeg + KASmem::SEG;
+  double* sStart = sE + KASmem::EH;
+  double* sU = sStart + KASmem::START;
+  double* sRed = sU + KASmem::UN;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sRed + KASmem::RED);
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(
+      (reinterpret_cast<uintptr_t>(bar) + 16 + 15) & ~static_cast<uintptr_t>(15)); /* TMA destination: 16-byte aligned */
+
+  const int s = db.scene_id[b];
+  const int M = db.obst_count[s];
+  const int lo = max(p0 - 2, 0), hi = min(p0 + TP + 2, n); /* poses staged */
+  const double* gP = db.poses + (size_t)b * db.n_cap * 4;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytesP = (uint32_t)(hi - lo) * 32u;
+    const uint32_t bytesO = (uint32_t)M * (uint32_t)sizeof(TebObstacle);
+    mbar_expect_tx(bar, bytesP + bytesO);
+    tma_load_1d(sP + (size_t)(lo - (p0 - 2)) * 4, gP + (size_t)lo * 4, bytesP, bar);
+    if (bytesO) tma_load_1d(so, db.obstacles + (size_t)s * db.M_cap, bytesO, bar);
+  }
+  /* zero the Jacobian blocks while the copies are in flight */
+  {
+    double2* z2 = reinterpret_cast<double2*>(sJ); /* sJ is 16-byte aligned, JB is even */
+    for (int k = tid; k < KASmem::JB / 2; k += KA_THREADS) z2[k] = make_double2(0.0, 0.0);
+  }
+  for (int k = tid; k < KASmem::EH + KASmem::START; k += KA_THREADS) sE[k] = 0.0;
+  mbar_wait(bar, 0);
+
+  double chi[4] = {0, 0, 0, 0}; /* obstacles, via, time-optimal, other */
+
+  /* stage 1 (warps 0-2): sin/cos of every staged pose and the derivative bundle of the segment that starts there
+   * (slot j <-> pose / segment p0-2+j); stage 1' (warps 6-7, concurrently): unary terms of the tile's poses */
+  if (tid < TP + 4) {
+    const int i = p0 - 2 + tid;
+    if (i >= lo && i < hi) {
+      double sn, cs;
+      sincos(sP[4 * tid + 2], &sn, &cs);
+      sSC[2 * tid] = cs;
+      sSC[2 * tid + 1] = sn;
+      if (tid < TP + 3 && i + 1 < hi && i <= n - 2) {
+        const double* pa = sP + 4 * tid;
+        const double* pb = pa + 4;
+        SegDer sd = seg_derivs(kp, pa[0], pa[1], pa[2], cs, sn, pb[0], pb[1], pb[2], pa[3]);
+        double* q = sSeg + 9 * tid;
+        q[0] = sd.v; q[1] = sd.w; q[2] = sd.idt;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q[3 + k] = sd.dv[k];
+      }
+    }
+  }
+  {
+    const int il = tid - (KA_THREADS - TP); /* last TP threads */
+    if (il >= 0) {
+      const int i = p0 + il;
+      double U[6] = {0, 0, 0, 0, 0, 0}, ub[3] = {0, 0, 0};
+      if (i < n) {
+        const int j = il + 2;
+        double sn = 0, cs = 1;
+        if (kp.p.footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
+        unary_terms(kp, db, b, s, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
+        if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
+          const double dt = sP[4 * j + 3];
+          chi[2] += kp.p.weight_optimaltime * dt * dt;
+        }
+      }
+      double* u = sU + 9 * il;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) u[k] = U[k];
+      u[6] = ub[0]; u[7] = ub[1]; u[8] = ub[2];
+    }
+  }
+  __syncthreads();
+
+
+  /* stage 3a: chain edges anchored at a (EdgeVelocity, EdgeKinematics*, EdgeShortestPath, EdgePreferRotDir,
+   * EdgeAcceleration / Start / Goal) -> sqrt(weight)-scaled Jacobian rows over the columns 4a .. 4a+10 */
+  /* group 0 (warps 0-2): velocity / kinematics / shortest-path / rotdir rows; group 1 (warps 3-5): acceleration rows */
+  const int part = (tid < TP + 2) ? 0 : ((tid >= KA_P1OFF && tid < KA_P1OFF + TP + 2) ? 1 : -1);
+  if (part >= 0) {
+    const int at = part == 0 ? tid : tid - KA_P1OFF; /* anchor slot */
+    chi[3] += anchor_rows(kp, db, b, part, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
+  }
+
+  __syncthreads();
+
+  /* stage 4: one thread per band row r = 4i + c gathers J^T J over the (<= 3) anchors that touch it */
+  double acc[11];
+  double brow;
+  gather_row(kp, tid, p0, n, sP, sJ, sE, sStart, sU, acc, brow);
   __syncthreads(); /* every thread is done reading sJ: reuse it as the output stage */
   {
     double* o = sJ + (size_t)tid * HROW;
@@ -737,23 +758,186 @@ __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParam
     tma_store_1d(gH, sJ, (uint32_t)rows * HROW * 8u);
     tma_store_commit_wait();
   }
-  /* max diagonal of the tile's real rows (computeLambdaInit) */
+  /* tile partials: chi2 by family and the max diagonal of the real rows (computeLambdaInit). Every thread parks its
+   * five values in shared memory (the dead Jacobian region behind the output stage), then ONE warp folds them in a
+   * fixed order - a quarter of the shuffle traffic of a per-warp tree reduction. */
   {
     const int il = tid >> 2, c = tid & 3;
     const int r = 4 * (p0 + il) + c;
-    double dm = (p0 + il < n && row_is_real(r, n)) ? fabs(acc[0]) : 0.0;
-    dm = warp_max(dm);
-    if ((tid & 31) == 0) sRed[4 * (KA_THREADS / 32) + 8 + (tid >> 5)] = dm;
+    const double dm = (p0 + il < n && row_is_real(r, n)) ? fabs(acc[0]) : 0.0;
+    static_assert((KASmem::JB > KASmem::STAGE ? KASmem::JB : KASmem::STAGE) >= KA_THREADS * HROW + 5 * KA_THREADS,
+                  "partials do not fit behind the output stage");
+    double* park = sJ + KA_THREADS * HROW; /* stage uses KA_THREADS*HROW doubles of the JBMAX region */
+    park[0 * KA_THREADS + tid] = chi[0];
+    park[1 * KA_THREADS + tid] = chi[1];
+    park[2 * KA_THREADS + tid] = chi[2];
+    park[3 * KA_THREADS + tid] = chi[3];
+    park[4 * KA_THREADS + tid] = dm;
+    __syncthreads();
+    if (tid < 32) {
+      double v[5];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        double sacc = 0;
+#pragma unroll
+        for (int w = 0; w < KA_THREADS / 32; ++w) sacc += park[k * KA_THREADS + w * 32 + tid];
+        v[k] = warp_sum(sacc);
+      }
+      double m = 0;
+#pragma unroll
+      for (int w = 0; w < KA_THREADS / 32; ++w) m = fmax(m, park[4 * KA_THREADS + w * 32 + tid]);
+      v[4] = warp_max(m);
+      if (tid == 0) {
+        double* cp = db.chi_parts + ((size_t)b * db.chunks + blockIdx.x) * 4;
+        cp[0] = v[0]; cp[1] = v[1]; cp[2] = v[2]; cp[3] = v[3];
+        db.dmax_parts[(size_t)b * db.chunks + blockIdx.x] = v[4];
+      }
+    }
   }
-  /* chi2 partials of this tile */
-  block_sum<4, KA_THREADS / 32>(chi, sRed, sRed + 4 * (KA_THREADS / 32));
-  if (tid == 0) {
-    double* cp = db.chi_parts + ((size_t)b * db.chunks + blockIdx.x) * 4;
-    const double* r = sRed + 4 * (KA_THREADS / 32);
-    cp[0] = r[0]; cp[1] = r[1]; cp[2] = r[2]; cp[3] = r[3];
-    double dm = 0;
-    for (int w = 0; w < KA_THREADS / 32; ++w) dm = fmax(dm, sRed[4 * (KA_THREADS / 32) + 8 + w]);
-    db.dmax_parts[(size_t)b * db.chunks + blockIdx.x] = dm;
+}
+
+/* ------------------------------------------------------------------ k_linearize_w ("kernel A", warp per tile)
+ * Same arithmetic as k_linearize (shared device functions), different mapping: ONE WARP owns a 32-pose tile end to end,
+ * so every phase runs with all 32 lanes busy (pose / anchor / row per lane) and the only synchronisation is
+ * __syncwarp. A CTA holds KW_WARPS independent tiles of the same band and shares the scene's obstacle table. */
+constexpr int KW_WARPS = 4;
+struct KWSmem {
+  static constexpr int JBMAX = (KASmem::JB > 4 * TP * HROW ? KASmem::JB : 4 * TP * HROW);
+  static constexpr int REG = ((KASmem::POSES + JBMAX + KASmem::SC + KASmem::SEG + KASmem::EH + KASmem::START + KASmem::UN + 2 + 1) / 2) * 2;
+};
+__host__ __device__ inline size_t kw_smem_bytes(int M_cap) {
+  return (size_t)KW_WARPS * KWSmem::REG * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 64;
+}
+
+__global__ void __launch_bounds__(32 * KW_WARPS) k_linearize_w(const __grid_constant__ DevBatch db,
+                                                               const __grid_constant__ KParams kp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  static_assert(TP == 32, "the warp-per-tile kernel maps one pose / four rows to a lane");
+  const int b = blockIdx.y;
+  if (!db.state[b].active) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = db.n[b];
+  const int s = db.scene_id[b];
+  const int M = db.obst_count[s];
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(reinterpret_cast<double*>(smem_raw) + (size_t)KW_WARPS * KWSmem::REG);
+  {
+    const double2* src = reinterpret_cast<const double2*>(db.obstacles + (size_t)s * db.M_cap);
+    double2* dst = reinterpret_cast<double2*>(so);
+    for (int k = threadIdx.x; k < 3 * M; k += 32 * KW_WARPS) dst[k] = src[k];
+  }
+  __syncthreads();
+  const int chunk = blockIdx.x * KW_WARPS + warp;
+  const int p0 = chunk * TP;
+  if (p0 >= n) return;
+
+  double* sP = reinterpret_cast<double*>(smem_raw) + (size_t)warp * KWSmem::REG; /* poses tile, slot j <-> pose p0-2+j */
+  double* sJ = sP + KASmem::POSES;                                               /* Jacobian blocks, later the output stage */
+  double* sSC = sJ + KWSmem::JBMAX;
+  double* sSeg = sSC + KASmem::SC;
+  double* sE = sSeg + KASmem::SEG;
+  double* sStart = sE + KASmem::EH;
+  double* sU = sStart + KASmem::START;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sU + KASmem::UN);
+
+  const int lo = max(p0 - 2, 0), hi = min(p0 + TP + 2, n); /* poses staged */
+  const double* gP = db.poses + (size_t)b * db.n_cap * 4;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const uint32_t bytesP = (uint32_t)(hi - lo) * 32u;
+    mbar_expect_tx(bar, bytesP);
+    tma_load_1d(sP + (size_t)(lo - (p0 - 2)) * 4, gP + (size_t)lo * 4, bytesP, bar);
+  }
+  { /* zero the Jacobian blocks while the copy is in flight */
+    double2* z2 = reinterpret_cast<double2*>(sJ);
+    for (int k = lane; k < KASmem::JB / 2; k += 32) z2[k] = make_double2(0.0, 0.0);
+    for (int k = lane; k < KASmem::EH + KASmem::START; k += 32) sE[k] = 0.0;
+  }
+  mbar_wait(bar, 0);
+
+  double chi[4] = {0, 0, 0, 0}; /* obstacles, via, time-optimal, other */
+  /* phase I: sin/cos + segment derivative bundle per staged pose; unary terms of the lane's pose */
+  for (int tt = lane; tt < TP + 4; tt += 32) {
+    const int i = p0 - 2 + tt;
+    if (i >= lo && i < hi) {
+      double sn, cs;
+      sincos(sP[4 * tt + 2], &sn, &cs);
+      sSC[2 * tt] = cs;
+      sSC[2 * tt + 1] = sn;
+      if (tt < TP + 3 && i + 1 < hi && i <= n - 2) {
+        const double* pa = sP + 4 * tt;
+        const double* pb = pa + 4;
+        SegDer sd = seg_derivs(kp, pa[0], pa[1], pa[2], cs, sn, pb[0], pb[1], pb[2], pa[3]);
+        double* q = sSeg + 9 * tt;
+        q[0] = sd.v; q[1] = sd.w; q[2] = sd.idt;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q[3 + k] = sd.dv[k];
+      }
+    }
+  }
+  {
+    const int il = lane;
+    const int i = p0 + il;
+    double U[6] = {0, 0, 0, 0, 0, 0}, ub[3] = {0, 0, 0};
+    if (i < n) {
+      const int j = il + 2;
+      double sn = 0, cs = 1;
+      if (kp.p.footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
+      unary_terms(kp, db, b, s, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
+      if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
+        const double dt = sP[4 * j + 3];
+        chi[2] += kp.p.weight_optimaltime * dt * dt;
+      }
+    }
+    double* u = sU + 9 * il;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) u[k] = U[k];
+    u[6] = ub[0]; u[7] = ub[1]; u[8] = ub[2];
+  }
+  __syncwarp();
+  /* phase II: chain-edge Jacobian rows of every anchor of the tile (+2 halo anchors) */
+  for (int at = lane; at < TP + 2; at += 32) {
+    chi[3] += anchor_rows(kp, db, b, 0, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
+    chi[3] += anchor_rows(kp, db, b, 1, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
+  }
+  __syncwarp();
+  /* phase III: four band rows per lane */
+  double accs[4][11], brows[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) gather_row(kp, q * 32 + lane, p0, n, sP, sJ, sE, sStart, sU, accs[q], brows[q]);
+  __syncwarp(); /* every lane is done reading sJ: reuse it as the output stage */
+  double dm = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int t = q * 32 + lane;
+    double* o = sJ + (size_t)t * HROW;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) o[k] = accs[q][k];
+    o[11] = brows[q];
+    const int r = 4 * p0 + t;
+    if (p0 + (t >> 2) < n) {
+      db.rhs[(size_t)b * 4 * db.n_cap + r] = brows[q];
+      if (row_is_real(r, n)) dm = fmax(dm, fabs(accs[q][0]));
+    }
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    const int rows = 4 * (min(p0 + TP, n) - p0);
+    double* gH = db.Hb + ((size_t)b * 4 * db.n_cap + (size_t)4 * p0) * HROW;
+    tma_store_1d(gH, sJ, (uint32_t)rows * HROW * 8u);
+    tma_store_commit_wait();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) chi[k] = warp_sum(chi[k]);
+  dm = warp_max(dm);
+  if (lane == 0) {
+    double* cp = db.chi_parts + ((size_t)b * db.chunks + chunk) * 4;
+    cp[0] = chi[0]; cp[1] = chi[1]; cp[2] = chi[2]; cp[3] = chi[3];
+    db.dmax_parts[(size_t)b * db.chunks + chunk] = dm;
   }
 }
 

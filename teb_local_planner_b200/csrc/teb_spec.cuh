@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
  * The four trial solutions of a band sit in adjacent lanes of the solver's interleaved scratch (one 32-byte sector per
  * row), so the CTA stages them - and the scene's obstacle table and the four trial states - in shared memory once. */
 __host__ __device__ inline size_t eval_smem_bytes(int n_cap, int M_cap, int K) {
-  return (size_t)K * 4 * n_cap * sizeof(double) * 2 + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 16;
+  return ((size_t)K * 2 + 2) * 4 * n_cap * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 16;
 }
 
 __global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KParams kp, SpecBufs sp, int round) {
@@ -234,7 +234,9 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KPa
   const int N = 4 * n;
   double* sdx = reinterpret_cast<double*>(ev_raw);           /* [K][4 n_cap] */
   double* sT = sdx + (size_t)SPEC_K * 4 * db.n_cap;           /* [K][n_cap][4] */
-  TebObstacle* so = reinterpret_cast<TebObstacle*>(sT + (size_t)SPEC_K * 4 * db.n_cap);
+  double* sP0 = sT + (size_t)SPEC_K * 4 * db.n_cap;           /* [n_cap][4] current band */
+  double* sB = sP0 + (size_t)4 * db.n_cap;                    /* [4 n_cap] right-hand side */
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(sB + (size_t)4 * db.n_cap);
   const int sc = db.scene_id[b];
   const int M = db.obst_count[sc];
   {
@@ -242,7 +244,11 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KPa
     for (int m = tid; m < M; m += 32 * SPEC_K) so[m] = go[m];
     /* rows of the K trial solutions: system index K b + k -> solver warp (K b + k) >> 5, lane (K b + k) & 31: the
      * trials of a band are adjacent lanes of the interleaved scratch (K even: pairs never straddle a tile) */
+    const double* gP = db.poses + (size_t)b * db.n_cap * 4;
+    const double* grhs = db.rhs + (size_t)b * 4 * db.n_cap;
     for (int r = tid; r < N; r += 32 * SPEC_K) {
+      sP0[r] = gP[r];
+      sB[r] = grhs[r];
       for (int kk = 0; kk < SPEC_K; kk += 2) {
         const int tsys = b * SPEC_K + kk;
         const double2 a = *reinterpret_cast<const double2*>(sp.dx + (size_t)(tsys >> 5) * 32 * 4 * db.n_cap +
@@ -260,16 +266,14 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KPa
   if (mine) {
     const bool ok = res[5] != 0.0;
     const double lambda = res[6];
-    const double* gP = db.poses + (size_t)b * db.n_cap * 4;
-    const double* grhs = db.rhs + (size_t)b * 4 * db.n_cap;
     const double* mydx = sdx + (size_t)k * 4 * db.n_cap;
     double* myT = sT + (size_t)k * 4 * db.n_cap;
     double* gT = sp.T + ((size_t)b * SPEC_K + k) * 4 * db.n_cap;
     /* trial state x [+] dx and computeScale() = sum dx (lambda dx + b) */
     for (int r = lane; r < N; r += 32) {
-      double xv = gP[r];
+      double xv = sP0[r];
       if (row_is_real(r, n)) {
-        const double bb = grhs[r];
+        const double bb = sB[r];
         const double dx = ok ? mydx[r] : bb; /* CSparse leaves x = b when the factorisation fails */
         scl += dx * (lambda * dx + bb);
         xv = ((r & 3) == 2) ? normalize_theta(xv + dx) : xv + dx;

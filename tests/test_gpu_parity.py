@@ -71,6 +71,19 @@ def test_kernel_a_system_matches_oracle(oracle, cfg):
     g.close()
 
 
+def test_kernel_a_thread_mappings_agree():
+    """warp-per-tile (default) and CTA-per-tile kernel A share their arithmetic: identical band, chi2 to round-off"""
+    p, hb = scenes.make_config_batch("C4", candidates=6, seed=2)
+    g = _gpu(hb, p)
+    g.set_linearize_variant(1)
+    H1, c1 = g.build_system(hb, 2)
+    g.set_linearize_variant(0)
+    H0, c0 = g.build_system(hb, 2)
+    g.close()
+    assert np.array_equal(H1, H0)
+    assert np.allclose(c1, c0, rtol=1e-13)
+
+
 def test_kernel_a_all_edge_families(oracle):
     """two-circles footprint, cost exponent, exact arc length, shortest path, prefer-rotdir, car-like, free goal vel"""
     p, hb = scenes.make_config_batch("C3", candidates=4, seed=5)
