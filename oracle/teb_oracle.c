@@ -86,7 +86,7 @@ static inline double fast_sigmoid(double x) { return x / (1 + fabs(x)); } /* mis
 /* ------------------------------------------------------------------ band / graph data structures */
 enum EdgeType {
   E_OBST = 0, E_INFL, E_DYN, E_VIA, E_VEL, E_ACC, E_ACC_START, E_ACC_GOAL, E_TIMEOPT, E_SHORTEST,
-  E_KIN_DD, E_KIN_CL, E_ROTDIR, E_VEL_OBST_RATIO, E_NTYPES
+  E_KIN_DD, E_KIN_CL, E_ROTDIR, E_VEL_OBST_RATIO, E_VEL_HOLO, E_ACC_HOLO, E_ACC_HOLO_START, E_ACC_HOLO_GOAL, E_NTYPES
 };
 
 typedef struct Graph Graph;
@@ -96,16 +96,16 @@ typedef struct Edge {
   int nv;          /* number of vertices */
   int vkind[5];    /* 0 pose, 1 timediff */
   int vidx[5];     /* pose / timediff index in the band */
-  int dim;         /* error dimension */
-  double info[2];  /* diagonal information matrix */
-  double err[2];   /* cached _error */
+  int dim;         /* error dimension (<= 3) */
+  double info[3];  /* diagonal information matrix */
+  double err[3];   /* cached _error */
   double t;        /* EdgeDynamicObstacle::t_ */
   double meas;     /* EdgePreferRotDir::_measurement */
   const TebObstacle* ob;
   const double* via;
   const double* twist; /* vel_start / vel_goal */
   void (*compute_error)(struct Edge*, Graph*);
-  double J[5][6];  /* per vertex: row-major dim x vdim */
+  double J[5][9];  /* per vertex: row-major dim x vdim */
 } Edge;
 
 struct Graph {
@@ -294,6 +294,62 @@ static void ce_vel_obst_ratio(Edge* e, Graph* g) {
   e->err[0] = teb_oracle_penalty_interval(vel, max_vel_fwd, 0);
   e->err[1] = teb_oracle_penalty_interval(omega, max_omega, 0);
 }
+/* holonomic segment velocities in the frame of the first pose (edge_velocity.h:247-254, edge_acceleration.h:502-517) */
+static inline void seg_vel_holo(const double* p1, const double* p2, double dt, double* vx, double* vy, double* omega) {
+  double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+  double c1 = cos(p1[2]), s1 = sin(p1[2]);
+  double r_dx = c1 * dx + s1 * dy;
+  double r_dy = -s1 * dx + c1 * dy;
+  *vx = r_dx / dt;
+  *vy = r_dy / dt;
+  *omega = nt(p2[2] - p1[2]) / dt;
+}
+/* EdgeVelocityHolonomic::computeError edge_velocity.h:236-273 */
+static void ce_velocity_holo(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double vx, vy, omega;
+  seg_vel_holo(P(g, e->vidx[0]), P(g, e->vidx[1]), DT(g, e->vidx[2]), &vx, &vy, &omega);
+  double rem_y = sqrt(fmax(0.0, c->max_vel_trans * c->max_vel_trans - vx * vx));
+  double rem_x = sqrt(fmax(0.0, c->max_vel_trans * c->max_vel_trans - vy * vy));
+  double max_vel_y = fmin(rem_y, c->max_vel_y);
+  double max_vel_x = fmin(rem_x, c->max_vel_x);
+  double max_vel_x_backwards = fmin(rem_x, c->max_vel_x_backwards);
+  e->err[0] = teb_oracle_penalty_interval2(vx, -max_vel_x_backwards, max_vel_x, 0.0);
+  e->err[1] = teb_oracle_penalty_interval(vy, max_vel_y, 0.0);
+  e->err[2] = teb_oracle_penalty_interval(omega, c->max_vel_theta, c->penalty_epsilon);
+}
+/* EdgeAccelerationHolonomic::computeError edge_acceleration.h:487-540 */
+static void ce_acc_holo(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double dt1 = DT(g, e->vidx[3]), dt2 = DT(g, e->vidx[4]);
+  double v1x, v1y, w1, v2x, v2y, w2;
+  seg_vel_holo(P(g, e->vidx[0]), P(g, e->vidx[1]), dt1, &v1x, &v1y, &w1);
+  seg_vel_holo(P(g, e->vidx[1]), P(g, e->vidx[2]), dt2, &v2x, &v2y, &w2);
+  double dt12 = dt1 + dt2;
+  e->err[0] = teb_oracle_penalty_interval((v2x - v1x) * 2 / dt12, c->acc_lim_x, c->penalty_epsilon);
+  e->err[1] = teb_oracle_penalty_interval((v2y - v1y) * 2 / dt12, c->acc_lim_y, c->penalty_epsilon);
+  e->err[2] = teb_oracle_penalty_interval((w2 - w1) * 2 / dt12, c->acc_lim_theta, c->penalty_epsilon);
+}
+/* EdgeAccelerationHolonomicStart::computeError edge_acceleration.h:580-620 */
+static void ce_acc_holo_start(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double dt = DT(g, e->vidx[2]);
+  double v2x, v2y, w2;
+  seg_vel_holo(P(g, e->vidx[0]), P(g, e->vidx[1]), dt, &v2x, &v2y, &w2);
+  e->err[0] = teb_oracle_penalty_interval((v2x - e->twist[0]) / dt, c->acc_lim_x, c->penalty_epsilon);
+  e->err[1] = teb_oracle_penalty_interval((v2y - e->twist[1]) / dt, c->acc_lim_y, c->penalty_epsilon);
+  e->err[2] = teb_oracle_penalty_interval((w2 - e->twist[2]) / dt, c->acc_lim_theta, c->penalty_epsilon);
+}
+/* EdgeAccelerationHolonomicGoal::computeError edge_acceleration.h:672-712 */
+static void ce_acc_holo_goal(Edge* e, Graph* g) {
+  const TebParams* c = g->cfg;
+  double dt = DT(g, e->vidx[2]);
+  double v1x, v1y, w1;
+  seg_vel_holo(P(g, e->vidx[0]), P(g, e->vidx[1]), dt, &v1x, &v1y, &w1);
+  e->err[0] = teb_oracle_penalty_interval((e->twist[0] - v1x) / dt, c->acc_lim_x, c->penalty_epsilon);
+  e->err[1] = teb_oracle_penalty_interval((e->twist[1] - v1y) / dt, c->acc_lim_y, c->penalty_epsilon);
+  e->err[2] = teb_oracle_penalty_interval((e->twist[2] - w1) / dt, c->acc_lim_theta, c->penalty_epsilon);
+}
 /* EdgeTimeOptimal::computeError edge_time_optimal.h:88-96 */
 static void ce_timeopt(Edge* e, Graph* g) { e->err[0] = DT(g, e->vidx[0]); }
 /* EdgeShortestPath::computeError edge_shortest_path.h:73-81 */
@@ -352,7 +408,7 @@ static inline void vertex_oplus(Graph* g, int kind, int idx, const double* d) {
 static void linearize_numeric(Edge* e, Graph* g) {
   const double delta = 1e-9;
   const double scalar = 1.0 / (2 * delta);
-  double err_before[2] = {e->err[0], e->err[1]};
+  double err_before[3] = {e->err[0], e->err[1], e->err[2]};
   for (int k = 0; k < e->nv; ++k) {
     if (edge_vertex_fixed(g, e, k)) continue;
     int vd = vdim(e->vkind[k]);
@@ -363,20 +419,23 @@ static void linearize_numeric(Edge* e, Graph* g) {
       add[d] = delta;
       vertex_oplus(g, e->vkind[k], e->vidx[k], add);
       e->compute_error(e, g);
-      double eb0 = e->err[0], eb1 = e->err[1];
+      double eb0 = e->err[0], eb1 = e->err[1], eb2 = e->err[2];
       r[0] = save[0]; r[1] = save[1]; r[2] = save[2]; r[3] = save[3]; /* pop() */
       add[d] = -delta;
       vertex_oplus(g, e->vkind[k], e->vidx[k], add);
       e->compute_error(e, g);
       eb0 -= e->err[0];
       eb1 -= e->err[1];
+      eb2 -= e->err[2];
       r[0] = save[0]; r[1] = save[1]; r[2] = save[2]; r[3] = save[3];
       e->J[k][0 * vd + d] = scalar * eb0;
       if (e->dim > 1) e->J[k][1 * vd + d] = scalar * eb1;
+      if (e->dim > 2) e->J[k][2 * vd + d] = scalar * eb2;
     }
   }
   e->err[0] = err_before[0];
   e->err[1] = err_before[1];
+  e->err[2] = err_before[2];
 }
 
 /* EdgeKinematicsDiffDrive::linearizeOplus — the analytic override compiled into the reference
@@ -472,6 +531,22 @@ static void footprint_grad(const TebParams* c, const double* pose, double ox, do
   grad[0] = nrm > 0 ? dx / nrm : 0;
   grad[1] = nrm > 0 ? dy / nrm : 0;
   grad[2] = 0;
+}
+
+typedef struct HoloD {
+  double vx, vy, w;
+  double dvx[7], dvy[7], dw[7]; /* d / d (x1,y1,th1,x2,y2,th2,dt) */
+} HoloD;
+static void holo_derivs(const double* p1, const double* p2, double dt, HoloD* h) {
+  double dx = p2[0] - p1[0], dy = p2[1] - p1[1];
+  double c1 = cos(p1[2]), s1 = sin(p1[2]);
+  double rdx = c1 * dx + s1 * dy, rdy = -s1 * dx + c1 * dy;
+  double idt = 1.0 / dt;
+  h->vx = rdx * idt; h->vy = rdy * idt; h->w = nt(p2[2] - p1[2]) * idt;
+  double a[7] = {-c1, -s1, rdy, c1, s1, 0, 0}, b[7] = {s1, -c1, -rdx, -s1, c1, 0, 0};
+  for (int k = 0; k < 6; ++k) { h->dvx[k] = a[k] * idt; h->dvy[k] = b[k] * idt; h->dw[k] = 0; }
+  h->dvx[6] = -h->vx * idt; h->dvy[6] = -h->vy * idt;
+  h->dw[2] = -idt; h->dw[5] = idt; h->dw[6] = -h->w * idt;
 }
 
 static void linearize_analytic(Edge* e, Graph* g) {
@@ -597,6 +672,73 @@ static void linearize_analytic(Edge* e, Graph* g) {
       }
       e->J[2][0] = s0 * s.dv[6];
       e->J[2][1] = s1 * s.dw[6];
+      break;
+    }
+    case E_VEL_HOLO: {
+      const double *p1 = P(g, e->vidx[0]), *p2 = P(g, e->vidx[1]);
+      double dt = DT(g, e->vidx[2]);
+      HoloD h;
+      holo_derivs(p1, p2, dt, &h);
+      double vt2 = c->max_vel_trans * c->max_vel_trans;
+      double rem_y = sqrt(fmax(0.0, vt2 - h.vx * h.vx)), rem_x = sqrt(fmax(0.0, vt2 - h.vy * h.vy));
+      double mvy = fmin(rem_y, c->max_vel_y), mvx = fmin(rem_x, c->max_vel_x), mvxb = fmin(rem_x, c->max_vel_x_backwards);
+      double s0 = d_interval2(h.vx, -mvxb, mvx, 0.0), s1 = d_interval(h.vy, mvy, 0.0);
+      double s2 = d_interval(h.w, c->max_vel_theta, c->penalty_epsilon);
+      /* bound derivative: d rem_x / d vy = -vy / rem_x when rem_x is the active (smaller) bound and positive */
+      double lim0 = s0 < 0 ? c->max_vel_x_backwards : c->max_vel_x;
+      double k0 = (s0 != 0 && !(lim0 < rem_x) && rem_x > 0) ? (-h.vy / rem_x) : 0.0; /* d bound / d vy */
+      double k1 = (s1 != 0 && !(c->max_vel_y < rem_y) && rem_y > 0) ? (-h.vx / rem_y) : 0.0; /* d bound / d vx */
+      for (int d = 0; d < 3; ++d) {
+        e->J[0][0 * 3 + d] = s0 * h.dvx[d] - k0 * h.dvy[d];         e->J[1][0 * 3 + d] = s0 * h.dvx[3 + d] - k0 * h.dvy[3 + d];
+        e->J[0][1 * 3 + d] = s1 * h.dvy[d] - k1 * h.dvx[d];         e->J[1][1 * 3 + d] = s1 * h.dvy[3 + d] - k1 * h.dvx[3 + d];
+        e->J[0][2 * 3 + d] = s2 * h.dw[d];                          e->J[1][2 * 3 + d] = s2 * h.dw[3 + d];
+      }
+      e->J[2][0] = s0 * h.dvx[6] - k0 * h.dvy[6];
+      e->J[2][1] = s1 * h.dvy[6] - k1 * h.dvx[6];
+      e->J[2][2] = s2 * h.dw[6];
+      break;
+    }
+    case E_ACC_HOLO: {
+      double dt1 = DT(g, e->vidx[3]), dt2 = DT(g, e->vidx[4]);
+      HoloD a, bq;
+      holo_derivs(P(g, e->vidx[0]), P(g, e->vidx[1]), dt1, &a);
+      holo_derivs(P(g, e->vidx[1]), P(g, e->vidx[2]), dt2, &bq);
+      double T = dt1 + dt2;
+      double acc[3] = {(bq.vx - a.vx) * 2 / T, (bq.vy - a.vy) * 2 / T, (bq.w - a.w) * 2 / T};
+      double sl[3] = {d_interval(acc[0], c->acc_lim_x, c->penalty_epsilon), d_interval(acc[1], c->acc_lim_y, c->penalty_epsilon),
+                      d_interval(acc[2], c->acc_lim_theta, c->penalty_epsilon)};
+      const double* da[3] = {a.dvx, a.dvy, a.dw};
+      const double* db[3] = {bq.dvx, bq.dvy, bq.dw};
+      for (int r = 0; r < 3; ++r) {
+        for (int d = 0; d < 3; ++d) {
+          e->J[0][r * 3 + d] = sl[r] * (-2 * da[r][d] / T);
+          e->J[1][r * 3 + d] = sl[r] * (2 * (db[r][d] - da[r][3 + d]) / T);
+          e->J[2][r * 3 + d] = sl[r] * (2 * db[r][3 + d] / T);
+        }
+        e->J[3][r] = sl[r] * (-2 * da[r][6] / T - acc[r] / T);
+        e->J[4][r] = sl[r] * (2 * db[r][6] / T - acc[r] / T);
+      }
+      break;
+    }
+    case E_ACC_HOLO_START:
+    case E_ACC_HOLO_GOAL: {
+      double dt = DT(g, e->vidx[2]);
+      HoloD h;
+      holo_derivs(P(g, e->vidx[0]), P(g, e->vidx[1]), dt, &h);
+      double sg = (e->type == E_ACC_HOLO_START) ? 1.0 : -1.0; /* start: (v_seg - v0)/dt, goal: (v_goal - v_seg)/dt */
+      double val[3] = {h.vx, h.vy, h.w};
+      double acc[3], sl[3];
+      double lim[3] = {c->acc_lim_x, c->acc_lim_y, c->acc_lim_theta};
+      const double* dd[3] = {h.dvx, h.dvy, h.dw};
+      for (int r = 0; r < 3; ++r) {
+        acc[r] = sg * (val[r] - e->twist[r]) / dt;
+        sl[r] = d_interval(acc[r], lim[r], c->penalty_epsilon);
+        for (int d = 0; d < 3; ++d) {
+          e->J[0][r * 3 + d] = sl[r] * sg * dd[r][d] / dt;
+          e->J[1][r * 3 + d] = sl[r] * sg * dd[r][3 + d] / dt;
+        }
+        e->J[2][r] = sl[r] * (sg * dd[r][6] / dt - acc[r] / dt);
+      }
       break;
     }
     case E_TIMEOPT: e->J[0][0] = 1; break;
@@ -856,6 +998,19 @@ static void add_edges_via_points(Graph* g) {
 /* AddEdgesVelocity optimal_planner.cpp:720-769 (non-holonomic branch) */
 static void add_edges_velocity(Graph* g) {
   const TebParams* c = g->cfg;
+  if (c->max_vel_y != 0) { /* holonomic robot (optimal_planner.cpp:745-767) */
+    if (c->weight_max_vel_x == 0 && c->weight_max_vel_y == 0 && c->weight_max_vel_theta == 0) return;
+    for (int i = 0; i < g->n - 1; ++i) {
+      Edge* e = new_edge(g, E_VEL_HOLO, 3, ce_velocity_holo);
+      set_vertex(e, 0, 0, i);
+      set_vertex(e, 1, 0, i + 1);
+      set_vertex(e, 2, 1, i);
+      e->info[0] = c->weight_max_vel_x;
+      e->info[1] = c->weight_max_vel_y;
+      e->info[2] = c->weight_max_vel_theta;
+    }
+    return;
+  }
   if (c->weight_max_vel_x == 0 && c->weight_max_vel_theta == 0) return;
   for (int i = 0; i < g->n - 1; ++i) {
     Edge* e = new_edge(g, E_VEL, 2, ce_velocity);
@@ -872,6 +1027,27 @@ static void add_edges_acceleration(Graph* g) {
   const TebParams* c = g->cfg;
   if (c->weight_acc_lim_x == 0 && c->weight_acc_lim_theta == 0) return;
   int n = g->n;
+  if (!(c->max_vel_y == 0 || c->acc_lim_y == 0)) { /* holonomic robot (optimal_planner.cpp:824-871) */
+    if (g->vel_start[3] != 0) {
+      Edge* e = new_edge(g, E_ACC_HOLO_START, 3, ce_acc_holo_start);
+      set_vertex(e, 0, 0, 0); set_vertex(e, 1, 0, 1); set_vertex(e, 2, 1, 0);
+      e->twist = g->vel_start;
+      e->info[0] = c->weight_acc_lim_x; e->info[1] = c->weight_acc_lim_y; e->info[2] = c->weight_acc_lim_theta;
+    }
+    for (int i = 0; i < n - 2; ++i) {
+      Edge* e = new_edge(g, E_ACC_HOLO, 3, ce_acc_holo);
+      set_vertex(e, 0, 0, i); set_vertex(e, 1, 0, i + 1); set_vertex(e, 2, 0, i + 2);
+      set_vertex(e, 3, 1, i); set_vertex(e, 4, 1, i + 1);
+      e->info[0] = c->weight_acc_lim_x; e->info[1] = c->weight_acc_lim_y; e->info[2] = c->weight_acc_lim_theta;
+    }
+    if (g->vel_goal[3] != 0) {
+      Edge* e = new_edge(g, E_ACC_HOLO_GOAL, 3, ce_acc_holo_goal);
+      set_vertex(e, 0, 0, n - 2); set_vertex(e, 1, 0, n - 1); set_vertex(e, 2, 1, n - 2);
+      e->twist = g->vel_goal;
+      e->info[0] = c->weight_acc_lim_x; e->info[1] = c->weight_acc_lim_y; e->info[2] = c->weight_acc_lim_theta;
+    }
+    return;
+  }
   if (g->vel_start[3] != 0) {
     Edge* e = new_edge(g, E_ACC_START, 2, ce_acc_start);
     set_vertex(e, 0, 0, 0);
@@ -961,7 +1137,6 @@ static void clear_graph(Graph* g) {
 /* buildGraph optimal_planner.cpp:323-366 */
 static int build_graph(Graph* g, double weight_multiplier) {
   const TebParams* c = g->cfg;
-  if (c->max_vel_y != 0) return TEBGPU_ERR_UNSUPPORTED;                 /* holonomic edges not restated */
   /* AddTEBVertices resizes and clears obstacles_per_vertex_ (optimal_planner.cpp:427-439) */
   free(g->opv); free(g->opv_cnt);
   g->opv = (int*)malloc(sizeof(int) * (size_t)g->n * (g->M + 2));
@@ -1014,7 +1189,7 @@ static void build_system(Graph* g, int jac_mode) {
   for (int k = 0; k < g->n_edges; ++k) {
     Edge* e = g->edges[k];
     linearize(e, g, jac_mode);
-    double omega_r[2];
+    double omega_r[3];
     for (int d = 0; d < e->dim; ++d) omega_r[d] = -e->info[d] * e->err[d];
     for (int i = 0; i < e->nv; ++i) {
       if (edge_vertex_fixed(g, e, i)) continue;

@@ -219,16 +219,20 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     c->err = "shared-memory footprint exceeds 227 KB for these limits (max_poses / max_obstacles too large)";
     return TEBGPU_ERR_CAPACITY;
   }
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
   if ((int)nc <= BCR_MAX_POSES && kb_bcr_smem_bytes((int)nc, (int)M) <= 232448)
     CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kb_bcr_smem_bytes((int)nc, (int)M)));
   CUDA_TRY(c, cudaFuncSetAttribute(k_build_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_g));
   /* ask for the full shared-memory carveout: occupancy of the tile kernels is shared-memory bound */
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   tebgpu_default_params(&c->params);
@@ -251,7 +255,6 @@ int32_t tebgpu_destroy(tebgpu_ctx* ctx) {
 int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* p) {
   if (!ctx || !p) return TEBGPU_ERR_INVALID_ARG;
   /* cost terms without a kernel yet: refuse instead of silently dropping them */
-  if (p->max_vel_y != 0) { ctx->err = "holonomic edges (max_vel_y != 0) are not implemented"; return TEBGPU_ERR_UNSUPPORTED; }
   if (p->footprint_type < 0 || p->footprint_type > TEB_FOOTPRINT_TWO_CIRCLES) { ctx->err = "unsupported footprint model"; return TEBGPU_ERR_UNSUPPORTED; }
   ctx->params = *p;
   ctx->have_params = true;
@@ -259,11 +262,14 @@ int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* p) {
 }
 
 static void launch_linearize(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int M_cap, cudaStream_t st) {
+  const bool holo = kp.holo_vel || kp.holo_acc; /* holonomic rows (vy, acc y) compiled into their own instantiation */
   if (ctx->linearize_variant == 1) {
     const int groups = (db.chunks + KW_WARPS - 1) / KW_WARPS;
-    k_linearize_w<<<dim3(groups, B), 32 * KW_WARPS, kw_smem_bytes(M_cap), st>>>(db, kp);
+    if (holo) k_linearize_w<true><<<dim3(groups, B), 32 * KW_WARPS, kw_smem_bytes(M_cap), st>>>(db, kp);
+    else k_linearize_w<false><<<dim3(groups, B), 32 * KW_WARPS, kw_smem_bytes(M_cap), st>>>(db, kp);
   } else {
-    k_linearize<<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(M_cap), st>>>(db, kp);
+    if (holo) k_linearize<true><<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(M_cap), st>>>(db, kp);
+    else k_linearize<false><<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(M_cap), st>>>(db, kp);
   }
 }
 
@@ -280,8 +286,13 @@ static KParams make_kparams(const TebParams& p, double weight_multiplier) {
   k.sw_kin_2 = std::sqrt(k.carlike ? p.weight_kinematics_turning_radius : p.weight_kinematics_forward_drive);
   k.sw_sp = std::sqrt(p.weight_shortest_path);
   k.sw_rot = std::sqrt(p.weight_prefer_rotdir);
-  k.has_vel = !(p.weight_max_vel_x == 0 && p.weight_max_vel_theta == 0);
-  k.has_acc = !(p.weight_acc_lim_x == 0 && p.weight_acc_lim_theta == 0);
+  /* holonomic edge families: optimal_planner.cpp:722 / :745 (velocity), :778 / :824 (acceleration) */
+  k.holo_vel = p.max_vel_y != 0;
+  k.holo_acc = p.max_vel_y != 0 && p.acc_lim_y != 0;
+  k.sw_vel_y = std::sqrt(p.weight_max_vel_y); k.sw_acc_y = std::sqrt(p.weight_acc_lim_y);
+  k.has_vel = k.holo_vel ? !(p.weight_max_vel_x == 0 && p.weight_max_vel_y == 0 && p.weight_max_vel_theta == 0)
+                         : !(p.weight_max_vel_x == 0 && p.weight_max_vel_theta == 0);
+  k.has_acc = !(p.weight_acc_lim_x == 0 && p.weight_acc_lim_theta == 0); /* weight_acc_lim_y is not consulted (:768) */
   k.has_kin = k.carlike ? !(p.weight_kinematics_nh == 0 && p.weight_kinematics_turning_radius == 0)
                         : !(p.weight_kinematics_nh == 0 && p.weight_kinematics_forward_drive == 0);
   k.has_sp = p.weight_shortest_path != 0;

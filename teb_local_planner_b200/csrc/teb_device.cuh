@@ -29,6 +29,9 @@ struct KParams {
   int32_t has_vel, has_acc, has_kin, has_sp, has_rot, has_time, has_obst, has_dyn, has_via;
   int32_t pow_exponent; /* obstacle_cost_exponent != 1 && min_obstacle_dist > 0                     */
   int32_t has_vor;      /* weight_velocity_obstacle_ratio > 0 (optimal_planner.cpp:362)              */
+  int32_t holo_vel;     /* max_vel_y != 0: EdgeVelocityHolonomic (optimal_planner.cpp:722, :745)        */
+  int32_t holo_acc;     /* max_vel_y != 0 && acc_lim_y != 0: EdgeAccelerationHolonomic* (:778, :824)     */
+  double sw_vel_y, sw_acc_y;
 };
 
 /* ------------------------------------------------------------------ g2o/stuff/misc.h */
@@ -63,7 +66,7 @@ __device__ __forceinline__ double pen_below(double var, double a, double eps, do
 
 /* ------------------------------------------------------------------ segment quantities shared by EdgeVelocity /
  * EdgeAcceleration{,Start,Goal} (edge_velocity.h:97-111, edge_acceleration.h:103-145, :316-341, :408-433). */
-struct SegVal { double v, w; };
+struct SegVal { double v, w, vx, vy; }; /* vx, vy: velocity in the frame of the first pose (holonomic edges) */
 
 __device__ __forceinline__ SegVal seg_value(const KParams& kp, double xa, double ya, double tha, double ca, double sa,
                                             double xb, double yb, double thb, double dt) {
@@ -78,6 +81,9 @@ __device__ __forceinline__ SegVal seg_value(const KParams& kp, double xa, double
   SegVal s;
   s.v = dist / dt * (u / (1 + fabs(u)));  /* fast_sigmoid misc.h:95 */
   s.w = ad / dt;
+  const double idt = 1.0 / dt;
+  s.vx = (ca * dx + sa * dy) * idt;       /* edge_velocity.h:250-254 */
+  s.vy = (-sa * dx + ca * dy) * idt;
   return s;
 }
 
@@ -120,6 +126,35 @@ __device__ __forceinline__ SegDer seg_derivs(const KParams& kp, double xa, doubl
   s.dv[4] = a * uy + bq * sa;
   s.dv[5] = dLth * sig * idt;
   return s;
+}
+
+/* holonomic segment velocities and their derivatives: d[0..5] wrt (xa, ya, tha, xb, yb, thb); d/d dt = -value/dt
+ * (edge_velocity.h:247-256, edge_acceleration.h:502-517) */
+struct HoloDer { double vx, vy, w, idt, dvx[6], dvy[6]; };
+__device__ __forceinline__ HoloDer holo_derivs(double xa, double ya, double tha, double ca, double sa, double xb, double yb,
+                                               double thb, double dt) {
+  const double dx = xb - xa, dy = yb - ya;
+  const double rdx = ca * dx + sa * dy, rdy = -sa * dx + ca * dy;
+  HoloDer h;
+  h.idt = 1.0 / dt;
+  h.vx = rdx * h.idt; h.vy = rdy * h.idt; h.w = normalize_theta(thb - tha) * h.idt;
+  h.dvx[0] = -ca * h.idt; h.dvx[1] = -sa * h.idt; h.dvx[2] = rdy * h.idt; h.dvx[3] = ca * h.idt; h.dvx[4] = sa * h.idt; h.dvx[5] = 0;
+  h.dvy[0] = sa * h.idt; h.dvy[1] = -ca * h.idt; h.dvy[2] = -rdx * h.idt; h.dvy[3] = -sa * h.idt; h.dvy[4] = ca * h.idt; h.dvy[5] = 0;
+  return h;
+}
+/* EdgeVelocityHolonomic bounds coupled through max_vel_trans (edge_velocity.h:258-269): returns the three residuals,
+ * their slopes and the bound-coupling factors k0 = d bound_x / d vy, k1 = d bound_y / d vx (0 when inactive). */
+__device__ __forceinline__ void holo_velocity_terms(const KParams& kp, double vx, double vy, double w, double (&e)[3],
+                                                    double (&sl)[3], double& k0, double& k1) {
+  const double vt2 = kp.p.max_vel_trans * kp.p.max_vel_trans;
+  const double rem_y = sqrt(fmax(0.0, vt2 - vx * vx)), rem_x = sqrt(fmax(0.0, vt2 - vy * vy));
+  const double mvy = fmin(rem_y, kp.p.max_vel_y), mvx = fmin(rem_x, kp.p.max_vel_x), mvxb = fmin(rem_x, kp.p.max_vel_x_backwards);
+  e[0] = pen_interval2(vx, -mvxb, mvx, 0.0, sl[0]);
+  e[1] = pen_interval(vy, mvy, 0.0, sl[1]);
+  e[2] = pen_interval(w, kp.p.max_vel_theta, kp.p.penalty_epsilon, sl[2]);
+  const double lim0 = sl[0] < 0 ? kp.p.max_vel_x_backwards : kp.p.max_vel_x;
+  k0 = (sl[0] != 0 && !(lim0 < rem_x) && rem_x > 0) ? (-vy / rem_x) : 0.0;
+  k1 = (sl[1] != 0 && !(kp.p.max_vel_y < rem_y) && rem_y > 0) ? (-vx / rem_y) : 0.0;
 }
 
 /* ------------------------------------------------------------------ footprint / obstacle distance

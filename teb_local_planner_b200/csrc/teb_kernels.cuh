@@ -27,7 +27,10 @@ namespace tebgpu {
 constexpr int TP = 32;                 /* poses per kernel-A tile */
 constexpr int KA_P1OFF = ((TP + 2 + 31) / 32) * 32; /* first thread of the acceleration-row group */
 constexpr int KA_THREADS = 4 * TP;     /* one thread per band row of the tile */
-constexpr int JSTRIDE = 65;            /* doubles per anchor Jacobian block (6x7 + 2x11 = 64, +1 pad) */
+constexpr int JSTRIDE = 83;            /* doubles per anchor Jacobian block: 7 rows x 7 columns + 3 rows x 11 (+1 pad) */
+constexpr int J_ACC = 49;              /* offset of the acceleration rows (x, theta, y) inside a block */
+constexpr int ESTR = 10;               /* residual slots per anchor: vx|v, omega, kin0, kin1, sp, rot, vy, acc x, acc theta, acc y */
+constexpr int START_E = 21;            /* start-edge block: 3 rows x 7 columns, then its 3 residuals */
 constexpr int HROW = 12;               /* doubles per band row: 11 band entries + rhs */
 constexpr int KB_THREADS = 128;
 constexpr int MAX_MW = 4;              /* association bitmask words per pose (<= 256 obstacles) */
@@ -355,14 +358,15 @@ __device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& d
 /* Jacobian rows of the chain edges anchored at a = p0-2+at (sqrt(weight)-scaled, columns 4a .. 4a+10).
  * part 0: EdgeVelocity, EdgeKinematics*, EdgeShortestPath, EdgePreferRotDir rows; part 1: EdgeAcceleration / Start / Goal
  * rows. Returns this part's chi2 contribution if the anchor belongs to the tile (a >= p0), else 0. */
+template <bool HOLO>
 __device__ __forceinline__ double anchor_rows(const KParams& kp, const DevBatch& db, int b, int part, int at, int p0, int n,
                                               const double* sP, const double* sSC, const double* sSeg, double* sJ,
                                               double* sE, double* sStart) {
   double chi3 = 0;
     const int a = p0 - 2 + at;
     if (a >= 0 && a <= n - 2) {
-      double* J = sJ + (size_t)at * JSTRIDE; /* rows 0..5: 7 columns, rows 6,7: 11 columns at offset 42 */
-      double* eh = sE + 8 * at;
+      double* J = sJ + (size_t)at * JSTRIDE; /* rows 0..6: 7 columns (v|vx, omega, kin0, kin1, sp, rot, vy); rows at J_ACC: 11 columns (acc x, theta, y) */
+      double* eh = sE + ESTR * at;
       const double* pa = sP + 4 * at;
       const double* pb = pa + 4;
       const double ca = sSC[2 * at], sa = sSC[2 * at + 1], cb = sSC[2 * at + 2], sb = sSC[2 * at + 3];
@@ -371,7 +375,24 @@ __device__ __forceinline__ double anchor_rows(const KParams& kp, const DevBatch&
       const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
       const bool fa = (a == 0), fb = (a + 1 == n - 1);
       double csum = 0;
-      if (part == 0 && kp.has_vel) { /* EdgeVelocity edge_velocity.h:113-114 */
+      if (HOLO && part == 0 && kp.has_vel && kp.holo_vel) { /* EdgeVelocityHolonomic edge_velocity.h:236-273 */
+        const HoloDer h = holo_derivs(pa[0], pa[1], pa[2], ca, sa, pb[0], pb[1], pb[2], pa[3]);
+        double e[3], sl[3], c0, c1;
+        holo_velocity_terms(kp, h.vx, h.vy, h.w, e, sl, c0, c1);
+        const double kx = kp.sw_vel_x, ky = kp.sw_vel_y, kw = kp.sw_vel_th * sl[2];
+        double* Rx = J;       /* row 0: vx */
+        double* Ry = J + 42;  /* row 6: vy */
+        /* columns: x_a, y_a, th_a, dt_a, x_b, y_b, th_b */
+        Rx[0] = kx * (sl[0] * h.dvx[0] - c0 * h.dvy[0]); Rx[1] = kx * (sl[0] * h.dvx[1] - c0 * h.dvy[1]);
+        Rx[2] = kx * (sl[0] * h.dvx[2] - c0 * h.dvy[2]); Rx[3] = kx * (-sl[0] * h.vx + c0 * h.vy) * h.idt;
+        Rx[4] = kx * (sl[0] * h.dvx[3] - c0 * h.dvy[3]); Rx[5] = kx * (sl[0] * h.dvx[4] - c0 * h.dvy[4]); Rx[6] = 0;
+        Ry[0] = ky * (sl[1] * h.dvy[0] - c1 * h.dvx[0]); Ry[1] = ky * (sl[1] * h.dvy[1] - c1 * h.dvx[1]);
+        Ry[2] = ky * (sl[1] * h.dvy[2] - c1 * h.dvx[2]); Ry[3] = ky * (-sl[1] * h.vy + c1 * h.vx) * h.idt;
+        Ry[4] = ky * (sl[1] * h.dvy[3] - c1 * h.dvx[3]); Ry[5] = ky * (sl[1] * h.dvy[4] - c1 * h.dvx[4]); Ry[6] = 0;
+        J[7 + 0] = J[7 + 1] = J[7 + 4] = J[7 + 5] = 0;
+        J[7 + 2] = -kw * h.idt; J[7 + 3] = -kw * h.w * h.idt; J[7 + 6] = kw * h.idt;
+        eh[0] = kx * e[0]; eh[6] = ky * e[1]; eh[1] = kp.sw_vel_th * e[2];
+      } else if (part == 0 && kp.has_vel) { /* EdgeVelocity edge_velocity.h:113-114 */
         double s0, s1;
         const double e0 = pen_interval2(v1, -kp.p.max_vel_x_backwards, kp.p.max_vel_x, kp.p.penalty_epsilon, s0);
         const double e1 = pen_interval(w1, kp.p.max_vel_theta, kp.p.penalty_epsilon, s1);
@@ -443,9 +464,82 @@ __device__ __forceinline__ double anchor_rows(const KParams& kp, const DevBatch&
           eh[5] = kp.sw_rot * e0;
         }
       }
-      if (part == 1 && kp.has_acc) {
-        double* R0 = J + 42;
-        double* R1 = J + 53;
+      if (HOLO && part == 1 && kp.has_acc && kp.holo_acc) {
+        /* EdgeAccelerationHolonomic / Start / Goal edge_acceleration.h:487-540, :580-620, :672-712 */
+        const HoloDer h1 = holo_derivs(pa[0], pa[1], pa[2], ca, sa, pb[0], pb[1], pb[2], pa[3]);
+        const double sw[3] = {kp.sw_acc_x, kp.sw_acc_th, kp.sw_acc_y};
+        const double lim[3] = {kp.p.acc_lim_x, kp.p.acc_lim_theta, kp.p.acc_lim_y};
+        /* value / derivative tables in row order x, theta, y */
+        const double v1r[3] = {h1.vx, h1.w, h1.vy};
+        double d1[3][6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { d1[0][k] = h1.dvx[k]; d1[2][k] = h1.dvy[k]; d1[1][k] = 0; }
+        d1[1][2] = -h1.idt; d1[1][5] = h1.idt;
+        if (a <= n - 3) {
+          const double* pc = pb + 4;
+          const HoloDer h2 = holo_derivs(pb[0], pb[1], pb[2], cb, sb, pc[0], pc[1], pc[2], pb[3]);
+          const double v2r[3] = {h2.vx, h2.w, h2.vy};
+          double d2[3][6];
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { d2[0][k] = h2.dvx[k]; d2[2][k] = h2.dvy[k]; d2[1][k] = 0; }
+          d2[1][2] = -h2.idt; d2[1][5] = h2.idt;
+          const double iT = 1.0 / (pa[3] + pb[3]);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const double acc = (v2r[r] - v1r[r]) * 2 * iT;
+            double sl;
+            const double e = pen_interval(acc, lim[r], kp.p.penalty_epsilon, sl);
+            const double kk = sw[r] * sl * iT;
+            double* R = J + J_ACC + 11 * r;
+            R[0] = -2 * kk * d1[r][0]; R[1] = -2 * kk * d1[r][1]; R[2] = -2 * kk * d1[r][2];
+            R[3] = kk * (2 * v1r[r] * h1.idt - acc);
+            R[4] = 2 * kk * (d2[r][0] - d1[r][3]); R[5] = 2 * kk * (d2[r][1] - d1[r][4]); R[6] = 2 * kk * (d2[r][2] - d1[r][5]);
+            R[7] = kk * (-2 * v2r[r] * h2.idt - acc);
+            R[8] = 2 * kk * d2[r][3]; R[9] = 2 * kk * d2[r][4]; R[10] = 2 * kk * d2[r][5];
+            if (a + 2 == n - 1) { R[8] = R[9] = R[10] = 0; }
+            eh[7 + r] = sw[r] * e;
+          }
+        } else { /* a == n-2: goal edge */
+          const double* vg = db.vel_goal + 4 * (size_t)b;
+          if (vg[3] != 0) {
+            const double tw[3] = {vg[0], vg[2], vg[1]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const double acc = (tw[r] - v1r[r]) * h1.idt;
+              double sl;
+              const double e = pen_interval(acc, lim[r], kp.p.penalty_epsilon, sl);
+              const double kk = sw[r] * sl * h1.idt;
+              double* R = J + J_ACC + 11 * r;
+              R[0] = -kk * d1[r][0]; R[1] = -kk * d1[r][1]; R[2] = -kk * d1[r][2];
+              R[3] = kk * (v1r[r] * h1.idt - acc);
+              R[4] = -kk * d1[r][3]; R[5] = -kk * d1[r][4]; R[6] = -kk * d1[r][5];
+              eh[7 + r] = sw[r] * e;
+            }
+          }
+        }
+        if (a == 0) { /* start edge */
+          const double* vs = db.vel_start + 4 * (size_t)b;
+          if (vs[3] != 0) {
+            const double tw[3] = {vs[0], vs[2], vs[1]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const double acc = (v1r[r] - tw[r]) * h1.idt;
+              double sl;
+              const double e = pen_interval(acc, lim[r], kp.p.penalty_epsilon, sl);
+              const double kk = sw[r] * sl * h1.idt;
+              double* S = sStart + 7 * r;
+              S[0] = S[1] = S[2] = 0; /* pose 0 is fixed */
+              S[3] = kk * (-v1r[r] * h1.idt - acc);
+              S[4] = kk * d1[r][3]; S[5] = kk * d1[r][4]; S[6] = kk * d1[r][5];
+              if (fb) { S[4] = S[5] = S[6] = 0; }
+              sStart[START_E + r] = sw[r] * e;
+              if (a >= p0) csum += sStart[START_E + r] * sStart[START_E + r];
+            }
+          }
+        }
+      } else if (part == 1 && kp.has_acc) {
+        double* R0 = J + J_ACC;
+        double* R1 = J + J_ACC + 11;
         if (a <= n - 3) { /* EdgeAcceleration edge_acceleration.h:134-145 */
           const double* q2 = q1 + 9;
           const double v2 = q2[0], w2 = q2[1], idt2 = q2[2];
@@ -467,7 +561,7 @@ __device__ __forceinline__ double anchor_rows(const KParams& kp, const DevBatch&
           R1[6] = 2 * k1 * (-idt2 - idt1);
           R1[7] = k1 * (-2 * w2 * idt2 - accr);
           R1[10] = 2 * k1 * idt2;
-          eh[6] = kp.sw_acc_x * e0; eh[7] = kp.sw_acc_th * e1;
+          eh[7] = kp.sw_acc_x * e0; eh[8] = kp.sw_acc_th * e1;
           if (a + 2 == n - 1) { R0[8] = R0[9] = R0[10] = 0; R1[10] = 0; }
         } else { /* a == n-2: EdgeAccelerationGoal edge_acceleration.h:420-433 */
           const double* vg = db.vel_goal + 4 * (size_t)b;
@@ -482,7 +576,7 @@ __device__ __forceinline__ double anchor_rows(const KParams& kp, const DevBatch&
             R0[3] = k0 * (v1 * idt1 - acc);
             R0[4] = -k0 * q1[6]; R0[5] = -k0 * q1[7]; R0[6] = -k0 * q1[8];
             R1[2] = k1 * idt1; R1[3] = k1 * (w1 * idt1 - accr); R1[6] = -k1 * idt1;
-            eh[6] = kp.sw_acc_x * e0; eh[7] = kp.sw_acc_th * e1;
+            eh[7] = kp.sw_acc_x * e0; eh[8] = kp.sw_acc_th * e1;
           }
         }
         if (a == 0) { /* EdgeAccelerationStart edge_acceleration.h:328-341 */
@@ -503,8 +597,8 @@ __device__ __forceinline__ double anchor_rows(const KParams& kp, const DevBatch&
             S1[3] = k1 * (-w1 * idt1 - accr);
             S1[6] = k1 * idt1;
             if (fb) { S0[4] = S0[5] = S0[6] = 0; S1[6] = 0; }
-            sStart[14] = kp.sw_acc_x * e0; sStart[15] = kp.sw_acc_th * e1;
-            if (a >= p0) csum += sStart[14] * sStart[14] + sStart[15] * sStart[15];
+            sStart[START_E] = kp.sw_acc_x * e0; sStart[START_E + 1] = kp.sw_acc_th * e1;
+            if (a >= p0) csum += sStart[START_E] * sStart[START_E] + sStart[START_E + 1] * sStart[START_E + 1];
           }
         }
       }
@@ -512,25 +606,28 @@ __device__ __forceinline__ double anchor_rows(const KParams& kp, const DevBatch&
       if (fa) {
         if (part == 0) {
 #pragma unroll
-          for (int k = 0; k < 6; ++k) { J[7 * k] = 0; J[7 * k + 1] = 0; J[7 * k + 2] = 0; }
+          for (int k = 0; k < (HOLO ? 7 : 6); ++k) { J[7 * k] = 0; J[7 * k + 1] = 0; J[7 * k + 2] = 0; }
         } else {
-          J[42] = J[43] = J[44] = 0; J[53] = J[54] = J[55] = 0;
+#pragma unroll
+          for (int k = 0; k < (HOLO ? 3 : 2); ++k) { J[J_ACC + 11 * k] = 0; J[J_ACC + 11 * k + 1] = 0; J[J_ACC + 11 * k + 2] = 0; }
         }
       }
       if (fb) {
         if (part == 0) {
 #pragma unroll
-          for (int k = 0; k < 6; ++k) { J[7 * k + 4] = 0; J[7 * k + 5] = 0; J[7 * k + 6] = 0; }
+          for (int k = 0; k < (HOLO ? 7 : 6); ++k) { J[7 * k + 4] = 0; J[7 * k + 5] = 0; J[7 * k + 6] = 0; }
         } else {
-          J[46] = J[47] = J[48] = 0; J[57] = J[58] = J[59] = 0;
+#pragma unroll
+          for (int k = 0; k < (HOLO ? 3 : 2); ++k) { J[J_ACC + 11 * k + 4] = 0; J[J_ACC + 11 * k + 5] = 0; J[J_ACC + 11 * k + 6] = 0; }
         }
       }
       if (a >= p0) {
         if (part == 0) {
 #pragma unroll
-          for (int k = 0; k < 6; ++k) csum += eh[k] * eh[k];
+          for (int k = 0; k < (HOLO ? 7 : 6); ++k) csum += eh[k] * eh[k];
         } else {
-          csum += eh[6] * eh[6] + eh[7] * eh[7];
+          csum += eh[7] * eh[7] + eh[8] * eh[8];
+          if (HOLO) csum += eh[9] * eh[9];
         }
         chi3 += csum;
       }
@@ -540,6 +637,7 @@ __device__ __forceinline__ double anchor_rows(const KParams& kp, const DevBatch&
 
 /* One band row r = 4(p0 + t/4) + t%4: gathers J^T J over the (<= 3) anchors that touch it, adds the unary block and
  * the time-optimal term. acc[k] = H[r][r-k], brow = b[r]. */
+template <bool HOLO>
 __device__ __forceinline__ void gather_row(const KParams& kp, int t, int p0, int n, const double* sP, const double* sJ,
                                            const double* sE, const double* sStart, const double* sU, double (&acc)[11],
                                            double& brow) {
@@ -562,10 +660,10 @@ __device__ __forceinline__ void gather_row(const KParams& kp, int t, int p0, int
           if (a < 0 || a > n - 2 || l > 10) continue;
           const int slot = a - (p0 - 2);
           const double* J = sJ + (size_t)slot * JSTRIDE;
-          const double* eh = sE + 8 * slot;
+          const double* eh = sE + ESTR * slot;
           if (l <= 6) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
+            for (int k = 0; k < (HOLO ? 7 : 6); ++k) {
               const double jl = J[7 * k + l];
               if (jl != 0) {
                 brow -= jl * eh[k];
@@ -576,10 +674,10 @@ __device__ __forceinline__ void gather_row(const KParams& kp, int t, int p0, int
             }
             if (a == 0) {
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
+              for (int k = 0; k < (HOLO ? 3 : 2); ++k) {
                 const double jl = sStart[7 * k + l];
                 if (jl != 0) {
-                  brow -= jl * sStart[14 + k];
+                  brow -= jl * sStart[START_E + k];
 #pragma unroll
                   for (int o = 0; o <= 6; ++o)
                     if (o <= l) acc[o] += jl * sStart[7 * k + l - o];
@@ -588,11 +686,11 @@ __device__ __forceinline__ void gather_row(const KParams& kp, int t, int p0, int
             }
           }
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const double* R = J + 42 + 11 * k;
+          for (int k = 0; k < (HOLO ? 3 : 2); ++k) {
+            const double* R = J + J_ACC + 11 * k;
             const double jl = R[l];
             if (jl != 0) {
-              brow -= jl * eh[6 + k];
+              brow -= jl * eh[7 + k];
 #pragma unroll
               for (int o = 0; o <= 10; ++o)
                 if (o <= l) acc[o] += jl * R[l - o];
@@ -620,8 +718,8 @@ struct KASmem {
   static constexpr int SC = (TP + 4) * 2;
   static constexpr int SEG = (TP + 3) * 9;
   static constexpr int JB = (TP + 2) * JSTRIDE;
-  static constexpr int EH = (TP + 2) * 8;
-  static constexpr int START = 2 * 7 + 2;
+  static constexpr int EH = (TP + 2) * ESTR;
+  static constexpr int START = 3 * 7 + 3;
   static constexpr int UN = TP * 9;
   static constexpr int RED = 4 * (KA_THREADS / 32) + 8 + (KA_THREADS / 32);
   static constexpr int STAGE = KA_THREADS * HROW; /* aliases JB..: needs JB+EH+START+UN >= STAGE? no: separate */
@@ -633,6 +731,7 @@ __host__ __device__ inline size_t ka_smem_bytes(int M_cap) {
   return (d + jb) * sizeof(double) + (size_t)M_cap * sizeof(TebObstacle) + 64;
 }
 
+template <bool HOLO>
 __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = blockIdx.y;
@@ -733,7 +832,7 @@ __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParam
   const int part = (tid < TP + 2) ? 0 : ((tid >= KA_P1OFF && tid < KA_P1OFF + TP + 2) ? 1 : -1);
   if (part >= 0) {
     const int at = part == 0 ? tid : tid - KA_P1OFF; /* anchor slot */
-    chi[3] += anchor_rows(kp, db, b, part, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
+    chi[3] += anchor_rows<HOLO>(kp, db, b, part, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
   }
 
   __syncthreads();
@@ -741,7 +840,7 @@ __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParam
   /* stage 4: one thread per band row r = 4i + c gathers J^T J over the (<= 3) anchors that touch it */
   double acc[11];
   double brow;
-  gather_row(kp, tid, p0, n, sP, sJ, sE, sStart, sU, acc, brow);
+  gather_row<HOLO>(kp, tid, p0, n, sP, sJ, sE, sStart, sU, acc, brow);
   __syncthreads(); /* every thread is done reading sJ: reuse it as the output stage */
   {
     double* o = sJ + (size_t)tid * HROW;
@@ -809,6 +908,7 @@ __host__ __device__ inline size_t kw_smem_bytes(int M_cap) {
   return (size_t)KW_WARPS * KWSmem::REG * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 64;
 }
 
+template <bool HOLO>
 __global__ void __launch_bounds__(32 * KW_WARPS) k_linearize_w(const __grid_constant__ DevBatch db,
                                                                const __grid_constant__ KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -900,14 +1000,14 @@ __global__ void __launch_bounds__(32 * KW_WARPS) k_linearize_w(const __grid_cons
   __syncwarp();
   /* phase II: chain-edge Jacobian rows of every anchor of the tile (+2 halo anchors) */
   for (int at = lane; at < TP + 2; at += 32) {
-    chi[3] += anchor_rows(kp, db, b, 0, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
-    chi[3] += anchor_rows(kp, db, b, 1, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
+    chi[3] += anchor_rows<HOLO>(kp, db, b, 0, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
+    chi[3] += anchor_rows<HOLO>(kp, db, b, 1, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
   }
   __syncwarp();
   /* phase III: four band rows per lane */
   double accs[4][11], brows[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) gather_row(kp, q * 32 + lane, p0, n, sP, sJ, sE, sStart, sU, accs[q], brows[q]);
+  for (int q = 0; q < 4; ++q) gather_row<HOLO>(kp, q * 32 + lane, p0, n, sP, sJ, sE, sStart, sU, accs[q], brows[q]);
   __syncwarp(); /* every lane is done reading sJ: reuse it as the output stage */
   double dm = 0;
 #pragma unroll
@@ -971,7 +1071,12 @@ __device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db,
       const SegVal s1 = had_seg ? cy.s : seg_value(kp, pa[0], pa[1], pa[2], ca, sa, pb[0], pb[1], pb[2], pa[3]);
       const double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
       double sl, csum = 0;
-      if (kp.has_vel) {
+      if (kp.has_vel && kp.holo_vel) {
+        double e[3], s3[3], c0, c1;
+        holo_velocity_terms(kp, s1.vx, s1.vy, s1.w, e, s3, c0, c1);
+        const double e0 = kp.sw_vel_x * e[0], e1 = kp.sw_vel_y * e[1], e2 = kp.sw_vel_th * e[2];
+        csum += e0 * e0 + e1 * e1 + e2 * e2;
+      } else if (kp.has_vel) {
         const double e0 = kp.sw_vel_x * pen_interval2(s1.v, -kp.p.max_vel_x_backwards, kp.p.max_vel_x, kp.p.penalty_epsilon, sl);
         const double e1 = kp.sw_vel_th * pen_interval(s1.w, kp.p.max_vel_theta, kp.p.penalty_epsilon, sl);
         csum += e0 * e0 + e1 * e1;
@@ -1004,7 +1109,37 @@ __device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db,
           csum += e * e;
         }
       }
-      if (kp.has_acc) {
+      if (kp.has_acc && kp.holo_acc) {
+        const double idt1 = 1.0 / pa[3];
+        const double lim[3] = {kp.p.acc_lim_x, kp.p.acc_lim_y, kp.p.acc_lim_theta};
+        const double sw[3] = {kp.sw_acc_x, kp.sw_acc_y, kp.sw_acc_th};
+        const double u1[3] = {s1.vx, s1.vy, s1.w};
+        if (i <= n - 3) {
+          const double* pc = pb + 4;
+          const SegVal s2 = seg_value(kp, pb[0], pb[1], pb[2], cb, sb, pc[0], pc[1], pc[2], pb[3]);
+          cy.s = s2; cy.has_seg = true;
+          const double iT = 1.0 / (pa[3] + pb[3]);
+          const double u2[3] = {s2.vx, s2.vy, s2.w};
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const double e = sw[r] * pen_interval((u2[r] - u1[r]) * 2 * iT, lim[r], kp.p.penalty_epsilon, sl);
+            csum += e * e;
+          }
+        } else if (vg[3] != 0) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const double e = sw[r] * pen_interval((vg[r] - u1[r]) * idt1, lim[r], kp.p.penalty_epsilon, sl);
+            csum += e * e;
+          }
+        }
+        if (i == 0 && vs[3] != 0) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const double e = sw[r] * pen_interval((u1[r] - vs[r]) * idt1, lim[r], kp.p.penalty_epsilon, sl);
+            csum += e * e;
+          }
+        }
+      } else if (kp.has_acc) {
         const double idt1 = 1.0 / pa[3];
         if (i <= n - 3) {
           const double* pc = pb + 4;

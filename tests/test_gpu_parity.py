@@ -251,6 +251,52 @@ def test_legacy_association_and_velocity_obstacle_ratio(oracle, legacy, vor):
     assert np.allclose(hg.cost, ha.cost, rtol=1e-6) and np.array_equal(hg.lm_iters, ha.lm_iters)
 
 
+@pytest.mark.parametrize("acc_lim_y,max_vel_trans", [(0.5, 0.45), (0.0, 0.0), (0.4, 0.0)])
+def test_holonomic_edges(oracle, acc_lim_y, max_vel_trans):
+    """EdgeVelocityHolonomic (edge_velocity.h:236-273, bounds coupled through max_vel_trans) and
+    EdgeAccelerationHolonomic / Start / Goal (edge_acceleration.h:487-712); with acc_lim_y == 0 the reference keeps the
+    non-holonomic acceleration edges next to the holonomic velocity edge (optimal_planner.cpp:778)"""
+    p, hb0 = scenes.make_config_batch("C3", candidates=6, seed=8)
+    p.max_vel_y, p.acc_lim_y, p.max_vel_trans = 0.3, acc_lim_y, max_vel_trans
+    p.weight_kinematics_nh = 1.0
+    p.weight_max_vel_y, p.weight_acc_lim_y = 2.0, 1.5
+    rng = np.random.default_rng(3)
+    for b in range(hb0.B):                                   # sideways motion and limits in play, away from the kinks
+        n = hb0.n[b]
+        hb0.poses[b, 1:n - 1, 2] += rng.normal(0, 0.35, n - 2)
+        hb0.poses[b, :n - 1, 3] *= 0.8
+    hb0.vel_start[:, 0], hb0.vel_start[:, 1], hb0.vel_start[:, 2] = 0.25, 0.1, -0.1
+    hb0.vel_goal[1, 3] = 0.0
+    hb0.vel_goal[2, 1] = 0.15
+    g = _gpu(hb0, p)
+    for variant in (0, 1):
+        g.set_linearize_variant(variant)
+        Hb, chi2 = g.build_system(hb0, 1)
+        for b in range(hb0.B):
+            n = hb0.n[b]
+            Hd, bd, c2 = oracle.build_system(p, hb0.poses[b], n, hb0.obstacles[0][:hb0.obst_count[0]],
+                                             vel_start=hb0.vel_start[b], vel_goal=hb0.vel_goal[b], weight_multiplier=2.0,
+                                             jac_mode=oracle.JAC_ANALYTIC)
+            ref = _padded_from_dense(Hd, bd, n)
+            got = Hb[b, :4 * n]
+            assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max()
+            assert abs(chi2[b] - c2) <= 1e-12 * max(c2, 1.0)
+    g.set_linearize_variant(0)
+    args = abi.make_args(5, 4, True, 100.0, 1.0, False)
+    hg = hb0.copy()
+    g.optimize(hg, args)
+    g.close()
+    ha = hb0.copy()
+    oracle.optimize_batch(p, ha, args, jac_mode=oracle.JAC_ANALYTIC, threads=8)
+    assert np.array_equal(hg.n, ha.n)
+    assert _pose_diff(hg, ha).max() < 1e-6
+    assert np.allclose(hg.cost, ha.cost, rtol=1e-6) and np.array_equal(hg.lm_iters, ha.lm_iters)
+    hn = hb0.copy()
+    oracle.optimize_batch(p, hn, args, jac_mode=oracle.JAC_G2O, threads=8)
+    dn = _pose_diff(hg, hn)
+    assert np.median(dn) <= 1e-4, dn
+
+
 def test_solvers_and_speculation_widths_agree():
     """the three linear solvers give the same bands up to round-off; the speculation width K does not change a bit"""
     p, hb0 = scenes.make_config_batch("C4", candidates=12, seed=9)
@@ -277,9 +323,9 @@ def test_errors_are_loud():
     p, hb = scenes.make_config_batch("C1", candidates=2)
     g = T.TebGpu(2, 50, 1, 8, 0)
     q = abi.default_params()
-    q.max_vel_y = 0.1
+    q.footprint_type = 7
     with pytest.raises(T.TebGpuError, match="rc=-3"):
-        g.set_params(q)                                   # holonomic edges: unsupported, not silently ignored
+        g.set_params(q)                                   # unknown footprint model: refused, not approximated
     p2, big = scenes.make_config_batch("C2", candidates=4)
     with pytest.raises(T.TebGpuError, match="rc=-4"):
         g.optimize(big, abi.make_args())                  # exceeds the context limits

@@ -110,6 +110,51 @@ def test_two_circles_footprint_and_exponent_jacobians(oracle):
     assert np.abs(bn - ba).max() <= 2e-6 * np.abs(ba).max()
 
 
+@pytest.mark.parametrize("acc_lim_y,max_vel_trans", [(0.5, 0.45), (0.0, 0.0)])
+def test_holonomic_edges_jacobians_and_known_answers(oracle, acc_lim_y, max_vel_trans):
+    """EdgeVelocityHolonomic / EdgeAccelerationHolonomic*: closed-form Jacobians vs central differences, and the
+    residual values against a hand evaluation of edge_velocity.h:250-269 on one segment"""
+    p, hb = scenes.make_config_batch("C3", candidates=2, seed=8)
+    p.max_vel_y, p.acc_lim_y, p.max_vel_trans = 0.3, acc_lim_y, max_vel_trans
+    p.weight_kinematics_nh, p.weight_max_vel_y, p.weight_acc_lim_y = 1.0, 2.0, 1.5
+    rng = np.random.default_rng(3)
+    n = hb.n[0]
+    hb.poses[0, 1:n - 1, 2] += rng.normal(0, 0.35, n - 2)
+    hb.poses[0, :n - 1, 3] *= 0.8
+    obst = hb.obstacles[0][:hb.obst_count[0]]
+    vs = [0.25, 0.1, -0.1, 1.0]
+    Hn, bn, c2n = oracle.build_system(p, hb.poses[0], n, obst, vel_start=vs, jac_mode=0)
+    Ha, ba, c2a = oracle.build_system(p, hb.poses[0], n, obst, vel_start=vs, jac_mode=1)
+    assert c2n == c2a
+    assert np.abs(Hn - Ha).max() <= 2e-6 * np.abs(Ha).max()
+    assert np.abs(bn - ba).max() <= 2e-6 * max(np.abs(ba).max(), 1.0)
+    # chi2 of a 3-pose band with only the holonomic velocity edges switched on, by hand
+    q = abi.default_params()
+    q.max_vel_y, q.max_vel_trans, q.acc_lim_y = 0.3, max_vel_trans, acc_lim_y
+    for w in ("weight_acc_lim_x", "weight_acc_lim_theta", "weight_kinematics_nh", "weight_kinematics_forward_drive",
+              "weight_optimaltime", "weight_obstacle", "weight_shortest_path", "weight_viapoint"):
+        setattr(q, w, 0.0)
+    q.include_dynamic_obstacles = 0
+    band = np.array([[0, 0, 0.3, 1.0], [0.5, 0.4, 0.6, 1.2], [1.1, 0.5, 0.2, 0.0]])
+    _, _, c2 = oracle.build_system(q, band, 3, np.zeros(0, abi.OBST_DTYPE), jac_mode=1)
+    want = 0.0
+    for i in range(2):
+        dx, dy = band[i + 1, :2] - band[i, :2]
+        c, s_ = np.cos(band[i, 2]), np.sin(band[i, 2])
+        vx, vy = (c * dx + s_ * dy) / band[i, 3], (-s_ * dx + c * dy) / band[i, 3]
+        om = (band[i + 1, 2] - band[i, 2]) / band[i, 3]
+        mvx, mvxb, mvy = q.max_vel_x, q.max_vel_x_backwards, q.max_vel_y
+        # max_vel_trans == 0 (the header default, teb_config.h:280) collapses all three bounds to 0, as in the reference
+        mvy = min(mvy, np.sqrt(max(0.0, max_vel_trans ** 2 - vx ** 2)))
+        rem = np.sqrt(max(0.0, max_vel_trans ** 2 - vy ** 2))
+        mvx, mvxb = min(mvx, rem), min(mvxb, rem)
+        e0 = max(0.0, vx - mvx) if vx >= 0 else max(0.0, -vx - mvxb)          # penaltyBoundToInterval(vx, -b, a, 0)
+        e1 = max(0.0, abs(vy) - mvy)
+        e2 = max(0.0, abs(om) - (q.max_vel_theta - q.penalty_epsilon))
+        want += q.weight_max_vel_x * e0 ** 2 + q.weight_max_vel_y * e1 ** 2 + q.weight_max_vel_theta * e2 ** 2
+    assert want > 0 and abs(c2 - want) <= 1e-12 * want
+
+
 def test_banded_vs_dense_solver(oracle):
     p, hb = scenes.make_config_batch("C1", candidates=2, seed=1)
     obst = hb.obstacles[0][:hb.obst_count[0]]
