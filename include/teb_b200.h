@@ -237,7 +237,8 @@ int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k);
  * enable != 0 -> subsequent optimize calls record events. tebgpu_get_kernel_times synchronises, then returns for
  * kernel kind k (0 begin, 1 auto_resize, 2 build_graph, 3 linearize ["kernel A"], 4 lm_step [fused "kernel B" of
  * solvers 0/1; for solver 2: the solve/eval launches of the retry rounds >= 1], 5 finalize, 6 solve_tpb round 0,
- * 7 trial_eval round 0, 8 decide ["kernel B" of the default speculative solver])
+ * 7 trial_eval round 0 (includes the accept / reject replay), 8 unused since the replay was fused into trial_eval
+ * ["kernel B" of the default speculative solver])
  * the accumulated milliseconds and launch count since profiling was enabled, and resets the accumulators. */
 int32_t tebgpu_set_profiling(tebgpu_ctx* ctx, int32_t enable);
 int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[9], int64_t count_out[9]);

@@ -134,7 +134,7 @@ class TebGpu:
         ms, cnt = (C.c_double * 9)(), (C.c_int64 * 9)()
         self._check(self.lib.tebgpu_get_kernel_times(self.ctx, C.byref(ms), C.byref(cnt)), "tebgpu_get_kernel_times")
         names = ("k_begin", "k_auto_resize", "k_build_graph", "k_linearize", "k_lm_step_or_retry_rounds", "k_finalize",
-                 "k_solve_tpb", "k_trial_eval", "k_decide")
+                 "k_solve_tpb", "k_trial_eval", "unused")
         return {nme: (ms[i], cnt[i]) for i, nme in enumerate(names)}
 
     def launch_count(self):

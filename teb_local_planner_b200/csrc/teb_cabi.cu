@@ -13,6 +13,7 @@
 
 #include "teb_kernels.cuh"
 #include "teb_spec.cuh"
+#include <cstdlib>
 
 using namespace tebgpu;
 
@@ -42,6 +43,7 @@ struct tebgpu_ctx {
   int32_t* dyn_idx = nullptr;
   int32_t* dyn_cnt = nullptr;
   SpecBufs spec{};
+  int eval_minb = 2; /* k_trial_eval register budget: 2 -> 128 regs, 3 -> 80 regs (TEBGPU_EVAL_MINB, experiments) */
   BandState* state = nullptr;
   /* device mirrors for the host-buffer entry point */
   double* d_poses = nullptr; int32_t* d_n = nullptr; int32_t* d_scene = nullptr; TebObstacle* d_obst = nullptr;
@@ -143,7 +145,7 @@ const char* tebgpu_last_error_string(const tebgpu_ctx* ctx) { return ctx ? ctx->
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static void free_all(tebgpu_ctx* c) {
-  void* ptrs[] = {c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.T, c->spec.res, c->spec.need, c->spec.qmax, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+  void* ptrs[] = {c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
                   c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
                   c->d_status, c->d_iters};
   for (void* p : ptrs)
@@ -187,12 +189,15 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   {
     size_t ev = eval_smem_bytes((int)nc, (int)M, SPEC_K_MAX);
     if (ev > 232448) ev = 232448; /* wide speculation is only chosen when its staging fits (tebgpu_optimize_batch_device) */
-    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
+    if (const char* e = std::getenv("TEBGPU_EVAL_MINB")) c->eval_minb = std::atoi(e) == 3 ? 3 : 2;
   }
   const size_t spec_sys = ((B * SPEC_K_MAX + 31) / 32) * 32; /* whole warps of (band, trial) systems */
   CUDA_TRY(c, cudaMalloc(&c->spec.Lf, spec_sys * 4 * nc * HROW * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->spec.dx, spec_sys * 4 * nc * sizeof(double)));
-  CUDA_TRY(c, cudaMalloc(&c->spec.T, B * SPEC_K_MAX * 4 * nc * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.cnt, SPEC_CNT_CAP * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.list, 2 * B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.res, B * SPEC_K_MAX * RES_STRIDE * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->spec.need, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.qmax, B * sizeof(int32_t)));
@@ -356,6 +361,12 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   if (spec_K == 0) spec_K = ((long long)B * 6 <= 148LL * 4 * 32) ? 6 : 4;
   while (spec_K > 4 && eval_smem_bytes(bt->n_cap, bt->M_cap, spec_K) > 232448) spec_K -= 2;
   if (eval_smem_bytes(bt->n_cap, bt->M_cap, spec_K) > 232448) { ctx->err = "trial-evaluation staging exceeds shared memory"; return TEBGPU_ERR_CAPACITY; }
+  int g = 0; /* running index of the speculative rounds of this call: selects the retry-list counter / buffer */
+  if (ctx->solver == 2) {
+    const long long need_cnt = (long long)args->iterations_outerloop * args->iterations_innerloop * ((10 + spec_K - 1) / spec_K) + 2;
+    if (need_cnt > SPEC_CNT_CAP) { ctx->err = "outer x inner iterations exceed the retry-list counters"; return TEBGPU_ERR_CAPACITY; }
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->spec.cnt, 0, (size_t)need_cnt * sizeof(int32_t), st));
+  }
   double weight_multiplier = 1.0;
   KParams kp = make_kparams(p, weight_multiplier);
   prof_begin(ctx, st, 0); k_begin<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st);
@@ -371,10 +382,12 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
         ctx->spec.K = K;
         const int bk = B * K;
         const int rounds = (10 + K - 1) / K; /* g2o's maxTrialsAfterFailure = 10 */
-        for (int round = 0; round < rounds; ++round) {
-          prof_begin(ctx, st, round == 0 ? 6 : 4); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
-          prof_begin(ctx, st, round == 0 ? 7 : 4); k_trial_eval<<<B, 32 * K, eval_smem_bytes(bt->n_cap, bt->M_cap, K), st>>>(db, kp, ctx->spec, round); ++launches; prof_end(ctx, st);
-          prof_begin(ctx, st, 8); k_decide<<<(B + 3) / 4, 128, 0, st>>>(db, ctx->spec, it, round); ++launches; prof_end(ctx, st);
+        for (int round = 0; round < rounds; ++round, ++g) {
+          prof_begin(ctx, st, round == 0 ? 6 : 4); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, st>>>(db, ctx->spec, it, round, g); ++launches; prof_end(ctx, st);
+          prof_begin(ctx, st, round == 0 ? 7 : 4);
+          if (ctx->eval_minb == 3) k_trial_eval<3><<<B, 32 * K, eval_smem_bytes(bt->n_cap, bt->M_cap, K), st>>>(db, kp, ctx->spec, it, round, g);
+          else k_trial_eval<2><<<B, 32 * K, eval_smem_bytes(bt->n_cap, bt->M_cap, K), st>>>(db, kp, ctx->spec, it, round, g);
+          ++launches; prof_end(ctx, st);
         }
       } else {
         prof_begin(ctx, st, 4);

@@ -12,8 +12,10 @@
  *                 registers (fully unrolled by 11 so every index is static), rows of H streamed from HBM/L2, factor
  *                 rows streamed out, forward substitution fused, back substitution from the streamed factor.
  *                 Replaces LinearSolverCSparse::solve (optimal_planner.cpp:169-172).
- *   k_trial_eval  one WARP per (band, trial): trial state x [+] dx, trial chi2 by family, computeScale().
- *   k_decide      one WARP per band: replays the accept / reject chain, commits the accepted trial state.
+ *   k_trial_eval  one CTA per band, one WARP per trial: trial state x [+] dx, trial chi2 by family, computeScale();
+ *                 then one thread replays the accept / reject chain in order and the CTA commits the accepted trial
+ *                 state from shared memory. Bands whose K trials were all rejected are appended to a compact list;
+ *                 the (rare) retry rounds run over that list only.
  */
 #pragma once
 
@@ -22,15 +24,17 @@
 namespace tebgpu {
 
 constexpr int SPEC_K_MAX = 8;    /* trials solved concurrently per round: 4, 6 or 8 (runtime, SpecBufs::K) */
+constexpr int SPEC_CNT_CAP = 1 << 16; /* retry-list counters per call: outer x inner x rounds */
 constexpr int RES_STRIDE = 8;    /* per (band, trial): chi parts [4], scale, ok, lambda, unused */
 
 struct SpecBufs {
   double* Lf;    /* [B][K][4 n_cap][12] factor rows: 1/d, z, L[j+1..j+10][j] */
   double* dx;    /* [B][K][4 n_cap]     solution of trial k                   */
-  double* T;     /* [B][K][n_cap][4]    trial state                           */
   double* res;   /* [B][K][RES_STRIDE]                                         */
   int32_t* need; /* [B] band still needs trials in this LM iteration          */
   int32_t* qmax; /* [B] trials consumed in this LM iteration                  */
+  int32_t* cnt;  /* [rounds of the call + 1] length of the retry list a round reads (zeroed per call) */
+  int32_t* list; /* [2][B] bands of the retry list, double buffered by round parity                    */
   int32_t K;     /* speculation width of this call                            */
 };
 
@@ -60,21 +64,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
-__global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int iteration, int round) {
+__global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int iteration, int round, int g) {
   extern __shared__ __align__(16) unsigned char ring_raw[];
   const int lane = threadIdx.x;
   const int t = blockIdx.x * 32 + lane;
   const int SPEC_K = sp.K;
-  int b = t / SPEC_K;
-  const int k = t - b * SPEC_K;
-  bool work = b < db.B;
-  if (!work) b = db.B - 1;
+  /* system t = K * slot + k; round 0: slot = band, retry rounds: slot indexes the compact list of round g */
+  const int slot = t / SPEC_K;
+  const int k = t - slot * SPEC_K;
+  const int nslots = (round == 0) ? db.B : sp.cnt[g];
+  if (slot >= nslots) return; /* threads are independent: no warp-level primitive below */
+  const int b = (round == 0) ? slot : sp.list[(size_t)(g & 1) * db.B + slot];
+  bool work = true;
   const BandState* st = &db.state[b];
   if (!st->active) work = false;
-  if (round > 0 && !sp.need[b]) work = false;
   const int q0 = (round == 0) ? 0 : sp.qmax[b];
   if (q0 + k >= 10) work = false;
-  if (!work) return; /* threads are independent: no warp-level primitive below */
+  if (!work) return;
   const int n = db.n[b];
   const int N = 4 * n;
   double lambda, ni;
@@ -214,21 +220,115 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
   cp_async_wait<0>();
 }
 
-/* ------------------------------------------------------------------ k_trial_eval: CTA per band, warp k = trial k.
- * The four trial solutions of a band sit in adjacent lanes of the solver's interleaved scratch (one 32-byte sector per
- * row), so the CTA stages them - and the scene's obstacle table and the four trial states - in shared memory once. */
-__host__ __device__ inline size_t eval_smem_bytes(int n_cap, int M_cap, int K) {
-  return ((size_t)K * 2 + 2) * 4 * n_cap * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 16;
+/* Accept / reject replay (OptimizationAlgorithmLevenberg::solve), sequential over the K trials of one
+ * band; run by one thread. Returns the accepted trial (or -1). */
+struct DecideArgs { /* passed by value: a reference to the kernel parameters would force them into local memory */
+  BandState* st;
+  const double* chi_parts; /* this band's tile partials */
+  double lambda_init;
+  int32_t* need;           /* &need[b] */
+  int32_t* qmax;           /* &qmax[b] */
+  int32_t* cnt_next;       /* &cnt[g + 1] */
+  int32_t* list_next;      /* list buffer of round g + 1 */
+  int32_t b, n, K, iteration, round, q0;
+};
+__device__ __forceinline__ int spec_decide(const DecideArgs a, const double* sRes) {
+  const int SPEC_K = a.K, n = a.n, round = a.round, iteration = a.iteration, q0 = a.q0;
+  BandState* st = a.st;
+  int accepted = -1;
+  double lambda, ni, currentChi;
+  double cur_parts[4], last_parts[4];
+  int q;
+  if (round == 0) {
+    /* chi2 at the linearisation point = sum of the kernel-A tile partials (computeActiveErrors) */
+    const int chunks_used = (n + TP - 1) / TP;
+    const double* cp = a.chi_parts;
+    for (int c = 0; c < 4; ++c) cur_parts[c] = 0;
+    for (int ch = 0; ch < chunks_used; ++ch)
+      for (int c = 0; c < 4; ++c) cur_parts[c] += cp[4 * ch + c];
+    currentChi = cur_parts[0] + cur_parts[1] + cur_parts[2] + cur_parts[3];
+    if (iteration == 0) { lambda = a.lambda_init; ni = 2; }
+    else { lambda = st->lambda; ni = st->ni; }
+    q = 0;
+  } else {
+    lambda = st->lambda; ni = st->ni; currentChi = st->current_chi; q = q0;
+    for (int c = 0; c < 4; ++c) cur_parts[c] = st->parts_cur[c];
+  }
+  for (int c = 0; c < 4; ++c) last_parts[c] = st->parts_last[c];
+  int status_add = 0;
+  bool done = false;
+  double rho = 0;
+  for (int kk = 0; kk < SPEC_K && q < 10; ++kk) {
+    const double* r = sRes + kk * RES_STRIDE;
+    const bool ok2 = r[5] != 0.0;
+    for (int c = 0; c < 4; ++c) last_parts[c] = r[c];
+    double tempChi = r[0] + r[1] + r[2] + r[3];
+    if (!ok2) { tempChi = 1.7976931348623157e308; status_add |= TEB_STATUS_CHOL_FAILED; }
+    const double scale = r[4] + 1e-3;
+    rho = (currentChi - tempChi) / scale;
+    if (rho > 0 && isfinite(tempChi)) {
+      const double t3 = 2 * rho - 1;
+      double alpha = 1. - t3 * t3 * t3; /* pow(2 rho - 1, 3) to within 1.5 ulp, no libm call on the replay path */
+      alpha = fmin(alpha, 2. / 3.);
+      const double scaleFactor = fmax(1. / 3., alpha);
+      lambda *= scaleFactor;
+      ni = 2;
+      currentChi = tempChi;
+      for (int c = 0; c < 4; ++c) cur_parts[c] = last_parts[c];
+      accepted = kk;
+    } else {
+      lambda *= ni;
+      ni *= 2;
+      if (!isfinite(lambda)) { status_add |= TEB_STATUS_NONFINITE; done = true; break; }
+    }
+    q++;
+    if (!(rho < 0 && q < 10)) { done = true; break; }
+  }
+  st->lambda = lambda;
+  st->ni = ni;
+  st->current_chi = currentChi;
+  st->chi2_final = currentChi;
+  for (int c = 0; c < 4; ++c) { st->parts_last[c] = last_parts[c]; st->parts_cur[c] = cur_parts[c]; }
+  *a.qmax = q;
+  int stt = st->status | status_add;
+  if (done) {
+    const bool terminate = (q == 10 || rho == 0 || !isfinite(lambda));
+    st->lm_iters += 1;
+    if (terminate) { stt |= TEB_STATUS_TERMINATED; st->active = 0; }
+    else stt &= ~TEB_STATUS_TERMINATED;
+    *a.need = 0;
+  } else {
+    /* all K trials rejected: queue the band for the next round (slot order is arbitrary, results do not depend
+     * on it: every band only touches its own data) */
+    *a.need = 1;
+    const int s2 = atomicAdd(a.cnt_next, 1);
+    a.list_next[s2] = a.b;
+  }
+  st->status = stt;
+  return accepted;
 }
 
-__global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KParams kp, SpecBufs sp, int round) {
+/* ------------------------------------------------------------------ k_trial_eval: CTA per band, warp k = trial k.
+ * The K trial solutions of a band sit in adjacent lanes of the solver's interleaved scratch (one 32-byte sector per
+ * row at K = 4), so the CTA stages them - and the scene's obstacle table and the K trial states - in shared memory
+ * once. After the K chi2 are known, thread 0 replays g2o's accept / reject chain in trial order and
+ * the CTA copies the accepted trial state (discardTop()) from shared memory into the band. */
+__host__ __device__ inline size_t eval_smem_bytes(int n_cap, int M_cap, int K) {
+  return ((size_t)K * 2 + 2) * 4 * n_cap * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) +
+         (size_t)K * RES_STRIDE * sizeof(double) + 32;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch db, KParams kp, SpecBufs sp, int iteration,
+                                                                int round, int g) {
   extern __shared__ __align__(16) unsigned char ev_raw[];
   const int SPEC_K = sp.K;
-  const int b = blockIdx.x;
+  const int slot = blockIdx.x;
+  if (round > 0 && slot >= sp.cnt[g]) return;
+  const int b = (round == 0) ? slot : sp.list[(size_t)(g & 1) * db.B + slot];
   const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
-  const BandState* st = &db.state[b];
+  BandState* st = &db.state[b];
   if (!st->active) return;
-  if (round > 0 && !sp.need[b]) return;
   const int q0 = (round == 0) ? 0 : sp.qmax[b];
   const int n = db.n[b];
   const int N = 4 * n;
@@ -236,21 +336,23 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KPa
   double* sT = sdx + (size_t)SPEC_K * 4 * db.n_cap;           /* [K][n_cap][4] */
   double* sP0 = sT + (size_t)SPEC_K * 4 * db.n_cap;           /* [n_cap][4] current band */
   double* sB = sP0 + (size_t)4 * db.n_cap;                    /* [4 n_cap] right-hand side */
-  TebObstacle* so = reinterpret_cast<TebObstacle*>(sB + (size_t)4 * db.n_cap);
+  double* sRes = sB + (size_t)4 * db.n_cap;                   /* [K][RES_STRIDE] */
+  int* sAcc = reinterpret_cast<int*>(sRes + (size_t)SPEC_K * RES_STRIDE);
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(sAcc + 4);
   const int sc = db.scene_id[b];
   const int M = db.obst_count[sc];
   {
     const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
     for (int m = tid; m < M; m += 32 * SPEC_K) so[m] = go[m];
-    /* rows of the K trial solutions: system index K b + k -> solver warp (K b + k) >> 5, lane (K b + k) & 31: the
-     * trials of a band are adjacent lanes of the interleaved scratch (K even: pairs never straddle a tile) */
+    /* rows of the K trial solutions: system index K slot + k -> solver warp (K slot + k) >> 5, lane (K slot + k) & 31:
+     * the trials of a band are adjacent lanes of the interleaved scratch (K even: pairs never straddle a tile) */
     const double* gP = db.poses + (size_t)b * db.n_cap * 4;
     const double* grhs = db.rhs + (size_t)b * 4 * db.n_cap;
     for (int r = tid; r < N; r += 32 * SPEC_K) {
       sP0[r] = gP[r];
       sB[r] = grhs[r];
       for (int kk = 0; kk < SPEC_K; kk += 2) {
-        const int tsys = b * SPEC_K + kk;
+        const int tsys = slot * SPEC_K + kk;
         const double2 a = *reinterpret_cast<const double2*>(sp.dx + (size_t)(tsys >> 5) * 32 * 4 * db.n_cap +
                                                             (size_t)r * 32 + (tsys & 31));
         sdx[(size_t)kk * 4 * db.n_cap + r] = a.x;
@@ -260,15 +362,15 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KPa
   }
   __syncthreads();
   const bool mine = (q0 + k < 10);
-  double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
+  const double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
   double chi[4] = {0, 0, 0, 0};
   double scl = 0;
+  bool ok = true;
   if (mine) {
-    const bool ok = res[5] != 0.0;
+    ok = res[5] != 0.0;
     const double lambda = res[6];
     const double* mydx = sdx + (size_t)k * 4 * db.n_cap;
     double* myT = sT + (size_t)k * 4 * db.n_cap;
-    double* gT = sp.T + ((size_t)b * SPEC_K + k) * 4 * db.n_cap;
     /* trial state x [+] dx and computeScale() = sum dx (lambda dx + b) */
     for (int r = lane; r < N; r += 32) {
       double xv = sP0[r];
@@ -279,7 +381,6 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KPa
         xv = ((r & 3) == 2) ? normalize_theta(xv + dx) : xv + dx;
       }
       myT[r] = xv;
-      gT[r] = xv;
     }
     __syncwarp();
     const double* vs = db.vel_start + 4 * (size_t)b;
@@ -295,93 +396,30 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX) k_trial_eval(DevBatch db, KPa
   for (int c = 0; c < 4; ++c) chi[c] = warp_sum(chi[c]);
   scl = warp_sum(scl);
   if (mine && lane == 0) {
-    res[0] = chi[0]; res[1] = chi[1]; res[2] = chi[2]; res[3] = chi[3];
-    res[4] = scl;
+    double* r = sRes + k * RES_STRIDE;
+    r[0] = chi[0]; r[1] = chi[1]; r[2] = chi[2]; r[3] = chi[3];
+    r[4] = scl;
+    r[5] = ok ? 1.0 : 0.0;
   }
-}
+  __syncthreads();
 
-/* ------------------------------------------------------------------ k_decide: warp per band */
-__global__ void __launch_bounds__(128) k_decide(DevBatch db, SpecBufs sp, int iteration, int round) {
-  const int SPEC_K = sp.K;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (b >= db.B) return;
-  BandState* st = &db.state[b];
-  if (!st->active) return;
-  if (round > 0 && !sp.need[b]) return;
-  const int n = db.n[b];
-  int accepted = -1;
-  if (lane == 0) {
-    double lambda, ni, currentChi;
-    double cur_parts[4], last_parts[4];
-    int q;
-    if (round == 0) {
-      /* chi2 at the linearisation point = sum of the kernel-A tile partials (computeActiveErrors) */
-      const int chunks_used = (n + TP - 1) / TP;
-      const double* cp = db.chi_parts + (size_t)b * db.chunks * 4;
-      for (int c = 0; c < 4; ++c) cur_parts[c] = 0;
-      for (int ch = 0; ch < chunks_used; ++ch)
-        for (int c = 0; c < 4; ++c) cur_parts[c] += cp[4 * ch + c];
-      currentChi = cur_parts[0] + cur_parts[1] + cur_parts[2] + cur_parts[3];
-      if (iteration == 0) { lambda = band_lambda_init(db, b, n); ni = 2; }
-      else { lambda = st->lambda; ni = st->ni; }
-      q = 0;
-    } else {
-      lambda = st->lambda; ni = st->ni; currentChi = st->current_chi; q = sp.qmax[b];
-      for (int c = 0; c < 4; ++c) cur_parts[c] = st->parts_cur[c];
-    }
-    for (int c = 0; c < 4; ++c) last_parts[c] = st->parts_last[c];
-    int status_add = 0;
-    bool done = false;
-    double rho = 0;
-    for (int k = 0; k < SPEC_K && q < 10; ++k) {
-      const double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
-      const bool ok2 = res[5] != 0.0;
-      for (int c = 0; c < 4; ++c) last_parts[c] = res[c];
-      double tempChi = res[0] + res[1] + res[2] + res[3];
-      if (!ok2) { tempChi = 1.7976931348623157e308; status_add |= TEB_STATUS_CHOL_FAILED; }
-      const double scale = res[4] + 1e-3;
-      rho = (currentChi - tempChi) / scale;
-      if (rho > 0 && isfinite(tempChi)) {
-        double alpha = 1. - pow((2 * rho - 1), 3);
-        alpha = fmin(alpha, 2. / 3.);
-        const double scaleFactor = fmax(1. / 3., alpha);
-        lambda *= scaleFactor;
-        ni = 2;
-        currentChi = tempChi;
-        for (int c = 0; c < 4; ++c) cur_parts[c] = last_parts[c];
-        accepted = k;
-      } else {
-        lambda *= ni;
-        ni *= 2;
-        if (!isfinite(lambda)) { status_add |= TEB_STATUS_NONFINITE; done = true; break; }
-      }
-      q++;
-      if (!(rho < 0 && q < 10)) { done = true; break; }
-    }
-    st->lambda = lambda;
-    st->ni = ni;
-    st->current_chi = currentChi;
-    st->chi2_final = currentChi;
-    for (int c = 0; c < 4; ++c) { st->parts_last[c] = last_parts[c]; st->parts_cur[c] = cur_parts[c]; }
-    sp.qmax[b] = q;
-    int stt = st->status | status_add;
-    if (done) {
-      const bool terminate = (q == 10 || rho == 0 || !isfinite(lambda));
-      st->lm_iters += 1;
-      if (terminate) { stt |= TEB_STATUS_TERMINATED; st->active = 0; }
-      else stt &= ~TEB_STATUS_TERMINATED;
-      sp.need[b] = 0;
-    } else {
-      sp.need[b] = 1;
-    }
-    st->status = stt;
+  /* ---- accept / reject replay, sequential over the K trials */
+  if (tid == 0) {
+    DecideArgs da;
+    da.st = st; da.chi_parts = db.chi_parts + (size_t)b * db.chunks * 4;
+    da.lambda_init = (round == 0 && iteration == 0) ? band_lambda_init(db, b, n) : 0.0;
+    da.need = sp.need + b; da.qmax = sp.qmax + b; da.cnt_next = sp.cnt + g + 1;
+    da.list_next = sp.list + (size_t)((g + 1) & 1) * db.B;
+    da.b = b; da.n = n; da.K = SPEC_K; da.iteration = iteration; da.round = round; da.q0 = q0;
+    const int accepted = spec_decide(da, sRes);
+    sAcc[0] = accepted;
   }
-  accepted = __shfl_sync(0xffffffffu, accepted, 0);
+  __syncthreads();
+  const int accepted = sAcc[0];
   if (accepted >= 0) { /* discardTop(): the accepted trial state becomes the band */
     double* gP = db.poses + (size_t)b * db.n_cap * 4;
-    const double* gT = sp.T + ((size_t)b * SPEC_K + accepted) * 4 * db.n_cap;
-    for (int r = lane; r < 4 * n; r += 32) gP[r] = gT[r];
+    const double* aT = sT + (size_t)accepted * 4 * db.n_cap;
+    for (int r = tid; r < N; r += 32 * SPEC_K) gP[r] = aT[r];
   }
 }
 
