@@ -20,6 +20,10 @@ using namespace tebgpu;
 struct tebgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;        /* retry rounds of the speculative solver, overlapped with the next kernel A */
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int overlap = 1;                    /* 0: everything on one stream (TEBGPU_OVERLAP=0, profiling, k_vor) */
+  int32_t* defer = nullptr;           /* [B] */
   TebGpuLimits lim{};
   TebParams params{};
   bool have_params = false;
@@ -43,7 +47,8 @@ struct tebgpu_ctx {
   int32_t* dyn_idx = nullptr;
   int32_t* dyn_cnt = nullptr;
   SpecBufs spec{};
-  int eval_minb = 2; /* k_trial_eval register budget: 2 -> 128 regs, 3 -> 80 regs (TEBGPU_EVAL_MINB, experiments) */
+  int eval_minb = 3; /* k_trial_eval register budget: 3 -> 80 registers, 6 CTAs/SM (measured 3-4 % faster than 2 -> 122
+                        registers, 4 CTAs/SM, despite 180 bytes of spills); TEBGPU_EVAL_MINB=2 selects the other build */
   BandState* state = nullptr;
   /* device mirrors for the host-buffer entry point */
   double* d_poses = nullptr; int32_t* d_n = nullptr; int32_t* d_scene = nullptr; TebObstacle* d_obst = nullptr;
@@ -145,7 +150,7 @@ const char* tebgpu_last_error_string(const tebgpu_ctx* ctx) { return ctx ? ctx->
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static void free_all(tebgpu_ctx* c) {
-  void* ptrs[] = {c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+  void* ptrs[] = {c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
                   c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
                   c->d_status, c->d_iters};
   for (void* p : ptrs)
@@ -173,6 +178,14 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   *out = c;
   CUDA_TRY(c, cudaSetDevice(device));
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0; /* the latency-bound retry chain should never queue behind the bulk kernels */
+    CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(c, cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+  }
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  if (const char* e = std::getenv("TEBGPU_OVERLAP")) c->overlap = std::atoi(e) != 0;
   const size_t B = c->lim.max_bands, nc = c->lim.max_poses, S = c->lim.max_scenes, M = c->lim.max_obstacles,
                V = c->lim.max_viapoints > 0 ? c->lim.max_viapoints : 1;
   CUDA_TRY(c, cudaMalloc(&c->Hb, B * 4 * nc * HROW * sizeof(double)));
@@ -197,7 +210,8 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaMalloc(&c->spec.Lf, spec_sys * 4 * nc * HROW * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->spec.dx, spec_sys * 4 * nc * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->spec.cnt, SPEC_CNT_CAP * sizeof(int32_t)));
-  CUDA_TRY(c, cudaMalloc(&c->spec.list, 2 * B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.list, 3 * B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->defer, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.res, B * SPEC_K_MAX * RES_STRIDE * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->spec.need, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.qmax, B * sizeof(int32_t)));
@@ -238,6 +252,9 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   /* ask for the full shared-memory carveout: occupancy of the tile kernels is shared-memory bound */
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   tebgpu_default_params(&c->params);
@@ -253,6 +270,9 @@ int32_t tebgpu_destroy(tebgpu_ctx* ctx) {
   free_all(ctx);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
   return TEBGPU_OK;
 }
@@ -335,6 +355,7 @@ static DevBatch make_devbatch(tebgpu_ctx* ctx, const TebBatch* bt) {
   d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.assoc3 = ctx->assoc3; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts; d.dmax_parts = ctx->dmax_parts; d.rhs = ctx->rhs; d.dyn_idx = ctx->dyn_idx; d.dyn_cnt = ctx->dyn_cnt;
   d.state = ctx->state;
   d.chunks = (bt->n_cap + TP - 1) / TP;
+  d.defer = ctx->defer; d.a_list = nullptr; d.a_cnt = nullptr; d.skip_tag = 0;
   return d;
 }
 
@@ -366,7 +387,14 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
     const long long need_cnt = (long long)args->iterations_outerloop * args->iterations_innerloop * ((10 + spec_K - 1) / spec_K) + 2;
     if (need_cnt > SPEC_CNT_CAP) { ctx->err = "outer x inner iterations exceed the retry-list counters"; return TEBGPU_ERR_CAPACITY; }
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->spec.cnt, 0, (size_t)need_cnt * sizeof(int32_t), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->defer, 0, (size_t)B * sizeof(int32_t), st));
   }
+  /* Retry rounds (bands that rejected all K trials: ~5 % at K = 4) are latency bound and nearly empty. They run on a
+   * side stream, followed by kernel A of the next inner iteration for exactly those bands, while the main stream
+   * linearises all other bands; both join before the next solve. Bands never share data, so this is only a
+   * re-ordering of independent work. */
+  const bool overlap = ctx->solver == 2 && ctx->overlap && !ctx->profiling;
+  int tag = 0; /* running inner-iteration number (1-based) */
   double weight_multiplier = 1.0;
   KParams kp = make_kparams(p, weight_multiplier);
   prof_begin(ctx, st, 0); k_begin<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st);
@@ -374,20 +402,48 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
     kp = make_kparams(p, weight_multiplier);
     if (p.teb_autosize) { prof_begin(ctx, st, 1); k_auto_resize<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st); }
     prof_begin(ctx, st, 2); k_build_graph<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st);
+    bool deferred_done = false; /* kernel A of this iteration already ran for the deferred bands (side stream) */
     for (int it = 0; it < args->iterations_innerloop; ++it) {
-      prof_begin(ctx, st, 3); launch_linearize(ctx, db, kp, B, bt->M_cap, st); ++launches; prof_end(ctx, st);
-      if (kp.has_vor) { prof_begin(ctx, st, 3); k_vor<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st); }
+      ++tag;
+      {
+        DevBatch da = db;
+        if (deferred_done) da.skip_tag = tag - 1; /* bands queued during the previous iteration were linearised on the side stream */
+        prof_begin(ctx, st, 3); launch_linearize(ctx, da, kp, B, bt->M_cap, st); ++launches; prof_end(ctx, st);
+        if (kp.has_vor) { prof_begin(ctx, st, 3); k_vor<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st); }
+        if (deferred_done) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0)); deferred_done = false; }
+      }
       if (ctx->solver == 2) {
         const int K = spec_K;
         ctx->spec.K = K;
         const int bk = B * K;
         const int rounds = (10 + K - 1) / K; /* g2o's maxTrialsAfterFailure = 10 */
+        const size_t smem_e = eval_smem_bytes(bt->n_cap, bt->M_cap, K);
+        const bool fork = overlap && rounds > 1 && !kp.has_vor;
+        cudaStream_t rs = st;
         for (int round = 0; round < rounds; ++round, ++g) {
-          prof_begin(ctx, st, round == 0 ? 6 : 4); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, st>>>(db, ctx->spec, it, round, g); ++launches; prof_end(ctx, st);
+          if (round == 1 && fork) { /* retry rounds go to the side stream */
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+            rs = ctx->side;
+          }
+          prof_begin(ctx, st, round == 0 ? 6 : 4); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, rs>>>(db, ctx->spec, it, round, g); ++launches; prof_end(ctx, st);
           prof_begin(ctx, st, round == 0 ? 7 : 4);
-          if (ctx->eval_minb == 3) k_trial_eval<3><<<B, 32 * K, eval_smem_bytes(bt->n_cap, bt->M_cap, K), st>>>(db, kp, ctx->spec, it, round, g);
-          else k_trial_eval<2><<<B, 32 * K, eval_smem_bytes(bt->n_cap, bt->M_cap, K), st>>>(db, kp, ctx->spec, it, round, g);
+          if (ctx->eval_minb == 3) k_trial_eval<3><<<B, 32 * K, smem_e, rs>>>(db, kp, ctx->spec, it, round, g, tag);
+          else k_trial_eval<2><<<B, 32 * K, smem_e, rs>>>(db, kp, ctx->spec, it, round, g, tag);
           ++launches; prof_end(ctx, st);
+        }
+        if (fork) {
+          if (it + 1 < args->iterations_innerloop) { /* next kernel A for the bands of the round-1 list, then join */
+            DevBatch dl = db;
+            dl.a_list = ctx->spec.list + (size_t)((g - rounds + 1) % 3) * B;
+            dl.a_cnt = ctx->spec.cnt + (g - rounds + 1);
+            launch_linearize(ctx, dl, kp, B, bt->M_cap, ctx->side); ++launches;
+            deferred_done = true;
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+          } else {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+          }
         }
       } else {
         prof_begin(ctx, st, 4);

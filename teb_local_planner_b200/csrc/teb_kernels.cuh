@@ -75,7 +75,20 @@ struct DevBatch {
   double* dmax_parts;         /* [B][chunks] max |H_rr| over the real rows of the tile (LM lambda init) */
   BandState* state;           /* [B]              */
   int32_t chunks;
+  /* kernel A band selection (speculative solver, retry rounds overlapped with the next linearisation):
+   * a_list != NULL: blockIdx.y indexes the list (a_cnt entries); else bands with defer[b] == skip_tag are skipped */
+  const int32_t* a_list;
+  const int32_t* a_cnt;
+  int32_t* defer;             /* [B] tag of the inner iteration in which the band was queued for a retry round */
+  int32_t skip_tag;
 };
+
+/* band handled by this CTA of kernel A, or -1 */
+__device__ __forceinline__ int linearize_band(const DevBatch& db, int y) {
+  if (db.a_list) return (y < *db.a_cnt) ? db.a_list[y] : -1;
+  if (db.skip_tag != 0 && db.defer[y] == db.skip_tag) return -1;
+  return y;
+}
 
 /* ------------------------------------------------------------------ small block utilities */
 __device__ __forceinline__ double warp_sum(double v) {
@@ -734,7 +747,8 @@ __host__ __device__ inline size_t ka_smem_bytes(int M_cap) {
 template <bool HOLO>
 __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int b = blockIdx.y;
+  const int b = linearize_band(db, blockIdx.y);
+  if (b < 0) return;
   const BandState* st = &db.state[b];
   if (!st->active) return;
   const int n = db.n[b];
@@ -913,7 +927,8 @@ __global__ void __launch_bounds__(32 * KW_WARPS) k_linearize_w(const __grid_cons
                                                                const __grid_constant__ KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   static_assert(TP == 32, "the warp-per-tile kernel maps one pose / four rows to a lane");
-  const int b = blockIdx.y;
+  const int b = linearize_band(db, blockIdx.y);
+  if (b < 0) return;
   if (!db.state[b].active) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = db.n[b];

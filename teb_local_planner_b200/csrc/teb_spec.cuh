@@ -34,7 +34,7 @@ struct SpecBufs {
   int32_t* need; /* [B] band still needs trials in this LM iteration          */
   int32_t* qmax; /* [B] trials consumed in this LM iteration                  */
   int32_t* cnt;  /* [rounds of the call + 1] length of the retry list a round reads (zeroed per call) */
-  int32_t* list; /* [2][B] bands of the retry list, double buffered by round parity                    */
+  int32_t* list; /* [3][B] bands of the retry list, buffer g % 3 is read by round g                    */
   int32_t K;     /* speculation width of this call                            */
 };
 
@@ -51,11 +51,14 @@ __device__ __forceinline__ double band_lambda_init(const DevBatch& db, int b, in
 }
 
 /* ------------------------------------------------------------------ k_solve_tpb
- * One warp per CTA. Every thread owns a private ring of 11 row slots in shared memory ([slot][16-byte pair][lane] so
- * that a warp access is conflict free) that cp.async (LDGSTS) fills 11 rows ahead of their use: the H rows during the
- * factorisation, the factor rows during the back substitution. No registers are spent on prefetching and the global
- * latency is off the dependent chain. */
-constexpr int TPB_RING_BYTES = 11 * 6 * 32 * 16;
+ * One warp per CTA. Every thread owns a private ring of TPB_RING row slots in shared memory ([slot][16-byte pair][lane]
+ * so that a warp access is conflict free) that cp.async (LDGSTS) fills TPB_RING rows ahead of their use: the H rows
+ * during the factorisation, the factor rows during the back substitution. No registers are spent on prefetching and
+ * the global latency is off the dependent chain. 10 slots (30 KB) instead of 11 let SEVEN solver warps share an SM
+ * (7 x 31 KB <= 227 KB; 254 registers x 32 x 7 fits the register file), which is what makes 8192 bands x 4 trials a
+ * single wave on 148 SMs. */
+constexpr int TPB_RING = 10;
+constexpr int TPB_RING_BYTES = TPB_RING * 6 * 32 * 16;
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
   const int k = t - slot * SPEC_K;
   const int nslots = (round == 0) ? db.B : sp.cnt[g];
   if (slot >= nslots) return; /* threads are independent: no warp-level primitive below */
-  const int b = (round == 0) ? slot : sp.list[(size_t)(g & 1) * db.B + slot];
+  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
   bool work = true;
   const BandState* st = &db.state[b];
   if (!st->active) work = false;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
     Y[m] = h[11];
   }
 #pragma unroll
-  for (int m = 0; m < 11; ++m) {
+  for (int m = 0; m < TPB_RING; ++m) {
     const int r = 11 + m;
     if (r < N) {
 #pragma unroll
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
     cp_async_commit();
   }
   bool ok = true;
+  int rs = 0; /* ring slot that holds row j + 11 */
   /* rows N .. Npad-1 are identity rows: every block of 11 pivots runs unconditionally, which keeps the register
    * window's liveness static (a data-dependent early exit makes the compiler keep all 121 slots alive) */
   for (int j0 = 0; j0 < N; j0 += 11) {
@@ -148,13 +152,13 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
         if (u & 1) lprev = lu;
         else if (live) dst[(u / 2) * 32] = make_double2(lprev, lu);
       }
-      /* install row j + 11 (copied into ring slot s eleven pivots ago), then refill the slot with row j + 22 */
-      cp_async_wait<10>();
+      /* install row j + 11 (copied into ring slot rs TPB_RING pivots ago), then refill the slot with row j + 11 + TPB_RING */
+      cp_async_wait<TPB_RING - 1>();
       const int rn = j + 11;
       if (rn < N) {
 #pragma unroll
-        for (int v = 0; v < 5; ++v) { const double2 d2 = ringp[(s * 6 + v) * 32]; E[2 * v][s] = d2.x; E[2 * v + 1][s] = d2.y; }
-        const double2 d2 = ringp[(s * 6 + 5) * 32];
+        for (int v = 0; v < 5; ++v) { const double2 d2 = ringp[(rs * 6 + v) * 32]; E[2 * v][s] = d2.x; E[2 * v + 1][s] = d2.y; }
+        const double2 d2 = ringp[(rs * 6 + 5) * 32];
         E[10][s] = d2.x;
         Y[s] = d2.y;
         if (row_is_real(rn, n)) E[0][s] += lambda;
@@ -164,11 +168,12 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
         E[0][s] = 1.0;
         Y[s] = 0.0;
       }
-      if (rn + 11 < N) {
+      if (rn + TPB_RING < N) {
 #pragma unroll
-        for (int v = 0; v < 6; ++v) cp_async16(ring + (uint32_t)((s * 6 + v) * 512), gH + (size_t)(rn + 11) * HROW + 2 * v);
+        for (int v = 0; v < 6; ++v) cp_async16(ring + (uint32_t)((rs * 6 + v) * 512), gH + (size_t)(rn + TPB_RING) * HROW + 2 * v);
       }
       cp_async_commit();
+      rs = (rs + 1 == TPB_RING) ? 0 : rs + 1;
     }
   }
   cp_async_wait<0>();
@@ -183,33 +188,35 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
   for (int m = 0; m < 11; ++m) X[m] = 0;
   const int jtop = ((N - 1) / 11) * 11;
 #pragma unroll
-  for (int s = 10; s >= 0; --s) {
-    const int j = jtop + s;
+  for (int c = 0; c < TPB_RING; ++c) { /* rows jtop + 10 - c, c = 0 .. TPB_RING - 1 */
+    const int j = jtop + 10 - c;
     if (j < N) {
 #pragma unroll
-      for (int v = 0; v < 6; ++v) cp_async16(ring + (uint32_t)((s * 6 + v) * 512), gL + ((size_t)j * 6 + v) * 32);
+      for (int v = 0; v < 6; ++v) cp_async16(ring + (uint32_t)((c * 6 + v) * 512), gL + ((size_t)j * 6 + v) * 32);
     }
     cp_async_commit();
   }
+  rs = 0;
   for (int j0 = jtop; j0 >= 0; j0 -= 11) {
 #pragma unroll
     for (int s = 10; s >= 0; --s) {
       const int j = j0 + s;
       const bool live = j < N;
-      cp_async_wait<10>();
+      cp_async_wait<TPB_RING - 1>();
       double l[12];
       if (live) {
 #pragma unroll
-        for (int v = 0; v < 6; ++v) { const double2 d2 = ringp[(s * 6 + v) * 32]; l[2 * v] = d2.x; l[2 * v + 1] = d2.y; }
+        for (int v = 0; v < 6; ++v) { const double2 d2 = ringp[(rs * 6 + v) * 32]; l[2 * v] = d2.x; l[2 * v + 1] = d2.y; }
       } else {
 #pragma unroll
         for (int v = 0; v < 12; ++v) l[v] = 0.0;
       }
-      if (j - 11 >= 0) {
+      if (j - TPB_RING >= 0) {
 #pragma unroll
-        for (int v = 0; v < 6; ++v) cp_async16(ring + (uint32_t)((s * 6 + v) * 512), gL + ((size_t)(j - 11) * 6 + v) * 32);
+        for (int v = 0; v < 6; ++v) cp_async16(ring + (uint32_t)((rs * 6 + v) * 512), gL + ((size_t)(j - TPB_RING) * 6 + v) * 32);
       }
       cp_async_commit();
+      rs = (rs + 1 == TPB_RING) ? 0 : rs + 1;
       double acc = l[1];
 #pragma unroll
       for (int u = 10; u >= 1; --u) acc -= l[1 + u] * X[(s + u) % 11];
@@ -230,6 +237,8 @@ struct DecideArgs { /* passed by value: a reference to the kernel parameters wou
   int32_t* qmax;           /* &qmax[b] */
   int32_t* cnt_next;       /* &cnt[g + 1] */
   int32_t* list_next;      /* list buffer of round g + 1 */
+  int32_t* defer;          /* &defer[b] */
+  int32_t tag;             /* inner-iteration tag written to defer[b] when the band is queued */
   int32_t b, n, K, iteration, round, q0;
 };
 __device__ __forceinline__ int spec_decide(const DecideArgs a, const double* sRes) {
@@ -303,6 +312,7 @@ __device__ __forceinline__ int spec_decide(const DecideArgs a, const double* sRe
     *a.need = 1;
     const int s2 = atomicAdd(a.cnt_next, 1);
     a.list_next[s2] = a.b;
+    *a.defer = a.tag;
   }
   st->status = stt;
   return accepted;
@@ -320,12 +330,12 @@ __host__ __device__ inline size_t eval_smem_bytes(int n_cap, int M_cap, int K) {
 
 template <int MINB>
 __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch db, KParams kp, SpecBufs sp, int iteration,
-                                                                int round, int g) {
+                                                                int round, int g, int tag) {
   extern __shared__ __align__(16) unsigned char ev_raw[];
   const int SPEC_K = sp.K;
   const int slot = blockIdx.x;
   if (round > 0 && slot >= sp.cnt[g]) return;
-  const int b = (round == 0) ? slot : sp.list[(size_t)(g & 1) * db.B + slot];
+  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
   const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
   BandState* st = &db.state[b];
   if (!st->active) return;
@@ -409,7 +419,8 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch d
     da.st = st; da.chi_parts = db.chi_parts + (size_t)b * db.chunks * 4;
     da.lambda_init = (round == 0 && iteration == 0) ? band_lambda_init(db, b, n) : 0.0;
     da.need = sp.need + b; da.qmax = sp.qmax + b; da.cnt_next = sp.cnt + g + 1;
-    da.list_next = sp.list + (size_t)((g + 1) & 1) * db.B;
+    da.list_next = sp.list + (size_t)((g + 1) % 3) * db.B;
+    da.defer = db.defer + b; da.tag = tag;
     da.b = b; da.n = n; da.K = SPEC_K; da.iteration = iteration; da.round = round; da.q0 = q0;
     const int accepted = spec_decide(da, sRes);
     sAcc[0] = accepted;
