@@ -42,9 +42,16 @@ extern "C" {
 #define TEB_STATUS_TERMINATED     16   /* LM returned Terminate in the last optimizeGraph call      */
 #define TEB_STATUS_DISABLED       32   /* optimization_activate == false / max_vel_x < 0.01          */
 #define TEB_STATUS_CAPACITY       64   /* autoResize needed more than n_cap poses: band left unoptimised */
+#define TEB_STATUS_BAD_INPUT     128   /* the band's scene holds an obstacle row the batch cannot describe (vertex range
+                                          outside obst_vertices, unknown type): band left unoptimised */
 
-enum { TEB_FOOTPRINT_POINT = 0, TEB_FOOTPRINT_CIRCULAR = 1, TEB_FOOTPRINT_TWO_CIRCLES = 2 };
-enum { TEB_OBST_POINT = 0, TEB_OBST_CIRCULAR = 1 };
+/* robot_footprint_model.h: PointRobotFootprint :131, CircularRobotFootprint :205, TwoCirclesRobotFootprint :303,
+ * LineRobotFootprint :439, PolygonRobotFootprint :635 */
+enum { TEB_FOOTPRINT_POINT = 0, TEB_FOOTPRINT_CIRCULAR = 1, TEB_FOOTPRINT_TWO_CIRCLES = 2, TEB_FOOTPRINT_LINE = 3,
+       TEB_FOOTPRINT_POLYGON = 4 };
+/* obstacles.h: PointObstacle :305, CircularObstacle :447, LineObstacle :597, PillObstacle :746, PolygonObstacle :893 */
+enum { TEB_OBST_POINT = 0, TEB_OBST_CIRCULAR = 1, TEB_OBST_LINE = 2, TEB_OBST_PILL = 3, TEB_OBST_POLYGON = 4 };
+#define TEB_MAX_FOOTPRINT_VERTICES 16
 enum { TEB_ROTDIR_NONE = 0, TEB_ROTDIR_LEFT = 1, TEB_ROTDIR_RIGHT = 2 };
 
 /* POD mirror of the TebConfig fields read on the hot path
@@ -80,7 +87,9 @@ typedef struct TebParams {
   double  footprint_rear_offset;
   double  footprint_rear_radius;
   int32_t footprint_type;
-  int32_t _pad1;
+  int32_t footprint_vertex_count;  /* polygon: 1 .. TEB_MAX_FOOTPRINT_VERTICES (robot frame, not closed) */
+  double  footprint_line[4];       /* line: start x, y, end x, y in the robot frame (robot_footprint_model.h:439) */
+  double  footprint_vertices[2 * TEB_MAX_FOOTPRINT_VERTICES]; /* polygon: x0, y0, x1, y1, ... (:635) */
   /* obstacles */
   double  min_obstacle_dist;
   double  inflation_dist;
@@ -133,14 +142,22 @@ typedef struct TebParams {
   double  divergence_detection_max_chi_squared;
 } TebParams;
 
-/* Obstacle table row (48 bytes): Point / Circular obstacles with constant-velocity model
- * (include/teb_local_planner/obstacles.h:305-445 PointObstacle, :447-595 CircularObstacle). */
+/* Obstacle table row (64 bytes), constant-velocity model (obstacles.h:190-206).
+ * Point / Circular (obstacles.h:305-445, :447-595): (x, y) is the position, radius the circle radius.
+ * Line / Pill / Polygon (:597-740, :746-890, :893-1045): the shape is the vertex list
+ * obst_vertices[scene][vertex_begin .. vertex_begin + vertex_count) (2 vertices for Line / Pill; a polygon is closed
+ * implicitly when it has more than 2 vertices, distance_calculations.h:172-199), radius is the pill radius and (x, y)
+ * must hold getCentroid() (line midpoint :734; polygon centroid obstacles.cpp:47-97) — the obstacle association uses
+ * it to tell left from right (optimal_planner.cpp:503). */
 typedef struct TebObstacle {
-  double  x, y;       /* centroid */
-  double  vx, vy;     /* centroid velocity (obstacles.h:206) */
-  double  radius;     /* 0 for point obstacles */
-  int32_t dynamic;    /* isDynamic() (obstacles.h:199) */
-  int32_t type;       /* TEB_OBST_* */
+  double  x, y;          /* position / centroid */
+  double  vx, vy;        /* centroid velocity (obstacles.h:206) */
+  double  radius;        /* Circular, Pill; 0 otherwise */
+  int32_t dynamic;       /* isDynamic() (obstacles.h:199) */
+  int32_t type;          /* TEB_OBST_* */
+  int32_t vertex_begin;  /* Line / Pill / Polygon: first vertex in the scene's vertex pool */
+  int32_t vertex_count;
+  double  _pad;
 } TebObstacle;
 
 /* A batch of bands (homotopy candidates x planning requests). All pointers are HOST pointers for
@@ -151,12 +168,13 @@ typedef struct TebBatch {
   int32_t S;          /* number of scenes (obstacle tables)                 */
   int32_t M_cap;      /* obstacle rows per scene (stride)                   */
   int32_t V_cap;      /* via-points per band (stride); may be 0             */
-  int32_t _pad;
+  int32_t PV_cap;     /* obstacle vertices per scene (stride); 0 <=> only Point / Circular obstacles */
   double*            poses;       /* [B][n_cap][4]  in/out                              */
   int32_t*           n;           /* [B]            in/out (autoResize changes it)      */
   const int32_t*     scene_id;    /* [B]                                                */
   const TebObstacle* obstacles;   /* [S][M_cap]                                         */
   const int32_t*     obst_count;  /* [S]                                                */
+  const double*      obst_vertices; /* [S][PV_cap][2] vertex pool of the Line / Pill / Polygon obstacles, or NULL   */
   const double*      via;         /* [B][V_cap][2] or NULL                              */
   const int32_t*     via_count;   /* [B] or NULL                                        */
   const double*      vel_start;   /* [B][4] = vx, vy, omega, active(0/1)  (optimal_planner.cpp:233-245) */
@@ -184,7 +202,7 @@ typedef struct TebGpuLimits {
   int32_t max_scenes;
   int32_t max_obstacles;  /* M_cap capacity (<= 256) */
   int32_t max_viapoints;  /* V_cap capacity */
-  int32_t _pad;
+  int32_t max_obst_vertices; /* PV_cap capacity (0: Point / Circular obstacles only) */
 } TebGpuLimits;
 
 typedef struct tebgpu_ctx tebgpu_ctx;

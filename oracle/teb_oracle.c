@@ -114,6 +114,7 @@ struct Graph {
   int n;
   const TebObstacle* obst;
   int M;
+  const double* pverts; /* vertex pool of the scene's Line / Pill / Polygon obstacles: [PV][2] */
   const double* via;
   int V;
   double vel_start[4], vel_goal[4];
@@ -155,8 +156,151 @@ static inline double obst_dist_t(const TebObstacle* o, double px, double py, dou
   double dx = o->x + t * o->vx - px, dy = o->y + t * o->vy - py;
   return sqrt(dx * dx + dy * dy) - o->radius;
 }
-/* BaseRobotFootprintModel::calculateDistance (robot_footprint_model.h:160, :263, :351) */
-static double footprint_dist(const TebParams* c, const double* pose, const TebObstacle* o) {
+
+/* ------------------------------------------------------------------ generic shapes (distance_calculations.h)
+ * Line / Polygon footprints (robot_footprint_model.h:439-560, :635-760) and Line / Pill / Polygon obstacles
+ * (obstacles.h:597-1045). A shape is a vertex list: 1 vertex = point, 2 = one segment, k > 2 = closed polygon
+ * (k edges), exactly the edge enumeration of distance_point_to_polygon_2d / distance_segment_to_polygon_2d /
+ * distance_polygon_to_polygon_2d (:172-262). Besides the distance the functions return the pair of closest points,
+ * from which the closed-form gradient follows: d d / d(x, y) = n, d d / d theta = n . J (c_robot - p), n the unit
+ * vector from the obstacle's to the robot's closest point (0 when the shapes intersect). */
+#define ORACLE_MAX_SHAPE 64
+
+/* closest_point_on_line_segment_2d distance_calculations.h:60-75 */
+static void closest_on_segment(const double* pt, const double* a, const double* b, double* out) {
+  double dx = b[0] - a[0], dy = b[1] - a[1];
+  double sq = dx * dx + dy * dy;
+  if (sq == 0) { out[0] = a[0]; out[1] = a[1]; return; }
+  double u = ((pt[0] - a[0]) * dx + (pt[1] - a[1]) * dy) / sq;
+  if (u <= 0) { out[0] = a[0]; out[1] = a[1]; }
+  else if (u >= 1) { out[0] = b[0]; out[1] = b[1]; }
+  else { out[0] = a[0] + u * dx; out[1] = a[1] + u * dy; }
+}
+static double pt_dist(const double* a, const double* b) {
+  double dx = a[0] - b[0], dy = a[1] - b[1];
+  return sqrt(dx * dx + dy * dy);
+}
+/* check_line_segments_intersection_2d distance_calculations.h:97-127 */
+static int segments_intersect(const double* l1s, const double* l1e, const double* l2s, const double* l2e) {
+  double l1x = l1e[0] - l1s[0], l1y = l1e[1] - l1s[1];
+  double l2x = l2e[0] - l2s[0], l2y = l2e[1] - l2s[1];
+  double denom = l1x * l2y - l2x * l1y;
+  if (denom == 0) return 0;
+  int denom_pos = denom > 0;
+  double ax = l1s[0] - l2s[0], ay = l1s[1] - l2s[1];
+  double s_numer = l1x * ay - l1y * ax;
+  if ((s_numer < 0) == denom_pos) return 0;
+  double t_numer = l2x * ay - l2y * ax;
+  if ((t_numer < 0) == denom_pos) return 0;
+  if (((s_numer > denom) == denom_pos) || ((t_numer > denom) == denom_pos)) return 0;
+  return 1;
+}
+/* distance_segment_to_segment_2d distance_calculations.h:139-156; c1 on line1, c2 on line2 */
+static double seg_seg_dist(const double* l1s, const double* l1e, const double* l2s, const double* l2e, double* c1, double* c2) {
+  if (segments_intersect(l1s, l1e, l2s, l2e)) { c1[0] = c2[0] = l1s[0]; c1[1] = c2[1] = l1s[1]; return 0; }
+  double q[2], best, d;
+  closest_on_segment(l1s, l2s, l2e, q); best = pt_dist(l1s, q);
+  c1[0] = l1s[0]; c1[1] = l1s[1]; c2[0] = q[0]; c2[1] = q[1];
+  closest_on_segment(l1e, l2s, l2e, q); d = pt_dist(l1e, q);
+  if (d < best) { best = d; c1[0] = l1e[0]; c1[1] = l1e[1]; c2[0] = q[0]; c2[1] = q[1]; }
+  closest_on_segment(l2s, l1s, l1e, q); d = pt_dist(l2s, q);
+  if (d < best) { best = d; c2[0] = l2s[0]; c2[1] = l2s[1]; c1[0] = q[0]; c1[1] = q[1]; }
+  closest_on_segment(l2e, l1s, l1e, q); d = pt_dist(l2e, q);
+  if (d < best) { best = d; c2[0] = l2e[0]; c2[1] = l2e[1]; c1[0] = q[0]; c1[1] = q[1]; }
+  return best;
+}
+static int shape_edges(int k) { return k <= 1 ? 1 : (k == 2 ? 1 : k); }
+/* minimum distance between the robot shape rv[rk] and the obstacle shape ov[ok]; obst_first: the obstacle segment is
+ * line1 of distance_segment_to_segment_2d (LineObstacle / PillObstacle, obstacles.h:659, :806), else the robot's */
+static double shape_distance(const double* rv, int rk, const double* ov, int ok, int obst_first, double* cr, double* co) {
+  double best = HUGE_VAL;
+  cr[0] = rv[0]; cr[1] = rv[1]; co[0] = ov[0]; co[1] = ov[1];
+  int re = shape_edges(rk), oe = shape_edges(ok);
+  for (int i = 0; i < re; ++i) {
+    const double* r0 = rv + 2 * i;
+    const double* r1 = rv + 2 * ((i + 1) % rk);
+    for (int j = 0; j < oe; ++j) {
+      const double* o0 = ov + 2 * j;
+      const double* o1 = ov + 2 * ((j + 1) % ok);
+      double a[2], b[2], d;
+      if (rk == 1 && ok == 1) { a[0] = r0[0]; a[1] = r0[1]; b[0] = o0[0]; b[1] = o0[1]; d = pt_dist(r0, o0); }
+      else if (rk == 1) { closest_on_segment(r0, o0, o1, b); a[0] = r0[0]; a[1] = r0[1]; d = pt_dist(r0, b); }
+      else if (ok == 1) { closest_on_segment(o0, r0, r1, a); b[0] = o0[0]; b[1] = o0[1]; d = pt_dist(o0, a); }
+      else if (obst_first) d = seg_seg_dist(o0, o1, r0, r1, b, a);
+      else d = seg_seg_dist(r0, r1, o0, o1, a, b);
+      if (d < best) { best = d; cr[0] = a[0]; cr[1] = a[1]; co[0] = b[0]; co[1] = b[1]; }
+    }
+  }
+  return best;
+}
+static int generic_pair(const TebParams* c, const TebObstacle* o) {
+  return c->footprint_type >= TEB_FOOTPRINT_LINE || o->type >= TEB_OBST_LINE;
+}
+/* calculateDistance / estimateSpatioTemporalDistance for every footprint x obstacle combination; grad may be NULL */
+static double generic_distance(const TebParams* c, const double* pose, const TebObstacle* o, const double* pool, double t,
+                               double* grad) {
+  double ov[2 * ORACLE_MAX_SHAPE];
+  int ok;
+  double offx = t * o->vx, offy = t * o->vy;
+  if (o->type >= TEB_OBST_LINE && o->vertex_count >= 1 && pool) {
+    ok = o->vertex_count;
+    if (ok > ORACLE_MAX_SHAPE) ok = ORACLE_MAX_SHAPE;
+    for (int k = 0; k < ok; ++k) {
+      ov[2 * k] = pool[2 * (o->vertex_begin + k)] + offx;
+      ov[2 * k + 1] = pool[2 * (o->vertex_begin + k) + 1] + offy;
+    }
+  } else { ok = 1; ov[0] = o->x + offx; ov[1] = o->y + offy; }
+  const int obst_first = (o->type == TEB_OBST_LINE || o->type == TEB_OBST_PILL);
+  const double orad = (o->type == TEB_OBST_CIRCULAR || o->type == TEB_OBST_PILL) ? o->radius : 0.0;
+  double cs = cos(pose[2]), sn = sin(pose[2]);
+  double rv[2 * TEB_MAX_FOOTPRINT_VERTICES];
+  double best = HUGE_VAL, bcr[2] = {pose[0], pose[1]}, bco[2] = {pose[0], pose[1]};
+  int nsub = (c->footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) ? 2 : 1;
+  for (int sub = 0; sub < nsub; ++sub) {
+    int rk = 1;
+    double rrad = 0;
+    switch (c->footprint_type) {
+      case TEB_FOOTPRINT_CIRCULAR: rv[0] = pose[0]; rv[1] = pose[1]; rrad = c->footprint_radius; break;
+      case TEB_FOOTPRINT_TWO_CIRCLES: {
+        double off = sub == 0 ? c->footprint_front_offset : -c->footprint_rear_offset;
+        rv[0] = pose[0] + off * cs; rv[1] = pose[1] + off * sn;
+        rrad = sub == 0 ? c->footprint_front_radius : c->footprint_rear_radius;
+        break;
+      }
+      case TEB_FOOTPRINT_LINE: /* LineRobotFootprint::transformToWorld robot_footprint_model.h:604-612 */
+        rk = 2;
+        for (int k = 0; k < 2; ++k) {
+          double lx = c->footprint_line[2 * k], ly = c->footprint_line[2 * k + 1];
+          rv[2 * k] = pose[0] + cs * lx - sn * ly;
+          rv[2 * k + 1] = pose[1] + sn * lx + cs * ly;
+        }
+        break;
+      case TEB_FOOTPRINT_POLYGON: /* PolygonRobotFootprint::transformToWorld :757-766 */
+        rk = c->footprint_vertex_count;
+        for (int k = 0; k < rk; ++k) {
+          double lx = c->footprint_vertices[2 * k], ly = c->footprint_vertices[2 * k + 1];
+          rv[2 * k] = pose[0] + cs * lx - sn * ly;
+          rv[2 * k + 1] = pose[1] + sn * lx + cs * ly;
+        }
+        break;
+      default: rv[0] = pose[0]; rv[1] = pose[1]; break;
+    }
+    double cr[2], co[2];
+    double d = shape_distance(rv, rk, ov, ok, obst_first, cr, co) - orad - rrad;
+    if (d < best) { best = d; bcr[0] = cr[0]; bcr[1] = cr[1]; bco[0] = co[0]; bco[1] = co[1]; }
+  }
+  if (grad) {
+    double nx = bcr[0] - bco[0], ny = bcr[1] - bco[1];
+    double nn = sqrt(nx * nx + ny * ny);
+    if (nn > 0) { nx /= nn; ny /= nn; } else { nx = ny = 0; }
+    grad[0] = nx; grad[1] = ny;
+    grad[2] = -nx * (bcr[1] - pose[1]) + ny * (bcr[0] - pose[0]);
+  }
+  return best;
+}
+/* BaseRobotFootprintModel::calculateDistance (robot_footprint_model.h:160, :263, :351, :496, :690) */
+static double footprint_dist(const TebParams* c, const double* pose, const TebObstacle* o, const double* pool) {
+  if (generic_pair(c, o)) return generic_distance(c, pose, o, pool, 0.0, NULL);
   switch (c->footprint_type) {
     case TEB_FOOTPRINT_CIRCULAR: return obst_dist(o, pose[0], pose[1]) - c->footprint_radius;
     case TEB_FOOTPRINT_TWO_CIRCLES: {
@@ -171,7 +315,8 @@ static double footprint_dist(const TebParams* c, const double* pose, const TebOb
   }
 }
 /* estimateSpatioTemporalDistance (robot_footprint_model.h:172, :275, :366) */
-static double footprint_dist_t(const TebParams* c, const double* pose, const TebObstacle* o, double t) {
+static double footprint_dist_t(const TebParams* c, const double* pose, const TebObstacle* o, const double* pool, double t) {
+  if (generic_pair(c, o)) return generic_distance(c, pose, o, pool, t, NULL);
   switch (c->footprint_type) {
     case TEB_FOOTPRINT_CIRCULAR: return obst_dist_t(o, pose[0], pose[1], t) - c->footprint_radius;
     case TEB_FOOTPRINT_TWO_CIRCLES: {
@@ -190,7 +335,7 @@ static double footprint_dist_t(const TebParams* c, const double* pose, const Teb
 /* EdgeObstacle::computeError g2o_types/edge_obstacle.h:85-106 */
 static void ce_obstacle(Edge* e, Graph* g) {
   const TebParams* c = g->cfg;
-  double dist = footprint_dist(c, P(g, e->vidx[0]), e->ob);
+  double dist = footprint_dist(c, P(g, e->vidx[0]), e->ob, g->pverts);
   e->err[0] = teb_oracle_penalty_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
   if (c->obstacle_cost_exponent != 1.0 && c->min_obstacle_dist > 0.0)
     e->err[0] = c->min_obstacle_dist * pow(e->err[0] / c->min_obstacle_dist, c->obstacle_cost_exponent);
@@ -198,7 +343,7 @@ static void ce_obstacle(Edge* e, Graph* g) {
 /* EdgeInflatedObstacle::computeError edge_obstacle.h:207-233 */
 static void ce_inflated(Edge* e, Graph* g) {
   const TebParams* c = g->cfg;
-  double dist = footprint_dist(c, P(g, e->vidx[0]), e->ob);
+  double dist = footprint_dist(c, P(g, e->vidx[0]), e->ob, g->pverts);
   e->err[0] = teb_oracle_penalty_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
   if (c->obstacle_cost_exponent != 1.0 && c->min_obstacle_dist > 0.0)
     e->err[0] = c->min_obstacle_dist * pow(e->err[0] / c->min_obstacle_dist, c->obstacle_cost_exponent);
@@ -207,7 +352,7 @@ static void ce_inflated(Edge* e, Graph* g) {
 /* EdgeDynamicObstacle::computeError edge_dynamic_obstacle.h:93-104 */
 static void ce_dynamic(Edge* e, Graph* g) {
   const TebParams* c = g->cfg;
-  double dist = footprint_dist_t(c, P(g, e->vidx[0]), e->ob, e->t);
+  double dist = footprint_dist_t(c, P(g, e->vidx[0]), e->ob, g->pverts, e->t);
   e->err[0] = teb_oracle_penalty_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
   e->err[1] = teb_oracle_penalty_below(dist, c->dynamic_obstacle_inflation_dist, 0.0);
 }
@@ -282,7 +427,7 @@ static void ce_vel_obst_ratio(Edge* e, Graph* g) {
   const TebParams* c = g->cfg;
   double vel, omega;
   seg_vel(c, P(g, e->vidx[0]), P(g, e->vidx[1]), DT(g, e->vidx[2]), &vel, &omega);
-  double dist_to_obstacle = footprint_dist(c, P(g, e->vidx[0]), e->ob);
+  double dist_to_obstacle = footprint_dist(c, P(g, e->vidx[0]), e->ob, g->pverts);
   double ratio;
   if (dist_to_obstacle < c->obstacle_proximity_lower_bound) ratio = 0;
   else if (dist_to_obstacle > c->obstacle_proximity_upper_bound) ratio = 1;
@@ -559,7 +704,8 @@ static void linearize_analytic(Edge* e, Graph* g) {
       double dist, gr[3];
       double ox = e->ob->x, oy = e->ob->y;
       if (e->type == E_DYN) { ox += e->t * e->ob->vx; oy += e->t * e->ob->vy; }
-      footprint_grad(c, P(g, e->vidx[0]), ox, oy, e->ob->radius, &dist, gr);
+      if (generic_pair(c, e->ob)) dist = generic_distance(c, P(g, e->vidx[0]), e->ob, g->pverts, e->type == E_DYN ? e->t : 0.0, gr);
+      else footprint_grad(c, P(g, e->vidx[0]), ox, oy, e->ob->radius, &dist, gr);
       double s0 = d_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
       if (e->type != E_DYN && c->obstacle_cost_exponent != 1.0 && c->min_obstacle_dist > 0.0) {
         double e0 = teb_oracle_penalty_below(dist, c->min_obstacle_dist, c->penalty_epsilon);
@@ -653,7 +799,8 @@ static void linearize_analytic(Edge* e, Graph* g) {
       SegD s;
       seg_derivs(c, P(g, e->vidx[0]), P(g, e->vidx[1]), DT(g, e->vidx[2]), &s);
       double dist, gr[3];
-      footprint_grad(c, P(g, e->vidx[0]), e->ob->x, e->ob->y, e->ob->radius, &dist, gr);
+      if (generic_pair(c, e->ob)) dist = generic_distance(c, P(g, e->vidx[0]), e->ob, g->pverts, 0.0, gr);
+      else footprint_grad(c, P(g, e->vidx[0]), e->ob->x, e->ob->y, e->ob->radius, &dist, gr);
       double ratio, dratio = 0;
       if (dist < c->obstacle_proximity_lower_bound) ratio = 0;
       else if (dist > c->obstacle_proximity_upper_bound) ratio = 1;
@@ -851,7 +998,7 @@ static void add_edges_obstacles(Graph* g, double weight_multiplier) {
     for (int m = 0; m < g->M; ++m) {
       const TebObstacle* ob = &g->obst[m];
       if (c->include_dynamic_obstacles && ob->dynamic) continue;
-      double dist = footprint_dist(c, p, ob);
+      double dist = footprint_dist(c, p, ob, g->pverts);
       if (dist < c->min_obstacle_dist * c->obstacle_association_force_inclusion_factor) {
         list[cnt++] = m;
         continue;
@@ -904,6 +1051,37 @@ static void add_obstacle_edge(Graph* g, int i, int m, int inflated, double weigh
   e->ob = &g->obst[m];
 }
 static int find_closest_pose(Graph* g, const double* pt, int begin_idx);
+/* TimedElasticBand::findClosestTrajectoryPose(const Obstacle&) timed_elastic_band.cpp:532-547: Point -> position,
+ * Line -> segment (:480-500), Polygon -> vertex list (:502-530), everything else (Circular, Pill) -> centroid */
+static int find_closest_pose_obstacle(Graph* g, const TebObstacle* ob) {
+  const double* v = g->pverts ? g->pverts + 2 * (size_t)ob->vertex_begin : NULL;
+  int k = ob->vertex_count;
+  if (ob->type == TEB_OBST_POLYGON && k == 0) return 0;
+  if (ob->type == TEB_OBST_POLYGON && k == 1) return find_closest_pose(g, v, 0);
+  if (ob->type == TEB_OBST_LINE || (ob->type == TEB_OBST_POLYGON && k >= 2)) {
+    double min_dist = DBL_MAX;
+    int min_idx = -1;
+    for (int i = 0; i < g->n; i++) {
+      const double* pt = P(g, i);
+      double q[2], d;
+      if (ob->type == TEB_OBST_LINE || k == 2) {
+        closest_on_segment(pt, v, v + 2 * (k - 1), q);
+        d = pt_dist(pt, q);
+      } else {
+        d = DBL_MAX;
+        for (int j = 0; j < k; ++j) {
+          closest_on_segment(pt, v + 2 * j, v + 2 * ((j + 1) % k), q);
+          double dj = pt_dist(pt, q);
+          if (dj < d) d = dj;
+        }
+      }
+      if (d < min_dist) { min_dist = d; min_idx = i; }
+    }
+    return min_idx;
+  }
+  double pt[2] = {ob->x, ob->y};
+  return find_closest_pose(g, pt, 0);
+}
 static void add_edges_obstacles_legacy(Graph* g, double weight_multiplier) {
   const TebParams* c = g->cfg;
   if (c->weight_obstacle == 0 || weight_multiplier == 0 || g->obst == NULL) return;
@@ -913,7 +1091,7 @@ static void add_edges_obstacles_legacy(Graph* g, double weight_multiplier) {
     if (c->include_dynamic_obstacles && ob->dynamic) continue;
     int index;
     if (c->obstacle_poses_affected >= g->n) index = g->n / 2;
-    else { double pt[2] = {ob->x, ob->y}; index = find_closest_pose(g, pt, 0); }
+    else index = find_closest_pose_obstacle(g, ob);
     if ((index <= 1) || (index > g->n - 2)) continue;
     add_obstacle_edge(g, index, m, inflated, weight_multiplier);
     for (int nb = 0; nb < (int)floor(c->obstacle_poses_affected / 2); nb++) {
@@ -1512,7 +1690,7 @@ int32_t teb_oracle_optimize(const TebParams* cfg, double* rec, int32_t* n_io, in
                             const TebObstacle* obst, int32_t M, const double* via, int32_t V,
                             const double* vel_start4, const double* vel_goal4, int32_t prefer_rotdir,
                             const TebOptimizeArgs* args, const OracleOptions* opt,
-                            double* cost_out, OracleStats* stats) {
+                            double* cost_out, OracleStats* stats, const double* obst_vertices) {
   OracleStats st;
   memset(&st, 0, sizeof(st));
   OracleOptions o = {ORACLE_JAC_G2O, ORACLE_SOLVER_BANDED, 0, 0};
@@ -1522,7 +1700,7 @@ int32_t teb_oracle_optimize(const TebParams* cfg, double* rec, int32_t* n_io, in
   {
     Graph g;
     memset(&g, 0, sizeof(g));
-    g.cfg = cfg; g.rec = rec; g.n = *n_io; g.obst = obst; g.M = M; g.via = via; g.V = V;
+    g.cfg = cfg; g.rec = rec; g.n = *n_io; g.obst = obst; g.M = M; g.via = via; g.V = V; g.pverts = obst_vertices;
     memcpy(g.vel_start, vel_start4, sizeof(double) * 4);
     memcpy(g.vel_goal, vel_goal4, sizeof(double) * 4);
     g.rotdir = prefer_rotdir;
@@ -1559,16 +1737,26 @@ done:
   return rc;
 }
 
+double teb_oracle_distance(const TebParams* cfg, const double* pose3, const TebObstacle* obst, const double* obst_vertices,
+                           double t, double* grad3) {
+  if (!generic_pair(cfg, obst)) {
+    double d;
+    if (grad3) footprint_grad(cfg, pose3, obst->x + t * obst->vx, obst->y + t * obst->vy, obst->radius, &d, grad3);
+    return t == 0 ? footprint_dist(cfg, pose3, obst, obst_vertices) : footprint_dist_t(cfg, pose3, obst, obst_vertices, t);
+  }
+  return generic_distance(cfg, pose3, obst, obst_vertices, t, grad3);
+}
+
 int32_t teb_oracle_build_system(const TebParams* cfg, const double* rec_in, int32_t n,
                                 const TebObstacle* obst, int32_t M, const double* via, int32_t V,
                                 const double* vel_start4, const double* vel_goal4, int32_t prefer_rotdir,
                                 double weight_multiplier, int32_t jac_mode,
-                                double* H_dense, double* b, double* chi2) {
+                                double* H_dense, double* b, double* chi2, const double* obst_vertices) {
   Graph g;
   memset(&g, 0, sizeof(g));
   double* rec = (double*)malloc(sizeof(double) * 4 * (size_t)n);
   memcpy(rec, rec_in, sizeof(double) * 4 * (size_t)n);
-  g.cfg = cfg; g.rec = rec; g.n = n; g.obst = obst; g.M = M; g.via = via; g.V = V;
+  g.cfg = cfg; g.rec = rec; g.n = n; g.obst = obst; g.M = M; g.via = via; g.V = V; g.pverts = obst_vertices;
   memcpy(g.vel_start, vel_start4, sizeof(double) * 4);
   memcpy(g.vel_goal, vel_goal4, sizeof(double) * 4);
   g.rotdir = prefer_rotdir;
@@ -1619,7 +1807,8 @@ static void* batch_worker(void* p) {
                                  bt->via_count ? bt->via_count[bidx] : 0,
                                  bt->vel_start ? bt->vel_start + 4 * bidx : zero4,
                                  bt->vel_goal ? bt->vel_goal + 4 * bidx : zero4,
-                                 bt->prefer_rotdir ? bt->prefer_rotdir[bidx] : 0, job->args, job->opt, &cost, &st);
+                                 bt->prefer_rotdir ? bt->prefer_rotdir[bidx] : 0, job->args, job->opt, &cost, &st,
+                                 (bt->obst_vertices && bt->PV_cap > 0) ? bt->obst_vertices + (size_t)s * bt->PV_cap * 2 : NULL);
     bt->n[bidx] = nb;
     if (bt->cost) bt->cost[bidx] = cost;
     if (bt->chi2) bt->chi2[bidx] = st.chi2_final;

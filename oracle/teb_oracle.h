@@ -49,7 +49,7 @@ int32_t teb_oracle_optimize(const TebParams* cfg, double* rec, int32_t* n, int32
                             const TebObstacle* obst, int32_t M, const double* via, int32_t V,
                             const double* vel_start4, const double* vel_goal4, int32_t prefer_rotdir,
                             const TebOptimizeArgs* args, const OracleOptions* opt,
-                            double* cost_out, OracleStats* stats);
+                            double* cost_out, OracleStats* stats, const double* obst_vertices /* [PV][2] or NULL */);
 
 /* Whole batch with the TebBatch layout; `threads` host threads, one band at a time per thread
  * (the reference's optimizeAllTEBs model, homotopy_class_planner.cpp:466-493). */
@@ -63,7 +63,7 @@ int32_t teb_oracle_build_system(const TebParams* cfg, const double* rec, int32_t
                                 const TebObstacle* obst, int32_t M, const double* via, int32_t V,
                                 const double* vel_start4, const double* vel_goal4, int32_t prefer_rotdir,
                                 double weight_multiplier, int32_t jac_mode,
-                                double* H_dense, double* b, double* chi2);
+                                double* H_dense, double* b, double* chi2, const double* obst_vertices /* or NULL */);
 
 /* TimedElasticBand::autoResize (timed_elastic_band.cpp:227-286). Returns new n. */
 int32_t teb_oracle_auto_resize(double* rec, int32_t n, int32_t n_cap, double dt_ref, double dt_hysteresis,
@@ -73,6 +73,11 @@ int32_t teb_oracle_auto_resize(double* rec, int32_t n, int32_t n_cap, double dt_
  * (timed_elastic_band.cpp:325-387). Returns n. */
 int32_t teb_oracle_init_trajectory(const double* start3, const double* goal3, double diststep, double max_vel_x,
                                    int32_t min_samples, int32_t guess_backwards_motion, double* rec, int32_t n_cap);
+
+/* BaseRobotFootprintModel::calculateDistance (t = 0) / estimateSpatioTemporalDistance of the configured footprint to
+ * one obstacle, every footprint x obstacle combination; grad3 (optional) = d dist / d(x, y, theta) in closed form. */
+double teb_oracle_distance(const TebParams* cfg, const double* pose3, const TebObstacle* obst, const double* obst_vertices,
+                           double t, double* grad3);
 
 /* helpers exposed for unit tests */
 double teb_oracle_normalize_theta(double t);

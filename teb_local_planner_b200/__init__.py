@@ -80,9 +80,9 @@ class TebGpuError(RuntimeError):
 class TebGpu:
     """One tebgpu context (one device, one stream, its workspaces)."""
 
-    def __init__(self, max_bands, max_poses, max_scenes=1, max_obstacles=64, max_viapoints=0, device=0):
+    def __init__(self, max_bands, max_poses, max_scenes=1, max_obstacles=64, max_viapoints=0, device=0, max_obst_vertices=0):
         self.lib = load_library()
-        lim = abi.TebGpuLimits(max_bands, max_poses, max_scenes, max_obstacles, max_viapoints, 0)
+        lim = abi.TebGpuLimits(max_bands, max_poses, max_scenes, max_obstacles, max_viapoints, max_obst_vertices)
         self.ctx = C.c_void_p()
         rc = self.lib.tebgpu_create(C.byref(lim), device, C.byref(self.ctx))
         if rc != 0:

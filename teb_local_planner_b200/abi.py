@@ -21,9 +21,11 @@ TEB_STATUS_NONFINITE = 8
 TEB_STATUS_TERMINATED = 16
 TEB_STATUS_DISABLED = 32
 TEB_STATUS_CAPACITY = 64
+TEB_STATUS_BAD_INPUT = 128
 
-TEB_FOOTPRINT_POINT, TEB_FOOTPRINT_CIRCULAR, TEB_FOOTPRINT_TWO_CIRCLES = 0, 1, 2
-TEB_OBST_POINT, TEB_OBST_CIRCULAR = 0, 1
+TEB_FOOTPRINT_POINT, TEB_FOOTPRINT_CIRCULAR, TEB_FOOTPRINT_TWO_CIRCLES, TEB_FOOTPRINT_LINE, TEB_FOOTPRINT_POLYGON = range(5)
+TEB_OBST_POINT, TEB_OBST_CIRCULAR, TEB_OBST_LINE, TEB_OBST_PILL, TEB_OBST_POLYGON = range(5)
+TEB_MAX_FOOTPRINT_VERTICES = 16
 TEB_ROTDIR_NONE, TEB_ROTDIR_LEFT, TEB_ROTDIR_RIGHT = 0, 1, 2
 
 _d, _i = C.c_double, C.c_int32
@@ -44,7 +46,8 @@ class TebParams(C.Structure):
         # footprint
         ("footprint_radius", _d), ("footprint_front_offset", _d), ("footprint_front_radius", _d),
         ("footprint_rear_offset", _d), ("footprint_rear_radius", _d),
-        ("footprint_type", _i), ("_pad1", _i),
+        ("footprint_type", _i), ("footprint_vertex_count", _i),
+        ("footprint_line", _d * 4), ("footprint_vertices", _d * (2 * 16)),
         # obstacles
         ("min_obstacle_dist", _d), ("inflation_dist", _d), ("dynamic_obstacle_inflation_dist", _d),
         ("obstacle_association_force_inclusion_factor", _d), ("obstacle_association_cutoff_factor", _d),
@@ -74,19 +77,20 @@ class TebParams(C.Structure):
 
 
 class TebObstacle(C.Structure):
-    _fields_ = [("x", _d), ("y", _d), ("vx", _d), ("vy", _d), ("radius", _d), ("dynamic", _i), ("type", _i)]
+    _fields_ = [("x", _d), ("y", _d), ("vx", _d), ("vy", _d), ("radius", _d), ("dynamic", _i), ("type", _i),
+                ("vertex_begin", _i), ("vertex_count", _i), ("_pad", _d)]
 
 
 OBST_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("vx", "f8"), ("vy", "f8"), ("radius", "f8"),
-                       ("dynamic", "i4"), ("type", "i4")])
-assert OBST_DTYPE.itemsize == C.sizeof(TebObstacle) == 48
+                       ("dynamic", "i4"), ("type", "i4"), ("vertex_begin", "i4"), ("vertex_count", "i4"), ("_pad", "f8")])
+assert OBST_DTYPE.itemsize == C.sizeof(TebObstacle) == 64
 
 
 class TebBatch(C.Structure):
     _fields_ = [
-        ("B", _i), ("n_cap", _i), ("S", _i), ("M_cap", _i), ("V_cap", _i), ("_pad", _i),
+        ("B", _i), ("n_cap", _i), ("S", _i), ("M_cap", _i), ("V_cap", _i), ("PV_cap", _i),
         ("poses", C.c_void_p), ("n", C.c_void_p), ("scene_id", C.c_void_p),
-        ("obstacles", C.c_void_p), ("obst_count", C.c_void_p),
+        ("obstacles", C.c_void_p), ("obst_count", C.c_void_p), ("obst_vertices", C.c_void_p),
         ("via", C.c_void_p), ("via_count", C.c_void_p),
         ("vel_start", C.c_void_p), ("vel_goal", C.c_void_p), ("prefer_rotdir", C.c_void_p),
         ("cost", C.c_void_p), ("chi2", C.c_void_p), ("status", C.c_void_p), ("lm_iters", C.c_void_p),
@@ -101,7 +105,7 @@ class TebOptimizeArgs(C.Structure):
 
 class TebGpuLimits(C.Structure):
     _fields_ = [("max_bands", _i), ("max_poses", _i), ("max_scenes", _i), ("max_obstacles", _i),
-                ("max_viapoints", _i), ("_pad", _i)]
+                ("max_viapoints", _i), ("max_obst_vertices", _i)]
 
 
 def default_params() -> TebParams:
@@ -151,7 +155,7 @@ class HostBatch:
     """Owns the numpy arrays behind a host TebBatch (keeps them alive while the struct is in use)."""
 
     def __init__(self, poses, n, obstacles, obst_count, scene_id=None, via=None, via_count=None,
-                 vel_start=None, vel_goal=None, prefer_rotdir=None):
+                 vel_start=None, vel_goal=None, prefer_rotdir=None, obst_vertices=None):
         self.poses = np.ascontiguousarray(poses, dtype=np.float64)
         B, n_cap, four = self.poses.shape
         assert four == 4
@@ -161,6 +165,15 @@ class HostBatch:
             self.obstacles = self.obstacles[None, :]
         S, M_cap = self.obstacles.shape
         self.obst_count = np.ascontiguousarray(obst_count, dtype=np.int32).reshape(S)
+        # vertex pool of the Line / Pill / Polygon obstacles: [S][PV_cap][2]
+        if obst_vertices is None:
+            self.obst_vertices = np.zeros((S, 0, 2), np.float64)
+        else:
+            self.obst_vertices = np.ascontiguousarray(obst_vertices, dtype=np.float64)
+            if self.obst_vertices.ndim == 2:
+                self.obst_vertices = self.obst_vertices[None]
+        assert self.obst_vertices.shape[0] == S and self.obst_vertices.shape[2] == 2
+        self.PV_cap = self.obst_vertices.shape[1]
         self.scene_id = (np.zeros(B, np.int32) if scene_id is None
                          else np.ascontiguousarray(scene_id, dtype=np.int32))
         if via is None:
@@ -187,6 +200,8 @@ class HostBatch:
         b.B, b.n_cap, b.S, b.M_cap, b.V_cap = self.B, self.n_cap, self.S, self.M_cap, self.V_cap
         b.poses, b.n, b.scene_id = ptr(self.poses), ptr(self.n), ptr(self.scene_id)
         b.obstacles, b.obst_count = ptr(self.obstacles), ptr(self.obst_count)
+        b.PV_cap = self.PV_cap
+        b.obst_vertices = ptr(self.obst_vertices) if self.PV_cap > 0 else None
         b.via = ptr(self.via) if self.V_cap > 0 else None
         b.via_count = ptr(self.via_count)
         b.vel_start, b.vel_goal, b.prefer_rotdir = ptr(self.vel_start), ptr(self.vel_goal), ptr(self.prefer_rotdir)
@@ -197,7 +212,8 @@ class HostBatch:
         h = HostBatch(self.poses.copy(), self.n.copy(), self.obstacles.copy(), self.obst_count.copy(),
                       self.scene_id.copy(), self.via.copy() if self.V_cap > 0 else None,
                       self.via_count.copy() if self.V_cap > 0 else None,
-                      self.vel_start.copy(), self.vel_goal.copy(), self.prefer_rotdir.copy())
+                      self.vel_start.copy(), self.vel_goal.copy(), self.prefer_rotdir.copy(),
+                      self.obst_vertices.copy() if self.PV_cap > 0 else None)
         return h
 
 

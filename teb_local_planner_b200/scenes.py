@@ -118,3 +118,66 @@ def make_config_batch(name, requests=1, seed=0, candidates=None, autosize=False)
     n_cap = n if not autosize else min(2 * n, 512)
     hb = make_batch(n, M, cand, requests, seed, inflated, moving, via_pts, n_cap=n_cap)
     return p, hb
+
+
+def polygon_centroid(v):
+    """PolygonObstacle::calcCentroid (reference src/obstacles.cpp:56-119) for non-degenerate polygons."""
+    v = np.asarray(v, float)
+    if len(v) == 1:
+        return v[0].copy()
+    if len(v) == 2:
+        return 0.5 * (v[0] + v[1])
+    w = np.roll(v, -1, axis=0)
+    aux = v[:, 0] * w[:, 1] - w[:, 0] * v[:, 1]
+    A = 0.5 * aux.sum()
+    return ((v + w) * aux[:, None]).sum(0) / (6 * A)
+
+
+def add_shape_obstacles(hb, seed=0, kinds=(abi.TEB_OBST_LINE, abi.TEB_OBST_PILL, abi.TEB_OBST_POLYGON), every=2):
+    """Turn every `every`-th obstacle of each scene into a Line / Pill / Polygon obstacle around its old position
+    (vertices go to the scene's vertex pool, (x, y) becomes getCentroid()). Returns a new HostBatch."""
+    obst = hb.obstacles.copy()
+    pools = []
+    for s in range(hb.S):
+        rng = np.random.default_rng(seed * 7919 + s)
+        pool = []
+        for m in range(0, int(hb.obst_count[s]), every):
+            kind = kinds[(m // every) % len(kinds)]
+            c = np.array([obst[s, m]["x"], obst[s, m]["y"]])
+            if kind == abi.TEB_OBST_POLYGON:
+                nv = int(rng.integers(3, 6))
+                ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+                v = c + np.stack([np.cos(ang), np.sin(ang)], 1) * rng.uniform(0.15, 0.5, (nv, 1))
+            else:
+                a = rng.uniform(0, np.pi)
+                h = rng.uniform(0.2, 0.6)
+                v = np.array([c - h * np.array([np.cos(a), np.sin(a)]), c + h * np.array([np.cos(a), np.sin(a)])])
+            ctr = polygon_centroid(v)
+            obst[s, m]["x"], obst[s, m]["y"] = ctr
+            obst[s, m]["type"] = kind
+            obst[s, m]["radius"] = rng.uniform(0.05, 0.25) if kind == abi.TEB_OBST_PILL else 0.0
+            obst[s, m]["vertex_begin"], obst[s, m]["vertex_count"] = len(pool), len(v)
+            pool.extend(v.tolist())
+        pools.append(pool)
+    pv = max(1, max(len(p) for p in pools))
+    verts = np.zeros((hb.S, pv, 2))
+    for s, pool in enumerate(pools):
+        if pool:
+            verts[s, :len(pool)] = pool
+    return abi.HostBatch(hb.poses.copy(), hb.n.copy(), obst, hb.obst_count.copy(), hb.scene_id.copy(),
+                         hb.via.copy() if hb.V_cap > 0 else None, hb.via_count.copy() if hb.V_cap > 0 else None,
+                         hb.vel_start.copy(), hb.vel_goal.copy(), hb.prefer_rotdir.copy(), verts)
+
+
+def set_line_footprint(p, start=(-0.3, 0.0), end=(0.4, 0.0)):
+    p.footprint_type = abi.TEB_FOOTPRINT_LINE
+    p.footprint_line[0], p.footprint_line[1], p.footprint_line[2], p.footprint_line[3] = start[0], start[1], end[0], end[1]
+    return p
+
+
+def set_polygon_footprint(p, vertices=((-0.25, -0.2), (0.35, -0.2), (0.35, 0.2), (-0.25, 0.2))):
+    p.footprint_type = abi.TEB_FOOTPRINT_POLYGON
+    p.footprint_vertex_count = len(vertices)
+    for k, (x, y) in enumerate(vertices):
+        p.footprint_vertices[2 * k], p.footprint_vertices[2 * k + 1] = x, y
+    return p

@@ -49,13 +49,13 @@ def lib():
         L.teb_oracle_optimize.restype = C.c_int32
         L.teb_oracle_optimize.argtypes = [C.POINTER(abi.TebParams), vp, ip, C.c_int32, vp, C.c_int32, vp, C.c_int32,
                                           vp, vp, C.c_int32, C.POINTER(abi.TebOptimizeArgs), C.POINTER(OracleOptions),
-                                          dp, C.POINTER(OracleStats)]
+                                          dp, C.POINTER(OracleStats), vp]
         L.teb_oracle_optimize_batch.restype = C.c_int32
         L.teb_oracle_optimize_batch.argtypes = [C.POINTER(abi.TebParams), C.POINTER(abi.TebBatch),
                                                 C.POINTER(abi.TebOptimizeArgs), C.POINTER(OracleOptions), C.c_int32]
         L.teb_oracle_build_system.restype = C.c_int32
         L.teb_oracle_build_system.argtypes = [C.POINTER(abi.TebParams), vp, C.c_int32, vp, C.c_int32, vp, C.c_int32,
-                                              vp, vp, C.c_int32, C.c_double, C.c_int32, vp, vp, dp]
+                                              vp, vp, C.c_int32, C.c_double, C.c_int32, vp, vp, dp, vp]
         L.teb_oracle_auto_resize.restype = C.c_int32
         L.teb_oracle_auto_resize.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32]
         L.teb_oracle_init_trajectory.restype = C.c_int32
@@ -75,8 +75,29 @@ def lib():
     return _lib
 
 
+def _verts(obst_vertices):
+    if obst_vertices is None or len(obst_vertices) == 0:
+        return None, None
+    v = np.ascontiguousarray(obst_vertices, dtype=np.float64).reshape(-1, 2)
+    return v, v.ctypes.data
+
+
+def distance(params, pose, obstacle, obst_vertices=None, t=0.0, want_grad=False):
+    """calculateDistance / estimateSpatioTemporalDistance of the configured footprint to one obstacle row"""
+    L = lib()
+    L.teb_oracle_distance.restype = C.c_double
+    L.teb_oracle_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    pose = np.ascontiguousarray(pose, dtype=np.float64)
+    ob = np.ascontiguousarray(obstacle, dtype=abi.OBST_DTYPE).reshape(1)
+    v, vptr = _verts(obst_vertices)
+    g = np.zeros(3)
+    d = L.teb_oracle_distance(C.addressof(params), pose.ctypes.data, ob.ctypes.data, vptr, float(t),
+                              g.ctypes.data if want_grad else None)
+    return (d, g) if want_grad else d
+
+
 def optimize_band(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=None, rotdir=0,
-                  args=None, jac_mode=JAC_G2O, solver=SOLVER_BANDED, n_cap=None):
+                  args=None, jac_mode=JAC_G2O, solver=SOLVER_BANDED, n_cap=None, obst_vertices=None):
     """One optimizeTEB on one band. Returns (rec[n_new], cost, stats)."""
     L = lib()
     n_cap = rec.shape[0] if n_cap is None else n_cap
@@ -94,7 +115,7 @@ def optimize_band(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=
     rc = L.teb_oracle_optimize(C.byref(params), buf.ctypes.data, C.byref(nn), n_cap,
                                obstacles.ctypes.data if len(obstacles) else None, len(obstacles),
                                via.ctypes.data if len(via) else None, len(via), vs.ctypes.data, vg.ctypes.data,
-                               rotdir, C.byref(args), C.byref(opt), C.byref(cost), C.byref(st))
+                               rotdir, C.byref(args), C.byref(opt), C.byref(cost), C.byref(st), _verts(obst_vertices)[1])
     if rc != 0:
         raise RuntimeError(f"teb_oracle_optimize rc={rc}")
     return buf[:nn.value].copy(), cost.value, st
@@ -112,7 +133,7 @@ def optimize_batch(params, hb, args, jac_mode=JAC_G2O, solver=SOLVER_BANDED, thr
 
 
 def build_system(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=None, rotdir=0,
-                 weight_multiplier=1.0, jac_mode=JAC_G2O):
+                 weight_multiplier=1.0, jac_mode=JAC_G2O, obst_vertices=None):
     """Dense (H, b, chi2) of one band in g2o order (N = 4n-7)."""
     L = lib()
     N = 4 * n - 7
@@ -127,7 +148,8 @@ def build_system(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=N
     rc = L.teb_oracle_build_system(C.byref(params), rec.ctypes.data, n,
                                    obstacles.ctypes.data if len(obstacles) else None, len(obstacles),
                                    via.ctypes.data if len(via) else None, len(via), vs.ctypes.data, vg.ctypes.data,
-                                   rotdir, weight_multiplier, jac_mode, H.ctypes.data, b.ctypes.data, C.byref(chi2))
+                                   rotdir, weight_multiplier, jac_mode, H.ctypes.data, b.ctypes.data, C.byref(chi2),
+                                   _verts(obst_vertices)[1])
     if rc < 0:
         raise RuntimeError(f"teb_oracle_build_system rc={rc}")
     return H, b, chi2.value

@@ -213,3 +213,183 @@ def test_golden_fixtures_pin_oracle(oracle):
         for b in range(hb.B):
             assert np.abs(hb.poses[b, :hb.n[b]] - g[f"{name}_poses"][b, :hb.n[b]]).max() < 1e-9
         assert np.allclose(hb.cost, g[f"{name}_cost"], rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Line / Pill / Polygon obstacles and Line / Polygon footprints (distance_calculations.h, obstacles.h:597-1045,
+# robot_footprint_model.h:439-760)
+def _ob(type_, x=0.0, y=0.0, radius=0.0, vx=0.0, vy=0.0, begin=0, count=0, dynamic=0):
+    o = np.zeros(1, abi.OBST_DTYPE)
+    o["x"], o["y"], o["vx"], o["vy"], o["radius"] = x, y, vx, vy, radius
+    o["type"], o["dynamic"], o["vertex_begin"], o["vertex_count"] = type_, dynamic, begin, count
+    return o
+
+
+def _footprint(kind, line=None, poly=None):
+    p = abi.default_params()
+    p.footprint_type = kind
+    if line is not None:
+        for k, v in enumerate(line):
+            p.footprint_line[k] = v
+    if poly is not None:
+        p.footprint_vertex_count = len(poly)
+        for k, (x, y) in enumerate(poly):
+            p.footprint_vertices[2 * k], p.footprint_vertices[2 * k + 1] = x, y
+    return p
+
+
+def test_shape_distances_known_answers(oracle):
+    pt = _footprint(abi.TEB_FOOTPRINT_POINT)
+    line_v = [[1, -1], [1, 1]]
+    d, g = oracle.distance(pt, [0, 0, 0.3], _ob(abi.TEB_OBST_LINE, 1, 0, count=2), line_v, want_grad=True)
+    assert d == 1.0 and np.allclose(g, [-1, 0, 0])
+    assert oracle.distance(pt, [0, 0, 0], _ob(abi.TEB_OBST_PILL, 1, 0, radius=0.2, count=2), line_v) == 0.8
+    assert abs(oracle.distance(pt, [0, 3, 0], _ob(abi.TEB_OBST_LINE, 1, 0, count=2), line_v) - np.hypot(1, 2)) < 1e-15
+    sq = [[1, -1], [3, -1], [3, 1], [1, 1]]
+    assert oracle.distance(pt, [0, 0, 0], _ob(abi.TEB_OBST_POLYGON, 2, 0, count=4), sq) == 1.0
+    # inside a polygon the reference still returns the distance to the nearest edge (no interior test,
+    # distance_calculations.h:172-199)
+    assert oracle.distance(pt, [2, 0.5, 0], _ob(abi.TEB_OBST_POLYGON, 2, 0, count=4), sq) == 0.5
+    # vertex pool offset, 1-vertex and 2-vertex polygons (point / line case)
+    pool = [[9, 9], [9, 9], [1, -1], [1, 1], [4, 0]]
+    assert oracle.distance(pt, [0, 0, 0], _ob(abi.TEB_OBST_POLYGON, 1, 0, begin=2, count=2), pool) == 1.0
+    assert oracle.distance(pt, [0, 0, 0], _ob(abi.TEB_OBST_POLYGON, 4, 0, begin=4, count=1), pool) == 4.0
+    # constant-velocity prediction shifts every vertex (obstacles.h:676-696, predictVertices :994)
+    assert oracle.distance(pt, [0, 0, 0], _ob(abi.TEB_OBST_LINE, 1, 0, vx=1.0, count=2, dynamic=1), line_v, t=2.0) == 3.0
+    # circular footprint subtracts its radius
+    cf = _footprint(abi.TEB_FOOTPRINT_CIRCULAR)
+    cf.footprint_radius = 0.25
+    assert oracle.distance(cf, [0, 0, 0], _ob(abi.TEB_OBST_PILL, 1, 0, radius=0.25, count=2), line_v) == 0.5
+    # line footprint (-0.5,0)-(0.5,0) turned by 90 degrees
+    lf = _footprint(abi.TEB_FOOTPRINT_LINE, line=[-0.5, 0, 0.5, 0])
+    pose = [0, 0, np.pi / 2]
+    assert abs(oracle.distance(lf, pose, _ob(abi.TEB_OBST_POINT, 1, 0.2)) - 1.0) < 1e-15
+    assert abs(oracle.distance(lf, pose, _ob(abi.TEB_OBST_CIRCULAR, 1, 0.2, radius=0.3)) - 0.7) < 1e-15
+    assert abs(oracle.distance(lf, pose, _ob(abi.TEB_OBST_POINT, 0, 2.0)) - 1.5) < 1e-15          # beyond the end point
+    d, g = oracle.distance(lf, pose, _ob(abi.TEB_OBST_LINE, 0, 0, count=2), [[-1, 0.1], [1, 0.1]], want_grad=True)
+    assert d == 0.0 and np.all(g == 0)                                                              # crossing segments
+    assert abs(oracle.distance(lf, pose, _ob(abi.TEB_OBST_LINE, 0, 0, count=2), [[1, -3], [1, 3]]) - 1.0) < 1e-15
+    # polygon footprint: unit square turned by 45 degrees, corner towards the obstacle
+    pf = _footprint(abi.TEB_FOOTPRINT_POLYGON, poly=[(-0.5, -0.5), (0.5, -0.5), (0.5, 0.5), (-0.5, 0.5)])
+    d, g = oracle.distance(pf, [0, 0, np.pi / 4], _ob(abi.TEB_OBST_POINT, 2, 0), want_grad=True)
+    assert abs(d - (2 - np.sqrt(0.5))) < 1e-15 and np.allclose(g, [-1, 0, 0], atol=1e-15)
+    assert abs(oracle.distance(pf, [0, 0, 0], _ob(abi.TEB_OBST_POLYGON, 2, 0, count=4), sq) - 0.5) < 1e-15
+    assert oracle.distance(pf, [0.8, 0, 0], _ob(abi.TEB_OBST_POLYGON, 2, 0, count=4), sq) == 0.0    # overlapping polygons
+    # two-circles footprint against a line obstacle: min over the two circles
+    tc = _footprint(abi.TEB_FOOTPRINT_TWO_CIRCLES)
+    tc.footprint_front_offset, tc.footprint_front_radius, tc.footprint_rear_offset, tc.footprint_rear_radius = 0.4, 0.1, 0.3, 0.2
+    assert abs(oracle.distance(tc, [0, 0, 0], _ob(abi.TEB_OBST_LINE, 1, 0, count=2), line_v) - 0.5) < 1e-15
+
+
+def _seg_seg_ericson(p1, q1, p2, q2):
+    """independent closest distance of two segments (clamped quadratic minimisation), not the reference's scheme"""
+    d1, d2, r = q1 - p1, q2 - p2, p1 - p2
+    a, e, f = d1 @ d1, d2 @ d2, d2 @ r
+    if a <= 1e-300 and e <= 1e-300:
+        return np.linalg.norm(r)
+    if a <= 1e-300:
+        s, t = 0.0, np.clip(f / e, 0, 1)
+    else:
+        c = d1 @ r
+        if e <= 1e-300:
+            t, s = 0.0, np.clip(-c / a, 0, 1)
+        else:
+            b = d1 @ d2
+            den = a * e - b * b
+            s = np.clip((b * f - c * e) / den, 0, 1) if den > 1e-300 else 0.0
+            t = (b * s + f) / e
+            if t < 0:
+                t, s = 0.0, np.clip(-c / a, 0, 1)
+            elif t > 1:
+                t, s = 1.0, np.clip((b - c) / a, 0, 1)
+    return np.linalg.norm((p1 + d1 * s) - (p2 + d2 * t))
+
+
+def _edges(v):
+    v = np.asarray(v, float)
+    if len(v) == 1:
+        return [(v[0], v[0])]
+    if len(v) == 2:
+        return [(v[0], v[1])]
+    return [(v[i], v[(i + 1) % len(v)]) for i in range(len(v))]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_shape_distances_second_opinion_and_gradients(oracle, seed):
+    """every footprint x obstacle pair: value against an independent segment-segment routine, closed-form gradient
+    against central differences (skipping the kinks, where forward and backward differences disagree)"""
+    rng = np.random.default_rng(seed)
+    fps = [(_footprint(abi.TEB_FOOTPRINT_POINT), [(0, 0)], 0.0),
+           (_footprint(abi.TEB_FOOTPRINT_LINE, line=[-0.4, 0.1, 0.6, -0.05]), [(-0.4, 0.1), (0.6, -0.05)], 0.0),
+           (_footprint(abi.TEB_FOOTPRINT_POLYGON, poly=[(-0.3, -0.25), (0.5, -0.2), (0.45, 0.3), (-0.35, 0.2)]),
+            [(-0.3, -0.25), (0.5, -0.2), (0.45, 0.3), (-0.35, 0.2)], 0.0)]
+    c = _footprint(abi.TEB_FOOTPRINT_CIRCULAR)
+    c.footprint_radius = 0.2
+    fps.append((c, [(0, 0)], 0.2))
+    checked = 0
+    for p, local, rrad in fps:
+        for otype in (abi.TEB_OBST_POINT, abi.TEB_OBST_CIRCULAR, abi.TEB_OBST_LINE, abi.TEB_OBST_PILL, abi.TEB_OBST_POLYGON):
+            for _ in range(12):
+                pose = np.array([rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(-np.pi, np.pi)])
+                ctr = rng.uniform(-2.5, 2.5, 2)
+                nv = {abi.TEB_OBST_LINE: 2, abi.TEB_OBST_PILL: 2, abi.TEB_OBST_POLYGON: int(rng.integers(3, 7))}.get(otype, 0)
+                ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+                verts = ctr + np.stack([np.cos(ang), np.sin(ang)], 1) * rng.uniform(0.3, 1.0, (nv, 1)) if nv else np.zeros((0, 2))
+                orad = rng.uniform(0.05, 0.3) if otype in (abi.TEB_OBST_CIRCULAR, abi.TEB_OBST_PILL) else 0.0
+                vel = rng.uniform(-0.3, 0.3, 2)
+                t = float(rng.uniform(0, 3)) if rng.random() < 0.5 else 0.0
+                ob = _ob(otype, ctr[0], ctr[1], radius=orad, vx=vel[0], vy=vel[1], count=nv)
+                d, g = oracle.distance(p, pose, ob, verts, t=t, want_grad=True)
+                # second opinion
+                cs, sn = np.cos(pose[2]), np.sin(pose[2])
+                R = np.array([[cs, -sn], [sn, cs]])
+                rw = [pose[:2] + R @ np.array(v, float) for v in local]
+                ow = (verts if nv else ctr[None]) + t * vel
+                best = min(_seg_seg_ericson(a0, a1, b0, b1) for a0, a1 in _edges(rw) for b0, b1 in _edges(ow))
+                # the reference returns 0 for crossing segments and the Ericson routine as well
+                assert abs(d - (best - rrad - orad)) < 1e-12, (p.footprint_type, otype)
+                # gradient
+                h = 1e-6
+                fd = np.zeros(3)
+                smooth = True
+                for k in range(3):
+                    e = np.zeros(3)
+                    e[k] = h
+                    dp, dm = oracle.distance(p, pose + e, ob, verts, t=t), oracle.distance(p, pose - e, ob, verts, t=t)
+                    fd[k] = (dp - dm) / (2 * h)
+                    if abs((dp - d) - (d - dm)) > 1e-9:
+                        smooth = False
+                if smooth:
+                    assert np.abs(fd - g).max() < 1e-6, (p.footprint_type, otype, fd, g)
+                    checked += 1
+    assert checked > 150
+
+
+@pytest.mark.parametrize("footprint", ["point", "line", "polygon", "two_circles"])
+@pytest.mark.parametrize("legacy", [0, 1])
+def test_shape_obstacles_system_jacobians(oracle, footprint, legacy):
+    """buildGraph with Line / Pill / Polygon obstacles (static and moving) and Line / Polygon footprints: closed-form
+    system vs central differences; the association sees the shapes through calculateDistance and getCentroid"""
+    p, hb = scenes.make_config_batch("C4", candidates=2, seed=6)
+    hb = scenes.add_shape_obstacles(hb, seed=1)
+    p.legacy_obstacle_association, p.obstacle_poses_affected = legacy, 8
+    if footprint == "line":
+        scenes.set_line_footprint(p)
+    elif footprint == "polygon":
+        scenes.set_polygon_footprint(p)
+    elif footprint == "two_circles":
+        p.footprint_type = abi.TEB_FOOTPRINT_TWO_CIRCLES
+        p.footprint_front_offset, p.footprint_front_radius, p.footprint_rear_offset, p.footprint_rear_radius = 0.3, 0.15, 0.2, 0.2
+    obst = hb.obstacles[0][:hb.obst_count[0]].copy()
+    obst["dynamic"][::3] = 0           # a mix of static and moving shapes
+    for b in range(hb.B):
+        Hn, bn, c2n = oracle.build_system(p, hb.poses[b], hb.n[b], obst, via=hb.via[b], jac_mode=0, obst_vertices=hb.obst_vertices[0])
+        Ha, ba, c2a = oracle.build_system(p, hb.poses[b], hb.n[b], obst, via=hb.via[b], jac_mode=1, obst_vertices=hb.obst_vertices[0])
+        assert c2n == c2a and c2a > 0
+        assert np.abs(Hn - Ha).max() <= 5e-6 * np.abs(Ha).max()
+        assert np.abs(bn - ba).max() <= 5e-6 * max(np.abs(ba).max(), 1.0)
+    # the shapes matter: the same scene with the vertex obstacles collapsed to points gives another system
+    flat = obst.copy()
+    flat["type"], flat["radius"] = abi.TEB_OBST_POINT, 0.0
+    Hp, _, c2p = oracle.build_system(p, hb.poses[b], hb.n[b], flat, via=hb.via[b], jac_mode=1)
+    assert abs(c2p - c2a) > 1e-6 or np.abs(Hp - Ha).max() > 1e-6
