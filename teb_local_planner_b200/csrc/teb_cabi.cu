@@ -24,6 +24,8 @@ struct tebgpu_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int overlap = 1;                    /* 0: everything on one stream (TEBGPU_OVERLAP=0, profiling, k_vor) */
   int32_t* defer = nullptr;           /* [B] */
+  double* d_fp = nullptr;             /* footprint definition for the vertex-list distance path (FP_DOUBLES) */
+  double* d_pverts = nullptr;         /* [S][max_obst_vertices][2] mirror of TebBatch.obst_vertices */
   TebGpuLimits lim{};
   TebParams params{};
   bool have_params = false;
@@ -150,7 +152,7 @@ const char* tebgpu_last_error_string(const tebgpu_ctx* ctx) { return ctx ? ctx->
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static void free_all(tebgpu_ctx* c) {
-  void* ptrs[] = {c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+  void* ptrs[] = {c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->d_fp, c->d_pverts, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
                   c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
                   c->d_status, c->d_iters};
   for (void* p : ptrs)
@@ -202,8 +204,9 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   {
     size_t ev = eval_smem_bytes((int)nc, (int)M, SPEC_K_MAX);
     if (ev > 232448) ev = 232448; /* wide speculation is only chosen when its staging fits (tebgpu_optimize_batch_device) */
-    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
-    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
     if (const char* e = std::getenv("TEBGPU_EVAL_MINB")) c->eval_minb = std::atoi(e) == 3 ? 3 : 2;
   }
   const size_t spec_sys = ((B * SPEC_K_MAX + 31) / 32) * 32; /* whole warps of (band, trial) systems */
@@ -221,6 +224,9 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaMalloc(&c->d_obst, S * M * sizeof(TebObstacle)));
   CUDA_TRY(c, cudaMalloc(&c->d_ocount, S * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->d_via, B * V * 2 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_fp, FP_DOUBLES * sizeof(double)));
+  CUDA_TRY(c, cudaMemset(c->d_fp, 0, FP_DOUBLES * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_pverts, (S * (size_t)(lim->max_obst_vertices > 0 ? lim->max_obst_vertices : 1)) * 2 * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->d_vcount, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->d_vs, B * 4 * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->d_vg, B * 4 * sizeof(double)));
@@ -238,25 +244,41 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     c->err = "shared-memory footprint exceeds 227 KB for these limits (max_poses / max_obstacles too large)";
     return TEBGPU_ERR_CAPACITY;
   }
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
-  if ((int)nc <= BCR_MAX_POSES && kb_bcr_smem_bytes((int)nc, (int)M) <= 232448)
-    CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
+  if ((int)nc <= BCR_MAX_POSES && kb_bcr_smem_bytes((int)nc, (int)M) <= 232448) {
+    CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kb_bcr_smem_bytes((int)nc, (int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_build_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_g));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kb_bcr_smem_bytes((int)nc, (int)M)));
+  }
+  CUDA_TRY(c, cudaFuncSetAttribute(k_build_graph<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_g));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_build_graph<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_g));
   /* ask for the full shared-memory carveout: occupancy of the tile kernels is shared-memory bound */
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<1, KB_BCR_THREADS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   tebgpu_default_params(&c->params);
   c->have_params = true;
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -279,29 +301,73 @@ int32_t tebgpu_destroy(tebgpu_ctx* ctx) {
 
 int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* p) {
   if (!ctx || !p) return TEBGPU_ERR_INVALID_ARG;
-  /* cost terms without a kernel yet: refuse instead of silently dropping them */
-  if (p->footprint_type < 0 || p->footprint_type > TEB_FOOTPRINT_TWO_CIRCLES) { ctx->err = "unsupported footprint model"; return TEBGPU_ERR_UNSUPPORTED; }
+  if (p->footprint_type < 0 || p->footprint_type > TEB_FOOTPRINT_POLYGON) { ctx->err = "unknown footprint model"; return TEBGPU_ERR_UNSUPPORTED; }
+  if (p->footprint_type == TEB_FOOTPRINT_POLYGON &&
+      (p->footprint_vertex_count < 1 || p->footprint_vertex_count > TEB_MAX_FOOTPRINT_VERTICES)) {
+    ctx->err = "polygon footprint needs 1 .. TEB_MAX_FOOTPRINT_VERTICES vertices";
+    return TEBGPU_ERR_INVALID_ARG;
+  }
+  /* footprint definition for the vertex-list distance path: a small device array, read by generic_distance */
+  double fp[FP_DOUBLES];
+  std::memset(fp, 0, sizeof(fp));
+  fp[FP_RADIUS] = p->footprint_radius;
+  fp[FP_FRONT_OFF] = p->footprint_front_offset; fp[FP_FRONT_RAD] = p->footprint_front_radius;
+  fp[FP_REAR_OFF] = p->footprint_rear_offset; fp[FP_REAR_RAD] = p->footprint_rear_radius;
+  for (int k = 0; k < 4; ++k) fp[FP_LINE + k] = p->footprint_line[k];
+  fp[FP_COUNT] = (double)p->footprint_vertex_count;
+  for (int k = 0; k < 2 * TEB_MAX_FOOTPRINT_VERTICES; ++k) fp[FP_VERTS + k] = p->footprint_vertices[k];
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); /* no optimize call of this context may still read the old copy */
+  CUDA_TRY(ctx, cudaMemcpy(ctx->d_fp, fp, sizeof(fp), cudaMemcpyHostToDevice));
   ctx->params = *p;
   ctx->have_params = true;
   return TEBGPU_OK;
 }
 
+/* Kernel instantiations: HOLO = holonomic rows (vy, acc y); GEOM = vertex-list shapes (Line / Polygon footprint,
+ * Line / Pill / Polygon obstacles) reachable, i.e. the out-of-line generic_distance call is compiled in. The default
+ * diff-drive / car-like + Point / Circular configuration runs <false, false>: no extra rows, no call. */
 static void launch_linearize(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int M_cap, cudaStream_t st) {
-  const bool holo = kp.holo_vel || kp.holo_acc; /* holonomic rows (vy, acc y) compiled into their own instantiation */
+  const bool holo = kp.holo_vel || kp.holo_acc;
+  const bool geom = kp.generic != 0;
   if (ctx->linearize_variant == 1) {
-    const int groups = (db.chunks + KW_WARPS - 1) / KW_WARPS;
-    if (holo) k_linearize_w<true><<<dim3(groups, B), 32 * KW_WARPS, kw_smem_bytes(M_cap), st>>>(db, kp);
-    else k_linearize_w<false><<<dim3(groups, B), 32 * KW_WARPS, kw_smem_bytes(M_cap), st>>>(db, kp);
+    const dim3 grid((db.chunks + KW_WARPS - 1) / KW_WARPS, B);
+    const size_t sm = kw_smem_bytes(M_cap);
+    if (holo && geom) k_linearize_w<true, true><<<grid, 32 * KW_WARPS, sm, st>>>(db, kp);
+    else if (holo) k_linearize_w<true, false><<<grid, 32 * KW_WARPS, sm, st>>>(db, kp);
+    else if (geom) k_linearize_w<false, true><<<grid, 32 * KW_WARPS, sm, st>>>(db, kp);
+    else k_linearize_w<false, false><<<grid, 32 * KW_WARPS, sm, st>>>(db, kp);
   } else {
-    if (holo) k_linearize<true><<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(M_cap), st>>>(db, kp);
-    else k_linearize<false><<<dim3(db.chunks, B), KA_THREADS, ka_smem_bytes(M_cap), st>>>(db, kp);
+    const dim3 grid(db.chunks, B);
+    const size_t sm = ka_smem_bytes(M_cap);
+    if (holo && geom) k_linearize<true, true><<<grid, KA_THREADS, sm, st>>>(db, kp);
+    else if (holo) k_linearize<true, false><<<grid, KA_THREADS, sm, st>>>(db, kp);
+    else if (geom) k_linearize<false, true><<<grid, KA_THREADS, sm, st>>>(db, kp);
+    else k_linearize<false, false><<<grid, KA_THREADS, sm, st>>>(db, kp);
   }
 }
+static void launch_build_graph(const DevBatch& db, const KParams& kp, int B, size_t smem, cudaStream_t st) {
+  if (kp.generic) k_build_graph<true><<<B, 256, smem, st>>>(db, kp);
+  else k_build_graph<false><<<B, 256, smem, st>>>(db, kp);
+}
+static void launch_vor(const DevBatch& db, const KParams& kp, int B, size_t smem, cudaStream_t st) {
+  if (kp.generic) k_vor<true><<<B, 256, smem, st>>>(db, kp);
+  else k_vor<false><<<B, 256, smem, st>>>(db, kp);
+}
+static void launch_trial_eval(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int K, size_t smem, int it,
+                              int round, int g, int tag, cudaStream_t st) {
+  if (kp.generic) k_trial_eval<2, true><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+  else if (ctx->eval_minb == 3) k_trial_eval<3, false><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+  else k_trial_eval<2, false><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+}
 
-static KParams make_kparams(const TebParams& p, double weight_multiplier) {
+static KParams make_kparams(const tebgpu_ctx* ctx, const TebBatch* bt, double weight_multiplier) {
+  const TebParams& p = ctx->params;
   KParams k;
   std::memset(&k, 0, sizeof(k));
   k.p = p;
+  k.generic = p.footprint_type >= TEB_FOOTPRINT_LINE || bt->PV_cap > 0;
+  k.fp_geom = ctx->d_fp;
   k.w_obst = p.weight_obstacle * weight_multiplier;
   k.sw_vel_x = std::sqrt(p.weight_max_vel_x); k.sw_vel_th = std::sqrt(p.weight_max_vel_theta);
   k.sw_acc_x = std::sqrt(p.weight_acc_lim_x); k.sw_acc_th = std::sqrt(p.weight_acc_lim_theta);
@@ -340,6 +406,9 @@ static int32_t check_batch(tebgpu_ctx* ctx, const TebBatch* bt) {
   if (!bt->poses || !bt->n || !bt->scene_id || !bt->obst_count || !bt->vel_start || !bt->vel_goal) { ctx->err = "missing required batch array"; return TEBGPU_ERR_INVALID_ARG; }
   if (bt->M_cap > 0 && !bt->obstacles) { ctx->err = "obstacles == NULL"; return TEBGPU_ERR_INVALID_ARG; }
   if (bt->V_cap > 0 && (!bt->via || !bt->via_count)) { ctx->err = "via == NULL"; return TEBGPU_ERR_INVALID_ARG; }
+  if (bt->PV_cap < 0 || bt->PV_cap > ctx->lim.max_obst_vertices) { ctx->err = "PV_cap exceeds max_obst_vertices"; return TEBGPU_ERR_CAPACITY; }
+  if (bt->PV_cap > 0 && !bt->obst_vertices) { ctx->err = "obst_vertices == NULL"; return TEBGPU_ERR_INVALID_ARG; }
+  if (!ctx->have_params) { ctx->err = "tebgpu_set_params has not been called"; return TEBGPU_ERR_INVALID_ARG; }
   return TEBGPU_OK;
 }
 
@@ -355,6 +424,7 @@ static DevBatch make_devbatch(tebgpu_ctx* ctx, const TebBatch* bt) {
   d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.assoc3 = ctx->assoc3; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts; d.dmax_parts = ctx->dmax_parts; d.rhs = ctx->rhs; d.dyn_idx = ctx->dyn_idx; d.dyn_cnt = ctx->dyn_cnt;
   d.state = ctx->state;
   d.chunks = (bt->n_cap + TP - 1) / TP;
+  d.obst_vertices = bt->PV_cap > 0 ? bt->obst_vertices : nullptr; d.PV_cap = bt->PV_cap;
   d.defer = ctx->defer; d.a_list = nullptr; d.a_cnt = nullptr; d.skip_tag = 0;
   return d;
 }
@@ -396,12 +466,12 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   const bool overlap = ctx->solver == 2 && ctx->overlap && !ctx->profiling;
   int tag = 0; /* running inner-iteration number (1-based) */
   double weight_multiplier = 1.0;
-  KParams kp = make_kparams(p, weight_multiplier);
+  KParams kp = make_kparams(ctx, bt, weight_multiplier);
   prof_begin(ctx, st, 0); k_begin<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st);
   for (int o = 0; o < args->iterations_outerloop; ++o) {
-    kp = make_kparams(p, weight_multiplier);
+    kp = make_kparams(ctx, bt, weight_multiplier);
     if (p.teb_autosize) { prof_begin(ctx, st, 1); k_auto_resize<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st); }
-    prof_begin(ctx, st, 2); k_build_graph<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st);
+    prof_begin(ctx, st, 2); launch_build_graph(db, kp, B, smem_g, st); ++launches; prof_end(ctx, st);
     bool deferred_done = false; /* kernel A of this iteration already ran for the deferred bands (side stream) */
     for (int it = 0; it < args->iterations_innerloop; ++it) {
       ++tag;
@@ -409,7 +479,7 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
         DevBatch da = db;
         if (deferred_done) da.skip_tag = tag - 1; /* bands queued during the previous iteration were linearised on the side stream */
         prof_begin(ctx, st, 3); launch_linearize(ctx, da, kp, B, bt->M_cap, st); ++launches; prof_end(ctx, st);
-        if (kp.has_vor) { prof_begin(ctx, st, 3); k_vor<<<B, 256, smem_g, st>>>(db, kp); ++launches; prof_end(ctx, st); }
+        if (kp.has_vor) { prof_begin(ctx, st, 3); launch_vor(db, kp, B, smem_g, st); ++launches; prof_end(ctx, st); }
         if (deferred_done) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0)); deferred_done = false; }
       }
       if (ctx->solver == 2) {
@@ -428,8 +498,7 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
           }
           prof_begin(ctx, st, round == 0 ? 6 : 4); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, rs>>>(db, ctx->spec, it, round, g); ++launches; prof_end(ctx, st);
           prof_begin(ctx, st, round == 0 ? 7 : 4);
-          if (ctx->eval_minb == 3) k_trial_eval<3><<<B, 32 * K, smem_e, rs>>>(db, kp, ctx->spec, it, round, g, tag);
-          else k_trial_eval<2><<<B, 32 * K, smem_e, rs>>>(db, kp, ctx->spec, it, round, g, tag);
+          launch_trial_eval(ctx, db, kp, B, K, smem_e, it, round, g, tag, rs);
           ++launches; prof_end(ctx, st);
         }
         if (fork) {
@@ -447,8 +516,10 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
         }
       } else {
         prof_begin(ctx, st, 4);
-        if (use_bcr) k_lm_step_t<1, KB_BCR_THREADS><<<B, KB_BCR_THREADS, smem_bcr, st>>>(db, kp, it);
-        else k_lm_step_t<0, KB_THREADS><<<B, KB_THREADS, smem_b, st>>>(db, kp, it);
+        if (use_bcr && kp.generic) k_lm_step_t<1, KB_BCR_THREADS, true><<<B, KB_BCR_THREADS, smem_bcr, st>>>(db, kp, it);
+        else if (use_bcr) k_lm_step_t<1, KB_BCR_THREADS, false><<<B, KB_BCR_THREADS, smem_bcr, st>>>(db, kp, it);
+        else if (kp.generic) k_lm_step_t<0, KB_THREADS, true><<<B, KB_THREADS, smem_b, st>>>(db, kp, it);
+        else k_lm_step_t<0, KB_THREADS, false><<<B, KB_THREADS, smem_b, st>>>(db, kp, it);
         ++launches; prof_end(ctx, st);
       }
     }
@@ -511,6 +582,7 @@ static TebBatch mirror_batch(tebgpu_ctx* ctx, const TebBatch* bt) {
   d.via = bt->V_cap > 0 ? ctx->d_via : nullptr; d.via_count = bt->V_cap > 0 ? ctx->d_vcount : nullptr;
   d.vel_start = ctx->d_vs; d.vel_goal = ctx->d_vg; d.prefer_rotdir = bt->prefer_rotdir ? ctx->d_rot : nullptr;
   d.cost = ctx->d_cost; d.chi2 = ctx->d_chi2; d.status = ctx->d_status; d.lm_iters = ctx->d_iters;
+  d.obst_vertices = bt->PV_cap > 0 ? ctx->d_pverts : nullptr;
   return d;
 }
 
@@ -523,6 +595,22 @@ static int32_t upload_batch(tebgpu_ctx* ctx, const TebBatch* bt) {
   if (bt->M_cap > 0)
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_obst, bt->obstacles, (size_t)bt->S * bt->M_cap * sizeof(TebObstacle), cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ocount, bt->obst_count, (size_t)bt->S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (bt->PV_cap > 0)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pverts, bt->obst_vertices, (size_t)bt->S * bt->PV_cap * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  /* host entry points can check the obstacle table before it is used */
+  for (int sc = 0; sc < bt->S; ++sc)
+    for (int m = 0; m < bt->obst_count[sc] && m < bt->M_cap; ++m) {
+      const TebObstacle& o = bt->obstacles[(size_t)sc * bt->M_cap + m];
+      if (o.type < TEB_OBST_POINT || o.type > TEB_OBST_POLYGON) { ctx->err = "unknown obstacle type"; return TEBGPU_ERR_INVALID_ARG; }
+      if (o.type >= TEB_OBST_LINE) {
+        const int need = o.type == TEB_OBST_POLYGON ? 1 : 2;
+        if (o.vertex_count < need || (o.type != TEB_OBST_POLYGON && o.vertex_count != 2) || o.vertex_begin < 0 ||
+            (long long)o.vertex_begin + o.vertex_count > bt->PV_cap) {
+          ctx->err = "obstacle vertex range outside obst_vertices";
+          return TEBGPU_ERR_INVALID_ARG;
+        }
+      }
+    }
   if (bt->V_cap > 0) {
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_via, bt->via, B * bt->V_cap * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_vcount, bt->via_count, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -565,12 +653,12 @@ int32_t tebgpu_compute_cost(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimi
   TebBatch d = mirror_batch(ctx, bt);
   cudaStream_t st = ctx->stream;
   DevBatch db = make_devbatch(ctx, &d);
-  KParams kp = make_kparams(ctx->params, 1.0); /* buildGraph() default weight_multiplier (optimal_planner.h:536) */
+  KParams kp = make_kparams(ctx, bt, 1.0); /* buildGraph() default weight_multiplier (optimal_planner.h:536) */
   const int B = bt->B, tb = 128, gb = ((B > bt->S ? B : bt->S) + tb - 1) / tb;
   k_begin<<<gb, tb, 0, st>>>(db, kp);
-  k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
+  launch_build_graph(db, kp, B, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st);
   launch_linearize(ctx, db, kp, B, bt->M_cap, st);
-  if (kp.has_vor) k_vor<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
+  if (kp.has_vor) launch_vor(db, kp, B, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st);
   k_cost_only<<<gb, tb, 0, st>>>(db, kp, *args);
   ctx->launches = 4;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -596,12 +684,12 @@ int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* bt, int32_t outer_i
   DevBatch db = make_devbatch(ctx, &d);
   double mult = 1.0;
   for (int o = 0; o < outer_index; ++o) mult *= ctx->params.weight_adapt_factor;
-  KParams kp = make_kparams(ctx->params, mult);
+  KParams kp = make_kparams(ctx, bt, mult);
   const int B = bt->B, tb = 128, gb = ((B > bt->S ? B : bt->S) + tb - 1) / tb;
   k_begin<<<gb, tb, 0, st>>>(db, kp);
-  k_build_graph<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
+  launch_build_graph(db, kp, B, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st);
   launch_linearize(ctx, db, kp, B, bt->M_cap, st);
-  if (kp.has_vor) k_vor<<<B, 256, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st>>>(db, kp);
+  if (kp.has_vor) launch_vor(db, kp, B, (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle), st);
   ctx->launches = 3;
   CUDA_TRY(ctx, cudaGetLastError());
   const size_t per_band = (size_t)4 * bt->n_cap * HROW;

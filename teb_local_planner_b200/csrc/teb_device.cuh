@@ -32,6 +32,9 @@ struct KParams {
   int32_t holo_vel;     /* max_vel_y != 0: EdgeVelocityHolonomic (optimal_planner.cpp:722, :745)        */
   int32_t holo_acc;     /* max_vel_y != 0 && acc_lim_y != 0: EdgeAccelerationHolonomic* (:778, :824)     */
   double sw_vel_y, sw_acc_y;
+  int32_t generic;      /* Line / Polygon footprint or Line / Pill / Polygon obstacles present: vertex-list distance path */
+  int32_t _padg;
+  const double* fp_geom; /* device copy of the footprint definition for that path, see FP_* below */
 };
 
 /* ------------------------------------------------------------------ g2o/stuff/misc.h */
@@ -205,6 +208,165 @@ __device__ __forceinline__ double footprint_distance_only(const KParams& kp, dou
   double d = sqrt(dx * dx + dy * dy) - orad;
   if (kp.p.footprint_type == TEB_FOOTPRINT_CIRCULAR) d -= kp.p.footprint_radius;
   return d;
+}
+
+
+/* ------------------------------------------------------------------ vertex-list shapes (distance_calculations.h)
+ * Line / Polygon footprints (robot_footprint_model.h:439-560, :635-760) and Line / Pill / Polygon obstacles
+ * (obstacles.h:597-1045). A shape is a vertex list: 1 vertex = point, 2 = one segment, k > 2 = closed polygon, i.e. the
+ * edge enumeration of distance_point_to_polygon_2d / distance_segment_to_polygon_2d / distance_polygon_to_polygon_2d
+ * (:172-262). The function returns the distance and its gradient: with the closest points c_r (robot) and c_o
+ * (obstacle), n = (c_r - c_o)/|.|, d d/d(x, y) = n and d d/d theta = n . J (c_r - p); 0 when the shapes intersect.
+ * Kept out of line and only referenced by the GEOM = true kernel instantiations (chosen at launch when kp.generic), so
+ * that the Point / Circular fast path keeps its registers; the footprint definition is read from a small device array instead of the kernel parameters
+ * (taking their address would spill them to local memory). */
+enum { FP_RADIUS = 0, FP_FRONT_OFF = 1, FP_FRONT_RAD = 2, FP_REAR_OFF = 3, FP_REAR_RAD = 4, FP_LINE = 5, FP_COUNT = 9,
+       FP_VERTS = 10, FP_DOUBLES = 10 + 2 * TEB_MAX_FOOTPRINT_VERTICES };
+struct Dist4 { double d, gx, gy, gt; };
+
+/* closest_point_on_line_segment_2d distance_calculations.h:60-75 */
+__device__ __forceinline__ void closest_on_segment(double px, double py, double ax, double ay, double bx, double by,
+                                                   double& qx, double& qy) {
+  const double dx = bx - ax, dy = by - ay;
+  const double sq = dx * dx + dy * dy;
+  if (sq == 0) { qx = ax; qy = ay; return; }
+  const double u = ((px - ax) * dx + (py - ay) * dy) / sq;
+  if (u <= 0) { qx = ax; qy = ay; }
+  else if (u >= 1) { qx = bx; qy = by; }
+  else { qx = ax + u * dx; qy = ay + u * dy; }
+}
+/* check_line_segments_intersection_2d distance_calculations.h:97-127 */
+__device__ __forceinline__ bool segments_intersect(double l1sx, double l1sy, double l1ex, double l1ey, double l2sx,
+                                                   double l2sy, double l2ex, double l2ey) {
+  const double l1x = l1ex - l1sx, l1y = l1ey - l1sy, l2x = l2ex - l2sx, l2y = l2ey - l2sy;
+  const double denom = l1x * l2y - l2x * l1y;
+  if (denom == 0) return false;
+  const bool dp = denom > 0;
+  const double ax = l1sx - l2sx, ay = l1sy - l2sy;
+  const double s_numer = l1x * ay - l1y * ax;
+  if ((s_numer < 0) == dp) return false;
+  const double t_numer = l2x * ay - l2y * ax;
+  if ((t_numer < 0) == dp) return false;
+  if (((s_numer > denom) == dp) || ((t_numer > denom) == dp)) return false;
+  return true;
+}
+/* distance_segment_to_segment_2d distance_calculations.h:139-156; (c1x, c1y) on line 1, (c2x, c2y) on line 2 */
+__device__ __forceinline__ double seg_seg_dist(double l1sx, double l1sy, double l1ex, double l1ey, double l2sx, double l2sy,
+                                               double l2ex, double l2ey, double& c1x, double& c1y, double& c2x, double& c2y) {
+  if (segments_intersect(l1sx, l1sy, l1ex, l1ey, l2sx, l2sy, l2ex, l2ey)) { c1x = c2x = l1sx; c1y = c2y = l1sy; return 0.0; }
+  double qx, qy, best, d;
+  closest_on_segment(l1sx, l1sy, l2sx, l2sy, l2ex, l2ey, qx, qy);
+  best = sqrt((l1sx - qx) * (l1sx - qx) + (l1sy - qy) * (l1sy - qy));
+  c1x = l1sx; c1y = l1sy; c2x = qx; c2y = qy;
+  closest_on_segment(l1ex, l1ey, l2sx, l2sy, l2ex, l2ey, qx, qy);
+  d = sqrt((l1ex - qx) * (l1ex - qx) + (l1ey - qy) * (l1ey - qy));
+  if (d < best) { best = d; c1x = l1ex; c1y = l1ey; c2x = qx; c2y = qy; }
+  closest_on_segment(l2sx, l2sy, l1sx, l1sy, l1ex, l1ey, qx, qy);
+  d = sqrt((l2sx - qx) * (l2sx - qx) + (l2sy - qy) * (l2sy - qy));
+  if (d < best) { best = d; c2x = l2sx; c2y = l2sy; c1x = qx; c1y = qy; }
+  closest_on_segment(l2ex, l2ey, l1sx, l1sy, l1ex, l1ey, qx, qy);
+  d = sqrt((l2ex - qx) * (l2ex - qx) + (l2ey - qy) * (l2ey - qy));
+  if (d < best) { best = d; c2x = l2ex; c2y = l2ey; c1x = qx; c1y = qy; }
+  return best;
+}
+
+__device__ __noinline__ Dist4 generic_distance(int fp_type, const double* __restrict__ fp, const double* __restrict__ pool,
+                                               double px, double py, double c, double s, double ox, double oy,
+                                               double orad_in, int otype, int vbegin, int vcount, double offx, double offy) {
+  /* obstacle shape: vertex list in the pool (+ the constant-velocity offset) or the single point (ox, oy) */
+  const bool olist = otype >= TEB_OBST_LINE && vcount >= 1 && pool != nullptr;
+  const int ok = olist ? vcount : 1;
+  const double* ov = olist ? pool + 2 * (size_t)vbegin : nullptr;
+  const bool obst_first = (otype == TEB_OBST_LINE || otype == TEB_OBST_PILL);
+  const double orad = (otype == TEB_OBST_CIRCULAR || otype == TEB_OBST_PILL) ? orad_in : 0.0;
+  const int oe = ok <= 2 ? 1 : ok;
+  double best = 1.7976931348623157e308, bcrx = px, bcry = py, bcox = px, bcoy = py;
+  const int nsub = (fp_type == TEB_FOOTPRINT_TWO_CIRCLES) ? 2 : 1;
+  for (int sub = 0; sub < nsub; ++sub) {
+    int rk = 1;
+    double rrad = 0;
+    if (fp_type == TEB_FOOTPRINT_CIRCULAR) rrad = fp[FP_RADIUS];
+    else if (fp_type == TEB_FOOTPRINT_TWO_CIRCLES) rrad = sub == 0 ? fp[FP_FRONT_RAD] : fp[FP_REAR_RAD];
+    else if (fp_type == TEB_FOOTPRINT_LINE) rk = 2;
+    else if (fp_type == TEB_FOOTPRINT_POLYGON) rk = (int)fp[FP_COUNT];
+    const int re = rk <= 2 ? 1 : rk;
+    double sbest = 1.7976931348623157e308, scrx = px, scry = py, scox = px, scoy = py;
+    for (int i = 0; i < re; ++i) {
+      /* robot edge i in the world frame (transformToWorld robot_footprint_model.h:604-612, :757-766) */
+      double r0x, r0y, r1x, r1y;
+      if (fp_type == TEB_FOOTPRINT_LINE || fp_type == TEB_FOOTPRINT_POLYGON) {
+        const double* lv = fp + (fp_type == TEB_FOOTPRINT_LINE ? FP_LINE : FP_VERTS);
+        const int i1 = (i + 1) % rk;
+        const double ax = lv[2 * i], ay = lv[2 * i + 1], bx = lv[2 * i1], by = lv[2 * i1 + 1];
+        r0x = px + c * ax - s * ay; r0y = py + s * ax + c * ay;
+        r1x = px + c * bx - s * by; r1y = py + s * bx + c * by;
+      } else {
+        double off = 0;
+        if (fp_type == TEB_FOOTPRINT_TWO_CIRCLES) off = sub == 0 ? fp[FP_FRONT_OFF] : -fp[FP_REAR_OFF];
+        r0x = r1x = px + off * c; r0y = r1y = py + off * s;
+      }
+      for (int j = 0; j < oe; ++j) {
+        double o0x, o0y, o1x, o1y;
+        if (olist) {
+          const int j1 = (j + 1) % ok;
+          o0x = ov[2 * j] + offx; o0y = ov[2 * j + 1] + offy;
+          o1x = ov[2 * j1] + offx; o1y = ov[2 * j1 + 1] + offy;
+        } else { o0x = o1x = ox + offx; o0y = o1y = oy + offy; }
+        double ax, ay, bx, by, d;
+        if (rk == 1 && ok == 1) {
+          ax = r0x; ay = r0y; bx = o0x; by = o0y;
+          d = sqrt((r0x - o0x) * (r0x - o0x) + (r0y - o0y) * (r0y - o0y));
+        } else if (rk == 1) {
+          closest_on_segment(r0x, r0y, o0x, o0y, o1x, o1y, bx, by);
+          ax = r0x; ay = r0y;
+          d = sqrt((r0x - bx) * (r0x - bx) + (r0y - by) * (r0y - by));
+        } else if (ok == 1) {
+          closest_on_segment(o0x, o0y, r0x, r0y, r1x, r1y, ax, ay);
+          bx = o0x; by = o0y;
+          d = sqrt((o0x - ax) * (o0x - ax) + (o0y - ay) * (o0y - ay));
+        } else if (obst_first) {
+          d = seg_seg_dist(o0x, o0y, o1x, o1y, r0x, r0y, r1x, r1y, bx, by, ax, ay);
+        } else {
+          d = seg_seg_dist(r0x, r0y, r1x, r1y, o0x, o0y, o1x, o1y, ax, ay, bx, by);
+        }
+        if (d < sbest) { sbest = d; scrx = ax; scry = ay; scox = bx; scoy = by; }
+      }
+    }
+    const double dsub = sbest - orad - rrad;
+    if (dsub < best) { best = dsub; bcrx = scrx; bcry = scry; bcox = scox; bcoy = scoy; }
+  }
+  Dist4 r;
+  r.d = best;
+  double nx = bcrx - bcox, ny = bcry - bcoy;
+  const double nn = sqrt(nx * nx + ny * ny);
+  if (nn > 0) { nx /= nn; ny /= nn; } else { nx = 0; ny = 0; }
+  r.gx = nx; r.gy = ny;
+  r.gt = -nx * (bcry - py) + ny * (bcrx - px);
+  return r;
+}
+
+/* calculateDistance / estimateSpatioTemporalDistance of the configured footprint to one obstacle row. (ox, oy) is the
+ * position already advanced to time t (fast path), (offx, offy) = t * velocity the same shift for vertex lists. */
+template <bool GEOM>
+__device__ __forceinline__ double robot_obstacle_distance(const KParams& kp, const double* pool, double px, double py,
+                                                          double c, double s, const TebObstacle& ob, double ox, double oy,
+                                                          double offx, double offy, double grad[3]) {
+  if (GEOM) { /* instantiations without vertex-list shapes carry no call at all: the fast path keeps its registers */
+    const Dist4 r = generic_distance(kp.p.footprint_type, kp.fp_geom, pool, px, py, c, s, ob.x, ob.y, ob.radius, ob.type,
+                                     ob.vertex_begin, ob.vertex_count, offx, offy);
+    grad[0] = r.gx; grad[1] = r.gy; grad[2] = r.gt;
+    return r.d;
+  }
+  return footprint_distance(kp, px, py, c, s, ox, oy, ob.radius, grad);
+}
+template <bool GEOM>
+__device__ __forceinline__ double robot_obstacle_distance_only(const KParams& kp, const double* pool, double px, double py,
+                                                               double c, double s, const TebObstacle& ob, double ox,
+                                                               double oy, double offx, double offy) {
+  if (GEOM)
+    return generic_distance(kp.p.footprint_type, kp.fp_geom, pool, px, py, c, s, ob.x, ob.y, ob.radius, ob.type,
+                            ob.vertex_begin, ob.vertex_count, offx, offy).d;
+  return footprint_distance_only(kp, px, py, c, s, ox, oy, ob.radius);
 }
 
 /* EdgeObstacle / EdgeInflatedObstacle residual pair (edge_obstacle.h:85-106, :207-233): returns weighted

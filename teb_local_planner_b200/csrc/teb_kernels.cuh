@@ -75,6 +75,8 @@ struct DevBatch {
   double* dmax_parts;         /* [B][chunks] max |H_rr| over the real rows of the tile (LM lambda init) */
   BandState* state;           /* [B]              */
   int32_t chunks;
+  const double* obst_vertices; /* [S][PV_cap][2] vertex pool of the Line / Pill / Polygon obstacles (or NULL) */
+  int32_t PV_cap;
   /* kernel A band selection (speculative solver, retry rounds overlapped with the next linearisation):
    * a_list != NULL: blockIdx.y indexes the list (a_cnt entries); else bands with defer[b] == skip_tag are skipped */
   const int32_t* a_list;
@@ -144,6 +146,20 @@ __global__ void k_begin(DevBatch db, KParams kp) {
   for (int k = 0; k < 4; ++k) { st.parts_last[k] = 0; st.parts_cur[k] = 0; }
   st.active = 0; st.failed = 0; st.status = 0; st.lm_iters = 0;
   if (!kp.p.optimization_activate) { st.failed = 1; st.status |= TEB_STATUS_DISABLED; }
+  { /* obstacle rows the batch cannot describe (the device entry point cannot check them on the host) */
+    const int sc = db.scene_id[b];
+    const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
+    const int M = db.obst_count[sc];
+    bool bad = false;
+    for (int m = 0; m < M; ++m) {
+      const int type = go[m].type, vb = go[m].vertex_begin, vc = go[m].vertex_count;
+      if (type < TEB_OBST_POINT || type > TEB_OBST_POLYGON) bad = true;
+      else if (type >= TEB_OBST_LINE &&
+               (vc < 1 || (type != TEB_OBST_POLYGON && vc != 2) || vb < 0 || (long long)vb + vc > db.PV_cap))
+        bad = true;
+    }
+    if (bad) { st.failed = 1; st.status |= TEB_STATUS_BAD_INPUT; }
+  }
   db.state[b] = st;
 }
 
@@ -161,6 +177,7 @@ __global__ void k_auto_resize(DevBatch db, KParams kp) {
 }
 
 /* ------------------------------------------------------------------ k_build_graph (CTA per band) */
+template <bool GEOM>
 __global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TebObstacle* so = reinterpret_cast<TebObstacle*>(smem_raw);
@@ -185,6 +202,7 @@ __global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
   for (int m = threadIdx.x; m < M; m += blockDim.x) so[m] = go[m];
   __syncthreads();
   const double* P = db.poses + (size_t)b * db.n_cap * 4;
+  const double* pool = db.obst_vertices + (size_t)s * db.PV_cap * 2; /* only dereferenced for vertex-list obstacles */
   unsigned long long* assoc = db.assoc + (size_t)b * db.n_cap * db.MW;
 
   unsigned long long* assoc3 = db.assoc3 + (size_t)b * db.n_cap * db.MW;
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
         for (int m = 0; m < M; ++m) {
           const TebObstacle ob = so[m];
           if (kp.p.include_dynamic_obstacles && ob.dynamic) continue;
-          const double dist = footprint_distance_only(kp, px, py, cs, sn, ob.x, ob.y, ob.radius);
+          const double dist = robot_obstacle_distance_only<GEOM>(kp, pool, px, py, cs, sn, ob, ob.x, ob.y, 0.0, 0.0);
           if (dist < force_d) { mask[m >> 6] |= 1ull << (m & 63); continue; }
           if (dist > cut_d) continue;
           const double cx = ob.x - px, cy = ob.y - py;
@@ -232,10 +250,21 @@ __global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
         int index = -1;
         if (kp.p.obstacle_poses_affected >= n) {
           index = n / 2;
-        } else { /* findClosestTrajectoryPose(centroid) timed_elastic_band.cpp:455-478, :540-553 */
+        } else if (GEOM && (ob.type == TEB_OBST_LINE || (ob.type == TEB_OBST_POLYGON && ob.vertex_count >= 2))) {
+          /* findClosestTrajectoryPose(line) / (polygon) timed_elastic_band.cpp:480-530: distance of the pose
+           * POSITION to the vertex list (no footprint, no radius) */
           double best = 1.7976931348623157e308;
           for (int i = 0; i < n; ++i) {
-            const double dx = ob.x - P[4 * i], dy = ob.y - P[4 * i + 1];
+            const double d = generic_distance(TEB_FOOTPRINT_POINT, kp.fp_geom, pool, P[4 * i], P[4 * i + 1], 1.0, 0.0, ob.x, ob.y,
+                                              0.0, TEB_OBST_POLYGON, ob.vertex_begin, ob.vertex_count, 0.0, 0.0).d;
+            if (d < best) { best = d; index = i; }
+          }
+        } else { /* findClosestTrajectoryPose(point) :455-478; Circular and Pill obstacles: centroid (:545) */
+          double cx = ob.x, cy = ob.y;
+          if (GEOM && ob.type == TEB_OBST_POLYGON && ob.vertex_count == 1) { cx = pool[2 * ob.vertex_begin]; cy = pool[2 * ob.vertex_begin + 1]; }
+          double best = 1.7976931348623157e308;
+          for (int i = 0; i < n; ++i) {
+            const double dx = cx - P[4 * i], dy = cy - P[4 * i + 1];
             const double d2 = dx * dx + dy * dy;
             if (d2 < best) { best = d2; index = i; }
           }
@@ -305,11 +334,13 @@ __global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
 
 /* ------------------------------------------------------------------ unary terms of one pose (obstacles, dynamic
  * obstacles, via-points): accumulates U = sum kappa g g^T (xx,xy,yy,xt,yt,tt), ub = -sum beta g, chi2 by family */
+template <bool GEOM>
 __device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& db, int b, int sc, int i, int n, double px,
                                             double py, double cs, double sn, const TebObstacle* so, int M,
                                             bool want_grad, double U[6], double ub[3], double& chi_obst,
                                             double& chi_via) {
   if (i < 1 || i > n - 2) return;
+  const double* pool = db.obst_vertices + (size_t)sc * db.PV_cap * 2; /* only dereferenced for vertex-list obstacles */
   if (kp.has_obst) {
     const unsigned long long* assoc = db.assoc + ((size_t)b * db.n_cap + i) * db.MW;
     for (int w = 0; w < db.MW; ++w) {
@@ -319,7 +350,7 @@ __device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& d
         mask &= mask - 1;
         const TebObstacle ob = so[m];
         double g[3], kappa, beta;
-        const double d = footprint_distance(kp, px, py, cs, sn, ob.x, ob.y, ob.radius, g);
+        const double d = robot_obstacle_distance<GEOM>(kp, pool, px, py, cs, sn, ob, ob.x, ob.y, 0.0, 0.0, g);
         double cterm = obstacle_terms(kp, d, kappa, beta);
         if (kp.p.legacy_obstacle_association &&
             ((db.assoc3[((size_t)b * db.n_cap + i) * db.MW + w] >> (m & 63)) & 1ull)) {
@@ -341,7 +372,8 @@ __device__ __forceinline__ void unary_terms(const KParams& kp, const DevBatch& d
     for (int q = 0; q < nd; ++q) {
       const TebObstacle ob = so[di[q]];
       double g[3], kappa, beta;
-      const double d = footprint_distance(kp, px, py, cs, sn, ob.x + t * ob.vx, ob.y + t * ob.vy, ob.radius, g);
+      const double d = robot_obstacle_distance<GEOM>(kp, pool, px, py, cs, sn, ob, ob.x + t * ob.vx, ob.y + t * ob.vy, t * ob.vx,
+                                               t * ob.vy, g);
       chi_obst += dynamic_terms(kp, d, kappa, beta);
       if (want_grad && (kappa != 0 || beta != 0)) {
         U[0] += kappa * g[0] * g[0]; U[1] += kappa * g[0] * g[1]; U[2] += kappa * g[1] * g[1];
@@ -744,7 +776,7 @@ __host__ __device__ inline size_t ka_smem_bytes(int M_cap) {
   return (d + jb) * sizeof(double) + (size_t)M_cap * sizeof(TebObstacle) + 64;
 }
 
-template <bool HOLO>
+template <bool HOLO, bool GEOM>
 __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = linearize_band(db, blockIdx.y);
@@ -824,8 +856,8 @@ __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParam
       if (i < n) {
         const int j = il + 2;
         double sn = 0, cs = 1;
-        if (kp.p.footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
-        unary_terms(kp, db, b, s, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
+        if (kp.p.footprint_type >= TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
+        unary_terms<GEOM>(kp, db, b, s, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
         if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
           const double dt = sP[4 * j + 3];
           chi[2] += kp.p.weight_optimaltime * dt * dt;
@@ -922,7 +954,7 @@ __host__ __device__ inline size_t kw_smem_bytes(int M_cap) {
   return (size_t)KW_WARPS * KWSmem::REG * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 64;
 }
 
-template <bool HOLO>
+template <bool HOLO, bool GEOM>
 __global__ void __launch_bounds__(32 * KW_WARPS) k_linearize_w(const __grid_constant__ DevBatch db,
                                                                const __grid_constant__ KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -938,7 +970,7 @@ __global__ void __launch_bounds__(32 * KW_WARPS) k_linearize_w(const __grid_cons
   {
     const double2* src = reinterpret_cast<const double2*>(db.obstacles + (size_t)s * db.M_cap);
     double2* dst = reinterpret_cast<double2*>(so);
-    for (int k = threadIdx.x; k < 3 * M; k += 32 * KW_WARPS) dst[k] = src[k];
+    for (int k = threadIdx.x; k < (int)(sizeof(TebObstacle) / 16) * M; k += 32 * KW_WARPS) dst[k] = src[k];
   }
   __syncthreads();
   const int chunk = blockIdx.x * KW_WARPS + warp;
@@ -1000,8 +1032,8 @@ __global__ void __launch_bounds__(32 * KW_WARPS) k_linearize_w(const __grid_cons
     if (i < n) {
       const int j = il + 2;
       double sn = 0, cs = 1;
-      if (kp.p.footprint_type == TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
-      unary_terms(kp, db, b, s, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
+      if (kp.p.footprint_type >= TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
+      unary_terms<GEOM>(kp, db, b, s, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
       if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
         const double dt = sP[4 * j + 3];
         chi[2] += kp.p.weight_optimaltime * dt * dt;
@@ -1068,6 +1100,7 @@ struct ChainCarry {
   bool has_cs, has_seg;
 };
 
+template <bool GEOM>
 __device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db, int b, int sc, int i, int n, const double* sT,
                                           const TebObstacle* so, int M, const double* vs, const double* vg,
                                           double (&chi)[4], ChainCarry& cy) {
@@ -1184,7 +1217,8 @@ __device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db,
             mask &= mask - 1;
             const TebObstacle ob = so[m];
             double dratio;
-            const double d = footprint_distance_only(kp, pa[0], pa[1], ca, sa, ob.x, ob.y, ob.radius);
+            const double d = robot_obstacle_distance_only<GEOM>(kp, db.obst_vertices + (size_t)sc * db.PV_cap * 2, pa[0], pa[1], ca, sa, ob,
+                                                          ob.x, ob.y, 0.0, 0.0);
             const double ratio = proximity_ratio(kp, d, dratio);
             const double e0 = pen_interval(s1.v, ratio * kp.p.max_vel_x, 0, sl);
             const double e1 = pen_interval(s1.w, ratio * kp.p.max_vel_theta, 0, sl);
@@ -1196,10 +1230,10 @@ __device__ __forceinline__ void pose_chi2(const KParams& kp, const DevBatch& db,
       if (kp.has_time) chi[2] += kp.p.weight_optimaltime * pa[3] * pa[3];
     }
     double U[6], ub[3];
-    unary_terms(kp, db, b, sc, i, n, pa[0], pa[1], ca, sa, so, M, false, U, ub, chi[0], chi[1]);
+    unary_terms<GEOM>(kp, db, b, sc, i, n, pa[0], pa[1], ca, sa, so, M, false, U, ub, chi[0], chi[1]);
 }
 
-template <int NTHREADS>
+template <int NTHREADS, bool GEOM>
 __device__ __forceinline__ void eval_chi2_parts(const KParams& kp, const DevBatch& db, int b, int n, const double* sT,
                                                 const TebObstacle* so, int M, double* scratch, double* out) {
   double chi[4] = {0, 0, 0, 0};
@@ -1209,7 +1243,7 @@ __device__ __forceinline__ void eval_chi2_parts(const KParams& kp, const DevBatc
   for (int i = threadIdx.x; i < n; i += NTHREADS) {
     ChainCarry cy;
     cy.has_cs = false; cy.has_seg = false;
-    pose_chi2(kp, db, b, sc, i, n, sT, so, M, vs, vg, chi, cy);
+    pose_chi2<GEOM>(kp, db, b, sc, i, n, sT, so, M, vs, vg, chi, cy);
   }
   block_sum<4, NTHREADS / 32>(chi, scratch, out);
 }
@@ -1511,7 +1545,7 @@ __host__ __device__ inline size_t kb_bcr_smem_bytes(int n_cap, int M_cap) {
          (size_t)M_cap * sizeof(TebObstacle) + 64;
 }
 
-template <int SOLVER, int NT>
+template <int SOLVER, int NT, bool GEOM>
 __global__ void __launch_bounds__(NT, SOLVER == 1 ? 2 : 1) k_lm_step_t(DevBatch db, KParams kp, int iteration) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int b = blockIdx.x;
@@ -1664,7 +1698,7 @@ __global__ void __launch_bounds__(NT, SOLVER == 1 ? 2 : 1) k_lm_step_t(DevBatch 
     block_sum<1, NT / 32>(red, sRed, sRed + 40);
     const double scale = sRed[40] + 1e-3;
     __syncthreads();
-    eval_chi2_parts<NT>(kp, db, b, n, sT, so, M, sRed, sRed + 40);
+    eval_chi2_parts<NT, GEOM>(kp, db, b, n, sT, so, M, sRed, sRed + 40);
     for (int k = 0; k < 4; ++k) last_parts[k] = sRed[40 + k];
     __syncthreads();
     double tempChi = last_parts[0] + last_parts[1] + last_parts[2] + last_parts[3];
@@ -1744,6 +1778,7 @@ __global__ void k_finalize(DevBatch db, KParams kp, TebOptimizeArgs args) {
  * optimal_planner.cpp:999-1021). One edge per obstacle associated with pose a over (pose a, pose a+1, dt_a); the
  * 7x7 J^T Omega J of every anchor is added to the band written by kernel A. Even anchors first, then odd ones, so
  * that overlapping rows are updated in a fixed order (deterministic, no atomics). */
+template <bool GEOM>
 __global__ void __launch_bounds__(256) k_vor(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp) {
   extern __shared__ __align__(16) unsigned char vor_raw[];
   TebObstacle* so = reinterpret_cast<TebObstacle*>(vor_raw);
@@ -1756,6 +1791,7 @@ __global__ void __launch_bounds__(256) k_vor(const __grid_constant__ DevBatch db
   for (int m = threadIdx.x; m < M; m += blockDim.x) so[m] = db.obstacles[(size_t)sc * db.M_cap + m];
   __syncthreads();
   const double* P = db.poses + (size_t)b * db.n_cap * 4;
+  const double* pool = db.obst_vertices + (size_t)sc * db.PV_cap * 2;
   double* H = db.Hb + (size_t)b * 4 * db.n_cap * HROW;
   double* rhs = db.rhs + (size_t)b * 4 * db.n_cap;
   const double wv = kp.p.weight_velocity_obstacle_ratio;
@@ -1781,7 +1817,7 @@ __global__ void __launch_bounds__(256) k_vor(const __grid_constant__ DevBatch db
           mask &= mask - 1;
           const TebObstacle ob = so[m];
           double g[3], dratio;
-          const double d = footprint_distance(kp, pa[0], pa[1], cs, sn, ob.x, ob.y, ob.radius, g);
+          const double d = robot_obstacle_distance<GEOM>(kp, pool, pa[0], pa[1], cs, sn, ob, ob.x, ob.y, 0.0, 0.0, g);
           const double ratio = proximity_ratio(kp, d, dratio);
           double s0, s1;
           const double e0 = pen_interval(sd.v, ratio * kp.p.max_vel_x, 0, s0);

@@ -328,7 +328,7 @@ __host__ __device__ inline size_t eval_smem_bytes(int n_cap, int M_cap, int K) {
          (size_t)K * RES_STRIDE * sizeof(double) + 32;
 }
 
-template <int MINB>
+template <int MINB, bool GEOM>
 __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch db, KParams kp, SpecBufs sp, int iteration,
                                                                 int round, int g, int tag) {
   extern __shared__ __align__(16) unsigned char ev_raw[];
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch d
     const int i0 = lane * per, i1 = min(i0 + per, n);
     ChainCarry cy;
     cy.has_cs = false; cy.has_seg = false;
-    for (int i = i0; i < i1; ++i) pose_chi2(kp, db, b, sc, i, n, myT, so, M, vs, vg, chi, cy);
+    for (int i = i0; i < i1; ++i) pose_chi2<GEOM>(kp, db, b, sc, i, n, myT, so, M, vs, vg, chi, cy);
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) chi[c] = warp_sum(chi[c]);

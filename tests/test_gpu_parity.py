@@ -26,7 +26,7 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz")
 
 
 def _gpu(hb, p):
-    g = T.TebGpu(hb.B, hb.n_cap, hb.S, max(hb.M_cap, 1), hb.V_cap)
+    g = T.TebGpu(hb.B, hb.n_cap, hb.S, max(hb.M_cap, 1), hb.V_cap, max_obst_vertices=hb.PV_cap)
     g.set_params(p)
     return g
 
@@ -72,7 +72,7 @@ def test_kernel_a_system_matches_oracle(oracle, cfg):
 
 
 def test_kernel_a_thread_mappings_agree():
-    """warp-per-tile (default) and CTA-per-tile kernel A share their arithmetic: identical band, chi2 to round-off"""
+    """warp-per-tile and CTA-per-tile (default) kernel A share their arithmetic: band and chi2 equal to round-off"""
     p, hb = scenes.make_config_batch("C4", candidates=6, seed=2)
     g = _gpu(hb, p)
     g.set_linearize_variant(1)
@@ -80,7 +80,8 @@ def test_kernel_a_thread_mappings_agree():
     g.set_linearize_variant(0)
     H0, c0 = g.build_system(hb, 2)
     g.close()
-    assert np.array_equal(H1, H0)
+    # same device functions, two kernels: the compiler may contract multiply-adds differently, nothing more
+    assert np.abs(H1 - H0).max() <= 1e-13 * np.abs(H0).max()
     assert np.allclose(c1, c0, rtol=1e-13)
 
 
@@ -295,6 +296,75 @@ def test_holonomic_edges(oracle, acc_lim_y, max_vel_trans):
     oracle.optimize_batch(p, hn, args, jac_mode=oracle.JAC_G2O, threads=8)
     dn = _pose_diff(hg, hn)
     assert np.median(dn) <= 1e-4, dn
+
+
+@pytest.mark.parametrize("footprint,legacy,vor", [("point", 0, 0.0), ("line", 0, 0.0), ("polygon", 0, 0.0), ("two_circles", 0, 0.0),
+                                                  ("circular", 1, 0.0), ("polygon", 1, 0.0), ("line", 0, 2.0)])
+def test_shape_obstacles_and_footprints(oracle, footprint, legacy, vor):
+    """Line / Pill / Polygon obstacles (obstacles.h:597-1045; static and moving) with every footprint model incl.
+    Line / Polygon (robot_footprint_model.h:439-760): kernel-A system and the full optimisation against the oracle"""
+    p, hb0 = scenes.make_config_batch("C4", candidates=6, seed=6)
+    hb0 = scenes.add_shape_obstacles(hb0, seed=1)
+    hb0.obstacles["dynamic"][0, ::3] = 0           # a mix of static and moving shapes
+    p.legacy_obstacle_association, p.obstacle_poses_affected = legacy, 8
+    p.weight_velocity_obstacle_ratio = vor
+    p.obstacle_proximity_lower_bound, p.obstacle_proximity_upper_bound = 0.2, 1.0
+    if footprint == "line":
+        scenes.set_line_footprint(p)
+    elif footprint == "polygon":
+        scenes.set_polygon_footprint(p)
+    elif footprint == "circular":
+        p.footprint_type, p.footprint_radius = abi.TEB_FOOTPRINT_CIRCULAR, 0.2
+    elif footprint == "two_circles":
+        p.footprint_type = abi.TEB_FOOTPRINT_TWO_CIRCLES
+        p.footprint_front_offset, p.footprint_front_radius, p.footprint_rear_offset, p.footprint_rear_radius = 0.3, 0.15, 0.2, 0.2
+    g = _gpu(hb0, p)
+    obst = hb0.obstacles[0][:hb0.obst_count[0]]
+    for variant in (0, 1):
+        g.set_linearize_variant(variant)
+        Hb, chi2 = g.build_system(hb0, 1)
+        for b in range(hb0.B):
+            n = hb0.n[b]
+            Hd, bd, c2 = oracle.build_system(p, hb0.poses[b], n, obst, via=hb0.via[b], weight_multiplier=2.0,
+                                             jac_mode=oracle.JAC_ANALYTIC, obst_vertices=hb0.obst_vertices[0])
+            ref = _padded_from_dense(Hd, bd, n)
+            got = Hb[b, :4 * n]
+            assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+            assert abs(chi2[b] - c2) <= 1e-11 * max(c2, 1.0)
+    g.set_linearize_variant(0)
+    args = abi.make_args(5, 4, True, 100.0, 1.0, False)
+    outs = {}
+    for solver in (2, 0):
+        g.set_solver(solver)
+        h = hb0.copy()
+        g.optimize(h, args)
+        outs[solver] = h
+    g.close()
+    hg = outs[2]
+    assert _pose_diff(outs[0], hg).max() < 1e-7
+    ha = hb0.copy()
+    oracle.optimize_batch(p, ha, args, jac_mode=oracle.JAC_ANALYTIC, threads=8)
+    assert np.array_equal(hg.n, ha.n)
+    d = _pose_diff(hg, ha)
+    # a closest-feature switch (vertex <-> edge) is a kink of the distance: a band that sits on one may take another
+    # LM branch after a last-bit difference; all others agree to 1e-6
+    assert np.median(d) < 1e-8 and (d < 1e-6).mean() >= 0.8, d
+    assert np.all(hg.status & abi.TEB_STATUS_OPTIMIZED)
+
+
+def test_bad_obstacle_rows_are_reported():
+    p, hb = scenes.make_config_batch("C1", candidates=2)
+    hb = scenes.add_shape_obstacles(hb, seed=2)
+    g = _gpu(hb, p)
+    bad = hb.copy()
+    bad.obstacles["vertex_count"][0, 0] = 99                 # vertex range outside the pool
+    with pytest.raises(T.TebGpuError, match="rc=-1"):
+        g.optimize(bad, abi.make_args())
+    with pytest.raises(T.TebGpuError, match="rc=-3"):
+        q = abi.default_params()
+        q.footprint_type = 9
+        g.set_params(q)
+    g.close()
 
 
 def test_solvers_and_speculation_widths_agree():
