@@ -28,12 +28,13 @@ typedef std::shared_ptr<TebVisualization> TebVisualizationPtr;
 /* One tebgpu context (device buffers + stream), shared by every planner of a process unless told otherwise. */
 class TebGpuContext {
  public:
-  TebGpuContext(int max_bands, int max_poses, int max_obstacles, int max_viapoints, int device = 0);
+  TebGpuContext(int max_bands, int max_poses, int max_obstacles, int max_viapoints, int device = 0,
+                int max_obst_vertices = 2048);
   ~TebGpuContext();
   tebgpu_ctx* get() const { return ctx_; }
   const TebGpuLimits& limits() const { return lim_; }
   static std::shared_ptr<TebGpuContext> shared(int min_bands = 8, int min_poses = 512, int min_obstacles = 256,
-                                               int min_viapoints = 16);
+                                               int min_viapoints = 16, int min_obst_vertices = 2048);
  private:
   tebgpu_ctx* ctx_ = nullptr;
   TebGpuLimits lim_{};

@@ -9,12 +9,14 @@
 namespace teb_local_planner {
 
 /* ------------------------------------------------------------------ GPU context */
-TebGpuContext::TebGpuContext(int max_bands, int max_poses, int max_obstacles, int max_viapoints, int device) {
+TebGpuContext::TebGpuContext(int max_bands, int max_poses, int max_obstacles, int max_viapoints, int device,
+                             int max_obst_vertices) {
   lim_.max_bands = max_bands;
   lim_.max_poses = max_poses;
   lim_.max_scenes = 1;
   lim_.max_obstacles = max_obstacles;
   lim_.max_viapoints = max_viapoints;
+  lim_.max_obst_vertices = max_obst_vertices;
   int rc = tebgpu_create(&lim_, device, &ctx_);
   if (rc != TEBGPU_OK) {
     std::fprintf(stderr, "TebGpuContext: tebgpu_create failed rc=%d (%s)\n", rc, ctx_ ? tebgpu_last_error_string(ctx_) : "");
@@ -25,18 +27,21 @@ TebGpuContext::TebGpuContext(int max_bands, int max_poses, int max_obstacles, in
 TebGpuContext::~TebGpuContext() {
   if (ctx_) tebgpu_destroy(ctx_);
 }
-std::shared_ptr<TebGpuContext> TebGpuContext::shared(int min_bands, int min_poses, int min_obstacles, int min_viapoints) {
+std::shared_ptr<TebGpuContext> TebGpuContext::shared(int min_bands, int min_poses, int min_obstacles, int min_viapoints,
+                                                     int min_obst_vertices) {
   static std::mutex mu;
   static std::shared_ptr<TebGpuContext> inst;
   std::lock_guard<std::mutex> lock(mu);
   if (!inst || !inst->get() || inst->limits().max_bands < min_bands || inst->limits().max_poses < min_poses ||
-      inst->limits().max_obstacles < min_obstacles || inst->limits().max_viapoints < min_viapoints) {
+      inst->limits().max_obstacles < min_obstacles || inst->limits().max_viapoints < min_viapoints ||
+      inst->limits().max_obst_vertices < min_obst_vertices) {
     int mb = std::max(min_bands, inst ? inst->limits().max_bands : 0);
     int mp = std::max(min_poses, inst ? inst->limits().max_poses : 0);
     int mo = std::max(min_obstacles, inst ? inst->limits().max_obstacles : 0);
     int mv = std::max(min_viapoints, inst ? inst->limits().max_viapoints : 0);
+    int mpv = std::max(min_obst_vertices, inst ? inst->limits().max_obst_vertices : 0);
     inst.reset();
-    inst = std::make_shared<TebGpuContext>(mb, mp, mo, mv);
+    inst = std::make_shared<TebGpuContext>(mb, mp, mo, mv, 0, mpv);
   }
   return inst;
 }
@@ -186,17 +191,27 @@ bool TebOptimalPlanner::runBatch(const TebConfig& cfg, const std::vector<TebOpti
   if (M_cap > 256) { std::fprintf(stderr, "optimizeTEB: more than 256 obstacles per scene is not supported\n"); return false; }
   std::vector<TebObstacle> obst((size_t)S * M_cap);
   std::vector<int32_t> obst_count(S, 0);
+  std::vector<std::vector<double>> pools(S);
   for (int s = 0; s < S; ++s) {
     if (!scenes[s]) continue;
     obst_count[s] = (int)scenes[s]->size();
-    for (size_t m = 0; m < scenes[s]->size(); ++m) obst[(size_t)s * M_cap + m] = (*scenes[s])[m]->toRow();
+    for (size_t m = 0; m < scenes[s]->size(); ++m) {
+      TebObstacle& row = obst[(size_t)s * M_cap + m];
+      row = (*scenes[s])[m]->toRow();
+      (*scenes[s])[m]->appendVertices(pools[s], row); /* Line / Pill / Polygon: vertex range in the scene's pool */
+    }
   }
-  if (!gpu) gpu = TebGpuContext::shared(B, n_cap, M_cap, V_max);
+  int PV_cap = 0;
+  for (const std::vector<double>& pool : pools) PV_cap = std::max(PV_cap, (int)(pool.size() / 2));
+  std::vector<double> obst_vertices((size_t)S * std::max(PV_cap, 1) * 2, 0.0);
+  for (int s = 0; s < S; ++s) std::copy(pools[s].begin(), pools[s].end(), obst_vertices.begin() + (size_t)s * PV_cap * 2);
+  if (!gpu) gpu = TebGpuContext::shared(B, n_cap, M_cap, V_max, PV_cap);
   if (!gpu || !gpu->get()) return false;
   const TebGpuLimits& lim = gpu->limits();
-  if (lim.max_bands < B || lim.max_poses < n_cap || lim.max_obstacles < M_cap || lim.max_viapoints < V_max || lim.max_scenes < S) {
+  if (lim.max_bands < B || lim.max_poses < n_cap || lim.max_obstacles < M_cap || lim.max_viapoints < V_max || lim.max_scenes < S ||
+      lim.max_obst_vertices < PV_cap) {
     /* a caller-provided context that is too small: fall back to the (growing) shared one */
-    gpu = TebGpuContext::shared(B, n_cap, M_cap, V_max);
+    gpu = TebGpuContext::shared(B, n_cap, M_cap, V_max, PV_cap);
     if (!gpu || !gpu->get() || gpu->limits().max_scenes < S) {
       std::fprintf(stderr, "optimizeTEB: GPU context limits exceeded (scenes=%d)\n", S);
       return false;
@@ -232,6 +247,7 @@ bool TebOptimalPlanner::runBatch(const TebConfig& cfg, const std::vector<TebOpti
   }
   TebBatch bt{};
   bt.B = B; bt.n_cap = n_cap; bt.S = S; bt.M_cap = M_cap; bt.V_cap = V_max;
+  bt.PV_cap = PV_cap; bt.obst_vertices = PV_cap > 0 ? obst_vertices.data() : nullptr;
   bt.poses = poses.data(); bt.n = n.data(); bt.scene_id = scene_id.data(); bt.obstacles = obst.data();
   bt.obst_count = obst_count.data(); bt.via = V_max > 0 ? via.data() : nullptr; bt.via_count = V_max > 0 ? via_count.data() : nullptr;
   bt.vel_start = vel_start.data(); bt.vel_goal = vel_goal.data(); bt.prefer_rotdir = rotdir.data();

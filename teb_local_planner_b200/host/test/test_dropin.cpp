@@ -91,6 +91,37 @@ static void cpu_checks() {
   TwoCirclesRobotFootprint fp(0.3, 0.2, 0.2, 0.25);
   CircularObstacle co(2, 0, 0.5);
   CHECK(std::fabs(fp.calculateDistance(PoseSE2(0, 0, 0), &co) - (2 - 0.3 - 0.5 - 0.2)) < 1e-12);
+  /* Line / Pill / Polygon obstacles and Line / Polygon footprints: host-side queries (obstacles.h:597-1045,
+   * robot_footprint_model.h:439-775) */
+  LineObstacle lo(1, -1, 1, 1);
+  CHECK(lo.getMinimumDistance(Eigen::Vector2d(0, 0)) == 1.0 && lo.getCentroid().x() == 1.0 && lo.getCentroid().y() == 0.0);
+  CHECK(lo.toRow().type == TEB_OBST_LINE);
+  PillObstacle pill(1, -1, 1, 1, 0.2);
+  CHECK(std::fabs(pill.getMinimumDistance(Eigen::Vector2d(0, 0)) - 0.8) < 1e-15 && pill.toRow().type == TEB_OBST_PILL);
+  PolygonObstacle sq;
+  sq.pushBackVertex(1, -1); sq.pushBackVertex(3, -1); sq.pushBackVertex(3, 1); sq.pushBackVertex(1, 1); sq.pushBackVertex(1, -1);
+  sq.finalizePolygon();
+  CHECK(sq.noVertices() == 4 && std::fabs(sq.getCentroid().x() - 2.0) < 1e-15 && std::fabs(sq.getCentroid().y()) < 1e-15);
+  CHECK(sq.getMinimumDistance(Eigen::Vector2d(0, 0)) == 1.0 && sq.checkCollision(Eigen::Vector2d(2, 0), 0.0));
+  sq.setCentroidVelocity(Eigen::Vector2d(1, 0));
+  CHECK(sq.getMinimumSpatioTemporalDistance(Eigen::Vector2d(0, 0), 2.0) == 3.0);
+  LineRobotFootprint lf(Eigen::Vector2d(-0.5, 0), Eigen::Vector2d(0.5, 0));
+  CHECK(std::fabs(lf.calculateDistance(PoseSE2(0, 0, M_PI / 2), &lo) - 1.0) < 1e-15);
+  LineObstacle cross(-1, 0.1, 1, 0.1);
+  CHECK(lf.calculateDistance(PoseSE2(0, 0, M_PI / 2), &cross) == 0.0);
+  Point2dContainer unit = {Eigen::Vector2d(-0.5, -0.5), Eigen::Vector2d(0.5, -0.5), Eigen::Vector2d(0.5, 0.5), Eigen::Vector2d(-0.5, 0.5)};
+  PolygonRobotFootprint pf(unit);
+  PointObstacle far(2, 0);
+  CHECK(std::fabs(pf.calculateDistance(PoseSE2(0, 0, M_PI / 4), &far) - (2 - std::sqrt(0.5))) < 1e-15);
+  CHECK(std::fabs(pf.getInscribedRadius() - 0.5) < 1e-15);
+  std::vector<double> pool;
+  TebObstacle row = sq.toRow();
+  sq.appendVertices(pool, row);
+  CHECK(row.type == TEB_OBST_POLYGON && row.vertex_begin == 0 && row.vertex_count == 4 && pool.size() == 8 && row.dynamic == 1);
+  TebParams fpp;
+  tebgpu_default_params(&fpp);
+  pf.fillParams(fpp);
+  CHECK(fpp.footprint_type == TEB_FOOTPRINT_POLYGON && fpp.footprint_vertex_count == 4 && fpp.footprint_vertices[2] == 0.5);
 }
 
 static void print_band(const char* key, const TimedElasticBand& teb) {
@@ -160,6 +191,24 @@ static int gpu_checks() {
   }
   CHECK(hcp.bestTeb() != nullptr);
   CHECK(hcp.getVelocityCommand(vx, vy, om, 1));
+  { /* ---- polygon footprint among line / pill / polygon obstacles (one static, one moving) */
+    TebConfig scfg;
+    ObstContainer so;
+    so.push_back(ObstaclePtr(new LineObstacle(-1.0, 0.6, 0.5, 1.4)));
+    so.push_back(ObstaclePtr(new PillObstacle(1.0, -1.2, 2.0, -0.5, 0.15)));
+    PolygonObstacle* po = new PolygonObstacle();
+    po->pushBackVertex(-0.3, -0.6); po->pushBackVertex(0.4, -0.7); po->pushBackVertex(0.2, -0.1);
+    po->finalizePolygon();
+    so.push_back(ObstaclePtr(po));
+    so[1]->setCentroidVelocity(Eigen::Vector2d(-0.1, 0.1));
+    ViaPointContainer svia;
+    TebOptimalPlanner sp(scfg, &so, TebVisualizationPtr(), &svia);
+    Point2dContainer body = {Eigen::Vector2d(-0.25, -0.2), Eigen::Vector2d(0.35, -0.2), Eigen::Vector2d(0.35, 0.2), Eigen::Vector2d(-0.25, 0.2)};
+    sp.updateRobotModel(RobotFootprintModelPtr(new PolygonRobotFootprint(body)));
+    bool sok = sp.plan(PoseSE2(-4, 0, 0), PoseSE2(4, 0, 0));
+    std::printf("SHAPES_OK %d\nSHAPES_STATUS %d\n", sok ? 1 : 0, sp.lastStatus());
+    print_band("SHAPES", sp.teb());
+  }
   /* second cycle: hysteresis path of selectBestTeb + warm start of all candidates */
   ok = hcp.plan(PoseSE2(-3.95, 0, 0), PoseSE2(4, 0, 0), NULL);
   std::printf("HCP2_OK %d\nHCP2_BEST %d\n", ok ? 1 : 0, hcp.bestTebIdx());

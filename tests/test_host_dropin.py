@@ -144,3 +144,21 @@ def test_dropin_gpu_scenes_match_oracle(exe, oracle):
     from teb_local_planner_b200 import distributed as D
     assert int(vals["HCP_BEST"][0][0]) == D.select_best(costs, -1, 2, hp.selection_cost_hysteresis, hp.selection_prefer_initial_plan)
     assert vals["HCP2_OK"][0][0] == "1" and int(vals["HCP2_BEST"][0][0]) in (0, 1, 2)
+    # ---- polygon footprint among a line, a moving pill and a polygon obstacle
+    from teb_local_planner_b200 import scenes
+    sp = abi.default_params()
+    scenes.set_polygon_footprint(sp, ((-0.25, -0.2), (0.35, -0.2), (0.35, 0.2), (-0.25, 0.2)))
+    pool = np.array([[-1.0, 0.6], [0.5, 1.4], [1.0, -1.2], [2.0, -0.5], [-0.3, -0.6], [0.4, -0.7], [0.2, -0.1]])
+    sob = np.zeros(3, abi.OBST_DTYPE)
+    sob["type"] = [abi.TEB_OBST_LINE, abi.TEB_OBST_PILL, abi.TEB_OBST_POLYGON]
+    sob["vertex_begin"], sob["vertex_count"] = [0, 2, 4], [2, 2, 3]
+    sob["radius"] = [0.0, 0.15, 0.0]
+    sob["vx"], sob["vy"], sob["dynamic"] = [0, -0.1, 0], [0, 0.1, 0], [0, 1, 0]
+    ctr = [scenes.polygon_centroid(pool[b:b + c]) for b, c in zip(sob["vertex_begin"], sob["vertex_count"])]
+    sob["x"], sob["y"] = [c[0] for c in ctr], [c[1] for c in ctr]
+    rec0 = oracle.init_trajectory([-4, 0, 0], [4, 0, 0], 0.0, sp.max_vel_x, sp.min_samples)
+    sref, _, _ = oracle.optimize_band(sp, rec0, len(rec0), sob, args=abi.make_args(5, 4, False), jac_mode=oracle.JAC_ANALYTIC,
+                                      n_cap=512, obst_vertices=pool)
+    sgot = bands["SHAPES"]
+    assert vals["SHAPES_OK"][0][0] == "1" and len(sgot) == len(sref)
+    assert np.abs(sgot - sref).max() < 1e-6
