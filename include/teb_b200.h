@@ -136,6 +136,8 @@ typedef struct TebParams {
   double  selection_viapoint_cost_scale;
   int32_t selection_alternative_time_cost;
   int32_t enable_multithreading;
+  double  h_signature_prescaler;   /* teb_config.h:201, default 1   */
+  double  h_signature_threshold;   /* teb_config.h:202, default 0.1 */
   /* recovery */
   int32_t divergence_detection_enable;
   int32_t _pad4;
@@ -260,6 +262,16 @@ int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k);
  * the accumulated milliseconds and launch count since profiling was enabled, and resets the accumulators. */
 int32_t tebgpu_set_profiling(tebgpu_ctx* ctx, int32_t enable);
 int32_t tebgpu_get_kernel_times(tebgpu_ctx* ctx, double ms_out[9], int64_t count_out[9]);
+
+/* HomotopyClassPlanner::calculateEquivalenceClass (homotopy_class_planner.hpp:46-63) for every band of the batch, i.e.
+ * the step that decides which candidates are kept before they are optimised (renewAndAnalyzeOldTebs,
+ * homotopy_class_planner.cpp:214-256). include_dynamic_obstacles == 0: HSignature (h_signature.h:97-186), h_out[b] =
+ * (Re H, Im H), stride 2; otherwise HSignature3d (h_signature.h:282-353), h_out[b][l] for the M obstacles of the band's
+ * scene, stride M_cap. The path is the band's pose positions; use_timediffs != 0 takes the transition times from the
+ * band's dt, 0 approximates them by |z2 - z1| / max_vel_x (h_signature.h:307-315, graph-search candidates have no time
+ * information yet). The reference accumulates the 2-D signature in long double; the device uses fp64 (|dH| <= 1e-9 |H|
+ * against the long double oracle, far below h_signature_threshold). device_ptrs as in tebgpu_build_system. */
+int32_t tebgpu_h_signature(tebgpu_ctx* ctx, const TebBatch* batch, int32_t use_timediffs, double* h_out, int32_t device_ptrs);
 
 /* Number of kernels launched by the last optimize call (for bench.py's gpu_launches). */
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx);

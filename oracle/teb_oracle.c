@@ -1737,6 +1737,103 @@ done:
   return rc;
 }
 
+
+/* ------------------------------------------------------------------ H-signatures (h_signature.h) */
+#include <complex.h>
+typedef long double complex lcplx;
+
+/* HSignature::calculateHSignature h_signature.h:97-186: 2-D homology signature, obstacle centroids as poles */
+static void h_signature_2d(const TebParams* c, const double* rec, int n, const TebObstacle* obst, int M, double* out) {
+  out[0] = out[1] = 0;
+  if (M == 0 || n < 1) return;
+  int m = M - 1 > 5 ? M - 1 : 5;
+  int a = (int)ceil((double)m / 2.0);
+  int b = m - a;
+  lcplx start = (long double)rec[0] + I * (long double)rec[1];
+  lcplx end = (long double)rec[4 * (n - 1)] + I * (long double)rec[4 * (n - 1) + 1];
+  lcplx delta = end - start;
+  lcplx normal = -cimagl(delta) + I * creall(delta);
+  lcplx bl, tr;
+  if (cabsl(delta) < 3.0) { bl = start + (0 - 3.0L * I); tr = start + (3.0L + 3.0L * I); }
+  else { bl = start - normal; tr = start + delta + normal; }
+  lcplx H = 0;
+  for (int k = 0; k + 1 < n; ++k) {
+    lcplx z1 = (long double)rec[4 * k] + I * (long double)rec[4 * k + 1];
+    lcplx z2 = (long double)rec[4 * (k + 1)] + I * (long double)rec[4 * (k + 1) + 1];
+    for (int l = 0; l < M; ++l) {
+      lcplx ol = (long double)obst[l].x + I * (long double)obst[l].y;
+      lcplx f0 = (long double)c->h_signature_prescaler * (long double)a * (ol - bl) * (long double)b * (ol - tr);
+      lcplx Al = f0;
+      for (int j = 0; j < M; ++j) {
+        if (j == l) continue;
+        lcplx oj = (long double)obst[j].x + I * (long double)obst[j].y;
+        lcplx diff = ol - oj;
+        if (cabsl(diff) < 0.05) continue;
+        Al /= diff;
+      }
+      double diff2 = (double)cabsl(z2 - ol), diff1 = (double)cabsl(z1 - ol);
+      if (diff2 == 0 || diff1 == 0) continue;
+      double log_real = log(diff2) - log(diff1);
+      double arg_diff = (double)(cargl(z2 - ol) - cargl(z1 - ol));
+      double prop[5] = {arg_diff, arg_diff + 2 * M_PI, arg_diff - 2 * M_PI, arg_diff + 4 * M_PI, arg_diff - 4 * M_PI};
+      double log_imag = prop[0];
+      for (int q = 1; q < 5; ++q)
+        if (fabs(prop[q]) < fabs(log_imag)) log_imag = prop[q]; /* std::min_element(..., smaller_than_abs) */
+      lcplx lv = (long double)log_real + I * (long double)log_imag;
+      H += Al * lv;
+    }
+  }
+  out[0] = (double)creall(H);
+  out[1] = (double)cimagl(H);
+}
+
+/* HSignature3d::calculateHSignature h_signature.h:282-353: x-y-t signature, one value per obstacle ("current" along the
+ * obstacle's constant-velocity world line, Biot-Savart integral along the trajectory, 10 steps per segment) */
+static void h_signature_3d(const TebParams* c, const double* rec, int n, const TebObstacle* obst, int M, int use_dt, double* out) {
+  for (int l = 0; l < M; ++l) {
+    double H = 0, transition_time = 0, next_transition_time = 0;
+    const double t = 120;
+    double s1[3] = {obst[l].x, obst[l].y, 0};
+    double s2[3] = {obst[l].x + t * obst[l].vx, obst[l].y + t * obst[l].vy, t};
+    double ds[3] = {s2[0] - s1[0], s2[1] - s1[1], s2[2] - s1[2]};
+    double ds2 = ds[0] * ds[0] + ds[1] * ds[1] + ds[2] * ds[2];
+    for (int k = 0; k + 1 < n; ++k) {
+      const double* z1 = rec + 4 * k;
+      const double* z2 = rec + 4 * (k + 1);
+      transition_time = next_transition_time;
+      if (!use_dt) next_transition_time += cabsl(((long double)z2[0] - z1[0]) + I * ((long double)z2[1] - z1[1])) / c->max_vel_x;
+      else next_transition_time += z1[3];
+      double dir[3] = {z2[0] - z1[0], z2[1] - z1[1], next_transition_time - transition_time};
+      if (sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]) < 1e-15) continue;
+      double r[3] = {z1[0], z1[1], transition_time};
+      double dl[3] = {0.1 * dir[0], 0.1 * dir[1], 0.1 * dir[2]}; /* 1.0 / num_int_steps_per_segment * direction_vec */
+      for (int i = 0; i < 10; ++i) {
+        double p1[3] = {s1[0] - r[0], s1[1] - r[1], s1[2] - r[2]};
+        double p2[3] = {s2[0] - r[0], s2[1] - r[1], s2[2] - r[2]};
+        double cr[3] = {p1[1] * p2[2] - p1[2] * p2[1], p1[2] * p2[0] - p1[0] * p2[2], p1[0] * p2[1] - p1[1] * p2[0]};
+        double d[3] = {(ds[1] * cr[2] - ds[2] * cr[1]) / ds2, (ds[2] * cr[0] - ds[0] * cr[2]) / ds2, (ds[0] * cr[1] - ds[1] * cr[0]) / ds2};
+        double n1 = sqrt(p1[0] * p1[0] + p1[1] * p1[1] + p1[2] * p1[2]), n2 = sqrt(p2[0] * p2[0] + p2[1] * p2[1] + p2[2] * p2[2]);
+        double dxp2[3] = {d[1] * p2[2] - d[2] * p2[1], d[2] * p2[0] - d[0] * p2[2], d[0] * p2[1] - d[1] * p2[0]};
+        double dxp1[3] = {d[1] * p1[2] - d[2] * p1[1], d[2] * p1[0] - d[0] * p1[2], d[0] * p1[1] - d[1] * p1[0]};
+        double inv = 1.0 / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        double phi[3];
+        for (int q = 0; q < 3; ++q) phi[q] = inv * (dxp2[q] / n2 - dxp1[q] / n1);
+        H += phi[0] * dl[0] + phi[1] * dl[1] + phi[2] * dl[2];
+        for (int q = 0; q < 3; ++q) r[q] += dl[q];
+      }
+    }
+    out[l] = H / (4.0 * M_PI);
+  }
+}
+
+int32_t teb_oracle_h_signature(const TebParams* cfg, const double* rec, int32_t n, const TebObstacle* obst, int32_t M,
+                               int32_t use_timediffs, double* out) {
+  if (!cfg || !rec || !out || n < 1) return -1;
+  if (cfg->include_dynamic_obstacles) h_signature_3d(cfg, rec, n, obst, M, use_timediffs, out);
+  else h_signature_2d(cfg, rec, n, obst, M, out);
+  return 0;
+}
+
 double teb_oracle_distance(const TebParams* cfg, const double* pose3, const TebObstacle* obst, const double* obst_vertices,
                            double t, double* grad3) {
   if (!generic_pair(cfg, obst)) {

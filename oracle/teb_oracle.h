@@ -79,6 +79,12 @@ int32_t teb_oracle_init_trajectory(const double* start3, const double* goal3, do
 double teb_oracle_distance(const TebParams* cfg, const double* pose3, const TebObstacle* obst, const double* obst_vertices,
                            double t, double* grad3);
 
+/* HomotopyClassPlanner::calculateEquivalenceClass (homotopy_class_planner.hpp:46-63) on the positions of one band:
+ * include_dynamic_obstacles == 0 -> HSignature::calculateHSignature (h_signature.h:97-186, long double accumulation),
+ * out[0..1] = (Re, Im); else HSignature3d::calculateHSignature (:282-353), out[0..M). use_timediffs as in the C-ABI. */
+int32_t teb_oracle_h_signature(const TebParams* cfg, const double* rec, int32_t n, const TebObstacle* obst, int32_t M,
+                               int32_t use_timediffs, double* out);
+
 /* helpers exposed for unit tests */
 double teb_oracle_normalize_theta(double t);
 double teb_oracle_average_angle(double a, double b);

@@ -60,6 +60,8 @@ def load_library(build_if_missing=False):
     L.tebgpu_get_kernel_times.argtypes = [vp, C.POINTER(C.c_double * 9), C.POINTER(C.c_int64 * 9)]
     L.tebgpu_compute_cost.restype = C.c_int32
     L.tebgpu_compute_cost.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs)]
+    L.tebgpu_h_signature.restype = C.c_int32
+    L.tebgpu_h_signature.argtypes = [vp, C.POINTER(abi.TebBatch), C.c_int32, vp, C.c_int32]
     L.tebgpu_build_system.restype = C.c_int32
     L.tebgpu_build_system.argtypes = [vp, C.POINTER(abi.TebBatch), C.c_int32, vp, vp, C.c_int32]
     L.tebgpu_select_best.restype = C.c_int32
@@ -98,6 +100,7 @@ class TebGpu:
 
     def set_params(self, params):
         self._check(self.lib.tebgpu_set_params(self.ctx, C.byref(params)), "tebgpu_set_params")
+        self.params = params
 
     def optimize(self, hb, args):
         """Host-buffer call: hb is an abi.HostBatch, updated in place."""
@@ -136,6 +139,16 @@ class TebGpu:
         names = ("k_begin", "k_auto_resize", "k_build_graph", "k_linearize", "k_lm_step_or_retry_rounds", "k_finalize",
                  "k_solve_tpb", "k_trial_eval", "unused")
         return {nme: (ms[i], cnt[i]) for i, nme in enumerate(names)}
+
+    def h_signature(self, hb, use_timediffs=True):
+        """calculateEquivalenceClass for every band: complex array [B] (2-D) or float array [B][M_cap] (x-y-t)"""
+        import numpy as np
+        three_d = bool(self.params.include_dynamic_obstacles) if hasattr(self, "params") else False
+        out = np.zeros((hb.B, max(hb.M_cap, 1) if three_d else 2))
+        bs = hb.struct()
+        self._check(self.lib.tebgpu_h_signature(self.ctx, C.byref(bs), int(use_timediffs), out.ctypes.data, 0),
+                    "tebgpu_h_signature")
+        return out if three_d else out[:, 0] + 1j * out[:, 1]
 
     def launch_count(self):
         return int(self.lib.tebgpu_last_launch_count(self.ctx))

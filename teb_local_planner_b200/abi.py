@@ -70,6 +70,7 @@ class TebParams(C.Structure):
         ("selection_cost_hysteresis", _d), ("selection_prefer_initial_plan", _d),
         ("selection_obst_cost_scale", _d), ("selection_viapoint_cost_scale", _d),
         ("selection_alternative_time_cost", _i), ("enable_multithreading", _i),
+        ("h_signature_prescaler", _d), ("h_signature_threshold", _d),
         # recovery
         ("divergence_detection_enable", _i), ("_pad4", _i),
         ("divergence_detection_max_chi_squared", _d),
@@ -139,6 +140,7 @@ def default_params() -> TebParams:
     p.selection_cost_hysteresis, p.selection_prefer_initial_plan = 1.0, 0.95
     p.selection_obst_cost_scale, p.selection_viapoint_cost_scale = 100.0, 1.0
     p.selection_alternative_time_cost, p.enable_multithreading = 0, 1
+    p.h_signature_prescaler, p.h_signature_threshold = 1.0, 0.1
     p.divergence_detection_enable, p.divergence_detection_max_chi_squared = 0, 10.0
     return p
 

@@ -13,6 +13,7 @@
 
 #include "teb_kernels.cuh"
 #include "teb_spec.cuh"
+#include "teb_hsig.cuh"
 #include <cstdlib>
 
 using namespace tebgpu;
@@ -134,6 +135,7 @@ void tebgpu_default_params(TebParams* p) {
   p->selection_cost_hysteresis = 1.0; p->selection_prefer_initial_plan = 0.95;
   p->selection_obst_cost_scale = 100.0; p->selection_viapoint_cost_scale = 1.0;
   p->selection_alternative_time_cost = 0; p->enable_multithreading = 1;
+  p->h_signature_prescaler = 1; p->h_signature_threshold = 0.1;
   p->divergence_detection_enable = 0; p->divergence_detection_max_chi_squared = 10;
 }
 
@@ -666,6 +668,42 @@ int32_t tebgpu_compute_cost(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimi
   if (bt->chi2) CUDA_TRY(ctx, cudaMemcpyAsync(bt->chi2, ctx->d_chi2, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (bt->status) CUDA_TRY(ctx, cudaMemcpyAsync(bt->status, ctx->d_status, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_h_signature(tebgpu_ctx* ctx, const TebBatch* bt, int32_t use_timediffs, double* h_out, int32_t device_ptrs) {
+  int32_t rc = check_batch(ctx, bt);
+  if (rc) return rc;
+  if (!h_out) return TEBGPU_ERR_INVALID_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  TebBatch d = *bt;
+  if (!device_ptrs) {
+    rc = upload_batch(ctx, bt);
+    if (rc) return rc;
+    d = mirror_batch(ctx, bt);
+  }
+  cudaStream_t st = ctx->stream;
+  DevBatch db = make_devbatch(ctx, &d);
+  KParams kp = make_kparams(ctx, bt, 1.0);
+  const int B = bt->B;
+  const bool three_d = ctx->params.include_dynamic_obstacles != 0; /* homotopy_class_planner.hpp:50 */
+  const size_t stride = three_d ? (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) : 2;
+  const size_t smem = hsig_smem_bytes(bt->n_cap, bt->M_cap);
+  if (smem > 232448) { ctx->err = "h-signature staging exceeds shared memory"; return TEBGPU_ERR_CAPACITY; }
+  double* d_out = device_ptrs ? h_out : ctx->Hb; /* the normal-equation workspace is free outside optimize calls */
+  if (three_d) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_hsig3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_hsig3d<<<B, HSIG_THREADS, smem, st>>>(db, kp, use_timediffs, d_out);
+  } else {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_hsig2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_hsig2d<<<B, HSIG_THREADS, smem, st>>>(db, kp, d_out);
+  }
+  ctx->launches = 1;
+  CUDA_TRY(ctx, cudaGetLastError());
+  if (!device_ptrs) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_out, d_out, (size_t)B * stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  }
   return TEBGPU_OK;
 }
 

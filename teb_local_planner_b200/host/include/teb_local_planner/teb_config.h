@@ -213,6 +213,7 @@ class TebConfig {
     p.selection_viapoint_cost_scale = hcp.selection_viapoint_cost_scale;
     p.selection_alternative_time_cost = hcp.selection_alternative_time_cost;
     p.enable_multithreading = hcp.enable_multithreading;
+    p.h_signature_prescaler = hcp.h_signature_prescaler; p.h_signature_threshold = hcp.h_signature_threshold;
     p.divergence_detection_enable = recovery.divergence_detection_enable;
     p.divergence_detection_max_chi_squared = recovery.divergence_detection_max_chi_squared;
     return p;

@@ -96,6 +96,21 @@ def distance(params, pose, obstacle, obst_vertices=None, t=0.0, want_grad=False)
     return (d, g) if want_grad else d
 
 
+def h_signature(params, rec, n, obstacles, use_timediffs=True):
+    """calculateEquivalenceClass on one band: complex H (2-D) or an array of M values (x-y-t)"""
+    L = lib()
+    L.teb_oracle_h_signature.restype = C.c_int32
+    L.teb_oracle_h_signature.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    rec = np.ascontiguousarray(rec[:n], dtype=np.float64)
+    ob = np.ascontiguousarray(obstacles, dtype=abi.OBST_DTYPE)
+    out = np.zeros(max(2, len(ob)))
+    rc = L.teb_oracle_h_signature(C.addressof(params), rec.ctypes.data, n, ob.ctypes.data if len(ob) else None, len(ob),
+                                  int(use_timediffs), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"teb_oracle_h_signature rc={rc}")
+    return out[:len(ob)].copy() if params.include_dynamic_obstacles else complex(out[0], out[1])
+
+
 def optimize_band(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=None, rotdir=0,
                   args=None, jac_mode=JAC_G2O, solver=SOLVER_BANDED, n_cap=None, obst_vertices=None):
     """One optimizeTEB on one band. Returns (rec[n_new], cost, stats)."""

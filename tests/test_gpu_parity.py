@@ -367,6 +367,40 @@ def test_bad_obstacle_rows_are_reported():
     g.close()
 
 
+@pytest.mark.parametrize("cfg,use_dt", [("C1", True), ("C2", True), ("C3", True), ("C4", True), ("C4", False)])
+def test_h_signatures_match_oracle(oracle, cfg, use_dt):
+    """calculateEquivalenceClass for a batch of candidates: 2-D signature (static scenes) against the long double
+    oracle to 1e-9 relative, x-y-t signature (include_dynamic_obstacles) to 1e-12 absolute; equal candidates map to
+    equal classes with the reference's isEqual rules (h_signature.h:191-207, :366-388)"""
+    p, hb = scenes.make_config_batch(cfg, candidates=12, seed=13)
+    if cfg != "C4":
+        p.include_dynamic_obstacles = 0
+    g = _gpu(hb, p)
+    got = g.h_signature(hb, use_timediffs=use_dt)
+    g.close()
+    obst = hb.obstacles[0][:hb.obst_count[0]]
+    ref = [oracle.h_signature(p, hb.poses[b], hb.n[b], obst, use_timediffs=use_dt) for b in range(hb.B)]
+    if p.include_dynamic_obstacles:
+        ref = np.array(ref)
+        assert np.abs(got[:, :len(obst)] - ref).max() < 1e-12
+        def equal(x, y):
+            keep = (np.abs(x) >= p.h_signature_threshold) & (np.abs(y) >= p.h_signature_threshold)
+            return bool(np.all(np.sign(x[keep]) == np.sign(y[keep])))
+        classes_g = [[equal(got[i, :len(obst)], got[j, :len(obst)]) for j in range(hb.B)] for i in range(hb.B)]
+        classes_r = [[equal(ref[i], ref[j]) for j in range(hb.B)] for i in range(hb.B)]
+    else:
+        ref = np.array(ref)
+        assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()
+        eq = lambda x, y: abs(x.real - y.real) <= p.h_signature_threshold and abs(x.imag - y.imag) <= p.h_signature_threshold
+        classes_g = [[eq(got[i], got[j]) for j in range(hb.B)] for i in range(hb.B)]
+        classes_r = [[eq(ref[i], ref[j]) for j in range(hb.B)] for i in range(hb.B)]
+    assert classes_g == classes_r
+    # with 20+ obstacles the 2-D signature shrinks below h_signature_threshold (the product in A_l, h_signature.h:149-163)
+    # and every candidate falls into one class - in the reference as well; the small scene and the x-y-t variant separate
+    if cfg in ("C1", "C4"):
+        assert not all(all(r) for r in classes_r)
+
+
 def test_solvers_and_speculation_widths_agree():
     """the three linear solvers give the same bands up to round-off; the speculation width K does not change a bit"""
     p, hb0 = scenes.make_config_batch("C4", candidates=12, seed=9)

@@ -393,3 +393,59 @@ def test_shape_obstacles_system_jacobians(oracle, footprint, legacy):
     flat["type"], flat["radius"] = abi.TEB_OBST_POINT, 0.0
     Hp, _, c2p = oracle.build_system(p, hb.poses[b], hb.n[b], flat, via=hb.via[b], jac_mode=1)
     assert abs(c2p - c2a) > 1e-6 or np.abs(Hp - Ha).max() > 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# H-signatures (h_signature.h): which candidates are the same homotopy class
+def _path(points):
+    rec = np.zeros((len(points), 4))
+    rec[:, :2] = points
+    rec[:-1, 3] = np.hypot(*np.diff(np.asarray(points, float), axis=0).T) / 0.4
+    return rec
+
+
+def test_h_signature_2d_known_answer(oracle):
+    """one obstacle: H = A (ln|z_end - o| - ln|z_start - o| + i * swept angle), A = prescaler * a (o - BL) * b (o - TR) with
+    a = 3, b = 2 (h_signature.h:119-123, :160); passing above sweeps -pi, below +pi"""
+    p = abi.default_params()
+    p.include_dynamic_obstacles = 0
+    ob = _ob(abi.TEB_OBST_POINT, 0.5, 0.2)
+    s = np.linspace(0, 1, 41)
+    above = _path(np.stack([-4 + 8 * s, 1.5 * np.sin(np.pi * s)], 1))
+    below = _path(np.stack([-4 + 8 * s, -1.5 * np.sin(np.pi * s)], 1))
+    o = complex(0.5, 0.2)
+    start, end = complex(-4, 0), complex(4, 0)
+    normal = complex(0, 8)
+    A = 1.0 * 3 * (o - (start - normal)) * 2 * (o - (start + (end - start) + normal))
+    lr = np.log(abs(end - o)) - np.log(abs(start - o))
+    for path, swept in ((above, None), (below, None)):
+        ang = np.unwrap(np.angle((path[:, 0] + 1j * path[:, 1]) - o))
+        want = A * complex(lr, ang[-1] - ang[0])
+        got = oracle.h_signature(p, path, len(path), ob)
+        assert abs(got - want) <= 1e-12 * abs(want)
+    ha, hb = oracle.h_signature(p, above, len(above), ob), oracle.h_signature(p, below, len(below), ob)
+    assert abs(ha - hb) > p.h_signature_threshold                   # different classes
+    wiggle = above.copy()
+    wiggle[1:-1, 1] += 0.2
+    assert abs(oracle.h_signature(p, wiggle, len(wiggle), ob) - ha) < 1e-9 * abs(ha)   # same class: same signature
+    assert oracle.h_signature(p, above, len(above), np.zeros(0, abi.OBST_DTYPE)) == 0
+
+
+def test_h_signature_3d_properties(oracle):
+    """x-y-t signature (h_signature.h:282-353): sign = side of the obstacle (positive: obstacle on the left), |H| < 1 without
+    a loop, far obstacles ~ 0; the sign test of isEqual (:366-388) separates above / below"""
+    p = abi.default_params()
+    p.include_dynamic_obstacles = 1
+    obs = np.concatenate([_ob(abi.TEB_OBST_POINT, 0.0, 0.0), _ob(abi.TEB_OBST_POINT, 1.0, 40.0),
+                          _ob(abi.TEB_OBST_POINT, -1.0, 0.5, vx=0.05, vy=-0.02, dynamic=1)])
+    s = np.linspace(0, 1, 41)
+    above = _path(np.stack([-4 + 8 * s, 1.5 * np.sin(np.pi * s)], 1))
+    below = _path(np.stack([-4 + 8 * s, -1.5 * np.sin(np.pi * s)], 1))
+    ha, hb = oracle.h_signature(p, above, len(above), obs), oracle.h_signature(p, below, len(below), obs)
+    assert ha[0] < -p.h_signature_threshold and hb[0] > p.h_signature_threshold     # passing above: obstacle on the right
+    assert np.all(np.abs(ha) < 1) and np.all(np.abs(hb) < 1)
+    assert abs(ha[1]) < 0.02 and abs(hb[1]) < 0.02                                  # obstacle 40 m away
+    assert abs(ha[0] + hb[0]) < 1e-12                                               # mirror paths, static obstacle on the axis
+    # without time information the transition times are |dz| / max_vel_x (:309-310) = the dt of this synthetic path
+    hn = oracle.h_signature(p, above, len(above), obs, use_timediffs=False)
+    assert np.allclose(hn, ha, rtol=0, atol=1e-12)
