@@ -5,16 +5,18 @@
  * Mirrors teb_local_planner::HomotopyClassPlanner (include/teb_local_planner/homotopy_class_planner.h:108-560,
  * src/homotopy_class_planner.cpp): plan() = updateAllTEBs -> exploreEquivalenceClassesAndInitTebs -> via-points ->
  * optimizeAllTEBs -> selectBestTeb (:107-125). optimizeAllTEBs (:466-493) and selectBestTeb (:564-667) are the
- * hot-path rows; the graph search / H-signature exploration (graph_search.cpp, h_signature.h) that decides WHICH
- * candidates exist is out of scope for this round: exploreEquivalenceClassesAndInitTebs keeps
- * the existing candidates and makes sure at least one band exists; further candidates are seeded by the caller with
- * addAndInitNewTeb().
+ * hot-path rows. The equivalence classes of the candidates (H-signatures, h_signature.h) are computed for ALL candidates
+ * in one device call and filtered with the reference's first-come-first-serve rule (renewAndAnalyzeOldTebs :214-256,
+ * addEquivalenceClassIfNew :189-211). The graph search that PROPOSES new candidates (graph_search.cpp: lrKeyPointGraph /
+ * ProbRoadmapGraph + depth-first enumeration) is not built: further candidates are seeded by the caller with
+ * addAndInitNewTeb(), which keeps a candidate only if its class is new.
  */
 #ifndef TEB_B200_HOMOTOPY_CLASS_PLANNER_H_
 #define TEB_B200_HOMOTOPY_CLASS_PLANNER_H_
 
 #include <chrono>
 
+#include "teb_local_planner/h_signature.h"
 #include "teb_local_planner/optimal_planner.h"
 
 namespace teb_local_planner {
@@ -47,6 +49,16 @@ class HomotopyClassPlanner : public PlannerInterface {
   void optimizeAllTEBs(int iter_innerloop, int iter_outerloop);
   TebOptimalPlannerPtr getInitialPlanTEB();
   TebOptimalPlannerPtr selectBestTeb();
+  /* equivalence classes (homotopy_class_planner.h:388-520 of the reference) */
+  std::vector<EquivalenceClassPtr> calculateEquivalenceClasses(const std::vector<TebOptimalPlanner*>& planners);
+  EquivalenceClassPtr calculateEquivalenceClass(TebOptimalPlanner* planner);
+  bool addEquivalenceClassIfNew(const EquivalenceClassPtr& eq_class, bool lock = false);
+  bool hasEquivalenceClass(const EquivalenceClassPtr& eq_class) const;
+  bool isInBestTebClass(const EquivalenceClassPtr& eq_class) const;
+  int numTebsInClass(const EquivalenceClassPtr& eq_class) const;
+  int numTebsInBestTebClass() const;
+  void renewAndAnalyzeOldTebs(bool delete_detours);
+  const EquivalenceClassContainer& getEquivalenceClassRef() const { return equivalence_classes_; }
   void clearPlanner() override;
   void setPreferredTurningDir(RotType dir) override;
   const TebOptPlannerContainer& getTrajectoryContainer() const { return tebs_; }
@@ -74,6 +86,9 @@ class HomotopyClassPlanner : public PlannerInterface {
   RobotFootprintModelPtr robot_model_;
   const std::vector<geometry_msgs::PoseStamped>* initial_plan_ = nullptr;
   TebOptPlannerContainer tebs_;
+  EquivalenceClassContainer equivalence_classes_;
+  EquivalenceClassPtr best_teb_eq_class_;
+  EquivalenceClassPtr initial_plan_eq_class_;
   std::chrono::steady_clock::time_point last_eq_class_switching_time_;
   bool initialized_ = false;
   TebGpuContextPtr gpu_;

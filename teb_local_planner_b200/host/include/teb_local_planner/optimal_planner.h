@@ -109,11 +109,14 @@ class TebOptimalPlanner : public PlannerInterface {
   double lastChi2() const { return chi2_; }
   /* used by HomotopyClassPlanner::optimizeAllTEBs to optimise all candidates in one batched call */
   friend class HomotopyClassPlanner;
+  /* calculateEquivalenceClass for several planners in one device call: values[k] = (Re, Im) or one value per obstacle */
+  static bool hSignatureBatch(const TebConfig& cfg, const std::vector<TebOptimalPlanner*>& planners,
+                              std::shared_ptr<TebGpuContext> gpu, std::vector<std::vector<double>>& values);
   /* shared implementation of optimizeTebBatch / computeCurrentCost: packs the planners into one TebBatch */
   static bool runBatch(const TebConfig& cfg, const std::vector<TebOptimalPlanner*>& planners, int iterations_innerloop,
                        int iterations_outerloop, bool compute_cost_afterwards, double obst_cost_scale,
                        double viapoint_cost_scale, bool alternative_time_cost, std::shared_ptr<TebGpuContext> gpu,
-                       bool cost_only);
+                       bool cost_only, std::vector<std::vector<double>>* hsig_out = nullptr);
 
  protected:
   const TebConfig* cfg_ = nullptr;

@@ -61,13 +61,89 @@ bool HomotopyClassPlanner::getVelocityCommand(double& vx, double& vy, double& om
   return best_teb->getVelocityCommand(vx, vy, omega, look_ahead_poses);
 }
 
-/* :337-357 — exploration of NEW homotopy classes (graph search + H-signatures) is not part of this round; the
- * existing candidates are kept and a first band is created from the initial plan or the straight line. */
+/* ------------------------------------------------------------------ equivalence classes
+ * calculateEquivalenceClass (homotopy_class_planner.hpp:46-63) for a set of candidates = ONE tebgpu_h_signature call */
+std::vector<EquivalenceClassPtr> HomotopyClassPlanner::calculateEquivalenceClasses(const std::vector<TebOptimalPlanner*>& planners) {
+  std::vector<EquivalenceClassPtr> out(planners.size());
+  if (planners.empty()) return out;
+  std::vector<std::vector<double>> values;
+  if (!TebOptimalPlanner::hSignatureBatch(*cfg_, planners, gpu_, values)) return out; /* null classes: never "new" (:191) */
+  for (size_t k = 0; k < planners.size(); ++k) {
+    if (cfg_->obstacles.include_dynamic_obstacles) out[k] = EquivalenceClassPtr(new HSignature3d(*cfg_, values[k]));
+    else out[k] = EquivalenceClassPtr(new HSignature(*cfg_, std::complex<double>(values[k][0], values[k][1])));
+  }
+  return out;
+}
+EquivalenceClassPtr HomotopyClassPlanner::calculateEquivalenceClass(TebOptimalPlanner* planner) {
+  return calculateEquivalenceClasses(std::vector<TebOptimalPlanner*>(1, planner))[0];
+}
+
+/* :178-187 */
+bool HomotopyClassPlanner::hasEquivalenceClass(const EquivalenceClassPtr& eq_class) const {
+  for (const std::pair<EquivalenceClassPtr, bool>& eqrel : equivalence_classes_)
+    if (eq_class->isEqual(*eqrel.first)) return true;
+  return false;
+}
+/* :387-412 */
+bool HomotopyClassPlanner::isInBestTebClass(const EquivalenceClassPtr& eq_class) const {
+  return best_teb_eq_class_ ? best_teb_eq_class_->isEqual(*eq_class) : false;
+}
+int HomotopyClassPlanner::numTebsInClass(const EquivalenceClassPtr& eq_class) const {
+  int count = 0;
+  for (const std::pair<EquivalenceClassPtr, bool>& eqrel : equivalence_classes_)
+    if (eq_class->isEqual(*eqrel.first)) ++count;
+  return count;
+}
+int HomotopyClassPlanner::numTebsInBestTebClass() const { return best_teb_eq_class_ ? numTebsInClass(best_teb_eq_class_) : 0; }
+
+/* :189-211 */
+bool HomotopyClassPlanner::addEquivalenceClassIfNew(const EquivalenceClassPtr& eq_class, bool lock) {
+  if (!eq_class) return false;
+  if (!eq_class->isValid()) return false; /* invalid H-signature: ignored */
+  if (hasEquivalenceClass(eq_class)) {
+    /* up to max_number_plans_in_current_class bands may share the class of the current best band */
+    if (!isInBestTebClass(eq_class) || numTebsInBestTebClass() >= cfg_->hcp.max_number_plans_in_current_class) return false;
+  }
+  equivalence_classes_.push_back(std::make_pair(eq_class, lock));
+  return true;
+}
+
+/* :214-256: signatures of all existing bands (one device call), then first come first serve with the last best band
+ * first; bands whose class is already taken are dropped. deletePlansDetouringBackwards (:766-801) is not built. */
+void HomotopyClassPlanner::renewAndAnalyzeOldTebs(bool delete_detours) {
+  (void)delete_detours;
+  equivalence_classes_.clear();
+  if (tebs_.empty()) return;
+  auto it_best_teb = best_teb_ ? std::find(tebs_.begin(), tebs_.end(), best_teb_) : tebs_.end();
+  const bool has_best_teb = it_best_teb != tebs_.end();
+  if (has_best_teb) std::iter_swap(tebs_.begin(), it_best_teb);
+  std::vector<TebOptimalPlanner*> all;
+  for (auto& teb : tebs_) all.push_back(teb.get());
+  std::vector<EquivalenceClassPtr> classes = calculateEquivalenceClasses(all);
+  size_t k = 0;
+  auto it_teb = tebs_.begin();
+  if (has_best_teb) {
+    best_teb_eq_class_ = classes[0];
+    addEquivalenceClassIfNew(best_teb_eq_class_);
+    ++it_teb; ++k;
+  }
+  while (it_teb != tebs_.end()) {
+    if (!addEquivalenceClassIfNew(classes[k++])) { it_teb = tebs_.erase(it_teb); continue; }
+    ++it_teb;
+  }
+}
+
+/* :337-357 — renew the classes of the existing bands, inject the initial plan, make sure one band exists. The graph
+ * search that proposes bands of further classes (graph_search_->createGraph) is not built. */
 void HomotopyClassPlanner::exploreEquivalenceClassesAndInitTebs(const PoseSE2& start, const PoseSE2& goal, double dist_to_obst,
                                                                 const geometry_msgs::Twist* start_vel, bool free_goal_vel) {
   (void)dist_to_obst;
-  if (initial_plan_ && !initial_plan_teb_) {
+  renewAndAnalyzeOldTebs(cfg_->hcp.delete_detours_backwards);
+  if (initial_plan_) {
     initial_plan_teb_ = addAndInitNewTeb(*initial_plan_, start_vel, free_goal_vel);
+  } else {
+    initial_plan_teb_.reset();
+    initial_plan_teb_ = getInitialPlanTEB();
   }
   if (tebs_.empty()) addAndInitNewTeb(start, goal, start_vel, free_goal_vel);
 }
@@ -83,8 +159,13 @@ TebOptimalPlannerPtr HomotopyClassPlanner::addAndInitNewTeb(const PoseSE2& start
                                         cfg_->trajectory.allow_init_with_backwards_motion);
   if (start_velocity) candidate->setVelocityStart(*start_velocity);
   if (free_goal_vel) candidate->setVelocityGoalFree();
-  tebs_.push_back(candidate);
-  return tebs_.back();
+  /* keep the candidate only if it opens a new class (:370-385) */
+  EquivalenceClassPtr H = calculateEquivalenceClass(candidate.get());
+  if (addEquivalenceClassIfNew(H)) {
+    tebs_.push_back(candidate);
+    return tebs_.back();
+  }
+  return TebOptimalPlannerPtr();
 }
 
 /* :414-441 */
@@ -99,8 +180,13 @@ TebOptimalPlannerPtr HomotopyClassPlanner::addAndInitNewTeb(const std::vector<ge
                                         cfg_->trajectory.allow_init_with_backwards_motion);
   if (start_velocity) candidate->setVelocityStart(*start_velocity);
   if (free_goal_vel) candidate->setVelocityGoalFree();
-  tebs_.push_back(candidate);
-  return tebs_.back();
+  /* the class of the initial plan is stored and locked (:430-440) */
+  initial_plan_eq_class_ = calculateEquivalenceClass(candidate.get());
+  if (addEquivalenceClassIfNew(initial_plan_eq_class_, true)) {
+    tebs_.push_back(candidate);
+    return tebs_.back();
+  }
+  return TebOptimalPlannerPtr();
 }
 
 /* :443-463 */
@@ -110,6 +196,7 @@ void HomotopyClassPlanner::updateAllTEBs(const PoseSE2* start, const PoseSE2* go
        std::fabs(g2o::normalize_theta(goal->theta() - tebs_.front()->teb().BackPose().theta())) >=
            cfg_->trajectory.force_reinit_new_goal_angular)) {
     tebs_.clear();
+    equivalence_classes_.clear();
     initial_plan_teb_.reset();
   }
   for (auto& teb : tebs_) {
@@ -127,12 +214,16 @@ void HomotopyClassPlanner::optimizeAllTEBs(int iter_innerloop, int iter_outerloo
                    cfg_->hcp.selection_viapoint_cost_scale, cfg_->hcp.selection_alternative_time_cost, gpu_);
 }
 
-/* :495-537 (equivalence-class lookup reduced to the stored pointer: no H-signatures in this round) */
+/* :495-537: the stored pointer if that band still exists, else the band whose class equals the initial plan's */
 TebOptimalPlannerPtr HomotopyClassPlanner::getInitialPlanTEB() {
   if (initial_plan_teb_) {
     if (std::find(tebs_.begin(), tebs_.end(), initial_plan_teb_) != tebs_.end()) return initial_plan_teb_;
     initial_plan_teb_.reset();
   }
+  if (!initial_plan_eq_class_ || equivalence_classes_.size() != tebs_.size()) return TebOptimalPlannerPtr();
+  auto teb_it = tebs_.begin();
+  for (auto it = equivalence_classes_.begin(); it != equivalence_classes_.end(); ++it, ++teb_it)
+    if (it->first->isEqual(*initial_plan_eq_class_)) return *teb_it;
   return TebOptimalPlannerPtr();
 }
 
@@ -182,13 +273,21 @@ int HomotopyClassPlanner::bestTebIdx() const {
 }
 
 TebOptPlannerContainer::iterator HomotopyClassPlanner::removeTeb(TebOptimalPlannerPtr& teb) {
-  for (auto it = tebs_.begin(); it != tebs_.end(); ++it)
-    if (*it == teb) return tebs_.erase(it);
+  /* classes and bands are parallel containers (:686-707) */
+  size_t idx = 0;
+  for (auto it = tebs_.begin(); it != tebs_.end(); ++it, ++idx)
+    if (*it == teb) {
+      if (equivalence_classes_.size() == tebs_.size()) equivalence_classes_.erase(equivalence_classes_.begin() + idx);
+      return tebs_.erase(it);
+    }
   return tebs_.end();
 }
 
 void HomotopyClassPlanner::clearPlanner() {
   tebs_.clear();
+  equivalence_classes_.clear();
+  best_teb_eq_class_.reset();
+  initial_plan_eq_class_.reset();
   best_teb_.reset();
   last_best_teb_.reset();
   initial_plan_teb_.reset();

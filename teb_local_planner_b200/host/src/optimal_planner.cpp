@@ -160,7 +160,7 @@ static int rotdir_code(RotType r) { return r == RotType::left ? TEB_ROTDIR_LEFT 
 
 bool TebOptimalPlanner::runBatch(const TebConfig& cfg, const std::vector<TebOptimalPlanner*>& planners, int iterations_innerloop,
                                  int iterations_outerloop, bool compute_cost_afterwards, double obst_cost_scale,
-                                 double viapoint_cost_scale, bool alternative_time_cost, TebGpuContextPtr gpu, bool cost_only) {
+                                 double viapoint_cost_scale, bool alternative_time_cost, TebGpuContextPtr gpu, bool cost_only, std::vector<std::vector<double>>* hsig_out) {
   const int B = (int)planners.size();
   if (B == 0) return true;
   /* capacities: autoResize may grow a band up to max_samples + 1 poses (timed_elastic_band.cpp:239) */
@@ -243,7 +243,7 @@ bool TebOptimalPlanner::runBatch(const TebConfig& cfg, const std::vector<TebOpti
     vel_goal[4 * b] = pl->vel_goal_.second.linear.x; vel_goal[4 * b + 1] = pl->vel_goal_.second.linear.y;
     vel_goal[4 * b + 2] = pl->vel_goal_.second.angular.z; vel_goal[4 * b + 3] = pl->vel_goal_.first ? 1.0 : 0.0;
     rotdir[b] = rotdir_code(pl->prefer_rotdir_);
-    if (!cost_only) pl->optimized_ = false;
+    if (!cost_only && !hsig_out) pl->optimized_ = false;
   }
   TebBatch bt{};
   bt.B = B; bt.n_cap = n_cap; bt.S = S; bt.M_cap = M_cap; bt.V_cap = V_max;
@@ -256,6 +256,22 @@ bool TebOptimalPlanner::runBatch(const TebConfig& cfg, const std::vector<TebOpti
   args.iterations_innerloop = iterations_innerloop; args.iterations_outerloop = iterations_outerloop;
   args.compute_cost_afterwards = compute_cost_afterwards; args.alternative_time_cost = alternative_time_cost;
   args.obst_cost_scale = obst_cost_scale; args.viapoint_cost_scale = viapoint_cost_scale;
+  if (hsig_out) { /* calculateEquivalenceClass for every planner: one device call */
+    const bool three_d = cfg.obstacles.include_dynamic_obstacles;
+    const size_t stride = three_d ? (size_t)M_cap : 2;
+    std::vector<double> h((size_t)B * stride, 0.0);
+    rc = tebgpu_h_signature(gpu->get(), &bt, /*use_timediffs=*/1, h.data(), 0);
+    if (rc != TEBGPU_OK) {
+      std::fprintf(stderr, "calculateEquivalenceClass: tebgpu_h_signature rc=%d (%s)\n", rc, tebgpu_last_error_string(gpu->get()));
+      return false;
+    }
+    hsig_out->assign(B, std::vector<double>());
+    for (int b = 0; b < B; ++b) {
+      const size_t cnt = three_d ? (size_t)obst_count[scene_id[b]] : 2;
+      (*hsig_out)[b].assign(h.begin() + (size_t)b * stride, h.begin() + (size_t)b * stride + cnt);
+    }
+    return true;
+  }
   if (cost_only) {
     rc = tebgpu_compute_cost(gpu->get(), &bt, &args);
     if (rc != TEBGPU_OK) {
@@ -279,6 +295,11 @@ bool TebOptimalPlanner::runBatch(const TebConfig& cfg, const std::vector<TebOpti
     if (pl->optimized_ && compute_cost_afterwards) pl->cost_ = cost[b];
   }
   return true;
+}
+
+bool TebOptimalPlanner::hSignatureBatch(const TebConfig& cfg, const std::vector<TebOptimalPlanner*>& planners,
+                                        std::shared_ptr<TebGpuContext> gpu, std::vector<std::vector<double>>& values) {
+  return runBatch(cfg, planners, 0, 0, false, 1.0, 1.0, false, gpu, true, &values);
 }
 
 bool optimizeTebBatch(const TebConfig& cfg, const std::vector<TebOptimalPlanner*>& planners, int iterations_innerloop,

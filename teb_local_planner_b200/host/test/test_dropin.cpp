@@ -179,8 +179,19 @@ static int gpu_checks() {
   auto p0 = sine_plan(0.0, 21), p1 = sine_plan(1.2, 21), p2 = sine_plan(-1.0, 21);
   hcp.addAndInitNewTeb(p1, NULL);
   hcp.addAndInitNewTeb(p2, NULL);
+  /* a second band of the class of p1 (same side of every obstacle) is not kept (addEquivalenceClassIfNew) */
+  auto dup = sine_plan(0.9, 21);
+  std::printf("HCP_DUP_REJECTED %d\n", hcp.addAndInitNewTeb(dup, NULL) ? 0 : 1);
   ok = hcp.plan(p0, NULL);  /* the initial-plan candidate is created by exploreEquivalenceClassesAndInitTebs */
   std::printf("HCP_OK %d\nHCP_NUM %d\nHCP_BEST %d\n", ok ? 1 : 0, (int)hcp.getTrajectoryContainer().size(), hcp.bestTebIdx());
+  {
+    int c = 0;
+    for (const auto& eq : hcp.getEquivalenceClassRef()) { /* signatures of the bands as they were when classified */
+      const HSignature* h = dynamic_cast<const HSignature*>(eq.first.get());
+      if (h) std::printf("HCP_H %d %.17g %.17g\n", c, h->value().real(), h->value().imag());
+      ++c;
+    }
+  }
   int k = 0;
   for (auto& t : hcp.getTrajectoryContainer()) {
     std::printf("HCP_COST %d %.17g\n", k, t->getCurrentCost());
@@ -211,7 +222,7 @@ static int gpu_checks() {
   }
   /* second cycle: hysteresis path of selectBestTeb + warm start of all candidates */
   ok = hcp.plan(PoseSE2(-3.95, 0, 0), PoseSE2(4, 0, 0), NULL);
-  std::printf("HCP2_OK %d\nHCP2_BEST %d\n", ok ? 1 : 0, hcp.bestTebIdx());
+  std::printf("HCP2_OK %d\nHCP2_BEST %d\nHCP2_NUM %d\n", ok ? 1 : 0, hcp.bestTebIdx(), (int)hcp.getTrajectoryContainer().size());
   return 0;
 }
 

@@ -132,7 +132,20 @@ def test_dropin_gpu_scenes_match_oracle(exe, oracle):
         plans.append(np.stack([-4 + 8 * s, amp * np.sin(np.pi * s), np.zeros(21)], axis=1))
     args = abi.make_args(5, 4, True, hp.selection_obst_cost_scale, hp.selection_viapoint_cost_scale, False)
     costs = []
-    assert vals["HCP_NUM"][0][0] == "3"
+    assert vals["HCP_NUM"][0][0] == "3" and vals["HCP_DUP_REJECTED"][0][0] == "1"
+    hp2d = abi.default_params()
+    hp2d.include_dynamic_obstacles = 0
+    for k, plan in enumerate(plans):        # equivalence classes: H-signatures of the bands as initialised from the plans
+        r0 = _init_from_plan(plan, hp.max_vel_x, hp.max_vel_theta)
+        href = oracle.h_signature(hp2d, r0, len(r0), hob)
+        hk = [v for v in vals["HCP_H"] if int(v[0]) == k][0]
+        assert abs(complex(float(hk[1]), float(hk[2])) - href) <= 1e-9 * abs(href)
+    dup = np.stack([-4 + 8 * np.linspace(0, 1, 21), 0.9 * np.sin(np.pi * np.linspace(0, 1, 21)), np.zeros(21)], axis=1)
+    rd = _init_from_plan(dup, hp.max_vel_x, hp.max_vel_theta)
+    r1 = _init_from_plan(plans[0], hp.max_vel_x, hp.max_vel_theta)
+    hd, h1 = oracle.h_signature(hp2d, rd, len(rd), hob), oracle.h_signature(hp2d, r1, len(r1), hob)
+    assert abs(hd.real - h1.real) <= hp.h_signature_threshold and abs(hd.imag - h1.imag) <= hp.h_signature_threshold
+    assert vals["HCP2_NUM"][0][0] == "3"
     for k, plan in enumerate(plans):
         r0 = _init_from_plan(plan, hp.max_vel_x, hp.max_vel_theta)
         ref_k, cost_k, _ = oracle.optimize_band(hp, r0, len(r0), hob, args=args, jac_mode=oracle.JAC_ANALYTIC, n_cap=512)
