@@ -1,8 +1,9 @@
 """Map ncu SASS-level stall samples to source lines via nvdisasm line info.
-usage: ncu_lines.py report.ncu-rep kernel_regex mangled_substr [top]   (cubin extracted from libteb_b200.so)"""
+usage: ncu_lines.py report.ncu-rep kernel_regex mangled_substr [top [skip]]   (cubin extracted from libteb_b200.so)"""
 import csv, io, subprocess, sys, collections, re, os, glob, tempfile
 rep, kre, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+skip = sys.argv[5] if len(sys.argv) > 5 else "0"   # matching launches to skip inside the report
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "teb_local_planner_b200", "libteb_b200.so")], cwd=tmp, capture_output=True)
@@ -23,7 +24,7 @@ for ln in dis.splitlines():
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/', ln)
     if m and cur:
         off2line[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre, "-c", "1"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre, "-s", skip, "-c", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = None; base = None
 agg = collections.Counter(); inst = collections.Counter()
