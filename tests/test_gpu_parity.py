@@ -223,6 +223,41 @@ def test_full_size_properties_c3():
     g.close()
 
 
+@pytest.mark.parametrize("B,n,M,moving,autosize", [(64, 50, 8, False, False), (96, 400, 256, False, False), (4096, 50, 8, True, False),
+                                                   (64, 400, 256, True, True), (512, 150, 32, True, False)])
+def test_c5_sweep_corners(oracle, B, n, M, moving, autosize):
+    """corners of the BASELINE C5 sweep (B 64-4096 x n 50-400 x M 8-256) and C4 at full size (B = 512): capacity paths
+    (13 tiles per band, 4-word association masks, speculation width fallback), two bands against the oracle, the rest
+    through size-independent properties"""
+    p = scenes.config_params("C4" if moving else "C3")
+    p.teb_autosize = int(autosize)
+    n_cap = min(512, n + 112) if autosize else n
+    hb0 = scenes.make_batch(n, M, candidates=min(B, 32), requests=max(1, B // 32), seed=17, inflated=not moving, moving=moving,
+                            via_points=4 if moving else 0, n_cap=n_cap)
+    assert hb0.B == B
+    args = abi.make_args(3, 2, True, 100.0, 1.0, False)
+    g = _gpu(hb0, p)
+    hg = hb0.copy()
+    g.optimize(hg, args)
+    h2 = hb0.copy()
+    g.optimize(h2, args)
+    g.close()
+    assert np.array_equal(hg.poses, h2.poses) and np.array_equal(hg.cost, h2.cost)          # deterministic
+    assert np.all(hg.status & abi.TEB_STATUS_OPTIMIZED) and np.all(np.isfinite(hg.cost))
+    for b in range(B):
+        assert np.array_equal(hg.poses[b, 0, :3], hb0.poses[b, 0, :3])
+        assert np.array_equal(hg.poses[b, hg.n[b] - 1, :3], hb0.poses[b, hb0.n[b] - 1, :3])
+    assert np.all(np.isfinite(hg.poses))
+    for b in (0, B - 1):
+        s = hb0.scene_id[b]
+        ref, cost, st = oracle.optimize_band(p, hb0.poses[b], hb0.n[b], hb0.obstacles[s][:hb0.obst_count[s]],
+                                             via=hb0.via[b] if hb0.V_cap else None, args=args, jac_mode=oracle.JAC_ANALYTIC,
+                                             n_cap=n_cap)
+        assert len(ref) == hg.n[b]
+        assert np.abs(ref - hg.poses[b, :hg.n[b]]).max() < 1e-6
+        assert abs(cost - hg.cost[b]) <= 1e-6 * max(abs(cost), 1.0)
+
+
 @pytest.mark.parametrize("legacy,vor", [(1, 0.0), (0, 2.0), (1, 2.0)])
 def test_legacy_association_and_velocity_obstacle_ratio(oracle, legacy, vor):
     """AddEdgesObstaclesLegacy (optimal_planner.cpp:551-643, incl. the triple edge on the centre pose) and
