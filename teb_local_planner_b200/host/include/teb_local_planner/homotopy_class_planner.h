@@ -63,6 +63,11 @@ class HomotopyClassPlanner : public PlannerInterface {
   void setPreferredTurningDir(RotType dir) override;
   const TebOptPlannerContainer& getTrajectoryContainer() const { return tebs_; }
   bool hasDiverged() const override;
+  /* homotopy_class_planner.cpp:686-707: checks the best band, drops it if infeasible and tries the next best */
+  bool isTrajectoryFeasible(base_local_planner::CostmapModel* costmap_model, const std::vector<geometry_msgs::Point>& footprint_spec,
+                            double inscribed_radius = 0.0, double circumscribed_radius = 0.0, int look_ahead_idx = -1,
+                            double feasibility_check_lookahead_distance = -1.0) override;
+  TebOptimalPlannerPtr findBestTeb();
   void computeCurrentCost(std::vector<double>& cost, double obst_cost_scale = 1.0, double viapoint_cost_scale = 1.0,
                           bool alternative_time_cost = false);
   void computeCurrentCost(std::vector<double>& cost, double obst_cost_scale, bool alternative_time_cost) override {

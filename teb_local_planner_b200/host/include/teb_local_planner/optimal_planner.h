@@ -6,7 +6,8 @@
  * src/optimal_planner.cpp): same class / method names, argument meaning and bool-return error behaviour.
  * Replaced: buildGraph/optimizeGraph/clearGraph and the g2o optimizer (optimal_planner.cpp:161-179, 323-418) —
  * the whole optimizeTEB loop is one tebgpu_optimize_batch call. Not available (documented in INTEGRATION.md):
- * optimizer() accessors (no g2o object exists), visualize(), isTrajectoryFeasible() (needs costmap_2d).
+ * optimizer() accessors (no g2o object exists) and visualize(). isTrajectoryFeasible() takes the costmap through the
+ * abstract base_local_planner::CostmapModel declared in pose_se2.h (costmap_2d itself is not part of this repository).
  */
 #ifndef TEB_B200_OPTIMAL_PLANNER_H_
 #define TEB_B200_OPTIMAL_PLANNER_H_
@@ -57,8 +58,20 @@ class PlannerInterface {
     (void)cost; (void)obst_cost_scale; (void)alternative_time_cost;
   }
   virtual bool hasDiverged() const = 0;
+  /* planner_interface.h:181 */
+  virtual bool isTrajectoryFeasible(base_local_planner::CostmapModel* costmap_model, const std::vector<geometry_msgs::Point>& footprint_spec,
+                                    double inscribed_radius = 0.0, double circumscribed_radius = 0.0, int look_ahead_idx = -1,
+                                    double feasibility_check_lookahead_distance = -1.0) = 0;
 };
 typedef std::shared_ptr<PlannerInterface> PlannerInterfacePtr;
+
+/* teb_local_planner/TrajectoryPointMsg (msg/TrajectoryPointMsg.msg) without ROS */
+struct TrajectoryPointMsg {
+  geometry_msgs::Pose pose;
+  geometry_msgs::Twist velocity;
+  geometry_msgs::Twist acceleration;
+  double time_from_start = 0; /* seconds */
+};
 
 class TebOptimalPlanner : public PlannerInterface {
  public:
@@ -101,6 +114,13 @@ class TebOptimalPlanner : public PlannerInterface {
   double getCurrentCost() const { return cost_; }
   inline void extractVelocity(const PoseSE2& pose1, const PoseSE2& pose2, double dt, double& vx, double& vy, double& omega) const;
   void getVelocityProfile(std::vector<geometry_msgs::Twist>& velocity_profile) const;
+  /* optimal_planner.cpp:1197-1244; TrajectoryPointMsg = pose, velocity, time_from_start [s] */
+  void getFullTrajectory(std::vector<TrajectoryPointMsg>& trajectory) const;
+  /* optimal_planner.cpp:1247-1306: costmap check of the first poses (+ interpolated poses where consecutive poses are
+   * farther apart than the inscribed radius / min_resolution_collision_check_angular) */
+  bool isTrajectoryFeasible(base_local_planner::CostmapModel* costmap_model, const std::vector<geometry_msgs::Point>& footprint_spec,
+                            double inscribed_radius = 0.0, double circumscribed_radius = 0.0, int look_ahead_idx = -1,
+                            double feasibility_check_lookahead_distance = -1.0) override;
   void clearGraph() {}
 
   /* --- additions of this implementation (not in the reference) --- */

@@ -48,6 +48,17 @@ struct Pose { Point position; Quaternion orientation; };
 struct PoseStamped { Pose pose; };
 }  // namespace geometry_msgs
 
+/* the one costmap query the planners make (isTrajectoryFeasible): base_local_planner::CostmapModel::footprintCost
+ * returns -1 for a footprint in collision / off the map. The caller plugs its own map in by deriving from this. */
+namespace base_local_planner {
+class CostmapModel {
+ public:
+  virtual ~CostmapModel() {}
+  virtual double footprintCost(double x, double y, double theta, const std::vector<geometry_msgs::Point>& footprint_spec,
+                               double inscribed_radius = 0.0, double circumscribed_radius = 0.0) = 0;
+};
+}  // namespace base_local_planner
+
 namespace tf {
 inline double getYaw(const geometry_msgs::Quaternion& q) {
   return std::atan2(2.0 * (q.w * q.z + q.x * q.y), 1.0 - 2.0 * (q.y * q.y + q.z * q.z));

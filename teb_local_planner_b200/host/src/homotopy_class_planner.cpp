@@ -298,6 +298,33 @@ void HomotopyClassPlanner::setPreferredTurningDir(RotType dir) {
   for (auto& teb : tebs_) teb->setPreferredTurningDir(dir);
 }
 
+/* :709-714 */
+TebOptimalPlannerPtr HomotopyClassPlanner::findBestTeb() {
+  if (tebs_.empty()) return TebOptimalPlannerPtr();
+  if (!best_teb_ || std::find(tebs_.begin(), tebs_.end(), best_teb_) == tebs_.end()) best_teb_ = selectBestTeb();
+  return best_teb_;
+}
+
+/* :686-707 */
+bool HomotopyClassPlanner::isTrajectoryFeasible(base_local_planner::CostmapModel* costmap_model,
+                                                const std::vector<geometry_msgs::Point>& footprint_spec, double inscribed_radius,
+                                                double circumscribed_radius, int look_ahead_idx,
+                                                double feasibility_check_lookahead_distance) {
+  bool feasible = false;
+  while (!feasible && !tebs_.empty()) {
+    TebOptimalPlannerPtr best = findBestTeb();
+    if (!best) return false;
+    feasible = best->isTrajectoryFeasible(costmap_model, footprint_spec, inscribed_radius, circumscribed_radius, look_ahead_idx,
+                                          feasibility_check_lookahead_distance);
+    if (!feasible) {
+      const bool same_as_before = last_best_teb_ && last_best_teb_ == best;
+      removeTeb(best);
+      if (same_as_before) return feasible; /* not failing here could make the robot oscillate between plans */
+    }
+  }
+  return feasible;
+}
+
 bool HomotopyClassPlanner::hasDiverged() const {
   if (!best_teb_) return false;
   return best_teb_->hasDiverged();

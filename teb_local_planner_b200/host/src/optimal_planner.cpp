@@ -384,3 +384,83 @@ void TebOptimalPlanner::getVelocityProfile(std::vector<geometry_msgs::Twist>& ve
 }
 
 }  // namespace teb_local_planner
+
+namespace teb_local_planner {
+
+/* optimal_planner.cpp:1197-1244 */
+void TebOptimalPlanner::getFullTrajectory(std::vector<TrajectoryPointMsg>& trajectory) const {
+  const int n = teb_.sizePoses();
+  trajectory.resize(n);
+  if (n == 0) return;
+  auto fill_pose = [](const PoseSE2& p, geometry_msgs::Pose& out) {
+    out.position.x = p.x(); out.position.y = p.y(); out.position.z = 0;
+    out.orientation = tf::createQuaternionFromYaw(p.theta());
+  };
+  double curr_time = 0;
+  fill_pose(teb_.Pose(0), trajectory.front().pose);
+  trajectory.front().velocity = geometry_msgs::Twist();
+  trajectory.front().velocity.linear.x = vel_start_.second.linear.x;
+  trajectory.front().velocity.linear.y = vel_start_.second.linear.y;
+  trajectory.front().velocity.angular.z = vel_start_.second.angular.z;
+  trajectory.front().time_from_start = curr_time;
+  if (n == 1) return;
+  curr_time += teb_.TimeDiff(0);
+  for (int i = 1; i < n - 1; ++i) { /* mean of the velocities of the two adjacent segments */
+    TrajectoryPointMsg& point = trajectory[i];
+    fill_pose(teb_.Pose(i), point.pose);
+    double v1x, v1y, w1, v2x, v2y, w2;
+    extractVelocity(teb_.Pose(i - 1), teb_.Pose(i), teb_.TimeDiff(i - 1), v1x, v1y, w1);
+    extractVelocity(teb_.Pose(i), teb_.Pose(i + 1), teb_.TimeDiff(i), v2x, v2y, w2);
+    point.velocity = geometry_msgs::Twist();
+    point.velocity.linear.x = 0.5 * (v1x + v2x);
+    point.velocity.linear.y = 0.5 * (v1y + v2y);
+    point.velocity.angular.z = 0.5 * (w1 + w2);
+    point.time_from_start = curr_time;
+    curr_time += teb_.TimeDiff(i);
+  }
+  fill_pose(teb_.BackPose(), trajectory.back().pose);
+  trajectory.back().velocity = geometry_msgs::Twist();
+  trajectory.back().velocity.linear.x = vel_goal_.second.linear.x;
+  trajectory.back().velocity.linear.y = vel_goal_.second.linear.y;
+  trajectory.back().velocity.angular.z = vel_goal_.second.angular.z;
+  trajectory.back().time_from_start = curr_time;
+}
+
+/* optimal_planner.cpp:1247-1306 */
+bool TebOptimalPlanner::isTrajectoryFeasible(base_local_planner::CostmapModel* costmap_model,
+                                             const std::vector<geometry_msgs::Point>& footprint_spec, double inscribed_radius,
+                                             double circumscribed_radius, int look_ahead_idx,
+                                             double feasibility_check_lookahead_distance) {
+  if (!costmap_model || !cfg_) return false;
+  if (look_ahead_idx < 0 || look_ahead_idx >= teb().sizePoses()) look_ahead_idx = teb().sizePoses() - 1;
+  if (feasibility_check_lookahead_distance > 0) {
+    for (int i = 1; i < teb().sizePoses(); ++i) {
+      const double d = std::hypot(teb().Pose(i).x() - teb().Pose(0).x(), teb().Pose(i).y() - teb().Pose(0).y());
+      if (d > feasibility_check_lookahead_distance) { look_ahead_idx = i - 1; break; }
+    }
+  }
+  for (int i = 0; i <= look_ahead_idx; ++i) {
+    const PoseSE2& pi = teb().Pose(i);
+    if (costmap_model->footprintCost(pi.x(), pi.y(), pi.theta(), footprint_spec, inscribed_radius, circumscribed_radius) == -1) return false;
+    if (i == look_ahead_idx) break;
+    /* two consecutive poses pushed apart by an obstacle may straddle it: sample in between */
+    const PoseSE2& pn = teb().Pose(i + 1);
+    const double delta_rot = g2o::normalize_theta(g2o::normalize_theta(pn.theta()) - g2o::normalize_theta(pi.theta()));
+    const Eigen::Vector2d delta_dist = pn.position() - pi.position();
+    const double ang_res = cfg_->trajectory.min_resolution_collision_check_angular;
+    if (std::fabs(delta_rot) > ang_res || delta_dist.norm() > inscribed_radius) {
+      const int n_additional_samples =
+          (int)std::max(std::ceil(std::fabs(delta_rot) / ang_res), std::ceil(delta_dist.norm() / inscribed_radius)) - 1;
+      PoseSE2 mid = pi;
+      for (int step = 0; step < n_additional_samples; ++step) {
+        mid.position() = mid.position() + delta_dist / (n_additional_samples + 1.0);
+        mid.theta() = g2o::normalize_theta(mid.theta() + delta_rot / (n_additional_samples + 1.0));
+        if (costmap_model->footprintCost(mid.x(), mid.y(), mid.theta(), footprint_spec, inscribed_radius, circumscribed_radius) == -1)
+          return false;
+      }
+    }
+  }
+  return true;
+}
+
+}  // namespace teb_local_planner

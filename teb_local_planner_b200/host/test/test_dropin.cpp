@@ -124,6 +124,42 @@ static void cpu_checks() {
   CHECK(fpp.footprint_type == TEB_FOOTPRINT_POLYGON && fpp.footprint_vertex_count == 4 && fpp.footprint_vertices[2] == 0.5);
 }
 
+/* costmap stand-in: a wall x in [lo, hi] is lethal */
+struct WallModel : public base_local_planner::CostmapModel {
+  double lo, hi;
+  int queries = 0;
+  WallModel(double l, double h) : lo(l), hi(h) {}
+  double footprintCost(double x, double, double, const std::vector<geometry_msgs::Point>&, double, double) override {
+    ++queries;
+    return (x >= lo && x <= hi) ? -1.0 : 1.0;
+  }
+};
+
+static void postprocessing_checks() {
+  /* getFullTrajectory / isTrajectoryFeasible (optimal_planner.cpp:1197-1306) on a hand-made band */
+  TebConfig cfg;
+  TebOptimalPlanner pl(cfg);
+  for (int i = 0; i < 5; ++i) {
+    if (i == 0) pl.teb().addPose(0, 0, 0);
+    else pl.teb().addPoseAndTimeDiff(0.5 * i, 0, 0, 1.0 + 0.5 * (i - 1)); /* dt = 1, 1.5, 2, 2.5 */
+  }
+  std::vector<TrajectoryPointMsg> traj;
+  pl.getFullTrajectory(traj);
+  CHECK(traj.size() == 5 && traj[0].time_from_start == 0 && std::fabs(traj[4].time_from_start - 7.0) < 1e-15);
+  CHECK(std::fabs(traj[1].velocity.linear.x - 0.5 * (0.5 / 1.0 + 0.5 / 1.5)) < 1e-15 && traj[4].velocity.linear.x == 0);
+  std::vector<geometry_msgs::Point> fp;
+  WallModel open_space(10, 11), wall(1.1, 1.2), far_wall(1.9, 2.1);
+  CHECK(pl.isTrajectoryFeasible(&open_space, fp, 0.6, 0.8, -1));
+  CHECK(open_space.queries == 5);                       /* poses 0.5 m apart, inscribed radius 0.6: no extra samples */
+  /* the wall lies between the poses at x = 1.0 and 1.5: only the two interpolated samples (inscribed radius 0.2:
+   * x = 1.167, 1.333) can see it */
+  CHECK(pl.isTrajectoryFeasible(&wall, fp, 0.6, 0.8, -1));
+  CHECK(!pl.isTrajectoryFeasible(&wall, fp, 0.2, 0.8, -1));
+  CHECK(!pl.isTrajectoryFeasible(&far_wall, fp, 0.6, 0.8, -1));
+  CHECK(pl.isTrajectoryFeasible(&far_wall, fp, 0.6, 0.8, 2));            /* look-ahead index stops before the wall */
+  CHECK(pl.isTrajectoryFeasible(&far_wall, fp, 0.6, 0.8, -1, 1.2));     /* look-ahead distance: poses up to x = 1.0 */
+}
+
 static void print_band(const char* key, const TimedElasticBand& teb) {
   std::printf("%s_N %d\n", key, teb.sizePoses());
   for (int i = 0; i < teb.sizePoses(); ++i)
@@ -228,6 +264,7 @@ static int gpu_checks() {
 
 int main(int argc, char** argv) {
   cpu_checks();
+  postprocessing_checks();
   if (argc > 1 && std::string(argv[1]) == "gpu") gpu_checks();
   std::printf("RESULT %s (%d failed checks)\n", g_fail ? "FAIL" : "PASS", g_fail);
   return g_fail ? 1 : 0;
