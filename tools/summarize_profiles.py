@@ -1,4 +1,4 @@
-"""Summarise ncu artefacts from gpurun_out/ into profiles/ (tracked). usage: summarize_profiles.py TAG launches.csv full.ncu-rep [B]"""
+"""Summarise ncu artefacts from gpurun_out/ into profiles/ (tracked). usage: summarize_profiles.py TAG launches.csv full.ncu-rep[,second.ncu-rep,...] [B]"""
 import csv, io, json, os, subprocess, sys, collections
 tag, launches_csv, rep = sys.argv[1], sys.argv[2], sys.argv[3]
 B = sys.argv[4] if len(sys.argv) > 4 else "?"
@@ -27,17 +27,21 @@ for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 with open(os.path.join(out_dir, f"{tag}_launches.csv"), "w") as f:
     f.write("".join(l for l in open(launches_csv) if l.startswith('"')))
 # ---- full capture: key metrics per kernel
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(io.StringIO(raw)))
-h = rr[0]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 traffic = {}
-lines.append(f"\n## full captures ({os.path.basename(rep)}; ncu --set full --clock-control none --import-source on)\n")
-for r in rr[2:]:
+lines.append(f"\n## full captures ({', '.join(os.path.basename(x) for x in rep.split(','))}; ncu --set full --clock-control none --import-source on)\n")
+all_rows = []
+for one in rep.split(","):
+    raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    for r in rr[2:]:
+        all_rows.append((rr[0], rr[1], r))
+for h, units, r in all_rows:
+    rr = [h, units]
     name = r[h.index("Kernel Name")].split("(")[0].replace("tebgpu::", "")
     lines.append(f"### {name}\n")
     vals = {}
