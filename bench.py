@@ -124,12 +124,13 @@ def algorithmic_bytes(n, M, V, B, K):
     """per band per LM iteration; N = 4n - 7 unknowns, band rows of 11 + rhs.
     a: kernel A (read poses/obstacles/via, write band + rhs + chi2); b: fused kernel B of solvers 0/1;
     s: k_solve_tpb round 0 (read band once per band, write + read the factor and write the solution per trial);
-    e: k_trial_eval round 0 (read K solutions, poses, rhs, obstacles; write K trial states)."""
+    e: k_trial_eval round 0 (read K solutions, poses, rhs, obstacles; write the accepted trial state).
+    Obstacle rows are 64 bytes (include/teb_b200.h TebObstacle)."""
     N = 4 * n - 7
-    a = 32 * n + 48 * M + 16 * V + 8 * (11 * N + N) + 8
-    b = 8 * 12 * N + 32 * n + 48 * M + 32 * n + 32
+    a = 32 * n + 64 * M + 16 * V + 8 * (11 * N + N) + 8
+    b = 8 * 12 * N + 32 * n + 64 * M + 32 * n + 32
     s = 96 * N + K * (2 * 96 * N + 8 * N)
-    e = K * 8 * N + 32 * n + 8 * N + 48 * M + K * 32 * n
+    e = K * 8 * N + 32 * n + 8 * N + 64 * M + 32 * n
     return a * B, b * B, s * B, e * B
 
 
