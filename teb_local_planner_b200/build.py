@@ -39,7 +39,7 @@ HOST_DIR = os.path.join(HERE, "host")
 HOST_LIB = os.path.join(HERE, "libteb_local_planner_b200.so")
 HOST_TEST = os.path.join(HOST_DIR, "test", "test_dropin")
 HOST_SRCS = [os.path.join(HOST_DIR, "src", f) for f in ("timed_elastic_band.cpp", "optimal_planner.cpp",
-                                                         "homotopy_class_planner.cpp")]
+                                                         "homotopy_class_planner.cpp", "graph_search.cpp")]
 
 
 def build_host(force=False, verbose=False):

@@ -7,15 +7,16 @@
  * optimizeAllTEBs -> selectBestTeb (:107-125). optimizeAllTEBs (:466-493) and selectBestTeb (:564-667) are the
  * hot-path rows. The equivalence classes of the candidates (H-signatures, h_signature.h) are computed for ALL candidates
  * in one device call and filtered with the reference's first-come-first-serve rule (renewAndAnalyzeOldTebs :214-256,
- * addEquivalenceClassIfNew :189-211). The graph search that PROPOSES new candidates (graph_search.cpp: lrKeyPointGraph /
- * ProbRoadmapGraph + depth-first enumeration) is not built: further candidates are seeded by the caller with
- * addAndInitNewTeb(), which keeps a candidate only if its class is new.
+ * addEquivalenceClassIfNew :189-211). New candidates are proposed by the graph search (graph_search.h: lrKeyPointGraph when
+ * hcp.simple_exploration, else ProbRoadmapGraph, + depth-first enumeration); a proposed path becomes a band only if its
+ * class is new (addAndInitNewTebs).
  */
 #ifndef TEB_B200_HOMOTOPY_CLASS_PLANNER_H_
 #define TEB_B200_HOMOTOPY_CLASS_PLANNER_H_
 
 #include <chrono>
 
+#include "teb_local_planner/graph_search.h"
 #include "teb_local_planner/h_signature.h"
 #include "teb_local_planner/optimal_planner.h"
 
@@ -42,6 +43,10 @@ class HomotopyClassPlanner : public PlannerInterface {
   /* homotopy_class_planner.cpp:359 (start/goal straight-line init) */
   TebOptimalPlannerPtr addAndInitNewTeb(const PoseSE2& start, const PoseSE2& goal, const geometry_msgs::Twist* start_velocity,
                                         bool free_goal_vel = false);
+  /* homotopy_class_planner.hpp:67-100 for a chunk of graph-search paths: bands initialised from the paths, ONE device call
+   * for their equivalence classes, accepted in order while fewer than max_number_classes bands exist. false = device error */
+  bool addAndInitNewTebs(const std::vector<std::vector<Eigen::Vector2d>>& paths, double start_orientation, double goal_orientation,
+                         const geometry_msgs::Twist* start_velocity, bool free_goal_vel = false);
   /* homotopy_class_planner.cpp:414 (init from a reference path) */
   TebOptimalPlannerPtr addAndInitNewTeb(const std::vector<geometry_msgs::PoseStamped>& initial_plan,
                                         const geometry_msgs::Twist* start_velocity, bool free_goal_vel = false);
@@ -94,6 +99,7 @@ class HomotopyClassPlanner : public PlannerInterface {
   EquivalenceClassContainer equivalence_classes_;
   EquivalenceClassPtr best_teb_eq_class_;
   EquivalenceClassPtr initial_plan_eq_class_;
+  std::shared_ptr<GraphSearchInterface> graph_search_;
   std::chrono::steady_clock::time_point last_eq_class_switching_time_;
   bool initialized_ = false;
   TebGpuContextPtr gpu_;

@@ -101,6 +101,9 @@ class Obstacle {
   virtual bool checkCollision(const Eigen::Vector2d& position, double min_dist) const {
     return getMinimumDistance(position) < min_dist;
   }
+  /* does the segment come closer than min_dist (Point / Circular) resp. cross the shape (Line / Pill / Polygon,
+   * which ignore min_dist like the reference: obstacles.h:339, :483, :647, :794; obstacles.cpp:176-191) */
+  virtual bool checkLineIntersection(const Eigen::Vector2d& line_start, const Eigen::Vector2d& line_end, double min_dist = 0) const = 0;
   virtual void predictCentroidConstantVelocity(double t, Eigen::Vector2d& position) const {
     position = getCentroid() + t * getCentroidVelocity();
   }
@@ -151,6 +154,13 @@ class PointObstacle : public Obstacle {
   double getMinimumSpatioTemporalDistance(const Point2dContainer& polygon, double t) const override {
     return distance_point_to_polygon_2d(pos_ + t * centroid_velocity_, polygon);
   }
+  bool checkLineIntersection(const Eigen::Vector2d& line_start, const Eigen::Vector2d& line_end, double min_dist = 0) const override {
+    /* nearest point of the segment to the centre (parameter clamped to [0, 1]), then the point test */
+    const Eigen::Vector2d a = line_end - line_start, b = pos_ - line_start;
+    double t = a.dot(b) / a.dot(a);
+    if (t < 0) t = 0; else if (t > 1) t = 1;
+    return checkCollision(line_start + a * t, min_dist);
+  }
   const Eigen::Vector2d& position() const { return pos_; }
   Eigen::Vector2d& position() { return pos_; }
   double& x() { return pos_.x(); }
@@ -181,6 +191,13 @@ class CircularObstacle : public Obstacle {
   }
   double getMinimumSpatioTemporalDistance(const Point2dContainer& polygon, double t) const override {
     return distance_point_to_polygon_2d(pos_ + t * centroid_velocity_, polygon) - radius_;
+  }
+  bool checkLineIntersection(const Eigen::Vector2d& line_start, const Eigen::Vector2d& line_end, double min_dist = 0) const override {
+    /* nearest point of the segment to the centre (parameter clamped to [0, 1]), then the point test */
+    const Eigen::Vector2d a = line_end - line_start, b = pos_ - line_start;
+    double t = a.dot(b) / a.dot(a);
+    if (t < 0) t = 0; else if (t > 1) t = 1;
+    return checkCollision(line_start + a * t, min_dist);
   }
   const Eigen::Vector2d& position() const { return pos_; }
   Eigen::Vector2d& position() { return pos_; }
@@ -227,6 +244,10 @@ class LineObstacle : public Obstacle {
   double getMinimumSpatioTemporalDistance(const Point2dContainer& polygon, double t) const override {
     const Eigen::Vector2d off = t * centroid_velocity_;
     return distance_segment_to_polygon_2d(verts_[0] + off, verts_[1] + off, polygon) - radius_;
+  }
+  bool checkLineIntersection(const Eigen::Vector2d& line_start, const Eigen::Vector2d& line_end, double min_dist = 0) const override {
+    (void)min_dist;
+    return check_line_segments_intersection_2d(line_start, line_end, verts_[0], verts_[1]);
   }
   const Eigen::Vector2d& start() const { return verts_[0]; }
   const Eigen::Vector2d& end() const { return verts_[1]; }
@@ -291,6 +312,13 @@ class PolygonObstacle : public Obstacle {
     }
     if (inside) return true;
     return min_dist == 0 ? false : getMinimumDistance(point) < min_dist;
+  }
+  bool checkLineIntersection(const Eigen::Vector2d& line_start, const Eigen::Vector2d& line_end, double min_dist = 0) const override {
+    (void)min_dist;
+    for (int i = 0; i + 1 < noVertices(); ++i)
+      if (check_line_segments_intersection_2d(line_start, line_end, verts_[i], verts_[i + 1])) return true;
+    if (noVertices() <= 2) return false;
+    return check_line_segments_intersection_2d(line_start, line_end, verts_.back(), verts_.front());
   }
   double getMinimumDistance(const Eigen::Vector2d& position) const override { return distance_point_to_polygon_2d(position, verts_); }
   double getMinimumDistance(const Eigen::Vector2d& a, const Eigen::Vector2d& b) const override {

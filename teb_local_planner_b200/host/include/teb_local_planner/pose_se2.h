@@ -34,6 +34,9 @@ struct Vector2d {
   double dot(const Vector2d& o) const { return v[0] * o.v[0] + v[1] * o.v[1]; }
   double squaredNorm() const { return v[0] * v[0] + v[1] * v[1]; }
   double norm() const { return std::sqrt(squaredNorm()); }
+  /* Eigen: divides by sqrt(squaredNorm()) if that is positive */
+  void normalize() { const double z = squaredNorm(); if (z > 0) { const double r = std::sqrt(z); v[0] /= r; v[1] /= r; } }
+  Vector2d normalized() const { Vector2d o(*this); o.normalize(); return o; }
   static Vector2d Zero() { return Vector2d(0, 0); }
 };
 inline Vector2d operator*(double s, const Vector2d& a) { return a * s; }

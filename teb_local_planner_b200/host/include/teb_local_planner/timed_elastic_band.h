@@ -60,6 +60,10 @@ class TimedElasticBand {
                             int min_samples = 3, bool guess_backwards_motion = false);
   bool initTrajectoryToGoal(const std::vector<geometry_msgs::PoseStamped>& plan, double max_vel_x, double max_vel_theta,
                             bool estimate_orient = false, int min_samples = 3, bool guess_backwards_motion = false);
+  /* timed_elastic_band.hpp:46-185: initialise from a 2-D path (graph-search candidates); optional values as pointers */
+  bool initTrajectoryToGoal(const std::vector<Eigen::Vector2d>& path, double max_vel_x, double max_vel_theta,
+                            const double* max_acc_x, const double* max_acc_theta, const double* start_orientation,
+                            const double* goal_orientation, int min_samples = 3, bool guess_backwards_motion = false);
   /* pointers instead of boost::optional<const PoseSE2&>; NULL = leave unchanged */
   void updateAndPruneTEB(const PoseSE2* new_start, const PoseSE2* new_goal, int min_samples = 3);
   void updateAndPruneTEB(const PoseSE2& new_start, const PoseSE2& new_goal, int min_samples = 3) {

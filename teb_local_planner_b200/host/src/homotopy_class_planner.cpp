@@ -21,6 +21,9 @@ void HomotopyClassPlanner::initialize(const TebConfig& cfg, ObstContainer* obsta
   via_points_ = via_points;
   visualization_ = visual;
   last_eq_class_switching_time_ = std::chrono::steady_clock::now();
+  /* :69-72 */
+  if (cfg_->hcp.simple_exploration) graph_search_ = std::shared_ptr<GraphSearchInterface>(new lrKeyPointGraph(*cfg_, this));
+  else graph_search_ = std::shared_ptr<GraphSearchInterface>(new ProbRoadmapGraph(*cfg_, this));
   initialized_ = true;
 }
 
@@ -133,8 +136,7 @@ void HomotopyClassPlanner::renewAndAnalyzeOldTebs(bool delete_detours) {
   }
 }
 
-/* :337-357 — renew the classes of the existing bands, inject the initial plan, make sure one band exists. The graph
- * search that proposes bands of further classes (graph_search_->createGraph) is not built. */
+/* :337-357 — renew the classes of the existing bands, inject the initial plan, explore further classes */
 void HomotopyClassPlanner::exploreEquivalenceClassesAndInitTebs(const PoseSE2& start, const PoseSE2& goal, double dist_to_obst,
                                                                 const geometry_msgs::Twist* start_vel, bool free_goal_vel) {
   (void)dist_to_obst;
@@ -145,7 +147,35 @@ void HomotopyClassPlanner::exploreEquivalenceClassesAndInitTebs(const PoseSE2& s
     initial_plan_teb_.reset();
     initial_plan_teb_ = getInitialPlanTEB();
   }
-  if (tebs_.empty()) addAndInitNewTeb(start, goal, start_vel, free_goal_vel);
+  graph_search_->createGraph(start, goal, dist_to_obst, cfg_->hcp.obstacle_heading_threshold, start_vel, free_goal_vel);
+}
+
+/* homotopy_class_planner.hpp:67-100, chunked */
+bool HomotopyClassPlanner::addAndInitNewTebs(const std::vector<std::vector<Eigen::Vector2d>>& paths, double start_orientation,
+                                             double goal_orientation, const geometry_msgs::Twist* start_velocity, bool free_goal_vel) {
+  if ((int)tebs_.size() >= cfg_->hcp.max_number_classes) return true;
+  std::vector<TebOptimalPlannerPtr> cands;
+  std::vector<TebOptimalPlanner*> raw;
+  for (const std::vector<Eigen::Vector2d>& path : paths) {
+    TebOptimalPlannerPtr candidate(new TebOptimalPlanner(*cfg_, obstacles_));
+    candidate->setGpuContext(gpu_);
+    if (robot_model_) candidate->updateRobotModel(robot_model_);
+    candidate->teb().initTrajectoryToGoal(path, cfg_->robot.max_vel_x, cfg_->robot.max_vel_theta, &cfg_->robot.acc_lim_x,
+                                          &cfg_->robot.acc_lim_theta, &start_orientation, &goal_orientation,
+                                          cfg_->trajectory.min_samples, cfg_->trajectory.allow_init_with_backwards_motion);
+    if (start_velocity) candidate->setVelocityStart(*start_velocity);
+    if (free_goal_vel) candidate->setVelocityGoalFree();
+    cands.push_back(candidate);
+    raw.push_back(candidate.get());
+  }
+  std::vector<EquivalenceClassPtr> classes = calculateEquivalenceClasses(raw);
+  bool ok = true;
+  for (size_t k = 0; k < cands.size(); ++k) {
+    if ((int)tebs_.size() >= cfg_->hcp.max_number_classes) break;
+    if (!classes[k]) { ok = false; break; }
+    if (addEquivalenceClassIfNew(classes[k])) tebs_.push_back(cands[k]);
+  }
+  return ok;
 }
 
 /* :359-386 */

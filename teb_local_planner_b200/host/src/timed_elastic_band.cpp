@@ -222,4 +222,56 @@ void TimedElasticBand::fromRecords(const double* rec, int n) {
   }
 }
 
+/* timed_elastic_band.hpp:46-185: poses on the path points, heading along the incoming segment, time per segment from a
+ * constant-velocity / constant-acceleration estimate; samples are added towards the goal until min_samples is met */
+bool TimedElasticBand::initTrajectoryToGoal(const std::vector<Eigen::Vector2d>& path, double max_vel_x, double max_vel_theta,
+                                            const double* max_acc_x, const double* max_acc_theta, const double* start_orientation,
+                                            const double* goal_orientation, int min_samples, bool guess_backwards_motion) {
+  (void)max_vel_theta; (void)max_acc_theta;
+  if (path.empty()) return false;
+  if (isInit()) return false;
+  const Eigen::Vector2d start_position = path.front(), goal_position = path.back();
+  bool backwards = false;
+  double start_orient;
+  if (start_orientation) {
+    start_orient = *start_orientation;
+    if (guess_backwards_motion &&
+        (goal_position - start_position).dot(Eigen::Vector2d(std::cos(start_orient), std::sin(start_orient))) < 0)
+      backwards = true;
+  } else {
+    const Eigen::Vector2d start2goal = goal_position - start_position;
+    start_orient = std::atan2(start2goal[1], start2goal[0]);
+  }
+  const double goal_orient = goal_orientation ? *goal_orientation : start_orient;
+  double timestep = 1;
+  auto segment_time = [&](double length) {
+    const double t_vel = length / max_vel_x;
+    if (max_acc_x) {
+      const double t_acc = std::sqrt(2 * length / (*max_acc_x));
+      return t_vel < t_acc ? t_acc : t_vel;
+    }
+    return t_vel;
+  };
+  addPose(PoseSE2(start_position, start_orient));
+  setPoseVertexFixed(0, true);
+  int idx = 0;
+  for (size_t k = 1; k + 1 < path.size(); ++k, ++idx) { /* middle points */
+    const Eigen::Vector2d diff_last = path[k] - Pose(idx).position();
+    timestep = segment_time(diff_last.norm());
+    if (timestep <= 0) timestep = 0.2;
+    double yaw = std::atan2(diff_last[1], diff_last[0]);
+    if (backwards) yaw = g2o::normalize_theta(yaw + M_PI);
+    addPoseAndTimeDiff(PoseSE2(path[k], yaw), timestep);
+  }
+  timestep = segment_time((goal_position - Pose(idx).position()).norm());
+  const PoseSE2 goal(goal_position, goal_orient);
+  while (sizePoses() < min_samples - 1) { /* each inserted pose bisects the remaining distance and time */
+    timestep /= 2;
+    addPoseAndTimeDiff(PoseSE2::average(BackPose(), goal), timestep);
+  }
+  addPoseAndTimeDiff(goal, timestep);
+  setPoseVertexFixed(sizePoses() - 1, true);
+  return true;
+}
+
 }  // namespace teb_local_planner

@@ -207,6 +207,7 @@ static int gpu_checks() {
   /* ---- HomotopyClassPlanner: three seeded candidates, one batched optimisation, selection */
   TebConfig hcfg;
   hcfg.obstacles.include_dynamic_obstacles = false;
+  hcfg.hcp.max_number_classes = 3; /* the three seeded classes fill the container: no graph search in this scene */
   ObstContainer hob;
   hob.push_back(ObstaclePtr(new PointObstacle(0, 0.1)));
   hob.push_back(ObstaclePtr(new PointObstacle(-1.5, -0.4)));
@@ -256,16 +257,65 @@ static int gpu_checks() {
     std::printf("SHAPES_OK %d\nSHAPES_STATUS %d\n", sok ? 1 : 0, sp.lastStatus());
     print_band("SHAPES", sp.teb());
   }
+  { /* ---- the whole cycle with nothing seeded: explore (key-point graph) -> one batched optimisation -> select */
+    TebConfig acfg;
+    acfg.hcp.simple_exploration = true;
+    acfg.obstacles.include_dynamic_obstacles = false;
+    acfg.hcp.max_number_classes = 4;
+    ObstContainer aob;
+    aob.push_back(ObstaclePtr(new PointObstacle(-1.5, 0.3)));
+    aob.push_back(ObstaclePtr(new CircularObstacle(0.5, -0.4, 0.3)));
+    aob.push_back(ObstaclePtr(new PointObstacle(2.0, 0.5)));
+    HomotopyClassPlanner ahcp(acfg, &aob);
+    bool aok = ahcp.plan(PoseSE2(-4, 0, 0.1), PoseSE2(4, 0.2, -0.2), NULL);
+    std::printf("AUTO_OK %d\nAUTO_NUM %d\nAUTO_BEST %d\n", aok ? 1 : 0, (int)ahcp.getTrajectoryContainer().size(), ahcp.bestTebIdx());
+    int q = 0;
+    for (auto& t : ahcp.getTrajectoryContainer()) {
+      std::printf("AUTO_COST %d %.17g\n", q, t->getCurrentCost());
+      char key[32];
+      std::snprintf(key, sizeof(key), "AUTO%d", q++);
+      print_band(key, t->teb());
+    }
+  }
   /* second cycle: hysteresis path of selectBestTeb + warm start of all candidates */
   ok = hcp.plan(PoseSE2(-3.95, 0, 0), PoseSE2(4, 0, 0), NULL);
   std::printf("HCP2_OK %d\nHCP2_BEST %d\nHCP2_NUM %d\n", ok ? 1 : 0, hcp.bestTebIdx(), (int)hcp.getTrajectoryContainer().size());
   return 0;
 }
 
+/* exploreEquivalenceClassesAndInitTebs alone (no optimisation): the candidate bands the graph search proposes */
+static void explore_checks() {
+  for (int variant = 0; variant < 4; ++variant) {
+    TebConfig cfg;
+    cfg.hcp.simple_exploration = (variant & 1) != 0;            /* 0: ProbRoadmapGraph, 1: lrKeyPointGraph */
+    cfg.obstacles.include_dynamic_obstacles = (variant & 2) != 0; /* 2-D signature / x-y-t signature */
+    cfg.hcp.max_number_classes = 6;
+    ObstContainer obst;
+    obst.push_back(ObstaclePtr(new PointObstacle(-1.5, 0.3)));
+    obst.push_back(ObstaclePtr(new CircularObstacle(0.5, -0.4, 0.3)));
+    obst.push_back(ObstaclePtr(new PointObstacle(2.0, 0.5)));
+    obst.push_back(ObstaclePtr(new LineObstacle(-3.0, -1.5, -2.5, -0.8)));
+    if (variant & 2) obst[2]->setCentroidVelocity(Eigen::Vector2d(-0.1, 0.05));
+    HomotopyClassPlanner hcp(cfg, &obst);
+    for (int cycle = 0; cycle < 2; ++cycle) { /* the second cycle starts from the kept bands and a continued random stream */
+      hcp.exploreEquivalenceClassesAndInitTebs(PoseSE2(-4, 0, 0.1), PoseSE2(4, 0.2, -0.2), cfg.obstacles.min_obstacle_dist, NULL);
+      std::printf("EXPLORE%d_%d_NUM %d\n", variant, cycle, (int)hcp.getTrajectoryContainer().size());
+      int k = 0;
+      for (auto& t : hcp.getTrajectoryContainer()) {
+        char key[40];
+        std::snprintf(key, sizeof(key), "EXPLORE%d_%d_%d", variant, cycle, k++);
+        print_band(key, t->teb());
+      }
+      if (cycle == 0) hcp.clearPlanner(); /* fresh container, random stream continues (member of the graph object) */
+    }
+  }
+}
+
 int main(int argc, char** argv) {
   cpu_checks();
   postprocessing_checks();
   if (argc > 1 && std::string(argv[1]) == "gpu") gpu_checks();
+  if (argc > 1 && std::string(argv[1]) == "explore") explore_checks();
   std::printf("RESULT %s (%d failed checks)\n", g_fail ? "FAIL" : "PASS", g_fail);
   return g_fail ? 1 : 0;
 }

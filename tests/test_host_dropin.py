@@ -157,6 +157,25 @@ def test_dropin_gpu_scenes_match_oracle(exe, oracle):
     from teb_local_planner_b200 import distributed as D
     assert int(vals["HCP_BEST"][0][0]) == D.select_best(costs, -1, 2, hp.selection_cost_hysteresis, hp.selection_prefer_initial_plan)
     assert vals["HCP2_OK"][0][0] == "1" and int(vals["HCP2_BEST"][0][0]) in (0, 1, 2)
+    # ---- nothing seeded: key-point graph exploration -> batched optimisation -> selection
+    from oracle import hcp_explore as X
+    ap = abi.default_params()
+    ap.include_dynamic_obstacles = 0
+    arows = np.zeros(3, abi.OBST_DTYPE)
+    arows["x"], arows["y"], arows["radius"] = [-1.5, 0.5, 2.0], [0.3, -0.4, 0.5], [0, 0.3, 0]
+    arows["type"] = [abi.TEB_OBST_POINT, abi.TEB_OBST_CIRCULAR, abi.TEB_OBST_POINT]
+    ex = X.Explorer(ap, {"max_number_classes": 4, "obstacle_heading_threshold": 0.45}, oracle, arows,
+                    [X.Obst("point", (-1.5, 0.3)), X.Obst("circle", (0.5, -0.4), 0.3), X.Obst("point", (2.0, 0.5))])
+    ex.lr_key_point_graph([-4, 0, 0.1], [4, 0.2, -0.2], ap.min_obstacle_dist)
+    assert vals["AUTO_OK"][0][0] == "1" and int(vals["AUTO_NUM"][0][0]) == len(ex.tebs) and len(ex.tebs) >= 3
+    aargs = abi.make_args(5, 4, True, ap.selection_obst_cost_scale, ap.selection_viapoint_cost_scale, False)
+    acosts = []
+    for k, r0 in enumerate(ex.tebs):
+        ref_k, cost_k, _ = oracle.optimize_band(ap, r0, len(r0), arows, args=aargs, jac_mode=oracle.JAC_ANALYTIC, n_cap=512)
+        got_k = bands[f"AUTO{k}"]
+        assert len(got_k) == len(ref_k) and np.abs(got_k - ref_k).max() < 1e-6, k
+        acosts.append(cost_k)
+    assert int(vals["AUTO_BEST"][0][0]) == int(np.argmin(acosts))
     # ---- polygon footprint among a line, a moving pill and a polygon obstacle
     from teb_local_planner_b200 import scenes
     sp = abi.default_params()
@@ -175,3 +194,39 @@ def test_dropin_gpu_scenes_match_oracle(exe, oracle):
     sgot = bands["SHAPES"]
     assert vals["SHAPES_OK"][0][0] == "1" and len(sgot) == len(sref)
     assert np.abs(sgot - sref).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_dropin_exploration_matches_sequential_restatement(exe, oracle):
+    """HomotopyClassPlanner::exploreEquivalenceClassesAndInitTebs with both graph searches (graph_search.cpp) and both
+    signature kinds: the chunked, batched C++ exploration proposes exactly the bands of the sequential restatement in
+    oracle/hcp_explore.py (same paths, same order, same initial trajectories)"""
+    from oracle import hcp_explore as X
+    out = subprocess.run([exe, "explore"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "RESULT PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    vals, bands = _parse(out.stdout)
+    for variant in range(4):
+        p = abi.default_params()
+        p.include_dynamic_obstacles = 1 if variant & 2 else 0
+        rows = np.zeros(4, abi.OBST_DTYPE)
+        rows["x"], rows["y"] = [-1.5, 0.5, 2.0, -2.75], [0.3, -0.4, 0.5, -1.15]
+        rows["radius"] = [0, 0.3, 0, 0]
+        rows["type"] = [abi.TEB_OBST_POINT, abi.TEB_OBST_CIRCULAR, abi.TEB_OBST_POINT, abi.TEB_OBST_LINE]
+        if variant & 2:
+            rows["vx"][2], rows["vy"][2], rows["dynamic"][2] = -0.1, 0.05, 1
+        obstacles = [X.Obst("point", (-1.5, 0.3)), X.Obst("circle", (0.5, -0.4), 0.3), X.Obst("point", (2.0, 0.5)),
+                     X.Obst("line", (-2.75, -1.15), vertices=[(-3.0, -1.5), (-2.5, -0.8)])]
+        hcp = {"max_number_classes": 6, "obstacle_heading_threshold": 0.45, "roadmap_graph_area_width": 6.0,
+               "roadmap_graph_area_length_scale": 1.0, "roadmap_graph_no_samples": 15}
+        ex = X.Explorer(p, hcp, oracle, rows, obstacles)
+        for cycle in range(2):
+            ex.classes, ex.tebs = [], []
+            if variant & 1:
+                ex.lr_key_point_graph([-4, 0, 0.1], [4, 0.2, -0.2], p.min_obstacle_dist)
+            else:
+                ex.prob_roadmap_graph([-4, 0, 0.1], [4, 0.2, -0.2], p.min_obstacle_dist)
+            num = int(vals[f"EXPLORE{variant}_{cycle}_NUM"][0][0])
+            assert num == len(ex.tebs) and num >= 2, (variant, cycle, num, len(ex.tebs))
+            for k, ref in enumerate(ex.tebs):
+                got = bands[f"EXPLORE{variant}_{cycle}_{k}"]
+                assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-12, (variant, cycle, k)

@@ -449,3 +449,23 @@ def test_h_signature_3d_properties(oracle):
     # without time information the transition times are |dz| / max_vel_x (:309-310) = the dt of this synthetic path
     hn = oracle.h_signature(p, above, len(above), obs, use_timediffs=False)
     assert np.allclose(hn, ha, rtol=0, atol=1e-12)
+
+
+def test_exploration_restatement_pieces():
+    """oracle/hcp_explore.py: mt19937 known answers (first draw, the standard's 10000th value), the path initialisation
+    against a hand evaluation (timed_elastic_band.hpp:46-185), segment intersection corner cases"""
+    from oracle import hcp_explore as X
+    m = X.MT19937()
+    xs = [m() for _ in range(10000)]
+    assert xs[0] == 3499211612 and xs[-1] == 4123659995
+    rec = X.init_from_path([(0, 0), (1, 0), (1, 2)], max_vel_x=0.4, acc_lim_x=0.5, start_orient=0.3, goal_orient=-0.2,
+                           min_samples=3, guess_backwards=False)
+    assert rec.shape == (3, 4)
+    assert np.allclose(rec[:, :3], [[0, 0, 0.3], [1, 0, 0.0], [1, 2, -0.2]])
+    assert np.allclose(rec[:2, 3], [max(1 / 0.4, np.sqrt(2 * 1 / 0.5)), max(2 / 0.4, np.sqrt(2 * 2 / 0.5))])
+    short = X.init_from_path([(0, 0), (1, 0)], 0.4, 0.5, 0.0, 0.0, min_samples=4, guess_backwards=False)
+    assert len(short) == 4 and np.allclose(short[:, 0], [0, 0.5, 0.75, 1.0]) and np.allclose(short[:3, 3], [1.25, 0.625, 0.625])
+    a = np.array
+    assert X._segments_intersect(a([0., 0]), a([1., 1]), a([0., 1]), a([1., 0]))
+    assert not X._segments_intersect(a([0., 0]), a([1., 0]), a([0., 1]), a([1., 1]))       # parallel
+    assert not X._segments_intersect(a([0., 0]), a([1., 0]), a([2., -1]), a([2., 1]))      # beyond the end
