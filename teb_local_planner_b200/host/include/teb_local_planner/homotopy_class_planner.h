@@ -15,6 +15,7 @@
 #define TEB_B200_HOMOTOPY_CLASS_PLANNER_H_
 
 #include <chrono>
+#include <random>
 
 #include "teb_local_planner/graph_search.h"
 #include "teb_local_planner/h_signature.h"
@@ -63,6 +64,12 @@ class HomotopyClassPlanner : public PlannerInterface {
   int numTebsInClass(const EquivalenceClassPtr& eq_class) const;
   int numTebsInBestTebClass() const;
   void renewAndAnalyzeOldTebs(bool delete_detours);
+  /* :766-838: drop bands that start against the current direction of motion, could not be optimised or take much longer
+   * than the best band */
+  void deletePlansDetouringBackwards(const double orient_threshold, const double len_orientation_vector);
+  bool computeStartOrientation(const TebOptimalPlannerPtr plan, const double len_orientation_vector, double& orientation);
+  /* :539-562: with probability selection_dropping_probability a band other than the best is dropped (default 0) */
+  void randomlyDropTebs();
   const EquivalenceClassContainer& getEquivalenceClassRef() const { return equivalence_classes_; }
   void clearPlanner() override;
   void setPreferredTurningDir(RotType dir) override;
@@ -100,6 +107,7 @@ class HomotopyClassPlanner : public PlannerInterface {
   EquivalenceClassPtr best_teb_eq_class_;
   EquivalenceClassPtr initial_plan_eq_class_;
   std::shared_ptr<GraphSearchInterface> graph_search_;
+  std::default_random_engine random_;
   std::chrono::steady_clock::time_point last_eq_class_switching_time_;
   bool initialized_ = false;
   TebGpuContextPtr gpu_;

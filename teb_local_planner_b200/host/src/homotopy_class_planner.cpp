@@ -21,6 +21,8 @@ void HomotopyClassPlanner::initialize(const TebConfig& cfg, ObstContainer* obsta
   via_points_ = via_points;
   visualization_ = visual;
   last_eq_class_switching_time_ = std::chrono::steady_clock::now();
+  std::random_device rd; /* :73 */
+  random_.seed(rd());
   /* :69-72 */
   if (cfg_->hcp.simple_exploration) graph_search_ = std::shared_ptr<GraphSearchInterface>(new lrKeyPointGraph(*cfg_, this));
   else graph_search_ = std::shared_ptr<GraphSearchInterface>(new ProbRoadmapGraph(*cfg_, this));
@@ -112,9 +114,8 @@ bool HomotopyClassPlanner::addEquivalenceClassIfNew(const EquivalenceClassPtr& e
 }
 
 /* :214-256: signatures of all existing bands (one device call), then first come first serve with the last best band
- * first; bands whose class is already taken are dropped. deletePlansDetouringBackwards (:766-801) is not built. */
+ * first; bands whose class is already taken are dropped */
 void HomotopyClassPlanner::renewAndAnalyzeOldTebs(bool delete_detours) {
-  (void)delete_detours;
   equivalence_classes_.clear();
   if (tebs_.empty()) return;
   auto it_best_teb = best_teb_ ? std::find(tebs_.begin(), tebs_.end(), best_teb_) : tebs_.end();
@@ -134,6 +135,60 @@ void HomotopyClassPlanner::renewAndAnalyzeOldTebs(bool delete_detours) {
     if (!addEquivalenceClassIfNew(classes[k++])) { it_teb = tebs_.erase(it_teb); continue; }
     ++it_teb;
   }
+  if (delete_detours)
+    deletePlansDetouringBackwards(cfg_->hcp.detours_orientation_tolerance, cfg_->hcp.length_start_orientation_vector);
+}
+
+/* :803-838: direction from the first pose that is farther than len_orientation_vector from the start, to the start */
+bool HomotopyClassPlanner::computeStartOrientation(const TebOptimalPlannerPtr plan, const double len_orientation_vector,
+                                                   double& orientation) {
+  const PoseSE2 start_pose = plan->teb().Pose(0);
+  Eigen::Vector2d start_vector;
+  bool second_pose_found = false;
+  for (int i = 0; i < plan->teb().sizePoses(); ++i) {
+    start_vector = start_pose.position() - plan->teb().Pose(i).position();
+    if (start_vector.norm() > len_orientation_vector) { second_pose_found = true; break; }
+  }
+  if (!second_pose_found) return false; /* too short to tell */
+  orientation = std::atan2(start_vector[1], start_vector[0]);
+  return true;
+}
+
+/* :766-801 */
+void HomotopyClassPlanner::deletePlansDetouringBackwards(const double orient_threshold, const double len_orientation_vector) {
+  if (tebs_.size() < 2 || !best_teb_ || std::find(tebs_.begin(), tebs_.end(), best_teb_) == tebs_.end() ||
+      best_teb_->teb().sizePoses() < 2)
+    return; /* no direction of motion chosen yet */
+  double current_movement_orientation;
+  const double best_plan_duration = std::max(best_teb_->teb().getSumOfAllTimeDiffs(), 1.0);
+  if (!computeStartOrientation(best_teb_, len_orientation_vector, current_movement_orientation)) return;
+  for (auto it_teb = tebs_.begin(); it_teb != tebs_.end();) {
+    if (*it_teb == best_teb_) { ++it_teb; continue; }
+    double plan_orientation;
+    const bool drop = (*it_teb)->teb().sizePoses() < 2 || !computeStartOrientation(*it_teb, len_orientation_vector, plan_orientation) ||
+                      std::fabs(g2o::normalize_theta(plan_orientation - current_movement_orientation)) > orient_threshold ||
+                      !(*it_teb)->isOptimized() ||
+                      (*it_teb)->teb().getSumOfAllTimeDiffs() / best_plan_duration > cfg_->hcp.max_ratio_detours_duration_best_duration;
+    if (drop) { TebOptimalPlannerPtr victim = *it_teb; it_teb = removeTeb(victim); continue; }
+    ++it_teb;
+  }
+}
+
+/* :539-562 */
+void HomotopyClassPlanner::randomlyDropTebs() {
+  if (cfg_->hcp.selection_dropping_probability == 0.0) return;
+  auto it_eqrel = equivalence_classes_.begin();
+  auto it_teb = tebs_.begin();
+  while (it_teb != tebs_.end() && it_eqrel != equivalence_classes_.end()) {
+    if (it_teb->get() != best_teb_.get() &&
+        (double)random_() <= cfg_->hcp.selection_dropping_probability * (double)random_.max()) {
+      it_teb = tebs_.erase(it_teb);
+      it_eqrel = equivalence_classes_.erase(it_eqrel);
+    } else {
+      ++it_teb;
+      ++it_eqrel;
+    }
+  }
 }
 
 /* :337-357 — renew the classes of the existing bands, inject the initial plan, explore further classes */
@@ -141,6 +196,7 @@ void HomotopyClassPlanner::exploreEquivalenceClassesAndInitTebs(const PoseSE2& s
                                                                 const geometry_msgs::Twist* start_vel, bool free_goal_vel) {
   (void)dist_to_obst;
   renewAndAnalyzeOldTebs(cfg_->hcp.delete_detours_backwards);
+  randomlyDropTebs();
   if (initial_plan_) {
     initial_plan_teb_ = addAndInitNewTeb(*initial_plan_, start_vel, free_goal_vel);
   } else {
