@@ -8,9 +8,14 @@
  *   k_linearize      "kernel A": residuals + analytic Jacobians of every edge family + banded J^T Omega J / b
  *                    assembly in shared memory, TMA-staged inputs, TMA bulk store of the band tile
  *                                                                            (g2o buildSystem)
- *   k_lm_step        "kernel B": one Levenberg-Marquardt iteration per band: banded LDL^T, update, trial chi2,
- *                    rho / lambda accept-reject loop                          
+ *   k_linearize_w    the same arithmetic with one warp per tile (alternative mapping, tebgpu_set_linearize_variant)
+ *   k_vor            EdgeVelocityObstacleRatio rows added to the assembled band (only when that weight is > 0)
+ *   k_lm_step_t      "kernel B", solvers 0 / 1: one Levenberg-Marquardt iteration per band in one CTA: banded LDL^T
+ *                    (sequential warp solver or block cyclic reduction), update, trial chi2, rho / lambda
+ *                    accept-reject loop. The default solver 2 lives in teb_spec.cuh.
  *   k_finalize       computeCurrentCost with the selection scales, outputs   (optimal_planner.cpp:1041-1094)
+ *   k_cost_only      computeCurrentCost outside optimizeTEB
+ * Template flags: HOLO = holonomic rows (vy, acc y), GEOM = vertex-list shapes reachable (generic_distance compiled in).
  *
  * Unknown layout ("padded group layout"): scalar index 4*i + c, c = 0,1,2 -> (x,y,theta) of pose i, c = 3 -> dt_i.
  * It equals the g2o vertex-id order (dt_0, pose_1, dt_1, ...) shifted by 3; the fixed start/goal pose and the
@@ -767,7 +772,7 @@ struct KASmem {
   static constexpr int START = 3 * 7 + 3;
   static constexpr int UN = TP * 9;
   static constexpr int RED = 4 * (KA_THREADS / 32) + 8 + (KA_THREADS / 32);
-  static constexpr int STAGE = KA_THREADS * HROW; /* aliases JB..: needs JB+EH+START+UN >= STAGE? no: separate */
+  static constexpr int STAGE = KA_THREADS * HROW; /* output stage of the tile (128 rows x 12); reuses the Jacobian region */
 };
 
 __host__ __device__ inline size_t ka_smem_bytes(int M_cap) {
