@@ -470,11 +470,18 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   double weight_multiplier = 1.0;
   KParams kp = make_kparams(ctx, bt, weight_multiplier);
   prof_begin(ctx, st, 0); k_begin<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st);
+  bool carried = false; /* the side stream already ran autoResize / buildGraph / kernel A of this outer iteration for the
+                           bands that were still in a retry round when the previous outer iteration ended */
   for (int o = 0; o < args->iterations_outerloop; ++o) {
     kp = make_kparams(ctx, bt, weight_multiplier);
-    if (p.teb_autosize) { prof_begin(ctx, st, 1); k_auto_resize<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st); }
-    prof_begin(ctx, st, 2); launch_build_graph(db, kp, B, smem_g, st); ++launches; prof_end(ctx, st);
-    bool deferred_done = false; /* kernel A of this iteration already ran for the deferred bands (side stream) */
+    {
+      DevBatch dm = db;
+      if (carried) dm.skip_tag = tag;
+      if (p.teb_autosize) { prof_begin(ctx, st, 1); k_auto_resize<<<gb, tb, 0, st>>>(dm, kp); ++launches; prof_end(ctx, st); }
+      prof_begin(ctx, st, 2); launch_build_graph(dm, kp, B, smem_g, st); ++launches; prof_end(ctx, st);
+    }
+    bool deferred_done = carried; /* kernel A of this iteration already ran for the deferred bands (side stream) */
+    carried = false;
     for (int it = 0; it < args->iterations_innerloop; ++it) {
       ++tag;
       {
@@ -510,6 +517,18 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
             dl.a_cnt = ctx->spec.cnt + (g - rounds + 1);
             launch_linearize(ctx, dl, kp, B, bt->M_cap, ctx->side); ++launches;
             deferred_done = true;
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
+          } else if (o + 1 < args->iterations_outerloop) {
+            /* last inner iteration: the side stream goes on with the next outer iteration's autoResize / buildGraph /
+             * first kernel A for its bands (next weight multiplier), the main stream does the same for all others */
+            const KParams kn = make_kparams(ctx, bt, weight_multiplier * p.weight_adapt_factor);
+            DevBatch dl = db;
+            dl.a_list = ctx->spec.list + (size_t)((g - rounds + 1) % 3) * B;
+            dl.a_cnt = ctx->spec.cnt + (g - rounds + 1);
+            if (p.teb_autosize) { k_auto_resize<<<gb, tb, 0, ctx->side>>>(dl, kn); ++launches; }
+            launch_build_graph(dl, kn, B, smem_g, ctx->side); ++launches;
+            launch_linearize(ctx, dl, kn, B, bt->M_cap, ctx->side); ++launches;
+            carried = true;
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
           } else {
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side));

@@ -170,8 +170,10 @@ __global__ void k_begin(DevBatch db, KParams kp) {
 
 /* ------------------------------------------------------------------ k_auto_resize (thread per band) */
 __global__ void k_auto_resize(DevBatch db, KParams kp) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= db.B) return;
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= db.B) return;
+  const int b = linearize_band(db, y); /* all bands, or the deferred list / everything but the deferred bands */
+  if (b < 0) return;
   if (db.state[b].failed) return;
   const int fast_mode = !kp.p.include_dynamic_obstacles; /* optimal_planner.cpp:197 */
   int n = db.n[b];
@@ -186,7 +188,8 @@ template <bool GEOM>
 __global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TebObstacle* so = reinterpret_cast<TebObstacle*>(smem_raw);
-  const int b = blockIdx.x;
+  const int b = linearize_band(db, blockIdx.x);
+  if (b < 0) return;
   BandState* st = &db.state[b];
   const int n = db.n[b];
   if (threadIdx.x == 0) {

@@ -500,6 +500,7 @@ def test_device_pointer_entry_point_matches_host_entry_point():
     got = poses.cpu().numpy().view(np.float64).reshape(hb0.poses.shape)
     assert np.array_equal(got, ref.poses)
     assert np.array_equal(cost.cpu().numpy(), ref.cost)
-    # begin + outer*(build + inner*(A + 2 rounds x (solve, eval) [K=6]) + (inner-1) side-stream A of the retry list) + finalize
-    assert g.launch_count() == 1 + 4 * (1 + 5 * (1 + 2 * 2) + 4) + 1
+    # begin + outer*(build + inner*(A + 2 rounds x (solve, eval) [K=6]) + (inner-1) side-stream A of the retry list)
+    # + 3 outer boundaries x (side-stream build + A of the retry list) + finalize
+    assert g.launch_count() == 1 + 4 * (1 + 5 * (1 + 2 * 2) + 4) + 3 * 2 + 1
     g.close()
