@@ -249,7 +249,7 @@ int32_t tebgpu_set_solver(tebgpu_ctx* ctx, int32_t solver);
 /* Thread mapping of kernel A: 0 (default) one 128-thread CTA per 32-pose tile, 1 one warp per tile. Same results
  * (bitwise identical band); the CTA mapping is ~1.4x faster on B200 (occupancy), the warp mapping is kept for study. */
 int32_t tebgpu_set_linearize_variant(tebgpu_ctx* ctx, int32_t variant);
-/* Speculation width of solver 2: how many consecutive LM damping trials are solved per round (4, 6 or 8; 0 = auto).
+/* Speculation width of solver 2: how many consecutive LM damping trials are solved per round (2, 4, 6 or 8; 0 = auto).
  * Results do not depend on it (the accept / reject chain is replayed in order), only latency and traffic do. */
 int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k);
 

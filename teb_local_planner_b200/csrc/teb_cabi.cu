@@ -190,6 +190,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   if (const char* e = std::getenv("TEBGPU_OVERLAP")) c->overlap = std::atoi(e) != 0;
+  if (const char* e = std::getenv("TEBGPU_SPEC_K")) { const int k = std::atoi(e); if (k == 2 || k == 4 || k == 6 || k == 8) c->spec_k = k; }
   const size_t B = c->lim.max_bands, nc = c->lim.max_poses, S = c->lim.max_scenes, M = c->lim.max_obstacles,
                V = c->lim.max_viapoints > 0 ? c->lim.max_viapoints : 1;
   CUDA_TRY(c, cudaMalloc(&c->Hb, B * 4 * nc * HROW * sizeof(double)));
@@ -579,7 +580,7 @@ int32_t tebgpu_set_linearize_variant(tebgpu_ctx* ctx, int32_t v) {
 }
 
 int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k) {
-  if (!ctx || !(k == 0 || k == 4 || k == 6 || k == 8)) return TEBGPU_ERR_INVALID_ARG;
+  if (!ctx || !(k == 0 || k == 2 || k == 4 || k == 6 || k == 8)) return TEBGPU_ERR_INVALID_ARG;
   ctx->spec_k = k;
   return TEBGPU_OK;
 }

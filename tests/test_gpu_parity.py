@@ -442,14 +442,14 @@ def test_solvers_and_speculation_widths_agree():
     args = abi.make_args(5, 4, True, 100.0, 1.0, False)
     g = _gpu(hb0, p)
     outs = {}
-    for name, solver, k in (("spec4", 2, 4), ("spec6", 2, 6), ("spec8", 2, 8), ("bcr", 1, 0), ("seq", 0, 0)):
+    for name, solver, k in (("spec4", 2, 4), ("spec2", 2, 2), ("spec6", 2, 6), ("spec8", 2, 8), ("bcr", 1, 0), ("seq", 0, 0)):
         g.set_solver(solver)
         g.set_speculation(k)
         h = hb0.copy()
         g.optimize(h, args)
         outs[name] = h
     g.close()
-    for name in ("spec6", "spec8"):
+    for name in ("spec2", "spec6", "spec8"):
         assert np.array_equal(outs[name].poses, outs["spec4"].poses) and np.array_equal(outs[name].cost, outs["spec4"].cost)
         assert np.array_equal(outs[name].lm_iters, outs["spec4"].lm_iters)
     for name in ("bcr", "seq"):
