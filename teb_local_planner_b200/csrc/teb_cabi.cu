@@ -170,7 +170,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     return TEBGPU_ERR_NO_DEVICE;
   }
   if (lim->max_bands < 1 || lim->max_poses < 3 || lim->max_poses > 512 || lim->max_scenes < 1 || lim->max_obstacles < 0 ||
-      lim->max_obstacles > 64 * MAX_MW || lim->max_viapoints < 0)
+      lim->max_obstacles > 64 * MAX_MW || lim->max_viapoints < 0 || lim->max_obst_vertices < 0)
     return TEBGPU_ERR_INVALID_ARG;
   tebgpu_ctx* c = new (std::nothrow) tebgpu_ctx();
   if (!c) return TEBGPU_ERR_CUDA;
