@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.idx), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -86,9 +86,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
 
     def stop(self):
+        self.t1 = time.time()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -97,7 +101,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        inside = [ln for (ts, ln) in self.lines if t0 <= ts <= self.t1]
+        if not inside and self.lines:           # region shorter than one sampling period: the sample closest to it
+            inside = [min(self.lines, key=lambda x: abs(x[0] - 0.5 * (t0 + self.t1)))[1]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -258,15 +266,16 @@ def run_b200(a, rank, local_rank, world):
         if world > 1:
             dist.all_gather_into_tensor(d_all_cost, d_cost)  # the ONE collective: per-candidate costs
 
+    sampler = ClockSampler(local_rank)      # started before the warm-up so that nvidia-smi is already streaming
+    sampler.start()
     for _ in range(a.warmup):
         flush.zero_()
         device_step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     torch.cuda.synchronize()
+    sampler.mark_begin()                    # only samples taken inside the timed region are reported
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     for k in range(a.steps):
         flush.zero_()                                   # L2 flush between timed iterations (outside the events)
