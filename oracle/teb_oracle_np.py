@@ -9,7 +9,8 @@ Reference bodies followed (relative to the reference checkout):
   g2o_types/penalties.h:57-117, misc.h:95, g2o_types/edge_velocity.h:97-114, edge_acceleration.h:103-145,
   :316-341, :408-433, edge_kinematics.h:94-101, :203-215, edge_obstacle.h:90-103, :212-229,
   edge_dynamic_obstacle.h:98-101, edge_via_point.h:86, edge_time_optimal.h:93,
-  src/optimal_planner.cpp:182-231 (outer loop), :444-548 (association), :646-718, :1041-1094 (cost).
+  src/optimal_planner.cpp:182-231 (outer loop), :444-548 (association), :646-718, :1041-1094 (cost),
+  edge_velocity.h:236-273 and edge_acceleration.h:487-712 (holonomic variants), h_signature.h:97-186, :282-353.
 Supported subset: point / circular footprint, point / circular obstacles, no autoResize.
 """
 import math
@@ -147,9 +148,40 @@ class Band:
         for idx, v in self.via_idx:
             add(math.hypot(P[idx, 0] - v[0], P[idx, 1] - v[1]), c.weight_viapoint, 1)
         vw = [seg(c, P[i], P[i + 1], P[i, 3]) for i in range(n - 1)]
-        for i in range(n - 1):
-            add(p_int2(vw[i][0], -c.max_vel_x_backwards, c.max_vel_x, c.penalty_epsilon), c.weight_max_vel_x, 3)
-            add(p_int(vw[i][1], c.max_vel_theta, c.penalty_epsilon), c.weight_max_vel_theta, 3)
+        holo = c.max_vel_y != 0
+
+        def holo_vel(a, b, dt):          # velocity in the frame of the first pose (edge_velocity.h:247-254)
+            dx, dy = b[0] - a[0], b[1] - a[1]
+            cs, sn = math.cos(a[2]), math.sin(a[2])
+            return (cs * dx + sn * dy) / dt, (-sn * dx + cs * dy) / dt, nt(b[2] - a[2]) / dt
+
+        hv = [holo_vel(P[i], P[i + 1], P[i, 3]) for i in range(n - 1)] if holo else None
+        if holo:
+            for i in range(n - 1):
+                vx, vy, om = hv[i]
+                rem_y = math.sqrt(max(0.0, c.max_vel_trans ** 2 - vx * vx))
+                rem_x = math.sqrt(max(0.0, c.max_vel_trans ** 2 - vy * vy))
+                add(p_int2(vx, -min(rem_x, c.max_vel_x_backwards), min(rem_x, c.max_vel_x), 0.0), c.weight_max_vel_x, 3)
+                add(p_int(vy, min(rem_y, c.max_vel_y), 0.0), c.weight_max_vel_y, 3)
+                add(p_int(om, c.max_vel_theta, c.penalty_epsilon), c.weight_max_vel_theta, 3)
+        else:
+            for i in range(n - 1):
+                add(p_int2(vw[i][0], -c.max_vel_x_backwards, c.max_vel_x, c.penalty_epsilon), c.weight_max_vel_x, 3)
+                add(p_int(vw[i][1], c.max_vel_theta, c.penalty_epsilon), c.weight_max_vel_theta, 3)
+        if holo and c.acc_lim_y != 0:    # EdgeAccelerationHolonomic / Start / Goal (edge_acceleration.h:487-712)
+            lim = (c.acc_lim_x, c.acc_lim_y, c.acc_lim_theta)
+            wts = (c.weight_acc_lim_x, c.weight_acc_lim_y, c.weight_acc_lim_theta)
+            if self.vs[3]:
+                for k in range(3):
+                    add(p_int((hv[0][k] - self.vs[k]) / P[0, 3], lim[k], c.penalty_epsilon), wts[k], 3)
+            for i in range(n - 2):
+                T = P[i, 3] + P[i + 1, 3]
+                for k in range(3):
+                    add(p_int((hv[i + 1][k] - hv[i][k]) * 2 / T, lim[k], c.penalty_epsilon), wts[k], 3)
+            if self.vg[3]:
+                for k in range(3):
+                    add(p_int((self.vg[k] - hv[n - 2][k]) / P[n - 2, 3], lim[k], c.penalty_epsilon), wts[k], 3)
+            return self._tail(P, r, tag, add)
         if self.vs[3]:
             dt = P[0, 3]
             add(p_int((vw[0][0] - self.vs[0]) / dt, c.acc_lim_x, c.penalty_epsilon), c.weight_acc_lim_x, 3)
@@ -162,6 +194,10 @@ class Band:
             dt = P[n - 2, 3]
             add(p_int((self.vg[0] - vw[n - 2][0]) / dt, c.acc_lim_x, c.penalty_epsilon), c.weight_acc_lim_x, 3)
             add(p_int((self.vg[2] - vw[n - 2][1]) / dt, c.acc_lim_theta, c.penalty_epsilon), c.weight_acc_lim_theta, 3)
+        return self._tail(P, r, tag, add)
+
+    def _tail(self, P, r, tag, add):
+        c, n = self.c, self.n
         for i in range(n - 1):
             add(P[i, 3], c.weight_optimaltime, 2)
         carlike = not (c.min_turning_radius == 0 or c.weight_kinematics_turning_radius == 0)
@@ -256,3 +292,76 @@ def optimize(c, rec, obst, via=None, inner=5, outer=4, obst_scale=1.0, via_scale
             cost = obst_scale * sq[tag == 0].sum() + via_scale * sq[tag == 1].sum() + sq[tag == 2].sum() + sq[tag == 3].sum()
         mult *= c.weight_adapt_factor
     return band.rec, float(cost)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# H-signatures (h_signature.h), independent of oracle/teb_oracle.c: numpy longdouble / vector algebra
+def h_signature_2d(c, rec, obst):
+    """HSignature::calculateHSignature h_signature.h:97-186"""
+    M = len(obst)
+    if M == 0:
+        return 0j
+    ld = np.longdouble
+    z = np.array([complex(p[0], p[1]) for p in rec], dtype=np.clongdouble)
+    o = np.array([complex(ob["x"], ob["y"]) for ob in obst], dtype=np.clongdouble)
+    m = max(M - 1, 5)
+    a = int(math.ceil(m / 2.0))
+    b = m - a
+    delta = z[-1] - z[0]
+    normal = np.clongdouble(complex(-float(delta.imag), float(delta.real)))
+    if abs(delta) < 3.0:
+        bl, tr = z[0] + np.clongdouble(-3j), z[0] + np.clongdouble(3 + 3j)
+    else:
+        bl, tr = z[0] - normal, z[0] + delta + normal
+    H = np.clongdouble(0)
+    A = []
+    for l in range(M):
+        Al = ld(c.h_signature_prescaler) * ld(a) * (o[l] - bl) * ld(b) * (o[l] - tr)
+        for j in range(M):
+            if j == l:
+                continue
+            diff = o[l] - o[j]
+            if abs(diff) < 0.05:
+                continue
+            Al = Al / diff
+        A.append(Al)
+    for k in range(len(z) - 1):
+        for l in range(M):
+            d2, d1 = float(abs(z[k + 1] - o[l])), float(abs(z[k] - o[l]))
+            if d2 == 0 or d1 == 0:
+                continue
+            log_real = math.log(d2) - math.log(d1)
+            w2, w1 = z[k + 1] - o[l], z[k] - o[l]
+            arg_diff = float(np.arctan2(w2.imag, w2.real) - np.arctan2(w1.imag, w1.real))
+            cand = [arg_diff, arg_diff + 2 * PI, arg_diff - 2 * PI, arg_diff + 4 * PI, arg_diff - 4 * PI]
+            log_imag = min(cand, key=abs)
+            H = H + A[l] * np.clongdouble(complex(log_real, log_imag))
+    return complex(H)
+
+
+def h_signature_3d(c, rec, obst, use_timediffs=True):
+    """HSignature3d::calculateHSignature h_signature.h:282-353 (Biot-Savart integral, 10 steps per segment)"""
+    rec = np.asarray(rec, float)
+    t = np.zeros(len(rec))
+    for k in range(len(rec) - 1):
+        t[k + 1] = t[k] + (rec[k, 3] if use_timediffs else math.hypot(*(rec[k + 1, :2] - rec[k, :2])) / c.max_vel_x)
+    out = []
+    for ob in obst:
+        s1 = np.array([ob["x"], ob["y"], 0.0])
+        s2 = np.array([ob["x"] + 120 * ob["vx"], ob["y"] + 120 * ob["vy"], 120.0])
+        ds = s2 - s1
+        H = 0.0
+        for k in range(len(rec) - 1):
+            direction = np.array([rec[k + 1, 0] - rec[k, 0], rec[k + 1, 1] - rec[k, 1], t[k + 1] - t[k]])
+            if np.linalg.norm(direction) < 1e-15:
+                continue
+            r = np.array([rec[k, 0], rec[k, 1], t[k]])
+            dl = 0.1 * direction
+            for _ in range(10):
+                p1, p2 = s1 - r, s2 - r
+                d = np.cross(ds, np.cross(p1, p2)) / ds.dot(ds)
+                phi = (np.cross(d, p2) / np.linalg.norm(p2) - np.cross(d, p1) / np.linalg.norm(p1)) / d.dot(d)
+                H += phi.dot(dl)
+                r = r + dl
+        out.append(H / (4 * PI))
+    return np.array(out)

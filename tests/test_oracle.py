@@ -201,6 +201,57 @@ def test_numpy_second_opinion(oracle):
         assert abs(cgot - cref) <= 1e-5 * max(abs(cref), 1.0)
 
 
+def _load_np_oracle():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("teb_oracle_np", os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "teb_oracle_np.py"))
+    npo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(npo)
+    return npo
+
+
+@pytest.mark.parametrize("acc_lim_y", [0.5, 0.0])
+def test_numpy_second_opinion_holonomic(oracle, acc_lim_y):
+    """holonomic velocity / acceleration edges: the numpy restatement (stacked residuals, dense numeric Jacobian) and the C
+    oracle reach the same band"""
+    npo = _load_np_oracle()
+    p = abi.default_params()
+    p.teb_autosize = 0
+    p.max_vel_y, p.acc_lim_y, p.max_vel_trans, p.weight_kinematics_nh = 0.3, acc_lim_y, 0.45, 1.0
+    hb = scenes.make_batch(12, 3, 2, seed=11, moving=False)
+    rng = np.random.default_rng(2)
+    for b in range(2):
+        rec = hb.poses[b, :12].copy()
+        rec[1:-1, 2] += rng.normal(0, 0.3, 10)
+        rec[:-1, 3] *= 0.8
+        obst = hb.obstacles[0][:3].copy()
+        obst["x"], obst["y"] = rng.uniform(-0.5, 0.5, 3), rng.uniform(-0.6, 0.6, 3)
+        vs = [0.2, 0.05, -0.1, 1.0]
+        args = abi.make_args(3, 2, True, 100.0, 1.0, False)
+        ref, cref, _ = oracle.optimize_band(p, rec, 12, obst, vel_start=vs, args=args, jac_mode=0, solver=oracle.SOLVER_DENSE)
+        got, cgot = npo.optimize(p, rec, obst, inner=3, outer=2, obst_scale=100.0, via_scale=1.0, vel_start=vs)
+        # both sides use central differences with delta = 1e-9: their ~1e-7 relative Jacobian noise is amplified by the
+        # stiff holonomic problem; the north-star tolerance (1e-4 per pose component) is the bar
+        assert np.abs(got - ref).max() < 1e-4
+        assert abs(cgot - cref) <= 1e-4 * max(abs(cref), 1.0)
+
+
+def test_numpy_second_opinion_h_signatures(oracle):
+    """both signature kinds against an independent numpy evaluation (numpy longdouble complex arithmetic / numpy cross
+    products)"""
+    npo = _load_np_oracle()
+    p, hb = scenes.make_config_batch("C4", candidates=3, seed=5)
+    obst = hb.obstacles[0][:12]
+    for b in range(hb.B):
+        rec = hb.poses[b, :40].copy()
+        p.include_dynamic_obstacles = 0
+        h2 = oracle.h_signature(p, rec, 40, obst)
+        assert abs(h2 - npo.h_signature_2d(p, rec, obst)) <= 1e-13 * abs(h2)
+        p.include_dynamic_obstacles = 1
+        for use_dt in (True, False):
+            h3 = oracle.h_signature(p, rec, 40, obst, use_timediffs=use_dt)
+            assert np.abs(h3 - npo.h_signature_3d(p, rec, obst, use_dt)).max() < 1e-13
+
+
 def test_golden_fixtures_pin_oracle(oracle):
     """the committed golden vectors (tests/golden/make_golden.py) guard the oracle against drift"""
     path = os.path.join(GOLDEN, "golden_v1.npz")
