@@ -717,6 +717,7 @@ __device__ __forceinline__ void gather_row(const KParams& kp, int t, int p0, int
           if (l <= 6) {
 #pragma unroll
             for (int k = 0; k < (HOLO ? 7 : 6); ++k) {
+              if ((k == 4 && !kp.has_sp) || (k == 5 && !kp.has_rot)) continue; /* family switched off: rows are zero */
               const double jl = J[7 * k + l];
               if (jl != 0) {
                 brow -= jl * eh[k];
@@ -829,9 +830,19 @@ __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParam
   /* zero the Jacobian blocks while the copies are in flight */
   {
     double2* z2 = reinterpret_cast<double2*>(sJ); /* sJ is 16-byte aligned, JB is even */
-    for (int k = tid; k < KASmem::JB / 2; k += KA_THREADS) z2[k] = make_double2(0.0, 0.0);
+    constexpr int NZ2 = KASmem::JB / 2, NZE = KASmem::EH + KASmem::START;
+    /* fully unrolled: only the last store of each group needs a bounds test */
+#pragma unroll
+    for (int q = 0; q < (NZ2 + KA_THREADS - 1) / KA_THREADS; ++q) {
+      const int k = tid + q * KA_THREADS;
+      if ((q + 1) * KA_THREADS <= NZ2 || k < NZ2) z2[k] = make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < (NZE + KA_THREADS - 1) / KA_THREADS; ++q) {
+      const int k = tid + q * KA_THREADS;
+      if ((q + 1) * KA_THREADS <= NZE || k < NZE) sE[k] = 0.0;
+    }
   }
-  for (int k = tid; k < KASmem::EH + KASmem::START; k += KA_THREADS) sE[k] = 0.0;
   mbar_wait(bar, 0);
 
   double chi[4] = {0, 0, 0, 0}; /* obstacles, via, time-optimal, other */
