@@ -9,6 +9,8 @@
  *   HomotopyClassPlanner::optimizeAllTEBs     src/homotopy_class_planner.cpp:466-493
  *   HomotopyClassPlanner::selectBestTeb       src/homotopy_class_planner.cpp:564-667
  *   TimedElasticBand::autoResize              src/timed_elastic_band.cpp:227-286
+ *   HomotopyClassPlanner::calculateEquivalenceClass (HSignature / HSignature3d)
+ *                                             include/teb_local_planner/homotopy_class_planner.hpp:46-63, h_signature.h
  *
  * Plain C, plain pointers and sizes, no torch / CUDA types in any signature.
  * All state is fp64 (the reference is fp64 throughout).
@@ -30,7 +32,7 @@ extern "C" {
 #define TEBGPU_OK                  0
 #define TEBGPU_ERR_INVALID_ARG    -1
 #define TEBGPU_ERR_CUDA           -2
-#define TEBGPU_ERR_UNSUPPORTED    -3   /* a cost term / option that has no kernel yet: fail loudly */
+#define TEBGPU_ERR_UNSUPPORTED    -3   /* an option outside what the kernels cover (e.g. unknown footprint model): fail loudly */
 #define TEBGPU_ERR_CAPACITY       -4
 #define TEBGPU_ERR_NO_DEVICE      -5
 
