@@ -161,6 +161,33 @@ def test_golden_fixtures(oracle):
         assert np.array_equal(hb.status, gold[f"{name}_status"])
 
 
+def test_golden_fixtures_v2():
+    """golden_v2.npz without the oracle library: holonomic robot (exact), candidate classification (both signature kinds)"""
+    from tests.golden import make_golden
+    gold = np.load(os.path.join(os.path.dirname(GOLDEN), "golden_v2.npz"), allow_pickle=False)
+    for name, hb_in, p, args, gpu_exact in make_golden.cases_v2():
+        if not gpu_exact:
+            continue
+        hb = hb_in.copy()
+        g = _gpu(hb, p)
+        g.optimize(hb, args)
+        g.close()
+        assert np.array_equal(hb.n, gold[f"{name}_n"])
+        for b in range(hb.B):
+            assert np.abs(hb.poses[b, :hb.n[b]] - gold[f"{name}_poses"][b, :hb.n[b]]).max() < 1e-6
+        assert np.allclose(hb.cost, gold[f"{name}_cost"], rtol=1e-6)
+    for name, p, hb in make_golden.hsig_cases():
+        g = _gpu(hb, p)
+        got = g.h_signature(hb)
+        g.close()
+        want = gold[name]
+        if p.include_dynamic_obstacles:
+            assert np.abs(got[:, :want.shape[1]] - want).max() < 1e-12
+        else:
+            want = want[:, 0] + 1j * want[:, 1]
+            assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+
+
 def test_ragged_batch_multi_scene_and_edge_cases(oracle):
     """different n per band, several scenes with different obstacle counts (incl. none), minimal n = 3,
     too-few-poses guard, alternative time cost"""

@@ -266,6 +266,28 @@ def test_golden_fixtures_pin_oracle(oracle):
         assert np.allclose(hb.cost, g[f"{name}_cost"], rtol=1e-9)
 
 
+def test_golden_v2_pins_oracle(oracle):
+    """second fixture file: holonomic robot, vertex-list shapes with a polygon footprint, both H-signature kinds"""
+    g = np.load(os.path.join(GOLDEN, "golden_v2.npz"), allow_pickle=False)
+    from tests.golden import make_golden
+    for name, hb_in, p, args, _ in make_golden.cases_v2():
+        hb = hb_in.copy()
+        oracle.optimize_batch(p, hb, args, jac_mode=1)
+        assert np.array_equal(hb.n, g[f"{name}_n"])
+        for b in range(hb.B):
+            assert np.abs(hb.poses[b, :hb.n[b]] - g[f"{name}_poses"][b, :hb.n[b]]).max() < 1e-9
+        assert np.allclose(hb.cost, g[f"{name}_cost"], rtol=1e-9)
+    for name, p, hb in make_golden.hsig_cases():
+        obst = hb.obstacles[0][:hb.obst_count[0]]
+        for b in range(hb.B):
+            v = oracle.h_signature(p, hb.poses[b], hb.n[b], obst)
+            want = g[name][b]
+            if p.include_dynamic_obstacles:
+                assert np.array_equal(v, want[:len(obst)])
+            else:
+                assert v == complex(want[0], want[1])
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Line / Pill / Polygon obstacles and Line / Polygon footprints (distance_calculations.h, obstacles.h:597-1045,
 # robot_footprint_model.h:439-760)
