@@ -109,3 +109,24 @@ def test_shard_range_partitions():
             assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in rs]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_select_best_random_against_python_restatement(teblib):
+    """tebgpu_select_best vs the Python restatement on random cost vectors, incl. ties, infinities and every combination of
+    last-best / initial-plan indices (homotopy_class_planner.cpp:564-616)"""
+    from hypothesis import given, settings, strategies as st
+    from teb_local_planner_b200 import distributed as D
+
+    costs = st.lists(st.one_of(st.floats(min_value=0.0, max_value=100.0), st.sampled_from([1.0, 2.0, float("inf")])),
+                     min_size=1, max_size=12)
+
+    @settings(max_examples=300, deadline=None)
+    @given(costs, st.integers(-1, 11), st.integers(-1, 11), st.floats(0.5, 1.0), st.floats(0.1, 1.0))
+    def check(c, last, init, hyst, pref):
+        c = np.array(c, dtype=np.float64)
+        last = last if last < len(c) else -1
+        init = init if init < len(c) else -1
+        got = teblib.tebgpu_select_best(c.ctypes.data, len(c), last, init, hyst, pref)
+        assert got == D.select_best(c, last, init, hyst, pref)
+
+    check()
