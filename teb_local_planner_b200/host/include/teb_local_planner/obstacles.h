@@ -166,7 +166,7 @@ class PointObstacle : public Obstacle {
   double& x() { return pos_.x(); }
   double& y() { return pos_.y(); }
   TebObstacle toRow() const override {
-    TebObstacle o{pos_.x(), pos_.y(), centroid_velocity_.x(), centroid_velocity_.y(), 0.0, dynamic_ ? 1 : 0, TEB_OBST_POINT};
+    TebObstacle o{pos_.x(), pos_.y(), centroid_velocity_.x(), centroid_velocity_.y(), 0.0, dynamic_ ? 1 : 0, TEB_OBST_POINT, 0, 0, 0.0};
     return o;
   }
 
@@ -204,7 +204,7 @@ class CircularObstacle : public Obstacle {
   double& radius() { return radius_; }
   const double& radius() const { return radius_; }
   TebObstacle toRow() const override {
-    TebObstacle o{pos_.x(), pos_.y(), centroid_velocity_.x(), centroid_velocity_.y(), radius_, dynamic_ ? 1 : 0, TEB_OBST_CIRCULAR};
+    TebObstacle o{pos_.x(), pos_.y(), centroid_velocity_.x(), centroid_velocity_.y(), radius_, dynamic_ ? 1 : 0, TEB_OBST_CIRCULAR, 0, 0, 0.0};
     return o;
   }
 
@@ -255,7 +255,7 @@ class LineObstacle : public Obstacle {
   void setEnd(const Eigen::Vector2d& p) { verts_[1] = p; calcCentroid(); }
   TebObstacle toRow() const override {
     TebObstacle o{centroid_.x(), centroid_.y(), centroid_velocity_.x(), centroid_velocity_.y(), radius_, dynamic_ ? 1 : 0,
-                  radius_ > 0 ? TEB_OBST_PILL : TEB_OBST_LINE};
+                  radius_ > 0 ? TEB_OBST_PILL : TEB_OBST_LINE, 0, 0, 0.0};
     return o;
   }
   void appendVertices(std::vector<double>& pool, TebObstacle& row) const override { appendList(verts_, pool, row); }
@@ -335,7 +335,7 @@ class PolygonObstacle : public Obstacle {
     return distance_polygon_to_polygon_2d(polygon, shifted(verts_, t * centroid_velocity_));
   }
   TebObstacle toRow() const override {
-    TebObstacle o{centroid_.x(), centroid_.y(), centroid_velocity_.x(), centroid_velocity_.y(), 0.0, dynamic_ ? 1 : 0, TEB_OBST_POLYGON};
+    TebObstacle o{centroid_.x(), centroid_.y(), centroid_velocity_.x(), centroid_velocity_.y(), 0.0, dynamic_ ? 1 : 0, TEB_OBST_POLYGON, 0, 0, 0.0};
     return o;
   }
   void appendVertices(std::vector<double>& pool, TebObstacle& row) const override { appendList(verts_, pool, row); }
