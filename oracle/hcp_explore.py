@@ -274,3 +274,141 @@ class Explorer:
         pos.append(goal[:2].copy())
         adj = self._edges(pos, diff, thr, dist_to_obst)
         self._depth_first(pos, adj, [0], len(pos) - 1, start[2], goal[2])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole planning cycles of HomotopyClassPlanner::plan (src/homotopy_class_planner.cpp:107-125), sequential restatement:
+# updateAllTEBs -> exploreEquivalenceClassesAndInitTebs (renewAndAnalyzeOldTebs, initial plan, graph search) ->
+# optimizeAllTEBs -> selectBestTeb. The optimisation itself is oracle/teb_oracle.c (closed-form-Jacobian mode).
+class Planner(Explorer):
+    def __init__(self, params, hcp, oracle_binding, obst_rows, obstacles, simple_exploration=True):
+        super().__init__(params, hcp, oracle_binding, obst_rows, obstacles)
+        self.simple = simple_exploration
+        self.costs, self.optimized = [], []
+        self.best, self.best_class = None, None          # index into self.tebs / its class at classification time
+
+    # homotopy_class_planner.cpp:189-211 with a best band present
+    def _add_if_new(self, h):
+        valid = np.all(np.isfinite(h)) if self.p.include_dynamic_obstacles else (math.isfinite(h.real) and math.isfinite(h.imag))
+        if not valid:
+            return False
+        if any(self._is_equal(h, c) for c in self.classes):
+            in_best = self.best_class is not None and self._is_equal(self.best_class, h)
+            n_best = sum(1 for c in self.classes if self.best_class is not None and self._is_equal(self.best_class, c))
+            if not in_best or n_best >= self.hcp.get("max_number_plans_in_current_class", 1):
+                return False
+        self.classes.append(h)
+        return True
+
+    def _signature(self, rec):
+        return self.ob.h_signature(self.p, rec, len(rec), self.rows, use_timediffs=True)
+
+    # :214-256 (detour deletion :766-801 included)
+    def renew_and_analyze(self):
+        self.classes = []
+        order = list(range(len(self.tebs)))
+        if self.best is not None:       # std::iter_swap(tebs_.begin(), it_best_teb): a swap, not a rotation
+            order[0], order[self.best] = order[self.best], order[0]
+        tebs = [self.tebs[i] for i in order]
+        costs = [self.costs[i] for i in order]
+        opt = [self.optimized[i] for i in order]
+        keep = []
+        if self.best is not None:
+            self.best_class = self._signature(tebs[0])
+            self._add_if_new(self.best_class)
+            keep.append(0)
+        for k in range(1 if self.best is not None else 0, len(tebs)):
+            if self._add_if_new(self._signature(tebs[k])):
+                keep.append(k)
+            # else: band dropped, its class is taken
+        self.tebs, self.costs, self.optimized = [tebs[k] for k in keep], [costs[k] for k in keep], [opt[k] for k in keep]
+        self.best = 0 if self.best is not None else None
+        if self.hcp.get("delete_detours_backwards", True):
+            self._delete_detours()
+
+    def _start_orientation(self, rec, length):
+        for q in rec:
+            v = rec[0, :2] - q[:2]
+            if math.hypot(v[0], v[1]) > length:
+                return math.atan2(v[1], v[0])
+        return None
+
+    def _delete_detours(self):
+        if len(self.tebs) < 2 or self.best is None or len(self.tebs[self.best]) < 2:
+            return
+        length = self.hcp.get("length_start_orientation_vector", 0.4)
+        thr = self.hcp.get("detours_orientation_tolerance", math.pi / 2)
+        ratio = self.hcp.get("max_ratio_detours_duration_best_duration", 3.0)
+        cur = self._start_orientation(self.tebs[self.best], length)
+        if cur is None:
+            return
+        best_dur = max(self.tebs[self.best][:, 3].sum(), 1.0)
+        keep = []
+        for k, rec in enumerate(self.tebs):
+            if k == self.best:
+                keep.append(k)
+                continue
+            o = self._start_orientation(rec, length) if len(rec) >= 2 else None
+            if o is None or abs(_nt(o - cur)) > thr or not self.optimized[k] or rec[:, 3].sum() / best_dur > ratio:
+                continue
+            keep.append(k)
+        # parallel containers
+        self.classes = [self.classes[k] for k in keep] if len(self.classes) == len(self.tebs) else self.classes
+        self.best = keep.index(self.best)
+        self.tebs, self.costs, self.optimized = [self.tebs[k] for k in keep], [self.costs[k] for k in keep], [self.optimized[k] for k in keep]
+
+    def add_and_init(self, path, start_orient, goal_orient):
+        n0 = len(self.tebs)
+        super().add_and_init(path, start_orient, goal_orient)
+        if len(self.tebs) > n0:
+            self.costs.append(float("inf"))
+            self.optimized.append(False)
+
+    # timed_elastic_band.cpp:555-597
+    @staticmethod
+    def _prune(rec, new_start, new_goal, min_samples=3):
+        rec = rec.copy()
+        n = len(rec)
+        d_cache = math.hypot(new_start[0] - rec[0, 0], new_start[1] - rec[0, 1])
+        nearest = 0
+        for i in range(1, min(n - min_samples, 10) + 1):
+            d = math.hypot(new_start[0] - rec[i, 0], new_start[1] - rec[i, 1])
+            if d < d_cache:
+                d_cache, nearest = d, i
+            else:
+                break
+        if nearest > 0:
+            rec = np.concatenate([rec[:1], rec[1 + nearest:]])
+        rec[0, :3] = new_start
+        rec[-1, :3] = new_goal
+        return rec
+
+    def plan(self, start, goal, args, abi_module):
+        """one HomotopyClassPlanner::plan(start, goal) cycle; returns the index of the best band"""
+        start, goal = np.asarray(start, float), np.asarray(goal, float)
+        # updateAllTEBs :443-463
+        if self.tebs:
+            back = self.tebs[0][-1]
+            if (math.hypot(goal[0] - back[0], goal[1] - back[1]) >= self.p.force_reinit_new_goal_dist or
+                    abs(_nt(goal[2] - back[2])) >= self.p.force_reinit_new_goal_angular):
+                self.tebs, self.costs, self.optimized, self.classes, self.best = [], [], [], [], None
+        self.tebs = [self._prune(r, start, goal, self.p.min_samples) for r in self.tebs]
+        # explore :337-357
+        self.renew_and_analyze()
+        if self.simple:
+            self.lr_key_point_graph(start, goal, self.p.min_obstacle_dist)
+        else:
+            self.prob_roadmap_graph(start, goal, self.p.min_obstacle_dist)
+        # optimizeAllTEBs :466-493
+        for k, rec in enumerate(self.tebs):
+            out, cost, st = self.ob.optimize_band(self.p, rec, len(rec), self.rows, args=args, jac_mode=self.ob.JAC_ANALYTIC, n_cap=512)
+            self.tebs[k], self.costs[k] = out, cost
+            self.optimized[k] = bool(st.status & abi_module.TEB_STATUS_OPTIMIZED)
+        # selectBestTeb :564-616 (no initial-plan band in this entry point, no switching blocking period)
+        best, min_cost = None, float("inf")
+        for k, c in enumerate(self.costs):
+            cc = c * self.p.selection_cost_hysteresis if (self.best is not None and k == self.best) else c
+            if cc < min_cost:
+                best, min_cost = k, cc
+        self.best = best
+        return best

@@ -542,3 +542,34 @@ def test_exploration_restatement_pieces():
     assert X._segments_intersect(a([0., 0]), a([1., 1]), a([0., 1]), a([1., 0]))
     assert not X._segments_intersect(a([0., 0]), a([1., 0]), a([0., 1]), a([1., 1]))       # parallel
     assert not X._segments_intersect(a([0., 0]), a([1., 0]), a([2., -1]), a([2., 1]))      # beyond the end
+
+
+def test_planner_cycles_restatement_invariants(oracle):
+    """oracle/hcp_explore.py Planner: three HomotopyClassPlanner::plan cycles with a moving start pose keep at most
+    max_number_classes bands in pairwise different classes, keep the best band first in the class list, and the best
+    band only changes when another band beats its cost times the hysteresis factor"""
+    from oracle import hcp_explore as X
+    p = abi.default_params()
+    p.include_dynamic_obstacles = 0
+    rows = np.zeros(3, abi.OBST_DTYPE)
+    rows["x"], rows["y"], rows["radius"] = [-1.5, 0.5, 2.0], [0.3, -0.4, 0.5], [0, 0.3, 0]
+    rows["type"] = [abi.TEB_OBST_POINT, abi.TEB_OBST_CIRCULAR, abi.TEB_OBST_POINT]
+    obstacles = [X.Obst("point", (-1.5, 0.3)), X.Obst("circle", (0.5, -0.4), 0.3), X.Obst("point", (2.0, 0.5))]
+    pl = X.Planner(p, {"max_number_classes": 4, "obstacle_heading_threshold": 0.45}, oracle, rows, obstacles)
+    args = abi.make_args(5, 4, True, p.selection_obst_cost_scale, p.selection_viapoint_cost_scale, False)
+    prev_best_cost = None
+    for cycle, sx in enumerate((-4.0, -3.9, -3.8)):
+        best = pl.plan([sx, 0.0, 0.1], [4, 0.2, -0.2], args, abi)
+        assert best is not None and 2 <= len(pl.tebs) <= 4
+        sigs = [pl._signature(r) for r in pl.tebs]
+        if cycle == 0:      # freshly explored bands are pairwise in different classes (the optimiser may merge them later)
+            init_classes = list(pl.classes)
+            for i in range(len(init_classes)):
+                for j in range(i + 1, len(init_classes)):
+                    assert not pl._is_equal(init_classes[i], init_classes[j])
+        assert all(np.isfinite(c) for c in pl.costs)
+        assert all(np.array_equal(r[0, :3], [sx, 0.0, 0.1]) and np.array_equal(r[-1, :3], [4, 0.2, -0.2]) for r in pl.tebs)
+        assert pl.costs[best] * (p.selection_cost_hysteresis if prev_best_cost is not None else 1.0) <= min(pl.costs) + 1e-12 or \
+            pl.costs[best] == min(pl.costs)
+        prev_best_cost = pl.costs[best]
+        assert len(sigs) == len(pl.tebs)
