@@ -248,8 +248,9 @@ int32_t tebgpu_synchronize(tebgpu_ctx* ctx);
  * 1 block cyclic reduction on 8x8 blocks in shared memory (max_poses <= 256), one CTA per band;
  * 0 sequential banded LDL^T in shared memory, one CTA per band.  All three give the same results up to round-off. */
 int32_t tebgpu_set_solver(tebgpu_ctx* ctx, int32_t solver);
-/* Thread mapping of kernel A: 0 (default) one 128-thread CTA per 32-pose tile, 1 one warp per tile. Same results
- * (bitwise identical band); the CTA mapping is ~1.4x faster on B200 (occupancy), the warp mapping is kept for study. */
+/* Thread mapping of kernel A: 0 (default) k_linearize2: one thread per pose, 125-pose tiles, band rows accumulated in
+ * registers; 1 the first-generation kernel: one 128-thread CTA per 32-pose tile, one thread per band row. Same
+ * arithmetic, different summation order (results agree to round-off); variant 1 is kept as an independent cross-check. */
 int32_t tebgpu_set_linearize_variant(tebgpu_ctx* ctx, int32_t variant);
 /* Speculation width of solver 2: how many consecutive LM damping trials are solved per round (2, 4, 6 or 8; 0 = auto).
  * Results do not depend on it (the accept / reject chain is replayed in order), only latency and traffic do. */
@@ -277,6 +278,10 @@ int32_t tebgpu_h_signature(tebgpu_ctx* ctx, const TebBatch* batch, int32_t use_t
 
 /* Number of kernels launched by the last optimize call (for bench.py's gpu_launches). */
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx);
+/* Introspection for measurement scripts. which: 0 speculation width used by the last optimize call, 1 kernel-A variant,
+ * 2 solver, 3 communicator size (1 without tebgpu_comm_init), 4 communicator rank, 5 CUDA-graph replay enabled,
+ * 6 number of captured graphs held by the context. Returns -1 for an unknown key. */
+int64_t tebgpu_get_info(const tebgpu_ctx* ctx, int32_t which);
 
 /* Linearise only: build the padded banded normal equations of every band at its current state for
  * outer iteration `outer_index` (obstacle weight multiplier = weight_adapt_factor^outer_index).

@@ -21,11 +21,15 @@
  * generic numeric linearisation through computeError callbacks, sparse(banded) Cholesky per LM trial)
  * so that timing it is a fair "reference CPU path" baseline.
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE /* pthread_setaffinity_np, sched_getaffinity (thread pinning of the batch driver) */
+#endif
 #include "teb_oracle.h"
 
 #include <float.h>
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1884,9 +1888,32 @@ typedef struct BatchJob {
   const TebParams* cfg; const TebBatch* batch; const TebOptimizeArgs* args; const OracleOptions* opt;
   int next; pthread_mutex_t mu; int rc;
 } BatchJob;
+typedef struct BatchThread { BatchJob* job; int index; } BatchThread;
+
+/* pin the calling worker to the index-th CPU of the process affinity mask (round robin) */
+static void pin_worker(int index) {
+  cpu_set_t allowed;
+  CPU_ZERO(&allowed);
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return;
+  const int cnt = CPU_COUNT(&allowed);
+  if (cnt <= 0) return;
+  int want = index % cnt, seen = 0;
+  for (int c = 0; c < CPU_SETSIZE; ++c) {
+    if (!CPU_ISSET(c, &allowed)) continue;
+    if (seen++ == want) {
+      cpu_set_t one;
+      CPU_ZERO(&one);
+      CPU_SET(c, &one);
+      pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+      return;
+    }
+  }
+}
 
 static void* batch_worker(void* p) {
-  BatchJob* job = (BatchJob*)p;
+  BatchThread* me = (BatchThread*)p;
+  BatchJob* job = me->job;
+  if (job->opt && job->opt->pin_threads && me->index >= 0) pin_worker(me->index);
   const TebBatch* bt = job->batch;
   for (;;) {
     pthread_mutex_lock(&job->mu);
@@ -1924,11 +1951,14 @@ int32_t teb_oracle_optimize_batch(const TebParams* cfg, const TebBatch* batch, c
   if (threads < 1) threads = 1;
   if (threads > batch->B) threads = batch->B;
   if (threads == 1) {
-    batch_worker(&job);
+    BatchThread me = {&job, -1}; /* the caller's thread: never re-pinned */
+    batch_worker(&me);
   } else {
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
-    for (int t = 0; t < threads; ++t) pthread_create(&th[t], NULL, batch_worker, &job);
+    BatchThread* arg = (BatchThread*)malloc(sizeof(BatchThread) * threads);
+    for (int t = 0; t < threads; ++t) { arg[t].job = &job; arg[t].index = t; pthread_create(&th[t], NULL, batch_worker, &arg[t]); }
     for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+    free(arg);
     free(th);
   }
   pthread_mutex_destroy(&job.mu);

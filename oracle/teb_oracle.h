@@ -30,7 +30,7 @@ typedef struct OracleOptions {
   int32_t jac_mode;
   int32_t solver;
   int32_t verbose;
-  int32_t _pad;
+  int32_t pin_threads;  /* batch driver: pin worker t to the t-th CPU of the affinity mask (timing runs) */
 } OracleOptions;
 
 typedef struct OracleStats {

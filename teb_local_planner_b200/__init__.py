@@ -54,6 +54,8 @@ def load_library(build_if_missing=False):
     L.tebgpu_synchronize.argtypes = [vp]
     L.tebgpu_last_launch_count.restype = C.c_int64
     L.tebgpu_last_launch_count.argtypes = [vp]
+    L.tebgpu_get_info.restype = C.c_int64
+    L.tebgpu_get_info.argtypes = [vp, C.c_int32]
     L.tebgpu_set_profiling.restype = C.c_int32
     L.tebgpu_set_profiling.argtypes = [vp, C.c_int32]
     L.tebgpu_get_kernel_times.restype = C.c_int32
@@ -149,6 +151,13 @@ class TebGpu:
         self._check(self.lib.tebgpu_h_signature(self.ctx, C.byref(bs), int(use_timediffs), out.ctypes.data, 0),
                     "tebgpu_h_signature")
         return out if three_d else out[:, 0] + 1j * out[:, 1]
+
+    def info(self, which):
+        return int(self.lib.tebgpu_get_info(self.ctx, int(which)))
+
+    def speculation_width(self):
+        """speculation width (trials solved concurrently per round) chosen by the last optimize call"""
+        return self.info(0)
 
     def launch_count(self):
         return int(self.lib.tebgpu_last_launch_count(self.ctx))

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libteb_b200.so")
 SOURCES = [os.path.join(CSRC, "teb_cabi.cu")]
-DEPS = [os.path.join(CSRC, f) for f in ("teb_cabi.cu", "teb_kernels.cuh", "teb_device.cuh", "teb_resize.h")] + [
+DEPS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
     os.path.join(os.path.dirname(HERE), "include", "teb_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "teb_kernels.cuh"
+#include "teb_linearize.cuh"
 #include "teb_spec.cuh"
 #include "teb_hsig.cuh"
 #include <cstdlib>
@@ -32,8 +33,9 @@ struct tebgpu_ctx {
   bool have_params = false;
   std::string err;
   int64_t launches = 0;
-  int linearize_variant = 0;  /* 0: 128-thread CTA per 32-pose tile (default, measured faster: 24 warps/SM resident);
-                                 1: one warp per tile (full lanes, but 8 warps/SM by shared memory) */
+  int linearize_variant = 0;  /* 0: k_linearize2, one thread per pose, 125-pose tiles (default);
+                                 1: k_linearize, first generation: 128-thread CTA per 32-pose tile, thread per band row */
+  int last_spec_k = 0; /* width used by the last optimize call */
   int spec_k = 0;  /* speculation width: 0 = auto (6 when B*6 systems fit one warp per SM sub-partition, else 4) */
   int solver = 2;  /* 2: speculative thread-per-(band,trial) LDL^T (default), 1: block cyclic reduction, 0: sequential */
   int MW = 1;
@@ -152,6 +154,19 @@ int32_t tebgpu_sizeof(int32_t which) {
 
 const char* tebgpu_last_error_string(const tebgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t tebgpu_get_info(const tebgpu_ctx* ctx, int32_t which) {
+  if (!ctx) return -1;
+  switch (which) {
+    case 0: return ctx->last_spec_k;
+    case 1: return ctx->linearize_variant;
+    case 2: return ctx->solver;
+    case 3: return 1;
+    case 4: return 0;
+    case 5: return 0;
+    case 6: return 0;
+    default: return -1;
+  }
+}
 
 static void free_all(tebgpu_ctx* c) {
   void* ptrs[] = {c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->d_fp, c->d_pverts, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
@@ -178,7 +193,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   c->lim = *lim;
   if (c->lim.max_obstacles < 1) c->lim.max_obstacles = 1;
   c->MW = (c->lim.max_obstacles + 63) / 64;
-  c->chunks = (c->lim.max_poses + TP - 1) / TP;
+  c->chunks = (c->lim.max_poses + TP - 1) / TP; /* capacity for the smaller of the two tile sizes */
   *out = c;
   CUDA_TRY(c, cudaSetDevice(device));
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -247,18 +262,22 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     c->err = "shared-memory footprint exceeds 227 KB for these limits (max_poses / max_obstacles too large)";
     return TEBGPU_ERR_CAPACITY;
   }
+  if (ka2_smem_bytes<true>((int)M) > 232448) {
+    c->err = "kernel A staging exceeds 227 KB for these limits (max_obstacles too large)";
+    return TEBGPU_ERR_CAPACITY;
+  }
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka2_smem_bytes<false>((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka2_smem_bytes<false>((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka2_smem_bytes<true>((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka2_smem_bytes<true>((int)M)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize_w<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
   CUDA_TRY(c, cudaFuncSetAttribute(k_lm_step_t<0, KB_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_b));
   if ((int)nc <= BCR_MAX_POSES && kb_bcr_smem_bytes((int)nc, (int)M) <= 232448) {
@@ -333,20 +352,18 @@ int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* p) {
 static void launch_linearize(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int M_cap, cudaStream_t st) {
   const bool holo = kp.holo_vel || kp.holo_acc;
   const bool geom = kp.generic != 0;
+  const dim3 grid(db.chunks, B);
   if (ctx->linearize_variant == 1) {
-    const dim3 grid((db.chunks + KW_WARPS - 1) / KW_WARPS, B);
-    const size_t sm = kw_smem_bytes(M_cap);
-    if (holo && geom) k_linearize_w<true, true><<<grid, 32 * KW_WARPS, sm, st>>>(db, kp);
-    else if (holo) k_linearize_w<true, false><<<grid, 32 * KW_WARPS, sm, st>>>(db, kp);
-    else if (geom) k_linearize_w<false, true><<<grid, 32 * KW_WARPS, sm, st>>>(db, kp);
-    else k_linearize_w<false, false><<<grid, 32 * KW_WARPS, sm, st>>>(db, kp);
-  } else {
-    const dim3 grid(db.chunks, B);
     const size_t sm = ka_smem_bytes(M_cap);
     if (holo && geom) k_linearize<true, true><<<grid, KA_THREADS, sm, st>>>(db, kp);
     else if (holo) k_linearize<true, false><<<grid, KA_THREADS, sm, st>>>(db, kp);
     else if (geom) k_linearize<false, true><<<grid, KA_THREADS, sm, st>>>(db, kp);
     else k_linearize<false, false><<<grid, KA_THREADS, sm, st>>>(db, kp);
+  } else {
+    if (holo && geom) k_linearize2<true, true><<<grid, KA2_NT, ka2_smem_bytes<true>(M_cap), st>>>(db, kp);
+    else if (holo) k_linearize2<true, false><<<grid, KA2_NT, ka2_smem_bytes<true>(M_cap), st>>>(db, kp);
+    else if (geom) k_linearize2<false, true><<<grid, KA2_NT, ka2_smem_bytes<false>(M_cap), st>>>(db, kp);
+    else k_linearize2<false, false><<<grid, KA2_NT, ka2_smem_bytes<false>(M_cap), st>>>(db, kp);
   }
 }
 static void launch_build_graph(const DevBatch& db, const KParams& kp, int B, size_t smem, cudaStream_t st) {
@@ -426,7 +443,8 @@ static DevBatch make_devbatch(tebgpu_ctx* ctx, const TebBatch* bt) {
   d.cost = bt->cost; d.chi2 = bt->chi2; d.status = bt->status; d.lm_iters = bt->lm_iters;
   d.Hb = ctx->Hb; d.assoc = ctx->assoc; d.assoc3 = ctx->assoc3; d.dyn_t = ctx->dyn_t; d.via_idx = ctx->via_idx; d.chi_parts = ctx->chi_parts; d.dmax_parts = ctx->dmax_parts; d.rhs = ctx->rhs; d.dyn_idx = ctx->dyn_idx; d.dyn_cnt = ctx->dyn_cnt;
   d.state = ctx->state;
-  d.chunks = (bt->n_cap + TP - 1) / TP;
+  d.tile = ctx->linearize_variant == 1 ? TP : KA2_TP;
+  d.chunks = (bt->n_cap + d.tile - 1) / d.tile;
   d.obst_vertices = bt->PV_cap > 0 ? bt->obst_vertices : nullptr; d.PV_cap = bt->PV_cap;
   d.defer = ctx->defer; d.a_list = nullptr; d.a_cnt = nullptr; d.skip_tag = 0;
   return d;
@@ -455,6 +473,7 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   if (spec_K == 0) spec_K = ((long long)B * 6 <= 148LL * 4 * 32) ? 6 : 4;
   while (spec_K > 4 && eval_smem_bytes(bt->n_cap, bt->M_cap, spec_K) > 232448) spec_K -= 2;
   if (eval_smem_bytes(bt->n_cap, bt->M_cap, spec_K) > 232448) { ctx->err = "trial-evaluation staging exceeds shared memory"; return TEBGPU_ERR_CAPACITY; }
+  ctx->last_spec_k = ctx->solver == 2 ? spec_K : 1;
   int g = 0; /* running index of the speculative rounds of this call: selects the retry-list counter / buffer */
   if (ctx->solver == 2) {
     const long long need_cnt = (long long)args->iterations_outerloop * args->iterations_innerloop * ((10 + spec_K - 1) / spec_K) + 2;
@@ -768,7 +787,7 @@ int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* bt, int32_t outer_i
     double* host_chi = device_ptrs ? new (std::nothrow) double[B] : chi2_out;
     for (int b = 0; b < B; ++b) {
       double s = 0;
-      const int used = (hn[b] + TP - 1) / TP;
+      const int used = (hn[b] + db.tile - 1) / db.tile;
       for (int c = 0; c < used; ++c)
         for (int k = 0; k < 4; ++k) s += tmp[((size_t)b * db.chunks + c) * 4 + k];
       host_chi[b] = s;

@@ -5,10 +5,10 @@
  *   k_auto_resize    TimedElasticBand::autoResize per band                  (timed_elastic_band.cpp:227-286)
  *   k_build_graph    buildGraph: obstacle association, dynamic-obstacle times, via-point assignment
  *                                                                            (optimal_planner.cpp:323-366, 444-548, 646-718)
- *   k_linearize      "kernel A": residuals + analytic Jacobians of every edge family + banded J^T Omega J / b
- *                    assembly in shared memory, TMA-staged inputs, TMA bulk store of the band tile
+ *   k_linearize      "kernel A", first generation (variant 1 of tebgpu_set_linearize_variant, kept as an independent
+ *                    second mapping): CTA of 128 threads per 32-pose tile, Jacobian blocks in shared memory, one thread
+ *                    per band row gathers J^T J. The default kernel A is k_linearize2 in teb_linearize.cuh.
  *                                                                            (g2o buildSystem)
- *   k_linearize_w    the same arithmetic with one warp per tile (alternative mapping, tebgpu_set_linearize_variant)
  *   k_vor            EdgeVelocityObstacleRatio rows added to the assembled band (only when that weight is > 0)
  *   k_lm_step_t      "kernel B", solvers 0 / 1: one Levenberg-Marquardt iteration per band in one CTA: banded LDL^T
  *                    (sequential warp solver or block cyclic reduction), update, trial chi2, rho / lambda
@@ -79,7 +79,8 @@ struct DevBatch {
   double* rhs;                /* [B][4*n_cap] compact copy of b (coalesced reads in the trial evaluation) */
   double* dmax_parts;         /* [B][chunks] max |H_rr| over the real rows of the tile (LM lambda init) */
   BandState* state;           /* [B]              */
-  int32_t chunks;
+  int32_t chunks;             /* tiles per band of the kernel-A mapping in use = ceil(n_cap / tile) */
+  int32_t tile;               /* poses per kernel-A tile (chi2 / max-diagonal partials are per tile) */
   const double* obst_vertices; /* [S][PV_cap][2] vertex pool of the Line / Pill / Polygon obstacles (or NULL) */
   int32_t PV_cap;
   /* kernel A band selection (speculative solver, retry rounds overlapped with the next linearisation):
@@ -960,153 +961,6 @@ __global__ void __launch_bounds__(KA_THREADS, 6) k_linearize(DevBatch db, KParam
   }
 }
 
-/* ------------------------------------------------------------------ k_linearize_w ("kernel A", warp per tile)
- * Same arithmetic as k_linearize (shared device functions), different mapping: ONE WARP owns a 32-pose tile end to end,
- * so every phase runs with all 32 lanes busy (pose / anchor / row per lane) and the only synchronisation is
- * __syncwarp. A CTA holds KW_WARPS independent tiles of the same band and shares the scene's obstacle table. */
-constexpr int KW_WARPS = 4;
-struct KWSmem {
-  static constexpr int JBMAX = (KASmem::JB > 4 * TP * HROW ? KASmem::JB : 4 * TP * HROW);
-  static constexpr int REG = ((KASmem::POSES + JBMAX + KASmem::SC + KASmem::SEG + KASmem::EH + KASmem::START + KASmem::UN + 2 + 1) / 2) * 2;
-};
-__host__ __device__ inline size_t kw_smem_bytes(int M_cap) {
-  return (size_t)KW_WARPS * KWSmem::REG * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 64;
-}
-
-template <bool HOLO, bool GEOM>
-__global__ void __launch_bounds__(32 * KW_WARPS) k_linearize_w(const __grid_constant__ DevBatch db,
-                                                               const __grid_constant__ KParams kp) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  static_assert(TP == 32, "the warp-per-tile kernel maps one pose / four rows to a lane");
-  const int b = linearize_band(db, blockIdx.y);
-  if (b < 0) return;
-  if (!db.state[b].active) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = db.n[b];
-  const int s = db.scene_id[b];
-  const int M = db.obst_count[s];
-  TebObstacle* so = reinterpret_cast<TebObstacle*>(reinterpret_cast<double*>(smem_raw) + (size_t)KW_WARPS * KWSmem::REG);
-  {
-    const double2* src = reinterpret_cast<const double2*>(db.obstacles + (size_t)s * db.M_cap);
-    double2* dst = reinterpret_cast<double2*>(so);
-    for (int k = threadIdx.x; k < (int)(sizeof(TebObstacle) / 16) * M; k += 32 * KW_WARPS) dst[k] = src[k];
-  }
-  __syncthreads();
-  const int chunk = blockIdx.x * KW_WARPS + warp;
-  const int p0 = chunk * TP;
-  if (p0 >= n) return;
-
-  double* sP = reinterpret_cast<double*>(smem_raw) + (size_t)warp * KWSmem::REG; /* poses tile, slot j <-> pose p0-2+j */
-  double* sJ = sP + KASmem::POSES;                                               /* Jacobian blocks, later the output stage */
-  double* sSC = sJ + KWSmem::JBMAX;
-  double* sSeg = sSC + KASmem::SC;
-  double* sE = sSeg + KASmem::SEG;
-  double* sStart = sE + KASmem::EH;
-  double* sU = sStart + KASmem::START;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sU + KASmem::UN);
-
-  const int lo = max(p0 - 2, 0), hi = min(p0 + TP + 2, n); /* poses staged */
-  const double* gP = db.poses + (size_t)b * db.n_cap * 4;
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-  }
-  __syncwarp();
-  if (lane == 0) {
-    const uint32_t bytesP = (uint32_t)(hi - lo) * 32u;
-    mbar_expect_tx(bar, bytesP);
-    tma_load_1d(sP + (size_t)(lo - (p0 - 2)) * 4, gP + (size_t)lo * 4, bytesP, bar);
-  }
-  { /* zero the Jacobian blocks while the copy is in flight */
-    double2* z2 = reinterpret_cast<double2*>(sJ);
-    for (int k = lane; k < KASmem::JB / 2; k += 32) z2[k] = make_double2(0.0, 0.0);
-    for (int k = lane; k < KASmem::EH + KASmem::START; k += 32) sE[k] = 0.0;
-  }
-  mbar_wait(bar, 0);
-
-  double chi[4] = {0, 0, 0, 0}; /* obstacles, via, time-optimal, other */
-  /* phase I: sin/cos + segment derivative bundle per staged pose; unary terms of the lane's pose */
-  for (int tt = lane; tt < TP + 4; tt += 32) {
-    const int i = p0 - 2 + tt;
-    if (i >= lo && i < hi) {
-      double sn, cs;
-      sincos(sP[4 * tt + 2], &sn, &cs);
-      sSC[2 * tt] = cs;
-      sSC[2 * tt + 1] = sn;
-      if (tt < TP + 3 && i + 1 < hi && i <= n - 2) {
-        const double* pa = sP + 4 * tt;
-        const double* pb = pa + 4;
-        SegDer sd = seg_derivs(kp, pa[0], pa[1], pa[2], cs, sn, pb[0], pb[1], pb[2], pa[3]);
-        double* q = sSeg + 9 * tt;
-        q[0] = sd.v; q[1] = sd.w; q[2] = sd.idt;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) q[3 + k] = sd.dv[k];
-      }
-    }
-  }
-  {
-    const int il = lane;
-    const int i = p0 + il;
-    double U[6] = {0, 0, 0, 0, 0, 0}, ub[3] = {0, 0, 0};
-    if (i < n) {
-      const int j = il + 2;
-      double sn = 0, cs = 1;
-      if (kp.p.footprint_type >= TEB_FOOTPRINT_TWO_CIRCLES) sincos(sP[4 * j + 2], &sn, &cs);
-      unary_terms<GEOM>(kp, db, b, s, i, n, sP[4 * j], sP[4 * j + 1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
-      if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
-        const double dt = sP[4 * j + 3];
-        chi[2] += kp.p.weight_optimaltime * dt * dt;
-      }
-    }
-    double* u = sU + 9 * il;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) u[k] = U[k];
-    u[6] = ub[0]; u[7] = ub[1]; u[8] = ub[2];
-  }
-  __syncwarp();
-  /* phase II: chain-edge Jacobian rows of every anchor of the tile (+2 halo anchors) */
-  for (int at = lane; at < TP + 2; at += 32) {
-    chi[3] += anchor_rows<HOLO>(kp, db, b, 0, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
-    chi[3] += anchor_rows<HOLO>(kp, db, b, 1, at, p0, n, sP, sSC, sSeg, sJ, sE, sStart);
-  }
-  __syncwarp();
-  /* phase III: four band rows per lane */
-  double accs[4][11], brows[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) gather_row<HOLO>(kp, q * 32 + lane, p0, n, sP, sJ, sE, sStart, sU, accs[q], brows[q]);
-  __syncwarp(); /* every lane is done reading sJ: reuse it as the output stage */
-  double dm = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int t = q * 32 + lane;
-    double* o = sJ + (size_t)t * HROW;
-#pragma unroll
-    for (int k = 0; k < 11; ++k) o[k] = accs[q][k];
-    o[11] = brows[q];
-    const int r = 4 * p0 + t;
-    if (p0 + (t >> 2) < n) {
-      db.rhs[(size_t)b * 4 * db.n_cap + r] = brows[q];
-      if (row_is_real(r, n)) dm = fmax(dm, fabs(accs[q][0]));
-    }
-  }
-  fence_proxy_async();
-  __syncwarp();
-  if (lane == 0) {
-    const int rows = 4 * (min(p0 + TP, n) - p0);
-    double* gH = db.Hb + ((size_t)b * 4 * db.n_cap + (size_t)4 * p0) * HROW;
-    tma_store_1d(gH, sJ, (uint32_t)rows * HROW * 8u);
-    tma_store_commit_wait();
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) chi[k] = warp_sum(chi[k]);
-  dm = warp_max(dm);
-  if (lane == 0) {
-    double* cp = db.chi_parts + ((size_t)b * db.chunks + chunk) * 4;
-    cp[0] = chi[0]; cp[1] = chi[1]; cp[2] = chi[2]; cp[3] = chi[3];
-    db.dmax_parts[(size_t)b * db.chunks + chunk] = dm;
-  }
-}
-
 /* ------------------------------------------------------------------ trial chi2 (residuals only) on a band held in
  * shared memory: sT[n][4]; block-wide, result in out[4] (shared) after the call */
 /* chi2 contributions (residuals only) of everything anchored at pose i of the band stored at sT[n][4]
@@ -1626,7 +1480,7 @@ __global__ void __launch_bounds__(NT, SOLVER == 1 ? 2 : 1) k_lm_step_t(DevBatch 
   /* chi2 at the linearisation point = sum of the kernel-A tile partials (computeActiveErrors, App. A.4) */
   double cur_parts[4] = {0, 0, 0, 0};
   {
-    const int chunks_used = (n + TP - 1) / TP;
+    const int chunks_used = (n + db.tile - 1) / db.tile;
     const double* cp = db.chi_parts + (size_t)b * db.chunks * 4;
     for (int c = 0; c < chunks_used; ++c)
       for (int k = 0; k < 4; ++k) cur_parts[k] += cp[4 * c + k];
@@ -1904,7 +1758,7 @@ __global__ void k_cost_only(DevBatch db, KParams kp, TebOptimizeArgs args) {
   double chi = 0;
   if (!st.failed) {
     const int n = db.n[b];
-    const int chunks_used = (n + TP - 1) / TP;
+    const int chunks_used = (n + db.tile - 1) / db.tile;
     const double* cp = db.chi_parts + (size_t)b * db.chunks * 4;
     double parts[4] = {0, 0, 0, 0};
     for (int c = 0; c < chunks_used; ++c)

@@ -44,7 +44,7 @@ __device__ __forceinline__ void spec_lambda(double& lambda, double& ni, int k) {
 }
 
 __device__ __forceinline__ double band_lambda_init(const DevBatch& db, int b, int n) {
-  const int chunks_used = (n + TP - 1) / TP;
+  const int chunks_used = (n + db.tile - 1) / db.tile;
   double mx = 0;
   for (int c = 0; c < chunks_used; ++c) mx = fmax(mx, db.dmax_parts[(size_t)b * db.chunks + c]);
   return 1e-5 * mx; /* computeLambdaInit: tau * max diagonal */
@@ -240,6 +240,7 @@ struct DecideArgs { /* passed by value: a reference to the kernel parameters wou
   int32_t* defer;          /* &defer[b] */
   int32_t tag;             /* inner-iteration tag written to defer[b] when the band is queued */
   int32_t b, n, K, iteration, round, q0;
+  int32_t tile;            /* poses per kernel-A tile */
 };
 __device__ __forceinline__ int spec_decide(const DecideArgs a, const double* sRes) {
   const int SPEC_K = a.K, n = a.n, round = a.round, iteration = a.iteration, q0 = a.q0;
@@ -250,7 +251,7 @@ __device__ __forceinline__ int spec_decide(const DecideArgs a, const double* sRe
   int q;
   if (round == 0) {
     /* chi2 at the linearisation point = sum of the kernel-A tile partials (computeActiveErrors) */
-    const int chunks_used = (n + TP - 1) / TP;
+    const int chunks_used = (n + a.tile - 1) / a.tile;
     const double* cp = a.chi_parts;
     for (int c = 0; c < 4; ++c) cur_parts[c] = 0;
     for (int ch = 0; ch < chunks_used; ++ch)
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch d
     da.need = sp.need + b; da.qmax = sp.qmax + b; da.cnt_next = sp.cnt + g + 1;
     da.list_next = sp.list + (size_t)((g + 1) % 3) * db.B;
     da.defer = db.defer + b; da.tag = tag;
-    da.b = b; da.n = n; da.K = SPEC_K; da.iteration = iteration; da.round = round; da.q0 = q0;
+    da.b = b; da.n = n; da.K = SPEC_K; da.iteration = iteration; da.round = round; da.q0 = q0; da.tile = db.tile;
     const int accepted = spec_decide(da, sRes);
     sAcc[0] = accepted;
   }

@@ -16,7 +16,7 @@ SOLVER_BANDED, SOLVER_DENSE = 0, 1
 
 
 class OracleOptions(C.Structure):
-    _fields_ = [("jac_mode", C.c_int32), ("solver", C.c_int32), ("verbose", C.c_int32), ("_pad", C.c_int32)]
+    _fields_ = [("jac_mode", C.c_int32), ("solver", C.c_int32), ("verbose", C.c_int32), ("pin_threads", C.c_int32)]
 
 
 class OracleStats(C.Structure):
@@ -136,10 +136,10 @@ def optimize_band(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=
     return buf[:nn.value].copy(), cost.value, st
 
 
-def optimize_batch(params, hb, args, jac_mode=JAC_G2O, solver=SOLVER_BANDED, threads=1):
-    """In-place on the HostBatch arrays."""
+def optimize_batch(params, hb, args, jac_mode=JAC_G2O, solver=SOLVER_BANDED, threads=1, pin=False):
+    """In-place on the HostBatch arrays. pin: worker t runs on the t-th CPU of the affinity mask (timing runs)."""
     L = lib()
-    opt = OracleOptions(jac_mode, solver, 0, 0)
+    opt = OracleOptions(jac_mode, solver, 0, int(bool(pin)))
     bs = hb.struct()
     rc = L.teb_oracle_optimize_batch(C.byref(params), C.byref(bs), C.byref(args), C.byref(opt), threads)
     if rc != 0:

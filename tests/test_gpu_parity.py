@@ -72,7 +72,8 @@ def test_kernel_a_system_matches_oracle(oracle, cfg):
 
 
 def test_kernel_a_thread_mappings_agree():
-    """warp-per-tile and CTA-per-tile (default) kernel A share their arithmetic: band and chi2 equal to round-off"""
+    """thread-per-pose (default, k_linearize2) and thread-per-band-row (first generation) kernel A: two independent
+    mappings of the same formulas; band and chi2 equal to round-off (different summation order)"""
     p, hb = scenes.make_config_batch("C4", candidates=6, seed=2)
     g = _gpu(hb, p)
     g.set_linearize_variant(1)
@@ -80,9 +81,8 @@ def test_kernel_a_thread_mappings_agree():
     g.set_linearize_variant(0)
     H0, c0 = g.build_system(hb, 2)
     g.close()
-    # same device functions, two kernels: the compiler may contract multiply-adds differently, nothing more
-    assert np.abs(H1 - H0).max() <= 1e-13 * np.abs(H0).max()
-    assert np.allclose(c1, c0, rtol=1e-13)
+    assert np.abs(H1 - H0).max() <= 1e-12 * np.abs(H0).max()
+    assert np.allclose(c1, c0, rtol=1e-12)
 
 
 def test_kernel_a_all_edge_families(oracle):
