@@ -1,0 +1,401 @@
+/*
+ * ref_driver.cpp — C interface over the REFERENCE'S OWN sources, compiled where they lie under /root/reference
+ * (TEST INFRASTRUCTURE; builds oracle/_ref/libteb_ref.so, see oracle/Makefile target `ref`).
+ *
+ * Compiled from the reference, unmodified: src/optimal_planner.cpp (optimizeTEB, buildGraph, every AddEdges*,
+ * optimizeGraph, computeCurrentCost, hasDiverged), src/timed_elastic_band.cpp (+ .hpp: autoResize, initTrajectoryToGoal,
+ * updateAndPruneTEB, findClosestTrajectoryPose), src/obstacles.cpp, and every header they include from
+ * include/teb_local_planner/ (g2o_types/edge_*.h computeError / linearizeOplus bodies, penalties.h, misc.h,
+ * distance_calculations.h, obstacles.h, robot_footprint_model.h, pose_se2.h, teb_config.h incl. the TebConfig() defaults).
+ * NOT from the reference (absent third-party code, replaced by oracle/ref_shims/): Eigen (a small fixed-size matrix
+ * class), boost / ROS message types (plain structs), and g2o - its vertex / edge base classes, numeric linearizeOplus,
+ * Levenberg-Marquardt loop and linear solver are restated in ref_shims/g2o/ following SURVEY.md Appendix A.
+ * So oracle/_ref pins the oracle restatement (oracle/teb_oracle.c) for everything that IS reference code; only the g2o
+ * optimizer internals remain "restated from published behaviour".
+ */
+#include <teb_local_planner/optimal_planner.h>
+#include <teb_local_planner/g2o_types/penalties.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../include/teb_b200.h"
+
+using namespace teb_local_planner;
+
+/* teb_config.cpp is not compiled (ROS parameter server); the few out-of-line members are never called here */
+namespace {
+
+struct Scene {
+  TebConfig cfg;
+  ObstContainer obstacles;
+  ViaPointContainer via;
+};
+
+void fill_config(const TebParams* p, TebConfig& c) {
+  c.trajectory.teb_autosize = p->teb_autosize;
+  c.trajectory.dt_ref = p->dt_ref;
+  c.trajectory.dt_hysteresis = p->dt_hysteresis;
+  c.trajectory.min_samples = p->min_samples;
+  c.trajectory.max_samples = p->max_samples;
+  c.trajectory.exact_arc_length = p->exact_arc_length != 0;
+  c.trajectory.via_points_ordered = p->via_points_ordered != 0;
+  c.trajectory.allow_init_with_backwards_motion = p->allow_init_with_backwards_motion != 0;
+  c.trajectory.global_plan_overwrite_orientation = p->global_plan_overwrite_orientation != 0;
+  c.trajectory.force_reinit_new_goal_dist = p->force_reinit_new_goal_dist;
+  c.trajectory.force_reinit_new_goal_angular = p->force_reinit_new_goal_angular;
+  c.robot.max_vel_x = p->max_vel_x;
+  c.robot.max_vel_x_backwards = p->max_vel_x_backwards;
+  c.robot.max_vel_y = p->max_vel_y;
+  c.robot.max_vel_trans = p->max_vel_trans;
+  c.robot.max_vel_theta = p->max_vel_theta;
+  c.robot.acc_lim_x = p->acc_lim_x;
+  c.robot.acc_lim_y = p->acc_lim_y;
+  c.robot.acc_lim_theta = p->acc_lim_theta;
+  c.robot.min_turning_radius = p->min_turning_radius;
+  c.obstacles.min_obstacle_dist = p->min_obstacle_dist;
+  c.obstacles.inflation_dist = p->inflation_dist;
+  c.obstacles.dynamic_obstacle_inflation_dist = p->dynamic_obstacle_inflation_dist;
+  c.obstacles.include_dynamic_obstacles = p->include_dynamic_obstacles != 0;
+  c.obstacles.legacy_obstacle_association = p->legacy_obstacle_association != 0;
+  c.obstacles.obstacle_poses_affected = p->obstacle_poses_affected;
+  c.obstacles.obstacle_association_force_inclusion_factor = p->obstacle_association_force_inclusion_factor;
+  c.obstacles.obstacle_association_cutoff_factor = p->obstacle_association_cutoff_factor;
+  c.obstacles.obstacle_proximity_ratio_max_vel = p->obstacle_proximity_ratio_max_vel;
+  c.obstacles.obstacle_proximity_lower_bound = p->obstacle_proximity_lower_bound;
+  c.obstacles.obstacle_proximity_upper_bound = p->obstacle_proximity_upper_bound;
+  c.optim.no_inner_iterations = p->no_inner_iterations;
+  c.optim.no_outer_iterations = p->no_outer_iterations;
+  c.optim.optimization_activate = p->optimization_activate != 0;
+  c.optim.optimization_verbose = false;
+  c.optim.penalty_epsilon = p->penalty_epsilon;
+  c.optim.weight_max_vel_x = p->weight_max_vel_x;
+  c.optim.weight_max_vel_y = p->weight_max_vel_y;
+  c.optim.weight_max_vel_theta = p->weight_max_vel_theta;
+  c.optim.weight_acc_lim_x = p->weight_acc_lim_x;
+  c.optim.weight_acc_lim_y = p->weight_acc_lim_y;
+  c.optim.weight_acc_lim_theta = p->weight_acc_lim_theta;
+  c.optim.weight_kinematics_nh = p->weight_kinematics_nh;
+  c.optim.weight_kinematics_forward_drive = p->weight_kinematics_forward_drive;
+  c.optim.weight_kinematics_turning_radius = p->weight_kinematics_turning_radius;
+  c.optim.weight_optimaltime = p->weight_optimaltime;
+  c.optim.weight_shortest_path = p->weight_shortest_path;
+  c.optim.weight_obstacle = p->weight_obstacle;
+  c.optim.weight_inflation = p->weight_inflation;
+  c.optim.weight_dynamic_obstacle = p->weight_dynamic_obstacle;
+  c.optim.weight_dynamic_obstacle_inflation = p->weight_dynamic_obstacle_inflation;
+  c.optim.weight_velocity_obstacle_ratio = p->weight_velocity_obstacle_ratio;
+  c.optim.weight_viapoint = p->weight_viapoint;
+  c.optim.weight_prefer_rotdir = p->weight_prefer_rotdir;
+  c.optim.weight_adapt_factor = p->weight_adapt_factor;
+  c.optim.obstacle_cost_exponent = p->obstacle_cost_exponent;
+  c.hcp.selection_cost_hysteresis = p->selection_cost_hysteresis;
+  c.hcp.selection_prefer_initial_plan = p->selection_prefer_initial_plan;
+  c.hcp.selection_obst_cost_scale = p->selection_obst_cost_scale;
+  c.hcp.selection_viapoint_cost_scale = p->selection_viapoint_cost_scale;
+  c.hcp.selection_alternative_time_cost = p->selection_alternative_time_cost != 0;
+  c.hcp.enable_multithreading = p->enable_multithreading != 0;
+  c.hcp.h_signature_prescaler = p->h_signature_prescaler;
+  c.hcp.h_signature_threshold = p->h_signature_threshold;
+  c.recovery.divergence_detection_enable = p->divergence_detection_enable != 0;
+  c.recovery.divergence_detection_max_chi_squared = (int)p->divergence_detection_max_chi_squared;
+  switch (p->footprint_type) {
+    case TEB_FOOTPRINT_CIRCULAR: c.robot_model = boost::make_shared<CircularRobotFootprint>(p->footprint_radius); break;
+    case TEB_FOOTPRINT_TWO_CIRCLES:
+      c.robot_model = boost::make_shared<TwoCirclesRobotFootprint>(p->footprint_front_offset, p->footprint_front_radius,
+                                                                    p->footprint_rear_offset, p->footprint_rear_radius);
+      break;
+    case TEB_FOOTPRINT_LINE:
+      c.robot_model = boost::make_shared<LineRobotFootprint>(Eigen::Vector2d(p->footprint_line[0], p->footprint_line[1]),
+                                                              Eigen::Vector2d(p->footprint_line[2], p->footprint_line[3]), 0.0);
+      break;
+    case TEB_FOOTPRINT_POLYGON: {
+      Point2dContainer v;
+      for (int k = 0; k < p->footprint_vertex_count; ++k) v.push_back(Eigen::Vector2d(p->footprint_vertices[2 * k], p->footprint_vertices[2 * k + 1]));
+      c.robot_model = boost::make_shared<PolygonRobotFootprint>(v);
+      break;
+    }
+    default: c.robot_model = boost::make_shared<PointRobotFootprint>(); break;
+  }
+}
+
+ObstaclePtr make_obstacle(const TebObstacle& o, const double* verts) {
+  ObstaclePtr ob;
+  switch (o.type) {
+    case TEB_OBST_CIRCULAR: ob = ObstaclePtr(new CircularObstacle(o.x, o.y, o.radius)); break;
+    case TEB_OBST_LINE: {
+      const double* v = verts + 2 * (size_t)o.vertex_begin;
+      ob = ObstaclePtr(new LineObstacle(v[0], v[1], v[2], v[3]));
+      break;
+    }
+    case TEB_OBST_PILL: {
+      const double* v = verts + 2 * (size_t)o.vertex_begin;
+      ob = ObstaclePtr(new PillObstacle(v[0], v[1], v[2], v[3], o.radius));
+      break;
+    }
+    case TEB_OBST_POLYGON: {
+      PolygonObstacle* po = new PolygonObstacle();
+      for (int k = 0; k < o.vertex_count; ++k) po->pushBackVertex(verts[2 * (size_t)(o.vertex_begin + k)], verts[2 * (size_t)(o.vertex_begin + k) + 1]);
+      po->finalizePolygon();
+      ob = ObstaclePtr(po);
+      break;
+    }
+    default: ob = ObstaclePtr(new PointObstacle(o.x, o.y)); break;
+  }
+  if (o.dynamic) ob->setCentroidVelocity(Eigen::Vector2d(o.vx, o.vy));
+  return ob;
+}
+
+void fill_scene(Scene& s, const TebParams* p, const TebObstacle* obst, int M, const double* verts, const double* via, int V) {
+  fill_config(p, s.cfg);
+  for (int m = 0; m < M; ++m) s.obstacles.push_back(make_obstacle(obst[m], verts));
+  for (int v = 0; v < V; ++v) s.via.push_back(Eigen::Vector2d(via[2 * v], via[2 * v + 1]));
+}
+
+/* opens the protected graph functions of the reference planner */
+class RefPlanner : public TebOptimalPlanner {
+ public:
+  RefPlanner(const TebConfig& cfg, ObstContainer* obst, const ViaPointContainer* via) : TebOptimalPlanner(cfg, obst, TebVisualizationPtr(), via) {}
+  using TebOptimalPlanner::buildGraph;
+  using TebOptimalPlanner::clearGraph;
+};
+
+void load_band(TimedElasticBand& teb, const double* rec, int n) {
+  /* same container state as initTrajectoryToGoal leaves behind: first and last pose fixed (timed_elastic_band.cpp:330,377) */
+  for (int i = 0; i < n; ++i) {
+    teb.addPose(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], i == 0 || i == n - 1);
+    if (i < n - 1) teb.addTimeDiff(rec[4 * i + 3]);
+  }
+}
+void store_band(const TimedElasticBand& teb, double* rec, int n_cap) {
+  const int n = teb.sizePoses();
+  for (int i = 0; i < n && i < n_cap; ++i) {
+    rec[4 * i] = teb.Pose(i).x(); rec[4 * i + 1] = teb.Pose(i).y(); rec[4 * i + 2] = teb.Pose(i).theta();
+    rec[4 * i + 3] = i < teb.sizeTimeDiffs() ? teb.TimeDiff(i) : 0.0;
+  }
+}
+void set_velocities(RefPlanner& pl, const double* vs, const double* vg, int rotdir) {
+  /* vel_start_.first / vel_goal_.first are true with zero twists after construction (optimal_planner.cpp:94-102) */
+  if (vs && vs[3] != 0) {
+    geometry_msgs::Twist t;
+    t.linear.x = vs[0]; t.linear.y = vs[1]; t.angular.z = vs[2];
+    pl.setVelocityStart(t);
+  }
+  if (vg) {
+    if (vg[3] != 0) {
+      geometry_msgs::Twist t;
+      t.linear.x = vg[0]; t.linear.y = vg[1]; t.angular.z = vg[2];
+      pl.setVelocityGoal(t);
+    } else {
+      pl.setVelocityGoalFree();
+    }
+  }
+  pl.setPreferredTurningDir(rotdir == TEB_ROTDIR_LEFT ? RotType::left : (rotdir == TEB_ROTDIR_RIGHT ? RotType::right : RotType::none));
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t teb_ref_abi(void) { return 2; }
+
+/* TebConfig::TebConfig() (teb_config.h:245-390) read back through the POD mirror */
+void teb_ref_default_params(TebParams* p) {
+  std::memset(p, 0, sizeof(*p));
+  TebConfig c;
+  p->dt_ref = c.trajectory.dt_ref; p->dt_hysteresis = c.trajectory.dt_hysteresis;
+  p->force_reinit_new_goal_dist = c.trajectory.force_reinit_new_goal_dist;
+  p->force_reinit_new_goal_angular = c.trajectory.force_reinit_new_goal_angular;
+  p->teb_autosize = c.trajectory.teb_autosize != 0; p->min_samples = c.trajectory.min_samples; p->max_samples = c.trajectory.max_samples;
+  p->exact_arc_length = c.trajectory.exact_arc_length; p->via_points_ordered = c.trajectory.via_points_ordered;
+  p->allow_init_with_backwards_motion = c.trajectory.allow_init_with_backwards_motion;
+  p->global_plan_overwrite_orientation = c.trajectory.global_plan_overwrite_orientation;
+  p->max_vel_x = c.robot.max_vel_x; p->max_vel_x_backwards = c.robot.max_vel_x_backwards; p->max_vel_y = c.robot.max_vel_y;
+  p->max_vel_trans = c.robot.max_vel_trans; p->max_vel_theta = c.robot.max_vel_theta;
+  p->acc_lim_x = c.robot.acc_lim_x; p->acc_lim_y = c.robot.acc_lim_y; p->acc_lim_theta = c.robot.acc_lim_theta;
+  p->min_turning_radius = c.robot.min_turning_radius;
+  p->footprint_type = TEB_FOOTPRINT_POINT;
+  p->min_obstacle_dist = c.obstacles.min_obstacle_dist; p->inflation_dist = c.obstacles.inflation_dist;
+  p->dynamic_obstacle_inflation_dist = c.obstacles.dynamic_obstacle_inflation_dist;
+  p->obstacle_association_force_inclusion_factor = c.obstacles.obstacle_association_force_inclusion_factor;
+  p->obstacle_association_cutoff_factor = c.obstacles.obstacle_association_cutoff_factor;
+  p->obstacle_proximity_ratio_max_vel = c.obstacles.obstacle_proximity_ratio_max_vel;
+  p->obstacle_proximity_lower_bound = c.obstacles.obstacle_proximity_lower_bound;
+  p->obstacle_proximity_upper_bound = c.obstacles.obstacle_proximity_upper_bound;
+  p->include_dynamic_obstacles = c.obstacles.include_dynamic_obstacles;
+  p->legacy_obstacle_association = c.obstacles.legacy_obstacle_association;
+  p->obstacle_poses_affected = c.obstacles.obstacle_poses_affected;
+  p->penalty_epsilon = c.optim.penalty_epsilon;
+  p->weight_max_vel_x = c.optim.weight_max_vel_x; p->weight_max_vel_y = c.optim.weight_max_vel_y; p->weight_max_vel_theta = c.optim.weight_max_vel_theta;
+  p->weight_acc_lim_x = c.optim.weight_acc_lim_x; p->weight_acc_lim_y = c.optim.weight_acc_lim_y; p->weight_acc_lim_theta = c.optim.weight_acc_lim_theta;
+  p->weight_kinematics_nh = c.optim.weight_kinematics_nh; p->weight_kinematics_forward_drive = c.optim.weight_kinematics_forward_drive;
+  p->weight_kinematics_turning_radius = c.optim.weight_kinematics_turning_radius;
+  p->weight_optimaltime = c.optim.weight_optimaltime; p->weight_shortest_path = c.optim.weight_shortest_path;
+  p->weight_obstacle = c.optim.weight_obstacle; p->weight_inflation = c.optim.weight_inflation;
+  p->weight_dynamic_obstacle = c.optim.weight_dynamic_obstacle; p->weight_dynamic_obstacle_inflation = c.optim.weight_dynamic_obstacle_inflation;
+  p->weight_velocity_obstacle_ratio = c.optim.weight_velocity_obstacle_ratio;
+  p->weight_viapoint = c.optim.weight_viapoint; p->weight_prefer_rotdir = c.optim.weight_prefer_rotdir;
+  p->weight_adapt_factor = c.optim.weight_adapt_factor; p->obstacle_cost_exponent = c.optim.obstacle_cost_exponent;
+  p->no_inner_iterations = c.optim.no_inner_iterations; p->no_outer_iterations = c.optim.no_outer_iterations;
+  p->optimization_activate = c.optim.optimization_activate;
+  p->selection_cost_hysteresis = c.hcp.selection_cost_hysteresis; p->selection_prefer_initial_plan = c.hcp.selection_prefer_initial_plan;
+  p->selection_obst_cost_scale = c.hcp.selection_obst_cost_scale; p->selection_viapoint_cost_scale = c.hcp.selection_viapoint_cost_scale;
+  p->selection_alternative_time_cost = c.hcp.selection_alternative_time_cost; p->enable_multithreading = c.hcp.enable_multithreading;
+  p->h_signature_prescaler = c.hcp.h_signature_prescaler; p->h_signature_threshold = c.hcp.h_signature_threshold;
+  /* recovery.divergence_detection_* are left uninitialised by the reference's constructor: the
+   * dynamic_reconfigure defaults are reported instead */
+  p->divergence_detection_enable = 0; p->divergence_detection_max_chi_squared = 10;
+}
+
+/* penalties.h: which 0 penaltyBoundToInterval(var,a,eps) 1 (var,a,b,eps) 2 penaltyBoundFromBelow 3..5 their derivatives */
+double teb_ref_penalty(int32_t which, double var, double a, double b, double eps) {
+  switch (which) {
+    case 0: return penaltyBoundToInterval(var, a, eps);
+    case 1: return penaltyBoundToInterval(var, a, b, eps);
+    case 2: return penaltyBoundFromBelow(var, a, eps);
+    case 3: return penaltyBoundToIntervalDerivative(var, a, eps);
+    case 4: return penaltyBoundToIntervalDerivative(var, a, b, eps);
+    case 5: return penaltyBoundFromBelowDerivative(var, a, eps);
+    default: return NAN;
+  }
+}
+double teb_ref_fast_sigmoid(double x) { return fast_sigmoid(x); }
+
+/* robot_model->calculateDistance (t < 0) / estimateSpatioTemporalDistance (t >= 0) on the reference's own classes */
+double teb_ref_distance(const TebParams* p, const double* pose3, const TebObstacle* o, const double* verts, double t) {
+  TebConfig cfg;
+  fill_config(p, cfg);
+  ObstaclePtr ob = make_obstacle(*o, verts);
+  const PoseSE2 pose(pose3[0], pose3[1], pose3[2]);
+  if (t < 0) return cfg.robot_model->calculateDistance(pose, ob.get());
+  return cfg.robot_model->estimateSpatioTemporalDistance(pose, ob.get(), t);
+}
+
+/* TimedElasticBand::autoResize (timed_elastic_band.cpp:227-286) */
+int32_t teb_ref_auto_resize(double* rec, int32_t n, int32_t n_cap, double dt_ref, double dt_hysteresis, int32_t min_samples,
+                            int32_t max_samples, int32_t fast_mode) {
+  TimedElasticBand teb;
+  load_band(teb, rec, n);
+  teb.autoResize(dt_ref, dt_hysteresis, min_samples, max_samples, fast_mode != 0);
+  if (teb.sizePoses() > n_cap) return -1;
+  store_band(teb, rec, n_cap);
+  return teb.sizePoses();
+}
+
+/* TimedElasticBand::initTrajectoryToGoal(start, goal, diststep, max_vel_x, min_samples, guess_backwards_motion) :325-387 */
+int32_t teb_ref_init_trajectory(const double* start3, const double* goal3, double diststep, double max_vel_x, int32_t min_samples,
+                                int32_t backwards, double* rec, int32_t n_cap) {
+  TimedElasticBand teb;
+  teb.initTrajectoryToGoal(PoseSE2(start3[0], start3[1], start3[2]), PoseSE2(goal3[0], goal3[1], goal3[2]), diststep, max_vel_x,
+                           min_samples, backwards != 0);
+  if (teb.sizePoses() > n_cap) return -1;
+  store_band(teb, rec, n_cap);
+  return teb.sizePoses();
+}
+
+/* updateAndPruneTEB (timed_elastic_band.cpp:555-597) */
+int32_t teb_ref_update_and_prune(double* rec, int32_t n, int32_t n_cap, const double* new_start3, const double* new_goal3, int32_t min_samples) {
+  TimedElasticBand teb;
+  load_band(teb, rec, n);
+  const PoseSE2 s(new_start3[0], new_start3[1], new_start3[2]), g(new_goal3[0], new_goal3[1], new_goal3[2]);
+  teb.updateAndPruneTEB(s, g, min_samples);
+  store_band(teb, rec, n_cap);
+  return teb.sizePoses();
+}
+
+/* TebOptimalPlanner::optimizeTEB (optimal_planner.cpp:182-231) on one band. stats: [0] lm_trials [1] rejected trials
+ * [2] last optimize() ended with Terminate [3] a factorisation failed [4] hasDiverged() [5] isOptimized(). Returns 1/0 =
+ * optimizeTEB's return value. */
+int32_t teb_ref_optimize(const TebParams* p, double* rec, int32_t* n_io, int32_t n_cap, const TebObstacle* obst, int32_t M,
+                         const double* verts, const double* via, int32_t V, const double* vel_start4, const double* vel_goal4,
+                         int32_t rotdir, const TebOptimizeArgs* args, double* cost_out, double* stats6) {
+  Scene s;
+  fill_scene(s, p, obst, M, verts, via, V);
+  RefPlanner pl(s.cfg, &s.obstacles, &s.via);
+  load_band(pl.teb(), rec, *n_io);
+  set_velocities(pl, vel_start4, vel_goal4, rotdir);
+  const bool ok = pl.optimizeTEB(args->iterations_innerloop, args->iterations_outerloop, args->compute_cost_afterwards != 0,
+                                 args->obst_cost_scale, args->viapoint_cost_scale, args->alternative_time_cost != 0);
+  if (pl.teb().sizePoses() > n_cap) return -1;
+  store_band(pl.teb(), rec, n_cap);
+  *n_io = pl.teb().sizePoses();
+  if (cost_out) *cost_out = pl.getCurrentCost();
+  if (stats6) {
+    stats6[0] = (double)pl.optimizer()->lm_trials; stats6[1] = (double)pl.optimizer()->lm_rejected;
+    stats6[2] = pl.optimizer()->last_terminated; stats6[3] = pl.optimizer()->chol_failed;
+    stats6[4] = pl.hasDiverged(); stats6[5] = pl.isOptimized();
+  }
+  return ok ? 1 : 0;
+}
+
+/* computeCurrentCost called outside optimizeTEB (optimal_planner.cpp:1041-1094: graph rebuilt with multiplier 1) */
+double teb_ref_compute_cost(const TebParams* p, const double* rec, int32_t n, const TebObstacle* obst, int32_t M, const double* verts,
+                            const double* via, int32_t V, const double* vel_start4, const double* vel_goal4, int32_t rotdir,
+                            const TebOptimizeArgs* args) {
+  Scene s;
+  fill_scene(s, p, obst, M, verts, via, V);
+  RefPlanner pl(s.cfg, &s.obstacles, &s.via);
+  load_band(pl.teb(), rec, n);
+  set_velocities(pl, vel_start4, vel_goal4, rotdir);
+  pl.computeCurrentCost(args->obst_cost_scale, args->viapoint_cost_scale, args->alternative_time_cost != 0);
+  return pl.getCurrentCost();
+}
+
+/* buildGraph(weight_multiplier) + computeActiveErrors + buildSystem. H_dense [N][N] (full symmetric), b [N], N = system
+ * size in g2o order (dt_0, pose_1, dt_1, ...); chi2 = activeChi2. edges_out (optional, up to max_edges rows of 64
+ * doubles): per active edge in insertion order: [0] error dimension, [1] vertex count, [2..4] error, [5..7] information
+ * diagonal, [8 + 9 k ...] Jacobian of vertex k (row major dim x vdim, zero for fixed vertices), [53 + k] vertex dimension,
+ * [58 + k] vertex id. Returns N (or -1); *n_edges receives the number of active edges. */
+int32_t teb_ref_build_system(const TebParams* p, const double* rec, int32_t n, const TebObstacle* obst, int32_t M, const double* verts,
+                             const double* via, int32_t V, const double* vel_start4, const double* vel_goal4, int32_t rotdir,
+                             double weight_multiplier, double* H_dense, double* b, double* chi2, double* edges_out, int32_t max_edges,
+                             int32_t* n_edges) {
+  Scene s;
+  fill_scene(s, p, obst, M, verts, via, V);
+  RefPlanner pl(s.cfg, &s.obstacles, &s.via);
+  load_band(pl.teb(), rec, n);
+  set_velocities(pl, vel_start4, vel_goal4, rotdir);
+  if (!pl.buildGraph(weight_multiplier)) return -1;
+  g2o::SparseOptimizer& opt = *pl.optimizer();
+  opt.initializeOptimization();
+  opt.buildSystemOnly();
+  const int N = opt.systemSize(), W = opt.halfBandwidth() + 1;
+  if (H_dense) {
+    std::memset(H_dense, 0, sizeof(double) * (size_t)N * N);
+    for (int r = 0; r < N; ++r)
+      for (int k = 0; k < W && k <= r; ++k) {
+        const double v = opt.bandedH()[(size_t)r * W + k];
+        H_dense[(size_t)r * N + (r - k)] = v;
+        H_dense[(size_t)(r - k) * N + r] = v;
+      }
+  }
+  if (b) std::memcpy(b, opt.rhs().data(), sizeof(double) * (size_t)N);
+  double c2 = 0;
+  const g2o::SparseOptimizer::EdgeContainer& act = opt.activeEdges();
+  for (size_t k = 0; k < act.size(); ++k) {
+    g2o::OptimizableGraph::Edge* e = act[k];
+    const int D = e->dimension();
+    for (int d = 0; d < D; ++d) c2 += e->errorData()[d] * e->informationData()[d + D * d] * e->errorData()[d];
+    if (edges_out && (int)k < max_edges) {
+      double* row = edges_out + 64 * k;
+      std::memset(row, 0, 64 * sizeof(double));
+      row[0] = D; row[1] = (double)e->numVertices();
+      for (int d = 0; d < D; ++d) { row[2 + d] = e->errorData()[d]; row[5 + d] = e->informationData()[d + D * d]; }
+      for (size_t v = 0; v < e->numVertices() && v < 5; ++v) {
+        const int vd = e->vertexAt(v)->dimension();
+        row[53 + v] = vd; row[58 + v] = e->vertexAt(v)->id();
+        if (e->vertexAt(v)->fixed()) continue;
+        const double* J = e->jacobianData(v); /* column major D x vd */
+        for (int d = 0; d < D; ++d)
+          for (int a = 0; a < vd; ++a) row[8 + 9 * v + d * vd + a] = J[d + D * a];
+      }
+    }
+  }
+  if (chi2) *chi2 = c2;
+  if (n_edges) *n_edges = (int32_t)act.size();
+  pl.clearGraph();
+  return N;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,1 @@
+#include <g2o/core/sparse_optimizer.h>
