@@ -1883,6 +1883,51 @@ int32_t teb_oracle_build_system(const TebParams* cfg, const double* rec_in, int3
   return N;
 }
 
+/* Per-edge dump of the graph buildGraph() produces at the given state, in insertion order, after computeActiveErrors
+ * and linearisation: rows of 64 doubles, same layout as oracle/ref_driver.cpp's teb_ref_build_system(edges_out):
+ * [0] error dimension, [1] vertex count, [2..4] error, [5..7] information diagonal, [8 + 9 k ...] Jacobian of vertex k
+ * (row major dim x vdim, zero for fixed vertices), [53 + k] vertex dimension, [58 + k] g2o vertex id (pose i: 2 i,
+ * dt_i: 2 i + 1, optimal_planner.cpp:426-437). Returns the number of active edges (or <0). */
+int32_t teb_oracle_dump_edges(const TebParams* cfg, const double* rec_in, int32_t n, const TebObstacle* obst, int32_t M,
+                              const double* via, int32_t V, const double* vel_start4, const double* vel_goal4,
+                              int32_t prefer_rotdir, double weight_multiplier, int32_t jac_mode, double* rows,
+                              int32_t max_rows, const double* obst_vertices) {
+  Graph g;
+  memset(&g, 0, sizeof(g));
+  double* rec = (double*)malloc(sizeof(double) * 4 * (size_t)n);
+  memcpy(rec, rec_in, sizeof(double) * 4 * (size_t)n);
+  g.cfg = cfg; g.rec = rec; g.n = n; g.obst = obst; g.M = M; g.via = via; g.V = V; g.pverts = obst_vertices;
+  memcpy(g.vel_start, vel_start4, sizeof(double) * 4);
+  memcpy(g.vel_goal, vel_goal4, sizeof(double) * 4);
+  g.rotdir = prefer_rotdir;
+  graph_alloc(&g, n);
+  int rc = build_graph(&g, weight_multiplier);
+  if (rc) { graph_free(&g); free(rec); return rc; }
+  compute_active_errors(&g);
+  for (int k = 0; k < g.n_edges; ++k) {
+    Edge* e = g.edges[k];
+    memset(e->J, 0, sizeof(e->J));
+    linearize(e, &g, jac_mode);
+    if (k >= max_rows) continue;
+    double* row = rows + 64 * (size_t)k;
+    memset(row, 0, 64 * sizeof(double));
+    row[0] = e->dim; row[1] = e->nv;
+    for (int d = 0; d < e->dim; ++d) { row[2 + d] = e->err[d]; row[5 + d] = e->info[d]; }
+    for (int v = 0; v < e->nv && v < 5; ++v) {
+      const int vd = vdim(e->vkind[v]);
+      row[53 + v] = vd;
+      row[58 + v] = 2 * e->vidx[v] + (e->vkind[v] == 1 ? 1 : 0);
+      if (edge_vertex_fixed(&g, e, v)) continue;
+      for (int d = 0; d < e->dim; ++d)
+        for (int a = 0; a < vd; ++a) row[8 + 9 * v + d * vd + a] = e->J[v][d * vd + a];
+    }
+  }
+  const int ne = g.n_edges;
+  graph_free(&g);
+  free(rec);
+  return ne;
+}
+
 /* ------------------------------------------------------------------ batch driver (thread per band) */
 typedef struct BatchJob {
   const TebParams* cfg; const TebBatch* batch; const TebOptimizeArgs* args; const OracleOptions* opt;

@@ -65,6 +65,13 @@ int32_t teb_oracle_build_system(const TebParams* cfg, const double* rec, int32_t
                                 double weight_multiplier, int32_t jac_mode,
                                 double* H_dense, double* b, double* chi2, const double* obst_vertices /* or NULL */);
 
+/* Per-edge dump (errors, information, Jacobians, vertex ids) of the graph at the given state; 64 doubles per active edge,
+ * layout in teb_oracle.c. Lets tests compare the restatement with oracle/_ref edge by edge. */
+int32_t teb_oracle_dump_edges(const TebParams* cfg, const double* rec, int32_t n, const TebObstacle* obst, int32_t M,
+                              const double* via, int32_t V, const double* vel_start4, const double* vel_goal4,
+                              int32_t prefer_rotdir, double weight_multiplier, int32_t jac_mode, double* rows,
+                              int32_t max_rows, const double* obst_vertices);
+
 /* TimedElasticBand::autoResize (timed_elastic_band.cpp:227-286). Returns new n. */
 int32_t teb_oracle_auto_resize(double* rec, int32_t n, int32_t n_cap, double dt_ref, double dt_hysteresis,
                                int32_t min_samples, int32_t max_samples, int32_t fast_mode);

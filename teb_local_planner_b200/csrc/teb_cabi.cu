@@ -35,6 +35,7 @@ struct tebgpu_ctx {
   int64_t launches = 0;
   int linearize_variant = 0;  /* 0: k_linearize2, one thread per pose, 125-pose tiles (default);
                                  1: k_linearize, first generation: 128-thread CTA per 32-pose tile, thread per band row */
+  int ka_staged = 0;   /* kernel A output: 0 direct 128-bit global stores, 1 shared-memory slot + TMA bulk store per lane */
   int last_spec_k = 0; /* width used by the last optimize call */
   int spec_k = 0;  /* speculation width: 0 = auto (6 when B*6 systems fit one warp per SM sub-partition, else 4) */
   int solver = 2;  /* 2: speculative thread-per-(band,trial) LDL^T (default), 1: block cyclic reduction, 0: sequential */
@@ -193,7 +194,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   c->lim = *lim;
   if (c->lim.max_obstacles < 1) c->lim.max_obstacles = 1;
   c->MW = (c->lim.max_obstacles + 63) / 64;
-  c->chunks = (c->lim.max_poses + TP - 1) / TP; /* capacity for the smaller of the two tile sizes */
+  c->chunks = (c->lim.max_poses + KA2_TP - 1) / KA2_TP; /* capacity for the smaller of the two tile sizes */
   *out = c;
   CUDA_TRY(c, cudaSetDevice(device));
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -266,14 +267,13 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     c->err = "kernel A staging exceeds 227 KB for these limits (max_obstacles too large)";
     return TEBGPU_ERR_CAPACITY;
   }
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka2_smem_bytes<false>((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka2_smem_bytes<false>((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka2_smem_bytes<true>((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka2_smem_bytes<true>((int)M)));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#define KA2_ATTR(H, G, O)                                                                                                    \
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<H, G, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ka2_smem_bytes<H>((int)M))); \
+  CUDA_TRY(c, cudaFuncSetAttribute(k_linearize2<H, G, O>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  KA2_ATTR(false, false, true) KA2_ATTR(false, true, true) KA2_ATTR(true, false, true) KA2_ATTR(true, true, true)
+  KA2_ATTR(false, false, false) KA2_ATTR(false, true, false) KA2_ATTR(true, false, false) KA2_ATTR(true, true, false)
+#undef KA2_ATTR
+  if (const char* e = std::getenv("TEBGPU_KA_STAGED")) c->ka_staged = std::atoi(e) != 0;
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
@@ -352,18 +352,26 @@ int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* p) {
 static void launch_linearize(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int M_cap, cudaStream_t st) {
   const bool holo = kp.holo_vel || kp.holo_acc;
   const bool geom = kp.generic != 0;
-  const dim3 grid(db.chunks, B);
   if (ctx->linearize_variant == 1) {
+    const dim3 grid(db.chunks, B);
     const size_t sm = ka_smem_bytes(M_cap);
     if (holo && geom) k_linearize<true, true><<<grid, KA_THREADS, sm, st>>>(db, kp);
     else if (holo) k_linearize<true, false><<<grid, KA_THREADS, sm, st>>>(db, kp);
     else if (geom) k_linearize<false, true><<<grid, KA_THREADS, sm, st>>>(db, kp);
     else k_linearize<false, false><<<grid, KA_THREADS, sm, st>>>(db, kp);
   } else {
-    if (holo && geom) k_linearize2<true, true><<<grid, KA2_NT, ka2_smem_bytes<true>(M_cap), st>>>(db, kp);
-    else if (holo) k_linearize2<true, false><<<grid, KA2_NT, ka2_smem_bytes<true>(M_cap), st>>>(db, kp);
-    else if (geom) k_linearize2<false, true><<<grid, KA2_NT, ka2_smem_bytes<false>(M_cap), st>>>(db, kp);
-    else k_linearize2<false, false><<<grid, KA2_NT, ka2_smem_bytes<false>(M_cap), st>>>(db, kp);
+    const dim3 g2((db.chunks + KA2_W - 1) / KA2_W, B);
+    const size_t sm = holo ? ka2_smem_bytes<true>(M_cap) : ka2_smem_bytes<false>(M_cap);
+#define KA2_LAUNCH(H, G)                                                                      \
+  do {                                                                                        \
+    if (ctx->ka_staged) k_linearize2<H, G, false><<<g2, KA2_THREADS, sm, st>>>(db, kp);       \
+    else k_linearize2<H, G, true><<<g2, KA2_THREADS, sm, st>>>(db, kp);                       \
+  } while (0)
+    if (holo && geom) KA2_LAUNCH(true, true);
+    else if (holo) KA2_LAUNCH(true, false);
+    else if (geom) KA2_LAUNCH(false, true);
+    else KA2_LAUNCH(false, false);
+#undef KA2_LAUNCH
   }
 }
 static void launch_build_graph(const DevBatch& db, const KParams& kp, int B, size_t smem, cudaStream_t st) {

@@ -1,21 +1,22 @@
 /*
  * teb_linearize.cuh — "kernel A", second generation (the default): residuals + closed-form Jacobians of every edge
- * family + banded J^T Omega J / b assembly, ONE THREAD PER POSE.
+ * family + banded J^T Omega J / b assembly, ONE THREAD PER POSE, ONE WARP PER TILE, no block-wide barrier on the path.
  *
- * Mapping. A CTA of NT threads owns TP2 = NT - 3 consecutive poses of one band; thread t <-> pose / anchor
- * i = p0 - 2 + t (two halo anchors on the left, one halo segment on the right). Every phase keeps all lanes busy:
- *   P1  sin/cos of the own pose, derivative bundle of the own segment (stays in registers; a copy goes to shared
- *       memory for the left neighbour), unary terms (obstacles / dynamic obstacles / via-points) of the own pose
- *       accumulated in registers
+ * Mapping. A warp owns KA2_TP = 29 consecutive poses of one band; lane l <-> pose / anchor i = q0 - 2 + l (two halo
+ * anchors on the left, one halo segment on the right, recomputed by the neighbouring tile: 9 % redundancy instead of
+ * any cross-warp synchronisation). A CTA is KA2_W = 4 such warps over adjacent tiles; it shares one TMA-staged pose
+ * range and the scene's obstacle table (two 1-D bulk copies on one mbarrier, issued before anything else is known).
+ *   P1  sin/cos of the own pose, derivative bundle of the own segment (registers; the right neighbour's bundle arrives
+ *       by warp shuffles), unary terms (obstacles / dynamic obstacles / via-points) of the own pose in registers
  *   P2  sqrt(weight)-scaled Jacobian rows of the chain edges anchored at the own pose, written as a COMPACT record
- *       (structural zeros are not stored) into shared memory, element-major ([element][slot]: every access of a warp
- *       is a contiguous 256-byte run, no bank conflicts)
+ *       (structural zeros are not stored) into the warp's shared-memory region, element-major ([element][lane]: every
+ *       access of the warp is one contiguous 256-byte run, no bank conflicts); __syncwarp
  *   P3  the four band rows of the own pose (4 x 11 entries + 4 rhs) are accumulated IN REGISTERS from the records of
  *       the three anchors that touch them; structural zeros are compiled out, rows whose residual is exactly zero
  *       (inactive penalties: most velocity / acceleration rows of a converged band) are skipped at run time
- *   P4  the 384 bytes of a pose go to a padded shared-memory slot (conflict-free 128-bit stores) and leave with one
- *       TMA bulk store per lane (cp.async.bulk.global.shared::cta); b also goes to the compact rhs array
- * Inputs arrive by 1-D TMA bulk copies (poses tile, scene obstacle table) signalled on one mbarrier.
+ *   P4  the 384 bytes of a pose leave the registers as 128-bit global stores (OUT_DIRECT, default: every 32-byte sector
+ *       is completed by two consecutive store instructions of the same lane) or through a padded shared-memory slot and
+ *       one TMA bulk store per lane (cp.async.bulk.global.shared::cta); b also goes to the compact rhs array
  *
  * Arithmetic = the computeError bodies cited in teb_device.cuh / below, Jacobians in closed form; identical formulas to
  * the first-generation kernel (k_linearize in teb_kernels.cuh, kept as variant 1), different summation order.
@@ -27,8 +28,11 @@
 
 namespace tebgpu {
 
-constexpr int KA2_NT = 128;          /* threads per CTA */
-constexpr int KA2_TP = KA2_NT - 3;   /* poses (band row groups) produced per CTA */
+constexpr int KA2_W = 4;             /* warps (tiles) per CTA */
+constexpr int KA2_THREADS = 32 * KA2_W;
+constexpr int KA2_TP = 29;           /* poses (band row groups) produced per warp: lanes 2 .. 30 */
+constexpr int KA2_SLOTS = KA2_W * KA2_TP + 4; /* poses staged per CTA: slot j <-> pose P0 - 2 + j */
+constexpr int KA2_NT = 32;           /* record stride: element-major within the warp's region */
 constexpr int OUT_STRIDE = 50;       /* doubles per staging slot: 48 + 2 pad -> 400 B lane stride, conflict-free STS.128 */
 
 /* Compact Jacobian record of one anchor (columns: x_a y_a th_a dt_a x_b y_b th_b [dt_b x_c y_c th_c]).
@@ -70,29 +74,28 @@ struct JRec {
 };
 
 struct KA2Smem {
-  static constexpr int POSES = (KA2_NT + 1) * 4;
-  static constexpr int SC = 2 * KA2_NT;
-  static constexpr int SEG = 9 * KA2_NT;
+  static constexpr int POSES = KA2_SLOTS * 4;
   static constexpr int START = 24;
-  static constexpr int RED = 5 * (KA2_NT / 32) + 8;
   template <bool HOLO>
-  __host__ __device__ static constexpr int jdoubles() {
-    return (JL<HOLO>::COUNT * KA2_NT > OUT_STRIDE * KA2_NT) ? JL<HOLO>::COUNT * KA2_NT : OUT_STRIDE * KA2_NT;
+  __host__ __device__ static constexpr int rec_doubles() { /* records of the 32 lanes; later the 32 output slots */
+    return JL<HOLO>::COUNT * 32 > OUT_STRIDE * 32 ? JL<HOLO>::COUNT * 32 : OUT_STRIDE * 32;
   }
+  template <bool HOLO>
+  __host__ __device__ static constexpr int warp_doubles() { return rec_doubles<HOLO>() + START; }
 };
 template <bool HOLO>
 __host__ __device__ inline size_t ka2_smem_bytes(int M_cap) {
-  const size_t d = KA2Smem::POSES + KA2Smem::SC + KA2Smem::SEG + KA2Smem::START + KA2Smem::RED + 2 + KA2Smem::jdoubles<HOLO>();
+  const size_t d = KA2Smem::POSES + (size_t)KA2_W * KA2Smem::warp_doubles<HOLO>() + 2;
   return d * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) + 64;
 }
 
 /* ------------------------------------------------------------------ P2: Jacobian rows of the chain edges anchored at
- * pose a (sqrt(weight)-scaled). sd = derivative bundle of segment a (registers), q2[k * KA2_NT] = bundle of segment
- * a+1 (shared memory, written by the right neighbour). Returns the anchor's chi2 ("other" family). */
+ * pose a (sqrt(weight)-scaled). sd = derivative bundle of segment a, sd2 = bundle of segment a+1 (from the right
+ * neighbour lane). Returns the anchor's chi2 ("other" family). */
 template <bool HOLO>
 __device__ __forceinline__ double anchor_rows2(const KParams& kp, const DevBatch& db, int b, int a, int n,
                                                const double* pa /* sP + 4 slot */, double ca, double sa, double cb,
-                                               double sb, const SegDer& sd, const double* q2, const JRec J,
+                                               double sb, const SegDer& sd, const SegDer& sd2, const JRec J,
                                                double* sStart) {
   using L = JL<HOLO>;
   const double* pb = pa + 4;
@@ -294,7 +297,7 @@ __device__ __forceinline__ double anchor_rows2(const KParams& kp, const DevBatch
   } else if (kp.has_acc) {
     double r0 = 0, r1 = 0;
     if (a <= n - 3) { /* EdgeAcceleration edge_acceleration.h:134-145 */
-      const double v2 = q2[0], w2 = q2[KA2_NT], idt2 = q2[2 * KA2_NT];
+      const double v2 = sd2.v, w2 = sd2.w, idt2 = sd2.idt;
       const double dt1 = pa[3], dt2 = pb[3];
       const double iT = 1.0 / (dt1 + dt2);
       const double acc = (v2 - v1) * 2 * iT;
@@ -306,10 +309,10 @@ __device__ __forceinline__ double anchor_rows2(const KParams& kp, const DevBatch
       const double mc = (a + 2 == n - 1) ? 0.0 : 1.0;
       J.set<L::A0, M_A0, 0>(-2 * k0 * sd.dv[0] * ma); J.set<L::A0, M_A0, 1>(-2 * k0 * sd.dv[1] * ma); J.set<L::A0, M_A0, 2>(-2 * k0 * sd.dv[2] * ma);
       J.set<L::A0, M_A0, 3>(k0 * (2 * v1 * idt1 - acc));
-      J.set<L::A0, M_A0, 4>(2 * k0 * (q2[3 * KA2_NT] - sd.dv[3]) * mb); J.set<L::A0, M_A0, 5>(2 * k0 * (q2[4 * KA2_NT] - sd.dv[4]) * mb);
-      J.set<L::A0, M_A0, 6>(2 * k0 * (q2[5 * KA2_NT] - sd.dv[5]) * mb);
+      J.set<L::A0, M_A0, 4>(2 * k0 * (sd2.dv[0] - sd.dv[3]) * mb); J.set<L::A0, M_A0, 5>(2 * k0 * (sd2.dv[1] - sd.dv[4]) * mb);
+      J.set<L::A0, M_A0, 6>(2 * k0 * (sd2.dv[2] - sd.dv[5]) * mb);
       J.set<L::A0, M_A0, 7>(k0 * (-2 * v2 * idt2 - acc));
-      J.set<L::A0, M_A0, 8>(2 * k0 * q2[6 * KA2_NT] * mc); J.set<L::A0, M_A0, 9>(2 * k0 * q2[7 * KA2_NT] * mc); J.set<L::A0, M_A0, 10>(2 * k0 * q2[8 * KA2_NT] * mc);
+      J.set<L::A0, M_A0, 8>(2 * k0 * sd2.dv[3] * mc); J.set<L::A0, M_A0, 9>(2 * k0 * sd2.dv[4] * mc); J.set<L::A0, M_A0, 10>(2 * k0 * sd2.dv[5] * mc);
       J.set<L::A1, M_A1, 2>(2 * k1 * idt1 * ma);
       J.set<L::A1, M_A1, 3>(k1 * (2 * w1 * idt1 - accr));
       J.set<L::A1, M_A1, 6>(2 * k1 * (-idt2 - idt1) * mb);
@@ -447,58 +450,129 @@ __device__ __forceinline__ void gram_start(const double* sStart, double (&acc)[4
   }
 }
 
+/* unary terms of pose i with the first association word already in a register (prefetched before the TMA wait) */
+template <bool GEOM>
+__device__ __forceinline__ void unary_terms2(const KParams& kp, const DevBatch& db, int b, int sc, int i, int n, double px,
+                                             double py, double cs, double sn, const TebObstacle* so, unsigned long long mask0,
+                                             double U[6], double ub[3], double& chi_obst, double& chi_via) {
+  if (i < 1 || i > n - 2) return;
+  const double* pool = db.obst_vertices + (size_t)sc * db.PV_cap * 2; /* only dereferenced for vertex-list obstacles */
+  if (kp.has_obst) {
+    const unsigned long long* assoc = db.assoc + ((size_t)b * db.n_cap + i) * db.MW;
+    for (int w = 0; w < db.MW; ++w) {
+      unsigned long long mask = (w == 0) ? mask0 : assoc[w];
+      while (mask) {
+        const int m = (w << 6) + __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const TebObstacle ob = so[m];
+        double g[3], kappa, beta;
+        const double d = robot_obstacle_distance<GEOM>(kp, pool, px, py, cs, sn, ob, ob.x, ob.y, 0.0, 0.0, g);
+        double cterm = obstacle_terms(kp, d, kappa, beta);
+        if (kp.p.legacy_obstacle_association &&
+            ((db.assoc3[((size_t)b * db.n_cap + i) * db.MW + w] >> (m & 63)) & 1ull)) {
+          cterm *= 3; kappa *= 3; beta *= 3; /* three identical edges on the centre pose */
+        }
+        chi_obst += cterm;
+        if (kappa != 0 || beta != 0) {
+          U[0] += kappa * g[0] * g[0]; U[1] += kappa * g[0] * g[1]; U[2] += kappa * g[1] * g[1];
+          U[3] += kappa * g[0] * g[2]; U[4] += kappa * g[1] * g[2]; U[5] += kappa * g[2] * g[2];
+          ub[0] -= beta * g[0]; ub[1] -= beta * g[1]; ub[2] -= beta * g[2];
+        }
+      }
+    }
+  }
+  if (kp.has_dyn) {
+    const double t = db.dyn_t[(size_t)b * db.n_cap + i];
+    const int nd = db.dyn_cnt[sc];
+    const int32_t* di = db.dyn_idx + (size_t)sc * db.M_cap;
+    for (int q = 0; q < nd; ++q) {
+      const TebObstacle ob = so[di[q]];
+      double g[3], kappa, beta;
+      const double d = robot_obstacle_distance<GEOM>(kp, pool, px, py, cs, sn, ob, ob.x + t * ob.vx, ob.y + t * ob.vy, t * ob.vx,
+                                               t * ob.vy, g);
+      chi_obst += dynamic_terms(kp, d, kappa, beta);
+      if (kappa != 0 || beta != 0) {
+        U[0] += kappa * g[0] * g[0]; U[1] += kappa * g[0] * g[1]; U[2] += kappa * g[1] * g[1];
+        U[3] += kappa * g[0] * g[2]; U[4] += kappa * g[1] * g[2]; U[5] += kappa * g[2] * g[2];
+        ub[0] -= beta * g[0]; ub[1] -= beta * g[1]; ub[2] -= beta * g[2];
+      }
+    }
+  }
+  if (kp.has_via && db.V_cap > 0) {
+    const int32_t* vidx = db.via_idx + (size_t)b * db.V_cap;
+    const double* via = db.via + (size_t)b * db.V_cap * 2;
+    const double wv = kp.p.weight_viapoint;
+    for (int v = 0; v < db.V_cap; ++v) {
+      if (vidx[v] != i) continue;
+      const double dx = px - via[2 * v], dy = py - via[2 * v + 1];
+      const double e = sqrt(dx * dx + dy * dy); /* EdgeViaPoint edge_via_point.h:86 */
+      chi_via += wv * e * e;
+      if (e > 0) {
+        const double gx = dx / e, gy = dy / e;
+        U[0] += wv * gx * gx; U[1] += wv * gx * gy; U[2] += wv * gy * gy;
+        ub[0] -= wv * e * gx; ub[1] -= wv * e * gy;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ double shfl_down1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
 /* ------------------------------------------------------------------ k_linearize2 */
-template <bool HOLO, bool GEOM>
-__global__ void __launch_bounds__(KA2_NT, 3) k_linearize2(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp) {
+template <bool HOLO, bool GEOM, bool OUT_DIRECT>
+__global__ void __launch_bounds__(KA2_THREADS, 3) k_linearize2(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using L = JL<HOLO>;
-  const int b = linearize_band(db, blockIdx.y);
-  if (b < 0) return;
-  if (!db.state[b].active) return;
-  const int n = db.n[b];
-  const int p0 = blockIdx.x * KA2_TP;
-  if (p0 >= n) return;
-  const int tid = threadIdx.x;
-  const int i = p0 - 2 + tid; /* pose / anchor of this thread */
-
-  double* sP = reinterpret_cast<double*>(smem_raw);       /* poses, slot j <-> pose p0-2+j, KA2_NT + 1 slots */
-  double* sJ = sP + KA2Smem::POSES;                       /* records [element][slot]; later the output slots   */
-  double* sSC = sJ + KA2Smem::jdoubles<HOLO>();           /* [2][NT] cos, sin                                  */
-  double* sSeg = sSC + KA2Smem::SC;                       /* [9][NT] v, w, 1/dt, dv[6] of the segment i -> i+1 */
-  double* sStart = sSeg + KA2Smem::SEG;
-  double* sRed = sStart + KA2Smem::START;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sRed + KA2Smem::RED);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* sP = reinterpret_cast<double*>(smem_raw);                      /* poses, slot j <-> pose P0 + j */
+  double* sW = sP + KA2Smem::POSES + (size_t)warp * KA2Smem::warp_doubles<HOLO>(); /* this warp's records / output slots */
+  double* sStart = sW + KA2Smem::rec_doubles<HOLO>();                    /* EdgeAccelerationStart rows (tile of anchor 0) */
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sP + KA2Smem::POSES + (size_t)KA2_W * KA2Smem::warp_doubles<HOLO>());
   TebObstacle* so = reinterpret_cast<TebObstacle*>((reinterpret_cast<uintptr_t>(bar) + 16 + 15) & ~static_cast<uintptr_t>(15));
 
+  /* everything the prologue needs is loaded at once: no chain of dependent global loads */
+  const int y = blockIdx.y;
+  int b = y, skip = 0;
+  if (db.a_list) { if (y < *db.a_cnt) b = db.a_list[y]; else skip = 1; }
+  else if (db.skip_tag != 0 && db.defer[y] == db.skip_tag) skip = 1;
+  if (skip) return; /* uniform for the CTA */
+  const int active = db.state[b].active;
+  const int n = db.n[b];
   const int s = db.scene_id[b];
-  const int M = db.obst_count[s];
-  const int lo = max(p0 - 2, 0), hi = min(p0 + KA2_TP + 2, n); /* poses staged: slots 0 .. NT */
-  const double* gP = db.poses + (size_t)b * db.n_cap * 4;
+  const int P0 = blockIdx.x * (KA2_W * KA2_TP) - 2;                       /* pose of slot 0 */
+  const int lo = max(P0, 0), hi = min(P0 + KA2_SLOTS, db.n_cap);          /* staged range: independent of n */
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
   }
-  __syncthreads();
+  if (!active || P0 + 2 >= n) return;                                     /* uniform for the CTA, nothing in flight yet */
   if (tid == 0) {
     const uint32_t bytesP = (uint32_t)(hi - lo) * 32u;
-    const uint32_t bytesO = (uint32_t)M * (uint32_t)sizeof(TebObstacle);
+    const uint32_t bytesO = (uint32_t)db.M_cap * (uint32_t)sizeof(TebObstacle);
     mbar_expect_tx(bar, bytesP + bytesO);
-    tma_load_1d(sP + (size_t)(lo - (p0 - 2)) * 4, gP + (size_t)lo * 4, bytesP, bar);
+    tma_load_1d(sP + (size_t)(lo - P0) * 4, db.poses + ((size_t)b * db.n_cap + lo) * 4, bytesP, bar);
     if (bytesO) tma_load_1d(so, db.obstacles + (size_t)s * db.M_cap, bytesO, bar);
   }
-  /* while the copies are in flight: zero the own record and the start block */
+  const int slot = warp * KA2_TP + lane;
+  const int i = P0 + slot;                                                /* pose / anchor of this lane */
+  const int q0 = P0 + 2 + warp * KA2_TP;                                  /* first pose this warp produces */
+  const bool out = (lane >= 2 && lane <= 30 && i < n);
+  /* while the copies are in flight: association word of the own pose, zeroed record and start block */
+  unsigned long long mask0 = 0ull;
+  if (out && kp.has_obst && i >= 1 && i <= n - 2) mask0 = db.assoc[((size_t)b * db.n_cap + i) * db.MW];
   {
-    double* rec = sJ + tid;
+    double* rec = sW + lane;
 #pragma unroll
-    for (int e = 0; e < L::COUNT; ++e) rec[e * KA2_NT] = 0.0;
-    if (tid < KA2Smem::START) sStart[tid] = 0.0;
+    for (int e = 0; e < L::COUNT; ++e) rec[e * 32] = 0.0;
+    if (lane < KA2Smem::START) sStart[lane] = 0.0;
   }
+  __syncthreads(); /* the mbarrier initialisation is visible to every waiting thread (the only block-wide barrier) */
   mbar_wait(bar, 0);
+  if (q0 >= n) return; /* whole warp: tile beyond the band */
 
   double chi[4] = {0, 0, 0, 0}; /* obstacles, via, time-optimal, other */
-  const bool have_pose = (i >= lo && i < hi);
-  const bool out = (tid >= 2 && tid < KA2_NT - 1 && i < n); /* this thread produces the band rows of pose i */
-  const double* pa = sP + 4 * tid;
+  const bool have_pose = (i >= 0 && i < n);
+  const double* pa = sP + 4 * slot;
   double cs = 1, sn = 0;
   SegDer sd;
   sd.v = 0; sd.w = 0; sd.idt = 0;
@@ -508,29 +582,24 @@ __global__ void __launch_bounds__(KA2_NT, 3) k_linearize2(const __grid_constant_
   /* ---- P1 */
   if (have_pose) {
     sincos(pa[2], &sn, &cs);
-    sSC[tid] = cs;
-    sSC[KA2_NT + tid] = sn;
-    if (i <= n - 2) { /* slot tid + 1 is staged whenever the segment exists (hi covers p0 + TP + 1) */
-      const double* pb = pa + 4;
-      sd = seg_derivs(kp, pa[0], pa[1], pa[2], cs, sn, pb[0], pb[1], pb[2], pa[3]);
-      sSeg[tid] = sd.v; sSeg[KA2_NT + tid] = sd.w; sSeg[2 * KA2_NT + tid] = sd.idt;
+    if (i <= n - 2) sd = seg_derivs(kp, pa[0], pa[1], pa[2], cs, sn, pa[4], pa[5], pa[6], pa[3]);
+    if (out) unary_terms2<GEOM>(kp, db, b, s, i, n, pa[0], pa[1], cs, sn, so, mask0, U, ub, chi[0], chi[1]);
+  }
+  /* the right neighbour's sin / cos and segment bundle (lane 31 receives nothing useful and anchors nothing) */
+  SegDer sd2;
+  const double cb = shfl_down1(cs), sb = shfl_down1(sn);
+  sd2.v = shfl_down1(sd.v); sd2.w = shfl_down1(sd.w); sd2.idt = shfl_down1(sd.idt);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) sSeg[(3 + k) * KA2_NT + tid] = sd.dv[k];
-    }
-    if (out) {
-      unary_terms<GEOM>(kp, db, b, s, i, n, pa[0], pa[1], cs, sn, so, M, true, U, ub, chi[0], chi[1]);
-      if (kp.has_time && i <= n - 2) chi[2] += kp.p.weight_optimaltime * pa[3] * pa[3]; /* EdgeTimeOptimal edge_time_optimal.h:93 */
-    }
-  }
-  __syncthreads();
-  /* ---- P2: chain edges anchored at i (threads 0 .. NT-2; the last thread only provides the halo segment) */
-  if (have_pose && i <= n - 2 && tid < KA2_NT - 1) {
+  for (int k = 0; k < 6; ++k) sd2.dv[k] = shfl_down1(sd.dv[k]);
+  __syncwarp(); /* start block zeroed by other lanes */
+  /* ---- P2: chain edges anchored at i */
+  if (have_pose && i <= n - 2 && lane < 31) {
     JRec J;
-    J.rec = sJ + tid;
-    const double c3 = anchor_rows2<HOLO>(kp, db, b, i, n, pa, cs, sn, sSC[tid + 1], sSC[KA2_NT + tid + 1], sd, sSeg + tid + 1, J, sStart);
-    if (tid >= 2) chi[3] += c3; /* halo anchors belong to the previous tile */
+    J.rec = sW + lane;
+    const double c3 = anchor_rows2<HOLO>(kp, db, b, i, n, pa, cs, sn, cb, sb, sd, sd2, J, sStart);
+    if (lane >= 2) chi[3] += c3; /* halo anchors belong to the previous tile */
   }
-  __syncthreads();
+  __syncwarp();
   /* ---- P3: band rows of pose i */
   double acc[4][11];
   double brow[4] = {0, 0, 0, 0};
@@ -540,9 +609,9 @@ __global__ void __launch_bounds__(KA2_NT, 3) k_linearize2(const __grid_constant_
     for (int k = 0; k < 11; ++k) acc[c][k] = 0;
   double dm = 0;
   if (out) {
-    const double* rec = sJ + tid;
+    const double* rec = sW + lane;
     if (i <= n - 2) gram_anchor<HOLO, 0>(kp, rec, acc, brow);
-    if (i >= 1 && i - 1 <= n - 2) gram_anchor<HOLO, 1>(kp, rec - 1, acc, brow);
+    if (i >= 1) gram_anchor<HOLO, 1>(kp, rec - 1, acc, brow);
     if (i >= 2) gram_anchor<HOLO, 2>(kp, rec - 2, acc, brow); /* anchor i-2 <= n-3 always exists here */
     if (kp.has_acc) {
       if (i == 0) gram_start<HOLO, 0>(sStart, acc, brow);
@@ -552,64 +621,69 @@ __global__ void __launch_bounds__(KA2_NT, 3) k_linearize2(const __grid_constant_
     acc[0][0] += U[0]; brow[0] += ub[0];
     acc[1][0] += U[2]; acc[1][1] += U[1]; brow[1] += ub[1];
     acc[2][0] += U[5]; acc[2][1] += U[4]; acc[2][2] += U[3]; brow[2] += ub[2];
-    if (kp.has_time) { acc[3][0] += kp.p.weight_optimaltime; brow[3] -= kp.p.weight_optimaltime * pa[3]; }
-    /* fixed start / goal pose and the non-existent dt_{n-1}: identity rows */
-    const bool pose_real = (i >= 1 && i <= n - 2), dt_real = (i <= n - 2);
+    if (kp.has_time && i <= n - 2) { /* EdgeTimeOptimal edge_time_optimal.h:93 */
+      chi[2] += kp.p.weight_optimaltime * pa[3] * pa[3];
+      acc[3][0] += kp.p.weight_optimaltime; brow[3] -= kp.p.weight_optimaltime * pa[3];
+    }
+    if (i == 0 || i >= n - 1) { /* fixed start / goal pose, non-existent dt_{n-1}: identity rows (first / last lane only) */
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const bool real = (c == 3) ? dt_real : pose_real;
-      if (!real) {
+      for (int c = 0; c < 4; ++c) {
+        if (c == 3 && i <= n - 2) continue; /* dt_0 is a real unknown */
 #pragma unroll
         for (int k = 0; k < 11; ++k) acc[c][k] = 0;
         acc[c][0] = 1.0;
         brow[c] = 0;
-      } else {
-        dm = fmax(dm, fabs(acc[c][0]));
       }
+      dm = (i <= n - 2) ? fabs(acc[3][0]) : 0.0;
+    } else {
+      dm = fmax(fmax(fabs(acc[0][0]), fabs(acc[1][0])), fmax(fabs(acc[2][0]), fabs(acc[3][0])));
     }
   }
-  __syncthreads(); /* every thread is done reading the records: the region becomes the output slots */
   /* ---- P4 */
-  if (out) {
-    double2* o2 = reinterpret_cast<double2*>(sJ + (size_t)tid * OUT_STRIDE);
+  if (OUT_DIRECT) {
+    if (out) {
+      double2* g2 = reinterpret_cast<double2*>(db.Hb + ((size_t)b * 4 * db.n_cap + 4 * (size_t)i) * HROW);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 4; ++c) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) o2[6 * c + k] = make_double2(acc[c][2 * k], acc[c][2 * k + 1]);
-      o2[6 * c + 5] = make_double2(acc[c][10], brow[c]);
+        for (int k = 0; k < 5; ++k) g2[6 * c + k] = make_double2(acc[c][2 * k], acc[c][2 * k + 1]);
+        g2[6 * c + 5] = make_double2(acc[c][10], brow[c]);
+      }
+      double2* r2 = reinterpret_cast<double2*>(db.rhs + (size_t)b * 4 * db.n_cap + 4 * (size_t)i);
+      r2[0] = make_double2(brow[0], brow[1]);
+      r2[1] = make_double2(brow[2], brow[3]);
     }
-    double2* r2 = reinterpret_cast<double2*>(db.rhs + (size_t)b * 4 * db.n_cap + 4 * (size_t)i);
-    r2[0] = make_double2(brow[0], brow[1]);
-    r2[1] = make_double2(brow[2], brow[3]);
-    fence_proxy_async();
-    tma_store_1d(db.Hb + ((size_t)b * 4 * db.n_cap + 4 * (size_t)i) * HROW, o2, 4 * HROW * 8u);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  } else {
+    __syncwarp(); /* every lane is done reading the records: the region becomes the output slots */
+    if (out) {
+      double2* o2 = reinterpret_cast<double2*>(sW + (size_t)lane * OUT_STRIDE);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) o2[6 * c + k] = make_double2(acc[c][2 * k], acc[c][2 * k + 1]);
+        o2[6 * c + 5] = make_double2(acc[c][10], brow[c]);
+      }
+      double2* r2 = reinterpret_cast<double2*>(db.rhs + (size_t)b * 4 * db.n_cap + 4 * (size_t)i);
+      r2[0] = make_double2(brow[0], brow[1]);
+      r2[1] = make_double2(brow[2], brow[3]);
+      fence_proxy_async();
+      tma_store_1d(db.Hb + ((size_t)b * 4 * db.n_cap + 4 * (size_t)i) * HROW, o2, 4 * HROW * 8u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
   }
   /* tile partials: chi2 by family and the max diagonal of the real rows (computeLambdaInit), fixed order */
   {
-    const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double v = warp_sum(chi[k]);
-      if (lane == 0) sRed[k * (KA2_NT / 32) + wid] = v;
-    }
-    const double m = warp_max(dm);
-    if (lane == 0) sRed[4 * (KA2_NT / 32) + wid] = m;
-    __syncthreads();
-    if (tid == 0) {
-      double v[4] = {0, 0, 0, 0}, mm = 0;
-#pragma unroll
-      for (int w = 0; w < KA2_NT / 32; ++w) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] += sRed[k * (KA2_NT / 32) + w];
-        mm = fmax(mm, sRed[4 * (KA2_NT / 32) + w]);
-      }
-      double* cp = db.chi_parts + ((size_t)b * db.chunks + blockIdx.x) * 4;
-      cp[0] = v[0]; cp[1] = v[1]; cp[2] = v[2]; cp[3] = v[3];
-      db.dmax_parts[(size_t)b * db.chunks + blockIdx.x] = mm;
+    for (int k = 0; k < 4; ++k) chi[k] = warp_sum(chi[k]);
+    dm = warp_max(dm);
+    if (lane == 0) {
+      const int tile = blockIdx.x * KA2_W + warp;
+      double* cp = db.chi_parts + ((size_t)b * db.chunks + tile) * 4;
+      cp[0] = chi[0]; cp[1] = chi[1]; cp[2] = chi[2]; cp[3] = chi[3];
+      db.dmax_parts[(size_t)b * db.chunks + tile] = dm;
     }
   }
-  if (out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); /* the slot must outlive the copy's read */
+  if (!OUT_DIRECT && out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); /* the slot must outlive the copy's read */
 }
 
 }  // namespace tebgpu

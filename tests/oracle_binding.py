@@ -170,6 +170,29 @@ def build_system(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=N
     return H, b, chi2.value
 
 
+def dump_edges(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=None, rotdir=0, weight_multiplier=1.0,
+               jac_mode=JAC_G2O, obst_vertices=None):
+    """rows [n_edges][64] of the graph at this state (layout: oracle/teb_oracle.c teb_oracle_dump_edges)"""
+    L = lib()
+    L.teb_oracle_dump_edges.restype = C.c_int32
+    L.teb_oracle_dump_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_int32,
+                                        C.c_void_p]
+    rec = np.ascontiguousarray(rec[:n], dtype=np.float64)
+    obstacles = np.ascontiguousarray(obstacles, dtype=abi.OBST_DTYPE)
+    via = np.zeros((0, 2)) if via is None else np.ascontiguousarray(via, dtype=np.float64)
+    vs = np.array([0, 0, 0, 1.0]) if vel_start is None else np.ascontiguousarray(vel_start, dtype=np.float64)
+    vg = np.array([0, 0, 0, 1.0]) if vel_goal is None else np.ascontiguousarray(vel_goal, dtype=np.float64)
+    cap = 64 * n + 4 * n * max(len(obstacles), 1)
+    rows = np.zeros((cap, 64))
+    ne = L.teb_oracle_dump_edges(C.addressof(params), rec.ctypes.data, n, obstacles.ctypes.data if len(obstacles) else None,
+                                 len(obstacles), via.ctypes.data if len(via) else None, len(via), vs.ctypes.data, vg.ctypes.data,
+                                 int(rotdir), float(weight_multiplier), int(jac_mode), rows.ctypes.data, cap, _verts(obst_vertices)[1])
+    if ne < 0:
+        raise RuntimeError(f"teb_oracle_dump_edges rc={ne}")
+    return rows[:ne]
+
+
 def auto_resize(rec, n, dt_ref, dt_hyst, min_samples, max_samples, fast_mode, n_cap=None):
     L = lib()
     n_cap = max(rec.shape[0], 4 * n) if n_cap is None else n_cap

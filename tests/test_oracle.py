@@ -573,3 +573,30 @@ def test_planner_cycles_restatement_invariants(oracle):
             pl.costs[best] == min(pl.costs)
         prev_best_cost = pl.costs[best]
         assert len(sigs) == len(pl.tebs)
+
+
+# --------------------------------------------------------------------------- reference-generated golden vectors
+def test_oracle_matches_reference_generated_golden(oracle):
+    """tests/golden/golden_ref_v1.npz was generated by the REFERENCE'S OWN code (oracle/_ref: src/optimal_planner.cpp,
+    src/timed_elastic_band.cpp, src/obstacles.cpp and their headers compiled against stand-ins for Eigen / boost / ROS /
+    the g2o optimizer; generator: tests/golden/make_golden_ref.py). The restatement must reproduce every stored number
+    bit for bit: chi2 and right-hand side of the normal equations at the initial state, final band, n, cost and the
+    number of LM trials of whole optimizeTEB calls, for all 24 feature scenarios of tests/scenarios.py."""
+    import os
+    from tests import scenarios
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref_v1.npz"), allow_pickle=False)
+    for name in scenarios.ALL:
+        p, hb = scenarios.scenario(name)
+        args = abi.make_args(p.no_inner_iterations, p.no_outer_iterations, True, p.selection_obst_cost_scale,
+                             p.selection_viapoint_cost_scale, False)
+        for b in range(hb.B):
+            kw = scenarios.band_kwargs(hb, b)
+            n = int(hb.n[b])
+            H, rhs, c2 = oracle.build_system(p, hb.poses[b], n, jac_mode=oracle.JAC_G2O, **kw)
+            assert c2 == z[name + "/chi2_0"][b], name
+            assert np.array_equal(rhs, z[name + "/b_0"][b][:len(rhs)]), name
+            rec, cost, st = oracle.optimize_band(p, hb.poses[b], n, args=args, jac_mode=oracle.JAC_G2O, n_cap=hb.n_cap, **kw)
+            assert len(rec) == z[name + "/n"][b], name
+            assert np.array_equal(rec, z[name + "/poses"][b][:len(rec)]), name
+            assert cost == z[name + "/cost"][b] and st.lm_trials == z[name + "/trials"][b], name
+            assert bool(st.status & abi.TEB_STATUS_TERMINATED) == bool(z[name + "/terminated"][b]), name

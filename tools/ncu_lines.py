@@ -4,6 +4,7 @@ import csv, io, subprocess, sys, collections, re, os, glob, tempfile
 rep, kre, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
 skip = sys.argv[5] if len(sys.argv) > 5 else "0"   # matching launches to skip inside the report
+by_inst = len(sys.argv) > 6 and sys.argv[6] == "inst"   # rank by executed warp instructions instead of stall samples
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "teb_local_planner_b200", "libteb_b200.so")], cwd=tmp, capture_output=True)
@@ -42,7 +43,9 @@ for r in rows:
 tot = sum(agg.values()) or 1
 print("total samples", tot, "total warp-instr", sum(inst.values()))
 srcs = {}
-for (f, l), v in agg.most_common(top):
+order = (inst if by_inst else agg).most_common(top)
+for (f, l), _ in order:
+    v = agg[(f, l)]
     if f not in srcs:
         for cand in glob.glob(os.path.join(root, "**", f), recursive=True):
             srcs[f] = open(cand).read().splitlines(); break
