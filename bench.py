@@ -362,8 +362,10 @@ def run_b200(a, rank, local_rank, world):
     kt = g.kernel_times()
     g.set_profiling(False)
     peak, peak_src = hbm_peak()
-    spec_k = g.speculation_width()        # what the library chose for this batch (tebgpu_get_info)
-    bm = byte_models(desc["n_poses"], desc["n_obstacles"], desc["via_points"], B, spec_k)
+    # speculation widths the library chose (tebgpu_get_info): first LM iteration after a graph rebuild / later ones
+    spec_k, spec_first = g.speculation_width(), g.info(7)
+    k_avg = (spec_first + (p.no_inner_iterations - 1) * spec_k) / max(1, p.no_inner_iterations)
+    bm = byte_models(desc["n_poses"], desc["n_obstacles"], desc["via_points"], B, k_avg)
     working_set_mb = B * 4 * n_cap * 96 / 1e6
     ws_note = ("H/b working set %.0f MB %s the 126 MB L2" % (working_set_mb, ">" if working_set_mb > 126 else "<=")
                + ("" if working_set_mb > 126 else ": L2-resident, latency-bound; HBM fraction is indicative only"))
@@ -502,7 +504,7 @@ def run_b200(a, rank, local_rank, world):
                 "gpu_launches": int(launches_per_step * a.steps),
                 "gpu_launches_per_step": int(launches_per_step),
                 "roofline": dominant, "roofline_kernel_a": roof_a, "roofline_kernel_b": roof_b,
-                "roofline_kernel_b_solve": roof_s, "roofline_kernel_b_eval": roof_e, "speculation_width": spec_k,
+                "roofline_kernel_b_solve": roof_s, "roofline_kernel_b_eval": roof_e, "speculation_width": spec_k, "speculation_width_first_iteration": spec_first,
                 "single_request": single, "parity_sample": parity,
                 "kernel_time_share": shares,
                 "kernel_time_share_note": "from a separate profiled pass (CUDA events around every launch, one stream); in the "

@@ -280,7 +280,8 @@ int32_t tebgpu_h_signature(tebgpu_ctx* ctx, const TebBatch* batch, int32_t use_t
 int64_t tebgpu_last_launch_count(const tebgpu_ctx* ctx);
 /* Introspection for measurement scripts. which: 0 speculation width used by the last optimize call, 1 kernel-A variant,
  * 2 solver, 3 communicator size (1 without tebgpu_comm_init), 4 communicator rank, 5 CUDA-graph replay enabled,
- * 6 number of captured graphs held by the context. Returns -1 for an unknown key. */
+ * 6 number of captured graphs held by the context, 7 speculation width of the first LM iteration after a graph rebuild
+ * (key 0 reports the width of the later iterations). Returns -1 for an unknown key. */
 int64_t tebgpu_get_info(const tebgpu_ctx* ctx, int32_t which);
 
 /* Linearise only: build the padded banded normal equations of every band at its current state for
@@ -301,6 +302,25 @@ int32_t tebgpu_compute_cost(tebgpu_ctx* ctx, const TebBatch* batch, const TebOpt
  * Host-side, pure function. Returns the index or -1 if count == 0. */
 int32_t tebgpu_select_best(const double* cost, int32_t count, int32_t last_best, int32_t initial_plan,
                            double selection_cost_hysteresis, double selection_prefer_initial_plan);
+
+/* ---- multi-GPU: one process (or thread) per GPU, each with its own context; the batch axis is sharded and bands never
+ * exchange anything while they are optimised. What replaces the join of HomotopyClassPlanner::optimizeAllTEBs' thread
+ * fan-out (homotopy_class_planner.cpp:466-493) before selectBestTeb (:564-616) is ONE all-gather of the per-candidate
+ * costs over NCCL on the context's stream. NCCL is resolved at run time (dlopen); single-GPU users never load it.
+ *   tebgpu_comm_get_unique_id  rank 0 creates the 128-byte id and distributes it out of band (MPI, a store, a file)
+ *   tebgpu_comm_init           every rank, collectively: ncclCommInitRank on the context's device
+ *   tebgpu_gather_costs        cost_all[r * count_local + k] = cost_local of rank r (same count on every rank);
+ *                              device_ptrs != 0: both pointers are device memory, stream ordered on the context stream, no
+ *                              synchronisation; 0: host memory, synchronous. Without a communicator (one rank): a copy.
+ *   tebgpu_optimize_batch_gather  tebgpu_optimize_batch followed by the gather of batch->cost: cost_all [world * B] (host)
+ * Errors: TEBGPU_ERR_UNSUPPORTED when NCCL cannot be loaded, TEBGPU_ERR_CUDA for NCCL / CUDA failures (see
+ * tebgpu_last_error_string). */
+#define TEBGPU_COMM_ID_BYTES 128
+int32_t tebgpu_comm_get_unique_id(void* id_out);
+int32_t tebgpu_comm_init(tebgpu_ctx* ctx, const void* id, int32_t world_size, int32_t rank);
+int32_t tebgpu_comm_destroy(tebgpu_ctx* ctx);
+int32_t tebgpu_gather_costs(tebgpu_ctx* ctx, const double* cost_local, int32_t count_local, double* cost_all, int32_t device_ptrs);
+int32_t tebgpu_optimize_batch_gather(tebgpu_ctx* ctx, const TebBatch* batch, const TebOptimizeArgs* args, double* cost_all);
 
 /* TimedElasticBand::autoResize (timed_elastic_band.cpp:227-286) on one host band; same routine the
  * device kernel runs. rec: [n_cap][4] in/out, returns the new n (or <0 on error). */

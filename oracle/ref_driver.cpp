@@ -16,8 +16,16 @@
 #include <teb_local_planner/optimal_planner.h>
 #include <teb_local_planner/g2o_types/penalties.h>
 
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <pthread.h>
+#include <sched.h>
+
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../include/teb_b200.h"
@@ -396,6 +404,56 @@ int32_t teb_ref_build_system(const TebParams* p, const double* rec, int32_t n, c
   if (n_edges) *n_edges = (int32_t)act.size();
   pl.clearGraph();
   return N;
+}
+
+/* Whole batch with the TebBatch layout: `threads` host threads, one band at a time per thread - the reference's own
+ * optimizeAllTEBs model (one boost::thread per candidate, homotopy_class_planner.cpp:466-493). pin != 0: worker t runs on
+ * the t-th CPU of the affinity mask. Used as the CPU arm of bench.py when this library exists. */
+int32_t teb_ref_optimize_batch(const TebParams* p, const TebBatch* bt, const TebOptimizeArgs* args, int32_t threads, int32_t pin) {
+  if (threads < 1) threads = 1;
+  if (threads > bt->B) threads = bt->B;
+  std::atomic<int> next(0), bad(0);
+  auto work = [&](int index) {
+    if (pin && index >= 0) {
+      cpu_set_t allowed;
+      CPU_ZERO(&allowed);
+      if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        const int cnt = CPU_COUNT(&allowed);
+        int want = cnt > 0 ? index % cnt : 0, seen = 0;
+        for (int c = 0; c < CPU_SETSIZE && cnt > 0; ++c) {
+          if (!CPU_ISSET(c, &allowed)) continue;
+          if (seen++ == want) { cpu_set_t one; CPU_ZERO(&one); CPU_SET(c, &one); pthread_setaffinity_np(pthread_self(), sizeof(one), &one); break; }
+        }
+      }
+    }
+    for (;;) {
+      const int b = next.fetch_add(1);
+      if (b >= bt->B) break;
+      const int s = bt->scene_id ? bt->scene_id[b] : 0;
+      int32_t nb = bt->n[b];
+      double cost = HUGE_VAL, st[6];
+      const double one4[4] = {0, 0, 0, 1};
+      const int32_t rc = teb_ref_optimize(p, bt->poses + (size_t)b * bt->n_cap * 4, &nb, bt->n_cap, bt->obstacles + (size_t)s * bt->M_cap,
+                                          bt->obst_count ? bt->obst_count[s] : 0,
+                                          (bt->obst_vertices && bt->PV_cap > 0) ? bt->obst_vertices + (size_t)s * bt->PV_cap * 2 : nullptr,
+                                          bt->via ? bt->via + (size_t)b * bt->V_cap * 2 : nullptr, bt->via_count ? bt->via_count[b] : 0,
+                                          bt->vel_start ? bt->vel_start + 4 * b : one4, bt->vel_goal ? bt->vel_goal + 4 * b : one4,
+                                          bt->prefer_rotdir ? bt->prefer_rotdir[b] : 0, args, &cost, st);
+      if (rc < 0) { bad = 1; continue; }
+      bt->n[b] = nb;
+      if (bt->cost) bt->cost[b] = cost;
+      if (bt->status) bt->status[b] = (rc == 1 ? TEB_STATUS_OPTIMIZED : 0) | (st[2] != 0 ? TEB_STATUS_TERMINATED : 0) | (st[3] != 0 ? TEB_STATUS_CHOL_FAILED : 0);
+      if (bt->lm_iters) bt->lm_iters[b] = 0;
+    }
+  };
+  if (threads == 1) {
+    work(-1);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+    for (auto& th : pool) th.join();
+  }
+  return bad ? -1 : 0;
 }
 
 }  /* extern "C" */

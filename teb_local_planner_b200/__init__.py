@@ -54,6 +54,16 @@ def load_library(build_if_missing=False):
     L.tebgpu_synchronize.argtypes = [vp]
     L.tebgpu_last_launch_count.restype = C.c_int64
     L.tebgpu_last_launch_count.argtypes = [vp]
+    L.tebgpu_comm_get_unique_id.restype = C.c_int32
+    L.tebgpu_comm_get_unique_id.argtypes = [vp]
+    L.tebgpu_comm_init.restype = C.c_int32
+    L.tebgpu_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.tebgpu_comm_destroy.restype = C.c_int32
+    L.tebgpu_comm_destroy.argtypes = [vp]
+    L.tebgpu_gather_costs.restype = C.c_int32
+    L.tebgpu_gather_costs.argtypes = [vp, vp, C.c_int32, vp, C.c_int32]
+    L.tebgpu_optimize_batch_gather.restype = C.c_int32
+    L.tebgpu_optimize_batch_gather.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs), vp]
     L.tebgpu_get_info.restype = C.c_int64
     L.tebgpu_get_info.argtypes = [vp, C.c_int32]
     L.tebgpu_set_profiling.restype = C.c_int32
@@ -151,6 +161,41 @@ class TebGpu:
         self._check(self.lib.tebgpu_h_signature(self.ctx, C.byref(bs), int(use_timediffs), out.ctypes.data, 0),
                     "tebgpu_h_signature")
         return out if three_d else out[:, 0] + 1j * out[:, 1]
+
+    # ---- the one collective (NCCL all-gather of the per-candidate costs), behind the C-ABI
+    def comm_get_unique_id(self, out128):
+        """rank 0: fill the 128-byte numpy uint8 array with a fresh NCCL unique id"""
+        rc = self.lib.tebgpu_comm_get_unique_id(out128.ctypes.data)
+        if rc != 0:
+            raise TebGpuError(f"tebgpu_comm_get_unique_id rc={rc} (NCCL not loadable?)")
+
+    def comm_init(self, ident128, world, rank):
+        self._check(self.lib.tebgpu_comm_init(self.ctx, ident128.ctypes.data, int(world), int(rank)), "tebgpu_comm_init")
+
+    def comm_destroy(self):
+        self._check(self.lib.tebgpu_comm_destroy(self.ctx), "tebgpu_comm_destroy")
+
+    def gather_costs_device(self, d_local_ptr, count_local, d_all_ptr):
+        """device pointers, stream ordered on the context stream (or the stream the batch was optimised on)"""
+        self._check(self.lib.tebgpu_gather_costs(self.ctx, d_local_ptr, int(count_local), d_all_ptr, 1), "tebgpu_gather_costs")
+
+    def gather_costs(self, local_cost):
+        """host numpy vector [count] -> [world * count]"""
+        import numpy as np
+        local_cost = np.ascontiguousarray(local_cost, dtype=np.float64)
+        out = np.zeros(self.info(3) * local_cost.size)
+        self._check(self.lib.tebgpu_gather_costs(self.ctx, local_cost.ctypes.data, local_cost.size, out.ctypes.data, 0),
+                    "tebgpu_gather_costs")
+        return out
+
+    def optimize_gather(self, hb, args):
+        """tebgpu_optimize_batch + all-gather of the costs: returns the gathered [world * B] vector"""
+        import numpy as np
+        bs = hb.struct()
+        out = np.zeros(self.info(3) * hb.B)
+        self._check(self.lib.tebgpu_optimize_batch_gather(self.ctx, C.byref(bs), C.byref(args), out.ctypes.data),
+                    "tebgpu_optimize_batch_gather")
+        return out
 
     def info(self, which):
         return int(self.lib.tebgpu_get_info(self.ctx, int(which)))

@@ -24,7 +24,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + SOURCES + ["-lcudart"]
+    cmd = [NVCC] + FLAGS + ["-o", LIB] + SOURCES + ["-lcudart", "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

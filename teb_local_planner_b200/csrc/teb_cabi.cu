@@ -15,6 +15,7 @@
 #include "teb_linearize.cuh"
 #include "teb_spec.cuh"
 #include "teb_hsig.cuh"
+#include "teb_comm.h"
 #include <cstdlib>
 
 using namespace tebgpu;
@@ -28,6 +29,7 @@ struct tebgpu_ctx {
   int32_t* defer = nullptr;           /* [B] */
   double* d_fp = nullptr;             /* footprint definition for the vertex-list distance path (FP_DOUBLES) */
   double* d_pverts = nullptr;         /* [S][max_obst_vertices][2] mirror of TebBatch.obst_vertices */
+  double* d_hsig = nullptr;           /* [max_bands][max(max_obstacles, 2)] H-signature output of the host-buffer entry point */
   TebGpuLimits lim{};
   TebParams params{};
   bool have_params = false;
@@ -35,8 +37,13 @@ struct tebgpu_ctx {
   int64_t launches = 0;
   int linearize_variant = 0;  /* 0: k_linearize2, one thread per pose, 125-pose tiles (default);
                                  1: k_linearize, first generation: 128-thread CTA per 32-pose tile, thread per band row */
-  int ka_staged = 0;   /* kernel A output: 0 direct 128-bit global stores, 1 shared-memory slot + TMA bulk store per lane */
-  int last_spec_k = 0; /* width used by the last optimize call */
+  ncclComm_t comm = nullptr;          /* cost all-gather across the ranks of a sharded batch (tebgpu_comm_init) */
+  int world = 1, rank = 0;
+  double* d_gather = nullptr;         /* [world][max_bands] gathered costs of the host-buffer entry point */
+  int eval_v1 = 0;     /* TEBGPU_EVAL_V1=1: first-generation trial evaluation (warp per trial, chunk per lane) */
+  int ka_staged = 1;   /* kernel A output: 1 (default) shared-memory slot + TMA bulk store per lane, 0 direct 128-bit global stores */
+  int last_spec_k = 0; /* round-0 width of the later LM iterations of the last optimize call */
+  int last_spec_first = 0; /* round-0 width of the first LM iteration after a graph rebuild */
   int spec_k = 0;  /* speculation width: 0 = auto (6 when B*6 systems fit one warp per SM sub-partition, else 4) */
   int solver = 2;  /* 2: speculative thread-per-(band,trial) LDL^T (default), 1: block cyclic reduction, 0: sequential */
   int MW = 1;
@@ -161,16 +168,17 @@ int64_t tebgpu_get_info(const tebgpu_ctx* ctx, int32_t which) {
     case 0: return ctx->last_spec_k;
     case 1: return ctx->linearize_variant;
     case 2: return ctx->solver;
-    case 3: return 1;
-    case 4: return 0;
+    case 3: return ctx->world;
+    case 4: return ctx->rank;
     case 5: return 0;
     case 6: return 0;
+    case 7: return ctx->last_spec_first;
     default: return -1;
   }
 }
 
 static void free_all(tebgpu_ctx* c) {
-  void* ptrs[] = {c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->d_fp, c->d_pverts, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+  void* ptrs[] = {c->d_gather, c->d_hsig, c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->d_fp, c->d_pverts, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
                   c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
                   c->d_status, c->d_iters};
   for (void* p : ptrs)
@@ -227,6 +235,13 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
     CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
     if (const char* e = std::getenv("TEBGPU_EVAL_MINB")) c->eval_minb = std::atoi(e) == 3 ? 3 : 2;
+    if (const char* e = std::getenv("TEBGPU_EVAL_V1")) c->eval_v1 = std::atoi(e) != 0;
+    size_t ev2 = eval2_smem_bytes((int)nc, (int)M, SPEC_K_MAX);
+    if (ev2 > 232448) ev2 = 232448;
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev2));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev2));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
   const size_t spec_sys = ((B * SPEC_K_MAX + 31) / 32) * 32; /* whole warps of (band, trial) systems */
   CUDA_TRY(c, cudaMalloc(&c->spec.Lf, spec_sys * 4 * nc * HROW * sizeof(double)));
@@ -246,6 +261,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaMalloc(&c->d_fp, FP_DOUBLES * sizeof(double)));
   CUDA_TRY(c, cudaMemset(c->d_fp, 0, FP_DOUBLES * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->d_pverts, (S * (size_t)(lim->max_obst_vertices > 0 ? lim->max_obst_vertices : 1)) * 2 * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->d_hsig, B * (M > 2 ? M : 2) * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->d_vcount, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->d_vs, B * 4 * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->d_vg, B * 4 * sizeof(double)));
@@ -273,6 +289,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   KA2_ATTR(false, false, true) KA2_ATTR(false, true, true) KA2_ATTR(true, false, true) KA2_ATTR(true, true, true)
   KA2_ATTR(false, false, false) KA2_ATTR(false, true, false) KA2_ATTR(true, false, false) KA2_ATTR(true, true, false)
 #undef KA2_ATTR
+  c->ka_staged = 1; /* measured: 0.44 ms (TMA bulk store per lane) vs 0.55 ms (direct 128-bit stores) per launch at C3 */
   if (const char* e = std::getenv("TEBGPU_KA_STAGED")) c->ka_staged = std::atoi(e) != 0;
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_a));
@@ -311,6 +328,7 @@ int32_t tebgpu_destroy(tebgpu_ctx* ctx) {
   if (!ctx) return TEBGPU_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+  if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
   free_all(ctx);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -382,8 +400,16 @@ static void launch_vor(const DevBatch& db, const KParams& kp, int B, size_t smem
   if (kp.generic) k_vor<true><<<B, 256, smem, st>>>(db, kp);
   else k_vor<false><<<B, 256, smem, st>>>(db, kp);
 }
+static size_t eval_bytes(const tebgpu_ctx* ctx, int n_cap, int M_cap, int K) {
+  return ctx->eval_v1 ? eval_smem_bytes(n_cap, M_cap, K) : eval2_smem_bytes(n_cap, M_cap, K);
+}
 static void launch_trial_eval(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int K, size_t smem, int it,
                               int round, int g, int tag, cudaStream_t st) {
+  if (!ctx->eval_v1) { /* second generation: one lane per pose */
+    if (kp.generic) k_trial_eval2<true><<<B, EV2_THREADS, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+    else k_trial_eval2<false><<<B, EV2_THREADS, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+    return;
+  }
   if (kp.generic) k_trial_eval<2, true><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
   else if (ctx->eval_minb == 3) k_trial_eval<3, false><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
   else k_trial_eval<2, false><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
@@ -477,14 +503,48 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   const size_t smem_g = (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) * sizeof(TebObstacle);
   /* speculation width: one solver warp per SM sub-partition is the latency-optimal regime (148 SMs x 4 x 32 lanes);
    * below it the wider speculation is free and removes the second round, above it the factor traffic dominates */
-  int spec_K = ctx->spec_k;
-  if (spec_K == 0) spec_K = ((long long)B * 6 <= 148LL * 4 * 32) ? 6 : 4;
-  while (spec_K > 4 && eval_smem_bytes(bt->n_cap, bt->M_cap, spec_K) > 232448) spec_K -= 2;
-  if (eval_smem_bytes(bt->n_cap, bt->M_cap, spec_K) > 232448) { ctx->err = "trial-evaluation staging exceeds shared memory"; return TEBGPU_ERR_CAPACITY; }
-  ctx->last_spec_k = ctx->solver == 2 ? spec_K : 1;
+  /* Speculation schedule: widths of the rounds of one LM iteration (they add up to g2o's 10 trials).
+   *   fixed width (tebgpu_set_speculation / TEBGPU_SPEC_K): K, K, ... as before;
+   *   automatic: the first LM iteration after every graph rebuild restarts at lambda = 1e-5 max diag and needs 4-5
+   *   damping escalations on 90 % of the bands, later iterations accept the first trial on 60 % (measured on C2-C4,
+   *   profiles/r2_history.md). Latency regime (all B x 8 systems fit one solver warp per SM sub-partition): {8, 2} -
+   *   the retry round practically never runs. Throughput regime: {6, 4} for the first iteration, {2, 4, 4} afterwards
+   *   - factor traffic and trial evaluations follow the width. */
+  int sched_first[5] = {0, 0, 0, 0, 0}, sched_later[5] = {0, 0, 0, 0, 0};
+  int n_first = 0, n_later = 0;
+  {
+    int kmax = SPEC_K_MAX;
+    while (kmax > 2 && eval_bytes(ctx, bt->n_cap, bt->M_cap, kmax) > 232448) kmax -= 2;
+    if (eval_bytes(ctx, bt->n_cap, bt->M_cap, kmax) > 232448) { ctx->err = "trial-evaluation staging exceeds shared memory"; return TEBGPU_ERR_CAPACITY; }
+    auto fill = [&](int* dst, int& cnt, std::initializer_list<int> want) {
+      int left = 10;
+      cnt = 0;
+      for (int w : want) {
+        if (left <= 0) break;
+        int k = w < kmax ? w : kmax;
+        dst[cnt++] = k;
+        left -= k;
+      }
+      while (left > 0) { dst[cnt++] = kmax < 4 ? kmax : 4; left -= dst[cnt - 1]; }
+    };
+    if (ctx->spec_k != 0) {
+      const int k = ctx->spec_k;
+      fill(sched_first, n_first, {k, k, k, k, k});
+      fill(sched_later, n_later, {k, k, k, k, k});
+    } else if ((long long)B * 8 <= 148LL * 4 * 32) {
+      fill(sched_first, n_first, {8, 2});
+      fill(sched_later, n_later, {8, 2});
+    } else {
+      fill(sched_first, n_first, {6, 4});
+      fill(sched_later, n_later, {2, 4, 4});
+    }
+  }
+  const int rounds_max = n_first > n_later ? n_first : n_later;
+  ctx->last_spec_k = ctx->solver == 2 ? sched_later[0] : 1;
+  ctx->last_spec_first = ctx->solver == 2 ? sched_first[0] : 1;
   int g = 0; /* running index of the speculative rounds of this call: selects the retry-list counter / buffer */
   if (ctx->solver == 2) {
-    const long long need_cnt = (long long)args->iterations_outerloop * args->iterations_innerloop * ((10 + spec_K - 1) / spec_K) + 2;
+    const long long need_cnt = (long long)args->iterations_outerloop * args->iterations_innerloop * rounds_max + 2;
     if (need_cnt > SPEC_CNT_CAP) { ctx->err = "outer x inner iterations exceed the retry-list counters"; return TEBGPU_ERR_CAPACITY; }
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->spec.cnt, 0, (size_t)need_cnt * sizeof(int32_t), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->defer, 0, (size_t)B * sizeof(int32_t), st));
@@ -520,14 +580,15 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
         if (deferred_done) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0)); deferred_done = false; }
       }
       if (ctx->solver == 2) {
-        const int K = spec_K;
-        ctx->spec.K = K;
-        const int bk = B * K;
-        const int rounds = (10 + K - 1) / K; /* g2o's maxTrialsAfterFailure = 10 */
-        const size_t smem_e = eval_smem_bytes(bt->n_cap, bt->M_cap, K);
+        const int* sched = (it == 0) ? sched_first : sched_later;
+        const int rounds = (it == 0) ? n_first : n_later; /* widths add up to g2o's maxTrialsAfterFailure = 10 */
         const bool fork = overlap && rounds > 1 && !kp.has_vor;
         cudaStream_t rs = st;
         for (int round = 0; round < rounds; ++round, ++g) {
+          const int K = sched[round];
+          ctx->spec.K = K;
+          const int bk = B * K;
+          const size_t smem_e = eval_bytes(ctx, bt->n_cap, bt->M_cap, K);
           if (round == 1 && fork) { /* retry rounds go to the side stream */
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
@@ -646,7 +707,14 @@ static int32_t upload_batch(tebgpu_ctx* ctx, const TebBatch* bt) {
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_ocount, bt->obst_count, (size_t)bt->S * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   if (bt->PV_cap > 0)
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pverts, bt->obst_vertices, (size_t)bt->S * bt->PV_cap * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  /* host entry points can check the obstacle table before it is used */
+  /* host entry points can check every per-element input before the device indexes with it */
+  for (int sc = 0; sc < bt->S; ++sc)
+    if (bt->obst_count[sc] < 0 || bt->obst_count[sc] > bt->M_cap) { ctx->err = "obst_count[s] outside 0 .. M_cap"; return TEBGPU_ERR_INVALID_ARG; }
+  for (int b = 0; b < bt->B; ++b) {
+    if (bt->scene_id[b] < 0 || bt->scene_id[b] >= bt->S) { ctx->err = "scene_id[b] outside 0 .. S-1"; return TEBGPU_ERR_INVALID_ARG; }
+    if (bt->n[b] < 0 || bt->n[b] > bt->n_cap) { ctx->err = "n[b] outside 0 .. n_cap"; return TEBGPU_ERR_INVALID_ARG; }
+    if (bt->V_cap > 0 && (bt->via_count[b] < 0 || bt->via_count[b] > bt->V_cap)) { ctx->err = "via_count[b] outside 0 .. V_cap"; return TEBGPU_ERR_INVALID_ARG; }
+  }
   for (int sc = 0; sc < bt->S; ++sc)
     for (int m = 0; m < bt->obst_count[sc] && m < bt->M_cap; ++m) {
       const TebObstacle& o = bt->obstacles[(size_t)sc * bt->M_cap + m];
@@ -737,7 +805,7 @@ int32_t tebgpu_h_signature(tebgpu_ctx* ctx, const TebBatch* bt, int32_t use_time
   const size_t stride = three_d ? (size_t)(bt->M_cap > 0 ? bt->M_cap : 1) : 2;
   const size_t smem = hsig_smem_bytes(bt->n_cap, bt->M_cap);
   if (smem > 232448) { ctx->err = "h-signature staging exceeds shared memory"; return TEBGPU_ERR_CAPACITY; }
-  double* d_out = device_ptrs ? h_out : ctx->Hb; /* the normal-equation workspace is free outside optimize calls */
+  double* d_out = device_ptrs ? h_out : ctx->d_hsig; /* [B][stride] <= [max_bands][max(max_obstacles, 2)] */
   if (three_d) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_hsig3d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_hsig3d<<<B, HSIG_THREADS, smem, st>>>(db, kp, use_timediffs, d_out);
@@ -807,6 +875,87 @@ int32_t tebgpu_build_system(tebgpu_ctx* ctx, const TebBatch* bt, int32_t outer_i
     delete[] tmp;
     delete[] hn;
   }
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return TEBGPU_OK;
+}
+
+/* ------------------------------------------------------------------ the one collective: all-gather of the costs */
+#define NCCL_TRY(ctx, expr)                                                                              \
+  do {                                                                                                   \
+    ncclResult_t _r = (expr);                                                                            \
+    if (_r != ncclSuccess) {                                                                             \
+      (ctx)->err = std::string(#expr) + ": " + (nccl_api().GetErrorString ? nccl_api().GetErrorString(_r) : "NCCL error"); \
+      return TEBGPU_ERR_CUDA;                                                                            \
+    }                                                                                                    \
+  } while (0)
+
+int32_t tebgpu_comm_get_unique_id(void* id_out) {
+  static_assert(sizeof(ncclUniqueId) == TEBGPU_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  if (!id_out) return TEBGPU_ERR_INVALID_ARG;
+  NcclApi& api = nccl_api();
+  if (!api.ok()) { std::fprintf(stderr, "tebgpu_comm_get_unique_id: %s\n", api.error.c_str()); return TEBGPU_ERR_UNSUPPORTED; }
+  ncclUniqueId id;
+  if (api.GetUniqueId(&id) != ncclSuccess) return TEBGPU_ERR_CUDA;
+  std::memcpy(id_out, &id, sizeof(id));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_comm_init(tebgpu_ctx* ctx, const void* id, int32_t world_size, int32_t rank) {
+  if (!ctx || !id || world_size < 1 || rank < 0 || rank >= world_size) return TEBGPU_ERR_INVALID_ARG;
+  NcclApi& api = nccl_api();
+  if (!api.ok()) { ctx->err = api.error.empty() ? "NCCL unavailable" : api.error; return TEBGPU_ERR_UNSUPPORTED; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->comm) { api.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof(uid));
+  NCCL_TRY(ctx, api.CommInitRank(&ctx->comm, world_size, uid, rank));
+  ctx->world = world_size;
+  ctx->rank = rank;
+  if (ctx->d_gather) { cudaFree(ctx->d_gather); ctx->d_gather = nullptr; }
+  CUDA_TRY(ctx, cudaMalloc(&ctx->d_gather, (size_t)world_size * ctx->lim.max_bands * sizeof(double)));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_comm_destroy(tebgpu_ctx* ctx) {
+  if (!ctx) return TEBGPU_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ctx->world = 1; ctx->rank = 0;
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_gather_costs(tebgpu_ctx* ctx, const double* cost_local, int32_t count_local, double* cost_all, int32_t device_ptrs) {
+  if (!ctx || !cost_local || !cost_all || count_local < 1) return TEBGPU_ERR_INVALID_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t bytes = (size_t)count_local * sizeof(double);
+  if (!ctx->comm) { /* one rank: the gathered vector is the local one */
+    if (device_ptrs) { if (cost_all != cost_local) CUDA_TRY(ctx, cudaMemcpyAsync(cost_all, cost_local, bytes, cudaMemcpyDeviceToDevice, st)); }
+    else std::memmove(cost_all, cost_local, bytes);
+    return TEBGPU_OK;
+  }
+  if (device_ptrs) {
+    NCCL_TRY(ctx, nccl_api().AllGather(cost_local, cost_all, (size_t)count_local, ncclDouble, ctx->comm, st));
+    return TEBGPU_OK;
+  }
+  if (count_local > ctx->lim.max_bands) { ctx->err = "gather of more than max_bands costs"; return TEBGPU_ERR_CAPACITY; }
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_cost, cost_local, bytes, cudaMemcpyHostToDevice, st));
+  NCCL_TRY(ctx, nccl_api().AllGather(ctx->d_cost, ctx->d_gather, (size_t)count_local, ncclDouble, ctx->comm, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(cost_all, ctx->d_gather, bytes * ctx->world, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_optimize_batch_gather(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimizeArgs* args, double* cost_all) {
+  if (!ctx || !bt || !cost_all || !bt->cost) return TEBGPU_ERR_INVALID_ARG;
+  /* the device-side costs of the host entry point live in d_cost: gather them before they travel to the host */
+  int32_t rc = tebgpu_optimize_batch(ctx, bt, args);
+  if (rc) return rc;
+  if (!ctx->comm) { std::memcpy(cost_all, bt->cost, (size_t)bt->B * sizeof(double)); return TEBGPU_OK; }
+  cudaStream_t st = ctx->stream;
+  NCCL_TRY(ctx, nccl_api().AllGather(ctx->d_cost, ctx->d_gather, (size_t)bt->B, ncclDouble, ctx->comm, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(cost_all, ctx->d_gather, (size_t)bt->B * ctx->world * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   return TEBGPU_OK;
 }

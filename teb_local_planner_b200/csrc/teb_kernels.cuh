@@ -141,7 +141,7 @@ __global__ void k_begin(DevBatch db, KParams kp) {
   if (b < db.S) { /* compact list of the scene's dynamic obstacles (AddEdgesDynamicObstacles iterates only those) */
     const TebObstacle* go = db.obstacles + (size_t)b * db.M_cap;
     int cnt = 0;
-    const int M = db.obst_count[b];
+    const int M = min(max(db.obst_count[b], 0), db.M_cap);
     for (int m = 0; m < M; ++m)
       if (go[m].dynamic) db.dyn_idx[(size_t)b * db.M_cap + cnt++] = m;
     db.dyn_cnt[b] = cnt;
@@ -152,11 +152,16 @@ __global__ void k_begin(DevBatch db, KParams kp) {
   for (int k = 0; k < 4; ++k) { st.parts_last[k] = 0; st.parts_cur[k] = 0; }
   st.active = 0; st.failed = 0; st.status = 0; st.lm_iters = 0;
   if (!kp.p.optimization_activate) { st.failed = 1; st.status |= TEB_STATUS_DISABLED; }
-  { /* obstacle rows the batch cannot describe (the device entry point cannot check them on the host) */
-    const int sc = db.scene_id[b];
-    const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
-    const int M = db.obst_count[sc];
+  { /* inputs the batch cannot describe (the device entry point cannot check them on the host): band length, scene
+     * index, obstacle / via-point counts, obstacle rows. Such a band is left untouched and reported. */
+    int sc = db.scene_id[b];
     bool bad = false;
+    if (sc < 0 || sc >= db.S) { bad = true; sc = 0; }
+    if (db.n[b] < 1 || db.n[b] > db.n_cap) bad = true;
+    if (db.V_cap > 0 && db.via_count && (db.via_count[b] < 0 || db.via_count[b] > db.V_cap)) bad = true;
+    int M = db.obst_count[sc];
+    if (M < 0 || M > db.M_cap) { bad = true; M = 0; }
+    const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
     for (int m = 0; m < M; ++m) {
       const int type = go[m].type, vb = go[m].vertex_begin, vc = go[m].vertex_count;
       if (type < TEB_OBST_POINT || type > TEB_OBST_POLYGON) bad = true;

@@ -86,7 +86,7 @@ TEB_HD inline int teb_auto_resize_records(double* rec, int n, int n_cap, double 
     }
     if (fast_mode) break;
   }
-  rec[4 * (n - 1) + 3] = 0.0;
+  if (n >= 1) rec[4 * (n - 1) + 3] = 0.0; /* an empty band stays empty (the reference has no time difference to touch) */
   return n;
 }
 

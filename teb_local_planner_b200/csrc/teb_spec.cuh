@@ -435,4 +435,274 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch d
   }
 }
 
+
+/* ====================================================================================================================
+ * k_trial_eval2 — trial evaluation, second generation (the default): ONE LANE PER POSE.
+ * A CTA still owns one band and stages the current band, the K trial solutions, the right-hand side and the scene's
+ * obstacle table once; but the chi2 of a trial is no longer a per-lane walk over a chunk of poses with a dependent carry:
+ * a warp takes a (trial, 30-pose tile) task, every lane forms the trial state of its own pose (x [+] dx), its sin / cos
+ * and the velocities of its own segment, the right neighbour's values arrive by warp shuffles (2 halo lanes per tile),
+ * and the lane evaluates all cost terms anchored at its pose. Tile partials are folded in a fixed order, then one thread
+ * replays g2o's accept / reject chain (spec_decide) and the CTA commits the accepted trial state.
+ * ==================================================================================================================== */
+constexpr int EV2_THREADS = 256;
+constexpr int EV2_TILE = 30;      /* poses evaluated per warp task: lanes 0 .. 29 (lanes 30, 31: halo) */
+__host__ __device__ inline int ev2_tiles(int n_cap) { return (n_cap + EV2_TILE - 1) / EV2_TILE; }
+__host__ __device__ inline size_t eval2_smem_bytes(int n_cap, int M_cap, int K) {
+  return ((size_t)K + 2) * 4 * n_cap * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) +
+         ((size_t)K * ev2_tiles(n_cap) * 5 + (size_t)K * RES_STRIDE) * sizeof(double) + 64;
+}
+
+/* chi2 contributions of everything anchored at pose i of a trial state held in registers: chain edges of segment i,
+ * time-optimal edge i, unary edges of pose i. (xa .. dta, ca, sa): pose i; (xb .. dtb, cb, sb): pose i+1; s1 / s2:
+ * velocities of the segments i and i+1. Same arithmetic as pose_chi2 (teb_kernels.cuh). */
+template <bool GEOM>
+__device__ __forceinline__ void pose_chi2_lane(const KParams& kp, const DevBatch& db, int b, int sc, int i, int n, double xa,
+                                               double ya, double tha, double dta, double ca, double sa, double xb, double yb,
+                                               double thb, double dtb, double cb, double sb, const SegVal& s1, const SegVal& s2,
+                                               const TebObstacle* so, int M, const double* vs, const double* vg, double (&chi)[4]) {
+  if (i <= n - 2) {
+    const double dx = xb - xa, dy = yb - ya;
+    double sl, csum = 0;
+    if (kp.has_vel && kp.holo_vel) {
+      double e[3], s3[3], c0, c1;
+      holo_velocity_terms(kp, s1.vx, s1.vy, s1.w, e, s3, c0, c1);
+      const double e0 = kp.sw_vel_x * e[0], e1 = kp.sw_vel_y * e[1], e2 = kp.sw_vel_th * e[2];
+      csum += e0 * e0 + e1 * e1 + e2 * e2;
+    } else if (kp.has_vel) {
+      const double e0 = kp.sw_vel_x * pen_interval2(s1.v, -kp.p.max_vel_x_backwards, kp.p.max_vel_x, kp.p.penalty_epsilon, sl);
+      const double e1 = kp.sw_vel_th * pen_interval(s1.w, kp.p.max_vel_theta, kp.p.penalty_epsilon, sl);
+      csum += e0 * e0 + e1 * e1;
+    }
+    if (kp.has_kin) {
+      const double e0 = kp.sw_kin_nh * fabs((ca + cb) * dy - (sa + sb) * dx);
+      double e1 = 0;
+      if (!kp.carlike) {
+        e1 = pen_below(dx * ca + dy * sa, 0, 0, sl);
+      } else {
+        const double ad = normalize_theta(thb - tha);
+        if (ad != 0) {
+          const double nrm = sqrt(dx * dx + dy * dy);
+          const double r = kp.p.exact_arc_length ? fabs(nrm / (2 * sin(ad / 2))) : nrm / fabs(ad);
+          e1 = pen_below(r, kp.p.min_turning_radius, 0.0, sl);
+        }
+      }
+      e1 *= kp.sw_kin_2;
+      csum += e0 * e0 + e1 * e1;
+    }
+    if (kp.has_sp) {
+      const double e = kp.sw_sp * sqrt(dx * dx + dy * dy);
+      csum += e * e;
+    }
+    if (kp.has_rot && i < 3) {
+      const int rd = db.prefer_rotdir ? db.prefer_rotdir[b] : 0;
+      if (rd == TEB_ROTDIR_LEFT || rd == TEB_ROTDIR_RIGHT) {
+        const double meas = (rd == TEB_ROTDIR_LEFT) ? 1.0 : -1.0;
+        const double e = kp.sw_rot * pen_below(meas * normalize_theta(thb - tha), 0, 0, sl);
+        csum += e * e;
+      }
+    }
+    if (kp.has_acc && kp.holo_acc) {
+      const double idt1 = 1.0 / dta;
+      const double lim[3] = {kp.p.acc_lim_x, kp.p.acc_lim_y, kp.p.acc_lim_theta};
+      const double sw[3] = {kp.sw_acc_x, kp.sw_acc_y, kp.sw_acc_th};
+      const double u1[3] = {s1.vx, s1.vy, s1.w};
+      if (i <= n - 3) {
+        const double iT = 1.0 / (dta + dtb);
+        const double u2[3] = {s2.vx, s2.vy, s2.w};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const double e = sw[r] * pen_interval((u2[r] - u1[r]) * 2 * iT, lim[r], kp.p.penalty_epsilon, sl);
+          csum += e * e;
+        }
+      } else if (vg[3] != 0) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const double e = sw[r] * pen_interval((vg[r] - u1[r]) * idt1, lim[r], kp.p.penalty_epsilon, sl);
+          csum += e * e;
+        }
+      }
+      if (i == 0 && vs[3] != 0) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const double e = sw[r] * pen_interval((u1[r] - vs[r]) * idt1, lim[r], kp.p.penalty_epsilon, sl);
+          csum += e * e;
+        }
+      }
+    } else if (kp.has_acc) {
+      const double idt1 = 1.0 / dta;
+      if (i <= n - 3) {
+        const double iT = 1.0 / (dta + dtb);
+        const double e0 = kp.sw_acc_x * pen_interval((s2.v - s1.v) * 2 * iT, kp.p.acc_lim_x, kp.p.penalty_epsilon, sl);
+        const double e1 = kp.sw_acc_th * pen_interval((s2.w - s1.w) * 2 * iT, kp.p.acc_lim_theta, kp.p.penalty_epsilon, sl);
+        csum += e0 * e0 + e1 * e1;
+      } else if (vg[3] != 0) {
+        const double e0 = kp.sw_acc_x * pen_interval((vg[0] - s1.v) * idt1, kp.p.acc_lim_x, kp.p.penalty_epsilon, sl);
+        const double e1 = kp.sw_acc_th * pen_interval((vg[2] - s1.w) * idt1, kp.p.acc_lim_theta, kp.p.penalty_epsilon, sl);
+        csum += e0 * e0 + e1 * e1;
+      }
+      if (i == 0 && vs[3] != 0) {
+        const double e0 = kp.sw_acc_x * pen_interval((s1.v - vs[0]) * idt1, kp.p.acc_lim_x, kp.p.penalty_epsilon, sl);
+        const double e1 = kp.sw_acc_th * pen_interval((s1.w - vs[2]) * idt1, kp.p.acc_lim_theta, kp.p.penalty_epsilon, sl);
+        csum += e0 * e0 + e1 * e1;
+      }
+    }
+    if (kp.has_vor) { /* EdgeVelocityObstacleRatio: obstacles associated with pose i (pose 0 included) */
+      const unsigned long long* am = db.assoc + ((size_t)b * db.n_cap + i) * db.MW;
+      for (int w = 0; w < db.MW; ++w) {
+        unsigned long long mask = am[w];
+        while (mask) {
+          const int m = (w << 6) + __ffsll((long long)mask) - 1;
+          mask &= mask - 1;
+          const TebObstacle ob = so[m];
+          double dratio;
+          const double d = robot_obstacle_distance_only<GEOM>(kp, db.obst_vertices + (size_t)sc * db.PV_cap * 2, xa, ya, ca, sa, ob,
+                                                        ob.x, ob.y, 0.0, 0.0);
+          const double ratio = proximity_ratio(kp, d, dratio);
+          const double e0 = pen_interval(s1.v, ratio * kp.p.max_vel_x, 0, sl);
+          const double e1 = pen_interval(s1.w, ratio * kp.p.max_vel_theta, 0, sl);
+          csum += kp.p.weight_velocity_obstacle_ratio * (e0 * e0 + e1 * e1);
+        }
+      }
+    }
+    chi[3] += csum;
+    if (kp.has_time) chi[2] += kp.p.weight_optimaltime * dta * dta;
+  }
+  double U[6], ub[3];
+  unary_terms<GEOM>(kp, db, b, sc, i, n, xa, ya, ca, sa, so, M, false, U, ub, chi[0], chi[1]);
+}
+
+template <bool GEOM>
+__global__ void __launch_bounds__(EV2_THREADS, 2) k_trial_eval2(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp,
+                                                             const __grid_constant__ SpecBufs sp, int iteration, int round,
+                                                             int g, int tag) {
+  extern __shared__ __align__(16) unsigned char ev_raw[];
+  const int SPEC_K = sp.K;
+  const int slot = blockIdx.x;
+  if (round > 0 && slot >= sp.cnt[g]) return;
+  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  BandState* st = &db.state[b];
+  if (!st->active) return;
+  const int q0 = (round == 0) ? 0 : sp.qmax[b];
+  const int n = db.n[b];
+  const int N = 4 * n;
+  const int tiles = (n + EV2_TILE - 1) / EV2_TILE;
+  double* sdx = reinterpret_cast<double*>(ev_raw);            /* [K][4 n_cap] trial solutions */
+  double* sP0 = sdx + (size_t)SPEC_K * 4 * db.n_cap;           /* [n_cap][4] current band */
+  double* sB = sP0 + (size_t)4 * db.n_cap;                     /* [4 n_cap] right-hand side */
+  double* sPart = sB + (size_t)4 * db.n_cap;                   /* [K][tiles(n_cap)][5] tile partials: chi by family, scale */
+  double* sRes = sPart + (size_t)SPEC_K * ev2_tiles(db.n_cap) * 5; /* [K][RES_STRIDE] */
+  int* sAcc = reinterpret_cast<int*>(sRes + (size_t)SPEC_K * RES_STRIDE);
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(sAcc + 4);
+  const int sc = db.scene_id[b];
+  const int M = db.obst_count[sc];
+  {
+    const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
+    for (int m = tid; m < M; m += EV2_THREADS) so[m] = go[m];
+    const double* gP = db.poses + (size_t)b * db.n_cap * 4;
+    const double* grhs = db.rhs + (size_t)b * 4 * db.n_cap;
+    /* the K trial solutions of a band sit in adjacent lanes of the solver's interleaved scratch (K even) */
+    for (int r = tid; r < N; r += EV2_THREADS) {
+      sP0[r] = gP[r];
+      sB[r] = grhs[r];
+      for (int kk = 0; kk < SPEC_K; kk += 2) {
+        const int tsys = slot * SPEC_K + kk;
+        const double2 a = *reinterpret_cast<const double2*>(sp.dx + (size_t)(tsys >> 5) * 32 * 4 * db.n_cap + (size_t)r * 32 + (tsys & 31));
+        sdx[(size_t)kk * 4 * db.n_cap + r] = a.x;
+        sdx[(size_t)(kk + 1) * 4 * db.n_cap + r] = a.y;
+      }
+    }
+  }
+  __syncthreads();
+  const int kact = min(SPEC_K, 10 - q0); /* trials of this round that exist (g2o stops after 10) */
+  const double* vs = db.vel_start + 4 * (size_t)b;
+  const double* vg = db.vel_goal + 4 * (size_t)b;
+  for (int task = warp; task < kact * tiles; task += EV2_THREADS / 32) {
+    const int k = task / tiles, tile = task - k * tiles;
+    const int i = tile * EV2_TILE + lane;
+    const double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
+    const bool ok = res[5] != 0.0;
+    const double lambda = res[6];
+    const double* mydx = sdx + (size_t)k * 4 * db.n_cap;
+    double chi[4] = {0, 0, 0, 0};
+    double scl = 0;
+    double x = 0, y = 0, th = 0, dt = 1, ca = 1, sa = 0;
+    SegVal s1;
+    s1.v = 0; s1.w = 0; s1.vx = 0; s1.vy = 0;
+    const bool have = i < n;
+    const bool own = have && lane < EV2_TILE;
+    if (have) { /* trial state x [+] dx (VertexPose::oplusImpl / VertexTimeDiff::oplusImpl), computeScale() on the owned rows */
+      double v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int r = 4 * i + c;
+        double xv = sP0[r];
+        if (row_is_real(r, n)) {
+          const double bb = sB[r];
+          const double dxv = ok ? mydx[r] : bb; /* CSparse leaves x = b when the factorisation fails */
+          if (own) scl += dxv * (lambda * dxv + bb);
+          xv = (c == 2) ? normalize_theta(xv + dxv) : xv + dxv;
+        }
+        v[c] = xv;
+      }
+      x = v[0]; y = v[1]; th = v[2]; dt = v[3];
+      sincos(th, &sa, &ca);
+    }
+    /* pose i+1 from the right neighbour */
+    const double xb = __shfl_down_sync(0xffffffffu, x, 1), yb = __shfl_down_sync(0xffffffffu, y, 1);
+    const double thb = __shfl_down_sync(0xffffffffu, th, 1), dtb = __shfl_down_sync(0xffffffffu, dt, 1);
+    const double cb = __shfl_down_sync(0xffffffffu, ca, 1), sb = __shfl_down_sync(0xffffffffu, sa, 1);
+    if (have && i <= n - 2 && lane < 31) s1 = seg_value(kp, x, y, th, ca, sa, xb, yb, thb, dt);
+    SegVal s2;
+    s2.v = __shfl_down_sync(0xffffffffu, s1.v, 1); s2.w = __shfl_down_sync(0xffffffffu, s1.w, 1);
+    s2.vx = __shfl_down_sync(0xffffffffu, s1.vx, 1); s2.vy = __shfl_down_sync(0xffffffffu, s1.vy, 1);
+    if (own) pose_chi2_lane<GEOM>(kp, db, b, sc, i, n, x, y, th, dt, ca, sa, xb, yb, thb, dtb, cb, sb, s1, s2, so, M, vs, vg, chi);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) chi[c] = warp_sum(chi[c]);
+    scl = warp_sum(scl);
+    if (lane == 0) {
+      double* pp = sPart + ((size_t)k * ev2_tiles(db.n_cap) + tile) * 5;
+      pp[0] = chi[0]; pp[1] = chi[1]; pp[2] = chi[2]; pp[3] = chi[3]; pp[4] = scl;
+    }
+  }
+  __syncthreads();
+  if (tid < kact) { /* fold the tile partials of trial tid in tile order */
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int t = 0; t < tiles; ++t) {
+      const double* pp = sPart + ((size_t)tid * ev2_tiles(db.n_cap) + t) * 5;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) a[c] += pp[c];
+    }
+    double* r = sRes + tid * RES_STRIDE;
+    r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = a[3]; r[4] = a[4];
+    r[5] = sp.res[((size_t)b * SPEC_K + tid) * RES_STRIDE + 5];
+  }
+  __syncthreads();
+  /* ---- accept / reject replay, sequential over the K trials */
+  if (tid == 0) {
+    DecideArgs da;
+    da.st = st; da.chi_parts = db.chi_parts + (size_t)b * db.chunks * 4;
+    da.lambda_init = (round == 0 && iteration == 0) ? band_lambda_init(db, b, n) : 0.0;
+    da.need = sp.need + b; da.qmax = sp.qmax + b; da.cnt_next = sp.cnt + g + 1;
+    da.list_next = sp.list + (size_t)((g + 1) % 3) * db.B;
+    da.defer = db.defer + b; da.tag = tag;
+    da.b = b; da.n = n; da.K = SPEC_K; da.iteration = iteration; da.round = round; da.q0 = q0; da.tile = db.tile;
+    sAcc[0] = spec_decide(da, sRes);
+  }
+  __syncthreads();
+  const int accepted = sAcc[0];
+  if (accepted >= 0) { /* discardTop(): the accepted trial state becomes the band (same arithmetic as above) */
+    double* gP = db.poses + (size_t)b * db.n_cap * 4;
+    const double* adx = sdx + (size_t)accepted * 4 * db.n_cap;
+    const bool ok = sRes[accepted * RES_STRIDE + 5] != 0.0;
+    for (int r = tid; r < N; r += EV2_THREADS) {
+      if (!row_is_real(r, n)) continue;
+      const double dxv = ok ? adx[r] : sB[r];
+      const double xv = sP0[r] + dxv;
+      gP[r] = ((r & 3) == 2) ? normalize_theta(xv) : xv;
+    }
+  }
+}
+
 }  // namespace tebgpu

@@ -1,8 +1,18 @@
 """Multi-GPU plumbing: one process per GPU, the batch axis (candidates x requests) sharded contiguously, ONE
 all-gather of the per-candidate costs per plan, then HomotopyClassPlanner::selectBestTeb on the gathered costs
 (reference src/homotopy_class_planner.cpp:466-493 fan-out, :564-616 selection). Bands never exchange data during
-optimisation, so there is no data-path collective.
+optimisation (SURVEY.md par. 8e), so there is no data-path collective.
+
+The collective itself lives BEHIND the C-ABI (tebgpu_comm_init / tebgpu_gather_costs: ncclAllGather on the context's
+stream, include/teb_b200.h). This module only
+  * splits the batch axis (`shard_range`),
+  * bootstraps the communicator: rank 0 creates the 128-byte NCCL id, `torch.distributed` (any backend) carries it to
+    the other ranks (`init_comm`) - the same job MPI or a file would do for a C++ host,
+  * restates selectBestTeb for whole request batches (`select_best_per_request`),
+  * offers the same gather over a torch process group for CPU tests (`gather_costs_torch`, gloo).
 """
+import ctypes as C
+
 import numpy as np
 
 
@@ -14,11 +24,32 @@ def shard_range(B, rank, world):
     return lo, hi
 
 
-def gather_costs(local_cost, world=None, group=None):
-    """Single all-gather of the local cost vector (torch tensor, cuda for NCCL / cpu for gloo).
+def shard_requests(requests, rank, world):
+    """Requests are never split across ranks when their count allows it (selection of one request then needs no
+    remote candidate, the gather is still done so that every rank knows every winner)."""
+    return shard_range(requests, rank, world)
 
-    Shards must have equal length (pad with +inf on the caller side otherwise). Returns the [world * len] tensor.
-    """
+
+def init_comm(gpu, rank, world, device=None):
+    """Collective: creates the NCCL communicator of `gpu` (a TebGpu context) across the ranks of the default torch process
+    group. rank 0 draws the unique id through the C-ABI; torch.distributed only transports those 128 bytes."""
+    import torch
+    import torch.distributed as dist
+    ident = np.zeros(128, np.uint8)
+    if rank == 0:
+        gpu.comm_get_unique_id(ident)
+    t = torch.from_numpy(ident)
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=0)
+    ident = t.cpu().numpy().copy()
+    gpu.comm_init(ident, world, rank)
+    return gpu
+
+
+def gather_costs_torch(local_cost, world=None, group=None):
+    """The same all-gather over a torch process group (gloo on CPU): used by the CPU tests of the N > 1 host logic.
+    Shards must have equal length. Returns the [world * len] tensor."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if world is None else world

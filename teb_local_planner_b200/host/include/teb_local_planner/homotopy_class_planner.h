@@ -52,6 +52,8 @@ class HomotopyClassPlanner : public PlannerInterface {
   TebOptimalPlannerPtr addAndInitNewTeb(const std::vector<geometry_msgs::PoseStamped>& initial_plan,
                                         const geometry_msgs::Twist* start_velocity, bool free_goal_vel = false);
   void updateAllTEBs(const PoseSE2* start, const PoseSE2* goal, const geometry_msgs::Twist* start_velocity);
+  /* homotopy_class_planner.cpp:304-335 */
+  void updateReferenceTrajectoryViaPoints(bool all_trajectories);
   void optimizeAllTEBs(int iter_innerloop, int iter_outerloop);
   TebOptimalPlannerPtr getInitialPlanTEB();
   TebOptimalPlannerPtr selectBestTeb();

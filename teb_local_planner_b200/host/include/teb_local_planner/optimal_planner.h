@@ -13,6 +13,7 @@
 #define TEB_B200_OPTIMAL_PLANNER_H_
 
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "teb_b200.h"
@@ -34,11 +35,13 @@ class TebGpuContext {
   ~TebGpuContext();
   tebgpu_ctx* get() const { return ctx_; }
   const TebGpuLimits& limits() const { return lim_; }
+  std::mutex& mutex() { return mutex_; } /* serialises set_params .. optimize sequences of planners sharing the context */
   static std::shared_ptr<TebGpuContext> shared(int min_bands = 8, int min_poses = 512, int min_obstacles = 256,
                                                int min_viapoints = 16, int min_obst_vertices = 2048);
  private:
   tebgpu_ctx* ctx_ = nullptr;
   TebGpuLimits lim_{};
+  std::mutex mutex_;
 };
 typedef std::shared_ptr<TebGpuContext> TebGpuContextPtr;
 

@@ -49,15 +49,27 @@ bool HomotopyClassPlanner::plan(const PoseSE2& start, const PoseSE2& goal, const
   if (!initialized_) return false;
   updateAllTEBs(&start, &goal, start_vel);
   exploreEquivalenceClassesAndInitTebs(start, goal, cfg_->obstacles.min_obstacle_dist, start_vel, free_goal_vel);
-  /* updateReferenceTrajectoryViaPoints (:304-335): all candidates, or only the one that follows the initial plan */
-  for (auto& teb : tebs_) {
-    if (cfg_->hcp.viapoints_all_candidates || teb == initial_plan_teb_) teb->setViaPoints(via_points_);
-    else teb->setViaPoints(NULL);
-  }
+  updateReferenceTrajectoryViaPoints(cfg_->hcp.viapoints_all_candidates);
   optimizeAllTEBs(cfg_->optim.no_inner_iterations, cfg_->optim.no_outer_iterations);
   selectBestTeb();
   initial_plan_ = nullptr;
   return true;
+}
+
+/* Which candidates are pulled towards the via-points (reference :304-335). Nothing changes when there is nothing to
+ * attach (no via-points, weight <= 0) or - in the "initial plan only" mode - when this cycle has no initial plan. Otherwise
+ * every candidate gets them, or exactly those whose equivalence class equals the class of the initial plan: the class is
+ * compared, not the band object, because from the second cycle on an older band usually holds that class already. */
+void HomotopyClassPlanner::updateReferenceTrajectoryViaPoints(bool all_trajectories) {
+  const bool nothing_to_attach = !via_points_ || via_points_->empty() || cfg_->optim.weight_viapoint <= 0;
+  if (nothing_to_attach || (!all_trajectories && !initial_plan_)) return;
+  if (equivalence_classes_.size() < tebs_.size()) return; /* classes and bands out of step: leave the assignment alone */
+  for (size_t k = 0; k < tebs_.size(); ++k) {
+    bool attach = all_trajectories;
+    if (!attach && initial_plan_eq_class_ && equivalence_classes_[k].first)
+      attach = initial_plan_eq_class_->isEqual(*equivalence_classes_[k].first);
+    tebs_[k]->setViaPoints(attach ? via_points_ : NULL);
+  }
 }
 
 bool HomotopyClassPlanner::getVelocityCommand(double& vx, double& vy, double& omega, int look_ahead_poses) const {

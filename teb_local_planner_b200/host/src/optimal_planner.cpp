@@ -217,6 +217,9 @@ bool TebOptimalPlanner::runBatch(const TebConfig& cfg, const std::vector<TebOpti
       return false;
     }
   }
+  /* one context = one stream + one parameter block: set_params .. optimize of two planners on different threads must
+   * not interleave on a shared context (the reference gives every planner its own optimizer) */
+  std::lock_guard<std::mutex> context_guard(gpu->mutex());
   TebParams params = cfg.toParams();
   if (planners[0]->robot_model_) planners[0]->robot_model_->fillParams(params);
   int rc = tebgpu_set_params(gpu->get(), &params);

@@ -62,6 +62,8 @@ def lib():
         L.teb_ref_compute_cost.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, vp, i, vp]
         L.teb_ref_build_system.restype = i
         L.teb_ref_build_system.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, vp, i, d, vp, vp, C.POINTER(d), vp, i, C.POINTER(i)]
+        L.teb_ref_optimize_batch.restype = i
+        L.teb_ref_optimize_batch.argtypes = [vp, vp, vp, i, i]
         assert L.teb_ref_abi() == 2
         _lib = L
     return _lib
@@ -140,6 +142,15 @@ def optimize_band(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=
     stats = {"lm_trials": int(st[0]), "rejected": int(st[1]), "terminated": bool(st[2]), "chol_failed": bool(st[3]),
              "diverged": bool(st[4]), "optimized": bool(st[5])}
     return buf[:nn.value].copy(), cost.value, stats, bool(rc)
+
+
+def optimize_batch(params, hb, args, threads=1, pin=False):
+    """In-place on the HostBatch arrays: one band at a time per host thread (the reference's optimizeAllTEBs model)."""
+    bs = hb.struct()
+    rc = lib().teb_ref_optimize_batch(C.addressof(params), C.addressof(bs), C.addressof(args), int(threads), int(bool(pin)))
+    if rc != 0:
+        raise RuntimeError(f"teb_ref_optimize_batch rc={rc}")
+    return hb
 
 
 def compute_cost(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=None, rotdir=0, args=None, obst_vertices=None):
