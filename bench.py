@@ -193,13 +193,19 @@ def sub_batch(hb, keep):
 
 
 def cpu_arm(p, hb, args, cand, workload, reps, warmup):
-    """The reference's CPU path on the host cores: oracle/teb_oracle.c in g2o mode (numeric Jacobians, banded
-    Cholesky), one band at a time per pinned worker thread (the reference's optimizeAllTEBs model). One repetition
-    processes `sampled_bands` bands of the workload (throughput is per band, bands are independent); the thread count is
-    chosen by a probe that runs the SAME sample; value = sampled_bands / median repetition time (BASELINE.md par. 2:
-    median + p10 / p90 of >= 20 repetitions for the reference arm). `effective_cores` = process CPU time / wall time
-    of the timed repetitions: what the box really served, whatever `nproc` says."""
+    """The reference's CPU path on the host cores, one band at a time per pinned worker thread (the reference's own
+    optimizeAllTEBs model). Two builds of it exist and BOTH are timed:
+      "reference"  oracle/_ref/libteb_ref.so: the reference's own optimal_planner.cpp / timed_elastic_band.cpp /
+                   obstacles.cpp + headers, compiled against stand-ins for Eigen / boost / ROS messages and a restated
+                   g2o optimizer (numeric Jacobians, LM, banded Cholesky) - the primary arm whenever the library exists;
+      "port"       oracle/teb_oracle.c in g2o mode, the plain-C restatement (bit-identical results, ~20 % faster).
+    One repetition processes `sampled_bands` bands of the workload (throughput is per band, bands are independent); the
+    thread count is chosen by a probe that runs the SAME sample; value = sampled_bands / median repetition time
+    (BASELINE.md par. 2: median + p10 / p90 of >= 20 repetitions for the reference arm). `effective_cores` = process CPU
+    time / wall time of the timed repetitions: what the box really served, whatever `nproc` says."""
     from tests import oracle_binding as ob
+    from tests import ref_binding as rb
+    have_ref = os.path.exists(rb.REF_SO)
     tmax = host_threads()
     # ~8 bands per thread and repetition, bounded to ~25 s of single-thread work per repetition
     per_band_ms = {"C1": 2.5, "C2": 6.0, "C3": 14.0, "C4": 22.0}[workload]
@@ -207,42 +213,60 @@ def cpu_arm(p, hb, args, cand, workload, reps, warmup):
     keep = min(keep, hb.B, max(cand, (int(25000.0 / per_band_ms) // cand) * cand))
     sub = sub_batch(hb, keep)
 
-    def one(threads):
+    def one(threads, kind):
         h = sub.copy()
         c0, t0 = time.process_time(), time.perf_counter()
-        ob.optimize_batch(p, h, args, jac_mode=ob.JAC_G2O, threads=threads, pin=True)
+        if kind == "reference":
+            rb.optimize_batch(p, h, args, threads=threads, pin=True)
+        else:
+            ob.optimize_batch(p, h, args, jac_mode=ob.JAC_G2O, threads=threads, pin=True)
         t1, c1 = time.perf_counter(), time.process_time()
         return t1 - t0, c1 - c0, h
 
+    primary = "reference" if have_ref else "port"
     # thread-count probe on the same sample: all visible CPUs, then halves (SMT siblings / quota-limited boxes)
     tried, best_t, best_sec = [], 1, float("inf")
     t = tmax
     while t >= 1:
-        sec = min(one(t)[0] for _ in range(2))
+        sec = min(one(t, primary)[0] for _ in range(2))
         tried.append((t, round(keep / sec, 1)))
         if sec < best_sec:
             best_t, best_sec = t, sec
         if t == 1 or t <= max(1, tmax // 8):
             break
         t = max(1, t // 2)
-    for _ in range(warmup):
-        one(best_t)
-    walls, cpus, h = [], [], None
-    for _ in range(reps):
-        w, c, h = one(best_t)
-        walls.append(w)
-        cpus.append(c)
-    walls = np.array(walls)
-    med = float(np.median(walls))
-    return {"value": keep / med, "unit": UNIT, "cores": best_t, "kind": "port",
-            "p10": keep / float(np.percentile(walls, 90)), "p90": keep / float(np.percentile(walls, 10)),
-            "reps": reps, "sampled_bands": int(keep), "ms_per_rep": med * 1e3,
-            "effective_cores": float(np.sum(cpus) / np.sum(walls)),
-            "host": {"visible_cpus": tmax, "cgroup_quota_cores": cpu_quota_cores(), "cpu_model": cpu_model()},
-            "thread_probe": tried, "lm_iters_per_s": float(h.lm_iters.sum()) / med,
-            "sample": f"{keep} bands of this workload per repetition, oracle/teb_oracle.c in g2o mode (numeric Jacobians, "
-                      f"banded Cholesky), one band at a time per pinned host thread, {best_t} threads (of {tmax} visible), "
-                      f"median of {reps} repetitions"}, sub, h
+
+    def measure(kind, nrep):
+        for _ in range(warmup):
+            one(best_t, kind)
+        walls, cpus, h = [], [], None
+        for _ in range(nrep):
+            w, c, h = one(best_t, kind)
+            walls.append(w)
+            cpus.append(c)
+        walls = np.array(walls)
+        med = float(np.median(walls))
+        return {"value": keep / med, "p10": keep / float(np.percentile(walls, 90)), "p90": keep / float(np.percentile(walls, 10)),
+                "ms_per_rep": med * 1e3, "effective_cores": float(np.sum(cpus) / np.sum(walls))}, h
+
+    main, h = measure(primary, reps)
+    other = None
+    if have_ref:
+        other, h_port = measure("port", min(reps, 5))
+        assert np.array_equal(h.poses, h_port.poses) and np.array_equal(h.cost, h_port.cost), "oracle/_ref and the port disagree"
+        h.lm_iters[...] = h_port.lm_iters
+    cpu = {"value": main["value"], "unit": UNIT, "cores": best_t, "kind": primary,
+           "p10": main["p10"], "p90": main["p90"], "reps": reps, "sampled_bands": int(keep), "ms_per_rep": main["ms_per_rep"],
+           "effective_cores": main["effective_cores"],
+           "host": {"visible_cpus": tmax, "cgroup_quota_cores": cpu_quota_cores(), "cpu_model": cpu_model()},
+           "thread_probe": tried, "lm_iters_per_s": float(h.lm_iters.sum()) / (main["ms_per_rep"] * 1e-3),
+           "port_value": other["value"] if other else None,
+           "sample": f"{keep} bands of this workload per repetition, " +
+                     ("oracle/_ref (the reference's own optimal_planner.cpp / timed_elastic_band.cpp / obstacles.cpp, restated g2o optimizer)"
+                      if have_ref else "oracle/teb_oracle.c in g2o mode (numeric Jacobians, banded Cholesky)") +
+                     f", one band at a time per pinned host thread, {best_t} threads (of {tmax} visible), median of {reps} repetitions"
+                     + ("; port_value = the plain-C restatement on the same sample (identical results)" if have_ref else "")}
+    return cpu, sub, h
 
 
 def run_reference(a, rank, world):
@@ -261,8 +285,8 @@ def run_reference(a, rank, world):
             "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "restated CPU g2o path (oracle/teb_oracle.c), not the upstream g2o binary: g2o / CSparse / Eigen / "
-                    "Boost / ROS are absent from the image, the reference cannot be built here (DESIGN.md par. 3)"}
+            "note": "the reference's own planner sources over a restated g2o optimizer (oracle/_ref), not the upstream g2o "
+                    "binary: g2o / CSparse / Eigen / Boost / ROS are absent from the image (DESIGN.md par. 3)"}
     print(json.dumps(line), flush=True)
 
 
@@ -487,7 +511,7 @@ def run_b200(a, rank, local_rank, world):
         g.optimize(got, args)
         dmax = np.array([np.abs(got.poses[b_, :got.n[b_]] - ref.poses[b_, :ref.n[b_]]).max() if got.n[b_] == ref.n[b_]
                          else np.inf for b_ in range(sub.B)])
-        parity = {"against": "cpu_baseline run (oracle g2o mode = numeric Jacobians, what the reference executes)",
+        parity = {"against": "cpu_baseline run (the reference's code path: numeric Jacobians, delta 1e-9)",
                   "bands": int(sub.B), "tolerance": 1e-4,
                   "fraction_within_1e-4": float(np.mean(dmax <= 1e-4)), "fraction_within_1e-6": float(np.mean(dmax <= 1e-6)),
                   "median_abs_pose_diff": float(np.median(dmax)), "max_abs_pose_diff": float(dmax.max()),

@@ -40,6 +40,7 @@ struct tebgpu_ctx {
   ncclComm_t comm = nullptr;          /* cost all-gather across the ranks of a sharded batch (tebgpu_comm_init) */
   int world = 1, rank = 0;
   double* d_gather = nullptr;         /* [world][max_bands] gathered costs of the host-buffer entry point */
+  int ring = 0;        /* solver prefetch ring: 0 = by resident warps per SM, else 10 / 20 / 30 rows (TEBGPU_RING) */
   int eval_v1 = 0;     /* TEBGPU_EVAL_V1=1: first-generation trial evaluation (warp per trial, chunk per lane) */
   int ka_staged = 1;   /* kernel A output: 1 (default) shared-memory slot + TMA bulk store per lane, 0 direct 128-bit global stores */
   int last_spec_k = 0; /* round-0 width of the later LM iterations of the last optimize call */
@@ -310,7 +311,12 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_linearize<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<10>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<20>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<30>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpb_ring_bytes(20)));
+  CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpb_ring_bytes(30)));
+  if (const char* e = std::getenv("TEBGPU_RING")) { const int r = std::atoi(e); if (r == 10 || r == 20 || r == 30) c->ring = r; }
   CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -594,7 +600,17 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
             rs = ctx->side;
           }
-          prof_begin(ctx, st, round == 0 ? 6 : 4); k_solve_tpb<<<(bk + 31) / 32, 32, TPB_RING_BYTES, rs>>>(db, ctx->spec, it, round, g); ++launches; prof_end(ctx, st);
+          prof_begin(ctx, st, round == 0 ? 6 : 4);
+          {
+            /* ring depth by the number of solver warps an SM will hold (round 0: all bands; retry rounds: a few) */
+            const int warps = (bk + 31) / 32;
+            int ring = ctx->ring;
+            if (ring == 0) ring = (round > 0 || warps <= 2 * 148) ? 30 : (warps <= 3 * 148 + 74 ? 20 : 10);
+            if (ring == 30) k_solve_tpb<30><<<warps, 32, tpb_ring_bytes(30), rs>>>(db, ctx->spec, it, round, g);
+            else if (ring == 20) k_solve_tpb<20><<<warps, 32, tpb_ring_bytes(20), rs>>>(db, ctx->spec, it, round, g);
+            else k_solve_tpb<10><<<warps, 32, tpb_ring_bytes(10), rs>>>(db, ctx->spec, it, round, g);
+          }
+          ++launches; prof_end(ctx, st);
           prof_begin(ctx, st, round == 0 ? 7 : 4);
           launch_trial_eval(ctx, db, kp, B, K, smem_e, it, round, g, tag, rs);
           ++launches; prof_end(ctx, st);

@@ -57,8 +57,8 @@ __device__ __forceinline__ double band_lambda_init(const DevBatch& db, int b, in
  * the global latency is off the dependent chain. 10 slots (30 KB) instead of 11 let SEVEN solver warps share an SM
  * (7 x 31 KB <= 227 KB; 254 registers x 32 x 7 fits the register file), which is what makes 8192 bands x 4 trials a
  * single wave on 148 SMs. */
-constexpr int TPB_RING = 10;
-constexpr int TPB_RING_BYTES = TPB_RING * 6 * 32 * 16;
+constexpr int TPB_RING_MIN = 10;
+__host__ __device__ constexpr int tpb_ring_bytes(int ring) { return ring * 6 * 32 * 16; }
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
@@ -67,6 +67,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
+/* TPB_RING = prefetch distance in rows = slots of the private ring. The dependent chain of a thread advances one pivot
+ * per (memory latency / TPB_RING) when few warps are resident, so launches that leave shared memory unused (small
+ * batches, narrow speculation) take a deeper ring: 10 rows (30 KB per warp, 7 warps per SM), 20 (60 KB) or 30 (90 KB). */
+template <int TPB_RING>
 __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int iteration, int round, int g) {
   extern __shared__ __align__(16) unsigned char ring_raw[];
   const int lane = threadIdx.x;
