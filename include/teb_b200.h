@@ -256,6 +256,13 @@ int32_t tebgpu_set_linearize_variant(tebgpu_ctx* ctx, int32_t variant);
  * Results do not depend on it (the accept / reject chain is replayed in order), only latency and traffic do. */
 int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k);
 
+/* CUDA-graph replay of the launch sequence of tebgpu_optimize_batch(_device): 0 never, 1 always, 2 (default) in the
+ * latency regime only (a batch of at most ~2300 bands, e.g. one planning request of 32 candidates, where the 130-170
+ * kernel launches of one optimizeTEB are comparable to the kernels themselves). A sequence is captured once per distinct
+ * (batch description incl. buffer addresses, optimize arguments, parameters, switches, stream) and replayed afterwards;
+ * the context keeps the 8 most recently used graphs. Results are identical to direct launches. */
+int32_t tebgpu_set_graph(tebgpu_ctx* ctx, int32_t mode);
+
 /* Per-kernel device timing (CUDA events on the launching stream around every launch) for roofline reporting.
  * enable != 0 -> subsequent optimize calls record events. tebgpu_get_kernel_times synchronises, then returns for
  * kernel kind k (0 begin, 1 auto_resize, 2 build_graph, 3 linearize ["kernel A"], 4 lm_step [fused "kernel B" of

@@ -64,6 +64,8 @@ def load_library(build_if_missing=False):
     L.tebgpu_gather_costs.argtypes = [vp, vp, C.c_int32, vp, C.c_int32]
     L.tebgpu_optimize_batch_gather.restype = C.c_int32
     L.tebgpu_optimize_batch_gather.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs), vp]
+    L.tebgpu_set_graph.restype = C.c_int32
+    L.tebgpu_set_graph.argtypes = [vp, C.c_int32]
     L.tebgpu_get_info.restype = C.c_int64
     L.tebgpu_get_info.argtypes = [vp, C.c_int32]
     L.tebgpu_set_profiling.restype = C.c_int32
@@ -134,6 +136,10 @@ class TebGpu:
 
     def set_speculation(self, k):
         self._check(self.lib.tebgpu_set_speculation(self.ctx, int(k)), "tebgpu_set_speculation")
+
+    def set_graph(self, mode):
+        """CUDA-graph replay of the launch sequence: 0 never, 1 always, 2 automatic (latency regime)"""
+        self._check(self.lib.tebgpu_set_graph(self.ctx, int(mode)), "tebgpu_set_graph")
 
     def set_solver(self, solver):
         self._check(self.lib.tebgpu_set_solver(self.ctx, int(solver)), "tebgpu_set_solver")

@@ -40,7 +40,12 @@ struct tebgpu_ctx {
   ncclComm_t comm = nullptr;          /* cost all-gather across the ranks of a sharded batch (tebgpu_comm_init) */
   int world = 1, rank = 0;
   double* d_gather = nullptr;         /* [world][max_bands] gathered costs of the host-buffer entry point */
-  int ring = 0;        /* solver prefetch ring: 0 = by resident warps per SM, else 10 / 20 / 30 rows (TEBGPU_RING) */
+  struct GraphEntry { uint64_t key = 0; cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t stamp = 0; int spec_k = 0, spec_first = 0; };
+  std::vector<GraphEntry> graphs;     /* captured launch sequences (tebgpu_set_graph) */
+  uint64_t graph_clock = 0;
+  uint64_t params_version = 0;        /* bumped by tebgpu_set_params: part of the graph key */
+  int graph_mode = 2;                 /* 0 never, 1 always, 2 automatic (latency regime only) */
+  int ring = 0;        /* solver prefetch ring: 0 = 10 rows (default), else 10 / 20 / 30 rows (TEBGPU_RING, experiments) */
   int eval_v1 = 0;     /* TEBGPU_EVAL_V1=1: first-generation trial evaluation (warp per trial, chunk per lane) */
   int ka_staged = 1;   /* kernel A output: 1 (default) shared-memory slot + TMA bulk store per lane, 0 direct 128-bit global stores */
   int last_spec_k = 0; /* round-0 width of the later LM iterations of the last optimize call */
@@ -171,8 +176,8 @@ int64_t tebgpu_get_info(const tebgpu_ctx* ctx, int32_t which) {
     case 2: return ctx->solver;
     case 3: return ctx->world;
     case 4: return ctx->rank;
-    case 5: return 0;
-    case 6: return 0;
+    case 5: return ctx->graph_mode;
+    case 6: return (int64_t)ctx->graphs.size();
     case 7: return ctx->last_spec_first;
     default: return -1;
   }
@@ -316,6 +321,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<30>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpb_ring_bytes(20)));
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpb_ring_bytes(30)));
+  if (const char* e = std::getenv("TEBGPU_GRAPH")) { const int m = std::atoi(e); if (m >= 0 && m <= 2) c->graph_mode = m; }
   if (const char* e = std::getenv("TEBGPU_RING")) { const int r = std::atoi(e); if (r == 10 || r == 20 || r == 30) c->ring = r; }
   CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -335,6 +341,8 @@ int32_t tebgpu_destroy(tebgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
   if (ctx->comm) { nccl_api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  for (auto& e : ctx->graphs) cudaGraphExecDestroy(e.exec);
+  ctx->graphs.clear();
   free_all(ctx);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -367,6 +375,7 @@ int32_t tebgpu_set_params(tebgpu_ctx* ctx, const TebParams* p) {
   CUDA_TRY(ctx, cudaMemcpy(ctx->d_fp, fp, sizeof(fp), cudaMemcpyHostToDevice));
   ctx->params = *p;
   ctx->have_params = true;
+  ++ctx->params_version;
   return TEBGPU_OK;
 }
 
@@ -490,12 +499,8 @@ static DevBatch make_devbatch(tebgpu_ctx* ctx, const TebBatch* bt) {
   return d;
 }
 
-int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimizeArgs* args, void* cuda_stream) {
-  int32_t rc = check_batch(ctx, bt);
-  if (rc) return rc;
-  if (!args || args->iterations_innerloop < 0 || args->iterations_outerloop < 0) { ctx->err = "bad optimize args"; return TEBGPU_ERR_INVALID_ARG; }
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+/* the launch sequence of one optimizeTEB over the batch, issued on `st` (directly, or into a stream capture) */
+static int32_t issue_optimize(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimizeArgs* args, cudaStream_t st) {
   DevBatch db = make_devbatch(ctx, bt);
   const TebParams& p = ctx->params;
   const int B = bt->B;
@@ -602,10 +607,11 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
           }
           prof_begin(ctx, st, round == 0 ? 6 : 4);
           {
-            /* ring depth by the number of solver warps an SM will hold (round 0: all bands; retry rounds: a few) */
+            /* ring depth: 10 rows unless TEBGPU_RING asks for 20 / 30. Measured (profiles/r2_history.md): deeper rings do
+             * not shorten the chain - a lone solver warp is bound by its own fp64 issue rate (~75 DFMA per pivot at 2
+             * cycles each), not by the prefetch distance - and they cost residency (20 rows: 3 warps per SM). */
             const int warps = (bk + 31) / 32;
-            int ring = ctx->ring;
-            if (ring == 0) ring = (round > 0 || warps <= 2 * 148) ? 30 : (warps <= 3 * 148 + 74 ? 20 : 10);
+            const int ring = ctx->ring == 0 ? 10 : ctx->ring;
             if (ring == 30) k_solve_tpb<30><<<warps, 32, tpb_ring_bytes(30), rs>>>(db, ctx->spec, it, round, g);
             else if (ring == 20) k_solve_tpb<20><<<warps, 32, tpb_ring_bytes(20), rs>>>(db, ctx->spec, it, round, g);
             else k_solve_tpb<10><<<warps, 32, tpb_ring_bytes(10), rs>>>(db, ctx->spec, it, round, g);
@@ -655,6 +661,81 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   ctx->launches = launches;
   if (ctx->profiling && ctx->ev_used > 4096) { cudaStreamSynchronize(st); prof_collect(ctx); }
   CUDA_TRY(ctx, cudaGetLastError());
+  return TEBGPU_OK;
+}
+
+/* CUDA-graph replay of the launch sequence. The sequence is a pure function of the batch description (dimensions and
+ * buffer addresses), the optimize arguments, the parameter block and the context switches, so it is captured once per
+ * distinct key (fork / join of the retry side stream included) and replayed afterwards: one graph launch instead of
+ * ~130-170 kernel launches. That only matters in the latency regime (a single planning request: kernels of 10-50 us), so
+ * graphs are used there by default (tebgpu_set_graph: 0 never, 1 always, 2 automatic). */
+static uint64_t graph_key(const tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimizeArgs* a, cudaStream_t st) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t nbytes) {
+    const unsigned char* c = static_cast<const unsigned char*>(p);
+    for (size_t k = 0; k < nbytes; ++k) { h ^= c[k]; h *= 1099511628211ull; }
+  };
+  mix(bt, sizeof(*bt));
+  mix(a, sizeof(*a));
+  mix(&ctx->params_version, sizeof(ctx->params_version));
+  const int sw[8] = {ctx->solver, ctx->spec_k, ctx->linearize_variant, ctx->ka_staged, ctx->eval_v1, ctx->ring, ctx->overlap, ctx->eval_minb};
+  mix(sw, sizeof(sw));
+  mix(&st, sizeof(st));
+  return h;
+}
+
+int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const TebOptimizeArgs* args, void* cuda_stream) {
+  int32_t rc = check_batch(ctx, bt);
+  if (rc) return rc;
+  if (!args || args->iterations_innerloop < 0 || args->iterations_outerloop < 0) { ctx->err = "bad optimize args"; return TEBGPU_ERR_INVALID_ARG; }
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  const bool latency_regime = (long long)bt->B * 8 <= 148LL * 4 * 32;
+  const bool use_graph = !ctx->profiling && (ctx->graph_mode == 1 || (ctx->graph_mode == 2 && latency_regime));
+  if (!use_graph) return issue_optimize(ctx, bt, args, st);
+  const uint64_t key = graph_key(ctx, bt, args, st);
+  for (auto& e : ctx->graphs)
+    if (e.key == key) {
+      e.stamp = ++ctx->graph_clock;
+      ctx->launches = e.launches;
+      ctx->last_spec_k = e.spec_k; ctx->last_spec_first = e.spec_first;
+      CUDA_TRY(ctx, cudaGraphLaunch(e.exec, st));
+      return TEBGPU_OK;
+    }
+  CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  rc = issue_optimize(ctx, bt, args, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != TEBGPU_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc == TEBGPU_OK) { /* capture itself failed: run the sequence directly */
+      ctx->graph_mode = 0;
+      return issue_optimize(ctx, bt, args, st);
+    }
+    return rc;
+  }
+  tebgpu_ctx::GraphEntry ent;
+  ent.key = key; ent.launches = ctx->launches; ent.stamp = ++ctx->graph_clock;
+  ent.spec_k = ctx->last_spec_k; ent.spec_first = ctx->last_spec_first;
+  const cudaError_t ie = cudaGraphInstantiate(&ent.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { cudaGetLastError(); ctx->graph_mode = 0; return issue_optimize(ctx, bt, args, st); }
+  if (ctx->graphs.size() >= 8) { /* drop the least recently used graph */
+    size_t old = 0;
+    for (size_t k = 1; k < ctx->graphs.size(); ++k)
+      if (ctx->graphs[k].stamp < ctx->graphs[old].stamp) old = k;
+    cudaGraphExecDestroy(ctx->graphs[old].exec);
+    ctx->graphs.erase(ctx->graphs.begin() + old);
+  }
+  ctx->graphs.push_back(ent);
+  CUDA_TRY(ctx, cudaGraphLaunch(ent.exec, st));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_set_graph(tebgpu_ctx* ctx, int32_t mode) {
+  if (!ctx || mode < 0 || mode > 2) return TEBGPU_ERR_INVALID_ARG;
+  ctx->graph_mode = mode;
   return TEBGPU_OK;
 }
 

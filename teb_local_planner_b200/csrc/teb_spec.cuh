@@ -67,9 +67,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
-/* TPB_RING = prefetch distance in rows = slots of the private ring. The dependent chain of a thread advances one pivot
- * per (memory latency / TPB_RING) when few warps are resident, so launches that leave shared memory unused (small
- * batches, narrow speculation) take a deeper ring: 10 rows (30 KB per warp, 7 warps per SM), 20 (60 KB) or 30 (90 KB). */
+/* TPB_RING = prefetch distance in rows = slots of the private ring: 10 rows (30 KB per warp, 7 warps per SM) is the
+ * default; 20 / 30 exist for experiments (TEBGPU_RING) and measured slower - see profiles/r2_history.md. */
 template <int TPB_RING>
 __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int iteration, int round, int g) {
   extern __shared__ __align__(16) unsigned char ring_raw[];

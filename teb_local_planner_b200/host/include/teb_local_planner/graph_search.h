@@ -46,6 +46,18 @@ class GraphSearchInterface {
                   const geometry_msgs::Twist* start_velocity, bool free_goal_vel);
   void flushPaths(double start_orientation, double goal_orientation, const geometry_msgs::Twist* start_velocity, bool free_goal_vel);
   bool classesFull() const;
+  /* what both graph builders share:
+   *   beginSearch     resets the search state; true when nothing is left to explore (class budget spent, or start and goal
+   *                   closer than xy_goal_tolerance: then at most one straight band is created to fix the orientation)
+   *   connectForward  directed edge u -> v for every ordered pair (the goal, the last vertex, has no out edges) whose
+   *                   direction agrees with `travel_dir` by more than `heading_threshold`, that `veto` does not reject and
+   *                   whose segment keeps `clearance` from every obstacle
+   *   enumerate       depth-first enumeration of all start -> goal paths + hand-over of the last partial chunk */
+  bool beginSearch(const PoseSE2& start, const PoseSE2& goal, const geometry_msgs::Twist* start_velocity, bool free_goal_vel);
+  template <typename Veto>
+  void connectForward(const Eigen::Vector2d& travel_dir, double heading_threshold, double clearance, Veto veto);
+  void enumerate(int start_vertex, int goal_vertex, const PoseSE2& start, const PoseSE2& goal,
+                 const geometry_msgs::Twist* start_velocity, bool free_goal_vel);
   const TebConfig* cfg_;
   HomotopyClassPlanner* hcp_;
   std::vector<std::vector<Eigen::Vector2d>> pending_;

@@ -47,121 +47,114 @@ void GraphSearchInterface::DepthFirst(std::vector<int>& visited, int goal, doubl
   }
 }
 
-/* :92-216 */
+bool GraphSearchInterface::beginSearch(const PoseSE2& start, const PoseSE2& goal, const geometry_msgs::Twist* start_velocity,
+                                       bool free_goal_vel) {
+  clearGraph();
+  pending_.clear();
+  stop_ = false;
+  if (classesFull()) return true;
+  if ((goal.position() - start.position()).norm() < cfg_->goal_tolerance.xy_goal_tolerance) {
+    if (hcp_->getTrajectoryContainer().empty()) hcp_->addAndInitNewTeb(start, goal, start_velocity, free_goal_vel);
+    return true;
+  }
+  return false;
+}
+
+template <typename Veto>
+void GraphSearchInterface::connectForward(const Eigen::Vector2d& travel_dir, double heading_threshold, double clearance, Veto veto) {
+  const ObstContainer* obstacles = hcp_->obstacles();
+  const int vertices = (int)graph_.pos.size();
+  for (int u = 0; u + 1 < vertices; ++u) {
+    for (int v = 0; v < vertices; ++v) {
+      if (u == v) continue;
+      const Eigen::Vector2d dir = (graph_.pos[v] - graph_.pos[u]).normalized();
+      if (dir.dot(travel_dir) <= heading_threshold) continue; /* backwards, or too far sideways */
+      if (veto(u, v)) continue;
+      bool blocked = false;
+      if (obstacles)
+        for (const ObstaclePtr& ob : *obstacles)
+          if (ob->checkLineIntersection(graph_.pos[u], graph_.pos[v], clearance)) { blocked = true; break; }
+      if (!blocked) graph_.addEdge(u, v);
+    }
+  }
+}
+
+void GraphSearchInterface::enumerate(int start_vertex, int goal_vertex, const PoseSE2& start, const PoseSE2& goal,
+                                     const geometry_msgs::Twist* start_velocity, bool free_goal_vel) {
+  std::vector<int> visited(1, start_vertex);
+  DepthFirst(visited, goal_vertex, start.theta(), goal.theta(), start_velocity, free_goal_vel);
+  flushPaths(start.theta(), goal.theta(), start_velocity, free_goal_vel);
+}
+
+/* Key-point graph (reference :92-216): two vertices per obstacle in front of the start, dist_to_obst to the left and to
+ * the right of its centroid (relative to the start -> goal line), then forward edges that clear the obstacles by half
+ * that distance. With a heading threshold, the two key points of the obstacle nearest to the start are only reachable
+ * from the start if they also lie ahead of the robot's current heading. */
 void lrKeyPointGraph::createGraph(const PoseSE2& start, const PoseSE2& goal, double dist_to_obst, double obstacle_heading_threshold,
                                   const geometry_msgs::Twist* start_velocity, bool free_goal_vel) {
-  clearGraph();
-  pending_.clear();
-  stop_ = false;
-  if (classesFull()) return;
-  Eigen::Vector2d diff = goal.position() - start.position();
-  if (diff.norm() < cfg_->goal_tolerance.xy_goal_tolerance) {
-    /* goal reached up to the tolerance: one short straight band to correct the orientation */
-    if (hcp_->getTrajectoryContainer().empty()) hcp_->addAndInitNewTeb(start, goal, start_velocity, free_goal_vel);
-    return;
-  }
-  Eigen::Vector2d normal(-diff[1], diff[0]);
-  normal.normalize();
-  normal = normal * dist_to_obst;
-  const int start_vtx = graph_.addVertex(start.position());
-  diff.normalize();
-  int nearest_u = -1, nearest_v = -1;
-  double min_dist = DBL_MAX;
-  const ObstContainer* obstacles = hcp_->obstacles();
-  if (obstacles) {
+  if (beginSearch(start, goal, start_velocity, free_goal_vel)) return;
+  const Eigen::Vector2d line = goal.position() - start.position();
+  const Eigen::Vector2d travel_dir = line.normalized();
+  const Eigen::Vector2d side = Eigen::Vector2d(-line[1], line[0]).normalized() * dist_to_obst;
+  const int start_vertex = graph_.addVertex(start.position());
+  int near_left = -1, near_right = -1;
+  double near_dist = DBL_MAX;
+  if (const ObstContainer* obstacles = hcp_->obstacles()) {
     for (const ObstaclePtr& ob : *obstacles) {
-      const Eigen::Vector2d start2obst = ob->getCentroid() - start.position();
-      const double dist = start2obst.norm();
-      if (start2obst.dot(diff) / dist < 0.1) continue; /* not in front of the start */
-      const int u = graph_.addVertex(ob->getCentroid() + normal);
-      const int v = graph_.addVertex(ob->getCentroid() - normal);
-      if (obstacle_heading_threshold && dist < min_dist) { min_dist = dist; nearest_u = u; nearest_v = v; }
+      const Eigen::Vector2d to_obst = ob->getCentroid() - start.position();
+      const double range = to_obst.norm();
+      if (to_obst.dot(travel_dir) / range < 0.1) continue; /* beside or behind the start: no key points */
+      const int left = graph_.addVertex(ob->getCentroid() + side);
+      const int right = graph_.addVertex(ob->getCentroid() - side);
+      if (obstacle_heading_threshold && range < near_dist) { near_dist = range; near_left = left; near_right = right; }
     }
   }
-  const int goal_vtx = graph_.addVertex(goal.position());
-  const int nv = (int)graph_.pos.size();
-  for (int i = 0; i < nv - 1; ++i) { /* the goal has no out edges */
-    for (int j = 0; j < nv; ++j) {
-      if (i == j) continue;
-      Eigen::Vector2d distij = graph_.pos[j] - graph_.pos[i];
-      distij.normalize();
-      if (distij.dot(diff) <= obstacle_heading_threshold) continue; /* backwards / too far sideways */
-      if (obstacle_heading_threshold && i == start_vtx && min_dist != DBL_MAX && (j == nearest_u || j == nearest_v)) {
-        Eigen::Vector2d keypoint_dist = graph_.pos[j] - start.position();
-        keypoint_dist.normalize();
-        const Eigen::Vector2d start_orient_vec(std::cos(start.theta()), std::sin(start.theta()));
-        if (start_orient_vec.dot(keypoint_dist) <= obstacle_heading_threshold) continue;
-      }
-      bool collision = false;
-      if (obstacles)
-        for (const ObstaclePtr& ob : *obstacles)
-          if (ob->checkLineIntersection(graph_.pos[i], graph_.pos[j], 0.5 * dist_to_obst)) { collision = true; break; }
-      if (collision) continue;
-      graph_.addEdge(i, j);
-    }
-  }
-  std::vector<int> visited(1, start_vtx);
-  DepthFirst(visited, goal_vtx, start.theta(), goal.theta(), start_velocity, free_goal_vel);
-  flushPaths(start.theta(), goal.theta(), start_velocity, free_goal_vel);
+  const int goal_vertex = graph_.addVertex(goal.position());
+  const Eigen::Vector2d heading(std::cos(start.theta()), std::sin(start.theta()));
+  const bool guard_nearest = obstacle_heading_threshold && near_dist != DBL_MAX;
+  connectForward(travel_dir, obstacle_heading_threshold, 0.5 * dist_to_obst, [&](int u, int v) {
+    if (!guard_nearest || u != start_vertex || (v != near_left && v != near_right)) return false;
+    const Eigen::Vector2d to_key = (graph_.pos[v] - start.position()).normalized();
+    return heading.dot(to_key) <= obstacle_heading_threshold;
+  });
+  enumerate(start_vertex, goal_vertex, start, goal, start_velocity, free_goal_vel);
 }
 
+/* boost::random::mt19937 (default seed) + uniform_real_distribution<double>: one 32-bit draw per sample, scaled to
+ * [lo, hi), redrawn in the (rounding) case that it reaches hi */
 double ProbRoadmapGraph::uniform(double lo, double hi) {
-  for (;;) {
-    const double r = (double)rnd_generator_() / 4294967296.0 * (hi - lo) + lo;
-    if (r < hi) return r;
-  }
+  double r;
+  do {
+    r = (double)rnd_generator_() / 4294967296.0 * (hi - lo) + lo;
+  } while (!(r < hi));
+  return r;
 }
 
-/* :220-342 */
+/* Probabilistic roadmap (reference :220-342): roadmap_graph_no_samples vertices drawn uniformly in a rectangle of width
+ * roadmap_graph_area_width around the start -> goal line (its length scaled by roadmap_graph_area_length_scale about the
+ * midpoint), then forward edges that clear the obstacles by dist_to_obst. */
 void ProbRoadmapGraph::createGraph(const PoseSE2& start, const PoseSE2& goal, double dist_to_obst, double obstacle_heading_threshold,
                                    const geometry_msgs::Twist* start_velocity, bool free_goal_vel) {
-  clearGraph();
-  pending_.clear();
-  stop_ = false;
-  if (classesFull()) return;
-  Eigen::Vector2d diff = goal.position() - start.position();
-  const double start_goal_dist = diff.norm();
-  if (start_goal_dist < cfg_->goal_tolerance.xy_goal_tolerance) {
-    if (hcp_->getTrajectoryContainer().empty()) hcp_->addAndInitNewTeb(start, goal, start_velocity, free_goal_vel);
-    return;
+  if (beginSearch(start, goal, start_velocity, free_goal_vel)) return;
+  const Eigen::Vector2d line = goal.position() - start.position();
+  const double span = line.norm();
+  const Eigen::Vector2d travel_dir = line.normalized();
+  const Eigen::Vector2d across = Eigen::Vector2d(-line[1], line[0]).normalized();
+  const double width = cfg_->hcp.roadmap_graph_area_width, stretch = cfg_->hcp.roadmap_graph_area_length_scale;
+  const double length = span * stretch;
+  const double angle = std::atan2(line[1], line[0]);
+  const double ca = std::cos(angle), sa = std::sin(angle);
+  Eigen::Vector2d corner = start.position() - 0.5 * width * across; /* rectangle corner: sample (0, 0) */
+  if (stretch != 1.0) corner = start.position() + 0.5 * (1.0 - stretch) * span * travel_dir - 0.5 * width * across;
+  const int start_vertex = graph_.addVertex(start.position());
+  for (int k = 0; k < cfg_->hcp.roadmap_graph_no_samples; ++k) {
+    const double along = uniform(0, length);
+    const double aside = uniform(0, width);
+    graph_.addVertex(corner + Eigen::Vector2d(ca * along - sa * aside, sa * along + ca * aside));
   }
-  Eigen::Vector2d normal(-diff[1], diff[0]);
-  normal.normalize();
-  const double area_width = cfg_->hcp.roadmap_graph_area_width;
-  const double len_scale = cfg_->hcp.roadmap_graph_area_length_scale;
-  const double x_hi = start_goal_dist * len_scale;
-  const double phi = std::atan2(diff[1], diff[0]);
-  const double cphi = std::cos(phi), sphi = std::sin(phi);
-  Eigen::Vector2d area_origin;
-  if (len_scale != 1.0) area_origin = start.position() + 0.5 * (1.0 - len_scale) * start_goal_dist * diff.normalized() - 0.5 * area_width * normal;
-  else area_origin = start.position() - 0.5 * area_width * normal;
-  const int start_vtx = graph_.addVertex(start.position());
-  diff.normalize();
-  for (int i = 0; i < cfg_->hcp.roadmap_graph_no_samples; ++i) {
-    const double sx = uniform(0, x_hi);
-    const double sy = uniform(0, area_width);
-    graph_.addVertex(area_origin + Eigen::Vector2d(cphi * sx - sphi * sy, sphi * sx + cphi * sy));
-  }
-  const int goal_vtx = graph_.addVertex(goal.position());
-  const int nv = (int)graph_.pos.size();
-  const ObstContainer* obstacles = hcp_->obstacles();
-  for (int i = 0; i < nv - 1; ++i) {
-    for (int j = 0; j < nv; ++j) {
-      if (i == j) continue;
-      Eigen::Vector2d distij = graph_.pos[j] - graph_.pos[i];
-      distij.normalize();
-      if (distij.dot(diff) <= obstacle_heading_threshold) continue;
-      bool collision = false;
-      if (obstacles)
-        for (const ObstaclePtr& ob : *obstacles)
-          if (ob->checkLineIntersection(graph_.pos[i], graph_.pos[j], dist_to_obst)) { collision = true; break; }
-      if (collision) continue;
-      graph_.addEdge(i, j);
-    }
-  }
-  std::vector<int> visited(1, start_vtx);
-  DepthFirst(visited, goal_vtx, start.theta(), goal.theta(), start_velocity, free_goal_vel);
-  flushPaths(start.theta(), goal.theta(), start_velocity, free_goal_vel);
+  const int goal_vertex = graph_.addVertex(goal.position());
+  connectForward(travel_dir, obstacle_heading_threshold, dist_to_obst, [](int, int) { return false; });
+  enumerate(start_vertex, goal_vertex, start, goal, start_velocity, free_goal_vel);
 }
 
 }  // namespace teb_local_planner

@@ -312,62 +312,53 @@ void HomotopyClassPlanner::optimizeAllTEBs(int iter_innerloop, int iter_outerloo
                    cfg_->hcp.selection_viapoint_cost_scale, cfg_->hcp.selection_alternative_time_cost, gpu_);
 }
 
-/* :495-537: the stored pointer if that band still exists, else the band whose class equals the initial plan's */
+namespace {
+/* position of a band in the container, -1 when it is not (or no longer) part of it */
+int index_of(const TebOptPlannerContainer& bands, const TebOptimalPlannerPtr& band) {
+  if (!band) return -1;
+  for (size_t k = 0; k < bands.size(); ++k)
+    if (bands[k] == band) return (int)k;
+  return -1;
+}
+}  // namespace
+
+/* The candidate that follows the initial plan (reference :495-537): the band created from it in this cycle if it
+ * survived the filtering, otherwise the first band whose equivalence class is the plan's class. */
 TebOptimalPlannerPtr HomotopyClassPlanner::getInitialPlanTEB() {
-  if (initial_plan_teb_) {
-    if (std::find(tebs_.begin(), tebs_.end(), initial_plan_teb_) != tebs_.end()) return initial_plan_teb_;
-    initial_plan_teb_.reset();
-  }
-  if (!initial_plan_eq_class_ || equivalence_classes_.size() != tebs_.size()) return TebOptimalPlannerPtr();
-  auto teb_it = tebs_.begin();
-  for (auto it = equivalence_classes_.begin(); it != equivalence_classes_.end(); ++it, ++teb_it)
-    if (it->first->isEqual(*initial_plan_eq_class_)) return *teb_it;
+  if (index_of(tebs_, initial_plan_teb_) >= 0) return initial_plan_teb_;
+  initial_plan_teb_.reset();
+  const bool comparable = initial_plan_eq_class_ && equivalence_classes_.size() == tebs_.size();
+  if (!comparable) return TebOptimalPlannerPtr();
+  for (size_t k = 0; k < tebs_.size(); ++k)
+    if (equivalence_classes_[k].first->isEqual(*initial_plan_eq_class_)) return tebs_[k];
   return TebOptimalPlannerPtr();
 }
 
-/* :564-667 */
+/* Best candidate of the cycle (reference :564-667). The comparison itself is the boundary function tebgpu_select_best on
+ * the candidates' costs: the previous winner competes with cost x selection_cost_hysteresis, the initial-plan candidate
+ * with cost x selection_prefer_initial_plan, strict '<', first minimum wins. A change of winner is only honoured once
+ * switching_blocking_period seconds have passed since the last change. */
 TebOptimalPlannerPtr HomotopyClassPlanner::selectBestTeb() {
-  double min_cost = std::numeric_limits<double>::max();
-  double min_cost_last_best = std::numeric_limits<double>::max();
-  double min_cost_initial_plan_teb = std::numeric_limits<double>::max();
-  TebOptimalPlannerPtr initial_plan_teb = getInitialPlanTEB();
-  if (best_teb_ && std::find(tebs_.begin(), tebs_.end(), best_teb_) != tebs_.end()) {
-    min_cost_last_best = best_teb_->getCurrentCost() * cfg_->hcp.selection_cost_hysteresis;
-    last_best_teb_ = best_teb_;
-  } else {
-    last_best_teb_.reset();
-  }
-  if (initial_plan_teb) min_cost_initial_plan_teb = initial_plan_teb->getCurrentCost() * cfg_->hcp.selection_prefer_initial_plan;
-  best_teb_.reset();
-  for (auto it_teb = tebs_.begin(); it_teb != tebs_.end(); ++it_teb) {
-    double teb_cost;
-    if (*it_teb == last_best_teb_) teb_cost = min_cost_last_best;
-    else if (*it_teb == initial_plan_teb) teb_cost = min_cost_initial_plan_teb;
-    else teb_cost = it_teb->get()->getCurrentCost();
-    if (teb_cost < min_cost) {
-      best_teb_ = *it_teb;
-      min_cost = teb_cost;
-    }
-  }
+  const int previous = index_of(tebs_, best_teb_);
+  last_best_teb_ = previous >= 0 ? best_teb_ : TebOptimalPlannerPtr();
+  const int from_plan = index_of(tebs_, getInitialPlanTEB());
+  std::vector<double> cost(tebs_.size());
+  for (size_t k = 0; k < tebs_.size(); ++k) cost[k] = tebs_[k]->getCurrentCost();
+  const int winner = tebgpu_select_best(cost.data(), (int32_t)cost.size(), previous, from_plan, cfg_->hcp.selection_cost_hysteresis,
+                                        cfg_->hcp.selection_prefer_initial_plan);
+  best_teb_ = winner >= 0 ? tebs_[winner] : TebOptimalPlannerPtr();
   if (last_best_teb_ && best_teb_ != last_best_teb_) {
-    auto now = std::chrono::steady_clock::now();
-    if (std::chrono::duration<double>(now - last_eq_class_switching_time_).count() > cfg_->hcp.switching_blocking_period) {
-      last_eq_class_switching_time_ = now;
-    } else {
-      best_teb_ = last_best_teb_;
-    }
+    const auto now = std::chrono::steady_clock::now();
+    const double since_last_switch = std::chrono::duration<double>(now - last_eq_class_switching_time_).count();
+    if (since_last_switch > cfg_->hcp.switching_blocking_period) last_eq_class_switching_time_ = now;
+    else best_teb_ = last_best_teb_; /* still blocked: keep the previous winner */
   }
   return best_teb_;
 }
 
-/* :669-683 */
+/* index of the current winner; a single candidate always wins (reference :669-683) */
 int HomotopyClassPlanner::bestTebIdx() const {
-  if (tebs_.size() == 1) return 0;
-  if (!best_teb_) return -1;
-  int idx = 0;
-  for (auto it_teb = tebs_.begin(); it_teb != tebs_.end(); ++it_teb, ++idx)
-    if (*it_teb == best_teb_) return idx;
-  return -1;
+  return tebs_.size() == 1 ? 0 : index_of(tebs_, best_teb_);
 }
 
 TebOptPlannerContainer::iterator HomotopyClassPlanner::removeTeb(TebOptimalPlannerPtr& teb) {
@@ -396,31 +387,31 @@ void HomotopyClassPlanner::setPreferredTurningDir(RotType dir) {
   for (auto& teb : tebs_) teb->setPreferredTurningDir(dir);
 }
 
-/* :709-714 */
+/* the stored winner while it is still a candidate, otherwise a fresh selection (reference :709-714) */
 TebOptimalPlannerPtr HomotopyClassPlanner::findBestTeb() {
   if (tebs_.empty()) return TebOptimalPlannerPtr();
-  if (!best_teb_ || std::find(tebs_.begin(), tebs_.end(), best_teb_) == tebs_.end()) best_teb_ = selectBestTeb();
+  if (index_of(tebs_, best_teb_) < 0) best_teb_ = selectBestTeb();
   return best_teb_;
 }
 
-/* :686-707 */
+/* Feasibility of the plan that will be executed (reference :686-707): the winner is checked against the costmap; an
+ * infeasible winner is discarded and the next best candidate takes its place - unless the discarded one was already the
+ * previous cycle's winner: then the call fails instead of letting the robot flip between plans. */
 bool HomotopyClassPlanner::isTrajectoryFeasible(base_local_planner::CostmapModel* costmap_model,
                                                 const std::vector<geometry_msgs::Point>& footprint_spec, double inscribed_radius,
                                                 double circumscribed_radius, int look_ahead_idx,
                                                 double feasibility_check_lookahead_distance) {
-  bool feasible = false;
-  while (!feasible && !tebs_.empty()) {
-    TebOptimalPlannerPtr best = findBestTeb();
-    if (!best) return false;
-    feasible = best->isTrajectoryFeasible(costmap_model, footprint_spec, inscribed_radius, circumscribed_radius, look_ahead_idx,
-                                          feasibility_check_lookahead_distance);
-    if (!feasible) {
-      const bool same_as_before = last_best_teb_ && last_best_teb_ == best;
-      removeTeb(best);
-      if (same_as_before) return feasible; /* not failing here could make the robot oscillate between plans */
-    }
+  while (!tebs_.empty()) {
+    TebOptimalPlannerPtr candidate = findBestTeb();
+    if (!candidate) return false;
+    if (candidate->isTrajectoryFeasible(costmap_model, footprint_spec, inscribed_radius, circumscribed_radius, look_ahead_idx,
+                                        feasibility_check_lookahead_distance))
+      return true;
+    const bool was_previous_winner = last_best_teb_ && last_best_teb_ == candidate;
+    removeTeb(candidate);
+    if (was_previous_winner) return false;
   }
-  return feasible;
+  return false;
 }
 
 bool HomotopyClassPlanner::hasDiverged() const {

@@ -325,65 +325,59 @@ bool TebOptimalPlanner::hasDiverged() const {
   return chi2_ > cfg_->recovery.divergence_detection_max_chi_squared;
 }
 
-/* :1097-1134 */
+/* Mean velocity that carries the robot from pose1 to pose2 in dt (reference :1097-1134). Non-holonomic robots
+ * (max_vel_y == 0) move along their heading: the speed is the segment length, signed by whether the displacement points
+ * forwards or backwards; holonomic robots get the displacement expressed in the frame of pose1. dt == 0 yields zero. */
 inline void TebOptimalPlanner::extractVelocity(const PoseSE2& pose1, const PoseSE2& pose2, double dt, double& vx, double& vy,
                                                double& omega) const {
-  if (dt == 0) { vx = 0; vy = 0; omega = 0; return; }
-  Eigen::Vector2d deltaS = pose2.position() - pose1.position();
+  vx = vy = omega = 0;
+  if (dt == 0) return;
+  const Eigen::Vector2d step = pose2.position() - pose1.position();
+  const double c = std::cos(pose1.theta()), s = std::sin(pose1.theta());
+  const double along = c * step.x() + s * step.y(), across = -s * step.x() + c * step.y();
   if (cfg_->robot.max_vel_y == 0) {
-    Eigen::Vector2d conf1dir(std::cos(pose1.theta()), std::sin(pose1.theta()));
-    double dir = deltaS.dot(conf1dir);
-    vx = (double)g2o::sign(dir) * deltaS.norm() / dt;
-    vy = 0;
+    vx = (double)g2o::sign(along) * step.norm() / dt;
   } else {
-    double cos_theta1 = std::cos(pose1.theta());
-    double sin_theta1 = std::sin(pose1.theta());
-    double p1_dx = cos_theta1 * deltaS.x() + sin_theta1 * deltaS.y();
-    double p1_dy = -sin_theta1 * deltaS.x() + cos_theta1 * deltaS.y();
-    vx = p1_dx / dt;
-    vy = p1_dy / dt;
+    vx = along / dt;
+    vy = across / dt;
   }
-  double orientdiff = g2o::normalize_theta(pose2.theta() - pose1.theta());
-  omega = orientdiff / dt;
+  omega = g2o::normalize_theta(pose2.theta() - pose1.theta()) / dt;
 }
 
-/* :1136-1172 */
+/* Velocity command for the controller (reference :1136-1172): the mean velocity from the first pose to the pose
+ * `look_ahead_poses` ahead - clamped so that it stays prevent_look_ahead_poses_near_goal poses away from the goal, and cut
+ * short as soon as the accumulated time reaches dt_ref x look_ahead_poses. */
 bool TebOptimalPlanner::getVelocityCommand(double& vx, double& vy, double& omega, int look_ahead_poses) const {
-  if (teb_.sizePoses() < 2) { vx = 0; vy = 0; omega = 0; return false; }
-  look_ahead_poses = std::max(1, std::min(look_ahead_poses, teb_.sizePoses() - 1 - cfg_->trajectory.prevent_look_ahead_poses_near_goal));
-  double dt = 0.0;
-  for (int counter = 0; counter < look_ahead_poses; ++counter) {
-    dt += teb_.TimeDiff(counter);
-    if (dt >= cfg_->trajectory.dt_ref * look_ahead_poses) {
-      look_ahead_poses = counter + 1;
-      break;
-    }
+  vx = vy = omega = 0;
+  const int poses = teb_.sizePoses();
+  if (poses < 2) return false;
+  int target = std::max(1, std::min(look_ahead_poses, poses - 1 - cfg_->trajectory.prevent_look_ahead_poses_near_goal));
+  const double horizon = cfg_->trajectory.dt_ref * target;
+  double elapsed = 0.0;
+  for (int k = 0; k < target; ++k) {
+    elapsed += teb_.TimeDiff(k);
+    if (elapsed >= horizon) { target = k + 1; break; }
   }
-  if (dt <= 0) { vx = 0; vy = 0; omega = 0; return false; }
-  extractVelocity(teb_.Pose(0), teb_.Pose(look_ahead_poses), dt, vx, vy, omega);
+  if (elapsed <= 0) return false;
+  extractVelocity(teb_.Pose(0), teb_.Pose(target), elapsed, vx, vy, omega);
   return true;
 }
 
-/* :1174-1200 */
+/* n + 1 twists for n poses (reference :1174-1200): the start velocity, the mean velocity of every segment, the goal velocity */
 void TebOptimalPlanner::getVelocityProfile(std::vector<geometry_msgs::Twist>& velocity_profile) const {
-  int n = teb_.sizePoses();
-  velocity_profile.resize(n + 1);
-  velocity_profile.front().linear.z = 0;
-  velocity_profile.front().angular.x = velocity_profile.front().angular.y = 0;
-  velocity_profile.front().linear.x = vel_start_.second.linear.x;
-  velocity_profile.front().linear.y = vel_start_.second.linear.y;
-  velocity_profile.front().angular.z = vel_start_.second.angular.z;
-  for (int i = 1; i < n; ++i) {
-    velocity_profile[i].linear.z = 0;
-    velocity_profile[i].angular.x = velocity_profile[i].angular.y = 0;
-    extractVelocity(teb_.Pose(i - 1), teb_.Pose(i), teb_.TimeDiff(i - 1), velocity_profile[i].linear.x,
-                    velocity_profile[i].linear.y, velocity_profile[i].angular.z);
+  const int poses = teb_.sizePoses();
+  velocity_profile.assign(poses + 1, geometry_msgs::Twist());
+  auto boundary = [](geometry_msgs::Twist& out, const geometry_msgs::Twist& given) {
+    out.linear.x = given.linear.x;
+    out.linear.y = given.linear.y;
+    out.angular.z = given.angular.z;
+  };
+  boundary(velocity_profile.front(), vel_start_.second);
+  for (int k = 1; k < poses; ++k) {
+    geometry_msgs::Twist& t = velocity_profile[k];
+    extractVelocity(teb_.Pose(k - 1), teb_.Pose(k), teb_.TimeDiff(k - 1), t.linear.x, t.linear.y, t.angular.z);
   }
-  velocity_profile.back().linear.z = 0;
-  velocity_profile.back().angular.x = velocity_profile.back().angular.y = 0;
-  velocity_profile.back().linear.x = vel_goal_.second.linear.x;
-  velocity_profile.back().linear.y = vel_goal_.second.linear.y;
-  velocity_profile.back().angular.z = vel_goal_.second.angular.z;
+  boundary(velocity_profile.back(), vel_goal_.second);
 }
 
 }  // namespace teb_local_planner

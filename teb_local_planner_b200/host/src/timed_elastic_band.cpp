@@ -10,27 +10,28 @@
 namespace teb_local_planner {
 
 namespace {
-/* estimateDeltaT (timed_elastic_band.cpp:52-65) */
-double estimateDeltaT(const PoseSE2& start, const PoseSE2& end, double max_vel_x, double max_vel_theta) {
-  double dt_constant_motion = 0.1;
-  if (max_vel_x > 0) {
-    double trans_dist = (end.position() - start.position()).norm();
-    dt_constant_motion = trans_dist / max_vel_x;
-  }
-  if (max_vel_theta > 0) {
-    double rot_dist = std::abs(g2o::normalize_theta(end.theta() - start.theta()));
-    dt_constant_motion = std::max(dt_constant_motion, rot_dist / max_vel_theta);
-  }
-  return dt_constant_motion;
+
+/* Time a robot limited to (v_max, w_max) needs from pose a to pose b when translation and rotation run concurrently:
+ * the slower of the two decides; 0.1 s when no translational limit is given (reference estimateDeltaT, :52-65). */
+double travel_time(const PoseSE2& a, const PoseSE2& b, double v_max, double w_max) {
+  double t = 0.1;
+  if (v_max > 0) t = (b.position() - a.position()).norm() / v_max;
+  if (w_max > 0) t = std::max(t, std::abs(g2o::normalize_theta(b.theta() - a.theta())) / w_max);
+  return t;
 }
+
+/* true when the goal lies behind the start pose's heading */
+bool goal_is_behind(const Eigen::Vector2d& start_to_goal, const PoseSE2& start) {
+  return start_to_goal.dot(start.orientationUnitVec()) < 0;
+}
+
 }  // namespace
 
-/* :141-150 */
+/* a pose / time-difference pair can only be appended while the band holds one more pose than time differences (:141-150) */
 void TimedElasticBand::addPoseAndTimeDiff(const PoseSE2& pose, double dt) {
-  if (sizePoses() != sizeTimeDiffs()) {
-    addPose(pose, false);
-    addTimeDiff(dt, false);
-  }
+  if (sizePoses() == sizeTimeDiffs()) return;
+  addPose(pose, false);
+  addTimeDiff(dt, false);
 }
 
 void TimedElasticBand::setPoseVertexFixed(int index, bool status) {
@@ -50,156 +51,140 @@ void TimedElasticBand::autoResize(double dt_ref, double dt_hysteresis, int min_s
   fromRecords(rec.data(), nn);
 }
 
-/* :325-387 */
+/* Straight-line band from start to goal (reference :325-387): samples every `diststep` metres along the connecting
+ * line, all with the line's heading (turned by pi when driving backwards is guessed), constant time step diststep /
+ * max_vel_x; a sample that would coincide with the goal is left out; midpoints towards the goal are appended until
+ * min_samples is reached; the goal closes the band. Refuses to touch an initialised band. */
 bool TimedElasticBand::initTrajectoryToGoal(const PoseSE2& start, const PoseSE2& goal, double diststep, double max_vel_x,
                                             int min_samples, bool guess_backwards_motion) {
-  if (!isInit()) {
-    addPose(start);
-    setPoseVertexFixed(0, true);
-    double timestep = 0.1;
-    if (diststep != 0) {
-      Eigen::Vector2d point_to_goal = goal.position() - start.position();
-      double dir_to_goal = std::atan2(point_to_goal[1], point_to_goal[0]);
-      double dx = diststep * std::cos(dir_to_goal);
-      double dy = diststep * std::sin(dir_to_goal);
-      double orient_init = dir_to_goal;
-      if (guess_backwards_motion && point_to_goal.dot(start.orientationUnitVec()) < 0)
-        orient_init = g2o::normalize_theta(orient_init + M_PI);
-      double dist_to_goal = point_to_goal.norm();
-      double no_steps_d = dist_to_goal / std::abs(diststep);
-      unsigned int no_steps = (unsigned int)std::floor(no_steps_d);
-      if (max_vel_x > 0) timestep = diststep / max_vel_x;
-      for (unsigned int i = 1; i <= no_steps; i++) {
-        if (i == no_steps && no_steps_d == (float)no_steps) break;
-        addPoseAndTimeDiff(start.x() + i * dx, start.y() + i * dy, orient_init, timestep);
-      }
+  if (isInit()) return false;
+  const bool timed = max_vel_x > 0;
+  double step_time = 0.1;
+  addPose(start);
+  setPoseVertexFixed(0, true);
+  if (diststep != 0) {
+    const Eigen::Vector2d to_goal = goal.position() - start.position();
+    const double line_heading = std::atan2(to_goal[1], to_goal[0]);
+    const double step_x = diststep * std::cos(line_heading), step_y = diststep * std::sin(line_heading);
+    const double heading = (guess_backwards_motion && goal_is_behind(to_goal, start)) ? g2o::normalize_theta(line_heading + M_PI)
+                                                                                      : line_heading;
+    const double steps_exact = to_goal.norm() / std::abs(diststep);
+    const unsigned int steps = (unsigned int)std::floor(steps_exact);
+    const bool last_hits_goal = steps_exact == (float)steps; /* single-precision comparison, as the reference does */
+    if (timed) step_time = diststep / max_vel_x;
+    for (unsigned int k = 1; k <= steps; ++k) {
+      if (k == steps && last_hits_goal) break;
+      addPoseAndTimeDiff(start.x() + k * step_x, start.y() + k * step_y, heading, step_time);
     }
-    if (sizePoses() < min_samples - 1) {
-      while (sizePoses() < min_samples - 1) {
-        PoseSE2 intermediate_pose = PoseSE2::average(BackPose(), goal);
-        if (max_vel_x > 0) timestep = (intermediate_pose.position() - BackPose().position()).norm() / max_vel_x;
-        addPoseAndTimeDiff(intermediate_pose, timestep);
-      }
-    }
-    if (max_vel_x > 0) timestep = (goal.position() - BackPose().position()).norm() / max_vel_x;
-    addPoseAndTimeDiff(goal, timestep);
-    setPoseVertexFixed(sizePoses() - 1, true);
-  } else {
-    return false;
   }
+  while (sizePoses() < min_samples - 1) { /* too few samples: keep bisecting the rest of the way */
+    const PoseSE2 mid = PoseSE2::average(BackPose(), goal);
+    if (timed) step_time = (mid.position() - BackPose().position()).norm() / max_vel_x;
+    addPoseAndTimeDiff(mid, step_time);
+  }
+  if (timed) step_time = (goal.position() - BackPose().position()).norm() / max_vel_x;
+  addPoseAndTimeDiff(goal, step_time);
+  setPoseVertexFixed(sizePoses() - 1, true);
   return true;
 }
 
-/* :389-452 */
+/* Band along a reference plan (reference :389-452): one pose per inner plan point, its heading either taken from the
+ * plan or estimated from the direction to the next plan point (turned by pi for a guessed backwards motion), time
+ * differences from travel_time(); padded with midpoints up to min_samples; closed by the plan's last pose. */
 bool TimedElasticBand::initTrajectoryToGoal(const std::vector<geometry_msgs::PoseStamped>& plan, double max_vel_x,
                                             double max_vel_theta, bool estimate_orient, int min_samples,
                                             bool guess_backwards_motion) {
-  if (!isInit()) {
-    PoseSE2 start(plan.front().pose);
-    PoseSE2 goal(plan.back().pose);
-    addPose(start);
-    setPoseVertexFixed(0, true);
-    bool backwards = false;
-    if (guess_backwards_motion && (goal.position() - start.position()).dot(start.orientationUnitVec()) < 0) backwards = true;
-    for (int i = 1; i < (int)plan.size() - 1; ++i) {
-      double yaw;
-      if (estimate_orient) {
-        double dx = plan[i + 1].pose.position.x - plan[i].pose.position.x;
-        double dy = plan[i + 1].pose.position.y - plan[i].pose.position.y;
-        yaw = std::atan2(dy, dx);
-        if (backwards) yaw = g2o::normalize_theta(yaw + M_PI);
-      } else {
-        yaw = tf::getYaw(plan[i].pose.orientation);
-      }
-      PoseSE2 intermediate_pose(plan[i].pose.position.x, plan[i].pose.position.y, yaw);
-      double dt = estimateDeltaT(BackPose(), intermediate_pose, max_vel_x, max_vel_theta);
-      addPoseAndTimeDiff(intermediate_pose, dt);
+  if (isInit()) return false;
+  const PoseSE2 first(plan.front().pose), last(plan.back().pose);
+  const bool reversed = guess_backwards_motion && goal_is_behind(last.position() - first.position(), first);
+  auto append = [&](const PoseSE2& pose) { addPoseAndTimeDiff(pose, travel_time(BackPose(), pose, max_vel_x, max_vel_theta)); };
+  addPose(first);
+  setPoseVertexFixed(0, true);
+  const int inner_end = (int)plan.size() - 1;
+  for (int k = 1; k < inner_end; ++k) {
+    const geometry_msgs::Point& here = plan[k].pose.position;
+    double heading = tf::getYaw(plan[k].pose.orientation);
+    if (estimate_orient) {
+      const geometry_msgs::Point& ahead = plan[k + 1].pose.position;
+      heading = std::atan2(ahead.y - here.y, ahead.x - here.x);
+      if (reversed) heading = g2o::normalize_theta(heading + M_PI);
     }
-    if (sizePoses() < min_samples - 1) {
-      while (sizePoses() < min_samples - 1) {
-        PoseSE2 intermediate_pose = PoseSE2::average(BackPose(), goal);
-        double dt = estimateDeltaT(BackPose(), intermediate_pose, max_vel_x, max_vel_theta);
-        addPoseAndTimeDiff(intermediate_pose, dt);
-      }
-    }
-    double dt = estimateDeltaT(BackPose(), goal, max_vel_x, max_vel_theta);
-    addPoseAndTimeDiff(goal, dt);
-    setPoseVertexFixed(sizePoses() - 1, true);
-  } else {
-    return false;
+    append(PoseSE2(here.x, here.y, heading));
   }
+  while (sizePoses() < min_samples - 1) append(PoseSE2::average(BackPose(), last));
+  append(last);
+  setPoseVertexFixed(sizePoses() - 1, true);
   return true;
 }
 
-/* :455-478 */
+/* index of the pose (from begin_idx on) nearest to ref_point, -1 for an invalid begin_idx; the first minimum wins
+ * (reference :455-478) */
 int TimedElasticBand::findClosestTrajectoryPose(const Eigen::Vector2d& ref_point, double* distance, int begin_idx) const {
-  int n = sizePoses();
-  if (begin_idx < 0 || begin_idx >= n) return -1;
-  double min_dist_sq = std::numeric_limits<double>::max();
-  int min_idx = -1;
-  for (int i = begin_idx; i < n; i++) {
-    double dist_sq = (ref_point - Pose(i).position()).squaredNorm();
-    if (dist_sq < min_dist_sq) {
-      min_dist_sq = dist_sq;
-      min_idx = i;
-    }
+  const int count = sizePoses();
+  if (begin_idx < 0 || begin_idx >= count) return -1;
+  int best = -1;
+  double best_sq = std::numeric_limits<double>::max();
+  for (int k = begin_idx; k < count; ++k) {
+    const double sq = (ref_point - Pose(k).position()).squaredNorm();
+    if (sq < best_sq) { best_sq = sq; best = k; }
   }
-  if (distance) *distance = std::sqrt(min_dist_sq);
-  return min_idx;
+  if (distance) *distance = std::sqrt(best_sq);
+  return best;
 }
 
-/* :555-597 */
+/* Warm start of the next planning cycle (reference :555-597): walking from the front, poses are dropped while they
+ * keep getting closer to the new start (at most 10, and never below min_samples); the first pose is then replaced by the
+ * new start and the last one by the new goal. */
 void TimedElasticBand::updateAndPruneTEB(const PoseSE2* new_start, const PoseSE2* new_goal, int min_samples) {
-  if (new_start && sizePoses() > 0) {
-    double dist_cache = (new_start->position() - Pose(0).position()).norm();
-    double dist;
-    int lookahead = std::min<int>(sizePoses() - min_samples, 10);
-    int nearest_idx = 0;
-    for (int i = 1; i <= lookahead; ++i) {
-      dist = (new_start->position() - Pose(i).position()).norm();
-      if (dist < dist_cache) {
-        dist_cache = dist;
-        nearest_idx = i;
-      } else {
-        break;
-      }
+  if (sizePoses() == 0) return;
+  if (new_start) {
+    const int reach = std::min<int>(sizePoses() - min_samples, 10);
+    double nearest = (new_start->position() - Pose(0).position()).norm();
+    int drop = 0; /* poses 1 .. drop go away */
+    while (drop < reach) {
+      const double d = (new_start->position() - Pose(drop + 1).position()).norm();
+      if (!(d < nearest)) break;
+      nearest = d;
+      ++drop;
     }
-    if (nearest_idx > 0) {
-      deletePoses(1, nearest_idx);
-      deleteTimeDiffs(1, nearest_idx);
+    if (drop > 0) {
+      deletePoses(1, drop);
+      deleteTimeDiffs(1, drop);
     }
     Pose(0) = *new_start;
   }
-  if (new_goal && sizePoses() > 0) BackPose() = *new_goal;
+  if (new_goal) BackPose() = *new_goal;
 }
 
 double TimedElasticBand::getSumOfAllTimeDiffs() const {
-  double time = 0;
-  for (double dt : timediff_vec_) time += dt;
-  return time;
+  double total = 0;
+  for (double dt : timediff_vec_) total += dt;
+  return total;
 }
 double TimedElasticBand::getSumOfTimeDiffsUpToIdx(int index) const {
-  double time = 0;
-  for (int i = 0; i < index; ++i) time += timediff_vec_.at(i);
-  return time;
+  double total = 0;
+  for (int k = 0; k < index; ++k) total += timediff_vec_.at(k);
+  return total;
 }
 double TimedElasticBand::getAccumulatedDistance() const {
-  double dist = 0;
-  for (int i = 1; i < sizePoses(); ++i) dist += (Pose(i).position() - Pose(i - 1).position()).norm();
-  return dist;
+  double length = 0;
+  for (int k = 1; k < sizePoses(); ++k) length += (Pose(k).position() - Pose(k - 1).position()).norm();
+  return length;
 }
 
-/* :600-631 */
+/* every (skip_poses + 1)-th pose must lie within `radius` of the robot and, when max_dist_behind_robot >= 0, not further
+ * than that behind it (reference :600-631) */
 bool TimedElasticBand::isTrajectoryInsideRegion(double radius, double max_dist_behind_robot, int skip_poses) {
-  if (sizePoses() <= 0) return true;
-  double radius_sq = radius * radius;
-  double max_dist_behind_robot_sq = max_dist_behind_robot * max_dist_behind_robot;
-  Eigen::Vector2d robot_orient = Pose(0).orientationUnitVec();
-  for (int i = 1; i < sizePoses(); i = i + skip_poses + 1) {
-    Eigen::Vector2d dist_vec = Pose(i).position() - Pose(0).position();
-    double dist_sq = dist_vec.squaredNorm();
-    if (dist_sq > radius_sq) return false;
-    if (max_dist_behind_robot >= 0 && dist_vec.dot(robot_orient) < 0 && dist_sq > max_dist_behind_robot_sq) return false;
+  const int count = sizePoses();
+  if (count <= 0) return true;
+  const Eigen::Vector2d origin = Pose(0).position(), forward = Pose(0).orientationUnitVec();
+  const bool check_behind = max_dist_behind_robot >= 0;
+  for (int k = 1; k < count; k += skip_poses + 1) {
+    const Eigen::Vector2d offset = Pose(k).position() - origin;
+    const double sq = offset.squaredNorm();
+    const bool too_far = sq > radius * radius;
+    const bool too_far_behind = check_behind && offset.dot(forward) < 0 && sq > max_dist_behind_robot * max_dist_behind_robot;
+    if (too_far || too_far_behind) return false;
   }
   return true;
 }
