@@ -303,6 +303,9 @@ def run_b200(a, rank, local_rank, world):
     B, n_cap = hb.B, hb.n_cap
     g = T.TebGpu(B, n_cap, hb.S, max(hb.M_cap, 1), hb.V_cap, device=local_rank)
     g.set_params(p)
+    if world > 1:   # the cost all-gather lives behind the C-ABI (ncclAllGather); torch.distributed only carries the id
+        from teb_local_planner_b200 import distributed as D0
+        D0.init_comm(g, rank, world, device=dev)
     # a non-default torch stream: its handle is passed to the C-ABI so that torch ops (input restore, NCCL) and
     # the optimizer kernels are ordered on ONE stream, and torch.cuda.Event timing sees the kernels
     stream = torch.cuda.Stream(device=dev)
@@ -336,8 +339,8 @@ def run_b200(a, rank, local_rank, world):
     def device_step():
         d_poses.copy_(d_pristine)                       # fresh synthetic inputs, already resident in HBM
         g.optimize_device(bs, args, stream.cuda_stream)  # all kernels of optimizeTEB for the whole batch
-        if world > 1:
-            dist.all_gather_into_tensor(d_all_cost, d_cost)  # the ONE collective: per-candidate costs
+        if world > 1:   # the ONE collective: per-candidate costs, tebgpu_gather_costs on the same stream
+            g.gather_costs_device(d_cost.data_ptr(), B, d_all_cost.data_ptr(), stream.cuda_stream)
 
     sampler = ClockSampler(local_rank)      # started before the warm-up so that nvidia-smi is already streaming
     sampler.start()
@@ -463,11 +466,10 @@ def run_b200(a, rank, local_rank, world):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        g.optimize(hp, args)                            # H2D, all kernels, D2H of poses/cost/status, synchronous
         if world > 1:
-            gather_in.copy_(torch.from_numpy(hp.cost))
-            dist.all_gather_into_tensor(d_all_cost, gather_in)
-            _ = d_all_cost.cpu()
+            host_all = g.optimize_gather(hp, args)      # tebgpu_optimize_batch_gather: H2D, kernels, all-gather, D2H
+        else:
+            g.optimize(hp, args)                        # H2D, all kernels, D2H of poses/cost/status, synchronous
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if k >= a.warmup:
@@ -524,7 +526,7 @@ def run_b200(a, rank, local_rank, world):
                 "config": dict(desc, l2="flushed between timed steps (256 MB memset)", timing="CUDA events per step on the launching stream, max over ranks"),
                 "lm_iters_per_s": lm_iters_step / (ms_per_step * 1e-3),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": e2e_ms, "api": "tebgpu_optimize_batch (C-ABI, pinned host buffers)"},
+                        "ms_per_step": e2e_ms, "api": "tebgpu_optimize_batch" + ("_gather" if world > 1 else "") + " (C-ABI, pinned host buffers)"},
                 "gpu_launches": int(launches_per_step * a.steps),
                 "gpu_launches_per_step": int(launches_per_step),
                 "roofline": dominant, "roofline_kernel_a": roof_a, "roofline_kernel_b": roof_b,

@@ -317,7 +317,8 @@ int32_t tebgpu_select_best(const double* cost, int32_t count, int32_t last_best,
  *   tebgpu_comm_get_unique_id  rank 0 creates the 128-byte id and distributes it out of band (MPI, a store, a file)
  *   tebgpu_comm_init           every rank, collectively: ncclCommInitRank on the context's device
  *   tebgpu_gather_costs        cost_all[r * count_local + k] = cost_local of rank r (same count on every rank);
- *                              device_ptrs != 0: both pointers are device memory, stream ordered on the context stream, no
+ *                              device_ptrs != 0: both pointers are device memory, stream ordered on `cuda_stream` (a
+ *                              cudaStream_t as void*; NULL = the context's stream, as in tebgpu_optimize_batch_device), no
  *                              synchronisation; 0: host memory, synchronous. Without a communicator (one rank): a copy.
  *   tebgpu_optimize_batch_gather  tebgpu_optimize_batch followed by the gather of batch->cost: cost_all [world * B] (host)
  * Errors: TEBGPU_ERR_UNSUPPORTED when NCCL cannot be loaded, TEBGPU_ERR_CUDA for NCCL / CUDA failures (see
@@ -326,7 +327,8 @@ int32_t tebgpu_select_best(const double* cost, int32_t count, int32_t last_best,
 int32_t tebgpu_comm_get_unique_id(void* id_out);
 int32_t tebgpu_comm_init(tebgpu_ctx* ctx, const void* id, int32_t world_size, int32_t rank);
 int32_t tebgpu_comm_destroy(tebgpu_ctx* ctx);
-int32_t tebgpu_gather_costs(tebgpu_ctx* ctx, const double* cost_local, int32_t count_local, double* cost_all, int32_t device_ptrs);
+int32_t tebgpu_gather_costs(tebgpu_ctx* ctx, const double* cost_local, int32_t count_local, double* cost_all, int32_t device_ptrs,
+                            void* cuda_stream);
 int32_t tebgpu_optimize_batch_gather(tebgpu_ctx* ctx, const TebBatch* batch, const TebOptimizeArgs* args, double* cost_all);
 
 /* TimedElasticBand::autoResize (timed_elastic_band.cpp:227-286) on one host band; same routine the

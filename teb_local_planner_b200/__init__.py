@@ -61,7 +61,7 @@ def load_library(build_if_missing=False):
     L.tebgpu_comm_destroy.restype = C.c_int32
     L.tebgpu_comm_destroy.argtypes = [vp]
     L.tebgpu_gather_costs.restype = C.c_int32
-    L.tebgpu_gather_costs.argtypes = [vp, vp, C.c_int32, vp, C.c_int32]
+    L.tebgpu_gather_costs.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.tebgpu_optimize_batch_gather.restype = C.c_int32
     L.tebgpu_optimize_batch_gather.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs), vp]
     L.tebgpu_set_graph.restype = C.c_int32
@@ -181,16 +181,17 @@ class TebGpu:
     def comm_destroy(self):
         self._check(self.lib.tebgpu_comm_destroy(self.ctx), "tebgpu_comm_destroy")
 
-    def gather_costs_device(self, d_local_ptr, count_local, d_all_ptr):
-        """device pointers, stream ordered on the context stream (or the stream the batch was optimised on)"""
-        self._check(self.lib.tebgpu_gather_costs(self.ctx, d_local_ptr, int(count_local), d_all_ptr, 1), "tebgpu_gather_costs")
+    def gather_costs_device(self, d_local_ptr, count_local, d_all_ptr, stream=None):
+        """device pointers, stream ordered on `stream` (cudaStream_t handle; None = the context's stream)"""
+        self._check(self.lib.tebgpu_gather_costs(self.ctx, d_local_ptr, int(count_local), d_all_ptr, 1, stream),
+                    "tebgpu_gather_costs")
 
     def gather_costs(self, local_cost):
         """host numpy vector [count] -> [world * count]"""
         import numpy as np
         local_cost = np.ascontiguousarray(local_cost, dtype=np.float64)
         out = np.zeros(self.info(3) * local_cost.size)
-        self._check(self.lib.tebgpu_gather_costs(self.ctx, local_cost.ctypes.data, local_cost.size, out.ctypes.data, 0),
+        self._check(self.lib.tebgpu_gather_costs(self.ctx, local_cost.ctypes.data, local_cost.size, out.ctypes.data, 0, None),
                     "tebgpu_gather_costs")
         return out
 

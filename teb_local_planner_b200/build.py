@@ -54,8 +54,9 @@ def build_host(force=False, verbose=False):
     common = [gxx, "-std=c++17", "-O2", "-fPIC", "-Wall", "-Wextra", "-march=x86-64-v3"] + inc
     link = ["-L", HERE, "-lteb_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + HERE]
     cmds = [common + ["-shared", "-o", HOST_LIB] + HOST_SRCS + link,
-            common + ["-o", HOST_TEST, os.path.join(HOST_DIR, "test", "test_dropin.cpp"), "-L", HERE,
-                      "-lteb_local_planner_b200", "-lteb_b200", "-Wl,-rpath," + HERE]]
+            common + ["-I", "/usr/local/cuda/include", "-o", HOST_TEST, os.path.join(HOST_DIR, "test", "test_dropin.cpp"), "-L", HERE,
+                      "-lteb_local_planner_b200", "-lteb_b200", "-L", "/usr/local/cuda/lib64", "-lcudart",
+                      "-Wl,-rpath," + HERE, "-Wl,-rpath,/usr/local/cuda/lib64"]]
     for cmd in cmds:
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or res.returncode != 0:

@@ -1022,10 +1022,11 @@ int32_t tebgpu_comm_destroy(tebgpu_ctx* ctx) {
   return TEBGPU_OK;
 }
 
-int32_t tebgpu_gather_costs(tebgpu_ctx* ctx, const double* cost_local, int32_t count_local, double* cost_all, int32_t device_ptrs) {
+int32_t tebgpu_gather_costs(tebgpu_ctx* ctx, const double* cost_local, int32_t count_local, double* cost_all, int32_t device_ptrs,
+                            void* cuda_stream) {
   if (!ctx || !cost_local || !cost_all || count_local < 1) return TEBGPU_ERR_INVALID_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = (device_ptrs && cuda_stream) ? (cudaStream_t)cuda_stream : ctx->stream;
   const size_t bytes = (size_t)count_local * sizeof(double);
   if (!ctx->comm) { /* one rank: the gathered vector is the local one */
     if (device_ptrs) { if (cost_all != cost_local) CUDA_TRY(ctx, cudaMemcpyAsync(cost_all, cost_local, bytes, cudaMemcpyDeviceToDevice, st)); }

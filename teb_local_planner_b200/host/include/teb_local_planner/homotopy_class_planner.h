@@ -93,6 +93,8 @@ class HomotopyClassPlanner : public PlannerInterface {
   const ObstContainer* obstacles() const { return obstacles_; }
   bool isInitialized() const { return initialized_; }
   void setGpuContext(TebGpuContextPtr ctx) { gpu_ = ctx; }
+  /* one context per device: optimizeAllTEBs shards the candidates over them (contiguous split, one host thread per device) */
+  void setGpuContexts(const std::vector<TebGpuContextPtr>& ctxs) { gpus_ = ctxs; if (!ctxs.empty()) gpu_ = ctxs.front(); }
 
  protected:
   const TebConfig* cfg_ = nullptr;
@@ -113,6 +115,7 @@ class HomotopyClassPlanner : public PlannerInterface {
   std::chrono::steady_clock::time_point last_eq_class_switching_time_;
   bool initialized_ = false;
   TebGpuContextPtr gpu_;
+  std::vector<TebGpuContextPtr> gpus_;
 };
 typedef std::shared_ptr<HomotopyClassPlanner> HomotopyClassPlannerPtr;
 

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <limits>
+#include <thread>
 
 namespace teb_local_planner {
 
@@ -303,13 +304,31 @@ void HomotopyClassPlanner::updateAllTEBs(const PoseSE2* start, const PoseSE2* go
   }
 }
 
-/* :466-493 — the per-candidate boost::thread fan-out becomes ONE batched launch sequence over all candidates */
+/* :466-493 — the per-candidate boost::thread fan-out becomes ONE batched launch sequence over all candidates. With
+ * several device contexts (setGpuContexts) the candidates are split contiguously over the devices, one host thread per
+ * device drives its shard, and the join of those threads is the point where every cost is known - the in-process
+ * counterpart of the NCCL all-gather that separate processes use (tebgpu_gather_costs). */
 void HomotopyClassPlanner::optimizeAllTEBs(int iter_innerloop, int iter_outerloop) {
   if (tebs_.empty() || !cfg_->optim.optimization_activate) return;
   std::vector<TebOptimalPlanner*> all;
   for (auto& teb : tebs_) all.push_back(teb.get());
-  optimizeTebBatch(*cfg_, all, iter_innerloop, iter_outerloop, true, cfg_->hcp.selection_obst_cost_scale,
-                   cfg_->hcp.selection_viapoint_cost_scale, cfg_->hcp.selection_alternative_time_cost, gpu_);
+  const size_t devices = std::min(gpus_.size(), all.size());
+  if (devices <= 1) {
+    optimizeTebBatch(*cfg_, all, iter_innerloop, iter_outerloop, true, cfg_->hcp.selection_obst_cost_scale,
+                     cfg_->hcp.selection_viapoint_cost_scale, cfg_->hcp.selection_alternative_time_cost,
+                     gpus_.empty() ? gpu_ : gpus_.front());
+    return;
+  }
+  std::vector<std::thread> workers;
+  for (size_t d = 0; d < devices; ++d) {
+    const size_t lo = all.size() * d / devices, hi = all.size() * (d + 1) / devices;
+    workers.emplace_back([this, &all, lo, hi, d, iter_innerloop, iter_outerloop]() {
+      const std::vector<TebOptimalPlanner*> shard(all.begin() + lo, all.begin() + hi);
+      optimizeTebBatch(*cfg_, shard, iter_innerloop, iter_outerloop, true, cfg_->hcp.selection_obst_cost_scale,
+                       cfg_->hcp.selection_viapoint_cost_scale, cfg_->hcp.selection_alternative_time_cost, gpus_[d]);
+    });
+  }
+  for (std::thread& w : workers) w.join();
 }
 
 namespace {

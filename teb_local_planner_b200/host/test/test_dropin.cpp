@@ -8,6 +8,7 @@
  */
 #include <cmath>
 #include <cstdio>
+#include <cuda_runtime_api.h>
 #include <cstring>
 #include <string>
 
@@ -276,6 +277,38 @@ static int gpu_checks() {
       std::snprintf(key, sizeof(key), "AUTO%d", q++);
       print_band(key, t->teb());
     }
+  }
+  { /* ---- optimizeAllTEBs sharded over two device contexts (device 1 when the box has one, else twice device 0): the
+     * candidates, their costs and the winner must be those of the single-context run */
+    int devices = 0;
+    cudaGetDeviceCount(&devices);
+    auto run = [&](bool sharded, std::vector<double>& costs, int& best) {
+      TebConfig mcfg;
+      mcfg.obstacles.include_dynamic_obstacles = false;
+      mcfg.hcp.max_number_classes = 3;
+      HomotopyClassPlanner m(mcfg, &hob);
+      if (sharded) {
+        std::vector<TebGpuContextPtr> ctxs;
+        ctxs.push_back(TebGpuContextPtr(new TebGpuContext(8, 512, 64, 8, 0)));
+        ctxs.push_back(TebGpuContextPtr(new TebGpuContext(8, 512, 64, 8, devices > 1 ? 1 : 0)));
+        m.setGpuContexts(ctxs);
+      }
+      m.addAndInitNewTeb(p1, NULL);
+      m.addAndInitNewTeb(p2, NULL);
+      const bool mok = m.plan(p0, NULL);
+      CHECK(mok);
+      for (auto& t : m.getTrajectoryContainer()) costs.push_back(t->getCurrentCost());
+      best = m.bestTebIdx();
+    };
+    std::vector<double> c_single, c_sharded;
+    int b_single = -2, b_sharded = -3;
+    run(false, c_single, b_single);
+    run(true, c_sharded, b_sharded);
+    CHECK(c_single.size() == c_sharded.size() && b_single == b_sharded);
+    bool same = c_single.size() == c_sharded.size();
+    for (size_t q = 0; same && q < c_single.size(); ++q) same = c_single[q] == c_sharded[q];
+    CHECK(same);
+    std::printf("SHARDED_OK %d devices %d candidates %d\n", same ? 1 : 0, devices, (int)c_sharded.size());
   }
   /* second cycle: hysteresis path of selectBestTeb + warm start of all candidates */
   ok = hcp.plan(PoseSE2(-3.95, 0, 0), PoseSE2(4, 0, 0), NULL);
