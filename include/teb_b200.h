@@ -256,6 +256,12 @@ int32_t tebgpu_set_linearize_variant(tebgpu_ctx* ctx, int32_t variant);
  * Results do not depend on it (the accept / reject chain is replayed in order), only latency and traffic do. */
 int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k);
 
+/* Mapping of the default solver's solve kernel: 0 one THREAD per (band, trial) system (k_solve_tpb: throughput regime),
+ * 1 one WARP per system (k_solve_warp: window spread over the lanes, axpy back substitution; latency regime),
+ * 2 (default) by regime: the warp mapping while a round has at most 148 x 8 systems. Factors and solutions of the two
+ * mappings are bit-identical. */
+int32_t tebgpu_set_warp_solver(tebgpu_ctx* ctx, int32_t mode);
+
 /* CUDA-graph replay of the launch sequence of tebgpu_optimize_batch(_device): 0 never, 1 always, 2 (default) in the
  * latency regime only (a batch of at most ~2300 bands, e.g. one planning request of 32 candidates, where the 130-170
  * kernel launches of one optimizeTEB are comparable to the kernels themselves). A sequence is captured once per distinct

@@ -1,7 +1,8 @@
 /*
  * teb_oracle.c — CPU restatement of the reference's TEB optimisation path ("g2o mode").
- * TEST INFRASTRUCTURE ONLY — see teb_oracle.h. PARITY UNPINNED (no reference golden vectors exist
- * for anything but autoResize; g2o/CSparse are third-party and absent from /root/reference).
+ * TEST INFRASTRUCTURE ONLY — see teb_oracle.h. Parity is PINNED by oracle/_ref (the reference's own sources compiled
+ * against stand-in headers): bit-identical on every compared quantity, tests/test_reference_pin.py. Only the g2o
+ * optimizer internals (third-party, absent from /root/reference) remain restated from published behaviour.
  *
  * What is restated and from where (all paths relative to /root/reference):
  *   penalties                         include/teb_local_planner/g2o_types/penalties.h:57-117

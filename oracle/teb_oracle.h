@@ -4,12 +4,15 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library. The product (teb_local_planner_b200/) never links or calls it.
  *
- * PARITY UNPINNED: the reference's own tests (test/teb_basics.cpp) pin only autoResize; the LM /
- * Hessian / Cholesky arithmetic lives in libg2o + CSparse, which are NOT under /root/reference and
- * cannot be built in this container (no g2o, SuiteSparse, Eigen, Boost, ROS; no network). The g2o
- * behaviour restated here follows upstream g2o 2018.3.25 / 2020.5.3
- * (ROS melodic / noetic libg2o) from published source knowledge and is anchored on the reference's
- * call sites (src/optimal_planner.cpp:161-179, 385-387, 1057-1072).
+ * PARITY PINNED against the reference's own code: oracle/_ref/libteb_ref.so (make ref) is src/optimal_planner.cpp +
+ * src/timed_elastic_band.cpp + src/obstacles.cpp and their headers, compiled where they lie under /root/reference against
+ * stand-ins for the absent third-party code (oracle/ref_shims/: Eigen, boost, ROS messages, the g2o optimizer).
+ * tests/test_reference_pin.py compares this restatement with it BIT FOR BIT: every edge (errors, information,
+ * Jacobians), H / b / chi2, whole optimizeTEB calls (poses, n, cost, LM trials) on 24 feature scenarios, autoResize,
+ * initTrajectoryToGoal, penalties, distances, TebConfig defaults; tests/golden/golden_ref_v1.npz holds vectors generated
+ * from it. What stays restated from published behaviour is only the g2o optimizer itself (libg2o + CSparse: third-party,
+ * NOT under /root/reference; SURVEY.md Appendix A, upstream g2o 2018.3.25 / 2020.5.3), anchored on the reference's call
+ * sites (src/optimal_planner.cpp:161-179, 385-387, 1057-1072).
  */
 #ifndef TEB_ORACLE_H
 #define TEB_ORACLE_H

@@ -64,6 +64,8 @@ def load_library(build_if_missing=False):
     L.tebgpu_gather_costs.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.tebgpu_optimize_batch_gather.restype = C.c_int32
     L.tebgpu_optimize_batch_gather.argtypes = [vp, C.POINTER(abi.TebBatch), C.POINTER(abi.TebOptimizeArgs), vp]
+    L.tebgpu_set_warp_solver.restype = C.c_int32
+    L.tebgpu_set_warp_solver.argtypes = [vp, C.c_int32]
     L.tebgpu_set_graph.restype = C.c_int32
     L.tebgpu_set_graph.argtypes = [vp, C.c_int32]
     L.tebgpu_get_info.restype = C.c_int64
@@ -136,6 +138,10 @@ class TebGpu:
 
     def set_speculation(self, k):
         self._check(self.lib.tebgpu_set_speculation(self.ctx, int(k)), "tebgpu_set_speculation")
+
+    def set_warp_solver(self, mode):
+        """solve kernel mapping: 0 thread per system, 1 warp per system, 2 by regime"""
+        self._check(self.lib.tebgpu_set_warp_solver(self.ctx, int(mode)), "tebgpu_set_warp_solver")
 
     def set_graph(self, mode):
         """CUDA-graph replay of the launch sequence: 0 never, 1 always, 2 automatic (latency regime)"""

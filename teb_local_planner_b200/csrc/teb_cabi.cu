@@ -14,6 +14,7 @@
 #include "teb_kernels.cuh"
 #include "teb_linearize.cuh"
 #include "teb_spec.cuh"
+#include "teb_solve_warp.cuh"
 #include "teb_hsig.cuh"
 #include "teb_comm.h"
 #include <cstdlib>
@@ -45,6 +46,7 @@ struct tebgpu_ctx {
   uint64_t graph_clock = 0;
   uint64_t params_version = 0;        /* bumped by tebgpu_set_params: part of the graph key */
   int graph_mode = 2;                 /* 0 never, 1 always, 2 automatic (latency regime only) */
+  int warp_solver = 2; /* solver 2, solve kernel: 0 thread per system, 1 warp per system, 2 by regime (TEBGPU_WARP_SOLVER) */
   int ring = 0;        /* solver prefetch ring: 0 = 10 rows (default), else 10 / 20 / 30 rows (TEBGPU_RING, experiments) */
   int eval_v1 = 0;     /* TEBGPU_EVAL_V1=1: first-generation trial evaluation (warp per trial, chunk per lane) */
   int ka_staged = 1;   /* kernel A output: 1 (default) shared-memory slot + TMA bulk store per lane, 0 direct 128-bit global stores */
@@ -244,10 +246,11 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     if (const char* e = std::getenv("TEBGPU_EVAL_V1")) c->eval_v1 = std::atoi(e) != 0;
     size_t ev2 = eval2_smem_bytes((int)nc, (int)M, SPEC_K_MAX);
     if (ev2 > 232448) ev2 = 232448;
-    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev2));
-    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev2));
-    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#define EV2_ATTR(G, T)                                                                                                  \
+  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<G, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev2));          \
+  CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<G, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    EV2_ATTR(false, 256) EV2_ATTR(true, 256) EV2_ATTR(false, 512) EV2_ATTR(true, 512)
+#undef EV2_ATTR
   }
   const size_t spec_sys = ((B * SPEC_K_MAX + 31) / 32) * 32; /* whole warps of (band, trial) systems */
   CUDA_TRY(c, cudaMalloc(&c->spec.Lf, spec_sys * 4 * nc * HROW * sizeof(double)));
@@ -321,6 +324,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<30>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpb_ring_bytes(20)));
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpb_ring_bytes(30)));
+  if (const char* e = std::getenv("TEBGPU_WARP_SOLVER")) { const int m = std::atoi(e); if (m >= 0 && m <= 2) c->warp_solver = m; }
   if (const char* e = std::getenv("TEBGPU_GRAPH")) { const int m = std::atoi(e); if (m >= 0 && m <= 2) c->graph_mode = m; }
   if (const char* e = std::getenv("TEBGPU_RING")) { const int r = std::atoi(e); if (r == 10 || r == 20 || r == 30) c->ring = r; }
   CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -421,8 +425,14 @@ static size_t eval_bytes(const tebgpu_ctx* ctx, int n_cap, int M_cap, int K) {
 static void launch_trial_eval(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int K, size_t smem, int it,
                               int round, int g, int tag, cudaStream_t st) {
   if (!ctx->eval_v1) { /* second generation: one lane per pose */
-    if (kp.generic) k_trial_eval2<true><<<B, EV2_THREADS, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
-    else k_trial_eval2<false><<<B, EV2_THREADS, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+    const bool wide = (long long)B * 2 <= 148; /* a CTA per band leaves SMs idle: give each band 16 warps */
+    if (kp.generic) {
+      if (wide) k_trial_eval2<true, 512><<<B, 512, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+      else k_trial_eval2<true, 256><<<B, 256, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+    } else {
+      if (wide) k_trial_eval2<false, 512><<<B, 512, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+      else k_trial_eval2<false, 256><<<B, 256, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+    }
     return;
   }
   if (kp.generic) k_trial_eval<2, true><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
@@ -612,6 +622,10 @@ static int32_t issue_optimize(tebgpu_ctx* ctx, const TebBatch* bt, const TebOpti
              * cycles each), not by the prefetch distance - and they cost residency (20 rows: 3 warps per SM). */
             const int warps = (bk + 31) / 32;
             const int ring = ctx->ring == 0 ? 10 : ctx->ring;
+            /* latency regime: one WARP per system (k_solve_warp) while all systems of the round fit a few warps per SM */
+            const bool warp_solver = ctx->warp_solver == 1 || (ctx->warp_solver == 2 && bk <= 148 * 8);
+            if (warp_solver) k_solve_warp<<<(bk + SW_WARPS - 1) / SW_WARPS, 32 * SW_WARPS, 0, rs>>>(db, ctx->spec, it, round, g);
+            else
             if (ring == 30) k_solve_tpb<30><<<warps, 32, tpb_ring_bytes(30), rs>>>(db, ctx->spec, it, round, g);
             else if (ring == 20) k_solve_tpb<20><<<warps, 32, tpb_ring_bytes(20), rs>>>(db, ctx->spec, it, round, g);
             else k_solve_tpb<10><<<warps, 32, tpb_ring_bytes(10), rs>>>(db, ctx->spec, it, round, g);
@@ -678,7 +692,7 @@ static uint64_t graph_key(const tebgpu_ctx* ctx, const TebBatch* bt, const TebOp
   mix(bt, sizeof(*bt));
   mix(a, sizeof(*a));
   mix(&ctx->params_version, sizeof(ctx->params_version));
-  const int sw[8] = {ctx->solver, ctx->spec_k, ctx->linearize_variant, ctx->ka_staged, ctx->eval_v1, ctx->ring, ctx->overlap, ctx->eval_minb};
+  const int sw[9] = {ctx->solver, ctx->spec_k, ctx->linearize_variant, ctx->ka_staged, ctx->eval_v1, ctx->ring, ctx->overlap, ctx->eval_minb, ctx->warp_solver};
   mix(sw, sizeof(sw));
   mix(&st, sizeof(st));
   return h;
@@ -730,6 +744,12 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
   }
   ctx->graphs.push_back(ent);
   CUDA_TRY(ctx, cudaGraphLaunch(ent.exec, st));
+  return TEBGPU_OK;
+}
+
+int32_t tebgpu_set_warp_solver(tebgpu_ctx* ctx, int32_t mode) {
+  if (!ctx || mode < 0 || mode > 2) return TEBGPU_ERR_INVALID_ARG;
+  ctx->warp_solver = mode;
   return TEBGPU_OK;
 }
 

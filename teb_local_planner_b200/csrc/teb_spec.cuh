@@ -575,8 +575,8 @@ __device__ __forceinline__ void pose_chi2_lane(const KParams& kp, const DevBatch
   unary_terms<GEOM>(kp, db, b, sc, i, n, xa, ya, ca, sa, so, M, false, U, ub, chi[0], chi[1]);
 }
 
-template <bool GEOM>
-__global__ void __launch_bounds__(EV2_THREADS, 2) k_trial_eval2(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp,
+template <bool GEOM, int NT> /* NT = 256 (throughput regime, 2 CTAs per SM) or 512 (latency regime: more warps per band) */
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp,
                                                              const __grid_constant__ SpecBufs sp, int iteration, int round,
                                                              int g, int tag) {
   extern __shared__ __align__(16) unsigned char ev_raw[];
@@ -602,11 +602,11 @@ __global__ void __launch_bounds__(EV2_THREADS, 2) k_trial_eval2(const __grid_con
   const int M = db.obst_count[sc];
   {
     const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
-    for (int m = tid; m < M; m += EV2_THREADS) so[m] = go[m];
+    for (int m = tid; m < M; m += NT) so[m] = go[m];
     const double* gP = db.poses + (size_t)b * db.n_cap * 4;
     const double* grhs = db.rhs + (size_t)b * 4 * db.n_cap;
     /* the K trial solutions of a band sit in adjacent lanes of the solver's interleaved scratch (K even) */
-    for (int r = tid; r < N; r += EV2_THREADS) {
+    for (int r = tid; r < N; r += NT) {
       sP0[r] = gP[r];
       sB[r] = grhs[r];
       for (int kk = 0; kk < SPEC_K; kk += 2) {
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(EV2_THREADS, 2) k_trial_eval2(const __grid_con
   const int kact = min(SPEC_K, 10 - q0); /* trials of this round that exist (g2o stops after 10) */
   const double* vs = db.vel_start + 4 * (size_t)b;
   const double* vg = db.vel_goal + 4 * (size_t)b;
-  for (int task = warp; task < kact * tiles; task += EV2_THREADS / 32) {
+  for (int task = warp; task < kact * tiles; task += NT / 32) {
     const int k = task / tiles, tile = task - k * tiles;
     const int i = tile * EV2_TILE + lane;
     const double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(EV2_THREADS, 2) k_trial_eval2(const __grid_con
     double* gP = db.poses + (size_t)b * db.n_cap * 4;
     const double* adx = sdx + (size_t)accepted * 4 * db.n_cap;
     const bool ok = sRes[accepted * RES_STRIDE + 5] != 0.0;
-    for (int r = tid; r < N; r += EV2_THREADS) {
+    for (int r = tid; r < N; r += NT) {
       if (!row_is_real(r, n)) continue;
       const double dxv = ok ? adx[r] : sB[r];
       const double xv = sP0[r] + dxv;

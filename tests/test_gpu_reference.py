@@ -120,8 +120,8 @@ def test_optimization_deactivated_and_capacity_overflow():
     g.close()
     # autoResize would need more records than the batch provides: reported per band, others unaffected
     p2, hb1 = scenes.make_config_batch("C2", candidates=4, seed=3, autosize=True)
-    tight = abi.HostBatch(hb1.poses[:, :hb1.n.max() + 1].copy(), hb1.n, hb1.obstacles, hb1.obst_count, hb1.scene_id)
-    tight.poses[0, :tight.n[0] - 1, 3] *= 3.0     # band 0: time differences far above dt_ref -> many insertions
+    tight = abi.HostBatch(hb1.poses[:, :hb1.n.max() + 12].copy(), hb1.n, hb1.obstacles, hb1.obst_count, hb1.scene_id)
+    tight.poses[0, :tight.n[0] - 1, 3] *= 6.0     # band 0: time differences far above dt_ref -> far more than 12 insertions
     g = _gpu(tight, p2)
     h = tight.copy()
     g.optimize(h, args)
@@ -205,3 +205,23 @@ def test_cuda_graph_replay_gives_identical_results():
     g.optimize(h, args)
     assert g.info(6) == 2 and not np.array_equal(h.cost, outs[1].cost)
     g.close()
+
+
+@pytest.mark.parametrize("cfg,autosize", [("C1", True), ("C3", False), ("C4", True)])
+def test_warp_solver_is_bit_identical_to_thread_solver(cfg, autosize):
+    """k_solve_warp (one warp per system) and k_solve_tpb (one thread per system) run the same factorisation in the same
+    operation order: final bands, costs and LM iteration counts must agree bit for bit"""
+    p, hb0 = scenes.make_config_batch(cfg, candidates=32, seed=19, autosize=autosize)
+    args = _args(p)
+    g = _gpu(hb0, p)
+    g.set_graph(0)
+    outs = {}
+    for mode in (0, 1):
+        g.set_warp_solver(mode)
+        h = hb0.copy()
+        g.optimize(h, args)
+        outs[mode] = h
+    g.close()
+    assert np.array_equal(outs[0].n, outs[1].n) and np.array_equal(outs[0].lm_iters, outs[1].lm_iters)
+    assert np.array_equal(outs[0].poses, outs[1].poses) and np.array_equal(outs[0].cost, outs[1].cost)
+    assert np.array_equal(outs[0].status, outs[1].status)
