@@ -256,10 +256,11 @@ int32_t tebgpu_set_linearize_variant(tebgpu_ctx* ctx, int32_t variant);
  * Results do not depend on it (the accept / reject chain is replayed in order), only latency and traffic do. */
 int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k);
 
-/* Mapping of the default solver's solve kernel: 0 one THREAD per (band, trial) system (k_solve_tpb: throughput regime),
- * 1 one WARP per system (k_solve_warp: window spread over the lanes, axpy back substitution; latency regime),
- * 2 (default) by regime: the warp mapping while a round has at most 148 x 8 systems. Factors and solutions of the two
- * mappings are bit-identical. */
+/* Mapping of the default solver's solve kernel: 0 (default) one THREAD per (band, trial) system (k_solve_tpb), 1 one WARP
+ * per system (k_solve_warp: window spread over the lanes, pivot column through shared memory, axpy back substitution),
+ * 2 the warp mapping while a round has at most 148 x 8 systems. Factors and solutions of the two mappings are
+ * bit-identical; the warp mapping measured 2.8x slower per solve on B200 (profiles/r2_history.md) and is kept as an
+ * independent cross-check of the factorisation. */
 int32_t tebgpu_set_warp_solver(tebgpu_ctx* ctx, int32_t mode);
 
 /* CUDA-graph replay of the launch sequence of tebgpu_optimize_batch(_device): 0 never, 1 always, 2 (default) in the

@@ -46,7 +46,10 @@ struct tebgpu_ctx {
   uint64_t graph_clock = 0;
   uint64_t params_version = 0;        /* bumped by tebgpu_set_params: part of the graph key */
   int graph_mode = 2;                 /* 0 never, 1 always, 2 automatic (latency regime only) */
-  int warp_solver = 2; /* solver 2, solve kernel: 0 thread per system, 1 warp per system, 2 by regime (TEBGPU_WARP_SOLVER) */
+  int warp_solver = 0; /* solver 2, solve kernel: 0 thread per system (default), 1 warp per system, 2 warp per system in the
+                          latency regime (TEBGPU_WARP_SOLVER). Measured: the warp mapping is 2.8x SLOWER per solve (0.74 vs 0.26
+                          ms at 200 poses): its per-pivot chain (publish -> __syncwarp -> load -> fp64 divide -> update) is longer
+                          than the single thread's register-resident one. Kept as a bit-identical cross-check. */
   int ring = 0;        /* solver prefetch ring: 0 = 10 rows (default), else 10 / 20 / 30 rows (TEBGPU_RING, experiments) */
   int eval_v1 = 0;     /* TEBGPU_EVAL_V1=1: first-generation trial evaluation (warp per trial, chunk per lane) */
   int ka_staged = 1;   /* kernel A output: 1 (default) shared-memory slot + TMA bulk store per lane, 0 direct 128-bit global stores */
@@ -425,13 +428,19 @@ static size_t eval_bytes(const tebgpu_ctx* ctx, int n_cap, int M_cap, int K) {
 static void launch_trial_eval(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int K, size_t smem, int it,
                               int round, int g, int tag, cudaStream_t st) {
   if (!ctx->eval_v1) { /* second generation: one lane per pose */
-    const bool wide = (long long)B * 2 <= 148; /* a CTA per band leaves SMs idle: give each band 16 warps */
+    const bool wide = (long long)B * 2 <= 148; /* a CTA per band leaves SMs idle: give each band up to 16 warps */
+    /* one warp per 30-pose tile of the longest band (2 .. 8 warps; 4 .. 16 in the wide variant: two trials side by side),
+     * so that the K x tiles warp tasks split evenly and nobody idles at the barrier */
+    int warps = ev2_tiles(db.n_cap);
+    warps = warps < 2 ? 2 : (warps > 8 ? 8 : warps);
+    if (wide) warps = 2 * warps;
+    const int nt = 32 * warps;
     if (kp.generic) {
-      if (wide) k_trial_eval2<true, 512><<<B, 512, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
-      else k_trial_eval2<true, 256><<<B, 256, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+      if (wide) k_trial_eval2<true, 512><<<B, nt, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+      else k_trial_eval2<true, 256><<<B, nt, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
     } else {
-      if (wide) k_trial_eval2<false, 512><<<B, 512, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
-      else k_trial_eval2<false, 256><<<B, 256, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+      if (wide) k_trial_eval2<false, 512><<<B, nt, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+      else k_trial_eval2<false, 256><<<B, nt, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
     }
     return;
   }

@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
   if (round > 0 && slot >= sp.cnt[g]) return;
   const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x; /* <= NT: as many warps as the band has 30-pose tiles, so that the K x tiles tasks split evenly */
   BandState* st = &db.state[b];
   if (!st->active) return;
   const int q0 = (round == 0) ? 0 : sp.qmax[b];
@@ -602,11 +603,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
   const int M = db.obst_count[sc];
   {
     const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
-    for (int m = tid; m < M; m += NT) so[m] = go[m];
+    for (int m = tid; m < M; m += nthreads) so[m] = go[m];
     const double* gP = db.poses + (size_t)b * db.n_cap * 4;
     const double* grhs = db.rhs + (size_t)b * 4 * db.n_cap;
     /* the K trial solutions of a band sit in adjacent lanes of the solver's interleaved scratch (K even) */
-    for (int r = tid; r < N; r += NT) {
+    for (int r = tid; r < N; r += nthreads) {
       sP0[r] = gP[r];
       sB[r] = grhs[r];
       for (int kk = 0; kk < SPEC_K; kk += 2) {
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
   const int kact = min(SPEC_K, 10 - q0); /* trials of this round that exist (g2o stops after 10) */
   const double* vs = db.vel_start + 4 * (size_t)b;
   const double* vg = db.vel_goal + 4 * (size_t)b;
-  for (int task = warp; task < kact * tiles; task += NT / 32) {
+  for (int task = warp; task < kact * tiles; task += nthreads / 32) {
     const int k = task / tiles, tile = task - k * tiles;
     const int i = tile * EV2_TILE + lane;
     const double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
     double* gP = db.poses + (size_t)b * db.n_cap * 4;
     const double* adx = sdx + (size_t)accepted * 4 * db.n_cap;
     const bool ok = sRes[accepted * RES_STRIDE + 5] != 0.0;
-    for (int r = tid; r < N; r += NT) {
+    for (int r = tid; r < N; r += nthreads) {
       if (!row_is_real(r, n)) continue;
       const double dxv = ok ? adx[r] : sB[r];
       const double xv = sP0[r] + dxv;
