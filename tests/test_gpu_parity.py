@@ -408,9 +408,8 @@ def test_shape_obstacles_and_footprints(oracle, footprint, legacy, vor):
     oracle.optimize_batch(p, ha, args, jac_mode=oracle.JAC_ANALYTIC, threads=8)
     assert np.array_equal(hg.n, ha.n)
     d = _pose_diff(hg, ha)
-    # a closest-feature switch (vertex <-> edge) is a kink of the distance: a band that sits on one may take another
-    # LM branch after a last-bit difference; all others agree to 1e-6
-    assert np.median(d) < 1e-8 and (d < 1e-6).mean() >= 0.8, d
+    print("shape parity", footprint, legacy, vor, "max", d.max(), "bands > 1e-6:", np.where(d > 1e-6)[0].tolist())
+    assert d.max() < 1e-6, d
     assert np.all(hg.status & abi.TEB_STATUS_OPTIMIZED)
 
 
