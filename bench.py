@@ -44,16 +44,23 @@ def parse():
     ap.add_argument("--cpu-reps", type=int, default=None, help="timed repetitions of the CPU sample (default: 20 for "
                     "--impl reference as BASELINE.md par. 2 asks, 5 for the cpu_baseline leg of the GPU arm)")
     ap.add_argument("--no-single-request", action="store_true")
+    ap.add_argument("--total-bands", type=int, default=None, help="STRONG scaling: this many bands in total, split evenly over "
+                    "the GPUs (BASELINE config 4: --workload C4 --total-bands 512 --gpus 4); overrides --requests")
     return ap.parse_args()
 
 
 def make_workload(a, rank):
     n, M, cand, inflated, moving, via_pts = scenes.CONFIG_SHAPES[a.workload]
+    world = max(1, int(os.environ.get("WORLD_SIZE", "1"))) if a.impl == "b200" else 1
     cand = a.candidates or (32 if a.workload in ("C1",) else cand)
     if a.workload == "C3" and a.candidates is None:
         cand = 32  # north-star scene: 200 poses / 64 obstacles / 32 candidates
     if a.workload == "C4" and a.candidates is None:
         cand = 32
+    if a.total_bands:   # strong scaling: the job is fixed, every rank takes its share of the requests
+        if a.total_bands % (cand * world):
+            raise SystemExit(f"--total-bands {a.total_bands} is not a multiple of candidates x GPUs = {cand} x {world}")
+        a.requests = a.total_bands // (cand * world)
     p = scenes.config_params(a.workload)
     p.teb_autosize = 0  # throughput runs use fixed n; autosize parity is covered by tests/
     hb = scenes.make_batch(n, M, cand, a.requests, seed=1000 + rank, inflated=inflated, moving=moving,
@@ -66,6 +73,8 @@ def make_workload(a, rank):
                         f"{p.no_inner_iterations} LM iterations, teb_autosize=false",
             "n_poses": n, "n_obstacles": M, "candidates": cand, "requests_per_gpu": a.requests,
             "bands_per_gpu": hb.B, "via_points": via_pts}
+    if a.total_bands:
+        desc["total_bands"] = a.total_bands
     return p, hb, args, desc, cand
 
 
@@ -521,7 +530,7 @@ def run_b200(a, rank, local_rank, world):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if a.total_bands else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": dict(desc, l2="flushed between timed steps (256 MB memset)", timing="CUDA events per step on the launching stream, max over ranks"),
                 "lm_iters_per_s": lm_iters_step / (ms_per_step * 1e-3),

@@ -256,11 +256,16 @@ int32_t tebgpu_set_linearize_variant(tebgpu_ctx* ctx, int32_t variant);
  * Results do not depend on it (the accept / reject chain is replayed in order), only latency and traffic do. */
 int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k);
 
-/* Mapping of the default solver's solve kernel: 0 (default) one THREAD per (band, trial) system (k_solve_tpb), 1 one WARP
- * per system (k_solve_warp: window spread over the lanes, pivot column through shared memory, axpy back substitution),
- * 2 the warp mapping while a round has at most 148 x 8 systems. Factors and solutions of the two mappings are
- * bit-identical; the warp mapping measured 2.8x slower per solve on B200 (profiles/r2_history.md) and is kept as an
- * independent cross-check of the factorisation. */
+/* Mapping of the default solver's solve kernel (replaces LinearSolverCSparse::solve, optimal_planner.cpp:169-172):
+ *   0  one THREAD per (band, trial) system (k_solve_tpb) always - the throughput mapping;
+ *   1  one WARP per system (k_solve_warp: window spread over the lanes, pivot column through shared memory, axpy back
+ *      substitution), 2 the same only while a round has at most 148 x 8 systems. Bit-identical to mode 0, measured 2.8x
+ *      slower per solve on B200 (profiles/r2_history.md); kept as an independent cross-check of the factorisation;
+ *   3  k_solve_lat always: one warp per system, the system resident in shared memory, TWISTED factorisation (the two
+ *      half-warps eliminate from both ends towards an 11-unknown middle block), 2.6x faster per solve than mode 0 when
+ *      the machine is not full; another elimination order, so results agree with mode 0 to rounding, not bit for bit;
+ *   4  (default) k_solve_lat while the systems of a round fit two waves of resident CTAs - the latency regime of a
+ *      single planning request - and k_solve_tpb above that. */
 int32_t tebgpu_set_warp_solver(tebgpu_ctx* ctx, int32_t mode);
 
 /* CUDA-graph replay of the launch sequence of tebgpu_optimize_batch(_device): 0 never, 1 always, 2 (default) in the

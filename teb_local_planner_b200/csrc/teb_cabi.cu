@@ -15,6 +15,7 @@
 #include "teb_linearize.cuh"
 #include "teb_spec.cuh"
 #include "teb_solve_warp.cuh"
+#include "teb_solve_lat.cuh"
 #include "teb_hsig.cuh"
 #include "teb_comm.h"
 #include <cstdlib>
@@ -46,10 +47,12 @@ struct tebgpu_ctx {
   uint64_t graph_clock = 0;
   uint64_t params_version = 0;        /* bumped by tebgpu_set_params: part of the graph key */
   int graph_mode = 2;                 /* 0 never, 1 always, 2 automatic (latency regime only) */
-  int warp_solver = 0; /* solver 2, solve kernel: 0 thread per system (default), 1 warp per system, 2 warp per system in the
-                          latency regime (TEBGPU_WARP_SOLVER). Measured: the warp mapping is 2.8x SLOWER per solve (0.74 vs 0.26
-                          ms at 200 poses): its per-pivot chain (publish -> __syncwarp -> load -> fp64 divide -> update) is longer
-                          than the single thread's register-resident one. Kept as a bit-identical cross-check. */
+  int warp_solver = 4; /* solver 2, solve kernel (TEBGPU_WARP_SOLVER / tebgpu_set_warp_solver):
+                          0 thread per system (k_solve_tpb) always,
+                          1 / 2 k_solve_warp always / in the latency regime - measured 2.8x SLOWER per solve than k_solve_tpb,
+                            kept as an independently mapped, bit-identical implementation,
+                          3 / 4 k_solve_lat (twisted factorisation, system resident in shared memory) always / while the
+                            systems of a round fit LAT_WAVES waves of resident CTAs (the latency regime; DEFAULT) */
   int ring = 0;        /* solver prefetch ring: 0 = 10 rows (default), else 10 / 20 / 30 rows (TEBGPU_RING, experiments) */
   int eval_v1 = 0;     /* TEBGPU_EVAL_V1=1: first-generation trial evaluation (warp per trial, chunk per lane) */
   int ka_staged = 1;   /* kernel A output: 1 (default) shared-memory slot + TMA bulk store per lane, 0 direct 128-bit global stores */
@@ -327,7 +330,9 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<30>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpb_ring_bytes(20)));
   CUDA_TRY(c, cudaFuncSetAttribute(k_solve_tpb<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, tpb_ring_bytes(30)));
-  if (const char* e = std::getenv("TEBGPU_WARP_SOLVER")) { const int m = std::atoi(e); if (m >= 0 && m <= 2) c->warp_solver = m; }
+  CUDA_TRY(c, cudaFuncSetAttribute(k_solve_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  if (const char* e = std::getenv("TEBGPU_LAT_TIMING")) { const int v = std::atoi(e); CUDA_TRY(c, cudaMemcpyToSymbol(g_lat_timing, &v, sizeof(int))); }
+  if (const char* e = std::getenv("TEBGPU_WARP_SOLVER")) { const int m = std::atoi(e); if (m >= 0 && m <= 4) c->warp_solver = m; }
   if (const char* e = std::getenv("TEBGPU_GRAPH")) { const int m = std::atoi(e); if (m >= 0 && m <= 2) c->graph_mode = m; }
   if (const char* e = std::getenv("TEBGPU_RING")) { const int r = std::atoi(e); if (r == 10 || r == 20 || r == 30) c->ring = r; }
   CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -633,6 +638,13 @@ static int32_t issue_optimize(tebgpu_ctx* ctx, const TebBatch* bt, const TebOpti
             const int ring = ctx->ring == 0 ? 10 : ctx->ring;
             /* latency regime: one WARP per system (k_solve_warp) while all systems of the round fit a few warps per SM */
             const bool warp_solver = ctx->warp_solver == 1 || (ctx->warp_solver == 2 && bk <= 148 * 8);
+            const size_t smem_lat = solve_lat_smem_bytes(bt->n_cap);
+            /* automatic: while the round's systems fit two waves of resident CTAs (one warp + its whole system per CTA) the
+             * twisted solver's ~0.1 ms per wave beats the 0.26 ms a thread-per-system solve takes regardless of the count */
+            const long long lat_wave = smem_lat <= 232448 ? 148LL * (232448 / smem_lat > 16 ? 16 : 232448 / smem_lat) : 0;
+            const bool lat_solver = lat_wave > 0 && (ctx->warp_solver == 3 || (ctx->warp_solver == 4 && bk <= LAT_WAVES * lat_wave));
+            if (lat_solver) k_solve_lat<<<bk, 32, smem_lat, rs>>>(db, ctx->spec, it, round, g);
+            else
             if (warp_solver) k_solve_warp<<<(bk + SW_WARPS - 1) / SW_WARPS, 32 * SW_WARPS, 0, rs>>>(db, ctx->spec, it, round, g);
             else
             if (ring == 30) k_solve_tpb<30><<<warps, 32, tpb_ring_bytes(30), rs>>>(db, ctx->spec, it, round, g);
@@ -757,7 +769,7 @@ int32_t tebgpu_optimize_batch_device(tebgpu_ctx* ctx, const TebBatch* bt, const 
 }
 
 int32_t tebgpu_set_warp_solver(tebgpu_ctx* ctx, int32_t mode) {
-  if (!ctx || mode < 0 || mode > 2) return TEBGPU_ERR_INVALID_ARG;
+  if (!ctx || mode < 0 || mode > 4) return TEBGPU_ERR_INVALID_ARG;
   ctx->warp_solver = mode;
   return TEBGPU_OK;
 }
