@@ -41,6 +41,8 @@ struct tebgpu_ctx {
                                  1: k_linearize, first generation: 128-thread CTA per 32-pose tile, thread per band row */
   ncclComm_t comm = nullptr;          /* cost all-gather across the ranks of a sharded batch (tebgpu_comm_init) */
   int world = 1, rank = 0;
+  int32_t* arrive = nullptr;          /* [max_bands] k_trial_eval3: CTAs of a band that have published their trial (0 between rounds) */
+  int eval_mode = 2;                  /* 2 automatic (k_trial_eval3 in the latency regime), 0 k_trial_eval2 always, 1 k_trial_eval3 always (TEBGPU_EVAL3) */
   double* d_gather = nullptr;         /* [world][max_bands] gathered costs of the host-buffer entry point */
   struct GraphEntry { uint64_t key = 0; cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t stamp = 0; int spec_k = 0, spec_first = 0; };
   std::vector<GraphEntry> graphs;     /* captured launch sequences (tebgpu_set_graph) */
@@ -192,7 +194,7 @@ int64_t tebgpu_get_info(const tebgpu_ctx* ctx, int32_t which) {
 }
 
 static void free_all(tebgpu_ctx* c) {
-  void* ptrs[] = {c->d_gather, c->d_hsig, c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->d_fp, c->d_pverts, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+  void* ptrs[] = {c->arrive, c->d_gather, c->d_hsig, c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->d_fp, c->d_pverts, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
                   c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
                   c->d_status, c->d_iters};
   for (void* p : ptrs)
@@ -248,6 +250,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
     CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
     CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
     CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev));
+    if (const char* e = std::getenv("TEBGPU_EVAL3")) { const int m = std::atoi(e); if (m >= 0 && m <= 2) c->eval_mode = m; }
     if (const char* e = std::getenv("TEBGPU_EVAL_MINB")) c->eval_minb = std::atoi(e) == 3 ? 3 : 2;
     if (const char* e = std::getenv("TEBGPU_EVAL_V1")) c->eval_v1 = std::atoi(e) != 0;
     size_t ev2 = eval2_smem_bytes((int)nc, (int)M, SPEC_K_MAX);
@@ -257,6 +260,10 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval2<G, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     EV2_ATTR(false, 256) EV2_ATTR(true, 256) EV2_ATTR(false, 512) EV2_ATTR(true, 512)
 #undef EV2_ATTR
+    size_t ev3 = eval3_smem_bytes((int)nc, (int)M, SPEC_K_MAX);
+    if (ev3 > 232448) ev3 = 232448;
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev3));
+    CUDA_TRY(c, cudaFuncSetAttribute(k_trial_eval3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ev3));
   }
   const size_t spec_sys = ((B * SPEC_K_MAX + 31) / 32) * 32; /* whole warps of (band, trial) systems */
   CUDA_TRY(c, cudaMalloc(&c->spec.Lf, spec_sys * 4 * nc * HROW * sizeof(double)));
@@ -265,6 +272,8 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaMalloc(&c->spec.list, 3 * B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->defer, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.res, B * SPEC_K_MAX * RES_STRIDE * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->arrive, B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMemset(c->arrive, 0, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.need, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.qmax, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->d_poses, B * nc * 4 * sizeof(double)));
@@ -432,6 +441,16 @@ static size_t eval_bytes(const tebgpu_ctx* ctx, int n_cap, int M_cap, int K) {
 }
 static void launch_trial_eval(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int K, size_t smem, int it,
                               int round, int g, int tag, cudaStream_t st) {
+  /* latency regime: a CTA per (band, trial) instead of a CTA per band while that still fits ~3 CTAs per SM */
+  const size_t smem3 = eval3_smem_bytes(db.n_cap, db.M_cap, K);
+  if (!ctx->eval_v1 && smem3 <= 232448 && (ctx->eval_mode == 1 || (ctx->eval_mode == 2 && (long long)B * K <= 148 * 3))) {
+    int warps = ev2_tiles(db.n_cap);
+    warps = warps < 1 ? 1 : (warps > 16 ? 16 : warps);
+    const dim3 grid(K, B);
+    if (kp.generic) k_trial_eval3<true><<<grid, 32 * warps, smem3, st>>>(db, kp, ctx->spec, it, round, g, tag, ctx->arrive);
+    else k_trial_eval3<false><<<grid, 32 * warps, smem3, st>>>(db, kp, ctx->spec, it, round, g, tag, ctx->arrive);
+    return;
+  }
   if (!ctx->eval_v1) { /* second generation: one lane per pose */
     const bool wide = (long long)B * 2 <= 148; /* a CTA per band leaves SMs idle: give each band up to 16 warps */
     /* one warp per 30-pose tile of the longest band (2 .. 8 warps; 4 .. 16 in the wide variant: two trials side by side),
@@ -713,7 +732,7 @@ static uint64_t graph_key(const tebgpu_ctx* ctx, const TebBatch* bt, const TebOp
   mix(bt, sizeof(*bt));
   mix(a, sizeof(*a));
   mix(&ctx->params_version, sizeof(ctx->params_version));
-  const int sw[9] = {ctx->solver, ctx->spec_k, ctx->linearize_variant, ctx->ka_staged, ctx->eval_v1, ctx->ring, ctx->overlap, ctx->eval_minb, ctx->warp_solver};
+  const int sw[10] = {ctx->solver, ctx->spec_k, ctx->linearize_variant, ctx->ka_staged, ctx->eval_v1, ctx->ring, ctx->overlap, ctx->eval_minb, ctx->warp_solver, ctx->eval_mode};
   mix(sw, sizeof(sw));
   mix(&st, sizeof(st));
   return h;

@@ -575,6 +575,53 @@ __device__ __forceinline__ void pose_chi2_lane(const KParams& kp, const DevBatch
   unary_terms<GEOM>(kp, db, b, sc, i, n, xa, ya, ca, sa, so, M, false, U, ub, chi[0], chi[1]);
 }
 
+/* One (trial, 30-pose tile) task of a warp: lane -> pose i = tile * 30 + lane (lanes 30, 31 are the halo). Forms the trial
+ * state x [+] dx of its pose, gets the right neighbour's by shuffles, evaluates every cost term anchored at the pose and
+ * returns the warp sums: chi2 by family and the computeScale() part of the owned rows. Shared by k_trial_eval2 / 3. */
+template <bool GEOM>
+__device__ __forceinline__ void eval_tile_task(const KParams& kp, const DevBatch& db, int b, int sc, int n, int tile, int lane, bool ok,
+                                               double lambda, const double* mydx, const double* sP0, const double* sB,
+                                               const TebObstacle* so, int M, const double* vs, const double* vg, double (&chi)[4],
+                                               double& scl) {
+  const int i = tile * EV2_TILE + lane;
+  chi[0] = chi[1] = chi[2] = chi[3] = 0;
+  scl = 0;
+  double x = 0, y = 0, th = 0, dt = 1, ca = 1, sa = 0;
+  SegVal s1;
+  s1.v = 0; s1.w = 0; s1.vx = 0; s1.vy = 0;
+  const bool have = i < n;
+  const bool own = have && lane < EV2_TILE;
+  if (have) { /* trial state x [+] dx (VertexPose::oplusImpl / VertexTimeDiff::oplusImpl), computeScale() on the owned rows */
+    double v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int r = 4 * i + c;
+      double xv = sP0[r];
+      if (row_is_real(r, n)) {
+        const double bb = sB[r];
+        const double dxv = ok ? mydx[r] : bb; /* CSparse leaves x = b when the factorisation fails */
+        if (own) scl += dxv * (lambda * dxv + bb);
+        xv = (c == 2) ? normalize_theta(xv + dxv) : xv + dxv;
+      }
+      v[c] = xv;
+    }
+    x = v[0]; y = v[1]; th = v[2]; dt = v[3];
+    sincos(th, &sa, &ca);
+  }
+  /* pose i+1 from the right neighbour */
+  const double xb = __shfl_down_sync(0xffffffffu, x, 1), yb = __shfl_down_sync(0xffffffffu, y, 1);
+  const double thb = __shfl_down_sync(0xffffffffu, th, 1), dtb = __shfl_down_sync(0xffffffffu, dt, 1);
+  const double cb = __shfl_down_sync(0xffffffffu, ca, 1), sb = __shfl_down_sync(0xffffffffu, sa, 1);
+  if (have && i <= n - 2 && lane < 31) s1 = seg_value(kp, x, y, th, ca, sa, xb, yb, thb, dt);
+  SegVal s2;
+  s2.v = __shfl_down_sync(0xffffffffu, s1.v, 1); s2.w = __shfl_down_sync(0xffffffffu, s1.w, 1);
+  s2.vx = __shfl_down_sync(0xffffffffu, s1.vx, 1); s2.vy = __shfl_down_sync(0xffffffffu, s1.vy, 1);
+  if (own) pose_chi2_lane<GEOM>(kp, db, b, sc, i, n, x, y, th, dt, ca, sa, xb, yb, thb, dtb, cb, sb, s1, s2, so, M, vs, vg, chi);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) chi[c] = warp_sum(chi[c]);
+  scl = warp_sum(scl);
+}
+
 template <bool GEOM, int NT> /* NT = 256 (throughput regime, 2 CTAs per SM) or 512 (latency regime: more warps per band) */
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp,
                                                              const __grid_constant__ SpecBufs sp, int iteration, int round,
@@ -624,47 +671,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
   const double* vg = db.vel_goal + 4 * (size_t)b;
   for (int task = warp; task < kact * tiles; task += nthreads / 32) {
     const int k = task / tiles, tile = task - k * tiles;
-    const int i = tile * EV2_TILE + lane;
     const double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
-    const bool ok = res[5] != 0.0;
-    const double lambda = res[6];
-    const double* mydx = sdx + (size_t)k * 4 * db.n_cap;
-    double chi[4] = {0, 0, 0, 0};
-    double scl = 0;
-    double x = 0, y = 0, th = 0, dt = 1, ca = 1, sa = 0;
-    SegVal s1;
-    s1.v = 0; s1.w = 0; s1.vx = 0; s1.vy = 0;
-    const bool have = i < n;
-    const bool own = have && lane < EV2_TILE;
-    if (have) { /* trial state x [+] dx (VertexPose::oplusImpl / VertexTimeDiff::oplusImpl), computeScale() on the owned rows */
-      double v[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int r = 4 * i + c;
-        double xv = sP0[r];
-        if (row_is_real(r, n)) {
-          const double bb = sB[r];
-          const double dxv = ok ? mydx[r] : bb; /* CSparse leaves x = b when the factorisation fails */
-          if (own) scl += dxv * (lambda * dxv + bb);
-          xv = (c == 2) ? normalize_theta(xv + dxv) : xv + dxv;
-        }
-        v[c] = xv;
-      }
-      x = v[0]; y = v[1]; th = v[2]; dt = v[3];
-      sincos(th, &sa, &ca);
-    }
-    /* pose i+1 from the right neighbour */
-    const double xb = __shfl_down_sync(0xffffffffu, x, 1), yb = __shfl_down_sync(0xffffffffu, y, 1);
-    const double thb = __shfl_down_sync(0xffffffffu, th, 1), dtb = __shfl_down_sync(0xffffffffu, dt, 1);
-    const double cb = __shfl_down_sync(0xffffffffu, ca, 1), sb = __shfl_down_sync(0xffffffffu, sa, 1);
-    if (have && i <= n - 2 && lane < 31) s1 = seg_value(kp, x, y, th, ca, sa, xb, yb, thb, dt);
-    SegVal s2;
-    s2.v = __shfl_down_sync(0xffffffffu, s1.v, 1); s2.w = __shfl_down_sync(0xffffffffu, s1.w, 1);
-    s2.vx = __shfl_down_sync(0xffffffffu, s1.vx, 1); s2.vy = __shfl_down_sync(0xffffffffu, s1.vy, 1);
-    if (own) pose_chi2_lane<GEOM>(kp, db, b, sc, i, n, x, y, th, dt, ca, sa, xb, yb, thb, dtb, cb, sb, s1, s2, so, M, vs, vg, chi);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) chi[c] = warp_sum(chi[c]);
-    scl = warp_sum(scl);
+    double chi[4], scl;
+    eval_tile_task<GEOM>(kp, db, b, sc, n, tile, lane, res[5] != 0.0, res[6], sdx + (size_t)k * 4 * db.n_cap, sP0, sB, so, M, vs, vg,
+                         chi, scl);
     if (lane == 0) {
       double* pp = sPart + ((size_t)k * ev2_tiles(db.n_cap) + tile) * 5;
       pp[0] = chi[0]; pp[1] = chi[1]; pp[2] = chi[2]; pp[3] = chi[3]; pp[4] = scl;
@@ -703,6 +713,126 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
     for (int r = tid; r < N; r += nthreads) {
       if (!row_is_real(r, n)) continue;
       const double dxv = ok ? adx[r] : sB[r];
+      const double xv = sP0[r] + dxv;
+      gP[r] = ((r & 3) == 2) ? normalize_theta(xv) : xv;
+    }
+  }
+}
+
+/* ====================================================================================================================
+ * k_trial_eval3 — the trial evaluation of the LATENCY regime (one planning request: a few dozen bands). k_trial_eval2
+ * gives a band ONE CTA, i.e. 32 candidates keep 32 of the 148 SMs busy for 33 us. Here a CTA owns one (band, trial)
+ * pair - grid (K, bands), one warp per 30-pose tile - so a request spreads over the whole chip; the per-trial chi2 /
+ * scale go to sp.res in global memory and the LAST CTA of a band to arrive (one atomic counter per band) replays the
+ * accept / reject chain and commits the accepted trial, reading its dx back from the solver's scratch.
+ * Same tile tasks, same fold order, same spec_decide as k_trial_eval2: the results are bit-identical.
+ * ==================================================================================================================== */
+__host__ __device__ inline size_t eval3_smem_bytes(int n_cap, int M_cap, int K) {
+  return (size_t)3 * 4 * n_cap * sizeof(double) + (size_t)(M_cap > 0 ? M_cap : 1) * sizeof(TebObstacle) +
+         ((size_t)ev2_tiles(n_cap) * 5 + (size_t)K * RES_STRIDE) * sizeof(double) + 64;
+}
+
+template <bool GEOM>
+__global__ void __launch_bounds__(512, 1) k_trial_eval3(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp,
+                                                        const __grid_constant__ SpecBufs sp, int iteration, int round, int g,
+                                                        int tag, int32_t* arrive) {
+  extern __shared__ __align__(16) unsigned char ev_raw[];
+  const int SPEC_K = sp.K;
+  const int k = blockIdx.x, slot = blockIdx.y;
+  if (round > 0 && slot >= sp.cnt[g]) return;
+  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x;
+  BandState* st = &db.state[b];
+  if (!st->active) return;
+  const int q0 = (round == 0) ? 0 : sp.qmax[b];
+  const int kact = min(SPEC_K, 10 - q0); /* trials of this round that exist (g2o stops after 10) */
+  if (k >= kact) return;
+  const int n = db.n[b];
+  const int N = 4 * n;
+  const int tiles = (n + EV2_TILE - 1) / EV2_TILE;
+  double* sdx = reinterpret_cast<double*>(ev_raw);            /* [4 n_cap] this trial's solution */
+  double* sP0 = sdx + (size_t)4 * db.n_cap;                    /* [n_cap][4] current band */
+  double* sB = sP0 + (size_t)4 * db.n_cap;                     /* [4 n_cap] right-hand side */
+  double* sPart = sB + (size_t)4 * db.n_cap;                   /* [tiles(n_cap)][5] tile partials: chi by family, scale */
+  double* sRes = sPart + (size_t)ev2_tiles(db.n_cap) * 5;      /* [K][RES_STRIDE], filled by the deciding CTA */
+  int* sAcc = reinterpret_cast<int*>(sRes + (size_t)SPEC_K * RES_STRIDE);
+  TebObstacle* so = reinterpret_cast<TebObstacle*>(sAcc + 4);
+  const int sc = db.scene_id[b];
+  const int M = db.obst_count[sc];
+  double* gP = db.poses + (size_t)b * db.n_cap * 4;
+  auto dx_of = [&](int kk) { /* trial kk's solution in the solver's interleaved scratch: + r * 32 */
+    const int tsys = slot * SPEC_K + kk;
+    return sp.dx + (size_t)(tsys >> 5) * 32 * 4 * db.n_cap + (tsys & 31);
+  };
+  {
+    const TebObstacle* go = db.obstacles + (size_t)sc * db.M_cap;
+    for (int m = tid; m < M; m += nthreads) so[m] = go[m];
+    const double* grhs = db.rhs + (size_t)b * 4 * db.n_cap;
+    const double* gdx = dx_of(k);
+    for (int r = tid; r < N; r += nthreads) {
+      sP0[r] = gP[r];
+      sB[r] = grhs[r];
+      sdx[r] = gdx[(size_t)r * 32];
+    }
+  }
+  __syncthreads();
+  const double* vs = db.vel_start + 4 * (size_t)b;
+  const double* vg = db.vel_goal + 4 * (size_t)b;
+  double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
+  {
+    const bool ok = res[5] != 0.0;
+    const double lambda = res[6];
+    for (int tile = warp; tile < tiles; tile += nthreads / 32) {
+      double chi[4], scl;
+      eval_tile_task<GEOM>(kp, db, b, sc, n, tile, lane, ok, lambda, sdx, sP0, sB, so, M, vs, vg, chi, scl);
+      if (lane == 0) {
+        double* pp = sPart + (size_t)tile * 5;
+        pp[0] = chi[0]; pp[1] = chi[1]; pp[2] = chi[2]; pp[3] = chi[3]; pp[4] = scl;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) { /* fold the tile partials in tile order, publish, arrive */
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int t = 0; t < tiles; ++t) {
+#pragma unroll
+      for (int c = 0; c < 5; ++c) a[c] += sPart[(size_t)t * 5 + c];
+    }
+#pragma unroll
+    for (int c = 0; c < 5; ++c) __stcg(res + c, a[c]);
+    __threadfence();
+    const int old = atomicAdd(arrive + b, 1);
+    sAcc[1] = (old == kact - 1);
+  }
+  __syncthreads();
+  if (!sAcc[1]) return;
+  /* ---- the last CTA of the band: accept / reject replay, sequential over the K trials */
+  __threadfence();
+  if (tid < kact * RES_STRIDE) { /* L2 reads: the other trials' rows were written by other SMs */
+    const int kk = tid / RES_STRIDE, c = tid - kk * RES_STRIDE;
+    sRes[kk * RES_STRIDE + c] = __ldcg(sp.res + ((size_t)b * SPEC_K + kk) * RES_STRIDE + c);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    arrive[b] = 0; /* ready for the next round (stream order) */
+    DecideArgs da;
+    da.st = st; da.chi_parts = db.chi_parts + (size_t)b * db.chunks * 4;
+    da.lambda_init = (round == 0 && iteration == 0) ? band_lambda_init(db, b, n) : 0.0;
+    da.need = sp.need + b; da.qmax = sp.qmax + b; da.cnt_next = sp.cnt + g + 1;
+    da.list_next = sp.list + (size_t)((g + 1) % 3) * db.B;
+    da.defer = db.defer + b; da.tag = tag;
+    da.b = b; da.n = n; da.K = SPEC_K; da.iteration = iteration; da.round = round; da.q0 = q0; da.tile = db.tile;
+    sAcc[0] = spec_decide(da, sRes);
+  }
+  __syncthreads();
+  const int accepted = sAcc[0];
+  if (accepted >= 0) { /* discardTop(): the accepted trial state becomes the band (same arithmetic as the tile tasks) */
+    const double* adx = dx_of(accepted);
+    const bool ok = sRes[accepted * RES_STRIDE + 5] != 0.0;
+    for (int r = tid; r < N; r += nthreads) {
+      if (!row_is_real(r, n)) continue;
+      const double dxv = ok ? __ldcg(adx + (size_t)r * 32) : sB[r];
       const double xv = sP0[r] + dxv;
       gP[r] = ((r & 3) == 2) ? normalize_theta(xv) : xv;
     }

@@ -266,3 +266,29 @@ def test_short_bands_with_both_solvers(oracle, mode):
         # chi2 EXACTLY equal to the current one), a tie that the last bit decides; the trajectories then agree to 1e-8
         same = hg.lm_iters == ha.lm_iters
         assert np.all(same | (d < 1e-8)), (n, hg.lm_iters, ha.lm_iters, d)
+
+
+@pytest.mark.parametrize("cfg,autosize,cands", [("C1", True, 8), ("C3", False, 32), ("C4", True, 24), ("shapes", False, 0)])
+def test_per_trial_evaluation_kernel_is_bit_identical(cfg, autosize, cands, monkeypatch):
+    """k_trial_eval3 (a CTA per (band, trial), last CTA of a band decides) against k_trial_eval2 (a CTA per band): same tile
+    tasks, same fold order, same accept / reject replay - every output must agree bit for bit, retry rounds included
+    (speculation width 2 makes them frequent)"""
+    if cfg == "shapes":
+        p, hb0 = scenarios.scenario("shapes_polygon")
+    else:
+        p, hb0 = scenes.make_config_batch(cfg, candidates=cands, seed=31, autosize=autosize)
+    args = _args(p)
+    outs = {}
+    for spec in (0, 2):
+        for mode in ("0", "1"):
+            monkeypatch.setenv("TEBGPU_EVAL3", mode)
+            g = _gpu(hb0, p)
+            g.set_speculation(spec)
+            h = hb0.copy()
+            g.optimize(h, args)
+            g.close()
+            outs[(spec, mode)] = h
+    ref = outs[(0, "0")]
+    for key, h in outs.items():
+        assert np.array_equal(ref.n, h.n) and np.array_equal(ref.lm_iters, h.lm_iters) and np.array_equal(ref.status, h.status), key
+        assert np.array_equal(ref.poses, h.poses) and np.array_equal(ref.cost, h.cost), key
