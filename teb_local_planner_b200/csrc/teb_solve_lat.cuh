@@ -41,7 +41,7 @@ namespace tebgpu {
 constexpr int LAT_WAVES = 2;          /* automatic mode: k_solve_lat replaces k_solve_tpb while a round fits this many waves */
 constexpr int SL_REC = 24;            /* published pivot column: d, c_1 .. c_10 at [0..10], zeros at [11..21], y at [22] */
 constexpr int SL_CB = 2 * 2 * SL_REC; /* [half][buffer] */
-constexpr int SL_SPECIAL = 2 * HROW;  /* an all-zero column and an identity column */
+constexpr int SL_SPECIAL = 2 * HROW + SL_REC; /* an all-zero column, an identity column, the dummy record of the non-owners */
 constexpr int SL_MID = 11 * HROW;     /* the bottom sweep's contribution to the middle block */
 __host__ __device__ constexpr size_t solve_lat_smem_bytes(int n_cap) {
   return ((size_t)4 * n_cap * HROW + SL_CB + SL_SPECIAL + SL_MID) * sizeof(double) + 16;
@@ -85,19 +85,21 @@ __device__ __forceinline__ void ld_column_pred(uint32_t addr, double (&c)[11], d
       : "r"(addr), "r"((int)p)
       : "memory");
 }
-/* publish a pivot column: d, c_1 .. c_10 (and a zero) at [0..11], y at [22] */
-__device__ __forceinline__ void st_record_pred(uint32_t addr, const double (&c)[11], double y, bool p) {
+/* publish a pivot column: d, c_1 .. c_10 (and a zero) at [0..11], y at [22]. UNCONDITIONAL: the lanes that are not the
+ * owner pass the address of a dummy record (same-address stores cost one wavefront). Seven predicated stores in a row get
+ * turned into a divergent branch by ptxas, which puts a reconvergence barrier and a WARPSYNC on the pivot chain. */
+__device__ __forceinline__ void st_record(uint32_t addr, const double (&c)[11], double y) {
   asm volatile(
-      "{ .reg .pred q; .reg .f64 z; setp.ne.b32 q, %13, 0; mov.f64 z, 0d0000000000000000;\n"
-      "@q st.shared.v2.f64 [%12], {%0, %1};\n"
-      "@q st.shared.v2.f64 [%12+16], {%2, %3};\n"
-      "@q st.shared.v2.f64 [%12+32], {%4, %5};\n"
-      "@q st.shared.v2.f64 [%12+48], {%6, %7};\n"
-      "@q st.shared.v2.f64 [%12+64], {%8, %9};\n"
-      "@q st.shared.v2.f64 [%12+80], {%10, z};\n"
-      "@q st.shared.f64 [%12+176], %11; }" ::"d"(c[0]),
+      "{ .reg .f64 z; mov.f64 z, 0d0000000000000000;\n"
+      "st.shared.v2.f64 [%12], {%0, %1};\n"
+      "st.shared.v2.f64 [%12+16], {%2, %3};\n"
+      "st.shared.v2.f64 [%12+32], {%4, %5};\n"
+      "st.shared.v2.f64 [%12+48], {%6, %7};\n"
+      "st.shared.v2.f64 [%12+64], {%8, %9};\n"
+      "st.shared.v2.f64 [%12+80], {%10, z};\n"
+      "st.shared.f64 [%12+176], %11; }" ::"d"(c[0]),
       "d"(c[1]), "d"(c[2]), "d"(c[3]), "d"(c[4]), "d"(c[5]), "d"(c[6]), "d"(c[7]), "d"(c[8]), "d"(c[9]), "d"(c[10]), "d"(y),
-      "r"(addr), "r"((int)p)
+      "r"(addr)
       : "memory");
 }
 /* ten consecutive elements of a published column and its y: one block, so that the loads are issued back to back and
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
   asm volatile("mov.u32 %0, %0;" : "+r"(hs_u32));
   const uint32_t cb_u32 = hs_u32 + (uint32_t)(4 * db.n_cap * HROW + h * 2 * SL_REC) * 8u;
   const uint32_t zero_u32 = hs_u32 + (uint32_t)(4 * db.n_cap * HROW + SL_CB) * 8u, ident_u32 = zero_u32 + HROW * 8;
+  const uint32_t dummy_u32 = ident_u32 + HROW * 8;
   /* address of column q (sweep coordinates) of this half: the unknown's row, or the identity / zero column once the
    * sweep has left its own block (top: q >= m + 11, bottom: unknown < m + 11) */
   auto col_addr = [&](int q) -> uint32_t {
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
     const int uC = (mm - s) & 15;
     const uint32_t cbt = cb_u32 + (uint32_t)(t & 1) * (SL_REC * 8);
     const double d = __shfl_sync(0xffffffffu, R[0], s | src_base);
-    st_record_pred(cbt, R, Ry, act && uC == 0);
+    st_record((act && uC == 0) ? cbt : dummy_u32, R, Ry);
     __syncwarp();
     const bool upd = act && uC >= 1 && uC <= 10;
     const int ui = upd ? uC : 0;
@@ -255,7 +258,41 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
     }
   };
 
-  for (int t = 0; t < m; ++t) step(t, h == 0 || t < T_bot);
+  /* Main part, unrolled by the ownership period of 16 steps: while both sweeps are active and the fetched column
+   * (t + 15) lies inside the sweep's own block, everything that depends on (t mod 16, lane) - roles, record offsets,
+   * the source lane of the shuffle - is a per-lane constant of the unrolled body, and the addresses of the fetched column
+   * and of the factor row advance by one row per step. That takes ~25 integer instructions per step off a lone,
+   * in-order warp. The remaining steps (< 16 + 15 at the end of the sweeps, the middle block) use the generic step. */
+  const int nblk = T_bot > 15 ? (T_bot - 15) / 16 : 0;
+  {
+    const uint32_t rstep = h ? (uint32_t)(-(HROW * 8)) : (uint32_t)(HROW * 8);
+    uint32_t colp = hs_u32 + (uint32_t)(h ? N - 1 - 15 : 15) * (HROW * 8);
+    uint32_t facp = hs_u32 + (uint32_t)(h ? N - 1 : 0) * (HROW * 8);
+    for (int blk = 0; blk < nblk; ++blk) {
+#pragma unroll
+      for (int S = 0; S < 16; ++S) {
+        const int uC = (mm - S) & 15;
+        const uint32_t cbt = cb_u32 + (uint32_t)(S & 1) * (SL_REC * 8);
+        const double d = __shfl_sync(0xffffffffu, R[0], S | src_base);
+        st_record(uC == 0 ? cbt : dummy_u32, R, Ry);
+        __syncwarp();
+        const bool upd = (unsigned)(uC - 1) < 10u;
+        double ck[10], yj;
+        ld_record(cbt + (uint32_t)(upd ? uC : 0) * 8u, cbt + 22 * 8, ck, yj);
+        ld_column_pred(colp, R, Ry, uC == 15);
+        colp += rstep;
+        neg_or |= __double2hiint(d);
+        const double inv = fast_rcp(d);
+        const double lq = upd ? ck[0] * inv : 0.0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) R[k] -= ck[k] * lq;
+        Ry -= yj * lq;
+        st_shared_pred(facp + (uint32_t)(uC <= 10 ? uC : 0) * 8u, (uC == 0) ? yj * inv : lq, uC <= 10);
+        facp += rstep;
+      }
+    }
+  }
+  for (int t = nblk * 16; t < m; ++t) step(t, h == 0 || t < T_bot);
 
   /* merge: the bottom window now holds the bottom sweep's contribution to the middle block (its columns
    * q' = T_bot .. T_bot + 10 are the unknowns m + 10 .. m); add it to the top window */

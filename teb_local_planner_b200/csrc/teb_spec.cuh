@@ -809,10 +809,8 @@ __global__ void __launch_bounds__(512, 1) k_trial_eval3(const __grid_constant__ 
   if (!sAcc[1]) return;
   /* ---- the last CTA of the band: accept / reject replay, sequential over the K trials */
   __threadfence();
-  if (tid < kact * RES_STRIDE) { /* L2 reads: the other trials' rows were written by other SMs */
-    const int kk = tid / RES_STRIDE, c = tid - kk * RES_STRIDE;
-    sRes[kk * RES_STRIDE + c] = __ldcg(sp.res + ((size_t)b * SPEC_K + kk) * RES_STRIDE + c);
-  }
+  for (int e = tid; e < kact * RES_STRIDE; e += nthreads) /* L2 reads: the other trials' rows were written by other SMs */
+    sRes[e] = __ldcg(sp.res + (size_t)b * SPEC_K * RES_STRIDE + e);
   __syncthreads();
   if (tid == 0) {
     arrive[b] = 0; /* ready for the next round (stream order) */
