@@ -102,6 +102,20 @@ __device__ __forceinline__ void st_record(uint32_t addr, const double (&c)[11], 
       "r"(addr)
       : "memory");
 }
+__device__ __forceinline__ void st_record_pred(uint32_t addr, const double (&c)[11], double y, bool p) {
+  asm volatile(
+      "{ .reg .pred q; .reg .f64 z; setp.ne.b32 q, %13, 0; mov.f64 z, 0d0000000000000000;\n"
+      "@q st.shared.v2.f64 [%12], {%0, %1};\n"
+      "@q st.shared.v2.f64 [%12+16], {%2, %3};\n"
+      "@q st.shared.v2.f64 [%12+32], {%4, %5};\n"
+      "@q st.shared.v2.f64 [%12+48], {%6, %7};\n"
+      "@q st.shared.v2.f64 [%12+64], {%8, %9};\n"
+      "@q st.shared.v2.f64 [%12+80], {%10, z};\n"
+      "@q st.shared.f64 [%12+176], %11; }" ::"d"(c[0]),
+      "d"(c[1]), "d"(c[2]), "d"(c[3]), "d"(c[4]), "d"(c[5]), "d"(c[6]), "d"(c[7]), "d"(c[8]), "d"(c[9]), "d"(c[10]), "d"(y),
+      "r"(addr), "r"((int)p)
+      : "memory");
+}
 /* ten consecutive elements of a published column and its y: one block, so that the loads are issued back to back and
  * land together instead of one by one in front of the multiply that needs them */
 __device__ __forceinline__ void ld_record(uint32_t addr, uint32_t yaddr, double (&c)[10], double& y) {
@@ -264,6 +278,7 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
    * and of the factor row advance by one row per step. That takes ~25 integer instructions per step off a lone,
    * in-order warp. The remaining steps (< 16 + 15 at the end of the sweeps, the middle block) use the generic step. */
   const int nblk = T_bot > 15 ? (T_bot - 15) / 16 : 0;
+  const int rt_zero = (int)special[0];   /* a zero the assembler cannot see through */
   {
     const uint32_t rstep = h ? (uint32_t)(-(HROW * 8)) : (uint32_t)(HROW * 8);
     uint32_t colp = hs_u32 + (uint32_t)(h ? N - 1 - 15 : 15) * (HROW * 8);
@@ -271,10 +286,10 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
     for (int blk = 0; blk < nblk; ++blk) {
 #pragma unroll
       for (int S = 0; S < 16; ++S) {
-        const int uC = (mm - S) & 15;
+        const int uC = (mm - S - rt_zero) & 15;
         const uint32_t cbt = cb_u32 + (uint32_t)(S & 1) * (SL_REC * 8);
         const double d = __shfl_sync(0xffffffffu, R[0], S | src_base);
-        st_record(uC == 0 ? cbt : dummy_u32, R, Ry);
+        st_record_pred(cbt, R, Ry, uC == 0);
         __syncwarp();
         const bool upd = (unsigned)(uC - 1) < 10u;
         double ck[10], yj;
