@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
    *   [11]. Done in chunks of 32 rows, ascending: a chunk reads rows of its own and the next chunk only. */
   {
     const int top_rows = m + 11;
-    for (int q0r = 0; q0r < N; q0r += 32) {
+    for (int q0r = 0; q0r < top_rows; q0r += 32) {
       const int q = q0r + lane;
       double v[11];
       const bool is_top = q < top_rows;
@@ -202,20 +202,17 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
         const double x = Hs[on ? (q + k) * HROW + k : 0];
         v[k] = on ? x : 0.0;
       }
-      const bool in = q < N;
-      const double dg = Hs[in ? q * HROW : 0];
-      if (!is_top) v[0] = dg;
-      if (in && row_is_real(q, n)) v[0] += lambda;
+      if (is_top && row_is_real(q, n)) v[0] += lambda;
       __syncwarp();
-      if (in) {
-        Hs[q * HROW] = v[0];
-        if (is_top) {
+      if (is_top) {
 #pragma unroll
-          for (int k = 1; k < 11; ++k) Hs[q * HROW + k] = v[k];
-        }
+        for (int k = 0; k < 11; ++k) Hs[q * HROW + k] = v[k];
       }
       __syncwarp();
     }
+    for (int q = top_rows + lane; q < N; q += 32)
+      if (row_is_real(q, n)) Hs[q * HROW] += lambda;
+    __syncwarp();
   }
 
   /* the shared-window base goes through an opaque move: otherwise the compiler re-derives it inside the loops (an S2R of the
@@ -339,75 +336,82 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
   const long long c_fact = clock64();
   __syncwarp();
 
-  /* ---- back substitution from the middle outwards.
-   * z / l of the row a lane needs in the NEXT step are loaded one step ahead: the dependent chain per step is
-   * shuffle + DFMA only. */
-  double acc = 0.0;
-  int brow = -1;                                /* bottom half: the row (sweep coordinate) next to the middle block */
+  /* ---- back substitution from the middle outwards, dot-product form: x_j = z_j - sum_u l_{j,u} x_{j+u}.
+   * No communication at all: every lane of a half-warp computes the same values (the factor rows are broadcast reads),
+   * all 32 lanes solve the middle block, then the top half walks down to unknown 0 and the bottom half up to N-1. The
+   * ten most recent solutions live in a register ring whose indices are static after unrolling by ten; the newest one
+   * enters the sum last, so the dependent chain per row is ONE FMA and a row costs its eleven fp64 instructions
+   * (~28 cycles) instead of shuffle + FMA + bookkeeping (~90 cycles in the axpy form this replaced). */
   {
-    const int back = (T_bot - 1 - mm) & 15;
-    const int q = T_bot - 1 - back;
-    const bool have = h == 1 && back <= 9 && q >= 0;
-    const double z = Hs[have ? (N - 1 - q) * HROW : 0];
-    brow = have ? q : -1;
-    acc = have ? z : 0.0;
-  }
-  /* phase M: the top half solves the middle unknowns R = m + 10 .. m; both halves take the updates */
-  {
-    auto loadM = [&](int s, double& z, bool& enter, double& l) {
-      const int Rr = m + 10 - s;
-      /* top: row r = Rr - u of this lane; bottom: the fixed row brow, u = distance to the solved unknown */
-      const int ut = (Rr - mm) & 15, rt = Rr - ut;
-      const int ub = T_bot + s - brow;
-      const bool mine = s < 11 && (h == 0 ? (ut <= 10 && rt >= 0) : (brow >= 0 && ub >= 1 && ub <= 10));
-      const int u = h == 0 ? ut : ub;
-      const int row = mine ? (h == 0 ? rt : N - 1 - brow) : 0;
-      const double zv = Hs[row * HROW];
-      const double lv = Hs[row * HROW + (mine ? u : 0)];
-      enter = mine && h == 0 && (ut == 10 || s == 0);
-      z = zv;
-      l = (mine && u >= 1) ? lv : 0.0;
+    double W[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) W[k] = 0.0;
+    /* row = (z, l_1 .. l_10, pad), loaded one row ahead of its use; x_{j+u} = W[(P + u) % 10], the new solution goes to
+     * W[P]. Four partial sums keep the fp64 pipe busy without dependent stalls; x_{j+1} enters last. */
+    struct Row { double2 f0, f1, f2, f3, f4, f5; };
+    auto row_load = [&](const double* rowp) -> Row {
+      const double2* r2 = reinterpret_cast<const double2*>(rowp);
+      Row r;
+      r.f0 = r2[0]; r.f1 = r2[1]; r.f2 = r2[2]; r.f3 = r2[3]; r.f4 = r2[4]; r.f5 = r2[5];
+      return r;
     };
-    double z, l; bool enter;
-    loadM(0, z, enter, l);
-    for (int s = 0; s < 11; ++s) {
-      double zn, ln; bool en;
-      loadM(s + 1, zn, en, ln);
-      acc = enter ? z : acc;
-      const int Rr = m + 10 - s;
-      const double xR = __shfl_sync(0xffffffffu, acc, Rr & 15);
-      hi_max = max(hi_max, __double2hiint(xR) & 0x7fffffff);
-      if (lane == (Rr & 15)) gx[(size_t)Rr * 32] = xR;
-      acc -= l * xR;
-      z = zn; l = ln; enter = en;
+    auto row_solve = [&](const Row& r, int P) -> double {
+      double a = fma(-r.f5.x, W[(P + 10) % 10], r.f0.x);
+      double b = -r.f4.y * W[(P + 9) % 10];
+      double c = -r.f4.x * W[(P + 8) % 10];
+      double d = -r.f3.y * W[(P + 7) % 10];
+      a = fma(-r.f3.x, W[(P + 6) % 10], a);
+      b = fma(-r.f2.y, W[(P + 5) % 10], b);
+      c = fma(-r.f2.x, W[(P + 4) % 10], c);
+      d = fma(-r.f1.y, W[(P + 3) % 10], d);
+      a = fma(-r.f1.x, W[(P + 2) % 10], a);
+      return fma(-r.f0.y, W[(P + 1) % 10], (a + b) + (c + d));
+    };
+    /* the middle block m + 10 .. m (rows of the top sweep's factor), ring positions 9, 8, .., 0, 9 */
+    double xm10 = 0.0;
+    Row cur = row_load(Hs + (size_t)(m + 10) * HROW);
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+      const int P = (19 - i) % 10;
+      const int j = m + 10 - i;
+      /* next: the following middle row, or (after the last one) the first row of this half's outward walk */
+      const Row nxt = row_load(Hs + (size_t)(i < 10 ? j - 1 : (h ? (T_bot > 0 ? m + 11 : 0) : m - 1)) * HROW);
+      const double x = row_solve(cur, P);
+      if (i == 0) xm10 = x;
+      W[P] = x;
+      hi_max = max(hi_max, __double2hiint(x) & 0x7fffffff);
+      if (lane == 0) gx[(size_t)j * 32] = x;
+      cur = nxt;
     }
-  }
-  /* phase 2: top R = m - 1 .. 0, bottom (sweep coordinate) T_bot - 1 .. 0, in lockstep */
-  {
-    const int R0 = (h == 0 ? m : T_bot) - 1;
-    auto load2 = [&](int sp2, double& z, bool& enter, double& l) {
-      const int Rq = R0 - sp2;
-      const int u = (Rq - mm) & 15, r = Rq - u;
-      const bool mine = Rq >= 0 && u <= 10 && r >= 0;
-      const int row = mine ? (h == 0 ? r : N - 1 - r) : 0;
-      const double zv = Hs[row * HROW];
-      const double lv = Hs[row * HROW + (mine ? u : 0)];
-      enter = mine && u == 10;
-      z = zv;
-      l = (mine && u >= 1) ? lv : 0.0;
-    };
-    double z, l; bool enter;
-    load2(0, z, enter, l);
-    for (int sp2 = 0; sp2 < m; ++sp2) {
-      double zn, ln; bool en;
-      load2(sp2 + 1, zn, en, ln);
-      acc = enter ? z : acc;
-      const int Rq = R0 - sp2;
-      const double xR = __shfl_sync(0xffffffffu, acc, (Rq & 15) | src_base);
-      hi_max = max(hi_max, Rq >= 0 ? __double2hiint(xR) & 0x7fffffff : 0);
-      if (Rq >= 0 && mm == (Rq & 15)) gx[(size_t)(h == 0 ? Rq : N - 1 - Rq) * 32] = xR;
-      acc -= l * xR;
-      z = zn; l = ln; enter = en;
+    /* the ring now holds x_m (position 9), x_{m+1} .. x_{m+9} (positions 0 .. 8): what the top half needs next at
+     * position 8. The bottom half continues in its own sweep order: its x_{q'+u} is the unknown m + 11 - u. */
+    {
+      double Wb[10];
+      Wb[9] = xm10;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Wb[k] = W[8 - k];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) W[k] = h ? Wb[k] : W[k];
+    }
+    const int cnt = h ? T_bot : m;
+    const int rinc = h ? HROW : -HROW;
+    const double* rp = Hs + (size_t)(h ? m + 11 : m - 1) * HROW + rinc;   /* the row AFTER the one held in `cur` */
+    int un = h ? m + 11 : m - 1;
+    const int uinc = h ? 1 : -1;
+    for (int i0 = 0; i0 < m; i0 += 10) {
+#pragma unroll
+      for (int ii = 0; ii < 10; ++ii) {
+        const int P = (18 - ii) % 10;                     /* 8, 7, .., 0, 9 */
+        const bool valid = i0 + ii < cnt;                 /* past the end of a sweep: harmless row, nothing stored */
+        const Row nxt = row_load(i0 + ii + 1 < cnt ? rp : Hs);
+        const double x = row_solve(cur, P);
+        W[P] = x;
+        hi_max = max(hi_max, valid ? __double2hiint(x) & 0x7fffffff : 0);
+        if (valid && mm == 0) gx[(size_t)un * 32] = x;
+        rp += rinc;
+        un += uinc;
+        cur = nxt;
+      }
     }
   }
   {

@@ -128,62 +128,51 @@ def solve_lat(Hs, N):
     for t in range(m, m + 11):
         step(t, (True, False))
 
-    # back substitution
-    acc = np.zeros(32)
-    # bottom rows next to the middle block
-    brow = np.full(32, -1)
-    for lane in range(16, 32):
-        l = lane & 15
-        back = (T_bot - 1 - l) & 15
-        q = T_bot - 1 - back
-        if back <= 9 and q >= 0:
-            brow[lane] = q
-            acc[lane] = Hs[slot(1, q), 0]
-    for s in range(11):
-        Rr = m + 10 - s
-        # top: rows entering
-        for lane in range(16):
-            u = (Rr - lane) & 15
-            r = Rr - u
-            if u <= 10 and r >= 0 and (u == 10 or Rr == m + 10):
-                acc[lane] = Hs[r, 0]
-        xR = acc[Rr & 15]
-        x[Rr] = xR
-        for lane in range(16):
-            u = (Rr - lane) & 15
-            r = Rr - u
-            if 1 <= u <= 10 and r >= 0:
-                acc[lane] -= Hs[r, u] * xR
-        for lane in range(16, 32):
-            q = brow[lane]
-            if q >= 0:
-                u = T_bot + s - q
-                if 1 <= u <= 10:
-                    acc[lane] -= Hs[slot(1, q), u] * xR
-    for sp in range(m):
-        xs = {}
-        for h in range(2):
-            Rq = (m - 1 - sp) if h == 0 else (T_bot - 1 - sp)
-            if Rq < 0:
-                continue
-            for lane in range(16 * h, 16 * h + 16):
-                l = lane & 15
-                u = (Rq - l) & 15
-                r = Rq - u
-                if u == 10 and r >= 0:
-                    acc[lane] = Hs[slot(h, r), 0]
-            xs[h] = acc[16 * h + (Rq & 15)]
-            x[slot(h, Rq)] = xs[h]
-        for h in range(2):
-            Rq = (m - 1 - sp) if h == 0 else (T_bot - 1 - sp)
-            if Rq < 0:
-                continue
-            for lane in range(16 * h, 16 * h + 16):
-                l = lane & 15
-                u = (Rq - l) & 15
-                r = Rq - u
-                if 1 <= u <= 10 and r >= 0:
-                    acc[lane] -= Hs[slot(h, r), u] * xs[h]
+    # back substitution, dot-product form with a ring of the ten most recent solutions (every lane of a half computes
+    # the same values; the model keeps one copy per half)
+    def row_solve(row, W, P):
+        f = Hs[row]
+        a = f[0] - f[10] * W[(P + 10) % 10]
+        b2 = -f[9] * W[(P + 9) % 10]
+        c2 = -f[8] * W[(P + 8) % 10]
+        d2 = -f[7] * W[(P + 7) % 10]
+        a -= f[6] * W[(P + 6) % 10]
+        b2 -= f[5] * W[(P + 5) % 10]
+        c2 -= f[4] * W[(P + 4) % 10]
+        d2 -= f[3] * W[(P + 3) % 10]
+        a -= f[2] * W[(P + 2) % 10]
+        return ((a + b2) + (c2 + d2)) - f[1] * W[(P + 1) % 10]
+
+    W = [0.0] * 10
+    xm10 = 0.0
+    for i in range(11):
+        P = (19 - i) % 10
+        j = m + 10 - i
+        v = row_solve(j, W, P)
+        if i == 0:
+            xm10 = v
+        W[P] = v
+        x[j] = v
+    Wb = [0.0] * 10
+    Wb[9] = xm10
+    for k in range(9):
+        Wb[k] = W[8 - k]
+    Wh = [list(W), Wb]
+    for h in range(2):
+        cnt = T_bot if h else m
+        row = (m + 11) if h else (m - 1)
+        rinc = 1 if h else -1
+        i0 = 0
+        while i0 < m:
+            for ii in range(10):
+                P = (18 - ii) % 10
+                valid = i0 + ii < cnt
+                v = row_solve(row if valid else 0, Wh[h], P)
+                Wh[h][P] = v
+                if valid:
+                    x[row] = v
+                row += rinc
+            i0 += 10
     return x
 
 
