@@ -264,7 +264,7 @@ int32_t tebgpu_set_speculation(tebgpu_ctx* ctx, int32_t k);
  *   3  k_solve_lat always: one warp per system, the system resident in shared memory, TWISTED factorisation (the two
  *      half-warps eliminate from both ends towards an 11-unknown middle block), 2.6x faster per solve than mode 0 when
  *      the machine is not full; another elimination order, so results agree with mode 0 to rounding, not bit for bit;
- *   4  (default) k_solve_lat while the systems of a round fit two waves of resident CTAs - the latency regime of a
+ *   4  (default) k_solve_lat while the systems of a round fit three waves of resident CTAs - the latency regime of a
  *      single planning request - and k_solve_tpb above that. */
 int32_t tebgpu_set_warp_solver(tebgpu_ctx* ctx, int32_t mode);
 

@@ -658,8 +658,9 @@ static int32_t issue_optimize(tebgpu_ctx* ctx, const TebBatch* bt, const TebOpti
             /* latency regime: one WARP per system (k_solve_warp) while all systems of the round fit a few warps per SM */
             const bool warp_solver = ctx->warp_solver == 1 || (ctx->warp_solver == 2 && bk <= 148 * 8);
             const size_t smem_lat = solve_lat_smem_bytes(bt->n_cap);
-            /* automatic: while the round's systems fit two waves of resident CTAs (one warp + its whole system per CTA) the
-             * twisted solver's ~0.1 ms per wave beats the 0.26 ms a thread-per-system solve takes regardless of the count */
+            /* automatic: while the round's systems fit LAT_WAVES waves of resident CTAs (one warp + its whole system per CTA)
+             * the twisted solver's ~0.065 ms per wave (200 poses) beats the 0.26 ms a thread-per-system solve takes
+             * regardless of the count */
             const long long lat_wave = smem_lat <= 232448 ? 148LL * (232448 / smem_lat > 16 ? 16 : 232448 / smem_lat) : 0;
             const bool lat_solver = lat_wave > 0 && (ctx->warp_solver == 3 || (ctx->warp_solver == 4 && bk <= LAT_WAVES * lat_wave));
             if (lat_solver) k_solve_lat<<<bk, 32, smem_lat, rs>>>(db, ctx->spec, it, round, g);

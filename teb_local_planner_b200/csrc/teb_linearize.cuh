@@ -14,9 +14,10 @@
  *   P3  the four band rows of the own pose (4 x 11 entries + 4 rhs) are accumulated IN REGISTERS from the records of
  *       the three anchors that touch them; structural zeros are compiled out, rows whose residual is exactly zero
  *       (inactive penalties: most velocity / acceleration rows of a converged band) are skipped at run time
- *   P4  the 384 bytes of a pose leave the registers as 128-bit global stores (OUT_DIRECT, default: every 32-byte sector
- *       is completed by two consecutive store instructions of the same lane) or through a padded shared-memory slot and
- *       one TMA bulk store per lane (cp.async.bulk.global.shared::cta); b also goes to the compact rhs array
+ *   P4  the 384 bytes of a pose go through a padded shared-memory slot and leave with one TMA bulk store per lane
+ *       (cp.async.bulk.global.shared::cta; the default), or as 128-bit global stores straight from the registers
+ *       (OUT_DIRECT, TEBGPU_KA_STAGED=0: measured slower, 0.55 vs 0.44 ms - every store instruction fills half a 32-byte
+ *       sector); b also goes to the compact rhs array
  *
  * Arithmetic = the computeError bodies cited in teb_device.cuh / below, Jacobians in closed form; identical formulas to
  * the first-generation kernel (k_linearize in teb_kernels.cuh, kept as variant 1), different summation order.

@@ -38,7 +38,8 @@
 
 namespace tebgpu {
 
-constexpr int LAT_WAVES = 2;          /* automatic mode: k_solve_lat replaces k_solve_tpb while a round fits this many waves */
+constexpr int LAT_WAVES = 3;          /* automatic mode: k_solve_lat replaces k_solve_tpb while a round fits this many waves of
+                                         resident CTAs (a wave takes ~1/4 of the time k_solve_tpb needs for any number of systems) */
 constexpr int SL_REC = 24;            /* published pivot column: d, c_1 .. c_10 at [0..10], zeros at [11..21], y at [22] */
 constexpr int SL_CB = 2 * 2 * SL_REC; /* [half][buffer] */
 constexpr int SL_SPECIAL = 2 * HROW + SL_REC; /* an all-zero column, an identity column, the dummy record of the non-owners */
