@@ -430,6 +430,9 @@ def run_b200(a, rank, local_rank, world):
         r = {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
              "frac_algorithmic": ach / peak, "avg_launch_ms": t, "algorithmic_bytes_per_launch": int(alg_bytes),
              "traffic": ncu_tr.get(label), "peak_source": peak_src, "note": ws_note}
+        if r["traffic"] is None and all(nme in ncu_tr for nme in names):   # a launch PAIR: sum of the captured launches
+            r["traffic"] = int(sum(ncu_tr[nme] for nme in names))
+            r["traffic_note"] = "sum of the ncu DRAM bytes of one captured launch of each kernel (see profiles/ncu_traffic.json for which)"
         if model_traffic is not None:
             r["modelled_traffic_bytes_per_launch"] = int(model_traffic)
             r["frac_traffic"] = model_traffic / (t * 1e-3) / 1e9 / peak
