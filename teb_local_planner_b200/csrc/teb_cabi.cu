@@ -26,8 +26,13 @@ struct tebgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;        /* retry rounds of the speculative solver, overlapped with the next kernel A */
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int overlap = 1;                    /* 0: everything on one stream (TEBGPU_OVERLAP=0, profiling, k_vor) */
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_s0 = nullptr;
+  double* Lf2 = nullptr;              /* scratch of the side stream's solver launches (they overlap the main stream's) */
+  double* dx2 = nullptr;
+  int split = 1;                      /* throughput regime: the side stream also runs round 0 for its bands (TEBGPU_SPLIT) */
+  int overlap = 2;                    /* retry rounds on the side stream: 0 never (one stream), 1 always, 2 (default) only in the
+                                         latency regime - measured on C2 / C3 / C4 at 8192 bands the three schedules are within
+                                         +-3 % of each other, the machine is resource bound there (TEBGPU_OVERLAP) */
   int32_t* defer = nullptr;           /* [B] */
   double* d_fp = nullptr;             /* footprint definition for the vertex-list distance path (FP_DOUBLES) */
   double* d_pverts = nullptr;         /* [S][max_obst_vertices][2] mirror of TebBatch.obst_vertices */
@@ -194,7 +199,7 @@ int64_t tebgpu_get_info(const tebgpu_ctx* ctx, int32_t which) {
 }
 
 static void free_all(tebgpu_ctx* c) {
-  void* ptrs[] = {c->arrive, c->d_gather, c->d_hsig, c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->d_fp, c->d_pverts, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
+  void* ptrs[] = {c->Lf2, c->dx2, c->arrive, c->d_gather, c->d_hsig, c->assoc3, c->dyn_idx, c->dyn_cnt, c->rhs, c->dmax_parts, c->spec.Lf, c->spec.dx, c->spec.res, c->spec.need, c->spec.qmax, c->spec.cnt, c->spec.list, c->defer, c->d_fp, c->d_pverts, c->Hb, c->assoc, c->dyn_t, c->via_idx, c->chi_parts, c->state, c->d_poses, c->d_n, c->d_scene,
                   c->d_obst, c->d_ocount, c->d_via, c->d_vcount, c->d_vs, c->d_vg, c->d_rot, c->d_cost, c->d_chi2,
                   c->d_status, c->d_iters};
   for (void* p : ptrs)
@@ -229,7 +234,8 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   }
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-  if (const char* e = std::getenv("TEBGPU_OVERLAP")) c->overlap = std::atoi(e) != 0;
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_s0, cudaEventDisableTiming));
+  if (const char* e = std::getenv("TEBGPU_OVERLAP")) { const int m = std::atoi(e); if (m >= 0 && m <= 2) c->overlap = m; }
   if (const char* e = std::getenv("TEBGPU_SPEC_K")) { const int k = std::atoi(e); if (k == 2 || k == 4 || k == 6 || k == 8) c->spec_k = k; }
   const size_t B = c->lim.max_bands, nc = c->lim.max_poses, S = c->lim.max_scenes, M = c->lim.max_obstacles,
                V = c->lim.max_viapoints > 0 ? c->lim.max_viapoints : 1;
@@ -268,8 +274,12 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   const size_t spec_sys = ((B * SPEC_K_MAX + 31) / 32) * 32; /* whole warps of (band, trial) systems */
   CUDA_TRY(c, cudaMalloc(&c->spec.Lf, spec_sys * 4 * nc * HROW * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->spec.dx, spec_sys * 4 * nc * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->Lf2, spec_sys * 4 * nc * HROW * sizeof(double)));
+  CUDA_TRY(c, cudaMalloc(&c->dx2, spec_sys * 4 * nc * sizeof(double)));
+  c->spec.sel_list = nullptr; c->spec.sel_cnt = nullptr; c->spec.defer = nullptr; c->spec.skip_tag = 0;
+  if (const char* e = std::getenv("TEBGPU_SPLIT")) c->split = std::atoi(e) != 0;
   CUDA_TRY(c, cudaMalloc(&c->spec.cnt, SPEC_CNT_CAP * sizeof(int32_t)));
-  CUDA_TRY(c, cudaMalloc(&c->spec.list, 3 * B * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMalloc(&c->spec.list, SPEC_LISTS * B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->defer, B * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.res, B * SPEC_K_MAX * RES_STRIDE * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->arrive, B * sizeof(int32_t)));
@@ -370,6 +380,7 @@ int32_t tebgpu_destroy(tebgpu_ctx* ctx) {
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_s0) cudaEventDestroy(ctx->ev_s0);
   delete ctx;
   return TEBGPU_OK;
 }
@@ -439,16 +450,16 @@ static void launch_vor(const DevBatch& db, const KParams& kp, int B, size_t smem
 static size_t eval_bytes(const tebgpu_ctx* ctx, int n_cap, int M_cap, int K) {
   return ctx->eval_v1 ? eval_smem_bytes(n_cap, M_cap, K) : eval2_smem_bytes(n_cap, M_cap, K);
 }
-static void launch_trial_eval(tebgpu_ctx* ctx, const DevBatch& db, const KParams& kp, int B, int K, size_t smem, int it,
-                              int round, int g, int tag, cudaStream_t st) {
+static void launch_trial_eval(tebgpu_ctx* ctx, const SpecBufs& spec, const DevBatch& db, const KParams& kp, int B, int K,
+                              size_t smem, int it, int round, int g, int tag, cudaStream_t st) {
   /* latency regime: a CTA per (band, trial) instead of a CTA per band while that still fits ~3 CTAs per SM */
   const size_t smem3 = eval3_smem_bytes(db.n_cap, db.M_cap, K);
   if (!ctx->eval_v1 && smem3 <= 232448 && (ctx->eval_mode == 1 || (ctx->eval_mode == 2 && (long long)B * K <= 148 * 3))) {
     int warps = ev2_tiles(db.n_cap);
     warps = warps < 1 ? 1 : (warps > 16 ? 16 : warps);
     const dim3 grid(K, B);
-    if (kp.generic) k_trial_eval3<true><<<grid, 32 * warps, smem3, st>>>(db, kp, ctx->spec, it, round, g, tag, ctx->arrive);
-    else k_trial_eval3<false><<<grid, 32 * warps, smem3, st>>>(db, kp, ctx->spec, it, round, g, tag, ctx->arrive);
+    if (kp.generic) k_trial_eval3<true><<<grid, 32 * warps, smem3, st>>>(db, kp, spec, it, round, g, tag, ctx->arrive);
+    else k_trial_eval3<false><<<grid, 32 * warps, smem3, st>>>(db, kp, spec, it, round, g, tag, ctx->arrive);
     return;
   }
   if (!ctx->eval_v1) { /* second generation: one lane per pose */
@@ -460,17 +471,17 @@ static void launch_trial_eval(tebgpu_ctx* ctx, const DevBatch& db, const KParams
     if (wide) warps = 2 * warps;
     const int nt = 32 * warps;
     if (kp.generic) {
-      if (wide) k_trial_eval2<true, 512><<<B, nt, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
-      else k_trial_eval2<true, 256><<<B, nt, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+      if (wide) k_trial_eval2<true, 512><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
+      else k_trial_eval2<true, 256><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
     } else {
-      if (wide) k_trial_eval2<false, 512><<<B, nt, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
-      else k_trial_eval2<false, 256><<<B, nt, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+      if (wide) k_trial_eval2<false, 512><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
+      else k_trial_eval2<false, 256><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
     }
     return;
   }
-  if (kp.generic) k_trial_eval<2, true><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
-  else if (ctx->eval_minb == 3) k_trial_eval<3, false><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
-  else k_trial_eval<2, false><<<B, 32 * K, smem, st>>>(db, kp, ctx->spec, it, round, g, tag);
+  if (kp.generic) k_trial_eval<2, true><<<B, 32 * K, smem, st>>>(db, kp, spec, it, round, g, tag);
+  else if (ctx->eval_minb == 3) k_trial_eval<3, false><<<B, 32 * K, smem, st>>>(db, kp, spec, it, round, g, tag);
+  else k_trial_eval<2, false><<<B, 32 * K, smem, st>>>(db, kp, spec, it, round, g, tag);
 }
 
 static KParams make_kparams(const tebgpu_ctx* ctx, const TebBatch* bt, double weight_multiplier) {
@@ -603,15 +614,23 @@ static int32_t issue_optimize(tebgpu_ctx* ctx, const TebBatch* bt, const TebOpti
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->spec.cnt, 0, (size_t)need_cnt * sizeof(int32_t), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->defer, 0, (size_t)B * sizeof(int32_t), st));
   }
-  /* Retry rounds (bands that rejected all K trials: ~5 % at K = 4) are latency bound and nearly empty. They run on a
-   * side stream, followed by kernel A of the next inner iteration for exactly those bands, while the main stream
-   * linearises all other bands; both join before the next solve. Bands never share data, so this is only a
-   * re-ordering of independent work. */
-  const bool overlap = ctx->solver == 2 && ctx->overlap && !ctx->profiling;
+  /* Retry rounds (bands that rejected all trials of a round) can run on a side stream, followed by kernel A of the next
+   * inner iteration for exactly those bands - and, with TEBGPU_SPLIT, by ROUND 0 of that iteration for them - while the
+   * main stream works on all other bands. Bands never share data, so this is only a re-ordering of independent work
+   * (bit-identical results, tested). It pays when the retry rounds are nearly empty (fixed K = 4: ~5 % of the bands; the
+   * latency regime, where it is the default). With the width schedule {2, 4, 4} of the throughput regime 30-40 % of the
+   * bands retry, the retry solves move as many factor bytes as round 0, and the overlapped schedules measure within
+   * +-3 % of the serial one on C2 / C3 / C4 (profiles/r2_history.md): the machine is resource bound, so one stream is the
+   * default there. */
+  const bool latency_regime_b = (long long)B * 8 <= 148LL * 4 * 32;
+  const bool overlap = ctx->solver == 2 && (ctx->overlap == 1 || (ctx->overlap == 2 && latency_regime_b)) && !ctx->profiling;
   int tag = 0; /* running inner-iteration number (1-based) */
   double weight_multiplier = 1.0;
   KParams kp = make_kparams(ctx, bt, weight_multiplier);
   prof_begin(ctx, st, 0); k_begin<<<gb, tb, 0, st>>>(db, kp); ++launches; prof_end(ctx, st);
+  const bool split_ok = overlap && ctx->split && !latency_regime_b;
+  bool side_share = false;
+  int last_r1 = 0;      /* index g of round 1 of the latest LM iteration: its list = the side stream's bands */
   bool carried = false; /* the side stream already ran autoResize / buildGraph / kernel A of this outer iteration for the
                            bands that were still in a retry round when the previous outer iteration ended */
   for (int o = 0; o < args->iterations_outerloop; ++o) {
@@ -631,56 +650,78 @@ static int32_t issue_optimize(tebgpu_ctx* ctx, const TebBatch* bt, const TebOpti
         if (deferred_done) da.skip_tag = tag - 1; /* bands queued during the previous iteration were linearised on the side stream */
         prof_begin(ctx, st, 3); launch_linearize(ctx, da, kp, B, bt->M_cap, st); ++launches; prof_end(ctx, st);
         if (kp.has_vor) { prof_begin(ctx, st, 3); launch_vor(db, kp, B, smem_g, st); ++launches; prof_end(ctx, st); }
-        if (deferred_done) { CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0)); deferred_done = false; }
+        /* Split round 0 (throughput regime): the bands that needed retry rounds in the previous iteration were linearised
+         * on the side stream; instead of joining here, the side stream also solves / evaluates ROUND 0 for exactly those
+         * bands (list of the previous round 1, own scratch) while the main stream does it for all others. Both append to
+         * the same retry list; the main stream waits for the side stream's evaluation only before it needs the deferral
+         * tags again. Bands never share data: only the schedule changes, the results do not. */
+        side_share = deferred_done && split_ok;
+        if (deferred_done && !side_share) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        deferred_done = false;
       }
       if (ctx->solver == 2) {
         const int* sched = (it == 0) ? sched_first : sched_later;
         const int rounds = (it == 0) ? n_first : n_later; /* widths add up to g2o's maxTrialsAfterFailure = 10 */
         const bool fork = overlap && rounds > 1 && !kp.has_vor;
         cudaStream_t rs = st;
+        auto launch_solve = [&](const SpecBufs& spec, int K, int round, cudaStream_t s) {
+          /* ring depth: 10 rows unless TEBGPU_RING asks for 20 / 30. Measured (profiles/r2_history.md): deeper rings do
+           * not shorten the chain - a lone solver warp is bound by its own fp64 issue rate (~75 DFMA per pivot at 2
+           * cycles each), not by the prefetch distance - and they cost residency (20 rows: 3 warps per SM). */
+          const int bk = B * K;
+          const int warps = (bk + 31) / 32;
+          const int ring = ctx->ring == 0 ? 10 : ctx->ring;
+          /* k_solve_warp: the sequential order spread over a warp (cross-check only) */
+          const bool warp_solver = ctx->warp_solver == 1 || (ctx->warp_solver == 2 && bk <= 148 * 8);
+          const size_t smem_lat = solve_lat_smem_bytes(bt->n_cap);
+          /* automatic: while the round's systems fit LAT_WAVES waves of resident CTAs (one warp + its whole system per CTA)
+           * the twisted solver's ~0.065 ms per wave (200 poses) beats the 0.26 ms a thread-per-system solve takes
+           * regardless of the count */
+          const long long lat_wave = smem_lat <= 232448 ? 148LL * (232448 / smem_lat > 16 ? 16 : 232448 / smem_lat) : 0;
+          const bool lat_solver = lat_wave > 0 && (ctx->warp_solver == 3 || (ctx->warp_solver == 4 && bk <= LAT_WAVES * lat_wave));
+          if (lat_solver) k_solve_lat<<<bk, 32, smem_lat, s>>>(db, spec, it, round, g);
+          else if (warp_solver) k_solve_warp<<<(bk + SW_WARPS - 1) / SW_WARPS, 32 * SW_WARPS, 0, s>>>(db, spec, it, round, g);
+          else if (ring == 30) k_solve_tpb<30><<<warps, 32, tpb_ring_bytes(30), s>>>(db, spec, it, round, g);
+          else if (ring == 20) k_solve_tpb<20><<<warps, 32, tpb_ring_bytes(20), s>>>(db, spec, it, round, g);
+          else k_solve_tpb<10><<<warps, 32, tpb_ring_bytes(10), s>>>(db, spec, it, round, g);
+          ++launches;
+        };
         for (int round = 0; round < rounds; ++round, ++g) {
           const int K = sched[round];
           ctx->spec.K = K;
-          const int bk = B * K;
           const size_t smem_e = eval_bytes(ctx, bt->n_cap, bt->M_cap, K);
+          SpecBufs spec = ctx->spec; /* main-stream launch: every band, or every band but the side stream's share */
+          if (round == 0 && side_share) { spec.defer = ctx->defer; spec.skip_tag = tag - 1; }
           if (round == 1 && fork) { /* retry rounds go to the side stream */
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
             rs = ctx->side;
           }
-          prof_begin(ctx, st, round == 0 ? 6 : 4);
-          {
-            /* ring depth: 10 rows unless TEBGPU_RING asks for 20 / 30. Measured (profiles/r2_history.md): deeper rings do
-             * not shorten the chain - a lone solver warp is bound by its own fp64 issue rate (~75 DFMA per pivot at 2
-             * cycles each), not by the prefetch distance - and they cost residency (20 rows: 3 warps per SM). */
-            const int warps = (bk + 31) / 32;
-            const int ring = ctx->ring == 0 ? 10 : ctx->ring;
-            /* latency regime: one WARP per system (k_solve_warp) while all systems of the round fit a few warps per SM */
-            const bool warp_solver = ctx->warp_solver == 1 || (ctx->warp_solver == 2 && bk <= 148 * 8);
-            const size_t smem_lat = solve_lat_smem_bytes(bt->n_cap);
-            /* automatic: while the round's systems fit LAT_WAVES waves of resident CTAs (one warp + its whole system per CTA)
-             * the twisted solver's ~0.065 ms per wave (200 poses) beats the 0.26 ms a thread-per-system solve takes
-             * regardless of the count */
-            const long long lat_wave = smem_lat <= 232448 ? 148LL * (232448 / smem_lat > 16 ? 16 : 232448 / smem_lat) : 0;
-            const bool lat_solver = lat_wave > 0 && (ctx->warp_solver == 3 || (ctx->warp_solver == 4 && bk <= LAT_WAVES * lat_wave));
-            if (lat_solver) k_solve_lat<<<bk, 32, smem_lat, rs>>>(db, ctx->spec, it, round, g);
-            else
-            if (warp_solver) k_solve_warp<<<(bk + SW_WARPS - 1) / SW_WARPS, 32 * SW_WARPS, 0, rs>>>(db, ctx->spec, it, round, g);
-            else
-            if (ring == 30) k_solve_tpb<30><<<warps, 32, tpb_ring_bytes(30), rs>>>(db, ctx->spec, it, round, g);
-            else if (ring == 20) k_solve_tpb<20><<<warps, 32, tpb_ring_bytes(20), rs>>>(db, ctx->spec, it, round, g);
-            else k_solve_tpb<10><<<warps, 32, tpb_ring_bytes(10), rs>>>(db, ctx->spec, it, round, g);
+          if (rs == ctx->side) { spec.Lf = ctx->Lf2; spec.dx = ctx->dx2; } /* the side stream's own scratch */
+          if (round == 0 && side_share) { /* the side stream's share of round 0, issued before its retry rounds */
+            SpecBufs ss = ctx->spec;
+            ss.Lf = ctx->Lf2; ss.dx = ctx->dx2;
+            ss.sel_list = ctx->spec.list + (size_t)(last_r1 % SPEC_LISTS) * B;
+            ss.sel_cnt = ctx->spec.cnt + last_r1;
+            launch_solve(ss, K, 0, ctx->side);
+            launch_trial_eval(ctx, ss, db, kp, B, K, smem_e, it, 0, g, tag, ctx->side); ++launches;
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_s0, ctx->side));
           }
-          ++launches; prof_end(ctx, st);
+          prof_begin(ctx, st, round == 0 ? 6 : 4);
+          launch_solve(spec, K, round, rs);
+          prof_end(ctx, st);
           prof_begin(ctx, st, round == 0 ? 7 : 4);
-          launch_trial_eval(ctx, db, kp, B, K, smem_e, it, round, g, tag, rs);
+          launch_trial_eval(ctx, spec, db, kp, B, K, smem_e, it, round, g, tag, rs);
           ++launches; prof_end(ctx, st);
+          /* the deferral tags / the retry list of this iteration are complete once both halves of round 0 are done */
+          if (round == 0 && side_share) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_s0, 0));
         }
+        last_r1 = g - rounds + 1;
         if (fork) {
           if (it + 1 < args->iterations_innerloop) { /* next kernel A for the bands of the round-1 list, then join */
             DevBatch dl = db;
-            dl.a_list = ctx->spec.list + (size_t)((g - rounds + 1) % 3) * B;
-            dl.a_cnt = ctx->spec.cnt + (g - rounds + 1);
+            dl.a_list = ctx->spec.list + (size_t)(last_r1 % SPEC_LISTS) * B;
+            dl.a_cnt = ctx->spec.cnt + last_r1;
             launch_linearize(ctx, dl, kp, B, bt->M_cap, ctx->side); ++launches;
             deferred_done = true;
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->side));
@@ -689,8 +730,8 @@ static int32_t issue_optimize(tebgpu_ctx* ctx, const TebBatch* bt, const TebOpti
              * first kernel A for its bands (next weight multiplier), the main stream does the same for all others */
             const KParams kn = make_kparams(ctx, bt, weight_multiplier * p.weight_adapt_factor);
             DevBatch dl = db;
-            dl.a_list = ctx->spec.list + (size_t)((g - rounds + 1) % 3) * B;
-            dl.a_cnt = ctx->spec.cnt + (g - rounds + 1);
+            dl.a_list = ctx->spec.list + (size_t)(last_r1 % SPEC_LISTS) * B;
+            dl.a_cnt = ctx->spec.cnt + last_r1;
             if (p.teb_autosize) { k_auto_resize<<<gb, tb, 0, ctx->side>>>(dl, kn); ++launches; }
             launch_build_graph(dl, kn, B, smem_g, ctx->side); ++launches;
             launch_linearize(ctx, dl, kn, B, bt->M_cap, ctx->side); ++launches;
@@ -733,7 +774,7 @@ static uint64_t graph_key(const tebgpu_ctx* ctx, const TebBatch* bt, const TebOp
   mix(bt, sizeof(*bt));
   mix(a, sizeof(*a));
   mix(&ctx->params_version, sizeof(ctx->params_version));
-  const int sw[10] = {ctx->solver, ctx->spec_k, ctx->linearize_variant, ctx->ka_staged, ctx->eval_v1, ctx->ring, ctx->overlap, ctx->eval_minb, ctx->warp_solver, ctx->eval_mode};
+  const int sw[11] = {ctx->solver, ctx->spec_k, ctx->linearize_variant, ctx->ka_staged, ctx->eval_v1, ctx->ring, ctx->overlap, ctx->eval_minb, ctx->warp_solver, ctx->eval_mode, ctx->split};
   mix(sw, sizeof(sw));
   mix(&st, sizeof(st));
   return h;

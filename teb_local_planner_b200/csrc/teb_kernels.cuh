@@ -91,10 +91,16 @@ struct DevBatch {
   int32_t skip_tag;
 };
 
+/* A band belongs to the side stream's share when it was queued for retry rounds in the iteration with tag `skip_tag` -
+ * or, meanwhile, AGAIN in the following one: the side stream's own round 0 of the current iteration may re-queue it
+ * (defer = skip_tag + 1) while main-stream kernels of the same iteration are still deciding what to skip. */
+__device__ __forceinline__ bool deferred_since(int32_t defer_tag, int32_t skip_tag) {
+  return (uint32_t)(defer_tag - skip_tag) <= 1u;
+}
 /* band handled by this CTA of kernel A, or -1 */
 __device__ __forceinline__ int linearize_band(const DevBatch& db, int y) {
   if (db.a_list) return (y < *db.a_cnt) ? db.a_list[y] : -1;
-  if (db.skip_tag != 0 && db.defer[y] == db.skip_tag) return -1;
+  if (db.skip_tag != 0 && deferred_since(db.defer[y], db.skip_tag)) return -1;
   return y;
 }
 

@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(KA2_THREADS, 3) k_linearize2(const __grid_cons
   const int y = blockIdx.y;
   int b = y, skip = 0;
   if (db.a_list) { if (y < *db.a_cnt) b = db.a_list[y]; else skip = 1; }
-  else if (db.skip_tag != 0 && db.defer[y] == db.skip_tag) skip = 1;
+  else if (db.skip_tag != 0 && deferred_since(db.defer[y], db.skip_tag)) skip = 1;
   if (skip) return; /* uniform for the CTA */
   const int active = db.state[b].active;
   const int n = db.n[b];

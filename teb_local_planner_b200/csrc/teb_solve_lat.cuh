@@ -147,9 +147,8 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
   const int SPEC_K = sp.K;
   const int slot = t_sys / SPEC_K;
   const int k_trial = t_sys - slot * SPEC_K;
-  const int nslots = (round == 0) ? db.B : sp.cnt[g];
-  if (slot >= nslots) return;                         /* whole warp */
-  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
+  const int b = spec_band(db, sp, round, g, slot);
+  if (b < 0) return;                                  /* whole warp */
   const BandState* st = &db.state[b];
   if (!st->active) return;
   const int q0 = (round == 0) ? 0 : sp.qmax[b];
@@ -168,7 +167,7 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
   uint64_t* bar = reinterpret_cast<uint64_t*>(mid + SL_MID);
   const double* gH = db.Hb + (size_t)b * 4 * db.n_cap * HROW;
   double* gx = sp.dx + (size_t)(t_sys >> 5) * 32 * 4 * db.n_cap + (t_sys & 31); /* + r * 32: layout of k_trial_eval2 */
-  double* res = sp.res + ((size_t)b * SPEC_K + k_trial) * RES_STRIDE;
+  double* res = sp.res + ((size_t)b * SPEC_K_MAX + k_trial) * RES_STRIDE;
 
   const long long c_start = clock64();
   if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }

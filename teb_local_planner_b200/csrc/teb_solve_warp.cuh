@@ -42,9 +42,8 @@ __global__ void __launch_bounds__(32 * SW_WARPS) k_solve_warp(DevBatch db, SpecB
   const int SPEC_K = sp.K;
   const int slot = t / SPEC_K;
   const int k = t - slot * SPEC_K;
-  const int nslots = (round == 0) ? db.B : sp.cnt[g];
-  if (slot >= nslots) return;                         /* whole warp */
-  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
+  const int b = spec_band(db, sp, round, g, slot);
+  if (b < 0) return;                                  /* whole warp */
   const BandState* st = &db.state[b];
   if (!st->active) return;
   const int q0 = (round == 0) ? 0 : sp.qmax[b];
@@ -62,7 +61,7 @@ __global__ void __launch_bounds__(32 * SW_WARPS) k_solve_warp(DevBatch db, SpecB
   const double* gH = db.Hb + (size_t)b * 4 * db.n_cap * HROW;
   double* gF = sp.Lf + (size_t)t * 4 * db.n_cap * HROW;      /* this system's factor rows [row][12] */
   double* gx = sp.dx + (size_t)(t >> 5) * 32 * 4 * db.n_cap + (t & 31); /* + r * 32: layout of k_trial_eval2 */
-  double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
+  double* res = sp.res + ((size_t)b * SPEC_K_MAX + k) * RES_STRIDE;
 
   const int m = lane & 15, p = lane >> 4;
   const uint32_t ring_u32 = smem_u32(ring);

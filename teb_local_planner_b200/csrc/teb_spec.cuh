@@ -26,17 +26,37 @@ namespace tebgpu {
 constexpr int SPEC_K_MAX = 8;    /* trials solved concurrently per round: 4, 6 or 8 (runtime, SpecBufs::K) */
 constexpr int SPEC_CNT_CAP = 1 << 16; /* retry-list counters per call: outer x inner x rounds */
 constexpr int RES_STRIDE = 8;    /* per (band, trial): chi parts [4], scale, ok, lambda, unused */
+constexpr int SPEC_LISTS = 8;    /* rotating retry-list buffers: round g reads buffer g % SPEC_LISTS, writes (g + 1) % SPEC_LISTS */
 
 struct SpecBufs {
   double* Lf;    /* [B][K][4 n_cap][12] factor rows: 1/d, z, L[j+1..j+10][j] */
   double* dx;    /* [B][K][4 n_cap]     solution of trial k                   */
-  double* res;   /* [B][K][RES_STRIDE]                                         */
+  double* res;   /* [B][SPEC_K_MAX][RES_STRIDE]: the stride does not depend on the width of a launch (launches of
+                    different widths overlap in time)                           */
   int32_t* need; /* [B] band still needs trials in this LM iteration          */
   int32_t* qmax; /* [B] trials consumed in this LM iteration                  */
   int32_t* cnt;  /* [rounds of the call + 1] length of the retry list a round reads (zeroed per call) */
-  int32_t* list; /* [3][B] bands of the retry list, buffer g % 3 is read by round g                    */
+  int32_t* list; /* [SPEC_LISTS][B] bands of the retry lists, buffer g % SPEC_LISTS is read by round g */
   int32_t K;     /* speculation width of this call                            */
+  /* Band selection of a ROUND-0 launch (retry rounds always walk list g):
+   *   sel_list != NULL  the bands of that list (sel_cnt entries) - the side stream's share of an LM iteration: the bands
+   *                     that needed retries in the previous iteration and were linearised there;
+   *   else              every band except those with defer[b] == skip_tag (skip_tag 0: every band).
+   * Lf / dx above are the scratch of the LAUNCHING stream: main-stream and side-stream launches overlap in time. */
+  const int32_t* sel_list;
+  const int32_t* sel_cnt;
+  const int32_t* defer;
+  int32_t skip_tag;
 };
+
+/* the band of system slot `slot` in this launch, or -1 */
+__device__ __forceinline__ int spec_band(const DevBatch& db, const SpecBufs& sp, int round, int g, int slot) {
+  if (round > 0) return slot < sp.cnt[g] ? sp.list[(size_t)(g % SPEC_LISTS) * db.B + slot] : -1;
+  if (sp.sel_list) return slot < *sp.sel_cnt ? sp.sel_list[slot] : -1;
+  if (slot >= db.B) return -1;
+  if (sp.skip_tag != 0 && deferred_since(sp.defer[slot], sp.skip_tag)) return -1;
+  return slot;
+}
 
 /* lambda / nu of trial q0 + k given the state before trial q0 (only rejections in between) */
 __device__ __forceinline__ void spec_lambda(double& lambda, double& ni, int k) {
@@ -78,9 +98,8 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
   /* system t = K * slot + k; round 0: slot = band, retry rounds: slot indexes the compact list of round g */
   const int slot = t / SPEC_K;
   const int k = t - slot * SPEC_K;
-  const int nslots = (round == 0) ? db.B : sp.cnt[g];
-  if (slot >= nslots) return; /* threads are independent: no warp-level primitive below */
-  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
+  const int b = spec_band(db, sp, round, g, slot);
+  if (b < 0) return; /* threads are independent: no warp-level primitive below */
   bool work = true;
   const BandState* st = &db.state[b];
   if (!st->active) work = false;
@@ -99,7 +118,7 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
    * threads of a warp - 32 different (band, trial) systems - store and load contiguous 512 / 256 byte runs */
   double2* gL = reinterpret_cast<double2*>(sp.Lf + (size_t)blockIdx.x * 32 * 4 * db.n_cap * HROW) + lane;
   double* gx = sp.dx + (size_t)blockIdx.x * 32 * 4 * db.n_cap + lane;
-  double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
+  double* res = sp.res + ((size_t)b * SPEC_K_MAX + k) * RES_STRIDE;
   const uint32_t ring = smem_u32(ring_raw) + (uint32_t)lane * 16u;                 /* + (slot*6 + pair)*512 */
   const double2* ringp = reinterpret_cast<const double2*>(ring_raw) + lane;       /* [(slot*6 + pair)*32]  */
 
@@ -338,8 +357,8 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch d
   extern __shared__ __align__(16) unsigned char ev_raw[];
   const int SPEC_K = sp.K;
   const int slot = blockIdx.x;
-  if (round > 0 && slot >= sp.cnt[g]) return;
-  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
+  const int b = spec_band(db, sp, round, g, slot);
+  if (b < 0) return;
   const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
   BandState* st = &db.state[b];
   if (!st->active) return;
@@ -376,7 +395,7 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch d
   }
   __syncthreads();
   const bool mine = (q0 + k < 10);
-  const double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
+  const double* res = sp.res + ((size_t)b * SPEC_K_MAX + k) * RES_STRIDE;
   double chi[4] = {0, 0, 0, 0};
   double scl = 0;
   bool ok = true;
@@ -423,7 +442,7 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch d
     da.st = st; da.chi_parts = db.chi_parts + (size_t)b * db.chunks * 4;
     da.lambda_init = (round == 0 && iteration == 0) ? band_lambda_init(db, b, n) : 0.0;
     da.need = sp.need + b; da.qmax = sp.qmax + b; da.cnt_next = sp.cnt + g + 1;
-    da.list_next = sp.list + (size_t)((g + 1) % 3) * db.B;
+    da.list_next = sp.list + (size_t)((g + 1) % SPEC_LISTS) * db.B;
     da.defer = db.defer + b; da.tag = tag;
     da.b = b; da.n = n; da.K = SPEC_K; da.iteration = iteration; da.round = round; da.q0 = q0; da.tile = db.tile;
     const int accepted = spec_decide(da, sRes);
@@ -629,8 +648,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
   extern __shared__ __align__(16) unsigned char ev_raw[];
   const int SPEC_K = sp.K;
   const int slot = blockIdx.x;
-  if (round > 0 && slot >= sp.cnt[g]) return;
-  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
+  const int b = spec_band(db, sp, round, g, slot);
+  if (b < 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x; /* <= NT: as many warps as the band has 30-pose tiles, so that the K x tiles tasks split evenly */
   BandState* st = &db.state[b];
@@ -671,7 +690,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
   const double* vg = db.vel_goal + 4 * (size_t)b;
   for (int task = warp; task < kact * tiles; task += nthreads / 32) {
     const int k = task / tiles, tile = task - k * tiles;
-    const double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
+    const double* res = sp.res + ((size_t)b * SPEC_K_MAX + k) * RES_STRIDE;
     double chi[4], scl;
     eval_tile_task<GEOM>(kp, db, b, sc, n, tile, lane, res[5] != 0.0, res[6], sdx + (size_t)k * 4 * db.n_cap, sP0, sB, so, M, vs, vg,
                          chi, scl);
@@ -690,7 +709,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
     }
     double* r = sRes + tid * RES_STRIDE;
     r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = a[3]; r[4] = a[4];
-    r[5] = sp.res[((size_t)b * SPEC_K + tid) * RES_STRIDE + 5];
+    r[5] = sp.res[((size_t)b * SPEC_K_MAX + tid) * RES_STRIDE + 5];
   }
   __syncthreads();
   /* ---- accept / reject replay, sequential over the K trials */
@@ -699,7 +718,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __g
     da.st = st; da.chi_parts = db.chi_parts + (size_t)b * db.chunks * 4;
     da.lambda_init = (round == 0 && iteration == 0) ? band_lambda_init(db, b, n) : 0.0;
     da.need = sp.need + b; da.qmax = sp.qmax + b; da.cnt_next = sp.cnt + g + 1;
-    da.list_next = sp.list + (size_t)((g + 1) % 3) * db.B;
+    da.list_next = sp.list + (size_t)((g + 1) % SPEC_LISTS) * db.B;
     da.defer = db.defer + b; da.tag = tag;
     da.b = b; da.n = n; da.K = SPEC_K; da.iteration = iteration; da.round = round; da.q0 = q0; da.tile = db.tile;
     sAcc[0] = spec_decide(da, sRes);
@@ -739,8 +758,8 @@ __global__ void __launch_bounds__(512, 1) k_trial_eval3(const __grid_constant__ 
   extern __shared__ __align__(16) unsigned char ev_raw[];
   const int SPEC_K = sp.K;
   const int k = blockIdx.x, slot = blockIdx.y;
-  if (round > 0 && slot >= sp.cnt[g]) return;
-  const int b = (round == 0) ? slot : sp.list[(size_t)(g % 3) * db.B + slot];
+  const int b = spec_band(db, sp, round, g, slot);
+  if (b < 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x;
   BandState* st = &db.state[b];
@@ -779,7 +798,7 @@ __global__ void __launch_bounds__(512, 1) k_trial_eval3(const __grid_constant__ 
   __syncthreads();
   const double* vs = db.vel_start + 4 * (size_t)b;
   const double* vg = db.vel_goal + 4 * (size_t)b;
-  double* res = sp.res + ((size_t)b * SPEC_K + k) * RES_STRIDE;
+  double* res = sp.res + ((size_t)b * SPEC_K_MAX + k) * RES_STRIDE;
   {
     const bool ok = res[5] != 0.0;
     const double lambda = res[6];
@@ -810,7 +829,7 @@ __global__ void __launch_bounds__(512, 1) k_trial_eval3(const __grid_constant__ 
   /* ---- the last CTA of the band: accept / reject replay, sequential over the K trials */
   __threadfence();
   for (int e = tid; e < kact * RES_STRIDE; e += nthreads) /* L2 reads: the other trials' rows were written by other SMs */
-    sRes[e] = __ldcg(sp.res + (size_t)b * SPEC_K * RES_STRIDE + e);
+    sRes[e] = __ldcg(sp.res + (size_t)b * SPEC_K_MAX * RES_STRIDE + e);
   __syncthreads();
   if (tid == 0) {
     arrive[b] = 0; /* ready for the next round (stream order) */
@@ -818,7 +837,7 @@ __global__ void __launch_bounds__(512, 1) k_trial_eval3(const __grid_constant__ 
     da.st = st; da.chi_parts = db.chi_parts + (size_t)b * db.chunks * 4;
     da.lambda_init = (round == 0 && iteration == 0) ? band_lambda_init(db, b, n) : 0.0;
     da.need = sp.need + b; da.qmax = sp.qmax + b; da.cnt_next = sp.cnt + g + 1;
-    da.list_next = sp.list + (size_t)((g + 1) % 3) * db.B;
+    da.list_next = sp.list + (size_t)((g + 1) % SPEC_LISTS) * db.B;
     da.defer = db.defer + b; da.tag = tag;
     da.b = b; da.n = n; da.K = SPEC_K; da.iteration = iteration; da.round = round; da.q0 = q0; da.tile = db.tile;
     sAcc[0] = spec_decide(da, sRes);

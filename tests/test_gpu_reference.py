@@ -292,3 +292,25 @@ def test_per_trial_evaluation_kernel_is_bit_identical(cfg, autosize, cands, monk
     for key, h in outs.items():
         assert np.array_equal(ref.n, h.n) and np.array_equal(ref.lm_iters, h.lm_iters) and np.array_equal(ref.status, h.status), key
         assert np.array_equal(ref.poses, h.poses) and np.array_equal(ref.cost, h.cost), key
+
+
+@pytest.mark.parametrize("cfg,autosize", [("C1", True), ("C2", False)])
+def test_split_round0_schedule_is_bit_identical(cfg, autosize, monkeypatch):
+    """throughput regime (> 2368 bands), TEBGPU_OVERLAP=1: the retry rounds run on the side stream; with TEBGPU_SPLIT the side
+    stream also solves / evaluates round 0 for the bands it linearised while the main stream handles the others. Only the
+    schedule differs: every output must agree bit for bit with the one-stream schedule and with a repeat of itself"""
+    p, hb0 = scenes.make_config_batch(cfg, requests=80, candidates=32, seed=41, autosize=autosize)
+    assert hb0.B * 8 > 148 * 4 * 32
+    args = _args(p)
+    outs = []
+    for overlap, mode in (("0", "0"), ("1", "0"), ("1", "1"), ("1", "1")):
+        monkeypatch.setenv("TEBGPU_OVERLAP", overlap)
+        monkeypatch.setenv("TEBGPU_SPLIT", mode)
+        g = _gpu(hb0, p)
+        h = hb0.copy()
+        g.optimize(h, args)
+        g.close()
+        outs.append(h)
+    for h in outs[1:]:
+        assert np.array_equal(outs[0].n, h.n) and np.array_equal(outs[0].lm_iters, h.lm_iters) and np.array_equal(outs[0].status, h.status)
+        assert np.array_equal(outs[0].poses, h.poses) and np.array_equal(outs[0].cost, h.cost)
