@@ -276,7 +276,7 @@ int32_t tebgpu_create(const TebGpuLimits* lim, int32_t device, tebgpu_ctx** out)
   CUDA_TRY(c, cudaMalloc(&c->spec.dx, spec_sys * 4 * nc * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->Lf2, spec_sys * 4 * nc * HROW * sizeof(double)));
   CUDA_TRY(c, cudaMalloc(&c->dx2, spec_sys * 4 * nc * sizeof(double)));
-  c->spec.sel_list = nullptr; c->spec.sel_cnt = nullptr; c->spec.defer = nullptr; c->spec.skip_tag = 0;
+  c->spec.sel_list = nullptr; c->spec.sel_cnt = nullptr; c->spec.defer = nullptr; c->spec.skip_tag = 0; c->spec.lat_cap = 0;
   if (const char* e = std::getenv("TEBGPU_SPLIT")) c->split = std::atoi(e) != 0;
   CUDA_TRY(c, cudaMalloc(&c->spec.cnt, SPEC_CNT_CAP * sizeof(int32_t)));
   CUDA_TRY(c, cudaMalloc(&c->spec.list, SPEC_LISTS * B * sizeof(int32_t)));
@@ -680,6 +680,15 @@ static int32_t issue_optimize(tebgpu_ctx* ctx, const TebBatch* bt, const TebOpti
           const long long lat_wave = smem_lat <= 232448 ? 148LL * (232448 / smem_lat > 16 ? 16 : 232448 / smem_lat) : 0;
           const bool lat_solver = lat_wave > 0 && (ctx->warp_solver == 3 || (ctx->warp_solver == 4 && bk <= LAT_WAVES * lat_wave));
           if (lat_solver) k_solve_lat<<<bk, 32, smem_lat, s>>>(db, spec, it, round, g);
+          else if (round > 0 && ctx->warp_solver == 4 && lat_wave > 0) {
+            /* retry round of the throughput regime: both mappings are launched, the list length decides on the device */
+            SpecBufs sl = spec;
+            const long long cap = LAT_WAVES * lat_wave < bk ? LAT_WAVES * lat_wave : bk;
+            sl.lat_cap = (int32_t)cap;
+            k_solve_lat<<<(unsigned)cap, 32, smem_lat, s>>>(db, sl, it, round, g);
+            k_solve_tpb<10><<<warps, 32, tpb_ring_bytes(10), s>>>(db, sl, it, round, g);
+            ++launches;
+          }
           else if (warp_solver) k_solve_warp<<<(bk + SW_WARPS - 1) / SW_WARPS, 32 * SW_WARPS, 0, s>>>(db, spec, it, round, g);
           else if (ring == 30) k_solve_tpb<30><<<warps, 32, tpb_ring_bytes(30), s>>>(db, spec, it, round, g);
           else if (ring == 20) k_solve_tpb<20><<<warps, 32, tpb_ring_bytes(20), s>>>(db, spec, it, round, g);

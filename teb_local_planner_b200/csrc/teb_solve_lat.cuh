@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
   const int SPEC_K = sp.K;
   const int slot = t_sys / SPEC_K;
   const int k_trial = t_sys - slot * SPEC_K;
+  if (round > 0 && sp.lat_cap > 0 && !retry_round_takes_lat(sp, round, g)) return; /* list too long: k_solve_tpb does this round */
   const int b = spec_band(db, sp, round, g, slot);
   if (b < 0) return;                                  /* whole warp */
   const BandState* st = &db.state[b];

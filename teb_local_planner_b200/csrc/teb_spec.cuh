@@ -47,7 +47,15 @@ struct SpecBufs {
   const int32_t* sel_cnt;
   const int32_t* defer;
   int32_t skip_tag;
+  /* Retry rounds of the throughput regime are launched twice, as k_solve_lat (grid = lat_cap systems) and as
+   * k_solve_tpb; the length of the retry list, known only on the device, decides which of the two does the work:
+   * lists of up to lat_cap / K bands (the last retry round: a fraction of a percent of the bands) take the latency
+   * mapping instead of paying a thread-per-system solve's fixed 0.26 ms. 0: no such choice, the launched kernel works. */
+  int32_t lat_cap;
 };
+__device__ __forceinline__ bool retry_round_takes_lat(const SpecBufs& sp, int round, int g) {
+  return round > 0 && sp.lat_cap > 0 && (long long)sp.cnt[g] * sp.K <= sp.lat_cap;
+}
 
 /* the band of system slot `slot` in this launch, or -1 */
 __device__ __forceinline__ int spec_band(const DevBatch& db, const SpecBufs& sp, int round, int g, int slot) {
@@ -98,6 +106,7 @@ __global__ void __launch_bounds__(32) k_solve_tpb(DevBatch db, SpecBufs sp, int 
   /* system t = K * slot + k; round 0: slot = band, retry rounds: slot indexes the compact list of round g */
   const int slot = t / SPEC_K;
   const int k = t - slot * SPEC_K;
+  if (retry_round_takes_lat(sp, round, g)) return; /* k_solve_lat does this round */
   const int b = spec_band(db, sp, round, g, slot);
   if (b < 0) return; /* threads are independent: no warp-level primitive below */
   bool work = true;
@@ -468,6 +477,7 @@ __global__ void __launch_bounds__(32 * SPEC_K_MAX, MINB) k_trial_eval(DevBatch d
  * replays g2o's accept / reject chain (spec_decide) and the CTA commits the accepted trial state.
  * ==================================================================================================================== */
 constexpr int EV2_THREADS = 256;
+constexpr int EV2_MINB = 4;       /* CTAs per SM the throughput variant is compiled for (register cap 85) */
 constexpr int EV2_TILE = 30;      /* poses evaluated per warp task: lanes 0 .. 29 (lanes 30, 31: halo) */
 __host__ __device__ inline int ev2_tiles(int n_cap) { return (n_cap + EV2_TILE - 1) / EV2_TILE; }
 __host__ __device__ inline size_t eval2_smem_bytes(int n_cap, int M_cap, int K) {
@@ -642,7 +652,7 @@ __device__ __forceinline__ void eval_tile_task(const KParams& kp, const DevBatch
 }
 
 template <bool GEOM, int NT> /* NT = 256 (throughput regime, 2 CTAs per SM) or 512 (latency regime: more warps per band) */
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_trial_eval2(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp,
+__global__ void __launch_bounds__(NT, NT == 256 ? (GEOM ? 2 : EV2_MINB) : 1) k_trial_eval2(const __grid_constant__ DevBatch db, const __grid_constant__ KParams kp,
                                                              const __grid_constant__ SpecBufs sp, int iteration, int round,
                                                              int g, int tag) {
   extern __shared__ __align__(16) unsigned char ev_raw[];
