@@ -464,6 +464,9 @@ static void launch_trial_eval(tebgpu_ctx* ctx, const SpecBufs& spec, const DevBa
   }
   if (!ctx->eval_v1) { /* second generation: one lane per pose */
     const bool wide = (long long)B * 2 <= 148; /* a CTA per band leaves SMs idle: give each band up to 16 warps */
+    /* two compilations: <., 256> is built for 4 CTAs per SM (64 registers, a few spills) - what a full machine wants;
+     * <., 512> keeps all 116 registers - faster per thread, what a part-filled machine (the latency regime) wants */
+    const bool relaxed = wide || (long long)B * 8 <= 148LL * 4 * 32;
     /* one warp per 30-pose tile of the longest band (2 .. 8 warps; 4 .. 16 in the wide variant: two trials side by side),
      * so that the K x tiles warp tasks split evenly and nobody idles at the barrier */
     int warps = ev2_tiles(db.n_cap);
@@ -471,10 +474,10 @@ static void launch_trial_eval(tebgpu_ctx* ctx, const SpecBufs& spec, const DevBa
     if (wide) warps = 2 * warps;
     const int nt = 32 * warps;
     if (kp.generic) {
-      if (wide) k_trial_eval2<true, 512><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
+      if (relaxed) k_trial_eval2<true, 512><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
       else k_trial_eval2<true, 256><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
     } else {
-      if (wide) k_trial_eval2<false, 512><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
+      if (relaxed) k_trial_eval2<false, 512><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
       else k_trial_eval2<false, 256><<<B, nt, smem, st>>>(db, kp, spec, it, round, g, tag);
     }
     return;
