@@ -465,8 +465,9 @@ static void launch_trial_eval(tebgpu_ctx* ctx, const SpecBufs& spec, const DevBa
   if (!ctx->eval_v1) { /* second generation: one lane per pose */
     const bool wide = (long long)B * 2 <= 148; /* a CTA per band leaves SMs idle: give each band up to 16 warps */
     /* two compilations: <., 256> is built for 4 CTAs per SM (64 registers, a few spills) - what a full machine wants;
-     * <., 512> keeps all 116 registers - faster per thread, what a part-filled machine (the latency regime) wants */
-    const bool relaxed = wide || (long long)B * 8 <= 148LL * 4 * 32;
+     * <., 512> keeps all 116 registers - faster per thread, right while every CTA is resident at 2 per SM anyway
+     * (measured on C4: 128 / 256 bands 4.86 / 6.62 ms against 5.06 / 6.96; 512 bands 8.8 against 7.9 the other way) */
+    const bool relaxed = wide || B <= 2 * 148;
     /* one warp per 30-pose tile of the longest band (2 .. 8 warps; 4 .. 16 in the wide variant: two trials side by side),
      * so that the K x tiles warp tasks split evenly and nobody idles at the barrier */
     int warps = ev2_tiles(db.n_cap);
