@@ -204,7 +204,7 @@ typedef struct TebGpuLimits {
   int32_t max_bands;      /* B capacity */
   int32_t max_poses;      /* n_cap capacity (<= 512) */
   int32_t max_scenes;
-  int32_t max_obstacles;  /* M_cap capacity (<= 256) */
+  int32_t max_obstacles;  /* M_cap capacity (<= 1024: 16 association words per pose; the scene's table is staged in shared memory) */
   int32_t max_viapoints;  /* V_cap capacity */
   int32_t max_obst_vertices; /* PV_cap capacity (0: Point / Circular obstacles only) */
 } TebGpuLimits;

@@ -38,7 +38,7 @@ constexpr int ESTR = 10;               /* residual slots per anchor: vx|v, omega
 constexpr int START_E = 21;            /* start-edge block: 3 rows x 7 columns, then its 3 residuals */
 constexpr int HROW = 12;               /* doubles per band row: 11 band entries + rhs */
 constexpr int KB_THREADS = 128;
-constexpr int MAX_MW = 4;              /* association bitmask words per pose (<= 256 obstacles) */
+constexpr int MAX_MW = 16;             /* association bitmask words per pose (<= 1024 obstacles per scene) */
 
 struct BandState {
   double lambda, ni, current_chi, chi2_final;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) k_build_graph(DevBatch db, KParams kp) {
      * EdgeVelocityObstacleRatio (first_vertex, :482) */
     const int first_vertex = kp.has_vor ? 0 : 1;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      unsigned long long mask[MAX_MW] = {0, 0, 0, 0};
+      unsigned long long mask[MAX_MW] = {0};
       if (kp.has_obst && i >= first_vertex && i <= n - 2) {
         const double px = P[4 * i], py = P[4 * i + 1], th = P[4 * i + 2];
         double sn, cs;

@@ -188,7 +188,7 @@ bool TebOptimalPlanner::runBatch(const TebConfig& cfg, const std::vector<TebOpti
   int M_cap = 1;
   for (auto* oc : scenes)
     if (oc) M_cap = std::max(M_cap, (int)oc->size());
-  if (M_cap > 256) { std::fprintf(stderr, "optimizeTEB: more than 256 obstacles per scene is not supported\n"); return false; }
+  if (M_cap > 1024) { std::fprintf(stderr, "optimizeTEB: more than 1024 obstacles per scene is not supported\n"); return false; }
   std::vector<TebObstacle> obst((size_t)S * M_cap);
   std::vector<int32_t> obst_count(S, 0);
   std::vector<std::vector<double>> pools(S);

@@ -314,3 +314,21 @@ def test_split_round0_schedule_is_bit_identical(cfg, autosize, monkeypatch):
     for h in outs[1:]:
         assert np.array_equal(outs[0].n, h.n) and np.array_equal(outs[0].lm_iters, h.lm_iters) and np.array_equal(outs[0].status, h.status)
         assert np.array_equal(outs[0].poses, h.poses) and np.array_equal(outs[0].cost, h.cost)
+
+
+def test_many_obstacles_per_scene(oracle):
+    """600 point obstacles in one scene (10 association words per pose; round 1 stopped at 256): same association, same
+    trajectories as the closed-form oracle"""
+    p = abi.default_params()
+    p.teb_autosize = 0
+    hb = scenes.make_batch(40, 600, 6, seed=77, amp=1.0)
+    args = _args(p)
+    g = _gpu(hb, p)
+    hg = hb.copy()
+    g.optimize(hg, args)
+    g.close()
+    ha = hb.copy()
+    oracle.optimize_batch(p, ha, args, jac_mode=oracle.JAC_ANALYTIC, threads=4)
+    assert np.array_equal(hg.n, ha.n) and np.array_equal(hg.lm_iters, ha.lm_iters)
+    assert _diff(hg.poses, hg.n, ha.poses, ha.n).max() < 1e-6
+    assert np.allclose(hg.cost, ha.cost, rtol=1e-6)
