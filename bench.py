@@ -545,9 +545,9 @@ def run_b200(a, rank, local_rank, world):
                 "roofline_kernel_b_solve": roof_s, "roofline_kernel_b_eval": roof_e, "speculation_width": spec_k, "speculation_width_first_iteration": spec_first,
                 "single_request": single, "parity_sample": parity,
                 "kernel_time_share": shares,
-                "kernel_time_share_note": "from a separate profiled pass (CUDA events around every launch, one stream); in the "
-                                          "timed steps the retry rounds (k_lm_step_or_retry_rounds) run on a side stream under "
-                                          "the next k_linearize",
+                "kernel_time_share_note": "from a separate profiled pass (CUDA events around every launch); "
+                                          "k_lm_step_or_retry_rounds = the solve + evaluation launches of the retry rounds "
+                                          "(same stream as everything else in the throughput regime)",
                 "cpu_baseline": cpu, "clocks": clocks,
                 "best_candidate_of_request0": int(best[0])}
         print(json.dumps(line), flush=True)
