@@ -140,7 +140,7 @@ __device__ __forceinline__ void ld_record(uint32_t addr, uint32_t yaddr, double 
 /* TEBGPU_LAT_TIMING=1: block 0 prints the cycles of its phases (device printf; diagnostics only) */
 __device__ int g_lat_timing = 0;
 
-__global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int iteration, int round, int g) {
+__global__ void __launch_bounds__(32, 1) k_solve_lat(DevBatch db, SpecBufs sp, int iteration, int round, int g) {
   extern __shared__ __align__(128) unsigned char sl_raw[];
   const int lane = threadIdx.x;
   const int t_sys = blockIdx.x;                       /* system index = K * slot + k, as in k_solve_tpb */
@@ -193,21 +193,32 @@ __global__ void __launch_bounds__(32) k_solve_lat(DevBatch db, SpecBufs sp, int 
    *   [11]. Done in chunks of 32 rows, ascending: a chunk reads rows of its own and the next chunk only. */
   {
     const int top_rows = m + 11;
+    /* lane l reads element k = (j + l / 4) mod 11 of its column in step j: rows are 96 bytes apart, so with one k for
+     * the whole warp eight lanes would hit every bank (8-way conflict, 16 wavefronts per access); staggering k by l / 4
+     * spreads the 32 accesses over all banks (2 wavefronts, the minimum for 256 bytes) */
+    const int kst = lane >> 2;
     for (int q0r = 0; q0r < top_rows; q0r += 32) {
       const int q = q0r + lane;
       double v[11];
       const bool is_top = q < top_rows;
+      const bool real = is_top && row_is_real(q, n);
 #pragma unroll
-      for (int k = 0; k < 11; ++k) {
+      for (int j = 0; j < 11; ++j) {
+        int k = j + kst;
+        k = k >= 11 ? k - 11 : k;
         const bool on = is_top && q + k < top_rows;
         const double x = Hs[on ? (q + k) * HROW + k : 0];
-        v[k] = on ? x : 0.0;
+        v[j] = on ? x : 0.0;
+        if (k == 0 && real) v[j] += lambda;
       }
-      if (is_top && row_is_real(q, n)) v[0] += lambda;
       __syncwarp();
       if (is_top) {
 #pragma unroll
-        for (int k = 0; k < 11; ++k) Hs[q * HROW + k] = v[k];
+        for (int j = 0; j < 11; ++j) {
+          int k = j + kst;
+          k = k >= 11 ? k - 11 : k;
+          Hs[q * HROW + k] = v[j];
+        }
       }
       __syncwarp();
     }
