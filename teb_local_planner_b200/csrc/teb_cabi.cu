@@ -617,6 +617,8 @@ static int32_t issue_optimize(tebgpu_ctx* ctx, const TebBatch* bt, const TebOpti
     if (need_cnt > SPEC_CNT_CAP) { ctx->err = "outer x inner iterations exceed the retry-list counters"; return TEBGPU_ERR_CAPACITY; }
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->spec.cnt, 0, (size_t)need_cnt * sizeof(int32_t), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->defer, 0, (size_t)B * sizeof(int32_t), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->arrive, 0, (size_t)B * sizeof(int32_t), st)); /* k_trial_eval3's arrival counters: a call that
+                                                                                    was cut short must not leak into the next */
   }
   /* Retry rounds (bands that rejected all trials of a round) can run on a side stream, followed by kernel A of the next
    * inner iteration for exactly those bands - and, with TEBGPU_SPLIT, by ROUND 0 of that iteration for them - while the
