@@ -15,6 +15,7 @@
  */
 #include <teb_local_planner/optimal_planner.h>
 #include <teb_local_planner/g2o_types/penalties.h>
+#include <teb_local_planner/h_signature.h>
 
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
@@ -206,7 +207,7 @@ void set_velocities(RefPlanner& pl, const double* vs, const double* vg, int rotd
 
 extern "C" {
 
-int32_t teb_ref_abi(void) { return 2; }
+int32_t teb_ref_abi(void) { return 3; }
 
 /* TebConfig::TebConfig() (teb_config.h:245-390) read back through the POD mirror */
 void teb_ref_default_params(TebParams* p) {
@@ -454,6 +455,33 @@ int32_t teb_ref_optimize_batch(const TebParams* p, const TebBatch* bt, const Teb
     for (auto& th : pool) th.join();
   }
   return bad ? -1 : 0;
+}
+
+/* HomotopyClassPlanner::calculateEquivalenceClass (homotopy_class_planner.hpp:46-63) on the poses of one band, executed
+ * by the reference's own h_signature.h: include_dynamic_obstacles == 0 -> HSignature (out[0..1] = Re, Im of the long
+ * double value), else HSignature3d (out[0..M)); flags[0] = isValid(), flags[1] = isReasonable(). The point functor is
+ * homotopy_class_planner.h:72-75 (getCplxFromVertexPosePtr), restated here because that header pulls in boost::graph. */
+int32_t teb_ref_h_signature(const TebParams* p, const double* rec, int32_t n, const TebObstacle* obst, int32_t M, const double* verts,
+                            int32_t use_timediffs, double* out, int32_t* flags) {
+  Scene sc;
+  fill_scene(sc, p, obst, M, verts, nullptr, 0);
+  TimedElasticBand teb;
+  load_band(teb, rec, n);
+  auto cplx = [](const VertexPose* pose) { return std::complex<long double>(pose->x(), pose->y()); };
+  if (sc.cfg.obstacles.include_dynamic_obstacles) {
+    HSignature3d H(sc.cfg);
+    if (use_timediffs) H.calculateHSignature(teb.poses().begin(), teb.poses().end(), cplx, &sc.obstacles, teb.timediffs().begin(), teb.timediffs().end());
+    else H.calculateHSignature(teb.poses().begin(), teb.poses().end(), cplx, &sc.obstacles, boost::none, boost::none);
+    for (int m = 0; m < M && m < (int)H.values().size(); ++m) out[m] = H.values()[m];
+    if (flags) { flags[0] = H.isValid(); flags[1] = H.isReasonable(); }
+  } else {
+    HSignature H(sc.cfg);
+    H.calculateHSignature(teb.poses().begin(), teb.poses().end(), cplx, &sc.obstacles);
+    out[0] = (double)H.value().real();
+    out[1] = (double)H.value().imag();
+    if (flags) { flags[0] = H.isValid(); flags[1] = H.isReasonable(); }
+  }
+  return 0;
 }
 
 }  /* extern "C" */

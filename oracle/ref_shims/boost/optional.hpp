@@ -30,6 +30,8 @@ template <typename T> class optional<T&> {
  private:
   T* p_;
 };
+template <typename T> inline bool operator==(const optional<T>& o, none_t) { return !o; }
+template <typename T> inline bool operator!=(const optional<T>& o, none_t) { return bool(o); }
 template <typename It> inline It prior(It it) { return std::prev(it); }
 template <typename It> inline It next(It it) { return std::next(it); }
 }

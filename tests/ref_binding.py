@@ -64,7 +64,9 @@ def lib():
         L.teb_ref_build_system.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, vp, i, d, vp, vp, C.POINTER(d), vp, i, C.POINTER(i)]
         L.teb_ref_optimize_batch.restype = i
         L.teb_ref_optimize_batch.argtypes = [vp, vp, vp, i, i]
-        assert L.teb_ref_abi() == 2
+        L.teb_ref_h_signature.restype = i
+        L.teb_ref_h_signature.argtypes = [vp, vp, i, vp, i, vp, i, vp, vp]
+        assert L.teb_ref_abi() == 3
         _lib = L
     return _lib
 
@@ -183,3 +185,19 @@ def build_system(params, rec, n, obstacles, via=None, vel_start=None, vel_goal=N
     if want_edges:
         return H, b, chi2.value, edges[:ne.value]
     return H, b, chi2.value
+
+
+def h_signature(params, rec, n, obstacles, use_timediffs=True, obst_vertices=None):
+    """calculateEquivalenceClass by the reference's own h_signature.h: complex H (2-D) or M values (x-y-t), plus
+    (isValid, isReasonable)"""
+    rec = np.ascontiguousarray(rec[:n], dtype=np.float64)
+    ob = np.ascontiguousarray(obstacles, dtype=abi.OBST_DTYPE)
+    pv = None if obst_vertices is None or len(obst_vertices) == 0 else np.ascontiguousarray(obst_vertices, dtype=np.float64).reshape(-1, 2)
+    out = np.zeros(max(2, len(ob)))
+    flags = np.zeros(2, np.int32)
+    rc = lib().teb_ref_h_signature(C.addressof(params), rec.ctypes.data, n, ob.ctypes.data if len(ob) else None, len(ob),
+                                   pv.ctypes.data if pv is not None else None, int(use_timediffs), out.ctypes.data, flags.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"teb_ref_h_signature rc={rc}")
+    val = out[:len(ob)].copy() if params.include_dynamic_obstacles else complex(out[0], out[1])
+    return val, bool(flags[0]), bool(flags[1])

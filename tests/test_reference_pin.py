@@ -270,3 +270,47 @@ def test_golden_reference_vectors_are_current():
     fresh = make_golden_ref.generate(only=("C1", "via_ordered"))
     for k, v in fresh.items():
         assert np.array_equal(z[k], v), k
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3", "C4"])
+def test_h_signatures_match_the_reference_header(oracle, cfg):
+    """calculateEquivalenceClass executed by the reference's own h_signature.h (HSignature: long double complex
+    accumulation; HSignature3d: numeric integration over the x-y-t obstacle 'conductors', with and without the band's
+    time differences) against the oracle restatement, plus isValid / isReasonable and the class comparison the planner
+    derives from them. 2-D: relative 1e-15 of the long double result; 3-D: bit equal."""
+    from tests.golden import make_golden
+    p, hb = scenes.make_config_batch(cfg, candidates=6, seed=17)
+    obst = hb.obstacles[0][:hb.obst_count[0]]
+    sig2 = []
+    for b in range(hb.B):
+        rec, n = hb.poses[b], int(hb.n[b])
+        p.include_dynamic_obstacles = 0
+        want, valid, reasonable = rb.h_signature(p, rec, n, obst)
+        got = oracle.h_signature(p, rec, n, obst)
+        assert valid and np.isfinite(want.real) and np.isfinite(want.imag)
+        assert abs(got - want) <= 1e-15 * max(1.0, abs(want)), (cfg, b, got, want)
+        sig2.append((got, want))
+        p.include_dynamic_obstacles = 1
+        for use_dt in (True, False):
+            want3, valid3, reasonable3 = rb.h_signature(p, rec, n, obst, use_timediffs=use_dt)
+            got3 = oracle.h_signature(p, rec, n, obst, use_timediffs=use_dt)
+            assert valid3
+            assert np.array_equal(got3, want3), (cfg, b, use_dt, np.abs(got3 - want3).max())
+            assert reasonable3 == bool(np.all(want3 <= 1.0))
+    # HSignature::isEqual (h_signature.h:195-206): both parts within h_signature_threshold - same partition either way
+    thr = p.h_signature_threshold
+    eq = lambda x, y: abs(x.real - y.real) <= thr and abs(x.imag - y.imag) <= thr
+    for i in range(hb.B):
+        for j in range(hb.B):
+            assert eq(sig2[i][0], sig2[j][0]) == eq(sig2[i][1], sig2[j][1])
+    # the committed H-signature fixtures (tests/golden/golden_v2.npz) agree with the reference header as well
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v2.npz"), allow_pickle=False)
+    for name, pp, hbb in make_golden.hsig_cases():
+        ob = hbb.obstacles[0][:hbb.obst_count[0]]
+        for b in range(hbb.B):
+            want, _, _ = rb.h_signature(pp, hbb.poses[b], hbb.n[b], ob)
+            have = g[name][b]
+            if pp.include_dynamic_obstacles:
+                assert np.array_equal(want, have[:len(ob)])
+            else:
+                assert abs(want - complex(have[0], have[1])) <= 1e-15 * max(1.0, abs(want))
