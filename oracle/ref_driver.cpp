@@ -207,7 +207,7 @@ void set_velocities(RefPlanner& pl, const double* vs, const double* vg, int rotd
 
 extern "C" {
 
-int32_t teb_ref_abi(void) { return 3; }
+int32_t teb_ref_abi(void) { return 4; }
 
 /* TebConfig::TebConfig() (teb_config.h:245-390) read back through the POD mirror */
 void teb_ref_default_params(TebParams* p) {
@@ -482,6 +482,116 @@ int32_t teb_ref_h_signature(const TebParams* p, const double* rec, int32_t n, co
     if (flags) { flags[0] = H.isValid(); flags[1] = H.isReasonable(); }
   }
   return 0;
+}
+
+
+namespace {
+int put_band(const TimedElasticBand& teb, double* out, int cap) {
+  const int n = teb.sizePoses();
+  if (4 * n > cap) return -1;
+  store_band(teb, out, n);
+  return 4 * n;
+}
+void twist_from(const double* v, geometry_msgs::Twist& t) { t.linear.x = v[0]; t.linear.y = v[1]; t.angular.z = v[2]; }
+}  // namespace
+
+/* ---- band operations of the host-side API, one entry point for the pin test (tests/test_host_pin.py compares this
+ * library's answers with the drop-in layer's, operation by operation):
+ *   op 1  initTrajectoryToGoal(start, goal, diststep, max_vel_x, min_samples, backwards)   args: s[3] g[3] diststep vx min_samples backwards
+ *   op 2  initTrajectoryToGoal(plan, max_vel_x, max_vel_theta, estimate_orient, min_samples, backwards)   args: vx vth est min_samples backwards np plan[np][3]
+ *   op 3  initTrajectoryToGoal(2-D path, ...) of timed_elastic_band.hpp   args: vx vth accx acct so go (NaN = none) min_samples backwards np pts[np][2]
+ *   op 4  updateAndPruneTEB   rec in; args: s[3] g[3] min_samples
+ *   op 5  findClosestTrajectoryPose(point, &dist, begin_idx)   args: px py begin -> out: idx dist
+ *   op 6  getSumOfAllTimeDiffs, getAccumulatedDistance, getSumOfTimeDiffsUpToIdx(args[0])
+ *   op 7  isTrajectoryInsideRegion(radius, max_dist_behind_robot, skip_poses) -> out[0]
+ *   op 8  getVelocityCommand(look_ahead)   args: look_ahead max_vel_y -> out: ok vx vy omega
+ *   op 9  getVelocityProfile   args: max_vel_y vs[4] vg[4] -> out: (n + 1) x (vx, vy, omega)
+ *   op 10 getFullTrajectory    args: max_vel_y vs[4] vg[4] -> out: n x (x, y, yaw, vx, vy, omega, t)
+ *   op 11 autoResize(dt_ref, dt_hysteresis, min_samples, max_samples, fast_mode)
+ * Bands go in and out as (x, y, theta, dt) records; the return value is the number of output doubles (< 0: capacity). */
+
+int32_t teb_ref_band_op(int32_t op, const double* rec, int32_t n, const double* a, int32_t na, double* out, int32_t cap) {
+  (void)na;
+  TebConfig cfg;
+  TimedElasticBand teb;
+  if (rec && n > 0) load_band(teb, rec, n);
+  switch (op) {
+    case 1:
+      teb.initTrajectoryToGoal(PoseSE2(a[0], a[1], a[2]), PoseSE2(a[3], a[4], a[5]), a[6], a[7], (int)a[8], a[9] != 0);
+      return put_band(teb, out, cap);
+    case 2: {
+      std::vector<geometry_msgs::PoseStamped> plan((size_t)a[5]);
+      for (size_t i = 0; i < plan.size(); ++i) {
+        plan[i].pose.position.x = a[6 + 3 * i]; plan[i].pose.position.y = a[7 + 3 * i];
+        plan[i].pose.orientation = tf::createQuaternionMsgFromYaw(a[8 + 3 * i]);
+      }
+      teb.initTrajectoryToGoal(plan, a[0], a[1], a[2] != 0, (int)a[3], a[4] != 0);
+      return put_band(teb, out, cap);
+    }
+    case 3: {
+      std::vector<Eigen::Vector2d> path((size_t)a[8]);
+      for (size_t i = 0; i < path.size(); ++i) path[i] = Eigen::Vector2d(a[9 + 2 * i], a[10 + 2 * i]);
+      auto opt = [](double v) { return std::isnan(v) ? boost::optional<double>() : boost::optional<double>(v); };
+      teb.initTrajectoryToGoal(path.begin(), path.end(), [](const Eigen::Vector2d& p) -> const Eigen::Vector2d& { return p; }, a[0], a[1],
+                               opt(a[2]), opt(a[3]), opt(a[4]), opt(a[5]), (int)a[6], a[7] != 0);
+      return put_band(teb, out, cap);
+    }
+    case 4: {
+      PoseSE2 s(a[0], a[1], a[2]), g(a[3], a[4], a[5]);
+      teb.updateAndPruneTEB(s, g, (int)a[6]);
+      return put_band(teb, out, cap);
+    }
+    case 5: {
+      double dist = -1;
+      out[0] = teb.findClosestTrajectoryPose(Eigen::Vector2d(a[0], a[1]), &dist, (int)a[2]);
+      out[1] = dist;
+      return 2;
+    }
+    case 6:
+      out[0] = teb.getSumOfAllTimeDiffs(); out[1] = teb.getAccumulatedDistance(); out[2] = teb.getSumOfTimeDiffsUpToIdx((int)a[0]);
+      return 3;
+    case 7:
+      out[0] = teb.isTrajectoryInsideRegion(a[0], a[1], (int)a[2]);
+      return 1;
+    case 11:
+      teb.autoResize(a[0], a[1], (int)a[2], (int)a[3], a[4] != 0);
+      return put_band(teb, out, cap);
+    default: break;
+  }
+  /* planner-level operations */
+  cfg.robot.max_vel_y = (op == 8) ? a[1] : a[0];
+  ObstContainer obst;
+  RefPlanner pl(cfg, &obst, nullptr);
+  load_band(pl.teb(), rec, n);
+  if (op == 8) {
+    double vx = 0, vy = 0, om = 0;
+    out[0] = pl.getVelocityCommand(vx, vy, om, (int)a[0]);
+    out[1] = vx; out[2] = vy; out[3] = om;
+    return 4;
+  }
+  geometry_msgs::Twist ts, tg;
+  twist_from(a + 1, ts); twist_from(a + 5, tg);
+  if (a[4] != 0) pl.setVelocityStart(ts);
+  if (a[8] != 0) pl.setVelocityGoal(tg); else pl.setVelocityGoalFree();
+  if (op == 9) {
+    std::vector<geometry_msgs::Twist> prof;
+    pl.getVelocityProfile(prof);
+    if (3 * (int)prof.size() > cap) return -1;
+    for (size_t i = 0; i < prof.size(); ++i) { out[3 * i] = prof[i].linear.x; out[3 * i + 1] = prof[i].linear.y; out[3 * i + 2] = prof[i].angular.z; }
+    return 3 * (int)prof.size();
+  }
+  if (op == 10) {
+    std::vector<TrajectoryPointMsg> tr;
+    pl.getFullTrajectory(tr);
+    if (7 * (int)tr.size() > cap) return -1;
+    for (size_t i = 0; i < tr.size(); ++i) {
+      double* o = out + 7 * i;
+      o[0] = tr[i].pose.position.x; o[1] = tr[i].pose.position.y; o[2] = tf::getYaw(tr[i].pose.orientation);
+      o[3] = tr[i].velocity.linear.x; o[4] = tr[i].velocity.linear.y; o[5] = tr[i].velocity.angular.z; o[6] = tr[i].time_from_start.toSec();
+    }
+    return 7 * (int)tr.size();
+  }
+  return -2;
 }
 
 }  /* extern "C" */

@@ -66,7 +66,7 @@ def lib():
         L.teb_ref_optimize_batch.argtypes = [vp, vp, vp, i, i]
         L.teb_ref_h_signature.restype = i
         L.teb_ref_h_signature.argtypes = [vp, vp, i, vp, i, vp, i, vp, vp]
-        assert L.teb_ref_abi() == 3
+        assert L.teb_ref_abi() == 4
         _lib = L
     return _lib
 
