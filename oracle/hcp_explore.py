@@ -9,7 +9,12 @@ Follows the reference line by line, sequentially and without batching:
   * initTrajectoryToGoal (path version) include/teb_local_planner/timed_elastic_band.hpp:46-185
   * addEquivalenceClassIfNew, isEqual   src/homotopy_class_planner.cpp:178-211, h_signature.h:191-207, :366-388
 H-signature values come from oracle/teb_oracle.c (teb_oracle_h_signature, long double). Pure Python: small cases only.
-PARITY UNPINNED: boost is not available in this image, so the random stream is restated from the published algorithm.
+PARITY PINNED (tests/test_reference_pin.py::test_candidate_exploration_matches_the_reference_planner): the reference's own
+homotopy_class_planner.cpp / graph_search.cpp / h_signature.h, compiled into oracle/_ref against stand-in headers, propose
+the same candidates in the same order with the same initial bands (1e-12) on random scenes - both graphs, both signature
+kinds, two cycles. Restated on BOTH sides (boost is not in the image): mt19937 is the standard engine, the
+uniform_real_distribution follows boost's published one-draw algorithm. The pin caught one thing the restatement had
+wrong: the roadmap draws its y sample before its x sample (unspecified argument evaluation order, right-to-left with GCC).
 """
 import math
 
@@ -268,8 +273,11 @@ class Explorer:
         pos = [start[:2].copy()]
         diff = diff / sg
         for _ in range(self.hcp["roadmap_graph_no_samples"]):
-            sx = self.rng.uniform(0, sg * scale)
+            # Eigen::Vector2d(distribution_x(gen), distribution_y(gen)) (graph_search.cpp:274): the order in which the two
+            # arguments are evaluated is unspecified in C++; GCC - what the reference is built with - evaluates them right
+            # to left, so the y sample is drawn FIRST (pinned against the reference compiled here, tests/test_reference_pin.py)
             sy = self.rng.uniform(0, width)
+            sx = self.rng.uniform(0, sg * scale)
             pos.append(origin + np.array([c * sx - s * sy, s * sx + c * sy]))
         pos.append(goal[:2].copy())
         adj = self._edges(pos, diff, thr, dist_to_obst)

@@ -16,6 +16,7 @@
 #include <teb_local_planner/optimal_planner.h>
 #include <teb_local_planner/g2o_types/penalties.h>
 #include <teb_local_planner/h_signature.h>
+#include <teb_local_planner/homotopy_class_planner.h>
 
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
@@ -207,7 +208,7 @@ void set_velocities(RefPlanner& pl, const double* vs, const double* vg, int rotd
 
 extern "C" {
 
-int32_t teb_ref_abi(void) { return 4; }
+int32_t teb_ref_abi(void) { return 5; }
 
 /* TebConfig::TebConfig() (teb_config.h:245-390) read back through the POD mirror */
 void teb_ref_default_params(TebParams* p) {
@@ -592,6 +593,46 @@ int32_t teb_ref_band_op(int32_t op, const double* rec, int32_t n, const double* 
     return 7 * (int)tr.size();
   }
   return -2;
+}
+
+/* HomotopyClassPlanner::exploreEquivalenceClassesAndInitTebs (homotopy_class_planner.cpp:339-365) of the reference -
+ * graph_search.cpp's lrKeyPointGraph (hcp[5] == 0) or ProbRoadmapGraph (!= 0), DepthFirst, addAndInitNewTeb with the
+ * path variant of initTrajectoryToGoal, H-signature filtering - on a fresh planner, `cycles` times with clearPlanner() in
+ * between (the roadmap's random generator lives on, as it does between planning cycles).
+ * hcp = {max_number_classes, obstacle_heading_threshold, roadmap_graph_area_width, roadmap_graph_area_length_scale,
+ *        roadmap_graph_no_samples, simple_exploration}. counts[c] = candidates of cycle c; then, per candidate in order,
+ * its number of poses; out = the candidates' (x, y, theta, dt) records back to back. Returns the doubles written. */
+int32_t teb_ref_hcp_explore(const TebParams* p, const double* hcp, const double* start3, const double* goal3, const TebObstacle* obst,
+                            int32_t M, const double* verts, int32_t cycles, double* out, int32_t cap, int32_t* counts, int32_t counts_cap) {
+  Scene sc;
+  fill_scene(sc, p, obst, M, verts, nullptr, 0);
+  sc.cfg.hcp.max_number_classes = (int)hcp[0];
+  sc.cfg.hcp.obstacle_heading_threshold = hcp[1];
+  sc.cfg.hcp.roadmap_graph_area_width = hcp[2];
+  sc.cfg.hcp.roadmap_graph_area_length_scale = hcp[3];
+  sc.cfg.hcp.roadmap_graph_no_samples = (int)hcp[4];
+  sc.cfg.hcp.simple_exploration = hcp[5] == 0;      /* true: lrKeyPointGraph, false: ProbRoadmapGraph (homotopy_class_planner.cpp:84-87) */
+  sc.cfg.hcp.enable_multithreading = false;
+  HomotopyClassPlanner hcpl(sc.cfg, &sc.obstacles, TebVisualizationPtr(), nullptr);
+  const PoseSE2 start(start3[0], start3[1], start3[2]), goal(goal3[0], goal3[1], goal3[2]);
+  int w = 0, ci = 0;
+  for (int c = 0; c < cycles; ++c) {
+    if (c > 0) hcpl.clearPlanner();
+    hcpl.exploreEquivalenceClassesAndInitTebs(start, goal, sc.cfg.obstacles.min_obstacle_dist, nullptr, false);
+    const TebOptPlannerContainer& tebs = hcpl.getTrajectoryContainer();
+    if (c >= counts_cap) return -1;
+    counts[c] = (int32_t)tebs.size();
+    ci = ci < cycles ? cycles : ci;
+    for (size_t k = 0; k < tebs.size(); ++k) {
+      const TimedElasticBand& teb = tebs[k]->teb();
+      const int n = teb.sizePoses();
+      if (ci >= counts_cap || w + 4 * n > cap) return -1;
+      counts[ci++] = n;
+      store_band(teb, out + w, n);
+      w += 4 * n;
+    }
+  }
+  return w;
 }
 
 }  /* extern "C" */

@@ -10,6 +10,7 @@
 namespace ros {
 class NodeHandle {};
 struct Duration { double s; explicit Duration(double v = 0) : s(v) {} double toSec() const { return s; } Duration& fromSec(double v) { s = v; return *this; } };
+inline bool ok() { return true; }
 struct Time { double s; Time() : s(0) {} static Time now() { return Time(); } double toSec() const { return s; } Duration operator-(const Time& o) const { return Duration(s - o.s); } };
 }
 #endif

@@ -14,6 +14,9 @@ class TebVisualization {
   void publishRobotFootprintModel(const PoseSE2&, const BaseRobotFootprintModel&, const std::string& = "", const std_msgs::ColorRGBA& = std_msgs::ColorRGBA()) {}
   void publishInfeasibleRobotPose(const PoseSE2&, const BaseRobotFootprintModel&, const std::vector<geometry_msgs::Point>&) {}
   void publishFeedbackMessage(const TebOptimalPlanner&, const ObstContainer&) {}
+  template <class Container> void publishFeedbackMessage(const Container&, unsigned int, const ObstContainer&) {}
+  template <class Graph> void publishGraph(const Graph&, const std::string& = "") {}
+  template <class Container> void publishTebContainer(const Container&, const std::string& = "") {}
 };
 typedef boost::shared_ptr<TebVisualization> TebVisualizationPtr;
 typedef boost::shared_ptr<const TebVisualization> TebVisualizationConstPtr;

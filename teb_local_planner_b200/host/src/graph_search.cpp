@@ -148,8 +148,12 @@ void ProbRoadmapGraph::createGraph(const PoseSE2& start, const PoseSE2& goal, do
   if (stretch != 1.0) corner = start.position() + 0.5 * (1.0 - stretch) * span * travel_dir - 0.5 * width * across;
   const int start_vertex = graph_.addVertex(start.position());
   for (int k = 0; k < cfg_->hcp.roadmap_graph_no_samples; ++k) {
-    const double along = uniform(0, length);
+    /* the reference builds the sample as Vector2d(distribution_x(gen), distribution_y(gen)) (graph_search.cpp:274); the
+     * evaluation order of the two arguments is unspecified and GCC - what the reference is built with - goes right to
+     * left: the y sample comes out of the generator FIRST (pinned against the reference compiled with the same compiler,
+     * tests/test_reference_pin.py) */
     const double aside = uniform(0, width);
+    const double along = uniform(0, length);
     graph_.addVertex(corner + Eigen::Vector2d(ca * along - sa * aside, sa * along + ca * aside));
   }
   const int goal_vertex = graph_.addVertex(goal.position());

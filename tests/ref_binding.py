@@ -66,7 +66,9 @@ def lib():
         L.teb_ref_optimize_batch.argtypes = [vp, vp, vp, i, i]
         L.teb_ref_h_signature.restype = i
         L.teb_ref_h_signature.argtypes = [vp, vp, i, vp, i, vp, i, vp, vp]
-        assert L.teb_ref_abi() == 4
+        L.teb_ref_hcp_explore.restype = i
+        L.teb_ref_hcp_explore.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, i, vp, i]
+        assert L.teb_ref_abi() == 5
         _lib = L
     return _lib
 
@@ -201,3 +203,30 @@ def h_signature(params, rec, n, obstacles, use_timediffs=True, obst_vertices=Non
         raise RuntimeError(f"teb_ref_h_signature rc={rc}")
     val = out[:len(ob)].copy() if params.include_dynamic_obstacles else complex(out[0], out[1])
     return val, bool(flags[0]), bool(flags[1])
+
+
+def hcp_explore(params, hcp, start, goal, obstacles, obst_vertices=None, cycles=1, prm=False):
+    """exploreEquivalenceClassesAndInitTebs of the reference's HomotopyClassPlanner on a fresh planner (clearPlanner()
+    between cycles). hcp: dict with max_number_classes, obstacle_heading_threshold and, for the roadmap, area width /
+    length scale / number of samples. Returns a list (per cycle) of lists of candidate bands [n][4]."""
+    ob = np.ascontiguousarray(obstacles, dtype=abi.OBST_DTYPE)
+    pv = None if obst_vertices is None or len(obst_vertices) == 0 else np.ascontiguousarray(obst_vertices, dtype=np.float64).reshape(-1, 2)
+    h = np.array([hcp["max_number_classes"], hcp["obstacle_heading_threshold"], hcp.get("roadmap_graph_area_width", 6.0),
+                  hcp.get("roadmap_graph_area_length_scale", 1.0), hcp.get("roadmap_graph_no_samples", 15), 1.0 if prm else 0.0])
+    s, g = np.ascontiguousarray(start, dtype=np.float64), np.ascontiguousarray(goal, dtype=np.float64)
+    cap, ccap = 1 << 18, 4096
+    out = np.zeros(cap)
+    counts = np.zeros(ccap, np.int32)
+    w = lib().teb_ref_hcp_explore(C.addressof(params), h.ctypes.data, s.ctypes.data, g.ctypes.data, ob.ctypes.data if len(ob) else None, len(ob),
+                                  pv.ctypes.data if pv is not None else None, cycles, out.ctypes.data, cap, counts.ctypes.data, ccap)
+    if w < 0:
+        raise RuntimeError("teb_ref_hcp_explore: capacity")
+    res, ci, pos = [], cycles, 0
+    for c in range(cycles):
+        bands = []
+        for _ in range(int(counts[c])):
+            n = int(counts[ci]); ci += 1
+            bands.append(out[pos:pos + 4 * n].reshape(n, 4).copy())
+            pos += 4 * n
+        res.append(bands)
+    return res

@@ -314,3 +314,62 @@ def test_h_signatures_match_the_reference_header(oracle, cfg):
                 assert np.array_equal(want, have[:len(ob)])
             else:
                 assert abs(want - complex(have[0], have[1])) <= 1e-15 * max(1.0, abs(want))
+
+
+def _explorer_inputs(rng, n_obst, dynamic):
+    from oracle import hcp_explore as X
+    rows = np.zeros(n_obst, abi.OBST_DTYPE)
+    obstacles, pool = [], []
+    for m in range(n_obst):
+        kind = ["point", "circle", "line"][int(rng.integers(3))]
+        c = np.array([rng.uniform(-3.2, 3.2), rng.uniform(-1.6, 1.6)])
+        if kind == "point":
+            rows[m]["type"], rows[m]["x"], rows[m]["y"] = abi.TEB_OBST_POINT, c[0], c[1]
+            obstacles.append(X.Obst("point", tuple(c)))
+        elif kind == "circle":
+            r = rng.uniform(0.1, 0.4)
+            rows[m]["type"], rows[m]["x"], rows[m]["y"], rows[m]["radius"] = abi.TEB_OBST_CIRCULAR, c[0], c[1], r
+            obstacles.append(X.Obst("circle", tuple(c), r))
+        else:
+            d = rng.normal(0, 0.35, 2)
+            a, b = c - d, c + d
+            rows[m]["type"], rows[m]["vertex_begin"], rows[m]["vertex_count"] = abi.TEB_OBST_LINE, len(pool), 2
+            pool += [a, b]
+            ctr = 0.5 * (a + b)
+            rows[m]["x"], rows[m]["y"] = ctr[0], ctr[1]
+            obstacles.append(X.Obst("line", tuple(ctr), vertices=[tuple(a), tuple(b)]))
+        if dynamic and rng.random() < 0.4:
+            rows[m]["vx"], rows[m]["vy"], rows[m]["dynamic"] = rng.normal(0, 0.1), rng.normal(0, 0.1), 1
+    return rows, obstacles, (np.array(pool) if pool else None)
+
+
+@pytest.mark.parametrize("prm", [False, True])
+@pytest.mark.parametrize("dynamic", [0, 1])
+def test_candidate_exploration_matches_the_reference_planner(oracle, prm, dynamic):
+    """exploreEquivalenceClassesAndInitTebs of the reference's own HomotopyClassPlanner / graph_search.cpp (key-point graph
+    and probabilistic roadmap, DepthFirst enumeration order, addAndInitNewTeb with the path variant of
+    initTrajectoryToGoal, H-signature filtering with both signature kinds, class budget) against the sequential
+    restatement oracle/hcp_explore.py - the one the GPU test of the drop-in planner is compared with. Same candidates, same
+    order, initial bands equal to 1e-12 (the restatement evaluates atan2 / hypot in Python). The roadmap's random stream is
+    boost's (absent from the image): both sides restate the same published generator, so that part pins consistency only."""
+    from oracle import hcp_explore as X
+    rng = np.random.default_rng(100 + 2 * int(prm) + dynamic)
+    for case in range(12):
+        p = abi.default_params()
+        p.include_dynamic_obstacles = dynamic
+        rows, obstacles, pool = _explorer_inputs(rng, int(rng.integers(2, 7)), dynamic)
+        hcp = {"max_number_classes": int(rng.integers(2, 8)), "obstacle_heading_threshold": [0.0, 0.45, 0.7][int(rng.integers(3))],
+               "roadmap_graph_area_width": rng.uniform(3, 7), "roadmap_graph_area_length_scale": [1.0, 0.8][int(rng.integers(2))],
+               "roadmap_graph_no_samples": int(rng.integers(5, 16))}
+        start = [-4.0, rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4)]
+        goal = [4.0, rng.uniform(-0.5, 0.5), rng.uniform(-0.4, 0.4)]
+        cycles = 2
+        want = rb.hcp_explore(p, hcp, start, goal, rows, pool, cycles=cycles, prm=prm)
+        ex = X.Explorer(p, hcp, oracle, rows, obstacles)
+        for c in range(cycles):
+            ex.classes, ex.tebs = [], []
+            (ex.prob_roadmap_graph if prm else ex.lr_key_point_graph)(start, goal, p.min_obstacle_dist)
+            assert len(ex.tebs) == len(want[c]), (case, c, len(ex.tebs), len(want[c]))
+            for k, (got, ref) in enumerate(zip(ex.tebs, want[c])):
+                assert got.shape == ref.shape, (case, c, k, got.shape, ref.shape)
+                assert np.abs(got - ref).max() < 1e-12, (case, c, k, np.abs(got - ref).max())
