@@ -15,6 +15,7 @@ the same candidates in the same order with the same initial bands (1e-12) on ran
 kinds, two cycles. Restated on BOTH sides (boost is not in the image): mt19937 is the standard engine, the
 uniform_real_distribution follows boost's published one-draw algorithm. The pin caught one thing the restatement had
 wrong: the roadmap draws its y sample before its x sample (unspecified argument evaluation order, right-to-left with GCC).
+The Planner class below (whole plan() cycles) is pinned the same way (test_planning_cycles_match_the_reference_planner).
 """
 import math
 
@@ -292,6 +293,8 @@ class Planner(Explorer):
     def __init__(self, params, hcp, oracle_binding, obst_rows, obstacles, simple_exploration=True):
         super().__init__(params, hcp, oracle_binding, obst_rows, obstacles)
         self.simple = simple_exploration
+        self.obst_vertices = None                         # vertex pool of Line / Pill / Polygon obstacle rows (for the optimisation)
+        self.jac_mode = None                              # None: closed-form Jacobians; oracle_binding.JAC_G2O = the reference's numeric ones
         self.costs, self.optimized = [], []
         self.best, self.best_class = None, None          # index into self.tebs / its class at classification time
 
@@ -409,7 +412,9 @@ class Planner(Explorer):
             self.prob_roadmap_graph(start, goal, self.p.min_obstacle_dist)
         # optimizeAllTEBs :466-493
         for k, rec in enumerate(self.tebs):
-            out, cost, st = self.ob.optimize_band(self.p, rec, len(rec), self.rows, args=args, jac_mode=self.ob.JAC_ANALYTIC, n_cap=512)
+            out, cost, st = self.ob.optimize_band(self.p, rec, len(rec), self.rows, args=args,
+                                                 jac_mode=self.ob.JAC_ANALYTIC if self.jac_mode is None else self.jac_mode, n_cap=512,
+                                                 obst_vertices=self.obst_vertices)
             self.tebs[k], self.costs[k] = out, cost
             self.optimized[k] = bool(st.status & abi_module.TEB_STATUS_OPTIMIZED)
         # selectBestTeb :564-616 (no initial-plan band in this entry point, no switching blocking period)

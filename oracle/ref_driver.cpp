@@ -108,6 +108,9 @@ void fill_config(const TebParams* p, TebConfig& c) {
   c.hcp.enable_multithreading = p->enable_multithreading != 0;
   c.hcp.h_signature_prescaler = p->h_signature_prescaler;
   c.hcp.h_signature_threshold = p->h_signature_threshold;
+  /* left uninitialised by TebConfig's constructor (teb_config.h:245-390); a ROS node gets it from dynamic_reconfigure
+   * (cfg/TebLocalPlannerReconfigure.cfg:350, default 1) - without this line addEquivalenceClassIfNew reads garbage */
+  c.hcp.max_number_plans_in_current_class = 1;
   c.recovery.divergence_detection_enable = p->divergence_detection_enable != 0;
   c.recovery.divergence_detection_max_chi_squared = (int)p->divergence_detection_max_chi_squared;
   switch (p->footprint_type) {
@@ -208,7 +211,7 @@ void set_velocities(RefPlanner& pl, const double* vs, const double* vg, int rotd
 
 extern "C" {
 
-int32_t teb_ref_abi(void) { return 5; }
+int32_t teb_ref_abi(void) { return 6; }
 
 /* TebConfig::TebConfig() (teb_config.h:245-390) read back through the POD mirror */
 void teb_ref_default_params(TebParams* p) {
@@ -628,6 +631,49 @@ int32_t teb_ref_hcp_explore(const TebParams* p, const double* hcp, const double*
       const int n = teb.sizePoses();
       if (ci >= counts_cap || w + 4 * n > cap) return -1;
       counts[ci++] = n;
+      store_band(teb, out + w, n);
+      w += 4 * n;
+    }
+  }
+  return w;
+}
+
+/* `cycles` calls of HomotopyClassPlanner::plan(start_c, goal) (homotopy_class_planner.cpp:107-125: updateAllTEBs,
+ * exploreEquivalenceClassesAndInitTebs incl. renewAndAnalyzeOldTebs / deletePlansDetouringBackwards, optimizeAllTEBs,
+ * selectBestTeb) on ONE planner, the way consecutive control cycles use it. starts = [cycles][3]. hcp as in
+ * teb_ref_hcp_explore. Per cycle: counts[3 c] = candidates, counts[3 c + 1] = index of the best one (-1: none),
+ * counts[3 c + 2] = plan()'s return value; then (from counts[3 cycles] on) the pose count of every candidate of every
+ * cycle; out = per candidate its cost (one double) followed by its (x, y, theta, dt) records. */
+int32_t teb_ref_hcp_plan(const TebParams* p, const double* hcp, const double* starts, const double* goal3, const TebObstacle* obst,
+                         int32_t M, const double* verts, int32_t cycles, double* out, int32_t cap, int32_t* counts, int32_t counts_cap) {
+  Scene sc;
+  fill_scene(sc, p, obst, M, verts, nullptr, 0);
+  sc.cfg.hcp.max_number_classes = (int)hcp[0];
+  sc.cfg.hcp.obstacle_heading_threshold = hcp[1];
+  sc.cfg.hcp.roadmap_graph_area_width = hcp[2];
+  sc.cfg.hcp.roadmap_graph_area_length_scale = hcp[3];
+  sc.cfg.hcp.roadmap_graph_no_samples = (int)hcp[4];
+  sc.cfg.hcp.simple_exploration = hcp[5] == 0;
+  sc.cfg.hcp.enable_multithreading = false;
+  HomotopyClassPlanner hcpl(sc.cfg, &sc.obstacles, TebVisualizationPtr(), nullptr);
+  const PoseSE2 goal(goal3[0], goal3[1], goal3[2]);
+  int w = 0, ci = 3 * cycles;
+  if (ci > counts_cap) return -1;
+  for (int c = 0; c < cycles; ++c) {
+    const PoseSE2 start(starts[3 * c], starts[3 * c + 1], starts[3 * c + 2]);
+    const bool ok = hcpl.plan(start, goal, nullptr, false);
+    const TebOptPlannerContainer& tebs = hcpl.getTrajectoryContainer();
+    counts[3 * c] = (int32_t)tebs.size();
+    counts[3 * c + 1] = -1;
+    counts[3 * c + 2] = ok;
+    TebOptimalPlannerPtr best = hcpl.bestTeb();
+    for (size_t k = 0; k < tebs.size(); ++k) {
+      if (tebs[k] == best) counts[3 * c + 1] = (int32_t)k;
+      const TimedElasticBand& teb = tebs[k]->teb();
+      const int n = teb.sizePoses();
+      if (ci >= counts_cap || w + 1 + 4 * n > cap) return -1;
+      counts[ci++] = n;
+      out[w++] = tebs[k]->getCurrentCost();
       store_band(teb, out + w, n);
       w += 4 * n;
     }

@@ -68,7 +68,9 @@ def lib():
         L.teb_ref_h_signature.argtypes = [vp, vp, i, vp, i, vp, i, vp, vp]
         L.teb_ref_hcp_explore.restype = i
         L.teb_ref_hcp_explore.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, i, vp, i]
-        assert L.teb_ref_abi() == 5
+        L.teb_ref_hcp_plan.restype = i
+        L.teb_ref_hcp_plan.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, i, vp, i]
+        assert L.teb_ref_abi() == 6
         _lib = L
     return _lib
 
@@ -229,4 +231,33 @@ def hcp_explore(params, hcp, start, goal, obstacles, obst_vertices=None, cycles=
             bands.append(out[pos:pos + 4 * n].reshape(n, 4).copy())
             pos += 4 * n
         res.append(bands)
+    return res
+
+
+def hcp_plan(params, hcp, starts, goal, obstacles, obst_vertices=None, prm=False):
+    """consecutive HomotopyClassPlanner::plan(start_c, goal) calls on one reference planner. Returns per cycle
+    (ok, best_index, [(cost, band[n][4]), ...])."""
+    ob = np.ascontiguousarray(obstacles, dtype=abi.OBST_DTYPE)
+    pv = None if obst_vertices is None or len(obst_vertices) == 0 else np.ascontiguousarray(obst_vertices, dtype=np.float64).reshape(-1, 2)
+    h = np.array([hcp["max_number_classes"], hcp["obstacle_heading_threshold"], hcp.get("roadmap_graph_area_width", 6.0),
+                  hcp.get("roadmap_graph_area_length_scale", 1.0), hcp.get("roadmap_graph_no_samples", 15), 1.0 if prm else 0.0])
+    st = np.ascontiguousarray(starts, dtype=np.float64).reshape(-1, 3)
+    g = np.ascontiguousarray(goal, dtype=np.float64)
+    cycles = len(st)
+    cap, ccap = 1 << 20, 1 << 14
+    out = np.zeros(cap)
+    counts = np.zeros(ccap, np.int32)
+    w = lib().teb_ref_hcp_plan(C.addressof(params), h.ctypes.data, st.ctypes.data, g.ctypes.data, ob.ctypes.data if len(ob) else None, len(ob),
+                               pv.ctypes.data if pv is not None else None, cycles, out.ctypes.data, cap, counts.ctypes.data, ccap)
+    if w < 0:
+        raise RuntimeError("teb_ref_hcp_plan: capacity")
+    res, ci, pos = [], 3 * cycles, 0
+    for c in range(cycles):
+        cands = []
+        for _ in range(int(counts[3 * c])):
+            n = int(counts[ci]); ci += 1
+            cost = float(out[pos]); pos += 1
+            cands.append((cost, out[pos:pos + 4 * n].reshape(n, 4).copy()))
+            pos += 4 * n
+        res.append((bool(counts[3 * c + 2]), int(counts[3 * c + 1]), cands))
     return res

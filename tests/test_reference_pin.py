@@ -373,3 +373,39 @@ def test_candidate_exploration_matches_the_reference_planner(oracle, prm, dynami
             for k, (got, ref) in enumerate(zip(ex.tebs, want[c])):
                 assert got.shape == ref.shape, (case, c, k, got.shape, ref.shape)
                 assert np.abs(got - ref).max() < 1e-12, (case, c, k, np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("prm", [False, True])
+def test_planning_cycles_match_the_reference_planner(oracle, prm):
+    """consecutive HomotopyClassPlanner::plan(start, goal) calls of the reference's own planner (updateAllTEBs,
+    renewAndAnalyzeOldTebs, deletePlansDetouringBackwards, graph exploration, optimizeAllTEBs, selectBestTeb) against the
+    sequential restatement oracle/hcp_explore.py::Planner with the start pose moving along: same number of candidates,
+    same order, same pose counts, same selected candidate in every cycle. The reference optimises with numeric Jacobians
+    (the restatement is switched to that mode); initial bands that differ in the last bit (Python vs C atan2 / hypot) come
+    out ~1e-7 apart after 20 LM iterations, hence 1e-5 on poses and 1e-6 relative on costs.
+    The reference's TebConfig constructor leaves hcp.max_number_plans_in_current_class uninitialised (candidate counts
+    varied from process to process until oracle/ref_driver.cpp set the dynamic_reconfigure default 1)."""
+    from oracle import hcp_explore as X
+    rng = np.random.default_rng(300 + int(prm))
+    for case in range(5):
+        p = abi.default_params()
+        p.include_dynamic_obstacles = 0
+        rows, obstacles, pool = _explorer_inputs(rng, int(rng.integers(2, 5)), 0)
+        hcp = {"max_number_classes": int(rng.integers(2, 5)), "obstacle_heading_threshold": 0.45,
+               "roadmap_graph_area_width": 5.0, "roadmap_graph_area_length_scale": 1.0, "roadmap_graph_no_samples": 10}
+        goal = [4.0, rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2)]
+        starts = [[-4.0 + 0.2 * c, 0.03 * c + rng.normal(0, 0.01), 0.05] for c in range(4)]
+        want = rb.hcp_plan(p, hcp, starts, goal, rows, pool, prm=prm)
+        pl = X.Planner(p, hcp, oracle, rows, obstacles, simple_exploration=not prm)
+        pl.jac_mode = oracle.JAC_G2O
+        pl.obst_vertices = pool
+        args = abi.make_args(p.no_inner_iterations, p.no_outer_iterations, True, p.selection_obst_cost_scale, p.selection_viapoint_cost_scale,
+                             bool(p.selection_alternative_time_cost))
+        for c, (ok, best, cands) in enumerate(want):
+            got_best = pl.plan(starts[c], goal, args, abi)
+            assert ok and len(pl.tebs) == len(cands), (case, c, len(pl.tebs), len(cands))
+            assert (got_best if got_best is not None else -1) == best, (case, c, got_best, best)
+            for k, ((cost, band), rec) in enumerate(zip(cands, pl.tebs)):
+                assert band.shape == rec.shape, (case, c, k, band.shape, rec.shape)
+                assert np.abs(band - rec).max() < 1e-5, (case, c, k, np.abs(band - rec).max())
+                assert abs(cost - pl.costs[k]) <= 1e-6 * max(1.0, abs(cost)), (case, c, k, cost, pl.costs[k])
