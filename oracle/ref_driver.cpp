@@ -514,6 +514,22 @@ void twist_from(const double* v, geometry_msgs::Twist& t) { t.linear.x = v[0]; t
  *   op 11 autoResize(dt_ref, dt_hysteresis, min_samples, max_samples, fast_mode)
  * Bands go in and out as (x, y, theta, dt) records; the return value is the number of output doubles (< 0: capacity). */
 
+
+/* op 12: isTrajectoryFeasible against a costmap stand-in that RECORDS every footprint query and reports a collision
+ * (-1) inside any of the given discs. args: inscribed_radius circumscribed_radius look_ahead_idx lookahead_distance
+ * min_resolution_collision_check_angular n_discs (x y r)* -> out: feasible, number of queries, the queried (x, y, theta). */
+struct RecordingCostmap : public base_local_planner::CostmapModel {
+  std::vector<double> q;
+  const double* discs = nullptr;
+  int nd = 0;
+  double footprintCost(double x, double y, double th, const std::vector<geometry_msgs::Point>&, double = 0.0, double = 0.0) {
+    q.push_back(x); q.push_back(y); q.push_back(th);
+    for (int k = 0; k < nd; ++k)
+      if (std::hypot(x - discs[3 * k], y - discs[3 * k + 1]) <= discs[3 * k + 2]) return -1;
+    return 0;
+  }
+};
+
 int32_t teb_ref_band_op(int32_t op, const double* rec, int32_t n, const double* a, int32_t na, double* out, int32_t cap) {
   (void)na;
   TebConfig cfg;
@@ -567,6 +583,21 @@ int32_t teb_ref_band_op(int32_t op, const double* rec, int32_t n, const double* 
   ObstContainer obst;
   RefPlanner pl(cfg, &obst, nullptr);
   load_band(pl.teb(), rec, n);
+  if (op == 12) {
+    RecordingCostmap cm;
+    cm.discs = a + 6; cm.nd = (int)a[5];
+    TebConfig cfg12;
+    cfg12.trajectory.min_resolution_collision_check_angular = a[4];
+    ObstContainer obst12;
+    RefPlanner pl12(cfg12, &obst12, nullptr);
+    load_band(pl12.teb(), rec, n);
+    std::vector<geometry_msgs::Point> footprint;
+    out[0] = pl12.isTrajectoryFeasible(&cm, footprint, a[0], a[1], (int)a[2], a[3]);
+    out[1] = (double)(cm.q.size() / 3);
+    if (2 + (int)cm.q.size() > cap) return -1;
+    for (size_t k = 0; k < cm.q.size(); ++k) out[2 + k] = cm.q[k];
+    return 2 + (int)cm.q.size();
+  }
   if (op == 8) {
     double vx = 0, vy = 0, om = 0;
     out[0] = pl.getVelocityCommand(vx, vy, om, (int)a[0]);

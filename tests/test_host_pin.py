@@ -118,3 +118,22 @@ def test_velocity_command_profile_and_full_trajectory(ops):
         assert len(prof) == 3 * (n + 1)
         tr = ops(10, rec, [max_vel_y] + vs + vg)
         assert len(tr) == 7 * n
+
+
+def test_is_trajectory_feasible_queries_the_same_poses(ops):
+    """isTrajectoryFeasible (optimal_planner.cpp:1250-1310) with a costmap stand-in that records every footprint query:
+    same verdict, same number of queries and bit-identical queried poses (incl. the interpolated ones between poses that
+    are far apart or turned against each other), with a look-ahead index and a look-ahead distance"""
+    rng = np.random.default_rng(6)
+    for _ in range(200):
+        n = int(rng.integers(2, 40))
+        rec = _band(rng, n, wiggle=1.5)
+        nd = int(rng.integers(0, 4))
+        discs = []
+        for _k in range(nd):
+            i = int(rng.integers(0, n))
+            discs += [rec[i, 0] + rng.normal(0, 0.3), rec[i, 1] + rng.normal(0, 0.3), rng.uniform(0.02, 0.25)]
+        args = [rng.uniform(0.05, 0.4), rng.uniform(0.4, 0.8), int(rng.integers(-1, n + 2)), [0.0, 1.0, 3.0][int(rng.integers(3))],
+                rng.uniform(0.1, 0.6), nd] + discs
+        out = ops(12, rec, args)
+        assert out[0] in (0.0, 1.0) and len(out) == 2 + 3 * int(out[1])
