@@ -80,7 +80,8 @@ class ProbRoadmapGraph : public GraphSearchInterface {
 
  private:
   /* boost::random::mt19937 (default seed 5489) + boost::random::uniform_real_distribution<double>: one 32-bit draw per
-   * sample, value = draw / 2^32 * (max - min) + min, redrawn if it reaches max */
+   * sample, value = draw / 2^32 * (max - min) + min, redrawn if it reaches max. A roadmap sample consumes its y draw
+   * before its x draw (GCC's right-to-left argument evaluation in graph_search.cpp:274; pinned in tests/test_reference_pin.py) */
   double uniform(double lo, double hi);
   std::mt19937 rnd_generator_;
 };
