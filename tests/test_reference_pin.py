@@ -376,7 +376,7 @@ def test_candidate_exploration_matches_the_reference_planner(oracle, prm, dynami
 
 
 @pytest.mark.parametrize("prm", [False, True])
-def test_planning_cycles_match_the_reference_planner(oracle, prm):
+def test_planning_cycles_match_the_reference_planner(oracle, teblib, prm):
     """consecutive HomotopyClassPlanner::plan(start, goal) calls of the reference's own planner (updateAllTEBs,
     renewAndAnalyzeOldTebs, deletePlansDetouringBackwards, graph exploration, optimizeAllTEBs, selectBestTeb) against the
     sequential restatement oracle/hcp_explore.py::Planner with the start pose moving along: same number of candidates,
@@ -390,6 +390,8 @@ def test_planning_cycles_match_the_reference_planner(oracle, prm):
     for case in range(5):
         p = abi.default_params()
         p.include_dynamic_obstacles = 0
+        p.selection_cost_hysteresis = [1.0, 0.9, 0.8][case % 3]
+        carried_best = False
         rows, obstacles, pool = _explorer_inputs(rng, int(rng.integers(2, 5)), 0)
         hcp = {"max_number_classes": int(rng.integers(2, 5)), "obstacle_heading_threshold": 0.45,
                "roadmap_graph_area_width": 5.0, "roadmap_graph_area_length_scale": 1.0, "roadmap_graph_no_samples": 10}
@@ -405,6 +407,13 @@ def test_planning_cycles_match_the_reference_planner(oracle, prm):
             got_best = pl.plan(starts[c], goal, args, abi)
             assert ok and len(pl.tebs) == len(cands), (case, c, len(pl.tebs), len(cands))
             assert (got_best if got_best is not None else -1) == best, (case, c, got_best, best)
+            # tebgpu_select_best (the C-ABI's selectBestTeb, a pure host function) on the REFERENCE's own costs: the band the
+            # planner carried over as its best one sits at index 0 after renewAndAnalyzeOldTebs
+            costs_ref = np.array([x for x, _ in cands])
+            last = 0 if (c > 0 and carried_best) else -1
+            assert teblib.tebgpu_select_best(costs_ref.ctypes.data, len(costs_ref), last, -1, float(p.selection_cost_hysteresis),
+                                             float(p.selection_prefer_initial_plan)) == best, (case, c)
+            carried_best = best >= 0
             for k, ((cost, band), rec) in enumerate(zip(cands, pl.tebs)):
                 assert band.shape == rec.shape, (case, c, k, band.shape, rec.shape)
                 assert np.abs(band - rec).max() < 1e-5, (case, c, k, np.abs(band - rec).max())
