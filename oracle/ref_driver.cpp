@@ -583,6 +583,43 @@ int32_t teb_ref_band_op(int32_t op, const double* rec, int32_t n, const double* 
   ObstContainer obst;
   RefPlanner pl(cfg, &obst, nullptr);
   load_band(pl.teb(), rec, n);
+  if (op == 13) { /* plan() sequences with the optimisation switched off (optimization_activate = false): cold start,
+                     warm start (updateAndPruneTEB) and re-initialisation after a goal jump (optimal_planner.cpp:233-321).
+                     args: kind (0 poses / 1 plans) ncalls reinit_dist reinit_ang max_vel_x max_vel_theta min_samples
+                     backwards overwrite_orientation, then per call s[3] g[3] or np pts[np][3]; out: per call n, band */
+    TebConfig cfg13;
+    cfg13.optim.optimization_activate = false;
+    cfg13.trajectory.force_reinit_new_goal_dist = a[2];
+    cfg13.trajectory.force_reinit_new_goal_angular = a[3];
+    cfg13.robot.max_vel_x = a[4];
+    cfg13.robot.max_vel_theta = a[5];
+    cfg13.trajectory.min_samples = (int)a[6];
+    cfg13.trajectory.allow_init_with_backwards_motion = a[7] != 0;
+    cfg13.trajectory.global_plan_overwrite_orientation = a[8] != 0;
+    ObstContainer obst13;
+    RefPlanner pl13(cfg13, &obst13, nullptr);
+    int r = 9, w = 0;
+    for (int c = 0; c < (int)a[1]; ++c) {
+      if (a[0] == 0) {
+        pl13.plan(PoseSE2(a[r], a[r + 1], a[r + 2]), PoseSE2(a[r + 3], a[r + 4], a[r + 5]), nullptr, false);
+        r += 6;
+      } else {
+        const int np = (int)a[r++];
+        std::vector<geometry_msgs::PoseStamped> plan((size_t)np);
+        for (int i = 0; i < np; ++i, r += 3) {
+          plan[i].pose.position.x = a[r]; plan[i].pose.position.y = a[r + 1];
+          plan[i].pose.orientation = tf::createQuaternionMsgFromYaw(a[r + 2]);
+        }
+        pl13.plan(plan, nullptr, false);
+      }
+      const int nn = pl13.teb().sizePoses();
+      if (w + 1 + 4 * nn > cap) return -1;
+      out[w++] = nn;
+      const int k = put_band(pl13.teb(), out + w, cap - w);
+      w += k;
+    }
+    return w;
+  }
   if (op == 12) {
     RecordingCostmap cm;
     cm.discs = a + 6; cm.nd = (int)a[5];

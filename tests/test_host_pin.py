@@ -137,3 +137,32 @@ def test_is_trajectory_feasible_queries_the_same_poses(ops):
                 rng.uniform(0.1, 0.6), nd] + discs
         out = ops(12, rec, args)
         assert out[0] in (0.0, 1.0) and len(out) == 2 + 3 * int(out[1])
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_plan_cold_warm_and_reinit_flows(ops, kind):
+    """TebOptimalPlanner::plan(start, goal) / plan(initial_plan) call sequences with the optimisation switched off: cold
+    start, warm start (updateAndPruneTEB with the moved start / goal) and re-initialisation when the goal jumps beyond
+    force_reinit_new_goal_dist / _angular (optimal_planner.cpp:233-321): the band after every call is bit equal"""
+    rng = np.random.default_rng(7 + kind)
+    for _ in range(80):
+        ncalls = int(rng.integers(2, 6))
+        head = [kind, ncalls, rng.uniform(0.3, 1.5), rng.uniform(0.2, 1.2), rng.uniform(0.2, 0.8), rng.uniform(0.2, 0.8), int(rng.integers(3, 8)),
+                int(rng.integers(2)), int(rng.integers(2))]
+        body = []
+        s = np.array([rng.uniform(-2, 0), rng.uniform(-1, 1), rng.uniform(-1, 1)])
+        g = np.array([rng.uniform(3, 5), rng.uniform(-1, 1), rng.uniform(-1, 1)])
+        for c in range(ncalls):
+            s = s + np.array([rng.uniform(0, 0.3), rng.normal(0, 0.05), rng.normal(0, 0.05)])
+            jump = rng.random() < 0.3
+            g = g + (np.array([rng.normal(0, 1.5), rng.normal(0, 1.5), rng.normal(0, 1.0)]) if jump else np.array([rng.normal(0, 0.05)] * 3))
+            if kind == 0:
+                body += s.tolist() + g.tolist()
+            else:
+                npts = int(rng.integers(2, 12))
+                xs = np.linspace(s[0], g[0], npts)
+                ys = np.linspace(s[1], g[1], npts) + np.concatenate([[0], rng.normal(0, 0.1, npts - 2), [0]]) if npts > 2 else np.linspace(s[1], g[1], npts)
+                th = np.linspace(s[2], g[2], npts)
+                body += [npts] + np.stack([xs, ys, th], 1).reshape(-1).tolist()
+        out = ops(13, None, head + body)
+        assert len(out) > ncalls
